@@ -1,0 +1,117 @@
+"""ctypes wrapper of the CPU oracle (oracle/libgfn2_oracle.so).
+
+TEST INFRASTRUCTURE: imported only by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  Never imported by xtb_b200/.
+"""
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libgfn2_oracle.so")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "gfn2_oracle.cpp")):
+        subprocess.check_call(["make", "-C", _HERE, "libgfn2_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(build())
+        L.orc_create.restype = ctypes.c_void_p
+        L.orc_create.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_int]
+        L.orc_destroy.argtypes = [ctypes.c_void_p]
+        L.orc_set_params.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int]
+        L.orc_set_threads.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.orc_set_guess.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.orc_set_xyz.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_set_restart.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_singlepoint.argtypes = [ctypes.c_void_p]
+        L.orc_len64.restype = ctypes.c_long
+        L.orc_len64.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        L.orc_get.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_long]
+        L.orc_geti.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_long]
+        L.orc_cn_erf.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_eeq.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+INFO = ["niter", "converged", "nao", "nshell", "ndp", "nqp", "nel", "nopen", "ihomo", "ndim", "nbr"]
+ENERGIES = ["e_total", "e_elec", "e_rep", "e_es", "e_aes", "e_axc", "e_disp", "hl_gap", "gnorm", "e_atm", "eel", "ed"]
+
+
+class Oracle:
+    """One GFN2-xTB calculation on the CPU oracle. Units: bohr, Hartree."""
+
+    def __init__(self, numbers, positions, charge=0.0, uhf=0, acc=1.0, etemp=300.0, maxiter=250, guess="eeq",
+                 threads=None):
+        self.numbers = np.ascontiguousarray(numbers, dtype=np.int32)
+        self.positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+        self.nat = len(self.numbers)
+        L = lib()
+        self.h = L.orc_create(self.nat, self.numbers.ctypes.data, self.positions.ctypes.data, float(charge), int(uhf))
+        L.orc_set_params(self.h, float(acc), float(etemp), int(maxiter))
+        L.orc_set_guess(self.h, {"eeq": 0, "sad": 1, "restart": 2}[guess])
+        if threads is not None:
+            L.orc_set_threads(self.h, int(threads))
+        self.status = None
+
+    def __del__(self):
+        try:
+            lib().orc_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_positions(self, positions):
+        self.positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+        lib().orc_set_xyz(self.h, self.positions.ctypes.data)
+
+    def set_restart(self, qsh, dipm, qp):
+        qsh = np.ascontiguousarray(qsh, dtype=np.float64)
+        dipm = np.ascontiguousarray(dipm, dtype=np.float64)
+        qp = np.ascontiguousarray(qp, dtype=np.float64)
+        lib().orc_set_restart(self.h, qsh.ctypes.data, len(qsh), dipm.ctypes.data, qp.ctypes.data)
+        lib().orc_set_guess(self.h, 2)
+
+    def singlepoint(self):
+        self.status = lib().orc_singlepoint(self.h)
+        return self.status
+
+    def get(self, name):
+        L = lib()
+        n = L.orc_len64(self.h, name.encode())
+        if n < 0:
+            raise KeyError(name)
+        if name in ("mdlst", "mqlst", "info"):
+            buf = np.zeros(n, dtype=np.int32)
+            L.orc_geti(self.h, name.encode(), buf.ctypes.data, n)
+        else:
+            buf = np.zeros(n, dtype=np.float64)
+            L.orc_get(self.h, name.encode(), buf.ctypes.data, n)
+        return buf
+
+    @property
+    def info(self):
+        return dict(zip(INFO, self.get("info").tolist()))
+
+    @property
+    def energies(self):
+        return dict(zip(ENERGIES, self.get("energies").tolist()))
+
+    def cn_erf(self):
+        buf = np.zeros(self.nat)
+        lib().orc_cn_erf(self.h, buf.ctypes.data)
+        return buf
+
+    def eeq(self):
+        buf = np.zeros(self.nat)
+        rc = lib().orc_eeq(self.h, buf.ctypes.data)
+        if rc:
+            raise RuntimeError("EEQ solve failed")
+        return buf
