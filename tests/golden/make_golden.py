@@ -1,0 +1,92 @@
+#!/usr/bin/env python3
+"""Extract the geometries and known-answer values that the reference's own tests hold for the
+GFN2-xTB single point path into tests/golden/reference_kat.json.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+
+Sources: test/unit/molstock.f90 (geometries), test/unit/test_gfn2.f90:48-235,667-742,831-901,
+987-1091, test/api/c_api_example.c:30-112, test/unit/test_coulomb.f90:828-1079,
+test/unit/test_repulsion.f90, test/unit/test_eeq.f90.
+"""
+import json
+import os
+import re
+import sys
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+SYM = ("H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr "
+       "Rb Sr Y Zr Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe Cs Ba La Ce Pr Nd Pm Sm Eu Gd Tb Dy Ho Er Tm Yb Lu "
+       "Hf Ta W Re Os Ir Pt Au Hg Tl Pb Bi Po At Rn").split()
+NUM = re.compile(r'[-+]?\d+\.\d*(?:[eEdD][-+]?\d+)?(?=_wp)')
+
+
+def molstock(name):
+    src = open(os.path.join(REF, "test/unit/molstock.f90")).read()
+    m = re.search(r'subroutine\s+%s\s*\(mol\)(.*?)end subroutine' % re.escape(name), src, re.S | re.I)
+    body = m.group(1)
+    ms = re.search(r'sym\(nat\)\s*=\s*\[character\(len=\d+\)\s*::(.*?)\]', body, re.S)
+    if ms:
+        syms = re.findall(r'"\s*([A-Za-z]+)\s*"', ms.group(1))
+        numbers = [SYM.index(s.capitalize()) + 1 for s in syms]
+    else:
+        ma = re.search(r'at\(nat\)\s*=\s*&?\s*\[(.*?)\]', body, re.S)
+        numbers = [int(t) for t in re.findall(r'\d+', ma.group(1))]
+    xyz = re.search(r'xyz\(3,\s*nat\)\s*=\s*reshape\(\[(.*?)\]', body, re.S).group(1)
+    xyz = [float(t.replace('d', 'e').replace('D', 'e')) for t in NUM.findall(xyz)]
+    chrg = re.search(r'charge\s*=\s*([-+]?\d+\.?\d*)', body)
+    uhf = re.search(r'uhf\s*=\s*(\d+)', body)
+    assert len(xyz) == 3 * len(numbers), name
+    return dict(numbers=numbers, xyz=xyz, charge=float(chrg.group(1)) if chrg else 0.0,
+                uhf=int(uhf.group(1)) if uhf else 0)
+
+
+# test_gfn2.f90:989 takes aatoau from mctc-lib (mctc_io_convert: CODATA 2018 Bohr radius), not from xtb
+AATOAU = 1.0 / 0.529177210903
+out = {}
+for i in range(1, 11):
+    out["mindless%02d" % i] = molstock("mindless%02d" % i)
+for nm in ["caffeine", "rivaroxaban", "pdb_4qxx", "feco5", "co_cnx6", "fe_cnx6", "remdesivir", "taxol"]:
+    out[nm] = molstock(nm)
+for nm in ["co_cnx6", "fe_cnx6"]:  # given in Angstrom, test_gfn2.f90:1029,1064 multiply by aatoau
+    out[nm]["xyz"] = [x * AATOAU for x in out[nm]["xyz"]]
+
+e = [-30.348902328339, -24.069929673504, -23.718708414840, -22.751497890244, -27.735987617741,
+     -18.559531652263, -33.423246445911, -29.982410709899, -20.549458882257, -25.648093031152]
+g = [0.06081938165963, 0.05480379303387, 0.04179957306749, 0.06932568214054, 0.05133081215262,
+     0.05897000784363, 0.04600837003153, 0.06088718433105, 0.05314451272641, 0.04588800056975]
+h = [2.2611412120964, 1.2455369848896, 0.1490345448030, 1.2694246332861, 2.2362028272626,
+     2.6053844166160, 2.6312636988491, 0.8502228061534, 3.2960732039022, 0.4185654147579]
+for i in range(10):
+    out["mindless%02d" % (i + 1)]["kat"] = dict(energy=e[i], gnorm=g[i], hl_gap=h[i], tol=1e-8,
+                                                source="test/unit/test_gfn2.f90:698-712")
+out["feco5"]["kat"] = dict(energy=-34.066853522474, gnorm=0.26985488354859, hl_gap=2.9239308006972, tol=1e-8,
+                           source="test/unit/test_gfn2.f90:862-867")
+out["co_cnx6"]["kat"] = dict(energy=-34.191439852632, gnorm=0.041770673817, hl_gap=3.769023080904, tol=1e-8,
+                             wbo={"0,1": 0.889766438284303, "2,3": 1.728632460261216E-002, "1,9": 2.73380919723017},
+                             source="test/unit/test_gfn2.f90:1047-1054")
+out["fe_cnx6"]["kat"] = dict(energy=-33.314958144107, gnorm=0.018945181484, hl_gap=1.805948321662, tol=1e-8,
+                             wbo={"0,1": 0.587095913328687, "2,3": 3.798539382576892E-002, "1,9": 2.81892857328157},
+                             source="test/unit/test_gfn2.f90:1081-1089")
+out["h2o_scc"] = dict(
+    numbers=[8, 1, 1],
+    xyz=[0.0, 0.0, -0.73578586109551, 1.44183152868459, 0.0, 0.36789293054775, -1.44183152868459, 0.0, 0.36789293054775],
+    charge=0.0, uhf=0, guess="sad", maxiter=50,
+    kat=dict(energy=-5.070451355118, gnorm=0.006457420125, hl_gap=14.450372368833, e_elec=-5.104362813671,
+             e_es=0.031408028914, e_aes=0.000563300591, e_axc=-0.000813611055, e_disp=-0.000141250480,
+             e_rep=0.033911458523, q1=0.28158903353422, qsh0=0.25886041477578, dipm_2_0=-0.55238805565739E-01,
+             qp_0_5=0.41207363331933E-01, qp_2_0=0.95084219046109E-01, emo_homo=-12.166283951806,
+             nshell=4, nao=6, ihomo=4, tol=1e-7, source="test/unit/test_gfn2.f90:121-164"))
+out["c3h4_api"] = dict(
+    numbers=[6, 6, 6, 1, 1, 1, 1],
+    xyz=[0.0, 0.0, -1.79755622305860, 0.0, 0.0, 0.95338756106749, 0.0, 0.0, 3.22281255790261,
+         -0.96412815539807, -1.66991895015711, -2.53624948351102, -0.96412815539807, 1.66991895015711, -2.53624948351102,
+         1.92825631079613, 0.0, -2.53624948351102, 0.0, 0.0, 5.23010455462158],
+    charge=0.0, uhf=0, maxiter=30,
+    kat=dict(energy=-8.3824793849585, gnorm=0.11544410028854E-01, hl_gap=7.0005867526665,
+             g_2_1=0.0, g_0_2=-0.74649908147372E-03, g_3_0=-0.28433755158510E-03, g_6_2=0.99750545315944E-02,
+             q5=0.05184019996829, dipole2=-0.298279305689518, wbo9=2.89823984265213, tol=1e-9,
+             source="test/unit/test_gfn2.f90:226-233; test/api/c_api_example.c:87-112"))
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_kat.json"), "w") as f:
+    json.dump(out, f, indent=1)
+print("wrote", len(out), "systems")
