@@ -1,0 +1,74 @@
+/* xtb_b200.h -- batched extension of the xtb C ABI for conformer ensembles on B200.
+ *
+ * The reference API (include/xtb.h) evaluates one molecule per call; callers that own an
+ * ensemble (CREST-style conformer searches, the numerical Hessian loop of
+ * src/type/calculator.f90:116-200) loop over xtb_singlepoint.  This extension submits the whole
+ * ensemble in one call so that every kernel runs batched over molecules.  Plain pointers and
+ * sizes only; no CUDA or torch types.  All functions return 0 on success, non-zero on error with
+ * a message retrievable through xtbb200_lastError().
+ */
+#pragma once
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct _xtbb200_TBatch* xtbb200_TBatch;
+
+/* last error message of the calling thread ("" if none) */
+const char* xtbb200_lastError(void);
+
+/* number of visible CUDA devices (0: the engine cannot run; there is no CPU fallback) */
+int xtbb200_deviceCount(void);
+
+/* Create a batch of nmol molecules on `device`.
+ * natoms[nmol]; numbers: concatenated atomic numbers; charges/uhf [nmol] or NULL.
+ * Replaces per-molecule xtb_newMolecule + xtb_newCalculator + xtb_loadGFN2xTB. */
+xtbb200_TBatch xtbb200_newBatch(int nmol, const int* natoms, const int* numbers,
+                                const double* charges, const int* uhf, int device);
+void xtbb200_delBatch(xtbb200_TBatch* batch);
+
+/* accuracy / electronic temperature [K] / max SCC iterations (xtb_setAccuracy, xtb_setElectronicTemp,
+ * xtb_setMaxIter); guess: 0 = EEQ charges (reference default), 1 = uniform charges */
+int xtbb200_setOptions(xtbb200_TBatch batch, double accuracy, double etemp, int maxiter, int guess);
+
+/* GFN2-xTB single point + gradient for every molecule of the batch (batched xtb_singlepoint).
+ * positions: concatenated [natoms][3] in Bohr (host memory). restart != 0 reuses the converged
+ * wavefunction of the previous call as SCC start (src/api/interface.f90:82-101).
+ * Outputs (host memory, may be NULL): energies[nmol] in Eh, gradients concatenated [natoms][3]
+ * in Eh/Bohr, charges concatenated [natoms], niter[nmol], status[nmol] (0 = converged).
+ * Returns 0 if every molecule converged, 1 if some did not, <0 on error. */
+int xtbb200_singlepoint(xtbb200_TBatch batch, const double* positions, int restart,
+                        double* energies, double* gradients, double* charges, int* niter, int* status);
+
+/* same, with positions/gradients given as DEVICE pointers on the batch's device (no host copies) */
+int xtbb200_singlepointDevice(xtbb200_TBatch batch, const double* positions_dev, int restart,
+                              double* energies_dev_or_null);
+
+/* sizes */
+int xtbb200_getNMol(xtbb200_TBatch batch);
+int xtbb200_getSizes(xtbb200_TBatch batch, int imol, int* natoms, int* nshell, int* nao);
+size_t xtbb200_getDeviceBytes(xtbb200_TBatch batch);
+
+/* per-molecule scalar results of the last call:
+ * out[16] = energy, e_elec, e_rep, e_es, e_aes, e_axc, e_disp, hl_gap, gnorm, e_atm, dipole(3),
+ *           niter, converged, fail */
+int xtbb200_getResult(xtbb200_TBatch batch, int imol, double* out16);
+/* screening list lengths ndp, nqp and total Jacobi sweeps of one molecule */
+int xtbb200_getCounts(xtbb200_TBatch batch, int imol, int* ndp, int* nqp, int* sweeps);
+
+/* copy a named device array of the whole batch to the host; names: gradient q qsh dipm qp cn emo
+ * focc S dpint qpint H0 H0_noovlp P C wbo gab3 gab5 jmat dispmat gw ...; len = number of doubles */
+int xtbb200_getArrayLen(xtbb200_TBatch batch, const char* name, size_t* len);
+int xtbb200_getArray(xtbb200_TBatch batch, const char* name, double* out, size_t len);
+/* offsets of molecule imol inside the concatenated arrays: atoms, shells, AOs, nao^2, natoms^2 */
+int xtbb200_getOffsets(xtbb200_TBatch batch, int imol, long long* off5);
+/* dipole (bit 0) / quadrupole (bit 1) screening mask, one byte per AO pair, concatenated nao^2 */
+int xtbb200_getMask(xtbb200_TBatch batch, unsigned char* out, size_t len);
+
+/* device timings [ms] of the last call (setup+integrals, SCC, gradient+properties) and kernel launches */
+int xtbb200_getTimings(xtbb200_TBatch batch, float* ms3, int* launches);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,536 @@
+// C ABI of the B200 engine: the reference's include/xtb.h entry points (opaque handles, error log
+// on the environment) plus the batched extension of include/xtb_b200.h.
+//
+// Reference semantics followed (file:line in the reference):
+//   src/api/environment.f90:46-246   environment, error stack, verbosity, output unit
+//   src/api/molecule.f90:45-170      molecule creation / update / validation
+//   src/api/calculator.f90:57-696    calculator loading and setters (clamps, error messages)
+//   src/api/interface.f90:40-156     xtb_singlepoint (cache check, restart from res%chk)
+//   src/api/results.f90:37-504       getters (errors when data is missing)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/xtb.h"
+#include "../../include/xtb_b200.h"
+#include "engine.h"
+
+using xtbb200::Batch;
+using xtbb200::MolResult;
+
+namespace {
+thread_local std::string g_last_error;
+}
+
+struct _xtb_TEnvironment {
+    std::vector<std::string> log;   // message stack; error pending iff has_error
+    bool has_error = false;
+    int verbosity = 1;              // src/api/environment.f90:56
+    FILE* unit = nullptr;           // nullptr -> stdout
+    bool owns_unit = false;
+    void error(const std::string& msg, const char* source) {
+        log.push_back(std::string("-") + source + "- " + msg);
+        has_error = true;
+    }
+    void warning(const std::string& msg, const char* source) { log.push_back(std::string("#") + source + "# " + msg); }
+    FILE* out() { return unit ? unit : stdout; }
+};
+struct _xtb_TMolecule {
+    int n = 0;
+    std::vector<int> at;
+    std::vector<double> xyz;
+    double chrg = 0;
+    int uhf = 0;
+};
+struct _xtb_TCalculator {
+    std::shared_ptr<Batch> batch;   // engine for the element list the calculator was loaded with
+    std::vector<int> at;
+    double chrg = 0;
+    int uhf = 0;
+    double accuracy = 1.0, etemp = 300.0;
+    int maxiter = 250;
+    bool loaded = false;
+};
+struct _xtb_TResults {
+    bool has_energy = false, has_gradient = false, has_wfn = false, has_dipole = false;
+    int n = 0, nao = 0, nshell = 0;
+    double energy = 0, egap = 0;
+    std::vector<double> gradient, q, qsh, dipm, qp, wbo, emo, focc, C;
+    double dipole[3] = {0, 0, 0};
+    int niter = 0;
+};
+
+namespace {
+
+bool check_env(xtb_TEnvironment env) { return env != nullptr; }
+
+void unsupported(xtb_TEnvironment env, const char* what, const char* source) {
+    if (!check_env(env)) return;
+    env->error(std::string(what) + " is not available in the B200 GFN2-xTB engine", source);
+}
+
+}  // namespace
+
+extern "C" {
+
+int xtb_getAPIVersion(void) { return XTB_API_VERSION; }
+
+// ---------------------------------------------------------------- environment
+xtb_TEnvironment xtb_newEnvironment(void) { return new _xtb_TEnvironment(); }
+void xtb_delEnvironment(xtb_TEnvironment* env) {
+    if (!env || !*env) return;
+    if ((*env)->owns_unit && (*env)->unit) fclose((*env)->unit);
+    delete *env;
+    *env = nullptr;
+}
+int xtb_checkEnvironment(xtb_TEnvironment env) {
+    if (!env) return 2;
+    return env->has_error ? 1 : 0;
+}
+void xtb_showEnvironment(xtb_TEnvironment env, const char* message) {
+    if (!env) return;
+    FILE* f = env->out();
+    if (!env->log.empty()) {
+        if (message) fprintf(f, "%s\n", message);
+        for (auto it = env->log.rbegin(); it != env->log.rend(); ++it) fprintf(f, "%s\n", it->c_str());
+        fflush(f);
+    }
+    env->log.clear();
+    env->has_error = false;
+}
+void xtb_getError(xtb_TEnvironment env, char* buffer, const int* buffersize) {
+    if (!env || !buffer) return;
+    int max_length = buffersize ? *buffersize : 0;
+    std::string msg;
+    for (auto it = env->log.rbegin(); it != env->log.rend(); ++it) {
+        if (!msg.empty()) msg += "\n";
+        msg += *it;
+    }
+    if (max_length > 0) {
+        int n = std::min<int>((int)msg.size(), max_length - 1);
+        std::memcpy(buffer, msg.data(), n);
+        buffer[n] = '\0';
+    }
+    env->log.clear();
+    env->has_error = false;
+}
+void xtb_setOutput(xtb_TEnvironment env, const char* filename) {
+    if (!env) return;
+    if (env->owns_unit && env->unit) fclose(env->unit);
+    env->unit = nullptr; env->owns_unit = false;
+    if (!filename) return;
+    if (std::strcmp(filename, "-") == 0 || std::strcmp(filename, "STDOUT") == 0) return;
+    FILE* f = fopen(filename, "w");
+    if (!f) { env->error(std::string("Could not open output file '") + filename + "'", "xtb_api_setOutput"); return; }
+    env->unit = f; env->owns_unit = true;
+}
+void xtb_releaseOutput(xtb_TEnvironment env) {
+    if (!env) return;
+    if (env->owns_unit && env->unit) fclose(env->unit);
+    env->unit = nullptr; env->owns_unit = false;
+}
+void xtb_setVerbosity(xtb_TEnvironment env, int verbosity) {
+    if (!env) return;
+    env->verbosity = verbosity < 0 ? 0 : (verbosity > 2 ? 2 : verbosity);
+}
+
+// ---------------------------------------------------------------- molecule
+static bool verify_molecule(const _xtb_TMolecule& m) {  // src/api/utils.f90:63-72
+    for (int i = 0; i < m.n; ++i)
+        for (int j = 0; j < i; ++j) {
+            double r2 = 0;
+            for (int k = 0; k < 3; ++k) { double d = m.xyz[3 * i + k] - m.xyz[3 * j + k]; r2 += d * d; }
+            if (std::sqrt(r2) < 1.0e-9) return false;
+        }
+    return true;
+}
+xtb_TMolecule xtb_newMolecule(xtb_TEnvironment env, const int* natoms, const int* numbers, const double* positions,
+                              const double* charge, const int* uhf, const double* lattice, const bool* periodic) {
+    const char* source = "xtb_api_newMolecule";
+    if (!check_env(env)) return nullptr;
+    if (!natoms || *natoms <= 0) { env->error("Number of atoms must be positive", source); return nullptr; }
+    if (!numbers || !positions) { env->error("Atomic numbers and positions are required", source); return nullptr; }
+    for (int i = 0; i < *natoms; ++i)
+        if (numbers[i] < 1 || numbers[i] > 118) { env->error("Invalid atomic number present", source); return nullptr; }
+    if (periodic && (periodic[0] || periodic[1] || periodic[2])) {
+        env->error("Periodic boundary conditions are not available in the B200 GFN2-xTB engine", source);
+        return nullptr;
+    }
+    (void)lattice;
+    auto* m = new _xtb_TMolecule();
+    m->n = *natoms;
+    m->at.assign(numbers, numbers + m->n);
+    m->xyz.assign(positions, positions + 3 * m->n);
+    m->chrg = charge ? *charge : 0.0;
+    m->uhf = uhf ? *uhf : 0;
+    if (!verify_molecule(*m)) {
+        delete m;
+        env->error("Could not generate molecular structure", source);
+        return nullptr;
+    }
+    return m;
+}
+void xtb_delMolecule(xtb_TMolecule* mol) {
+    if (!mol || !*mol) return;
+    delete *mol;
+    *mol = nullptr;
+}
+void xtb_updateMolecule(xtb_TEnvironment env, xtb_TMolecule mol, const double* positions, const double* lattice) {
+    const char* source = "xtb_api_updateMolecule";
+    if (!check_env(env)) return;
+    if (!mol) { env->error("Molecular structure data is not allocated", source); return; }
+    if (!positions) { env->error("Positions are required", source); return; }
+    (void)lattice;
+    std::vector<double> old = mol->xyz;
+    mol->xyz.assign(positions, positions + 3 * mol->n);
+    if (!verify_molecule(*mol)) {
+        env->error("Could not update molecular structure", source);
+        mol->xyz = old;
+    }
+}
+
+// ---------------------------------------------------------------- calculator
+xtb_TCalculator xtb_newCalculator(void) { return new _xtb_TCalculator(); }
+void xtb_delCalculator(xtb_TCalculator* calc) {
+    if (!calc || !*calc) return;
+    delete *calc;
+    *calc = nullptr;
+}
+void xtb_loadGFN2xTB(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator calc, char* filename) {
+    const char* source = "xtb_api_loadGFN2xTB";
+    if (!check_env(env)) return;
+    if (!mol) { env->error("Molecular structure data is not allocated", source); return; }
+    if (!calc) { env->error("Calculator object is not allocated", source); return; }
+    // parameter files are not parsed: the compiled-in GFN2-xTB tables are the reference's own fallback
+    // (src/xtb/calculator.f90:147-160); a custom file would change the arithmetic, so refuse it loudly
+    if (filename && filename[0] != '\0' && std::strstr(filename, "param_gfn2-xtb.txt") == nullptr) {
+        env->error("Custom parameter files are not supported, only the built-in GFN2-xTB parametrisation", source);
+        return;
+    }
+    try {
+        double chrg = mol->chrg;
+        int uhf = mol->uhf;
+        calc->batch = std::make_shared<Batch>(1, &mol->n, mol->at.data(), &chrg, &uhf, 0);
+        calc->at = mol->at; calc->chrg = chrg; calc->uhf = uhf;
+        calc->accuracy = 1.0; calc->etemp = 300.0; calc->maxiter = 250;   // src/xtb/calculator.f90:138-145
+        calc->loaded = true;
+    } catch (const std::exception& e) {
+        calc->loaded = false;
+        calc->batch.reset();
+        env->error(std::string("Could not load parametrisation data: ") + e.what(), source);
+    }
+}
+void xtb_loadGFN0xTB(xtb_TEnvironment env, xtb_TMolecule, xtb_TCalculator, char*) { unsupported(env, "GFN0-xTB", "xtb_api_loadGFN0xTB"); }
+void xtb_loadGFN1xTB(xtb_TEnvironment env, xtb_TMolecule, xtb_TCalculator, char*) { unsupported(env, "GFN1-xTB", "xtb_api_loadGFN1xTB"); }
+void xtb_loadGFNFF(xtb_TEnvironment env, xtb_TMolecule, xtb_TCalculator, char*) { unsupported(env, "GFN-FF", "xtb_api_loadGFNFF"); }
+void xtb_setSolvent(xtb_TEnvironment env, xtb_TCalculator, char*, int*, double*, int*, char*) { unsupported(env, "Implicit solvation", "xtb_api_setSolvent"); }
+void xtb_releaseSolvent(xtb_TEnvironment env, xtb_TCalculator calc) {
+    if (!check_env(env)) return;
+    if (!calc) env->error("Calculator object is not allocated", "xtb_api_releaseSolvent");
+}
+void xtb_setExternalCharges(xtb_TEnvironment env, xtb_TCalculator, int*, int*, double*, double*) { unsupported(env, "Point charge embedding", "xtb_api_setExternalCharges"); }
+void xtb_releaseExternalCharges(xtb_TEnvironment env, xtb_TCalculator calc) {
+    if (!check_env(env)) return;
+    if (!calc) env->error("Calculator object is not allocated", "xtb_api_releaseExternalCharges");
+}
+void xtb_setAccuracy(xtb_TEnvironment env, xtb_TCalculator calc, double accuracy) {
+    const char* source = "xtb_api_setAccuracy";
+    if (!check_env(env)) return;
+    if (!calc) { env->error("Calculator object is not allocated", source); return; }
+    if (!calc->loaded) { env->error("Calculator is not allocated", source); return; }
+    if (accuracy < 1.e-4) { env->warning("We cannot provide this level of accuracy, resetted accuracy to 0.0001", source); calc->accuracy = 1.e-4; }
+    else if (accuracy > 1.e+3) { env->warning("We cannot provide this level of accuracy, resetted accuracy to 1000", source); calc->accuracy = 1.e+3; }
+    else calc->accuracy = accuracy;
+}
+void xtb_setMaxIter(xtb_TEnvironment env, xtb_TCalculator calc, int iterations) {
+    const char* source = "xtb_api_setMaxIter";
+    if (!check_env(env)) return;
+    if (!calc) { env->error("Calculator object is not allocated", source); return; }
+    if (!calc->loaded) { env->error("Calculator is not allocated", source); return; }
+    calc->maxiter = iterations < 1 ? 1 : iterations;
+}
+void xtb_setElectronicTemp(xtb_TEnvironment env, xtb_TCalculator calc, double temperature) {
+    const char* source = "xtb_api_setElectronicTemp";
+    if (!check_env(env)) return;
+    if (!calc) { env->error("Calculator object is not allocated", source); return; }
+    if (!calc->loaded) { env->error("Calculator is not allocated", source); return; }
+    calc->etemp = temperature < 1.e-6 ? 1.e-6 : temperature;
+}
+void xtb_cpcmx_calc(xtb_TEnvironment env, xtb_TMolecule, xtb_TCalculator, xtb_TResults) { unsupported(env, "CPCM-X", "xtb_api_cpcmx_calc"); }
+void xtb_hessian(xtb_TEnvironment env, xtb_TMolecule, xtb_TCalculator, xtb_TResults, double*, int*, int*, double*, double*) {
+    unsupported(env, "Numerical Hessian", "xtb_api_hessian");
+}
+
+void xtb_singlepoint(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator calc, xtb_TResults res) {
+    const char* source = "xtb_api_singlepoint";
+    if (!check_env(env)) return;
+    if (!mol) { env->error("Molecular structure data is not allocated", source); return; }
+    if (!calc) { env->error("Calculator object is not allocated", source); return; }
+    if (!calc->loaded || !calc->batch) { env->error("Calculator is not allocated", source); return; }
+    if (!res) { env->error("Results object is not allocated", source); return; }
+    if (calc->at != mol->at) { env->error("Calculator was loaded for a different molecule", source); return; }
+    try {
+        Batch& b = *calc->batch;
+        const int n = mol->n, nao = b.nao(0), nsh = b.nshell(0);
+        // restart cache check, src/api/interface.f90:82-101
+        bool cached = res->has_wfn && res->n == n && res->nao == nao && res->nshell == nsh;
+        if (!cached) res->has_wfn = false;
+        b.set_options(calc->accuracy, calc->etemp, calc->maxiter);
+        b.set_guess(0);
+        b.set_positions(mol->xyz.data());
+        if (cached) b.set_wavefunction(res->qsh.data(), res->dipm.data(), res->qp.data());
+        else b.invalidate_wavefunction();
+        int nfail = b.singlepoint(true);
+        MolResult r = b.result(0);
+        res->n = n; res->nao = nao; res->nshell = nsh;
+        res->energy = r.energy; res->egap = r.hl_gap; res->niter = r.niter;
+        res->gradient.resize(3 * n); b.fetch("gradient", res->gradient.data());
+        res->q.resize(n); b.fetch("q", res->q.data());
+        res->qsh.resize(nsh); b.fetch("qsh", res->qsh.data());
+        res->dipm.resize(3 * n); b.fetch("dipm", res->dipm.data());
+        res->qp.resize(6 * n); b.fetch("qp", res->qp.data());
+        res->wbo.resize((size_t)n * n); b.fetch("wbo", res->wbo.data());
+        res->emo.resize(nao); b.fetch("emo", res->emo.data());
+        res->focc.resize(nao); b.fetch("focc", res->focc.data());
+        res->C.resize((size_t)nao * nao); b.fetch("C", res->C.data());
+        for (int k = 0; k < 3; ++k) res->dipole[k] = r.dipole[k];
+        res->has_energy = res->has_gradient = res->has_wfn = res->has_dipole = true;
+        if (env->verbosity > 0) {
+            FILE* f = env->out();
+            fprintf(f, "   *** GFN2-xTB (B200): %s after %d iterations ***\n",
+                    r.converged ? "convergence criteria satisfied" : "convergence criteria cannot be satisfied", r.niter);
+            if (env->verbosity > 1) {
+                fprintf(f, "          total energy      %18.12f Eh\n", r.energy);
+                fprintf(f, "          gradient norm     %18.12f Eh/a0\n", r.gnorm);
+                fprintf(f, "          HOMO-LUMO gap     %18.12f eV\n", r.hl_gap);
+            }
+            fflush(f);
+        }
+        if (r.fail) env->error("Electronic structure method terminated (device error code " + std::to_string(r.fail) + ")", source);
+        else if (nfail) env->error("Self consistent charge iterator did not converge", "scf");   // src/scf_module.F90:806-808
+    } catch (const std::exception& e) {
+        env->error(std::string("Single point calculation failed: ") + e.what(), source);
+    }
+}
+
+// ---------------------------------------------------------------- results
+xtb_TResults xtb_newResults(void) { return new _xtb_TResults(); }
+void xtb_delResults(xtb_TResults* res) {
+    if (!res || !*res) return;
+    delete *res;
+    *res = nullptr;
+}
+xtb_TResults xtb_copyResults(xtb_TResults res) {
+    if (!res) return nullptr;
+    return new _xtb_TResults(*res);
+}
+#define XTB_GETTER_PROLOGUE(src)                                                     \
+    const char* source = src;                                                        \
+    if (!check_env(env)) return;                                                     \
+    if (!res) { env->error("Results object is not allocated", source); return; }
+void xtb_getEnergy(xtb_TEnvironment env, xtb_TResults res, double* energy) {
+    XTB_GETTER_PROLOGUE("xtb_api_getEnergy")
+    if (!res->has_energy) { env->error("Energy is not available in results", source); return; }
+    if (energy) *energy = res->energy;
+}
+void xtb_getSolvationEnergy(xtb_TEnvironment env, xtb_TResults res, double*) {
+    XTB_GETTER_PROLOGUE("xtb_api_getSolvationEnergy")
+    env->error("Solvation energy is not available in results", source);
+}
+void xtb_getGradient(xtb_TEnvironment env, xtb_TResults res, double* gradient) {
+    XTB_GETTER_PROLOGUE("xtb_api_getGradient")
+    if (!res->has_gradient) { env->error("Gradient is not available in results", source); return; }
+    if (gradient) std::memcpy(gradient, res->gradient.data(), res->gradient.size() * sizeof(double));
+}
+void xtb_getPCGradient(xtb_TEnvironment env, xtb_TResults res, double*) {
+    XTB_GETTER_PROLOGUE("xtb_api_getPCGradient")
+    env->error("Gradient on external charges is not available in results", source);
+}
+void xtb_getVirial(xtb_TEnvironment env, xtb_TResults res, double* virial) {
+    XTB_GETTER_PROLOGUE("xtb_api_getVirial")
+    if (!res->has_gradient) { env->error("Virial is not available in results", source); return; }
+    // GFN1/2 never fill sigma in the reference (src/xtb/calculator.f90:247; scf has no sigma argument)
+    if (virial) for (int k = 0; k < 9; ++k) virial[k] = 0.0;
+}
+void xtb_getDipole(xtb_TEnvironment env, xtb_TResults res, double* dipole) {
+    XTB_GETTER_PROLOGUE("xtb_api_getDipole")
+    if (!res->has_dipole) { env->error("Dipole is not available in results", source); return; }
+    if (dipole) for (int k = 0; k < 3; ++k) dipole[k] = res->dipole[k];
+}
+void xtb_getCharges(xtb_TEnvironment env, xtb_TResults res, double* charges) {
+    XTB_GETTER_PROLOGUE("xtb_api_getCharges")
+    if (!res->has_wfn) { env->error("Partial charges are not available in results", source); return; }
+    if (charges) std::memcpy(charges, res->q.data(), res->q.size() * sizeof(double));
+}
+void xtb_getBondOrders(xtb_TEnvironment env, xtb_TResults res, double* wbo) {
+    XTB_GETTER_PROLOGUE("xtb_api_getBondOrders")
+    if (!res->has_wfn) { env->error("Bond orders are not available in results", source); return; }
+    if (wbo) std::memcpy(wbo, res->wbo.data(), res->wbo.size() * sizeof(double));
+}
+void xtb_getNao(xtb_TEnvironment env, xtb_TResults res, int* nao) {
+    XTB_GETTER_PROLOGUE("xtb_api_getNao")
+    if (!res->has_wfn) { env->error("Wavefunction is not available in results", source); return; }
+    if (nao) *nao = res->nao;
+}
+void xtb_getOrbitalEigenvalues(xtb_TEnvironment env, xtb_TResults res, double* emo) {
+    XTB_GETTER_PROLOGUE("xtb_api_getOrbitalEigenvalues")
+    if (!res->has_wfn) { env->error("Orbital eigenvalues are not available in results", source); return; }
+    if (emo) for (int i = 0; i < res->nao; ++i) emo[i] = res->emo[i] * (1.0 / 27.21138505);   // src/api/results.f90:429
+}
+void xtb_getOrbitalOccupations(xtb_TEnvironment env, xtb_TResults res, double* focc) {
+    XTB_GETTER_PROLOGUE("xtb_api_getOrbitalOccupations")
+    if (!res->has_wfn) { env->error("Occupation numbers are not available in results", source); return; }
+    if (focc) std::memcpy(focc, res->focc.data(), res->focc.size() * sizeof(double));
+}
+void xtb_getOrbitalCoefficients(xtb_TEnvironment env, xtb_TResults res, double* c) {
+    XTB_GETTER_PROLOGUE("xtb_api_getOrbitalCoefficients")
+    if (!res->has_wfn) { env->error("Orbital coefficients are not available in results", source); return; }
+    if (c) std::memcpy(c, res->C.data(), res->C.size() * sizeof(double));
+}
+
+// ================================================================= batched extension
+struct _xtbb200_TBatch {
+    std::unique_ptr<Batch> b;
+    std::vector<double> scratch;
+};
+
+const char* xtbb200_lastError(void) { return g_last_error.c_str(); }
+int xtbb200_deviceCount(void) { return xtbb200::device_count(); }
+
+#define XTBB_TRY try {
+#define XTBB_CATCH(rc)                   \
+    }                                    \
+    catch (const std::exception& e) {    \
+        g_last_error = e.what();         \
+        return rc;                       \
+    }
+
+xtbb200_TBatch xtbb200_newBatch(int nmol, const int* natoms, const int* numbers, const double* charges, const int* uhf, int device) {
+    XTBB_TRY
+    if (nmol <= 0 || !natoms || !numbers) throw std::runtime_error("invalid batch description");
+    auto* h = new _xtbb200_TBatch();
+    try { h->b.reset(new Batch(nmol, natoms, numbers, charges, uhf, device)); }
+    catch (...) { delete h; throw; }
+    g_last_error.clear();
+    return h;
+    XTBB_CATCH(nullptr)
+}
+void xtbb200_delBatch(xtbb200_TBatch* batch) {
+    if (!batch || !*batch) return;
+    delete *batch;
+    *batch = nullptr;
+}
+int xtbb200_setOptions(xtbb200_TBatch batch, double accuracy, double etemp, int maxiter, int guess) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    accuracy = std::min(1.e+3, std::max(1.e-4, accuracy));
+    batch->b->set_options(accuracy, std::max(etemp, 1.e-6), std::max(maxiter, 1));
+    batch->b->set_guess(guess);
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_singlepoint(xtbb200_TBatch batch, const double* positions, int restart, double* energies, double* gradients,
+                        double* charges, int* niter, int* status) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    if (!positions) throw std::runtime_error("positions are required");
+    Batch& b = *batch->b;
+    b.set_positions(positions);
+    int nfail = b.singlepoint(restart != 0);
+    for (int i = 0; i < b.nmol(); ++i) {
+        MolResult r = b.result(i);
+        if (energies) energies[i] = r.energy;
+        if (niter) niter[i] = r.niter;
+        if (status) status[i] = r.fail ? r.fail : (r.converged ? 0 : 1);
+    }
+    if (gradients) b.fetch("gradient", gradients);
+    if (charges) b.fetch("q", charges);
+    return nfail ? 1 : 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_singlepointDevice(xtbb200_TBatch batch, const double* positions_dev, int restart, double*) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    Batch& b = *batch->b;
+    b.set_positions_device(positions_dev);
+    int nfail = b.singlepoint(restart != 0);
+    return nfail ? 1 : 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_getNMol(xtbb200_TBatch batch) { return batch ? batch->b->nmol() : -1; }
+int xtbb200_getSizes(xtbb200_TBatch batch, int imol, int* natoms, int* nshell, int* nao) {
+    XTBB_TRY
+    if (!batch || imol < 0 || imol >= batch->b->nmol()) throw std::runtime_error("invalid molecule index");
+    if (natoms) *natoms = batch->b->natoms(imol);
+    if (nshell) *nshell = batch->b->nshell(imol);
+    if (nao) *nao = batch->b->nao(imol);
+    return 0;
+    XTBB_CATCH(-1)
+}
+size_t xtbb200_getDeviceBytes(xtbb200_TBatch batch) { return batch ? batch->b->device_bytes() : 0; }
+int xtbb200_getResult(xtbb200_TBatch batch, int imol, double* out16) {
+    XTBB_TRY
+    if (!batch || imol < 0 || imol >= batch->b->nmol()) throw std::runtime_error("invalid molecule index");
+    MolResult r = batch->b->result(imol);
+    const double v[16] = {r.energy, r.e_elec, r.e_rep, r.e_es, r.e_aes, r.e_axc, r.e_disp, r.hl_gap, r.gnorm, r.e_atm,
+                          r.dipole[0], r.dipole[1], r.dipole[2], (double)r.niter, (double)r.converged, (double)r.fail};
+    std::memcpy(out16, v, sizeof(v));
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_getCounts(xtbb200_TBatch batch, int imol, int* ndp, int* nqp, int* sweeps) {
+    XTBB_TRY
+    if (!batch || imol < 0 || imol >= batch->b->nmol()) throw std::runtime_error("invalid molecule index");
+    MolResult r = batch->b->result(imol);
+    if (ndp) *ndp = r.ndp;
+    if (nqp) *nqp = r.nqp;
+    if (sweeps) *sweeps = r.sweeps;
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_getArrayLen(xtbb200_TBatch batch, const char* name, size_t* len) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    *len = batch->b->fetch_len(name);
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_getArray(xtbb200_TBatch batch, const char* name, double* out, size_t len) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    if (len < batch->b->fetch_len(name)) throw std::runtime_error("output buffer too small");
+    batch->b->fetch(name, out);
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_getOffsets(xtbb200_TBatch batch, int imol, long long* off5) {
+    XTBB_TRY
+    if (!batch || imol < 0 || imol >= batch->b->nmol()) throw std::runtime_error("invalid molecule index");
+    off5[0] = batch->b->atom_offset(imol); off5[1] = batch->b->shell_offset(imol); off5[2] = batch->b->ao_offset(imol);
+    off5[3] = batch->b->mat_offset(imol); off5[4] = batch->b->nn_offset(imol);
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_getMask(xtbb200_TBatch batch, unsigned char* out, size_t len) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    if (len < batch->b->fetch_len("S")) throw std::runtime_error("output buffer too small");
+    batch->b->fetch_mask(out);
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_getTimings(xtbb200_TBatch batch, float* ms3, int* launches) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    if (ms3) batch->b->timings(ms3);
+    if (launches) *launches = batch->b->launches();
+    return 0;
+    XTBB_CATCH(-1)
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// Common device definitions for the B200 GFN2-xTB engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "system.h"
+
+namespace xtbb200 {
+
+#define XTB_CUDA_CHECK(x)                                                                              \
+    do {                                                                                               \
+        cudaError_t err__ = (x);                                                                       \
+        if (err__ != cudaSuccess)                                                                      \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " + \
+                                     __FILE__ + ":" + std::to_string(__LINE__));                       \
+    } while (0)
+
+// per-molecule SCC state, lives on the device, mirrored to the host for convergence polling
+struct MolState {
+    int iter;        // iterations done
+    int converged;   // econverged && qconverged seen once
+    int lastdiag;
+    int done;        // SCC loop left
+    int fail;        // error code (0 ok)
+    int kocc;        // number of leading orbitals with non-zero occupation
+    int ndp, nqp;    // screening list lengths
+    int sweeps;      // Jacobi sweeps of the last diagonalisation
+    int sweeps_total;
+    int nrot_pad[2];
+    double eel, eold, ees, eaes, epol, ed, egap, ga, gb, efa, efb, rmsq;
+    double ep, embd, eh0;
+    double energy, gnorm;
+    double dipole[3];
+};
+
+// device pointer bundle
+struct Dev {
+    const MolDesc* mol;
+    MolState* st;
+    const AtomPar* atoms;
+    const ShellPar* shells;
+    const RefPar* refs;
+    const int* ao2sh;
+    const int* ao2at;
+    const double* c6ref;
+    int ntype;
+    int nmol;
+    int maxhist;
+    // options
+    double intcut, neglect, scfconv, qconv, etemp, broydamp;
+    int maxiter;
+    // per atom
+    double *xyz, *cn, *cn_cov, *cn_d4, *cn_erf, *radcn;
+    double *q, *q_out, *dipm, *dipm_out, *qp, *qp_out;
+    double *vs, *vd, *vq, *ashift;
+    double *grad, *dhdcn, *w_aes, *dEdcn, *e_atom;   // e_atom: [4] per atom partial energies (rep, aes, atm, spare)
+    double *zw;       // D4 gradient weights per atom: [5][7]
+    // per shell
+    double *selfE, *qsh, *qsh_out, *sshift, *jq;
+    // per AO
+    double *emo, *focc, *focca, *foccb, *aop;   // aop: [12] per AO partials
+    double *nrm;      // Jacobi column norms
+    int *rank;        // Jacobi eigenvalue ranks
+    // per ref
+    double *gw, *zeta, *dzeta, *dvec, *edref;
+    // matrices (nao^2)
+    double *S, *D, *Q, *H0, *H0n, *H, *X, *T, *Zm, *C, *P, *W;
+    uint8_t* mask;
+    long long tot_mat;
+    // nat^2
+    double *gab3, *gab5, *c6, *dc6, *c60, *dc60, *wbo;
+    // nsh^2 / ndim^2 / eeq
+    double *jmat, *dispmat, *eeqA;
+    const long long* eeq0;
+    // broyden
+    double *bdf, *bu, *ba, *bbeta, *bomega, *bqlast, *bdqlast, *bqin, *bdq;
+    // shell-pair gradient partials
+    double *gpair;   // [npair][4] : gx,gy,gz,dCN
+    const long long* pair0;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// deterministic block reduction (sum); result valid in all threads. red: >= 32 doubles of shared memory
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int i = 0; i < nw; ++i) r += red[i];
+    return r;
+}
+
+__device__ __forceinline__ int lin0(int a, int b) {  // packed index, 0-based (src/lin_mod.f90:28-36)
+    int mx = a > b ? a : b, mn = a > b ? b : a;
+    return mn + mx * (mx + 1) / 2;
+}
+
+}  // namespace xtbb200

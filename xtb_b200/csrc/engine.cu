@@ -1,0 +1,442 @@
+// B200-native batched GFN2-xTB single point + gradient engine (host driver).
+//
+// One Batch object = a set of molecules resident on one GPU.  All per-geometry state lives in HBM;
+// the host only launches kernels and polls a 4-byte "molecules still iterating" counter.
+// Reference path replaced: TxTBCalculator%singlepoint -> scf -> scc
+// (src/xtb/calculator.f90:195-350, src/scf_module.F90:74-920, src/scc_core.f90:255-640).
+#include "engine.h"
+
+#include <algorithm>
+#include <cstdio>
+
+#include "common.cuh"
+#include "kernels_geom.cuh"
+#include "kernels_grad.cuh"
+#include "kernels_int.cuh"
+#include "kernels_linalg.cuh"
+#include "kernels_scc.cuh"
+
+namespace xtbb200 {
+
+__global__ void k_reset_state(Dev d, int keep_wfn) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.nmol) return;
+    MolState& s = d.st[i];
+    s.iter = 0; s.converged = 0; s.lastdiag = 0; s.done = 0; s.fail = 0; s.kocc = 0; s.ndp = 0; s.nqp = 0;
+    s.sweeps = 0; s.sweeps_total = 0;
+    s.eel = 0; s.eold = 0; s.ees = 0; s.eaes = 0; s.epol = 0; s.ed = 0; s.egap = 0; s.ga = 0; s.gb = 0;
+    s.efa = 0; s.efb = 0; s.rmsq = 0; s.ep = 0; s.embd = 0; s.eh0 = 0; s.energy = 0; s.gnorm = 0;
+}
+__global__ void k_count_active(Dev d, int* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int a = (i < d.nmol && !d.st[i].done) ? 1 : 0;
+    unsigned b = __ballot_sync(0xffffffffu, a);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, __popc(b));
+}
+
+struct Batch::Impl {
+    BatchSystem sys;
+    Dev d;
+    std::vector<void*> allocs;
+    std::vector<long long> eeq0, pair0;
+    int* d_active = nullptr;
+    cudaStream_t stream = nullptr;
+    bool have_wfn = false;
+    bool positions_set = false;
+    std::vector<MolState> h_state;
+    int device = 0;
+    // options
+    double acc = 1.0, etemp = 300.0;
+    int maxiter = 250;
+    int guess = 0;
+    size_t bytes = 0;
+    // timing (ms) of the last single point
+    float t_setup = 0, t_scc = 0, t_grad = 0;
+    int launches = 0;
+
+    template <class T>
+    T* dalloc(size_t n) {
+        void* p = nullptr;
+        size_t b = std::max<size_t>(n, 1) * sizeof(T);
+        XTB_CUDA_CHECK(cudaMalloc(&p, b));
+        XTB_CUDA_CHECK(cudaMemsetAsync(p, 0, b, stream));
+        allocs.push_back(p);
+        bytes += b;
+        return (T*)p;
+    }
+    template <class T>
+    T* upload(const std::vector<T>& v) {
+        T* p = dalloc<T>(v.size());
+        if (!v.empty()) XTB_CUDA_CHECK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        return p;
+    }
+    ~Impl() {
+        for (void* p : allocs) cudaFree(p);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+int device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+static dim3 grid2(long long items, int block, int nmol) { return dim3((unsigned)std::max<long long>(1, (items + block - 1) / block), nmol); }
+
+Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* charges, const int* uhf, int device) {
+    p_ = new Impl();
+    Impl& I = *p_;
+    try {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw std::runtime_error("xtb_b200: no CUDA device available (this engine has no CPU fallback)");
+        I.device = device;
+        XTB_CUDA_CHECK(cudaSetDevice(device));
+        XTB_CUDA_CHECK(cudaStreamCreate(&I.stream));
+        const int maxhist = 120;
+        int off = 0;
+        for (int i = 0; i < nmol; ++i) {
+            I.sys.add_molecule(natoms[i], numbers + off, charges ? charges[i] : 0.0, uhf ? uhf[i] : 0, maxhist);
+            off += natoms[i];
+        }
+        I.sys.finalize();
+        BatchSystem& s = I.sys;
+        Dev& d = I.d;
+        std::memset(&d, 0, sizeof(d));
+        d.nmol = nmol; d.ntype = (int)s.etypes.size(); d.maxhist = maxhist;
+        d.mol = I.upload(s.mol);
+        d.atoms = I.upload(s.atoms);
+        d.shells = I.upload(s.shells);
+        d.refs = I.upload(s.refs);
+        d.ao2sh = I.upload(s.ao2sh);
+        d.ao2at = I.upload(s.ao2at);
+        d.c6ref = I.upload(s.c6ref);
+        d.st = I.dalloc<MolState>(nmol);
+        const size_t na = s.atoms.size(), ns = s.shells.size(), nao = s.ao2sh.size(), nr = s.refs.size();
+        d.xyz = I.dalloc<double>(3 * na); d.cn = I.dalloc<double>(na); d.cn_cov = I.dalloc<double>(na);
+        d.cn_d4 = I.dalloc<double>(na); d.cn_erf = I.dalloc<double>(na); d.radcn = I.dalloc<double>(na);
+        d.q = I.dalloc<double>(na); d.q_out = I.dalloc<double>(na);
+        d.dipm = I.dalloc<double>(3 * na); d.dipm_out = I.dalloc<double>(3 * na);
+        d.qp = I.dalloc<double>(6 * na); d.qp_out = I.dalloc<double>(6 * na);
+        d.vs = I.dalloc<double>(na); d.vd = I.dalloc<double>(3 * na); d.vq = I.dalloc<double>(6 * na);
+        d.ashift = I.dalloc<double>(na);
+        d.grad = I.dalloc<double>(3 * na); d.dhdcn = I.dalloc<double>(na); d.w_aes = I.dalloc<double>(na);
+        d.dEdcn = I.dalloc<double>(na); d.e_atom = I.dalloc<double>(4 * na); d.zw = I.dalloc<double>(35 * na);
+        d.selfE = I.dalloc<double>(ns); d.qsh = I.dalloc<double>(ns); d.qsh_out = I.dalloc<double>(ns);
+        d.sshift = I.dalloc<double>(ns); d.jq = I.dalloc<double>(ns);
+        d.emo = I.dalloc<double>(nao); d.focc = I.dalloc<double>(nao); d.focca = I.dalloc<double>(nao);
+        d.foccb = I.dalloc<double>(nao); d.aop = I.dalloc<double>(12 * nao); d.nrm = I.dalloc<double>(nao);
+        d.rank = I.dalloc<int>(nao);
+        d.gw = I.dalloc<double>(nr); d.zeta = I.dalloc<double>(nr); d.dzeta = I.dalloc<double>(nr);
+        d.dvec = I.dalloc<double>(nr); d.edref = nullptr;
+        d.tot_mat = s.tot_mat;
+        const size_t tm = (size_t)s.tot_mat;
+        d.S = I.dalloc<double>(tm); d.D = I.dalloc<double>(3 * tm); d.Q = I.dalloc<double>(6 * tm);
+        d.H0 = I.dalloc<double>(tm); d.H0n = I.dalloc<double>(tm); d.H = I.dalloc<double>(tm);
+        d.X = I.dalloc<double>(tm); d.T = I.dalloc<double>(tm); d.Zm = I.dalloc<double>(tm);
+        d.C = I.dalloc<double>(tm); d.P = I.dalloc<double>(tm); d.W = I.dalloc<double>(tm);
+        d.mask = I.dalloc<uint8_t>(tm);
+        const size_t tn = (size_t)s.tot_nn;
+        d.gab3 = I.dalloc<double>(tn); d.gab5 = I.dalloc<double>(tn); d.c6 = I.dalloc<double>(tn);
+        d.dc6 = I.dalloc<double>(tn); d.c60 = I.dalloc<double>(tn); d.dc60 = I.dalloc<double>(tn);
+        d.wbo = I.dalloc<double>(tn);
+        d.jmat = I.dalloc<double>((size_t)s.tot_ss);
+        d.dispmat = I.dalloc<double>((size_t)s.tot_dd);
+        long long te = 0, tp = 0;
+        for (int i = 0; i < nmol; ++i) {
+            I.eeq0.push_back(te); te += (long long)(s.mol[i].nat + 1) * (s.mol[i].nat + 2);
+            I.pair0.push_back(tp); tp += (long long)s.mol[i].nsh * (s.mol[i].nsh + 1) / 2;
+        }
+        d.eeqA = I.dalloc<double>((size_t)te);
+        d.eeq0 = I.upload(I.eeq0);
+        d.gpair = I.dalloc<double>(4 * (size_t)tp);
+        d.pair0 = I.upload(I.pair0);
+        d.bdf = I.dalloc<double>((size_t)s.tot_br); d.bu = I.dalloc<double>((size_t)s.tot_br);
+        d.ba = I.dalloc<double>((size_t)nmol * maxhist * maxhist); d.bbeta = I.dalloc<double>((size_t)nmol * maxhist * maxhist);
+        d.bomega = I.dalloc<double>((size_t)nmol * maxhist);
+        d.bqlast = I.dalloc<double>((size_t)s.tot_q); d.bdqlast = I.dalloc<double>((size_t)s.tot_q);
+        d.bqin = I.dalloc<double>((size_t)s.tot_q); d.bdq = I.dalloc<double>((size_t)s.tot_q);
+        I.d_active = I.dalloc<int>(1);
+        I.h_state.resize(nmol);
+        XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+        // opt in to large dynamic shared memory for the in-SM solvers
+        const int smax = 227 * 1024 - 2048;
+        cudaFuncSetAttribute(k_chol_inv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        cudaFuncSetAttribute(k_jacobi<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        cudaFuncSetAttribute(k_jacobi<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        cudaFuncSetAttribute(k_jacobi<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        cudaFuncSetAttribute(k_jacobi<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+    } catch (...) {
+        delete p_;
+        p_ = nullptr;
+        throw;
+    }
+}
+
+Batch::~Batch() { delete p_; }
+
+int Batch::nmol() const { return p_->d.nmol; }
+int Batch::natoms(int i) const { return p_->sys.mol[i].nat; }
+int Batch::nao(int i) const { return p_->sys.mol[i].nao; }
+int Batch::nshell(int i) const { return p_->sys.mol[i].nsh; }
+int Batch::atom_offset(int i) const { return p_->sys.mol[i].at0; }
+int Batch::shell_offset(int i) const { return p_->sys.mol[i].sh0; }
+int Batch::ao_offset(int i) const { return p_->sys.mol[i].ao0; }
+long long Batch::mat_offset(int i) const { return p_->sys.mol[i].mat0; }
+long long Batch::nn_offset(int i) const { return p_->sys.mol[i].nn0; }
+int Batch::total_atoms() const { return (int)p_->sys.atoms.size(); }
+int Batch::total_shells() const { return (int)p_->sys.shells.size(); }
+int Batch::total_ao() const { return (int)p_->sys.ao2sh.size(); }
+size_t Batch::device_bytes() const { return p_->bytes; }
+void* Batch::stream() const { return (void*)p_->stream; }
+
+void Batch::set_options(double accuracy, double etemp, int maxiter) {
+    p_->acc = accuracy; p_->etemp = etemp; p_->maxiter = maxiter;
+}
+void Batch::set_guess(int mode) { p_->guess = mode; }
+
+void Batch::set_positions(const double* xyz_host) {
+    Impl& I = *p_;
+    XTB_CUDA_CHECK(cudaSetDevice(I.device));
+    XTB_CUDA_CHECK(cudaMemcpyAsync(I.d.xyz, xyz_host, 3 * I.sys.atoms.size() * sizeof(double), cudaMemcpyHostToDevice, I.stream));
+    I.positions_set = true;
+}
+void Batch::set_positions_device(const double* xyz_dev) {
+    Impl& I = *p_;
+    XTB_CUDA_CHECK(cudaSetDevice(I.device));
+    XTB_CUDA_CHECK(cudaMemcpyAsync(I.d.xyz, xyz_dev, 3 * I.sys.atoms.size() * sizeof(double), cudaMemcpyDeviceToDevice, I.stream));
+    I.positions_set = true;
+}
+void Batch::invalidate_wavefunction() { p_->have_wfn = false; }
+bool Batch::has_wavefunction() const { return p_->have_wfn; }
+
+void Batch::set_wavefunction(const double* qsh, const double* dipm, const double* qp) {
+    Impl& I = *p_;
+    XTB_CUDA_CHECK(cudaSetDevice(I.device));
+    XTB_CUDA_CHECK(cudaMemcpyAsync(I.d.qsh, qsh, I.sys.shells.size() * sizeof(double), cudaMemcpyHostToDevice, I.stream));
+    XTB_CUDA_CHECK(cudaMemcpyAsync(I.d.dipm, dipm, 3 * I.sys.atoms.size() * sizeof(double), cudaMemcpyHostToDevice, I.stream));
+    XTB_CUDA_CHECK(cudaMemcpyAsync(I.d.qp, qp, 6 * I.sys.atoms.size() * sizeof(double), cudaMemcpyHostToDevice, I.stream));
+    I.have_wfn = true;
+}
+
+template <int TG>
+static void launch_jacobi(Dev& d, int nmol, int max_nao, bool sm, cudaStream_t st) {
+    const int npairs = (max_nao + 1) / 2;
+    int threads = std::min(1024, ((TG * npairs + 31) / 32) * 32);
+    threads = std::max(threads, 32);
+    if (sm) {
+        size_t bytes = (size_t)max_nao * (max_nao | 1) * sizeof(double);
+        k_jacobi<TG, true><<<nmol, threads, bytes, st>>>(d);
+    } else {
+        k_jacobi<TG, false><<<nmol, threads, 0, st>>>(d);
+    }
+}
+
+int Batch::singlepoint(bool restart) {
+    Impl& I = *p_;
+    Dev& d = I.d;
+    BatchSystem& s = I.sys;
+    if (!I.positions_set) throw std::runtime_error("positions not set");
+    XTB_CUDA_CHECK(cudaSetDevice(I.device));
+    cudaStream_t st = I.stream;
+    const int nmol = d.nmol;
+    // thresholds, src/scf_module.F90:264-277
+    d.intcut = std::max(20.0, 25.0 - 10.0 * std::log10(I.acc));
+    d.neglect = 10.0e-9 * I.acc;
+    d.scfconv = 1.e-6 * I.acc;
+    d.qconv = 1.e-4 * I.acc;
+    d.etemp = I.etemp;
+    d.broydamp = 0.4;   // src/setparam.f90:226
+    d.maxiter = I.maxiter;
+    cudaEvent_t ev[4];
+    for (auto& e : ev) cudaEventCreate(&e);
+    int nl = 0;
+    const int B = 128;
+    cudaEventRecord(ev[0], st);
+    k_reset_state<<<(nmol + 127) / 128, 128, 0, st>>>(d, 0); nl++;
+    // ---- geometry dependent setup
+    k_cn<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d); nl++;
+    const int mx = std::max(s.max_nat, std::max(s.max_nsh, s.max_ndim));
+    k_cn_dependent<<<grid2(mx, B, nmol), B, 0, st>>>(d); nl++;
+    k_gab<<<grid2((long long)s.max_nat * s.max_nat, 256, nmol), 256, 0, st>>>(d); nl++;
+    k_jmat<<<grid2((long long)s.max_nsh * s.max_nsh, 256, nmol), 256, 0, st>>>(d); nl++;
+    k_dispmat<<<grid2((long long)s.max_ndim * s.max_ndim, 256, nmol), 256, 0, st>>>(d); nl++;
+    k_repulsion<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d); nl++;
+    // ---- guess (src/api/interface.f90:82-101: reuse the cached wavefunction when present)
+    if (!(restart && I.have_wfn)) {
+        if (I.guess == 0) {
+            k_eeq_build<<<grid2((long long)(s.max_nat + 1) * (s.max_nat + 2), 256, nmol), 256, 0, st>>>(d); nl++;
+            k_eeq_solve<<<nmol, 256, 0, st>>>(d); nl++;
+        } else {
+            k_guess_uniform<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d); nl++;
+        }
+    }
+    k_qsh2qat<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d); nl++;
+    // ---- integrals
+    const long long max_pairs = (long long)s.max_nsh * (s.max_nsh + 1) / 2;
+    k_sdqh0<<<grid2(max_pairs, kIntWarps, nmol), kIntWarps * 32, 0, st>>>(d); nl++;
+    const long long nn2 = (long long)s.max_nao * s.max_nao;
+    k_dqmask<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d); nl++;
+    // ---- overlap factorisation
+    const size_t chol_bytes = (size_t)s.max_nao * (s.max_nao | 1) * sizeof(double);
+    const bool sm = chol_bytes <= (size_t)(227 * 1024 - 4096);
+    if (sm) k_chol_inv<true><<<nmol, 512, chol_bytes, st>>>(d);
+    else k_chol_inv<false><<<nmol, 512, 0, st>>>(d);
+    nl++;
+    cudaEventRecord(ev[1], st);
+    // ---- SCC iterations
+    const int tiles = (s.max_nao + GT - 1) / GT;
+    const dim3 ggrid(tiles * tiles, nmol);
+    const int npairs = (s.max_nao + 1) / 2;
+    int active = nmol;
+    for (int it = 0; it < I.maxiter && active > 0; ++it) {
+        k_pot_shell<<<grid2(s.max_nsh, B, nmol), B, 0, st>>>(d);
+        k_pot_aes<true><<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
+        k_d4_zeta<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d, 0);
+        k_d4_matvec<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d);
+        k_d4_shift<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d);
+        k_fock<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d);
+        k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.H, d.X, d.T, 0, 1);      // T = H X
+        k_gemm<true, false><<<ggrid, 128, 0, st>>>(d, d.X, d.T, d.W, 0, 1);       // W = X^T T
+        if (npairs * 32 <= 1024) launch_jacobi<32>(d, nmol, s.max_nao, sm, st);
+        else if (npairs * 16 <= 1024) launch_jacobi<16>(d, nmol, s.max_nao, sm, st);
+        else if (npairs * 8 <= 1024) launch_jacobi<8>(d, nmol, s.max_nao, sm, st);
+        else launch_jacobi<4>(d, nmol, s.max_nao, sm, st);
+        k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.Zm, d.C, 0, 1);     // C = X Z
+        k_fermi<<<nmol, 32, 0, st>>>(d);
+        k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 0);                // T = C f
+        k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.P, 1, 1);       // P = T C^T
+        k_pop_rows<<<grid2((long long)s.max_nao * 32, 256, nmol), 256, 0, st>>>(d);
+        k_pop_atoms<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
+        k_es_rows<<<grid2(s.max_nsh, B, nmol), B, 0, st>>>(d);
+        k_aes_rows<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
+        k_d4_zeta<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d, 1);
+        k_d4_matvec<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d);
+        k_scc_finish<<<nmol, 256, 0, st>>>(d);
+        nl += 20;
+        XTB_CUDA_CHECK(cudaMemsetAsync(I.d_active, 0, sizeof(int), st));
+        k_count_active<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.d_active); nl++;
+        XTB_CUDA_CHECK(cudaMemcpyAsync(&active, I.d_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+        XTB_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    cudaEventRecord(ev[2], st);
+    // ---- gradient
+    k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 1);                     // T = C (f e)
+    k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.H, 1, 0);            // H <- energy weighted density
+    k_pot_aes<false><<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
+    k_grad_h0<<<grid2(max_pairs, kIntWarps, nmol), kIntWarps * 32, 0, st>>>(d);
+    k_grad_h0_collect<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
+    k_grad_aes<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
+    k_d4_weights<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
+    k_d4_c6<<<grid2((long long)s.max_nat * s.max_nat, 128, nmol), 128, 0, st>>>(d);
+    k_grad_pairs<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
+    k_grad_atm<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
+    k_grad_cn<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
+    nl += 11;
+    // ---- properties: bond orders and dipole
+    bool any_open = false;
+    for (auto& m : s.mol) any_open |= (m.nopen != 0);
+    if (!any_open) {
+        k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.P, d.S, d.W, 0, 0); nl++;
+    } else {
+        // alpha / beta densities (scf_module.F90:869-879); closed-shell members of a mixed batch take this path too
+        k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 2);
+        k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.X, 0, 0);
+        k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.S, d.W, 0, 0);
+        k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 3);
+        k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.X, 0, 0);
+        k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.S, d.Zm, 0, 0);
+        nl += 6;
+    }
+    k_wbo<<<grid2((long long)s.max_nat * s.max_nat, 128, nmol), 128, 0, st>>>(d, any_open ? 1 : 0); nl++;
+    k_finish<<<nmol, 256, 0, st>>>(d); nl++;
+    cudaEventRecord(ev[3], st);
+    XTB_CUDA_CHECK(cudaMemcpyAsync(I.h_state.data(), d.st, nmol * sizeof(MolState), cudaMemcpyDeviceToHost, st));
+    XTB_CUDA_CHECK(cudaStreamSynchronize(st));
+    XTB_CUDA_CHECK(cudaGetLastError());
+    cudaEventElapsedTime(&I.t_setup, ev[0], ev[1]);
+    cudaEventElapsedTime(&I.t_scc, ev[1], ev[2]);
+    cudaEventElapsedTime(&I.t_grad, ev[2], ev[3]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    I.launches = nl;
+    I.have_wfn = true;
+    int nfail = 0;
+    for (int i = 0; i < nmol; ++i)
+        if (I.h_state[i].fail || !I.h_state[i].converged) nfail++;
+    return nfail;
+}
+
+int Batch::launches() const { return p_->launches; }
+void Batch::timings(float* t3) const { t3[0] = p_->t_setup; t3[1] = p_->t_scc; t3[2] = p_->t_grad; }
+
+MolResult Batch::result(int i) const {
+    const MolState& s = p_->h_state[i];
+    MolResult r;
+    r.energy = s.energy; r.e_elec = s.eel + s.embd; r.e_rep = s.ep; r.e_es = s.ees; r.e_aes = s.eaes; r.e_axc = s.epol;
+    r.e_disp = s.ed + s.embd; r.hl_gap = s.egap; r.gnorm = s.gnorm; r.e_atm = s.embd;
+    r.niter = s.iter; r.converged = s.converged; r.fail = s.fail; r.ndp = s.ndp; r.nqp = s.nqp; r.sweeps = s.sweeps_total;
+    for (int k = 0; k < 3; ++k) r.dipole[k] = s.dipole[k];
+    return r;
+}
+
+void Batch::fetch(const char* name, double* out) const {
+    Impl& I = *p_;
+    const Dev& d = I.d;
+    const size_t na = I.sys.atoms.size(), ns = I.sys.shells.size(), nao = I.sys.ao2sh.size(), nr = I.sys.refs.size();
+    const size_t tm = (size_t)I.sys.tot_mat, tn = (size_t)I.sys.tot_nn;
+    struct E { const char* n; const double* p; size_t c; };
+    const E tab[] = {
+        {"gradient", d.grad, 3 * na}, {"q", d.q, na}, {"qsh", d.qsh, ns}, {"dipm", d.dipm, 3 * na}, {"qp", d.qp, 6 * na},
+        {"cn", d.cn, na}, {"cn_cov", d.cn_cov, na}, {"cn_d4", d.cn_d4, na}, {"cn_erf", d.cn_erf, na}, {"radcn", d.radcn, na},
+        {"emo", d.emo, nao}, {"focc", d.focc, nao}, {"S", d.S, tm}, {"dpint", d.D, 3 * tm}, {"qpint", d.Q, 6 * tm},
+        {"H0", d.H0, tm}, {"H0_noovlp", d.H0n, tm}, {"P", d.P, tm}, {"C", d.C, tm}, {"X", d.X, tm}, {"wbo", d.wbo, tn},
+        {"gab3", d.gab3, tn}, {"gab5", d.gab5, tn}, {"jmat", d.jmat, (size_t)I.sys.tot_ss},
+        {"dispmat", d.dispmat, (size_t)I.sys.tot_dd}, {"gw", d.gw, nr}, {"selfenergy", d.selfE, ns}, {"xyz", d.xyz, 3 * na},
+        {"vs", d.vs, na}, {"vd", d.vd, 3 * na}, {"vq", d.vq, 6 * na}, {"q_out", d.q_out, na}, {"qsh_out", d.qsh_out, ns},
+    };
+    XTB_CUDA_CHECK(cudaSetDevice(I.device));
+    for (const E& e : tab)
+        if (std::strcmp(e.n, name) == 0) {
+            XTB_CUDA_CHECK(cudaMemcpyAsync(out, e.p, e.c * sizeof(double), cudaMemcpyDeviceToHost, I.stream));
+            XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+            return;
+        }
+    throw std::runtime_error(std::string("unknown array: ") + name);
+}
+size_t Batch::fetch_len(const char* name) const {
+    Impl& I = *p_;
+    const size_t na = I.sys.atoms.size(), ns = I.sys.shells.size(), nao = I.sys.ao2sh.size(), nr = I.sys.refs.size();
+    const size_t tm = (size_t)I.sys.tot_mat, tn = (size_t)I.sys.tot_nn;
+    std::string n(name);
+    if (n == "gradient" || n == "dipm" || n == "xyz" || n == "vd") return 3 * na;
+    if (n == "qp" || n == "vq") return 6 * na;
+    if (n == "q" || n == "cn" || n == "cn_cov" || n == "cn_d4" || n == "cn_erf" || n == "radcn" || n == "vs" || n == "q_out") return na;
+    if (n == "qsh" || n == "selfenergy" || n == "qsh_out") return ns;
+    if (n == "emo" || n == "focc") return nao;
+    if (n == "S" || n == "H0" || n == "H0_noovlp" || n == "P" || n == "C" || n == "X") return tm;
+    if (n == "dpint") return 3 * tm;
+    if (n == "qpint") return 6 * tm;
+    if (n == "wbo" || n == "gab3" || n == "gab5") return tn;
+    if (n == "jmat") return (size_t)I.sys.tot_ss;
+    if (n == "dispmat") return (size_t)I.sys.tot_dd;
+    if (n == "gw") return nr;
+    throw std::runtime_error(std::string("unknown array: ") + name);
+}
+void Batch::fetch_mask(unsigned char* out) const {
+    Impl& I = *p_;
+    XTB_CUDA_CHECK(cudaSetDevice(I.device));
+    XTB_CUDA_CHECK(cudaMemcpyAsync(out, I.d.mask, (size_t)I.sys.tot_mat, cudaMemcpyDeviceToHost, I.stream));
+    XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+}
+const double* Batch::device_ptr(const char* name) const {
+    const Dev& d = p_->d;
+    std::string n(name);
+    if (n == "gradient") return d.grad;
+    if (n == "xyz") return d.xyz;
+    if (n == "q") return d.q;
+    throw std::runtime_error(std::string("unknown device array: ") + name);
+}
+
+}  // namespace xtbb200

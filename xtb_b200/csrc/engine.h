@@ -1,0 +1,61 @@
+// Public C++ interface of the batched B200 GFN2-xTB engine (no CUDA types in the signatures).
+#pragma once
+#include <cstddef>
+
+namespace xtbb200 {
+
+struct MolResult {
+    double energy, e_elec, e_rep, e_es, e_aes, e_axc, e_disp, hl_gap, gnorm, e_atm;
+    double dipole[3];
+    int niter, converged, fail, ndp, nqp, sweeps;
+};
+
+int device_count();
+
+class Batch {
+ public:
+    // numbers: concatenated atomic numbers of all molecules; charges/uhf may be null (0)
+    Batch(int nmol, const int* natoms, const int* numbers, const double* charges, const int* uhf, int device = 0);
+    ~Batch();
+    Batch(const Batch&) = delete;
+    Batch& operator=(const Batch&) = delete;
+
+    void set_options(double accuracy, double etemp, int maxiter);
+    void set_guess(int mode);                      // 0: EEQ (default), 1: uniform charges
+    void set_positions(const double* xyz_host);    // concatenated (3, natoms) in bohr, host memory
+    void set_positions_device(const double* xyz_dev);
+    void set_wavefunction(const double* qsh, const double* dipm, const double* qp);
+    void invalidate_wavefunction();
+    bool has_wavefunction() const;
+    // runs SP + gradient for every molecule; returns the number of molecules that failed / did not converge
+    int singlepoint(bool restart);
+
+    int nmol() const;
+    int natoms(int i) const;
+    int nao(int i) const;
+    int nshell(int i) const;
+    int atom_offset(int i) const;
+    int shell_offset(int i) const;
+    int ao_offset(int i) const;
+    long long mat_offset(int i) const;
+    long long nn_offset(int i) const;
+    int total_atoms() const;
+    int total_shells() const;
+    int total_ao() const;
+    size_t device_bytes() const;
+    void* stream() const;
+    int launches() const;
+    void timings(float* t3) const;   // ms: setup+integrals, SCC, gradient+properties
+
+    MolResult result(int i) const;
+    void fetch(const char* name, double* out) const;   // device -> host copy of a named array
+    size_t fetch_len(const char* name) const;
+    void fetch_mask(unsigned char* out) const;
+    const double* device_ptr(const char* name) const;
+
+ private:
+    struct Impl;
+    Impl* p_;
+};
+
+}  // namespace xtbb200

@@ -1,0 +1,258 @@
+// Shell-pair integral kernels: overlap / dipole / quadrupole / H0 (build_SDQH0) and the
+// screening masks.  One warp per shell pair, lanes over Cartesian component pairs, contracted
+// Gaussian primitives of the two shells staged in shared memory.
+//
+// Reference: src/xtb/hamiltonian.F90:146-371 (build_SDQH0), src/intgrad.f90:95-111 (olapp),
+// 357-471 (horizontal_shift, form_product), 509-555 (multipole_3d), 879-955 (get_multiints),
+// 144-231 (dtrf2), src/scc_core.f90:644-680 (h0scal), 728-754 (shellPoly),
+// src/aespot.F90:34-85 (setdqlist), src/xtb/hamiltonian.F90:796-848 (count_dpint/qpint).
+#pragma once
+#include "common.cuh"
+
+namespace xtbb200 {
+
+__constant__ int c_lx[10] = {0, 1, 0, 0, 2, 0, 0, 1, 1, 0};
+__constant__ int c_ly[10] = {0, 0, 1, 0, 0, 2, 0, 1, 0, 1};
+__constant__ int c_lz[10] = {0, 0, 0, 1, 0, 0, 2, 0, 1, 1};
+__constant__ int c_itt[3] = {0, 1, 4};
+__constant__ int c_ncart[3] = {1, 3, 6};
+__constant__ int c_nsph[3] = {1, 3, 5};
+// columns 2..6 of trafo (intgrad.f90:70-86): [cart m][sph a]
+__constant__ double c_dtrafo[6][5] = {{0.86602540378443864676, 0.5, 0, 0, 0}, {-0.86602540378443864676, 0.5, 0, 0, 0},
+                                      {0, -1.0, 0, 0, 0}, {0, 0, 1, 0, 0}, {0, 0, 0, 1, 0}, {0, 0, 0, 0, 1}};
+__constant__ double c_dcart[6] = {1.0, 1.0, 1.0, 1.7320508075688772935, 1.7320508075688772935, 1.7320508075688772935};
+
+// one-dimensional overlap moments, intgrad.f90:95-111
+__device__ __forceinline__ double olapp(int l, double gm) {  // gm = 0.5/gamma
+    switch (l) {
+        case 0: return 1.0;
+        case 2: return gm;
+        case 4: return gm * gm * 3.0;
+        case 6: return gm * gm * gm * 15.0;
+        case 8: return gm * gm * gm * gm * 105.0;
+        default: return 0.0;
+    }
+}
+
+// expand (x - A)^l around the product centre: coefficients of (x-P)^k, ae = P - A
+__device__ __forceinline__ void shift_poly(double ae, int l, double* c) {
+    // c has c[l] = 1 on input (others 0), intgrad.f90:357-380
+    switch (l) {
+        case 1: c[0] += ae * c[1]; break;
+        case 2: c[0] += ae * ae * c[2]; c[1] += 2 * ae * c[2]; break;
+        case 3: c[0] += ae * ae * ae * c[3]; c[1] += 3 * ae * ae * c[3]; c[2] += 3 * ae * c[3]; break;
+        default: break;
+    }
+}
+
+// 1D moment integrals <i| (x-C)^{0,1,2} |j> for one Cartesian direction, intgrad.f90:509-538
+template <int MAXLI>
+__device__ __forceinline__ void moments_1d(int li, int lj, double pa, double pb, double rpc, const double* s1d, double* val) {
+    double vi[MAXLI + 1], vj[3], vv[MAXLI + 3];
+#pragma unroll
+    for (int k = 0; k <= MAXLI; ++k) vi[k] = 0.0;
+    vj[0] = vj[1] = vj[2] = 0.0;
+    vi[li] = 1.0; vj[lj] = 1.0;
+    shift_poly(pa, li, vi);
+    shift_poly(pb, lj, vj);
+#pragma unroll
+    for (int k = 0; k < MAXLI + 3; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a <= MAXLI; ++a) {
+            int b = k - a;
+            if (b >= 0 && b <= 2) s += vi[a] * vj[b];
+        }
+        vv[k] = s;
+    }
+    double v0 = 0, v1 = 0, v2 = 0;
+#pragma unroll
+    for (int l = 0; l < MAXLI + 3; ++l) {
+        if (l <= li + lj) {
+            v0 += s1d[l] * vv[l];
+            v1 += (s1d[l + 1] + rpc * s1d[l]) * vv[l];
+            v2 += (s1d[l + 2] + 2 * rpc * s1d[l + 1] + rpc * rpc * s1d[l]) * vv[l];
+        }
+    }
+    val[0] = v0; val[1] = v1; val[2] = v2;
+}
+
+// h0scal valence-valence branch (scc_core.f90:644-680), kScale/enScale from gfn2.f90:834-853
+__device__ __forceinline__ double h0scal(int li, int lj, double eni, double enj) {
+    const double kshell[3] = {1.85, 2.23, 2.23};
+    double ks = 0.5 * (kshell[li] + kshell[lj]);
+    if ((li == 0 && lj == 2) || (li == 2 && lj == 0)) ks = 2.0;
+    if ((li == 1 && lj == 2) || (li == 2 && lj == 1)) ks = 2.0;
+    double den = (eni - enj) * (eni - enj);
+    double enpoly = (1.0 + 0.02 * den * (1.0 + 0.0 * den));
+    return ks * enpoly * 1.0;
+}
+
+constexpr int kIntWarps = 4;
+
+// S, D, Q, H0, H0_noovlp for all shell pairs (is >= js).  grid = (ceil(npair/kIntWarps), nmol)
+__global__ void __launch_bounds__(kIntWarps * 32) k_sdqh0(Dev d) {
+    const MolDesc m = d.mol[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long npair = (long long)m.nsh * (m.nsh + 1) / 2;
+    long long p = (long long)blockIdx.x * kIntWarps + warp;
+    __shared__ double s_blk[kIntWarps][10][36];
+    __shared__ double s_alp[kIntWarps][2][6], s_cont[kIntWarps][2][6];
+    if (p >= npair) return;   // whole warp exits together
+    int is = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+    while ((long long)is * (is + 1) / 2 > p) --is;
+    while ((long long)(is + 1) * (is + 2) / 2 <= p) ++is;
+    int js = (int)(p - (long long)is * (is + 1) / 2);
+    const ShellPar& si = d.shells[m.sh0 + is];
+    const ShellPar& sj = d.shells[m.sh0 + js];
+    const int li = si.l, lj = sj.l, iat = si.atom, jat = sj.atom;
+    const int nci = c_ncart[li], ncj = c_ncart[lj], npi = si.nprim, npj = sj.nprim;
+    if (lane < 6) { s_alp[warp][0][lane] = si.alp[lane]; s_cont[warp][0][lane] = si.cont[lane]; }
+    else if (lane < 12) { s_alp[warp][1][lane - 6] = sj.alp[lane - 6]; s_cont[warp][1][lane - 6] = sj.cont[lane - 6]; }
+    __syncwarp();
+    const double* ri = d.xyz + 3 * (m.at0 + iat);
+    const double* rj = d.xyz + 3 * (m.at0 + jat);
+    const double rij[3] = {ri[0] - rj[0], ri[1] - rj[1], ri[2] - rj[2]};
+    const double rij2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
+    const double intcut = d.intcut;
+    const double sqrtpi = sqrt(kPi);
+    const int ncomp = nci * ncj;
+    for (int c = lane; c < 36; c += 32)
+        for (int k = 0; k < 10; ++k) s_blk[warp][k][c] = 0.0;
+    __syncwarp();
+    for (int c = lane; c < ncomp; c += 32) {
+        const int mli = c / ncj, mlj = c % ncj;
+        const int lix = c_lx[c_itt[li] + mli], liy = c_ly[c_itt[li] + mli], liz = c_lz[c_itt[li] + mli];
+        const int ljx = c_lx[c_itt[lj] + mlj], ljy = c_ly[c_itt[lj] + mlj], ljz = c_lz[c_itt[lj] + mlj];
+        const double fi = (li == 2) ? c_dcart[mli] : 1.0, fj = (lj == 2) ? c_dcart[mlj] : 1.0;
+        double acc[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc[k] = 0.0;
+        if (rij2 <= 2000.0) {
+            for (int ip = 0; ip < npi; ++ip) {
+                const double alpi = s_alp[warp][0][ip];
+                const double ci = s_cont[warp][0][ip] * fi;
+                for (int jp = 0; jp < npj; ++jp) {
+                    const double alpj = s_alp[warp][1][jp];
+                    double est = alpi * alpj * rij2;
+                    if (est > intcut * (alpi + alpj)) continue;
+                    const double ab = 1.0 / (alpi + alpj);
+                    est = est * ab;
+                    const double sq = sqrtpi * sqrt(ab);
+                    const double kab = exp(-est) * (sq * sq * sq);
+                    const double cc = kab * (s_cont[warp][1][jp] * fj) * ci;
+                    const double gm = 0.5 * ab;
+                    double t[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) t[k] = olapp(k, gm);
+                    double vx[3], vy[3], vz[3];
+                    {
+                        double rp = (alpi * ri[0] + alpj * rj[0]) * ab;
+                        moments_1d<2>(lix, ljx, rp - ri[0], rp - rj[0], rp, t, vx);
+                        rp = (alpi * ri[1] + alpj * rj[1]) * ab;
+                        moments_1d<2>(liy, ljy, rp - ri[1], rp - rj[1], rp, t, vy);
+                        rp = (alpi * ri[2] + alpj * rj[2]) * ab;
+                        moments_1d<2>(liz, ljz, rp - ri[2], rp - rj[2], rp, t, vz);
+                    }
+                    acc[0] += vx[0] * vy[0] * vz[0] * cc;
+                    acc[1] += vx[1] * vy[0] * vz[0] * cc;
+                    acc[2] += vx[0] * vy[1] * vz[0] * cc;
+                    acc[3] += vx[0] * vy[0] * vz[1] * cc;
+                    acc[4] += vx[2] * vy[0] * vz[0] * cc;
+                    acc[5] += vx[0] * vy[2] * vz[0] * cc;
+                    acc[6] += vx[0] * vy[0] * vz[2] * cc;
+                    acc[7] += vx[1] * vy[1] * vz[0] * cc;
+                    acc[8] += vx[1] * vy[0] * vz[1] * cc;
+                    acc[9] += vx[0] * vy[1] * vz[1] * cc;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) s_blk[warp][k][mli * 6 + mlj] = acc[k];
+    }
+    __syncwarp();
+    // CAO -> SAO and scatter.  Output element (ii, jj) of the spherical block, 10 operators.
+    const int nsi = c_nsph[li], nsj = c_nsph[lj];
+    const int nao = m.nao;
+    double hav = 0.0, shpoly = 1.0;
+    const bool offsite = (iat != jat);
+    if (offsite) {
+        const AtomPar& a = d.atoms[m.at0 + iat];
+        const AtomPar& b = d.atoms[m.at0 + jat];
+        double hii = d.selfE[m.sh0 + is], hjj = d.selfE[m.sh0 + js];
+        double zetaij = pow(2 * sqrt(si.zeta * sj.zeta) / (si.zeta + sj.zeta), 0.5);
+        double km = h0scal(li, lj, a.en, b.en);
+        hav = 0.5 * km * (hii + hjj) * zetaij;
+        double r = sqrt(rij2) / (b.rad + a.rad);
+        shpoly = (1.0 + 0.01 * si.poly * sqrt(r)) * (1.0 + 0.01 * sj.poly * sqrt(r));
+    }
+    for (int e = lane; e < nsi * nsj; e += 32) {
+        const int ii = e / nsj, jj = e % nsj;
+        const int iao = si.ao0 + ii, jao = sj.ao0 + jj;
+        if (!offsite && is == js && jao > iao) continue;
+        double out[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            double v = 0.0;
+            if (li == 2 && lj == 2) {
+                for (int a = 0; a < 6; ++a) {
+                    double ta = c_dtrafo[a][ii];
+                    if (ta == 0.0) continue;
+                    for (int b = 0; b < 6; ++b) v += ta * c_dtrafo[b][jj] * s_blk[warp][k][a * 6 + b];
+                }
+            } else if (li == 2) {
+                for (int a = 0; a < 6; ++a) v += c_dtrafo[a][ii] * s_blk[warp][k][a * 6 + jj];
+            } else if (lj == 2) {
+                for (int b = 0; b < 6; ++b) v += c_dtrafo[b][jj] * s_blk[warp][k][ii * 6 + b];
+            } else {
+                v = s_blk[warp][k][ii * 6 + jj];
+            }
+            out[k] = v;
+        }
+        const long long a1 = m.mat0 + iao + (long long)nao * jao, a2 = m.mat0 + jao + (long long)nao * iao;
+        if (offsite) {
+            d.S[a1] = out[0]; d.S[a2] = out[0];
+            double h = hav * shpoly * out[0], hn = hav * shpoly;
+            d.H0[a1] = h; d.H0[a2] = h; d.H0n[a1] = hn; d.H0n[a2] = hn;
+        } else {
+            double sv = (iao == jao) ? 1.0 : 0.0;
+            double hv = (iao == jao) ? d.selfE[m.sh0 + is] : 0.0;
+            d.S[a1] = sv; d.S[a2] = sv; d.H0[a1] = hv; d.H0[a2] = hv; d.H0n[a1] = hv; d.H0n[a2] = hv;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { d.D[k * d.tot_mat + a1] = out[1 + k]; d.D[k * d.tot_mat + a2] = out[1 + k]; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { d.Q[k * d.tot_mat + a1] = out[4 + k]; d.Q[k * d.tot_mat + a2] = out[4 + k]; }
+    }
+}
+
+// dipole / quadrupole screening masks + list lengths (aespot.F90:34-85); thread per (i,j)
+__global__ void k_dqmask(Dev d) {
+    const MolDesc m = d.mol[blockIdx.y];
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int nd = 0, nq = 0;
+    if (t < (long long)m.nao * m.nao) {
+        int i = (int)(t % m.nao), j = (int)(t / m.nao);
+        long long a = m.mat0 + t;
+        double thr2 = d.neglect * 1.0e-2;
+        double tmp1 = 0, tmp2 = 0;
+        for (int k = 0; k < 3; ++k) {
+            double dv = d.D[k * d.tot_mat + a], qv = d.Q[k * d.tot_mat + a];
+            tmp1 += dv * dv; tmp2 -= qv * qv;
+        }
+        for (int k = 0; k < 6; ++k) { double qv = d.Q[k * d.tot_mat + a]; tmp2 += 2.0 * qv * qv; }
+        uint8_t mk = 0;
+        if (tmp1 > thr2) mk |= 1;
+        if (tmp2 > thr2) mk |= 2;
+        d.mask[a] = mk;
+        if (j <= i) { nd = mk & 1; nq = (mk >> 1) & 1; }
+    }
+    // integer counts: order independent, atomics are exact
+    unsigned bd = __ballot_sync(0xffffffffu, nd), bq = __ballot_sync(0xffffffffu, nq);
+    if ((threadIdx.x & 31) == 0) {
+        if (bd) atomicAdd(&d.st[blockIdx.y].ndp, __popc(bd));
+        if (bq) atomicAdd(&d.st[blockIdx.y].nqp, __popc(bq));
+    }
+}
+
+}  // namespace xtbb200

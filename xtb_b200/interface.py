@@ -1,0 +1,426 @@
+"""ctypes binding of the C ABI (include/xtb.h, include/xtb_b200.h).
+
+Class and method names follow the reference's Python binding (xtb-python: xtb.interface.Calculator /
+Results / Param / XTBException, itself a thin wrapper of include/xtb.h) so that code written against
+it reads the same here.  Units: Bohr, Hartree.
+"""
+import ctypes
+import enum
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+
+
+class XTBException(Exception):
+    """Error raised from the environment log of the C API (xtb_checkEnvironment != 0)."""
+
+
+def library_path():
+    return os.path.join(_HERE, "lib", "libxtb_b200.so")
+
+
+def load_library():
+    """Load the CUDA engine; fails loudly when it has not been built (no fallback path exists)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise XTBException("CUDA engine %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)" % path)
+    L = ctypes.CDLL(path)
+    vp, cp, ci, cd = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_double
+    sig = {
+        "xtb_getAPIVersion": (ci, []),
+        "xtb_newEnvironment": (vp, []), "xtb_delEnvironment": (None, [ctypes.POINTER(vp)]),
+        "xtb_checkEnvironment": (ci, [vp]), "xtb_showEnvironment": (None, [vp, cp]),
+        "xtb_getError": (None, [vp, cp, _c_int_p]), "xtb_setOutput": (None, [vp, cp]),
+        "xtb_releaseOutput": (None, [vp]), "xtb_setVerbosity": (None, [vp, ci]),
+        "xtb_newMolecule": (vp, [vp, _c_int_p, _c_int_p, _c_double_p, _c_double_p, _c_int_p, _c_double_p, vp]),
+        "xtb_delMolecule": (None, [ctypes.POINTER(vp)]), "xtb_updateMolecule": (None, [vp, vp, _c_double_p, _c_double_p]),
+        "xtb_newCalculator": (vp, []), "xtb_delCalculator": (None, [ctypes.POINTER(vp)]),
+        "xtb_loadGFN0xTB": (None, [vp, vp, vp, cp]), "xtb_loadGFN1xTB": (None, [vp, vp, vp, cp]),
+        "xtb_loadGFN2xTB": (None, [vp, vp, vp, cp]), "xtb_loadGFNFF": (None, [vp, vp, vp, cp]),
+        "xtb_setSolvent": (None, [vp, vp, cp, _c_int_p, _c_double_p, _c_int_p, cp]),
+        "xtb_releaseSolvent": (None, [vp, vp]),
+        "xtb_setExternalCharges": (None, [vp, vp, _c_int_p, _c_int_p, _c_double_p, _c_double_p]),
+        "xtb_releaseExternalCharges": (None, [vp, vp]),
+        "xtb_setAccuracy": (None, [vp, vp, cd]), "xtb_setMaxIter": (None, [vp, vp, ci]),
+        "xtb_setElectronicTemp": (None, [vp, vp, cd]),
+        "xtb_cpcmx_calc": (None, [vp, vp, vp, vp]), "xtb_singlepoint": (None, [vp, vp, vp, vp]),
+        "xtb_hessian": (None, [vp, vp, vp, vp, _c_double_p, _c_int_p, _c_int_p, _c_double_p, _c_double_p]),
+        "xtb_newResults": (vp, []), "xtb_delResults": (None, [ctypes.POINTER(vp)]), "xtb_copyResults": (vp, [vp]),
+        "xtb_getEnergy": (None, [vp, vp, _c_double_p]), "xtb_getSolvationEnergy": (None, [vp, vp, _c_double_p]),
+        "xtb_getGradient": (None, [vp, vp, _c_double_p]), "xtb_getPCGradient": (None, [vp, vp, _c_double_p]),
+        "xtb_getVirial": (None, [vp, vp, _c_double_p]), "xtb_getDipole": (None, [vp, vp, _c_double_p]),
+        "xtb_getCharges": (None, [vp, vp, _c_double_p]), "xtb_getBondOrders": (None, [vp, vp, _c_double_p]),
+        "xtb_getNao": (None, [vp, vp, _c_int_p]), "xtb_getOrbitalEigenvalues": (None, [vp, vp, _c_double_p]),
+        "xtb_getOrbitalOccupations": (None, [vp, vp, _c_double_p]),
+        "xtb_getOrbitalCoefficients": (None, [vp, vp, _c_double_p]),
+        # batched extension
+        "xtbb200_lastError": (cp, []), "xtbb200_deviceCount": (ci, []),
+        "xtbb200_newBatch": (vp, [ci, _c_int_p, _c_int_p, _c_double_p, _c_int_p, ci]),
+        "xtbb200_delBatch": (None, [ctypes.POINTER(vp)]),
+        "xtbb200_setOptions": (ci, [vp, cd, cd, ci, ci]),
+        "xtbb200_singlepoint": (ci, [vp, _c_double_p, ci, _c_double_p, _c_double_p, _c_double_p, _c_int_p, _c_int_p]),
+        "xtbb200_singlepointDevice": (ci, [vp, vp, ci, vp]),
+        "xtbb200_getNMol": (ci, [vp]), "xtbb200_getSizes": (ci, [vp, ci, _c_int_p, _c_int_p, _c_int_p]),
+        "xtbb200_getDeviceBytes": (ctypes.c_size_t, [vp]),
+        "xtbb200_getResult": (ci, [vp, ci, _c_double_p]), "xtbb200_getCounts": (ci, [vp, ci, _c_int_p, _c_int_p, _c_int_p]),
+        "xtbb200_getArrayLen": (ci, [vp, cp, ctypes.POINTER(ctypes.c_size_t)]),
+        "xtbb200_getArray": (ci, [vp, cp, _c_double_p, ctypes.c_size_t]),
+        "xtbb200_getOffsets": (ci, [vp, ci, ctypes.POINTER(ctypes.c_longlong)]),
+        "xtbb200_getMask": (ci, [vp, ctypes.c_void_p, ctypes.c_size_t]),
+        "xtbb200_getTimings": (ci, [vp, ctypes.POINTER(ctypes.c_float), _c_int_p]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _LIB = L
+    return L
+
+
+EXPORTED_SYMBOLS = None  # filled lazily by tests from the headers
+
+
+def device_count():
+    return load_library().xtbb200_deviceCount()
+
+
+def _dp(a):
+    return a.ctypes.data_as(_c_double_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_c_int_p)
+
+
+class Param(enum.Enum):
+    """Parametrisations selectable through the API (include/xtb.h:154-180)."""
+    GFN2xTB = "xtb_loadGFN2xTB"
+    GFN1xTB = "xtb_loadGFN1xTB"
+    GFN0xTB = "xtb_loadGFN0xTB"
+    GFNFF = "xtb_loadGFNFF"
+
+
+VERBOSITY_FULL, VERBOSITY_MINIMAL, VERBOSITY_MUTED = 2, 1, 0
+
+
+class Environment:
+    """Calculation environment (xtb_TEnvironment): error log + output unit + verbosity."""
+
+    def __init__(self):
+        self._lib = load_library()
+        self._env = ctypes.c_void_p(self._lib.xtb_newEnvironment())
+
+    def __del__(self):
+        try:
+            self._lib.xtb_delEnvironment(ctypes.byref(self._env))
+        except Exception:
+            pass
+
+    def check(self):
+        return self._lib.xtb_checkEnvironment(self._env)
+
+    def get_error(self, message=None):
+        buf = ctypes.create_string_buffer(2048)
+        n = ctypes.c_int(2048)
+        self._lib.xtb_getError(self._env, buf, ctypes.byref(n))
+        msg = buf.value.decode()
+        return msg if message is None else "%s:\n%s" % (message, msg)
+
+    def raise_on_error(self, message):
+        if self.check() != 0:
+            raise XTBException(self.get_error(message))
+
+    def set_output(self, filename):
+        self._lib.xtb_setOutput(self._env, filename.encode())
+        self.raise_on_error("Failed to open output file")
+
+    def release_output(self):
+        self._lib.xtb_releaseOutput(self._env)
+
+    def set_verbosity(self, verbosity):
+        self._lib.xtb_setVerbosity(self._env, int(verbosity))
+
+
+class Molecule(Environment):
+    """Molecular structure data (xtb_TMolecule); positions in Bohr."""
+
+    def __init__(self, numbers, positions, charge=None, uhf=None, lattice=None, periodic=None):
+        Environment.__init__(self)
+        self._numbers = np.ascontiguousarray(numbers, dtype=np.int32)
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        if pos.size != 3 * self._numbers.size:
+            raise ValueError("Dimension missmatch between numbers and positions")
+        self._natoms = int(self._numbers.size)
+        n = ctypes.c_int(self._natoms)
+        chrg = ctypes.c_double(charge) if charge is not None else None
+        u = ctypes.c_int(uhf) if uhf is not None else None
+        per = None
+        if periodic is not None:
+            per = (ctypes.c_bool * 3)(*[bool(p) for p in periodic])
+        lat = _dp(np.ascontiguousarray(lattice, dtype=np.float64)) if lattice is not None else None
+        self._mol = ctypes.c_void_p(self._lib.xtb_newMolecule(
+            self._env, ctypes.byref(n), _ip(self._numbers), _dp(pos),
+            ctypes.byref(chrg) if chrg is not None else None, ctypes.byref(u) if u is not None else None,
+            lat, ctypes.cast(per, ctypes.c_void_p) if per is not None else None))
+        self.raise_on_error("Setup of molecular structure failed")
+
+    def __del__(self):
+        try:
+            self._lib.xtb_delMolecule(ctypes.byref(self._mol))
+        except Exception:
+            pass
+        Environment.__del__(self)
+
+    def __len__(self):
+        return self._natoms
+
+    def update(self, positions, lattice=None):
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        if pos.size != 3 * self._natoms:
+            raise ValueError("Dimension missmatch for positions")
+        self._lib.xtb_updateMolecule(self._env, self._mol, _dp(pos), None)
+        self.raise_on_error("Update of molecular structure failed")
+
+
+class Results(Environment):
+    """Single point results (xtb_TResults); also carries the restart wavefunction."""
+
+    def __init__(self, res):
+        Environment.__init__(self)
+        if isinstance(res, Results):
+            self._res = ctypes.c_void_p(self._lib.xtb_copyResults(res._res))
+            self._natoms = res._natoms
+        else:
+            self._res = ctypes.c_void_p(self._lib.xtb_newResults())
+            self._natoms = len(res)
+
+    def __del__(self):
+        try:
+            self._lib.xtb_delResults(ctypes.byref(self._res))
+        except Exception:
+            pass
+        Environment.__del__(self)
+
+    def __len__(self):
+        return self._natoms
+
+    def _scalar(self, fn, msg):
+        v = ctypes.c_double(0.0)
+        fn(self._env, self._res, ctypes.byref(v))
+        self.raise_on_error(msg)
+        return v.value
+
+    def _array(self, fn, shape, msg):
+        a = np.zeros(shape, dtype=np.float64)
+        fn(self._env, self._res, _dp(a))
+        self.raise_on_error(msg)
+        return a
+
+    def get_energy(self):
+        return self._scalar(self._lib.xtb_getEnergy, "Energy is not available")
+
+    def get_gradient(self):
+        return self._array(self._lib.xtb_getGradient, (self._natoms, 3), "Gradient is not available")
+
+    def get_virial(self):
+        return self._array(self._lib.xtb_getVirial, (3, 3), "Virial is not available")
+
+    def get_dipole(self):
+        return self._array(self._lib.xtb_getDipole, (3,), "Dipole is not available")
+
+    def get_charges(self):
+        return self._array(self._lib.xtb_getCharges, (self._natoms,), "Charges are not available")
+
+    def get_bond_orders(self):
+        return self._array(self._lib.xtb_getBondOrders, (self._natoms, self._natoms), "Bond orders are not available")
+
+    def get_number_of_orbitals(self):
+        n = ctypes.c_int(0)
+        self._lib.xtb_getNao(self._env, self._res, ctypes.byref(n))
+        self.raise_on_error("Number of orbitals is not available")
+        return n.value
+
+    def get_orbital_eigenvalues(self):
+        return self._array(self._lib.xtb_getOrbitalEigenvalues, (self.get_number_of_orbitals(),), "Not available")
+
+    def get_orbital_occupations(self):
+        return self._array(self._lib.xtb_getOrbitalOccupations, (self.get_number_of_orbitals(),), "Not available")
+
+    def get_orbital_coefficients(self):
+        n = self.get_number_of_orbitals()
+        return self._array(self._lib.xtb_getOrbitalCoefficients, (n, n), "Not available")
+
+
+class Calculator(Molecule):
+    """Single point calculator (xtb_TCalculator) bound to one molecule.
+
+    >>> calc = Calculator(Param.GFN2xTB, numbers, positions)
+    >>> res = calc.singlepoint()
+    >>> res.get_energy(), res.get_gradient()
+    """
+
+    def __init__(self, param, numbers, positions, charge=None, uhf=None, lattice=None, periodic=None):
+        Molecule.__init__(self, numbers, positions, charge, uhf, lattice, periodic)
+        self._calc = ctypes.c_void_p(self._lib.xtb_newCalculator())
+        getattr(self._lib, param.value)(self._env, self._mol, self._calc, None)
+        self.raise_on_error("Could not load parametrisation data")
+
+    def __del__(self):
+        try:
+            self._lib.xtb_delCalculator(ctypes.byref(self._calc))
+        except Exception:
+            pass
+        Molecule.__del__(self)
+
+    def set_accuracy(self, accuracy):
+        self._lib.xtb_setAccuracy(self._env, self._calc, float(accuracy))
+        self.raise_on_error("Could not set accuracy")
+
+    def set_max_iterations(self, maxiter):
+        self._lib.xtb_setMaxIter(self._env, self._calc, int(maxiter))
+        self.raise_on_error("Could not set max iterations")
+
+    def set_electronic_temperature(self, etemp):
+        self._lib.xtb_setElectronicTemp(self._env, self._calc, float(etemp))
+        self.raise_on_error("Could not set electronic temperature")
+
+    def set_solvent(self, solvent=None):
+        if solvent is None:
+            self._lib.xtb_releaseSolvent(self._env, self._calc)
+        else:
+            self._lib.xtb_setSolvent(self._env, self._calc, str(solvent).encode(), None, None, None, None)
+        self.raise_on_error("Failed to set solvent model")
+
+    def set_external_charges(self, numbers, charges, positions):
+        n = ctypes.c_int(len(numbers))
+        nu = np.ascontiguousarray(numbers, dtype=np.int32)
+        ch = np.ascontiguousarray(charges, dtype=np.float64)
+        po = np.ascontiguousarray(positions, dtype=np.float64)
+        self._lib.xtb_setExternalCharges(self._env, self._calc, ctypes.byref(n), _ip(nu), _dp(ch), _dp(po))
+        self.raise_on_error("Failed to set external charges")
+
+    def singlepoint(self, res=None, copy=False):
+        _res = Results(self) if res is None else (Results(res) if copy else res)
+        self._lib.xtb_singlepoint(self._env, self._mol, self._calc, _res._res)
+        self.raise_on_error("Single point calculation failed")
+        return _res
+
+
+RESULT_FIELDS = ["energy", "e_elec", "e_rep", "e_es", "e_aes", "e_axc", "e_disp", "hl_gap", "gnorm", "e_atm",
+                 "dipole_x", "dipole_y", "dipole_z", "niter", "converged", "fail"]
+
+
+class BatchCalculator:
+    """GFN2-xTB single points + gradients for an ensemble of molecules in one call (include/xtb_b200.h)."""
+
+    def __init__(self, numbers_list, charges=None, uhf=None, device=0, accuracy=1.0, etemp=300.0, maxiter=250,
+                 guess="eeq"):
+        self._lib = load_library()
+        self.natoms = np.array([len(n) for n in numbers_list], dtype=np.int32)
+        self.nmol = len(numbers_list)
+        numbers = np.ascontiguousarray(np.concatenate([np.asarray(n, dtype=np.int32) for n in numbers_list]), dtype=np.int32)
+        ch = np.ascontiguousarray(charges, dtype=np.float64) if charges is not None else None
+        uh = np.ascontiguousarray(uhf, dtype=np.int32) if uhf is not None else None
+        self._b = ctypes.c_void_p(self._lib.xtbb200_newBatch(self.nmol, _ip(self.natoms), _ip(numbers),
+                                                            _dp(ch) if ch is not None else None,
+                                                            _ip(uh) if uh is not None else None, int(device)))
+        if not self._b:
+            raise XTBException(self._lib.xtbb200_lastError().decode())
+        self.total_atoms = int(self.natoms.sum())
+        self.offsets = np.concatenate([[0], np.cumsum(self.natoms)])
+        self.set_options(accuracy, etemp, maxiter, guess)
+
+    def __del__(self):
+        try:
+            self._lib.xtbb200_delBatch(ctypes.byref(self._b))
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise XTBException(self._lib.xtbb200_lastError().decode())
+        return rc
+
+    def set_options(self, accuracy=1.0, etemp=300.0, maxiter=250, guess="eeq"):
+        self._check(self._lib.xtbb200_setOptions(self._b, float(accuracy), float(etemp), int(maxiter),
+                                                 {"eeq": 0, "sad": 1}[guess]))
+
+    def singlepoint(self, positions, restart=False):
+        """positions: (total_atoms, 3) Bohr. Returns dict(energies, gradients, charges, niter, status)."""
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        if pos.size != 3 * self.total_atoms:
+            raise ValueError("Dimension missmatch for positions")
+        e = np.zeros(self.nmol)
+        g = np.zeros((self.total_atoms, 3))
+        q = np.zeros(self.total_atoms)
+        it = np.zeros(self.nmol, dtype=np.int32)
+        st = np.zeros(self.nmol, dtype=np.int32)
+        rc = self._check(self._lib.xtbb200_singlepoint(self._b, _dp(pos), int(bool(restart)), _dp(e), _dp(g), _dp(q),
+                                                       _ip(it), _ip(st)))
+        return dict(energies=e, gradients=g, charges=q, niter=it, status=st, all_converged=(rc == 0))
+
+    def singlepoint_device(self, positions_ptr, restart=False):
+        """positions_ptr: integer device address of (total_atoms,3) float64 on this batch's GPU."""
+        return self._check(self._lib.xtbb200_singlepointDevice(self._b, ctypes.c_void_p(int(positions_ptr)),
+                                                               int(bool(restart)), None))
+
+    def result(self, imol):
+        out = np.zeros(16)
+        self._check(self._lib.xtbb200_getResult(self._b, int(imol), _dp(out)))
+        return dict(zip(RESULT_FIELDS, out.tolist()))
+
+    def counts(self, imol):
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self._lib.xtbb200_getCounts(self._b, int(imol), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return dict(ndp=a.value, nqp=b.value, sweeps=c.value)
+
+    def sizes(self, imol):
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self._lib.xtbb200_getSizes(self._b, int(imol), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return dict(natoms=a.value, nshell=b.value, nao=c.value)
+
+    def offsets_of(self, imol):
+        o = (ctypes.c_longlong * 5)()
+        self._check(self._lib.xtbb200_getOffsets(self._b, int(imol), o))
+        return dict(atom=o[0], shell=o[1], ao=o[2], mat=o[3], nn=o[4])
+
+    def array(self, name):
+        n = ctypes.c_size_t(0)
+        self._check(self._lib.xtbb200_getArrayLen(self._b, name.encode(), ctypes.byref(n)))
+        out = np.zeros(n.value)
+        self._check(self._lib.xtbb200_getArray(self._b, name.encode(), _dp(out), n.value))
+        return out
+
+    def matrix(self, name, imol, planes=1):
+        """nao x nao matrix (column-major on the device == symmetric here) of one molecule."""
+        full = self.array(name)
+        off = self.offsets_of(imol)
+        nao = self.sizes(imol)["nao"]
+        tot = full.size // planes
+        out = [full[p * tot + off["mat"]: p * tot + off["mat"] + nao * nao].reshape(nao, nao).T for p in range(planes)]
+        return out[0] if planes == 1 else np.stack(out)
+
+    def mask(self):
+        n = ctypes.c_size_t(0)
+        self._check(self._lib.xtbb200_getArrayLen(self._b, b"S", ctypes.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint8)
+        self._check(self._lib.xtbb200_getMask(self._b, out.ctypes.data, n.value))
+        return out
+
+    def timings(self):
+        t = (ctypes.c_float * 3)()
+        n = ctypes.c_int()
+        self._check(self._lib.xtbb200_getTimings(self._b, t, ctypes.byref(n)))
+        return dict(setup_ms=t[0], scc_ms=t[1], grad_ms=t[2], launches=n.value)
+
+    def device_bytes(self):
+        return int(self._lib.xtbb200_getDeviceBytes(self._b))
