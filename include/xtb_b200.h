@@ -69,6 +69,19 @@ int xtbb200_getMask(xtbb200_TBatch batch, unsigned char* out, size_t len);
 /* device timings [ms] of the last call (setup+integrals, SCC, gradient+properties) and kernel launches */
 int xtbb200_getTimings(xtbb200_TBatch batch, float* ms3, int* launches);
 
+/* device time [ms] of the last xtbb200_singlepoint call from the first host->device copy to the last device->host
+ * copy (CUDA events on the engine's stream) */
+int xtbb200_getCallTime(xtbb200_TBatch batch, float* ms);
+
+/* Per-kernel-class device timers.  Every launch whose class bit is set in class_mask is bracketed by CUDA events
+ * on the engine's own stream; times accumulate over xtbb200_singlepoint* calls until the next xtbb200_setProfile.
+ * ms / timed_launches / launches: arrays of xtbb200_kernelClassCount() entries (may be NULL);
+ * scc_passes: batch-wide SCC passes of the last call. */
+int xtbb200_setProfile(xtbb200_TBatch batch, unsigned long long class_mask);
+int xtbb200_kernelClassCount(void);
+const char* xtbb200_kernelClassName(int id);
+int xtbb200_getKernelTimes(xtbb200_TBatch batch, float* ms, int* timed_launches, int* launches, int* scc_passes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,269 @@
+"""Parity of the CUDA engine (through the C ABI) against the CPU oracle and the reference's golden values.
+
+Tolerances are the ones BASELINE.json's north_star states: energy 1e-7 Eh, gradient 1e-6 Eh/bohr,
+charges 1e-6 e; screening lists and SCC iteration counts identical (bit-exact integer compare).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+E_TOL, G_TOL, Q_TOL = 1e-7, 1e-6, 1e-6
+
+
+@pytest.fixture(scope="module")
+def xb():
+    import xtb_b200
+    if xtb_b200.device_count() < 1:
+        pytest.fail("no CUDA device: the engine has no CPU fallback")
+    return xtb_b200
+
+
+def _oracle(s, **kw):
+    from oracle.oracle import Oracle
+    o = Oracle(s["numbers"], s["xyz"], charge=s["charge"], uhf=s["uhf"], guess=s.get("guess", "eeq"),
+               maxiter=s.get("maxiter", 250), **kw)
+    assert o.singlepoint() == 0
+    return o
+
+
+def _lists_from_mask(mask, nao, bit):
+    """(i, j<=i) pairs in the reference's order (i outer, j inner), src/aespot.F90:34-85."""
+    m = mask.reshape(nao, nao)  # m[j, i]
+    out = []
+    for i in range(nao):
+        js = np.nonzero(m[: i + 1, i] & bit)[0]
+        for j in js:
+            out.extend((i, int(j)))
+    return np.array(out, dtype=np.int32)
+
+
+def _compare(xb, s, o, b, r, imol=0):
+    res = b.result(imol)
+    e = o.energies
+    info = o.info
+    a0, a1 = b.offsets[imol], b.offsets[imol + 1]
+    assert abs(res["energy"] - e["e_total"]) < E_TOL
+    g = o.get("gradient").reshape(-1, 3)
+    assert np.max(np.abs(r["gradients"][a0:a1] - g)) < G_TOL
+    assert np.max(np.abs(r["charges"][a0:a1] - o.get("q"))) < Q_TOL
+    assert int(res["niter"]) == info["niter"], "SCC iteration count differs"
+    cnt = b.counts(imol)
+    assert (cnt["ndp"], cnt["nqp"]) == (info["ndp"], info["nqp"])
+    for key, okey in [("e_rep", "e_rep"), ("e_es", "e_es"), ("e_aes", "e_aes"), ("e_axc", "e_axc"), ("e_disp", "e_disp"),
+                      ("e_atm", "e_atm")]:
+        assert abs(res[key] - e[okey]) < E_TOL, key
+    assert abs(res["hl_gap"] - e["hl_gap"]) < 1e-6
+    assert abs(res["gnorm"] - e["gnorm"]) < G_TOL
+    return res
+
+
+ALL_KAT = ["mindless%02d" % i for i in range(1, 11)] + ["feco5", "co_cnx6", "fe_cnx6", "h2o_scc", "c3h4_api"]
+ORACLE_ONLY = ["caffeine", "rivaroxaban", "pdb_4qxx", "remdesivir", "taxol"]
+
+
+@pytest.mark.parametrize("name", ALL_KAT + ORACLE_ONLY)
+def test_singlepoint_matches_oracle_and_golden(xb, kat, name):
+    s = kat[name]
+    o = _oracle(s)
+    b = xb.BatchCalculator([s["numbers"]], charges=[s["charge"]], uhf=[s["uhf"]], guess=s.get("guess", "eeq"),
+                           maxiter=s.get("maxiter", 250))
+    r = b.singlepoint(s["xyz"])
+    assert r["all_converged"]
+    res = _compare(xb, s, o, b, r)
+    k = s.get("kat") or {}
+    if "energy" in k:  # the reference's own number (test/unit/test_gfn2.f90)
+        tol = max(k.get("tol", 1e-7), 1e-9)
+        assert abs(res["energy"] - k["energy"]) < tol
+        assert abs(res["gnorm"] - k["gnorm"]) < tol
+        assert abs(res["hl_gap"] - k["hl_gap"]) < max(tol, 1e-4 if name == "h2o_scc" else tol)
+    if "wbo" in k:
+        n = len(s["numbers"])
+        w = b.array("wbo").reshape(n, n)
+        for key, val in k["wbo"].items():
+            i, j = map(int, key.split(","))
+            assert abs(w[i, j] - val) < k["tol"]
+
+
+@pytest.mark.parametrize("name", ["caffeine", "rivaroxaban", "feco5"])
+def test_integrals_and_screening_lists_identical(xb, kat, name):
+    s = kat[name]
+    o = _oracle(s)
+    b = xb.BatchCalculator([s["numbers"]], charges=[s["charge"]], uhf=[s["uhf"]])
+    b.singlepoint(s["xyz"])
+    nao = o.info["nao"]
+    S = o.get("S").reshape(nao, nao)
+    assert np.max(np.abs(S - b.matrix("S", 0))) < 1e-12
+    Dp = o.get("dpint").reshape(nao, nao, 3).transpose(2, 0, 1)
+    Qp = o.get("qpint").reshape(nao, nao, 6).transpose(2, 0, 1)
+    assert np.max(np.abs(Dp - b.matrix("dpint", 0, 3).transpose(0, 2, 1))) < 1e-11
+    assert np.max(np.abs(Qp - b.matrix("qpint", 0, 6).transpose(0, 2, 1))) < 1e-10
+    mask = b.mask()
+    assert np.array_equal(_lists_from_mask(mask, nao, 1), o.get("mdlst"))
+    assert np.array_equal(_lists_from_mask(mask, nao, 2), o.get("mqlst"))
+    for nm in ("cn", "gab3", "gab5", "jmat", "dispmat", "gw"):
+        ref = o.get(nm)
+        assert np.max(np.abs(ref - b.array(nm))) < 1e-11 * max(1.0, np.max(np.abs(ref))), nm
+    P = o.get("P").reshape(nao, nao)
+    assert np.max(np.abs(P - b.matrix("P", 0))) < 1e-6
+    assert np.max(np.abs(o.get("emo") - b.array("emo"))) < 1e-6
+    assert np.max(np.abs(o.get("qsh") - b.array("qsh"))) < Q_TOL
+    assert np.max(np.abs(o.get("dipm") - b.array("dipm"))) < Q_TOL
+    assert np.max(np.abs(o.get("qp") - b.array("qp"))) < Q_TOL
+    assert np.max(np.abs(o.get("wbo") - b.array("wbo"))) < 1e-6
+
+
+def test_c_api_example_flow(xb, kat):
+    """test/api/c_api_example.c:40-112 replayed through the same entry points."""
+    s = kat["c3h4_api"]
+    k = s["kat"]
+    L = xb.load_library()
+    vp = ctypes.c_void_p
+    env, calc, res = vp(L.xtb_newEnvironment()), vp(L.xtb_newCalculator()), vp(L.xtb_newResults())
+    natoms = ctypes.c_int(7)
+    at = np.ascontiguousarray(s["numbers"], dtype=np.int32)
+    xyz = np.ascontiguousarray(s["xyz"], dtype=np.float64)
+    dp = ctypes.POINTER(ctypes.c_double)
+    mol = vp(L.xtb_newMolecule(env, ctypes.byref(natoms), at.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                               xyz.ctypes.data_as(dp), None, None, None, None))
+    assert L.xtb_checkEnvironment(env) == 0
+    energy = ctypes.c_double(0)
+    L.xtb_getEnergy(env, res, ctypes.byref(energy))      # error: no results yet (c_api_example.c:77-81)
+    assert L.xtb_checkEnvironment(env) == 1
+    L.xtb_showEnvironment(env, None)
+    assert L.xtb_checkEnvironment(env) == 0
+    L.xtb_setVerbosity(env, 0)
+    L.xtb_loadGFN2xTB(env, mol, calc, None)
+    L.xtb_setAccuracy(env, calc, 1.0)
+    L.xtb_setElectronicTemp(env, calc, 300.0)
+    L.xtb_setMaxIter(env, calc, 30)
+    assert L.xtb_checkEnvironment(env) == 0
+    L.xtb_singlepoint(env, mol, calc, res)
+    assert L.xtb_checkEnvironment(env) == 0
+    q = np.zeros(7); dip = np.zeros(3); wbo = np.zeros(49); g = np.zeros(21)
+    L.xtb_getEnergy(env, res, ctypes.byref(energy))
+    L.xtb_getCharges(env, res, q.ctypes.data_as(dp))
+    L.xtb_getDipole(env, res, dip.ctypes.data_as(dp))
+    L.xtb_getBondOrders(env, res, wbo.ctypes.data_as(dp))
+    L.xtb_getGradient(env, res, g.ctypes.data_as(dp))
+    assert L.xtb_checkEnvironment(env) == 0
+    assert abs(energy.value - k["energy"]) < 1e-9
+    assert abs(q[5] - k["q5"]) < 1e-8
+    assert abs(dip[2] - k["dipole2"]) < 1e-6
+    assert abs(wbo[9] - k["wbo9"]) < 1e-8
+    g = g.reshape(7, 3)
+    assert abs(g[2, 1] - k["g_2_1"]) < 1e-9 and abs(g[0, 2] - k["g_0_2"]) < 1e-9
+    assert abs(np.sqrt((g ** 2).sum()) - k["gnorm"]) < 1e-9
+    nao = ctypes.c_int(0)
+    L.xtb_getNao(env, res, ctypes.byref(nao))
+    assert nao.value == 19
+    # second call restarts from the cached wavefunction (src/api/interface.f90:82-101)
+    L.xtb_singlepoint(env, mol, calc, res)
+    e2 = ctypes.c_double(0)
+    L.xtb_getEnergy(env, res, ctypes.byref(e2))
+    assert abs(e2.value - energy.value) < 1e-8
+    # unsupported methods raise on the environment instead of missing symbols
+    L.xtb_loadGFN1xTB(env, mol, calc, None)
+    assert L.xtb_checkEnvironment(env) == 1
+    L.xtb_showEnvironment(env, None)
+    for h, f in ((res, L.xtb_delResults), (calc, L.xtb_delCalculator), (mol, L.xtb_delMolecule), (env, L.xtb_delEnvironment)):
+        f(ctypes.byref(h))
+        assert not h.value
+
+
+def test_calculator_interface_restart_and_update(xb, kat):
+    s = kat["caffeine"]
+    o = _oracle(s)
+    calc = xb.Calculator(xb.Param.GFN2xTB, s["numbers"], s["xyz"])
+    calc.set_verbosity(0)
+    res = calc.singlepoint()
+    assert abs(res.get_energy() - o.energies["e_total"]) < E_TOL
+    assert np.max(np.abs(res.get_gradient() - o.get("gradient").reshape(-1, 3))) < G_TOL
+    assert np.max(np.abs(res.get_charges() - o.get("q"))) < Q_TOL
+    assert np.max(np.abs(res.get_bond_orders() - o.get("wbo").reshape(24, 24))) < 1e-6
+    assert np.max(np.abs(res.get_orbital_eigenvalues() - o.get("emo") / 27.21138505)) < 1e-7
+    assert np.all(res.get_virial() == 0.0)   # scf has no sigma argument
+    # displaced geometry, restart from the cached wavefunction: same answer as a fresh oracle run
+    x2 = s["xyz"].copy()
+    x2[3, 0] += 0.05
+    calc.update(x2)
+    res = calc.singlepoint(res)
+    from oracle.oracle import Oracle
+    o2 = Oracle(s["numbers"], x2)
+    assert o2.singlepoint() == 0
+    assert abs(res.get_energy() - o2.energies["e_total"]) < 5e-7   # different start vector, same fixed point
+    assert np.max(np.abs(res.get_gradient() - o2.get("gradient").reshape(-1, 3))) < 5e-6
+
+
+def test_error_behaviour(xb):
+    with pytest.raises(xb.XTBException):
+        xb.Molecule([1, 1], [[0, 0, 0], [0, 0, 0]])      # coinciding atoms, src/api/molecule.f90:66-86
+    with pytest.raises(xb.XTBException):
+        xb.Molecule([0, 1], [[0, 0, 0], [0, 0, 1.4]])    # invalid atomic number
+    calc = xb.Calculator(xb.Param.GFN2xTB, [1, 1], [[0, 0, 0], [0, 0, 1.4]])
+    calc.set_verbosity(0)
+    with pytest.raises(xb.XTBException):
+        calc.set_solvent("water")                         # not on this path: raises, never silently ignored
+    calc.set_max_iterations(1)
+    with pytest.raises(xb.XTBException):
+        calc.singlepoint()                                # not converged is an error (src/scf_module.F90:806-808)
+
+
+def test_ragged_batch_matches_per_molecule_oracle(xb, kat):
+    names = ["h2o_scc", "caffeine", "mindless03", "feco5", "rivaroxaban", "c3h4_api", "mindless02"]
+    sys_ = [kat[n] for n in names]
+    b = xb.BatchCalculator([s["numbers"] for s in sys_], charges=[s["charge"] for s in sys_], uhf=[s["uhf"] for s in sys_])
+    pos = np.concatenate([s["xyz"] for s in sys_])
+    r = b.singlepoint(pos)
+    assert r["all_converged"]
+    for i, s in enumerate(sys_):
+        s2 = dict(s); s2.pop("guess", None); s2.pop("maxiter", None)
+        o = _oracle(s2)
+        _compare(xb, s2, o, b, r, i)
+
+
+def test_ensemble_properties_full_size(xb, kat):
+    """BASELINE config 3 at full size (4096 conformers of a 47-atom drug): spot parity against the oracle plus
+    size-independent properties: zero net force, zero net torque, charge conservation, determinism."""
+    from bench import make_ensemble
+    s = kat["rivaroxaban"]
+    nmol = 4096
+    Z, pos = make_ensemble(s, nmol)
+    b = xb.BatchCalculator([Z] * nmol)
+    r = b.singlepoint(pos)
+    assert r["all_converged"]
+    g = r["gradients"].reshape(nmol, -1, 3)
+    x = pos.reshape(nmol, -1, 3)
+    assert np.max(np.abs(g.sum(axis=1))) < 1e-9                       # translational invariance
+    assert np.max(np.abs(np.cross(x, g).sum(axis=1))) < 1e-8          # rotational invariance
+    assert np.max(np.abs(r["charges"].reshape(nmol, -1).sum(axis=1))) < 1e-9
+    from oracle.oracle import Oracle
+    for i in (0, 1, 2047, 4095):
+        o = Oracle(Z, x[i])
+        assert o.singlepoint() == 0
+        assert abs(r["energies"][i] - o.energies["e_total"]) < E_TOL
+        assert np.max(np.abs(g[i] - o.get("gradient").reshape(-1, 3))) < G_TOL
+        assert r["niter"][i] == o.info["niter"]
+    # determinism: a second call on the same inputs is bit-identical
+    r2 = b.singlepoint(pos)
+    assert np.array_equal(r["energies"], r2["energies"]) and np.array_equal(r["gradients"], r2["gradients"])
+
+
+def test_gradient_matches_finite_difference(xb, kat):
+    s = kat["c3h4_api"]
+    Z = s["numbers"]
+    cases = [(0, 2), (3, 0), (6, 2)]
+    h = 1e-4
+    geoms = [s["xyz"]]
+    for (i, k) in cases:
+        for sgn in (+1, -1):
+            x = s["xyz"].copy(); x[i, k] += sgn * h
+            geoms.append(x)
+    b = xb.BatchCalculator([Z] * len(geoms), accuracy=0.01)
+    r = b.singlepoint(np.concatenate(geoms))
+    g = r["gradients"][:7]
+    for n, (i, k) in enumerate(cases):
+        fd = (r["energies"][1 + 2 * n] - r["energies"][2 + 2 * n]) / (2 * h)
+        assert abs(fd - g[i, k]) < 2e-7

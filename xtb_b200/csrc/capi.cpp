@@ -440,6 +440,7 @@ int xtbb200_singlepoint(xtbb200_TBatch batch, const double* positions, int resta
     if (!batch) throw std::runtime_error("batch is not allocated");
     if (!positions) throw std::runtime_error("positions are required");
     Batch& b = *batch->b;
+    b.mark_call(0);
     b.set_positions(positions);
     int nfail = b.singlepoint(restart != 0);
     for (int i = 0; i < b.nmol(); ++i) {
@@ -450,6 +451,7 @@ int xtbb200_singlepoint(xtbb200_TBatch batch, const double* positions, int resta
     }
     if (gradients) b.fetch("gradient", gradients);
     if (charges) b.fetch("q", charges);
+    b.mark_call(1);
     return nfail ? 1 : 0;
     XTBB_CATCH(-1)
 }
@@ -529,6 +531,30 @@ int xtbb200_getTimings(xtbb200_TBatch batch, float* ms3, int* launches) {
     if (!batch) throw std::runtime_error("batch is not allocated");
     if (ms3) batch->b->timings(ms3);
     if (launches) *launches = batch->b->launches();
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_getCallTime(xtbb200_TBatch batch, float* ms) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    *ms = batch->b->call_ms();
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_setProfile(xtbb200_TBatch batch, unsigned long long class_mask) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    batch->b->set_profile(class_mask);
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_kernelClassCount(void) { return Batch::kernel_classes(); }
+const char* xtbb200_kernelClassName(int id) { return Batch::kernel_class_name(id); }
+int xtbb200_getKernelTimes(xtbb200_TBatch batch, float* ms, int* timed_launches, int* launches, int* scc_passes) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    batch->b->kernel_times(ms, timed_launches, launches);
+    if (scc_passes) *scc_passes = batch->b->scc_passes();
     return 0;
     XTBB_CATCH(-1)
 }

@@ -34,7 +34,51 @@ __global__ void k_count_active(Dev d, int* out) {
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, __popc(b));
 }
 
+// kernel classes for the per-kernel device timers (bench.py roofline, profiles/)
+enum KernelId { K_SETUP = 0, K_EEQ, K_SDQH0, K_DQMASK, K_CHOL, K_POT, K_D4SCC, K_FOCK, K_GEMM_XHX, K_JACOBI, K_GEMM_C,
+                K_FERMI, K_DENSITY, K_POP, K_ENERGY, K_SCCFIN, K_GRAD_H0, K_GRAD_AES, K_GRAD_D4, K_GRAD_ATM, K_GRAD_MISC,
+                K_WBO, K_FINISH, K_COUNT };
+static const char* const kKernelNames[K_COUNT] = {
+    "setup(cn,gab,jmat,dispmat,rep)", "eeq_guess", "k_sdqh0", "k_dqmask", "k_chol_inv", "potentials(shell,aes)",
+    "d4_scc(zeta,matvec,shift)", "k_fock", "k_gemm(X^T H X)", "k_jacobi", "k_gemm(C=XZ)", "k_fermi",
+    "density(scale+k_gemm)", "populations(k_pop_rows,k_pop_atoms)", "energies(es,aes)", "k_scc_finish(broyden)",
+    "k_grad_h0(+W build,collect)", "k_grad_aes", "grad_d4(weights,c6,pairs)", "k_grad_atm", "k_grad_cn", "wbo(PS gemm,k_wbo)",
+    "k_finish"};
+
 struct Batch::Impl {
+    // per-kernel-class timers: events bracket every launch whose class bit is set in prof_mask
+    unsigned long long prof_mask = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_ids;       // class of each recorded (begin,end) pair
+    size_t ev_used = 0;
+    float k_ms[K_COUNT] = {0};
+    int k_calls[K_COUNT] = {0};
+    int k_launches[K_COUNT] = {0};
+    void prof_begin(int id, cudaStream_t st) {
+        if (!((prof_mask >> id) & 1ull)) return;
+        if (ev_used + 2 > ev_pool.size()) {
+            size_t old = ev_pool.size();
+            ev_pool.resize(old + 256);
+            for (size_t i = old; i < ev_pool.size(); ++i) cudaEventCreate(&ev_pool[i]);
+        }
+        cudaEventRecord(ev_pool[ev_used], st);
+    }
+    void prof_end(int id, cudaStream_t st) {
+        if (!((prof_mask >> id) & 1ull)) return;
+        cudaEventRecord(ev_pool[ev_used + 1], st);
+        ev_ids.push_back(id);
+        ev_used += 2;
+    }
+    void prof_collect() {   // call after the stream is synchronised
+        for (size_t i = 0; i < ev_ids.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev_pool[2 * i], ev_pool[2 * i + 1]);
+            k_ms[ev_ids[i]] += ms;
+            k_calls[ev_ids[i]]++;
+        }
+        ev_ids.clear();
+        ev_used = 0;
+    }
     BatchSystem sys;
     Dev d;
     std::vector<void*> allocs;
@@ -53,6 +97,10 @@ struct Batch::Impl {
     // timing (ms) of the last single point
     float t_setup = 0, t_scc = 0, t_grad = 0;
     int launches = 0;
+    int scc_passes = 0;
+    cudaEvent_t ev_phase[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_call[2] = {nullptr, nullptr};
+    float t_call = 0;
 
     template <class T>
     T* dalloc(size_t n) {
@@ -72,6 +120,9 @@ struct Batch::Impl {
     }
     ~Impl() {
         for (void* p : allocs) cudaFree(p);
+        for (auto& e : ev_pool) cudaEventDestroy(e);
+        for (auto& e : ev_phase) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_call) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -234,6 +285,16 @@ static void launch_jacobi(Dev& d, int nmol, int max_nao, bool sm, cudaStream_t s
     }
 }
 
+// KL(class, launch): one kernel launch, counted, and bracketed by events when its class is being profiled
+#define KL(id, ...)                 \
+    do {                            \
+        I.prof_begin(id, st);       \
+        __VA_ARGS__;                \
+        I.prof_end(id, st);         \
+        I.k_launches[id]++;         \
+        nl++;                       \
+    } while (0)
+
 int Batch::singlepoint(bool restart) {
     Impl& I = *p_;
     Dev& d = I.d;
@@ -250,108 +311,106 @@ int Batch::singlepoint(bool restart) {
     d.etemp = I.etemp;
     d.broydamp = 0.4;   // src/setparam.f90:226
     d.maxiter = I.maxiter;
-    cudaEvent_t ev[4];
-    for (auto& e : ev) cudaEventCreate(&e);
+    if (!I.ev_phase[0]) for (auto& e : I.ev_phase) cudaEventCreate(&e);
+    cudaEvent_t* ev = I.ev_phase;
     int nl = 0;
     const int B = 128;
     cudaEventRecord(ev[0], st);
-    k_reset_state<<<(nmol + 127) / 128, 128, 0, st>>>(d, 0); nl++;
+    KL(K_SETUP, k_reset_state<<<(nmol + 127) / 128, 128, 0, st>>>(d, 0));
     // ---- geometry dependent setup
-    k_cn<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d); nl++;
+    KL(K_SETUP, k_cn<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
     const int mx = std::max(s.max_nat, std::max(s.max_nsh, s.max_ndim));
-    k_cn_dependent<<<grid2(mx, B, nmol), B, 0, st>>>(d); nl++;
-    k_gab<<<grid2((long long)s.max_nat * s.max_nat, 256, nmol), 256, 0, st>>>(d); nl++;
-    k_jmat<<<grid2((long long)s.max_nsh * s.max_nsh, 256, nmol), 256, 0, st>>>(d); nl++;
-    k_dispmat<<<grid2((long long)s.max_ndim * s.max_ndim, 256, nmol), 256, 0, st>>>(d); nl++;
-    k_repulsion<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d); nl++;
+    KL(K_SETUP, k_cn_dependent<<<grid2(mx, B, nmol), B, 0, st>>>(d));
+    KL(K_SETUP, k_gab<<<grid2((long long)s.max_nat * s.max_nat, 256, nmol), 256, 0, st>>>(d));
+    KL(K_SETUP, k_jmat<<<grid2((long long)s.max_nsh * s.max_nsh, 256, nmol), 256, 0, st>>>(d));
+    KL(K_SETUP, k_dispmat<<<grid2((long long)s.max_ndim * s.max_ndim, 256, nmol), 256, 0, st>>>(d));
+    KL(K_SETUP, k_repulsion<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
     // ---- guess (src/api/interface.f90:82-101: reuse the cached wavefunction when present)
     if (!(restart && I.have_wfn)) {
         if (I.guess == 0) {
-            k_eeq_build<<<grid2((long long)(s.max_nat + 1) * (s.max_nat + 2), 256, nmol), 256, 0, st>>>(d); nl++;
-            k_eeq_solve<<<nmol, 256, 0, st>>>(d); nl++;
+            KL(K_EEQ, k_eeq_build<<<grid2((long long)(s.max_nat + 1) * (s.max_nat + 2), 256, nmol), 256, 0, st>>>(d));
+            KL(K_EEQ, k_eeq_solve<<<nmol, 256, 0, st>>>(d));
         } else {
-            k_guess_uniform<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d); nl++;
+            KL(K_EEQ, k_guess_uniform<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
         }
     }
-    k_qsh2qat<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d); nl++;
+    KL(K_EEQ, k_qsh2qat<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
     // ---- integrals
     const long long max_pairs = (long long)s.max_nsh * (s.max_nsh + 1) / 2;
-    k_sdqh0<<<grid2(max_pairs, kIntWarps, nmol), kIntWarps * 32, 0, st>>>(d); nl++;
+    KL(K_SDQH0, k_sdqh0<<<grid2(max_pairs, kIntWarps, nmol), kIntWarps * 32, 0, st>>>(d));
     const long long nn2 = (long long)s.max_nao * s.max_nao;
-    k_dqmask<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d); nl++;
+    KL(K_DQMASK, k_dqmask<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
     // ---- overlap factorisation
     const size_t chol_bytes = (size_t)s.max_nao * (s.max_nao | 1) * sizeof(double);
     const bool sm = chol_bytes <= (size_t)(227 * 1024 - 4096);
-    if (sm) k_chol_inv<true><<<nmol, 512, chol_bytes, st>>>(d);
-    else k_chol_inv<false><<<nmol, 512, 0, st>>>(d);
-    nl++;
+    if (sm) KL(K_CHOL, k_chol_inv<true><<<nmol, 512, chol_bytes, st>>>(d));
+    else KL(K_CHOL, k_chol_inv<false><<<nmol, 512, 0, st>>>(d));
     cudaEventRecord(ev[1], st);
     // ---- SCC iterations
     const int tiles = (s.max_nao + GT - 1) / GT;
     const dim3 ggrid(tiles * tiles, nmol);
     const int npairs = (s.max_nao + 1) / 2;
     int active = nmol;
+    int iters = 0;
     for (int it = 0; it < I.maxiter && active > 0; ++it) {
-        k_pot_shell<<<grid2(s.max_nsh, B, nmol), B, 0, st>>>(d);
-        k_pot_aes<true><<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
-        k_d4_zeta<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d, 0);
-        k_d4_matvec<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d);
-        k_d4_shift<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d);
-        k_fock<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d);
-        k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.H, d.X, d.T, 0, 1);      // T = H X
-        k_gemm<true, false><<<ggrid, 128, 0, st>>>(d, d.X, d.T, d.W, 0, 1);       // W = X^T T
-        if (npairs * 32 <= 1024) launch_jacobi<32>(d, nmol, s.max_nao, sm, st);
-        else if (npairs * 16 <= 1024) launch_jacobi<16>(d, nmol, s.max_nao, sm, st);
-        else if (npairs * 8 <= 1024) launch_jacobi<8>(d, nmol, s.max_nao, sm, st);
-        else launch_jacobi<4>(d, nmol, s.max_nao, sm, st);
-        k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.Zm, d.C, 0, 1);     // C = X Z
-        k_fermi<<<nmol, 32, 0, st>>>(d);
-        k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 0);                // T = C f
-        k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.P, 1, 1);       // P = T C^T
-        k_pop_rows<<<grid2((long long)s.max_nao * 32, 256, nmol), 256, 0, st>>>(d);
-        k_pop_atoms<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
-        k_es_rows<<<grid2(s.max_nsh, B, nmol), B, 0, st>>>(d);
-        k_aes_rows<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
-        k_d4_zeta<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d, 1);
-        k_d4_matvec<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d);
-        k_scc_finish<<<nmol, 256, 0, st>>>(d);
-        nl += 20;
+        KL(K_POT, k_pot_shell<<<grid2(s.max_nsh, B, nmol), B, 0, st>>>(d));
+        KL(K_POT, k_pot_aes<true><<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+        KL(K_D4SCC, k_d4_zeta<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d, 0));
+        KL(K_D4SCC, k_d4_matvec<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d));
+        KL(K_D4SCC, k_d4_shift<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
+        KL(K_FOCK, k_fock<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
+        KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.H, d.X, d.T, 0, 1));      // T = H X
+        KL(K_GEMM_XHX, k_gemm<true, false><<<ggrid, 128, 0, st>>>(d, d.X, d.T, d.W, 0, 1));       // W = X^T T
+        if (npairs * 32 <= 1024) KL(K_JACOBI, launch_jacobi<32>(d, nmol, s.max_nao, sm, st));
+        else if (npairs * 16 <= 1024) KL(K_JACOBI, launch_jacobi<16>(d, nmol, s.max_nao, sm, st));
+        else if (npairs * 8 <= 1024) KL(K_JACOBI, launch_jacobi<8>(d, nmol, s.max_nao, sm, st));
+        else KL(K_JACOBI, launch_jacobi<4>(d, nmol, s.max_nao, sm, st));
+        KL(K_GEMM_C, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.Zm, d.C, 0, 1));       // C = X Z
+        KL(K_FERMI, k_fermi<<<nmol, 32, 0, st>>>(d));
+        KL(K_DENSITY, k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 0));                // T = C f
+        KL(K_DENSITY, k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.P, 1, 1));       // P = T C^T
+        KL(K_POP, k_pop_rows<<<grid2((long long)s.max_nao * 32, 256, nmol), 256, 0, st>>>(d));
+        KL(K_POP, k_pop_atoms<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+        KL(K_ENERGY, k_es_rows<<<grid2(s.max_nsh, B, nmol), B, 0, st>>>(d));
+        KL(K_ENERGY, k_aes_rows<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+        KL(K_D4SCC, k_d4_zeta<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d, 1));
+        KL(K_D4SCC, k_d4_matvec<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d));
+        KL(K_SCCFIN, k_scc_finish<<<nmol, 256, 0, st>>>(d));
         XTB_CUDA_CHECK(cudaMemsetAsync(I.d_active, 0, sizeof(int), st));
-        k_count_active<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.d_active); nl++;
+        KL(K_SCCFIN, k_count_active<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.d_active));
         XTB_CUDA_CHECK(cudaMemcpyAsync(&active, I.d_active, sizeof(int), cudaMemcpyDeviceToHost, st));
         XTB_CUDA_CHECK(cudaStreamSynchronize(st));
+        iters++;
     }
     cudaEventRecord(ev[2], st);
     // ---- gradient
-    k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 1);                     // T = C (f e)
-    k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.H, 1, 0);            // H <- energy weighted density
-    k_pot_aes<false><<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
-    k_grad_h0<<<grid2(max_pairs, kIntWarps, nmol), kIntWarps * 32, 0, st>>>(d);
-    k_grad_h0_collect<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
-    k_grad_aes<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
-    k_d4_weights<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
-    k_d4_c6<<<grid2((long long)s.max_nat * s.max_nat, 128, nmol), 128, 0, st>>>(d);
-    k_grad_pairs<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
-    k_grad_atm<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
-    k_grad_cn<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d);
-    nl += 11;
+    KL(K_GRAD_H0, k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 1));                     // T = C (f e)
+    KL(K_GRAD_H0, k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.H, 1, 0));            // H <- energy weighted density
+    KL(K_GRAD_AES, k_pot_aes<false><<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+    KL(K_GRAD_H0, k_grad_h0<<<grid2(max_pairs, kIntWarps, nmol), kIntWarps * 32, 0, st>>>(d));
+    KL(K_GRAD_H0, k_grad_h0_collect<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+    KL(K_GRAD_AES, k_grad_aes<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+    KL(K_GRAD_D4, k_d4_weights<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+    KL(K_GRAD_D4, k_d4_c6<<<grid2((long long)s.max_nat * s.max_nat, 128, nmol), 128, 0, st>>>(d));
+    KL(K_GRAD_D4, k_grad_pairs<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+    KL(K_GRAD_ATM, k_grad_atm<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+    KL(K_GRAD_MISC, k_grad_cn<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
     // ---- properties: bond orders and dipole
     bool any_open = false;
     for (auto& m : s.mol) any_open |= (m.nopen != 0);
     if (!any_open) {
-        k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.P, d.S, d.W, 0, 0); nl++;
+        KL(K_WBO, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.P, d.S, d.W, 0, 0));
     } else {
         // alpha / beta densities (scf_module.F90:869-879); closed-shell members of a mixed batch take this path too
-        k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 2);
-        k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.X, 0, 0);
-        k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.S, d.W, 0, 0);
-        k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 3);
-        k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.X, 0, 0);
-        k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.S, d.Zm, 0, 0);
-        nl += 6;
+        KL(K_WBO, k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 2));
+        KL(K_WBO, k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.X, 0, 0));
+        KL(K_WBO, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.S, d.W, 0, 0));
+        KL(K_WBO, k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 3));
+        KL(K_WBO, k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.X, 0, 0));
+        KL(K_WBO, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.S, d.Zm, 0, 0));
     }
-    k_wbo<<<grid2((long long)s.max_nat * s.max_nat, 128, nmol), 128, 0, st>>>(d, any_open ? 1 : 0); nl++;
-    k_finish<<<nmol, 256, 0, st>>>(d); nl++;
+    KL(K_WBO, k_wbo<<<grid2((long long)s.max_nat * s.max_nat, 128, nmol), 128, 0, st>>>(d, any_open ? 1 : 0));
+    KL(K_FINISH, k_finish<<<nmol, 256, 0, st>>>(d));
     cudaEventRecord(ev[3], st);
     XTB_CUDA_CHECK(cudaMemcpyAsync(I.h_state.data(), d.st, nmol * sizeof(MolState), cudaMemcpyDeviceToHost, st));
     XTB_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -359,14 +418,42 @@ int Batch::singlepoint(bool restart) {
     cudaEventElapsedTime(&I.t_setup, ev[0], ev[1]);
     cudaEventElapsedTime(&I.t_scc, ev[1], ev[2]);
     cudaEventElapsedTime(&I.t_grad, ev[2], ev[3]);
-    for (auto& e : ev) cudaEventDestroy(e);
+    I.prof_collect();
     I.launches = nl;
+    I.scc_passes = iters;
     I.have_wfn = true;
     int nfail = 0;
     for (int i = 0; i < nmol; ++i)
         if (I.h_state[i].fail || !I.h_state[i].converged) nfail++;
     return nfail;
 }
+
+void Batch::set_profile(unsigned long long mask) {
+    Impl& I = *p_;
+    I.prof_mask = mask;
+    for (int k = 0; k < K_COUNT; ++k) { I.k_ms[k] = 0; I.k_calls[k] = 0; I.k_launches[k] = 0; }
+}
+int Batch::kernel_classes() { return K_COUNT; }
+const char* Batch::kernel_class_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : ""; }
+void Batch::kernel_times(float* ms, int* calls, int* launches) const {
+    for (int k = 0; k < K_COUNT; ++k) {
+        if (ms) ms[k] = p_->k_ms[k];
+        if (calls) calls[k] = p_->k_calls[k];
+        if (launches) launches[k] = p_->k_launches[k];
+    }
+}
+void Batch::mark_call(int end) {
+    Impl& I = *p_;
+    XTB_CUDA_CHECK(cudaSetDevice(I.device));
+    if (!I.ev_call[0]) for (auto& e : I.ev_call) cudaEventCreate(&e);
+    cudaEventRecord(I.ev_call[end ? 1 : 0], I.stream);
+    if (end) {
+        cudaEventSynchronize(I.ev_call[1]);
+        cudaEventElapsedTime(&I.t_call, I.ev_call[0], I.ev_call[1]);
+    }
+}
+float Batch::call_ms() const { return p_->t_call; }
+int Batch::scc_passes() const { return p_->scc_passes; }
 
 int Batch::launches() const { return p_->launches; }
 void Batch::timings(float* t3) const { t3[0] = p_->t_setup; t3[1] = p_->t_scc; t3[2] = p_->t_grad; }

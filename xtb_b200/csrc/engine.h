@@ -46,6 +46,15 @@ class Batch {
     void* stream() const;
     int launches() const;
     void timings(float* t3) const;   // ms: setup+integrals, SCC, gradient+properties
+    // per-kernel-class device timers: launches whose class bit is set in mask are bracketed by CUDA events on the
+    // engine's stream; times accumulate over singlepoint calls until the next set_profile
+    void set_profile(unsigned long long mask);
+    static int kernel_classes();
+    static const char* kernel_class_name(int id);
+    void kernel_times(float* ms, int* calls, int* launches) const;
+    void mark_call(int end);         // events around a whole host-buffer call (H2D ... D2H)
+    float call_ms() const;
+    int scc_passes() const;          // batch-wide SCC passes of the last call (= max niter over molecules)
 
     MolResult result(int i) const;
     void fetch(const char* name, double* out) const;   // device -> host copy of a named array

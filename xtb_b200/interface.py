@@ -77,6 +77,10 @@ def load_library():
         "xtbb200_getOffsets": (ci, [vp, ci, ctypes.POINTER(ctypes.c_longlong)]),
         "xtbb200_getMask": (ci, [vp, ctypes.c_void_p, ctypes.c_size_t]),
         "xtbb200_getTimings": (ci, [vp, ctypes.POINTER(ctypes.c_float), _c_int_p]),
+        "xtbb200_getCallTime": (ci, [vp, ctypes.POINTER(ctypes.c_float)]),
+        "xtbb200_setProfile": (ci, [vp, ctypes.c_ulonglong]), "xtbb200_kernelClassCount": (ci, []),
+        "xtbb200_kernelClassName": (cp, [ci]),
+        "xtbb200_getKernelTimes": (ci, [vp, ctypes.POINTER(ctypes.c_float), _c_int_p, _c_int_p, _c_int_p]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -421,6 +425,38 @@ class BatchCalculator:
         n = ctypes.c_int()
         self._check(self._lib.xtbb200_getTimings(self._b, t, ctypes.byref(n)))
         return dict(setup_ms=t[0], scc_ms=t[1], grad_ms=t[2], launches=n.value)
+
+    def call_ms(self):
+        """Device time of the last host-buffer singlepoint call, H2D of positions through D2H of results."""
+        t = ctypes.c_float()
+        self._check(self._lib.xtbb200_getCallTime(self._b, ctypes.byref(t)))
+        return t.value
+
+    def set_profile(self, classes="all"):
+        """Bracket the launches of the given kernel classes (names, ids, "all" or None) with CUDA events."""
+        n = self._lib.xtbb200_kernelClassCount()
+        names = [self._lib.xtbb200_kernelClassName(i).decode() for i in range(n)]
+        if classes is None:
+            mask = 0
+        elif classes == "all":
+            mask = (1 << n) - 1
+        else:
+            mask = 0
+            for c in classes:
+                mask |= 1 << (names.index(c) if isinstance(c, str) else int(c))
+        self._check(self._lib.xtbb200_setProfile(self._b, mask))
+
+    def kernel_times(self):
+        """{class name: dict(ms, timed_launches, launches)} accumulated since set_profile, plus scc_passes."""
+        n = self._lib.xtbb200_kernelClassCount()
+        ms = (ctypes.c_float * n)()
+        tl = (ctypes.c_int * n)()
+        nl = (ctypes.c_int * n)()
+        sp = ctypes.c_int()
+        self._check(self._lib.xtbb200_getKernelTimes(self._b, ms, tl, nl, ctypes.byref(sp)))
+        out = {self._lib.xtbb200_kernelClassName(i).decode(): dict(ms=ms[i], timed_launches=tl[i], launches=nl[i])
+               for i in range(n)}
+        return out, sp.value
 
     def device_bytes(self):
         return int(self._lib.xtbb200_getDeviceBytes(self._b))
