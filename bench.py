@@ -161,7 +161,7 @@ def run_reference(args):
     build()
     s = load_kat(args.molecule)
     cores = host_cores()
-    per_step = max(cores, min(4 * cores, 256))
+    per_step = 64 * cores   # ~5-10 s per step
     for w in range(args.warmup):
         cpu_ensemble_rate(s, cores, cores)
     rates, times = [], []
@@ -332,7 +332,7 @@ def run_engine(args):
         from oracle.oracle import build
         build()
         cores = host_cores()
-        n_cpu = max(cores, min(2 * cores, 128))
+        n_cpu = min(nmol, 96 * cores)   # ~10-20 s of CPU work
         rate, dt, its, es = cpu_ensemble_rate(s, n_cpu, cores, first=0)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "first %d conformers of the same ensemble, one single-threaded oracle process per core, %.1f s" % (n_cpu, dt),

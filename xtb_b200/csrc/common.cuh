@@ -26,7 +26,8 @@ struct MolState {
     int ndp, nqp;    // screening list lengths
     int sweeps;      // Jacobi sweeps of the last diagonalisation
     int sweeps_total;
-    int nrot_pad[2];
+    int zvalid;      // Zm holds orthonormal eigenvectors of an earlier diagonalisation (Jacobi warm start)
+    int pad0;
     double eel, eold, ees, eaes, epol, ed, egap, ga, gb, efa, efb, rmsq;
     double ep, embd, eh0;
     double energy, gnorm;

@@ -24,6 +24,7 @@ __global__ void k_reset_state(Dev d, int keep_wfn) {
     MolState& s = d.st[i];
     s.iter = 0; s.converged = 0; s.lastdiag = 0; s.done = 0; s.fail = 0; s.kocc = 0; s.ndp = 0; s.nqp = 0;
     s.sweeps = 0; s.sweeps_total = 0;
+    if (!keep_wfn) s.zvalid = 0;
     s.eel = 0; s.eold = 0; s.ees = 0; s.eaes = 0; s.epol = 0; s.ed = 0; s.egap = 0; s.ga = 0; s.gb = 0;
     s.efa = 0; s.efb = 0; s.rmsq = 0; s.ep = 0; s.embd = 0; s.eh0 = 0; s.energy = 0; s.gnorm = 0;
 }
@@ -316,7 +317,7 @@ int Batch::singlepoint(bool restart) {
     int nl = 0;
     const int B = 128;
     cudaEventRecord(ev[0], st);
-    KL(K_SETUP, k_reset_state<<<(nmol + 127) / 128, 128, 0, st>>>(d, 0));
+    KL(K_SETUP, k_reset_state<<<(nmol + 127) / 128, 128, 0, st>>>(d, (restart && I.have_wfn) ? 1 : 0));
     // ---- geometry dependent setup
     KL(K_SETUP, k_cn<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
     const int mx = std::max(s.max_nat, std::max(s.max_nsh, s.max_ndim));
@@ -361,6 +362,8 @@ int Batch::singlepoint(bool restart) {
         KL(K_FOCK, k_fock<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
         KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.H, d.X, d.T, 0, 1));      // T = H X
         KL(K_GEMM_XHX, k_gemm<true, false><<<ggrid, 128, 0, st>>>(d, d.X, d.T, d.W, 0, 1));       // W = X^T T
+        if (it > 0 || (restart && I.have_wfn))
+            KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.W, d.Zm, d.T, 0, 2));   // T = A' Z_prev
         if (npairs * 32 <= 1024) KL(K_JACOBI, launch_jacobi<32>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 16 <= 1024) KL(K_JACOBI, launch_jacobi<16>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 8 <= 1024) KL(K_JACOBI, launch_jacobi<8>(d, nmol, s.max_nao, sm, st));

@@ -26,12 +26,14 @@ constexpr int GK = 16;     // k tile
 constexpr int GLD = GT + 4;
 
 // kmode: 0 -> K = nao ; 1 -> K = st.kocc (density build over occupied columns)
-// skip_done: skip molecules that already left the SCC loop
+// skip_done: 1 = skip molecules that already left the SCC loop; 2 = additionally skip molecules without a valid
+// eigenvector guess (warm-start product A' Z_prev)
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ Ag, const double* __restrict__ Bg,
                                               double* __restrict__ Cg, int kmode, int skip_done) {
     const MolDesc m = d.mol[blockIdx.y];
     if (skip_done && d.st[blockIdx.y].done) return;
+    if (skip_done == 2 && !d.st[blockIdx.y].zvalid) return;
     const int n = m.nao;
     const int tiles = (n + GT - 1) / GT;
     if ((int)blockIdx.x >= tiles * tiles) return;
@@ -187,7 +189,16 @@ __global__ void __launch_bounds__(1024) k_jacobi(Dev d) {
     }
     __syncthreads();
     const double sigma = s_sigma;
-    if (SM) {
+    if (st.zvalid) {
+        // warm start: G = (A' + sigma I) Z_prev = T + sigma Z_prev, T = A' Z_prev from the preceding k_gemm.
+        // Z_prev is orthonormal, so the columns of G are already nearly orthogonal and a few sweeps finish the job.
+        const double* T = d.T + m.mat0;
+        const double* Zp = d.Zm + m.mat0;
+        for (long long t = tid; t < (long long)n * n; t += nt) {
+            int i = (int)(t % n), j = (int)(t / n);
+            G[i + (long long)ld * j] = T[t] + sigma * Zp[t];
+        }
+    } else if (SM) {
         for (long long t = tid; t < (long long)n * n; t += nt) {
             int i = (int)(t % n), j = (int)(t / n);
             // symmetrise on load: the two triangles of X^T H X agree only to rounding
@@ -279,7 +290,7 @@ __global__ void __launch_bounds__(1024) k_jacobi(Dev d) {
         const int r = (int)(t % n), j = (int)(t / n);
         Z[r + (long long)n * rank[j]] = G[r + (long long)ld * j] / nrm[j];
     }
-    if (tid == 0) { st.sweeps = sweep; st.sweeps_total += sweep; if (sweep >= 40) st.fail = 12; }
+    if (tid == 0) { st.sweeps = sweep; st.sweeps_total += sweep; st.zvalid = 1; if (sweep >= 40) st.fail = 12; }
 }
 
 }  // namespace xtbb200
