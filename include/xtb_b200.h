@@ -32,6 +32,10 @@ void xtbb200_delBatch(xtbb200_TBatch* batch);
  * xtb_setMaxIter); guess: 0 = EEQ charges (reference default), 1 = uniform charges */
 int xtbb200_setOptions(xtbb200_TBatch batch, double accuracy, double etemp, int maxiter, int guess);
 
+/* eigensolver selection: 0 = automatic (block Jacobi on the FP64 tensor path when the matrix fits in shared memory),
+ * 1 = scalar one-sided Jacobi.  Both give the same spectrum to rounding; used by the parity tests. */
+int xtbb200_setSolver(xtbb200_TBatch batch, int mode);
+
 /* GFN2-xTB single point + gradient for every molecule of the batch (batched xtb_singlepoint).
  * positions: concatenated [natoms][3] in Bohr (host memory). restart != 0 reuses the converged
  * wavefunction of the previous call as SCC start (src/api/interface.f90:82-101).

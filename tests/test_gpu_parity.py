@@ -267,3 +267,22 @@ def test_gradient_matches_finite_difference(xb, kat):
     for n, (i, k) in enumerate(cases):
         fd = (r["energies"][1 + 2 * n] - r["energies"][2 + 2 * n]) / (2 * h)
         assert abs(fd - g[i, k]) < 2e-7
+
+
+@pytest.mark.parametrize("name", ["rivaroxaban", "fe_cnx6", "caffeine", "mindless05"])
+def test_block_and_scalar_eigensolvers_agree(xb, kat, name):
+    """The DMMA block Jacobi and the scalar Jacobi kernels are two implementations of the same solver."""
+    s = kat[name]
+    out = []
+    for mode in (0, 1):
+        b = xb.BatchCalculator([s["numbers"]] * 3, charges=[s["charge"]] * 3, uhf=[s["uhf"]] * 3)
+        b.set_solver(mode)
+        r = b.singlepoint(np.concatenate([s["xyz"]] * 3))
+        assert r["all_converged"]
+        out.append((r, b.array("emo"), b.array("P")))
+    (r0, e0, p0), (r1, e1, p1) = out
+    assert np.array_equal(r0["niter"], r1["niter"])
+    assert np.max(np.abs(r0["energies"] - r1["energies"])) < 1e-10
+    assert np.max(np.abs(r0["gradients"] - r1["gradients"])) < 1e-9
+    assert np.max(np.abs(e0 - e1)) < 1e-9
+    assert np.max(np.abs(p0 - p1)) < 1e-8

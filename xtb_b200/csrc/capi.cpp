@@ -434,6 +434,13 @@ int xtbb200_setOptions(xtbb200_TBatch batch, double accuracy, double etemp, int 
     return 0;
     XTBB_CATCH(-1)
 }
+int xtbb200_setSolver(xtbb200_TBatch batch, int mode) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    batch->b->set_solver(mode);
+    return 0;
+    XTBB_CATCH(-1)
+}
 int xtbb200_singlepoint(xtbb200_TBatch batch, const double* positions, int restart, double* energies, double* gradients,
                         double* charges, int* niter, int* status) {
     XTBB_TRY

@@ -50,6 +50,7 @@ struct Dev {
     // options
     double intcut, neglect, scfconv, qconv, etemp, broydamp;
     int maxiter;
+    int jb_inner;     // inner sweeps per Gram block of the block Jacobi solver
     // per atom
     double *xyz, *cn, *cn_cov, *cn_d4, *cn_erf, *radcn;
     double *q, *q_out, *dipm, *dipm_out, *qp, *qp_out;

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels_geom.cuh"
@@ -94,6 +95,7 @@ struct Batch::Impl {
     double acc = 1.0, etemp = 300.0;
     int maxiter = 250;
     int guess = 0;
+    int solver = 0;     // 0: automatic, 1: scalar one-sided Jacobi (k_jacobi) even where the block kernel fits
     size_t bytes = 0;
     // timing (ms) of the last single point
     float t_setup = 0, t_scc = 0, t_grad = 0;
@@ -216,6 +218,7 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         // opt in to large dynamic shared memory for the in-SM solvers
         const int smax = 227 * 1024 - 2048;
         cudaFuncSetAttribute(k_chol_inv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        cudaFuncSetAttribute(k_jacobi_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_jacobi<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_jacobi<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_jacobi<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
@@ -248,6 +251,7 @@ void Batch::set_options(double accuracy, double etemp, int maxiter) {
     p_->acc = accuracy; p_->etemp = etemp; p_->maxiter = maxiter;
 }
 void Batch::set_guess(int mode) { p_->guess = mode; }
+void Batch::set_solver(int mode) { p_->solver = mode; }
 
 void Batch::set_positions(const double* xyz_host) {
     Impl& I = *p_;
@@ -312,6 +316,8 @@ int Batch::singlepoint(bool restart) {
     d.etemp = I.etemp;
     d.broydamp = 0.4;   // src/setparam.f90:226
     d.maxiter = I.maxiter;
+    d.jb_inner = kJbInnerSweeps;
+    if (const char* e = std::getenv("XTBB200_JB_INNER")) d.jb_inner = std::max(1, std::atoi(e));   // tuning knob
     if (!I.ev_phase[0]) for (auto& e : I.ev_phase) cudaEventCreate(&e);
     cudaEvent_t* ev = I.ev_phase;
     int nl = 0;
@@ -351,6 +357,10 @@ int Batch::singlepoint(bool restart) {
     const int tiles = (s.max_nao + GT - 1) / GT;
     const dim3 ggrid(tiles * tiles, nmol);
     const int npairs = (s.max_nao + 1) / 2;
+    // ensemble-sized matrices: block Jacobi on the FP64 tensor path, matrix resident in shared memory
+    const int jb_warps = std::max(1, std::min(20, jb_dims(s.max_nao).nb / 2));   // k_jacobi_blk: __launch_bounds__(640)
+    const size_t jb_bytes = jb_smem_bytes(s.max_nao, jb_warps);
+    const bool jb = jb_bytes <= (size_t)(227 * 1024 - 1024) && I.solver != 1;
     int active = nmol;
     int iters = 0;
     for (int it = 0; it < I.maxiter && active > 0; ++it) {
@@ -364,7 +374,8 @@ int Batch::singlepoint(bool restart) {
         KL(K_GEMM_XHX, k_gemm<true, false><<<ggrid, 128, 0, st>>>(d, d.X, d.T, d.W, 0, 1));       // W = X^T T
         if (it > 0 || (restart && I.have_wfn))
             KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.W, d.Zm, d.T, 0, 2));   // T = A' Z_prev
-        if (npairs * 32 <= 1024) KL(K_JACOBI, launch_jacobi<32>(d, nmol, s.max_nao, sm, st));
+        if (jb) KL(K_JACOBI, k_jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d));
+        else if (npairs * 32 <= 1024) KL(K_JACOBI, launch_jacobi<32>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 16 <= 1024) KL(K_JACOBI, launch_jacobi<16>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 8 <= 1024) KL(K_JACOBI, launch_jacobi<8>(d, nmol, s.max_nao, sm, st));
         else KL(K_JACOBI, launch_jacobi<4>(d, nmol, s.max_nao, sm, st));

@@ -22,6 +22,7 @@ class Batch {
 
     void set_options(double accuracy, double etemp, int maxiter);
     void set_guess(int mode);                      // 0: EEQ (default), 1: uniform charges
+    void set_solver(int mode);                     // 0: automatic, 1: force the scalar Jacobi kernel
     void set_positions(const double* xyz_host);    // concatenated (3, natoms) in bohr, host memory
     void set_positions_device(const double* xyz_dev);
     void set_wavefunction(const double* qsh, const double* dipm, const double* qp);

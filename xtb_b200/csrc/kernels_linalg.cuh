@@ -293,4 +293,258 @@ __global__ void __launch_bounds__(1024) k_jacobi(Dev d) {
     if (tid == 0) { st.sweeps = sweep; st.sweeps_total += sweep; st.zvalid = 1; if (sweep >= 40) st.fail = 12; }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Block one-sided Jacobi on the FP64 tensor path (the ensemble-sized solver, nao <= ~164).
+//
+// Same mathematics as k_jacobi (Hestenes orthogonalisation of the columns of G = (A' + sigma I) Z_prev) but the
+// columns are handled in blocks of 4: one warp owns one pair of blocks (8 columns, an n x 8 panel W in shared memory)
+// per tournament step and
+//   1. forms the 8x8 Gram matrix M = W^T W with DMMA m8n8k4 (A and B fragments are the same shared-memory element,
+//      one conflict-free 8-byte load per lane and k-step),
+//   2. skips the pair when every relative off-diagonal |M_pq|/sqrt(M_pp M_qq) is below tol,
+//   3. otherwise diagonalises M by a two-sided cyclic Jacobi in per-warp shared memory (32 lanes = 4 disjoint
+//      rotations x 8 rows), accumulating the 8x8 orthogonal J,
+//   4. applies W <- W J with DMMA (2 k-steps per 8-row tile).
+// Shared-memory traffic per rotated column pair drops ~10x against the scalar kernel, which is shared-memory bound.
+// Layout: G column-major, leading dimension ld = nr + 4 (nr = n rounded up to 8) so that ld = 4 mod 8: the 4 rows x 4
+// columns touched by a half-warp fall into 16 distinct 8-byte banks.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void jb_block_pair(int step, int pr, int nb, int& P, int& Q) {
+    const int mm1 = nb - 1;
+    int p, q;
+    if (pr == 0) { p = step % mm1; q = mm1; }
+    else { p = (step + pr) % mm1; q = (step - pr + mm1) % mm1; }
+    P = p < q ? p : q; Q = p < q ? q : p;
+}
+
+constexpr int kJbInnerSweeps = 1;  // inner sweeps per Gram block (early exit when a sweep rotates nothing)
+constexpr int kJbScratch = 144;   // doubles of per-warp scratch: M[8][9], J[8][9]
+
+struct JbDims { int nr, ld, nb; };
+__host__ __device__ inline JbDims jb_dims(int n) {
+    JbDims r;
+    r.nr = (n + 7) & ~7;
+    r.ld = r.nr + 4;
+    r.nb = (n + 3) / 4;
+    if (r.nb & 1) r.nb++;
+    if (r.nb < 2) r.nb = 2;
+    return r;
+}
+inline size_t jb_smem_bytes(int n, int nwarps) {
+    JbDims g = jb_dims(n);
+    return ((size_t)g.ld * g.nb * 4 + (size_t)nwarps * kJbScratch) * sizeof(double);
+}
+
+#ifdef XTBB200_JB_TIMING
+#define JB_T(k) do { long long t_ = clock64(); jbt[k] += t_ - jbt0; jbt0 = t_; } while (0)
+#else
+#define JB_T(k)
+#endif
+__global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
+#ifdef XTBB200_JB_TIMING
+    long long jbt[6] = {0, 0, 0, 0, 0, 0}, jbt0 = clock64();
+#endif
+    const int im = blockIdx.x;
+    const MolDesc m = d.mol[im];
+    MolState& st = d.st[im];
+    if (st.done) return;
+    const int n = m.nao;
+    const JbDims dm = jb_dims(n);
+    const int nr = dm.nr, ld = dm.ld, nb = dm.nb;
+    extern __shared__ double smem[];
+    double* G = smem;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    double* Msh = smem + (size_t)ld * nb * 4 + (size_t)warp * kJbScratch;
+    double* Jsh = Msh + 72;
+    __shared__ double red[32];
+    __shared__ double s_sigma;
+    const double* A = d.W + m.mat0;
+    // Gershgorin bound -> shift that makes G positive definite
+    double mx = 0.0;
+    for (int i = tid; i < n; i += nt) {
+        double s = 0;
+        for (int j = 0; j < n; ++j) s += fabs(A[i + (long long)n * j]);
+        mx = fmax(mx, s);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        double v = 0;
+        for (int w = 0; w < nwarps; ++w) v = fmax(v, red[w]);
+        s_sigma = 1.05 * v + 1.0;
+    }
+    __syncthreads();
+    const double sigma = s_sigma;
+    const int ncolp = nb * 4;
+    const bool warm = st.zvalid != 0;
+    {
+        const double* T = d.T + m.mat0;
+        const double* Zp = d.Zm + m.mat0;
+        for (int t = tid; t < ld * ncolp; t += nt) {
+            const int i = t % ld, j = t / ld;
+            double v = 0.0;
+            if (i < n && j < n) {
+                const long long a = i + (long long)n * j;
+                if (warm) v = T[a] + sigma * Zp[a];
+                else v = 0.5 * (A[a] + A[j + (long long)n * i]) + (i == j ? sigma : 0.0);
+            }
+            G[t] = v;
+        }
+    }
+    __syncthreads();
+    const double tol = 8.0 * sqrt((double)n) * 2.220446049250313e-16;
+    const double tol2 = tol * tol;
+    const double tol_in2 = 2.220446049250313e-16 * 2.220446049250313e-16;
+    const int nbp = nb / 2;
+    const int l4 = lane >> 2, l3 = lane & 3;
+    // inner tournament of the 8 panel columns: lane = (slot, idx); slot's pair at inner step s7 packed 6 bits per step
+    const int slot = lane >> 3, idx = lane & 7;
+    unsigned long long pairtab = 0;
+    for (int s7 = 0; s7 < 7; ++s7) {
+        int p, q;
+        if (slot == 0) { p = s7; q = 7; }
+        else { const int a = (s7 + slot) % 7, b = (s7 - slot + 7) % 7; p = a < b ? a : b; q = a < b ? b : a; }
+        pairtab |= (unsigned long long)(p | (q << 3)) << (6 * s7);
+    }
+    int sweep = 0;
+    for (; sweep < 40; ++sweep) {
+        int rotated = 0;
+        for (int step = 0; step < nb - 1; ++step) {
+            for (int pr = warp; pr < nbp; pr += nwarps) {
+                int P, Q;
+                jb_block_pair(step, pr, nb, P, Q);
+                if (4 * Q >= n) continue;                       // dummy block (all-zero columns)
+                JB_T(0);
+                // ---- Gram matrix of the 8 panel columns
+                const int gcol = l4 < 4 ? 4 * P + l4 : 4 * Q + l4 - 4;
+                const double* wp = G + (size_t)ld * gcol + l3;
+                double a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, e0 = 0, e1 = 0;
+                int k0 = 0;
+                for (; k0 + 16 <= nr; k0 += 16) {
+                    const double w0 = wp[k0], w1 = wp[k0 + 4], w2 = wp[k0 + 8], w3 = wp[k0 + 12];
+                    dmma_884(a0, a1, w0, w0); dmma_884(b0, b1, w1, w1);
+                    dmma_884(c0, c1, w2, w2); dmma_884(e0, e1, w3, w3);
+                }
+                for (; k0 < nr; k0 += 4) { const double w0 = wp[k0]; dmma_884(a0, a1, w0, w0); }
+                const double m0 = (a0 + b0) + (c0 + e0), m1 = (a1 + b1) + (c1 + e1);
+                __syncwarp();
+                Msh[l4 * 9 + 2 * l3] = m0; Msh[l4 * 9 + 2 * l3 + 1] = m1;
+                Jsh[l4 * 9 + 2 * l3] = (l4 == 2 * l3) ? 1.0 : 0.0; Jsh[l4 * 9 + 2 * l3 + 1] = (l4 == 2 * l3 + 1) ? 1.0 : 0.0;
+                __syncwarp();
+                JB_T(1);
+                // ---- needs work?  (squared form of |M_pq| > tol sqrt(M_pp M_qq): no square roots on this path)
+                int need = 0;
+                {
+                    const double dii = Msh[l4 * 10];
+                    const int j0 = 2 * l3, j1 = 2 * l3 + 1;
+                    if (j0 != l4) need |= (m0 * m0 > tol2 * dii * Msh[j0 * 10]) ? 1 : 0;
+                    if (j1 != l4) need |= (m1 * m1 > tol2 * dii * Msh[j1 * 10]) ? 1 : 0;
+                }
+                if (!__any_sync(0xffffffffu, need)) continue;
+                rotated = 1;
+                // ---- two-sided Jacobi on the 8x8 Gram matrix; lane = (pair slot, row/column index).
+                // A bounded number of inner sweeps is enough: the outer loop re-forms every Gram matrix, so the inner
+                // solve only sets the convergence rate, never the final accuracy.  M and J have row stride 9
+                // (conflict-free column access).
+                for (int isw = 0; isw < d.jb_inner; ++isw) {
+                    int anyrot = 0;
+#pragma unroll
+                    for (int s7 = 0; s7 < 7; ++s7) {
+                        const int p = (int)(pairtab >> (6 * s7)) & 7, q = (int)(pairtab >> (6 * s7 + 3)) & 7;
+                        const double app = Msh[p * 10], aqq = Msh[q * 10], apq = Msh[p * 9 + q];
+                        double c = 1.0, s = 0.0;
+                        if (apq * apq > tol_in2 * app * aqq) {
+                            // rotation angle |theta| <= pi/4 from two reciprocal square roots (no divisions):
+                            // cos 2t = |tau|/r, r = hypot(tau, 2 apq); c = sqrt((1 + cos 2t)/2); s = sgn(tau) apq/(r c)
+                            const double tau = aqq - app;
+                            const double ir = rsqrt(tau * tau + 4.0 * apq * apq);
+                            const double c2 = 0.5 + 0.5 * fabs(tau) * ir;
+                            const double ic = rsqrt(c2);
+                            c = c2 * ic;
+                            s = (tau >= 0.0 ? apq : -apq) * ir * ic;
+                            anyrot = 1;
+                        }
+                        __syncwarp();
+                        {   // columns p,q of M and J (row idx)
+                            const double mp = Msh[idx * 9 + p], mq = Msh[idx * 9 + q];
+                            const double jp = Jsh[idx * 9 + p], jq = Jsh[idx * 9 + q];
+                            Msh[idx * 9 + p] = c * mp - s * mq; Msh[idx * 9 + q] = s * mp + c * mq;
+                            Jsh[idx * 9 + p] = c * jp - s * jq; Jsh[idx * 9 + q] = s * jp + c * jq;
+                        }
+                        __syncwarp();
+                        {   // rows p,q of M (column idx)
+                            const double mp = Msh[p * 9 + idx], mq = Msh[q * 9 + idx];
+                            Msh[p * 9 + idx] = c * mp - s * mq; Msh[q * 9 + idx] = s * mp + c * mq;
+                        }
+                        __syncwarp();
+                    }
+                    if (!__any_sync(0xffffffffu, anyrot)) break;
+                }
+                JB_T(2);
+                // ---- W <- W J : four 8-row tiles in flight per iteration
+                {
+                    const double bj0 = Jsh[l3 * 9 + l4], bj1 = Jsh[(4 + l3) * 9 + l4];
+                    const double* ap0 = G + (size_t)ld * (4 * P + l3) + l4;
+                    const double* ap1 = G + (size_t)ld * (4 * Q + l3) + l4;
+                    const int oc = (l3 < 2) ? 4 * P + 2 * l3 : 4 * Q + 2 * l3 - 4;
+                    double* op = G + (size_t)ld * oc + l4;
+                    for (int r0 = 0; r0 < nr; r0 += 32) {
+                        double xa[4], xb[4], y0[4], y1[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const bool on = r0 + 8 * u < nr;
+                            xa[u] = on ? ap0[r0 + 8 * u] : 0.0;
+                            xb[u] = on ? ap1[r0 + 8 * u] : 0.0;
+                            y0[u] = 0.0; y1[u] = 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) dmma_884(y0[u], y1[u], xa[u], bj0);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) dmma_884(y0[u], y1[u], xb[u], bj1);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (r0 + 8 * u < nr) { op[r0 + 8 * u] = y0[u]; op[r0 + 8 * u + ld] = y1[u]; }
+                    }
+                }
+                JB_T(3);
+            }
+            JB_T(4);
+            __syncthreads();
+            JB_T(5);
+        }
+        if (!__syncthreads_or(rotated)) { ++sweep; break; }
+    }
+    // eigenvalues, ordering, normalised eigenvectors
+    double* nrm = d.nrm + m.ao0;
+    for (int j = tid; j < n; j += nt) {
+        double s = 0;
+        const double* g = G + (size_t)ld * j;
+        for (int r = 0; r < n; ++r) s += g[r] * g[r];
+        nrm[j] = sqrt(s);
+    }
+    __syncthreads();
+    double* Z = d.Zm + m.mat0;
+    double* emo = d.emo + m.ao0;
+    int* rank = d.rank + m.ao0;
+    for (int j = tid; j < n; j += nt) {
+        const double v = nrm[j];
+        int rk = 0;
+        for (int k = 0; k < n; ++k) { const double w = nrm[k]; rk += (w < v || (w == v && k < j)) ? 1 : 0; }
+        emo[rk] = v - sigma;
+        rank[j] = rk;
+    }
+    __syncthreads();
+    for (int t = tid; t < n * n; t += nt) {
+        const int r = t % n, j = t / n;
+        Z[r + (long long)n * rank[j]] = G[r + (size_t)ld * j] / nrm[j];
+    }
+    if (tid == 0) { st.sweeps = sweep; st.sweeps_total += sweep; st.zvalid = 1; if (sweep >= 40) st.fail = 12; }
+#ifdef XTBB200_JB_TIMING
+    if (im == 0 && (tid == 0 || tid == 32 * 7))
+        printf("jb timing warp %d sweeps %d: other %lld gram %lld inner %lld apply %lld looptail %lld barrier %lld\n", warp, sweep,
+               jbt[0], jbt[1], jbt[2], jbt[3], jbt[4], jbt[5]);
+#endif
+}
+
 }  // namespace xtbb200

@@ -21,7 +21,8 @@ class XTBException(Exception):
 
 
 def library_path():
-    return os.path.join(_HERE, "lib", "libxtb_b200.so")
+    # XTBB200_LIB: diagnostic builds of the same engine (e.g. clock64-instrumented kernels); never a different backend
+    return os.environ.get("XTBB200_LIB") or os.path.join(_HERE, "lib", "libxtb_b200.so")
 
 
 def load_library():
@@ -67,6 +68,7 @@ def load_library():
         "xtbb200_newBatch": (vp, [ci, _c_int_p, _c_int_p, _c_double_p, _c_int_p, ci]),
         "xtbb200_delBatch": (None, [ctypes.POINTER(vp)]),
         "xtbb200_setOptions": (ci, [vp, cd, cd, ci, ci]),
+        "xtbb200_setSolver": (ci, [vp, ci]),
         "xtbb200_singlepoint": (ci, [vp, _c_double_p, ci, _c_double_p, _c_double_p, _c_double_p, _c_int_p, _c_int_p]),
         "xtbb200_singlepointDevice": (ci, [vp, vp, ci, vp]),
         "xtbb200_getNMol": (ci, [vp]), "xtbb200_getSizes": (ci, [vp, ci, _c_int_p, _c_int_p, _c_int_p]),
@@ -357,6 +359,10 @@ class BatchCalculator:
     def set_options(self, accuracy=1.0, etemp=300.0, maxiter=250, guess="eeq"):
         self._check(self._lib.xtbb200_setOptions(self._b, float(accuracy), float(etemp), int(maxiter),
                                                  {"eeq": 0, "sad": 1}[guess]))
+
+    def set_solver(self, mode):
+        """0: automatic, 1: scalar Jacobi kernel."""
+        self._check(self._lib.xtbb200_setSolver(self._b, int(mode)))
 
     def singlepoint(self, positions, restart=False):
         """positions: (total_atoms, 3) Bohr. Returns dict(energies, gradients, charges, niter, status)."""
