@@ -51,6 +51,7 @@ struct Dev {
     double intcut, neglect, scfconv, qconv, etemp, broydamp;
     int maxiter;
     int jb_inner;     // inner sweeps per Gram block of the block Jacobi solver
+    double jb_tol;    // relative orthogonality threshold of the block Jacobi solver (0: 8 sqrt(n) eps)
     // per atom
     double *xyz, *cn, *cn_cov, *cn_d4, *cn_erf, *radcn;
     double *q, *q_out, *dipm, *dipm_out, *qp, *qp_out;

@@ -317,6 +317,8 @@ int Batch::singlepoint(bool restart) {
     d.broydamp = 0.4;   // src/setparam.f90:226
     d.maxiter = I.maxiter;
     d.jb_inner = kJbInnerSweeps;
+    d.jb_tol = 0.0;
+    if (const char* e = std::getenv("XTBB200_JB_TOL")) d.jb_tol = std::atof(e);   // tuning knob
     if (const char* e = std::getenv("XTBB200_JB_INNER")) d.jb_inner = std::max(1, std::atoi(e));   // tuning knob
     if (!I.ev_phase[0]) for (auto& e : I.ev_phase) cudaEventCreate(&e);
     cudaEvent_t* ev = I.ev_phase;

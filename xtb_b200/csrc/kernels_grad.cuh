@@ -106,7 +106,14 @@ __global__ void __launch_bounds__(kIntWarps * 32) k_grad_h0(Dev d) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) { vqi[k] = d.vq[6 * (m.at0 + iat) + k]; vqj[k] = d.vq[6 * (m.at0 + jat) + k]; }
     double gx[3] = {0, 0, 0};
-    for (int c = lane; c < nci * ncj; c += 32) {
+    // lpc lanes share one Cartesian component pair and split its primitive pairs (everything below is linear in the
+    // primitive contributions, so per-lane partial sums are contracted independently and added by the warp reduction)
+    const int ncomp = nci * ncj, npp = npi * npj;
+    const int lpc = ncomp >= 32 ? 1 : 32 / ncomp;
+    const int ngrp = 32 / lpc;
+    const int grp = lane / lpc, sub = lane % lpc;
+    for (int c = grp; c < ncomp; c += ngrp) {
+        if (grp >= ngrp) break;
         const int mli = c / ncj, mlj = c % ncj;
         const int lxi[3] = {c_lx[c_itt[li] + mli], c_ly[c_itt[li] + mli], c_lz[c_itt[li] + mli]};
         const int lxj[3] = {c_lx[c_itt[lj] + mlj], c_ly[c_itt[lj] + mlj], c_lz[c_itt[lj] + mlj]};
@@ -126,37 +133,36 @@ __global__ void __launch_bounds__(kIntWarps * 32) k_grad_h0(Dev d) {
         double sdq[10], sdqg[3][10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) { sdq[k] = 0.0; sdqg[0][k] = sdqg[1][k] = sdqg[2][k] = 0.0; }
-        for (int ip = 0; ip < npi; ++ip) {
+        for (int pp = sub; pp < npp; pp += lpc) {
+            const int ip = pp / npj, jp = pp % npj;
             const double alpi = s_alp[warp][0][ip];
             const double ci = s_cont[warp][0][ip] * fi;
-            for (int jp = 0; jp < npj; ++jp) {
-                const double alpj = s_alp[warp][1][jp];
-                double est = alpi * alpj * rij2;
-                if (est > intcut * (alpi + alpj)) continue;
-                const double ab = 1.0 / (alpi + alpj);
-                est = est * ab;
-                const double sq = sqrtpi * sqrt(ab);
-                const double kab = exp(-est) * (sq * sq * sq);
-                const double cc = kab * (s_cont[warp][1][jp] * fj) * ci;
-                const double gm = 0.5 * ab;
-                double t[9];
+            const double alpj = s_alp[warp][1][jp];
+            double est = alpi * alpj * rij2;
+            if (est > intcut * (alpi + alpj)) continue;
+            const double ab = 1.0 / (alpi + alpj);
+            est = est * ab;
+            const double sq = sqrtpi * sqrt(ab);
+            const double kab = exp(-est) * (sq * sq * sq);
+            const double cc = kab * (s_cont[warp][1][jp] * fj) * ci;
+            const double gm = 0.5 * ab;
+            double t[9];
 #pragma unroll
-                for (int k = 0; k < 9; ++k) t[k] = olapp(k, gm);
-                double val[3][3], gra[3][3];
+            for (int k = 0; k < 9; ++k) t[k] = olapp(k, gm);
+            double val[3][3], gra[3][3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const double rp = (alpi * ri[k] + alpj * rj[k]) * ab;
-                    // operator origin on atom j (rc = rj), intgrad.f90:1020
-                    moments_grad_1d(lxi[k], lxj[k], alpi, rp - ri[k], rp - rj[k], rp - rj[k], t, val[k], gra[k]);
-                }
+            for (int k = 0; k < 3; ++k) {
+                const double rp = (alpi * ri[k] + alpj * rj[k]) * ab;
+                // operator origin on atom j (rc = rj), intgrad.f90:1020
+                moments_grad_1d(lxi[k], lxj[k], alpi, rp - ri[k], rp - rj[k], rp - rj[k], t, val[k], gra[k]);
+            }
 #pragma unroll
-                for (int k = 0; k < 10; ++k) {
-                    const int ox = c_ord[k][0], oy = c_ord[k][1], oz = c_ord[k][2];
-                    sdq[k] += val[0][ox] * val[1][oy] * val[2][oz] * cc;
-                    sdqg[0][k] += gra[0][ox] * val[1][oy] * val[2][oz] * cc;
-                    sdqg[1][k] += val[0][ox] * gra[1][oy] * val[2][oz] * cc;
-                    sdqg[2][k] += val[0][ox] * val[1][oy] * gra[2][oz] * cc;
-                }
+            for (int k = 0; k < 10; ++k) {
+                const int ox = c_ord[k][0], oy = c_ord[k][1], oz = c_ord[k][2];
+                sdq[k] += val[0][ox] * val[1][oy] * val[2][oz] * cc;
+                sdqg[0][k] += gra[0][ox] * val[1][oy] * val[2][oz] * cc;
+                sdqg[1][k] += val[0][ox] * gra[1][oy] * val[2][oz] * cc;
+                sdqg[2][k] += val[0][ox] * val[1][oy] * gra[2][oz] * cc;
             }
         }
         // shiftintg (intgrad.f90:703-728): operator moved from j to i, then contract

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kIntWarps * 32) k_sdqh0(Dev d) {
     long long npair = (long long)m.nsh * (m.nsh + 1) / 2;
     long long p = (long long)blockIdx.x * kIntWarps + warp;
     __shared__ double s_blk[kIntWarps][10][36];
+    __shared__ double s_part[kIntWarps][10][33];
     __shared__ double s_alp[kIntWarps][2][6], s_cont[kIntWarps][2][6];
     if (p >= npair) return;   // whole warp exits together
     int is = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
@@ -120,57 +121,75 @@ __global__ void __launch_bounds__(kIntWarps * 32) k_sdqh0(Dev d) {
     for (int c = lane; c < 36; c += 32)
         for (int k = 0; k < 10; ++k) s_blk[warp][k][c] = 0.0;
     __syncwarp();
-    for (int c = lane; c < ncomp; c += 32) {
-        const int mli = c / ncj, mlj = c % ncj;
-        const int lix = c_lx[c_itt[li] + mli], liy = c_ly[c_itt[li] + mli], liz = c_lz[c_itt[li] + mli];
-        const int ljx = c_lx[c_itt[lj] + mlj], ljy = c_ly[c_itt[lj] + mlj], ljz = c_lz[c_itt[lj] + mlj];
-        const double fi = (li == 2) ? c_dcart[mli] : 1.0, fj = (lj == 2) ? c_dcart[mlj] : 1.0;
+    // Work decomposition: lpc lanes share one Cartesian component pair and split its primitive pairs, so that s-s,
+    // s-p and p-p shell pairs (1, 3, 9 components) still occupy most of the warp.
+    const int npp = npi * npj;
+    const int lpc = ncomp >= 32 ? 1 : 32 / ncomp;
+    const int ngrp = 32 / lpc;
+    const int grp = lane / lpc, sub = lane % lpc;
+    for (int c0 = 0; c0 < ncomp; c0 += ngrp) {
+        const int c = c0 + grp;
+        const bool on = (grp < ngrp) && (c < ncomp);
         double acc[10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) acc[k] = 0.0;
-        if (rij2 <= 2000.0) {
-            for (int ip = 0; ip < npi; ++ip) {
+        int mli = 0, mlj = 0;
+        if (on && rij2 <= 2000.0) {
+            mli = c / ncj; mlj = c % ncj;
+            const int lix = c_lx[c_itt[li] + mli], liy = c_ly[c_itt[li] + mli], liz = c_lz[c_itt[li] + mli];
+            const int ljx = c_lx[c_itt[lj] + mlj], ljy = c_ly[c_itt[lj] + mlj], ljz = c_lz[c_itt[lj] + mlj];
+            const double fi = (li == 2) ? c_dcart[mli] : 1.0, fj = (lj == 2) ? c_dcart[mlj] : 1.0;
+            for (int pp = sub; pp < npp; pp += lpc) {
+                const int ip = pp / npj, jp = pp % npj;
                 const double alpi = s_alp[warp][0][ip];
                 const double ci = s_cont[warp][0][ip] * fi;
-                for (int jp = 0; jp < npj; ++jp) {
-                    const double alpj = s_alp[warp][1][jp];
-                    double est = alpi * alpj * rij2;
-                    if (est > intcut * (alpi + alpj)) continue;
-                    const double ab = 1.0 / (alpi + alpj);
-                    est = est * ab;
-                    const double sq = sqrtpi * sqrt(ab);
-                    const double kab = exp(-est) * (sq * sq * sq);
-                    const double cc = kab * (s_cont[warp][1][jp] * fj) * ci;
-                    const double gm = 0.5 * ab;
-                    double t[9];
+                const double alpj = s_alp[warp][1][jp];
+                double est = alpi * alpj * rij2;
+                if (est > intcut * (alpi + alpj)) continue;
+                const double ab = 1.0 / (alpi + alpj);
+                est = est * ab;
+                const double sq = sqrtpi * sqrt(ab);
+                const double kab = exp(-est) * (sq * sq * sq);
+                const double cc = kab * (s_cont[warp][1][jp] * fj) * ci;
+                const double gm = 0.5 * ab;
+                double t[9];
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) t[k] = olapp(k, gm);
-                    double vx[3], vy[3], vz[3];
-                    {
-                        double rp = (alpi * ri[0] + alpj * rj[0]) * ab;
-                        moments_1d<2>(lix, ljx, rp - ri[0], rp - rj[0], rp, t, vx);
-                        rp = (alpi * ri[1] + alpj * rj[1]) * ab;
-                        moments_1d<2>(liy, ljy, rp - ri[1], rp - rj[1], rp, t, vy);
-                        rp = (alpi * ri[2] + alpj * rj[2]) * ab;
-                        moments_1d<2>(liz, ljz, rp - ri[2], rp - rj[2], rp, t, vz);
-                    }
-                    acc[0] += vx[0] * vy[0] * vz[0] * cc;
-                    acc[1] += vx[1] * vy[0] * vz[0] * cc;
-                    acc[2] += vx[0] * vy[1] * vz[0] * cc;
-                    acc[3] += vx[0] * vy[0] * vz[1] * cc;
-                    acc[4] += vx[2] * vy[0] * vz[0] * cc;
-                    acc[5] += vx[0] * vy[2] * vz[0] * cc;
-                    acc[6] += vx[0] * vy[0] * vz[2] * cc;
-                    acc[7] += vx[1] * vy[1] * vz[0] * cc;
-                    acc[8] += vx[1] * vy[0] * vz[1] * cc;
-                    acc[9] += vx[0] * vy[1] * vz[1] * cc;
+                for (int k = 0; k < 9; ++k) t[k] = olapp(k, gm);
+                double vx[3], vy[3], vz[3];
+                {
+                    double rp = (alpi * ri[0] + alpj * rj[0]) * ab;
+                    moments_1d<2>(lix, ljx, rp - ri[0], rp - rj[0], rp, t, vx);
+                    rp = (alpi * ri[1] + alpj * rj[1]) * ab;
+                    moments_1d<2>(liy, ljy, rp - ri[1], rp - rj[1], rp, t, vy);
+                    rp = (alpi * ri[2] + alpj * rj[2]) * ab;
+                    moments_1d<2>(liz, ljz, rp - ri[2], rp - rj[2], rp, t, vz);
                 }
+                acc[0] += vx[0] * vy[0] * vz[0] * cc;
+                acc[1] += vx[1] * vy[0] * vz[0] * cc;
+                acc[2] += vx[0] * vy[1] * vz[0] * cc;
+                acc[3] += vx[0] * vy[0] * vz[1] * cc;
+                acc[4] += vx[2] * vy[0] * vz[0] * cc;
+                acc[5] += vx[0] * vy[2] * vz[0] * cc;
+                acc[6] += vx[0] * vy[0] * vz[2] * cc;
+                acc[7] += vx[1] * vy[1] * vz[0] * cc;
+                acc[8] += vx[1] * vy[0] * vz[1] * cc;
+                acc[9] += vx[0] * vy[1] * vz[1] * cc;
             }
         }
+        // fixed-order reduction over the lanes of each component group (deterministic)
 #pragma unroll
-        for (int k = 0; k < 10; ++k) s_blk[warp][k][mli * 6 + mlj] = acc[k];
+        for (int k = 0; k < 10; ++k) s_part[warp][k][lane] = acc[k];
+        __syncwarp();
+        for (int e = lane; e < ngrp * 10; e += 32) {
+            const int g = e / 10, k = e % 10, cc2 = c0 + g;
+            if (cc2 < ncomp) {
+                double v = 0.0;
+                for (int u = 0; u < lpc; ++u) v += s_part[warp][k][g * lpc + u];
+                s_blk[warp][k][(cc2 / ncj) * 6 + (cc2 % ncj)] = v;
+            }
+        }
+        __syncwarp();
     }
-    __syncwarp();
     // CAO -> SAO and scatter.  Output element (ii, jj) of the spherical block, 10 operators.
     const int nsi = c_nsph[li], nsj = c_nsph[lj];
     const int nao = m.nao;

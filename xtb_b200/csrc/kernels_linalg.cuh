@@ -50,35 +50,41 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    // software pipeline: the global loads of tile k+1 are in flight (registers) while tile k is multiplied from shared memory
+    double ra[GT * GK / 128], rb[GT * GK / 128];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < GT * GK / 128; ++u) {
+            const int t = tid + 128 * u;
+            if (!TA) {
+                const int r = t % GT, kk = t / GT, gr = r0 + r, gk = k0 + kk;
+                ra[u] = (gr < n && gk < K) ? A[gr + (long long)n * gk] : 0.0;
+            } else {
+                const int kk = t % GK, r = t / GK, gr = r0 + r, gk = k0 + kk;
+                ra[u] = (gr < n && gk < K) ? A[gk + (long long)n * gr] : 0.0;
+            }
+            if (!TB) {
+                const int kk = t % GK, c = t / GK, gc = c0 + c, gk = k0 + kk;
+                rb[u] = (gc < n && gk < K) ? B[gk + (long long)n * gc] : 0.0;
+            } else {
+                const int c = t % GT, kk = t / GT, gc = c0 + c, gk = k0 + kk;
+                rb[u] = (gc < n && gk < K) ? B[gc + (long long)n * gk] : 0.0;
+            }
+        }
+    };
+    auto stage = [&]() {   // As[kk][r] = op(A)(r0+r, k0+kk), Bs[kk][c] = op(B)(k0+kk, c0+c)
+#pragma unroll
+        for (int u = 0; u < GT * GK / 128; ++u) {
+            const int t = tid + 128 * u;
+            if (!TA) As[t / GT][t % GT] = ra[u]; else As[t % GK][t / GK] = ra[u];
+            if (!TB) Bs[t % GK][t / GK] = rb[u]; else Bs[t / GT][t % GT] = rb[u];
+        }
+    };
+    if (K > 0) fetch(0);
     for (int k0 = 0; k0 < K; k0 += GK) {
-        // stage tiles: As[kk][r] = op(A)(r0+r, k0+kk), Bs[kk][c] = op(B)(k0+kk, c0+c)
-        if (!TA) {
-            for (int t = tid; t < GT * GK; t += 128) {
-                int r = t % GT, kk = t / GT;
-                int gr = r0 + r, gk = k0 + kk;
-                As[kk][r] = (gr < n && gk < K) ? A[gr + (long long)n * gk] : 0.0;
-            }
-        } else {
-            for (int t = tid; t < GT * GK; t += 128) {
-                int kk = t % GK, r = t / GK;
-                int gr = r0 + r, gk = k0 + kk;
-                As[kk][r] = (gr < n && gk < K) ? A[gk + (long long)n * gr] : 0.0;
-            }
-        }
-        if (!TB) {
-            for (int t = tid; t < GT * GK; t += 128) {
-                int kk = t % GK, c = t / GK;
-                int gc = c0 + c, gk = k0 + kk;
-                Bs[kk][c] = (gc < n && gk < K) ? B[gk + (long long)n * gc] : 0.0;
-            }
-        } else {
-            for (int t = tid; t < GT * GK; t += 128) {
-                int c = t % GT, kk = t / GT;
-                int gc = c0 + c, gk = k0 + kk;
-                Bs[kk][c] = (gc < n && gk < K) ? B[gc + (long long)n * gk] : 0.0;
-            }
-        }
+        stage();
         __syncthreads();
+        if (k0 + GK < K) fetch(k0 + GK);
 #pragma unroll
         for (int ks = 0; ks < GK; ks += 4) {
             double af[4], bf[4];
@@ -317,6 +323,24 @@ __device__ __forceinline__ void jb_block_pair(int step, int pr, int nb, int& P, 
     P = p < q ? p : q; Q = p < q ? q : p;
 }
 
+
+// 1/sqrt(x) for x in the normal float range: single-precision seed + two Newton steps (full double accuracy,
+// no special-case branches)
+__device__ __forceinline__ double jb_rsqrt(double x) {
+    double y = (double)rsqrtf((float)x);
+    const double h = 0.5 * x;
+    y = y * (1.5 - h * y * y);
+    y = y * (1.5 - h * y * y);
+    return y;
+}
+
+// release the two column blocks of a finished rotation to the warps that need them in the next tournament step
+__device__ __forceinline__ void jb_publish(volatile int* ver, int P, int Q, int v, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) { ver[P] = v; ver[Q] = v; }
+}
+
 constexpr int kJbInnerSweeps = 1;  // inner sweeps per Gram block (early exit when a sweep rotates nothing)
 constexpr int kJbScratch = 144;   // doubles of per-warp scratch: M[8][9], J[8][9]
 
@@ -358,6 +382,10 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
     double* Jsh = Msh + 72;
     __shared__ double red[32];
     __shared__ double s_sigma;
+    // ver[b] = number of tournament steps column block b has completed.  Warps synchronise on the two blocks they are
+    // about to rotate instead of a CTA-wide barrier per step, so the DMMA phases (Gram, apply) of some warps overlap
+    // the latency-bound inner solves of others.
+    __shared__ volatile int ver[64];
     const double* A = d.W + m.mat0;
     // Gershgorin bound -> shift that makes G positive definite
     double mx = 0.0;
@@ -392,8 +420,9 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
             G[t] = v;
         }
     }
+    if (tid < 64) ver[tid] = 0;
     __syncthreads();
-    const double tol = 8.0 * sqrt((double)n) * 2.220446049250313e-16;
+    const double tol = d.jb_tol > 0.0 ? d.jb_tol : 8.0 * sqrt((double)n) * 2.220446049250313e-16;
     const double tol2 = tol * tol;
     const double tol_in2 = 2.220446049250313e-16 * 2.220446049250313e-16;
     const int nbp = nb / 2;
@@ -408,13 +437,19 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
         pairtab |= (unsigned long long)(p | (q << 3)) << (6 * s7);
     }
     int sweep = 0;
+    int tstep = 0;     // tournament steps completed so far (all sweeps)
     for (; sweep < 40; ++sweep) {
         int rotated = 0;
-        for (int step = 0; step < nb - 1; ++step) {
+        for (int step = 0; step < nb - 1; ++step, ++tstep) {
             for (int pr = warp; pr < nbp; pr += nwarps) {
                 int P, Q;
                 jb_block_pair(step, pr, nb, P, Q);
-                if (4 * Q >= n) continue;                       // dummy block (all-zero columns)
+                // wait until both blocks have finished the previous step, work, then publish (see jb_publish)
+                if (lane == 0) { while (ver[P] < tstep || ver[Q] < tstep) {} }
+                __syncwarp();
+                __threadfence_block();
+                JB_T(5);
+                if (4 * Q >= n) { jb_publish(ver, P, Q, tstep + 1, lane); continue; }   // dummy block (all-zero columns)
                 JB_T(0);
                 // ---- Gram matrix of the 8 panel columns
                 const int gcol = l4 < 4 ? 4 * P + l4 : 4 * Q + l4 - 4;
@@ -441,7 +476,7 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
                     if (j0 != l4) need |= (m0 * m0 > tol2 * dii * Msh[j0 * 10]) ? 1 : 0;
                     if (j1 != l4) need |= (m1 * m1 > tol2 * dii * Msh[j1 * 10]) ? 1 : 0;
                 }
-                if (!__any_sync(0xffffffffu, need)) continue;
+                if (!__any_sync(0xffffffffu, need)) { jb_publish(ver, P, Q, tstep + 1, lane); continue; }
                 rotated = 1;
                 // ---- two-sided Jacobi on the 8x8 Gram matrix; lane = (pair slot, row/column index).
                 // A bounded number of inner sweeps is enough: the outer loop re-forms every Gram matrix, so the inner
@@ -458,9 +493,9 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
                             // rotation angle |theta| <= pi/4 from two reciprocal square roots (no divisions):
                             // cos 2t = |tau|/r, r = hypot(tau, 2 apq); c = sqrt((1 + cos 2t)/2); s = sgn(tau) apq/(r c)
                             const double tau = aqq - app;
-                            const double ir = rsqrt(tau * tau + 4.0 * apq * apq);
+                            const double ir = jb_rsqrt(tau * tau + 4.0 * apq * apq);
                             const double c2 = 0.5 + 0.5 * fabs(tau) * ir;
-                            const double ic = rsqrt(c2);
+                            const double ic = jb_rsqrt(c2);
                             c = c2 * ic;
                             s = (tau >= 0.0 ? apq : -apq) * ir * ic;
                             anyrot = 1;
@@ -507,11 +542,9 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
                             if (r0 + 8 * u < nr) { op[r0 + 8 * u] = y0[u]; op[r0 + 8 * u + ld] = y1[u]; }
                     }
                 }
+                jb_publish(ver, P, Q, tstep + 1, lane);
                 JB_T(3);
             }
-            JB_T(4);
-            __syncthreads();
-            JB_T(5);
         }
         if (!__syncthreads_or(rotated)) { ++sweep; break; }
     }
