@@ -74,6 +74,19 @@ def make_water_cluster(nwat, seed=3000, spacing=5.86):
     return Z, np.concatenate(xyz)
 
 
+def make_peptide_cluster(s, ncopy, gap=8.0):
+    """Stand-in for a protein-sized system (crambin coordinates are not available offline): ncopy copies
+    of the 76-atom peptide pdb-4qxx (test/unit/molstock.f90:739-909) on a cubic grid, `gap` bohr between bounding boxes."""
+    Z0 = np.asarray(s["numbers"], dtype=np.int32)
+    x0 = np.asarray(s["xyz"], dtype=np.float64).reshape(-1, 3)
+    x0 = x0 - x0.mean(axis=0)
+    ext = x0.max(axis=0) - x0.min(axis=0) + gap
+    m = int(np.ceil(ncopy ** (1 / 3)))
+    cells = [(a, b, c) for a in range(m) for b in range(m) for c in range(m)][:ncopy]
+    xyz = np.concatenate([x0 + np.array(c) * ext for c in cells])
+    return np.tile(Z0, ncopy), xyz
+
+
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     """Samples SM clock and throttle reasons with nvidia-smi while the timed region runs."""

@@ -286,3 +286,37 @@ def test_block_and_scalar_eigensolvers_agree(xb, kat, name):
     assert np.max(np.abs(r0["gradients"] - r1["gradients"])) < 1e-9
     assert np.max(np.abs(e0 - e1)) < 1e-9
     assert np.max(np.abs(p0 - p1)) < 1e-8
+
+
+@pytest.mark.parametrize("kind", ["water64", "peptide3"])
+def test_large_system_two_level_jacobi(xb, kat, kind):
+    """Matrices beyond the shared-memory solvers (two-level block Jacobi in HBM, overlap orthogonaliser from the
+    eigen-decomposition of S): same energies, gradients, charges and iteration count as the oracle."""
+    from bench import make_peptide_cluster, make_water_cluster
+    from oracle.oracle import Oracle
+    if kind == "water64":
+        Z, xyz = make_water_cluster(64)
+    else:
+        Z, xyz = make_peptide_cluster(kat["pdb_4qxx"], 3)
+    o = Oracle(Z, xyz)
+    assert o.singlepoint() == 0
+    b = xb.BatchCalculator([Z])
+    r = b.singlepoint(xyz)
+    assert r["all_converged"]
+    res = b.result(0)
+    assert abs(res["energy"] - o.energies["e_total"]) < E_TOL
+    assert np.max(np.abs(r["gradients"] - o.get("gradient").reshape(-1, 3))) < G_TOL
+    assert np.max(np.abs(r["charges"] - o.get("q"))) < Q_TOL
+    assert int(res["niter"]) == o.info["niter"]
+    cnt = b.counts(0)
+    assert (cnt["ndp"], cnt["nqp"]) == (o.info["ndp"], o.info["nqp"])
+
+
+def test_ensemble_runner_single_rank(xb, kat):
+    from xtb_b200.ensemble import EnsembleRunner
+    names = ["caffeine", "h2o_scc", "mindless01"]
+    numbers = [kat[n]["numbers"] for n in names]
+    pos = np.concatenate([kat[n]["xyz"] for n in names])
+    res = EnsembleRunner(numbers).singlepoint(pos)
+    ref = xb.BatchCalculator(numbers).singlepoint(pos)
+    assert np.array_equal(res["energies"], ref["energies"]) and np.array_equal(res["gradients"], ref["gradients"])

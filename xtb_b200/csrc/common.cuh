@@ -77,6 +77,9 @@ struct Dev {
     const long long* eeq0;
     // broyden
     double *bdf, *bu, *ba, *bbeta, *bomega, *bqlast, *bdqlast, *bqin, *bdq;
+    // two-level Jacobi (large matrices): G in HBM, per block pair Gram matrix / rotation, flags and counters
+    double *hjG, *hjM, *hjJ, *hj_sigma;
+    int *hj_flag, *hj_count, *hj_conv;
     // shell-pair gradient partials
     double *gpair;   // [npair][4] : gx,gy,gz,dCN
     const long long* pair0;

@@ -14,6 +14,7 @@
 #include "kernels_geom.cuh"
 #include "kernels_grad.cuh"
 #include "kernels_int.cuh"
+#include "kernels_hjacobi.cuh"
 #include "kernels_linalg.cuh"
 #include "kernels_scc.cuh"
 
@@ -96,6 +97,7 @@ struct Batch::Impl {
     int maxiter = 250;
     int guess = 0;
     int solver = 0;     // 0: automatic, 1: scalar one-sided Jacobi (k_jacobi) even where the block kernel fits
+    bool fits_blk = false, fits_scalar = false;
     size_t bytes = 0;
     // timing (ms) of the last single point
     float t_setup = 0, t_scc = 0, t_grad = 0;
@@ -212,6 +214,18 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         d.bomega = I.dalloc<double>((size_t)nmol * maxhist);
         d.bqlast = I.dalloc<double>((size_t)s.tot_q); d.bdqlast = I.dalloc<double>((size_t)s.tot_q);
         d.bqin = I.dalloc<double>((size_t)s.tot_q); d.bdq = I.dalloc<double>((size_t)s.tot_q);
+        // solver selection by the largest matrix of the batch: shared-memory kernels when it fits, two-level Jacobi else
+        {
+            const int jbw = std::max(1, std::min(20, jb_dims(s.max_nao).nb / 2));
+            I.fits_blk = jb_smem_bytes(s.max_nao, jbw) <= (size_t)(227 * 1024 - 1024);
+            I.fits_scalar = (size_t)s.max_nao * (s.max_nao | 1) * sizeof(double) <= (size_t)(227 * 1024 - 4096);
+        }
+        if (!I.fits_blk || !I.fits_scalar) {
+            d.hjG = I.dalloc<double>(tm);
+            d.hjM = I.dalloc<double>((size_t)s.tot_hj); d.hjJ = I.dalloc<double>((size_t)s.tot_hj);
+            d.hj_flag = I.dalloc<int>((size_t)(s.tot_hj / (128 * 128)));
+            d.hj_count = I.dalloc<int>(nmol); d.hj_conv = I.dalloc<int>(nmol); d.hj_sigma = I.dalloc<double>(nmol);
+        }
         I.d_active = I.dalloc<int>(1);
         I.h_state.resize(nmol);
         XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
@@ -219,6 +233,8 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         const int smax = 227 * 1024 - 2048;
         cudaFuncSetAttribute(k_chol_inv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_jacobi_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        cudaFuncSetAttribute(k_hj_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        cudaFuncSetAttribute(k_hj_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, HP * GLD * (int)sizeof(double));
         cudaFuncSetAttribute(k_jacobi<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_jacobi<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_jacobi<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
@@ -349,11 +365,41 @@ int Batch::singlepoint(bool restart) {
     KL(K_SDQH0, k_sdqh0<<<grid2(max_pairs, kIntWarps, nmol), kIntWarps * 32, 0, st>>>(d));
     const long long nn2 = (long long)s.max_nao * s.max_nao;
     KL(K_DQMASK, k_dqmask<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
-    // ---- overlap factorisation
-    const size_t chol_bytes = (size_t)s.max_nao * (s.max_nao | 1) * sizeof(double);
-    const bool sm = chol_bytes <= (size_t)(227 * 1024 - 4096);
-    if (sm) KL(K_CHOL, k_chol_inv<true><<<nmol, 512, chol_bytes, st>>>(d));
-    else KL(K_CHOL, k_chol_inv<false><<<nmol, 512, 0, st>>>(d));
+    // ---- solver selection and overlap factorisation
+    const bool use_blk = I.fits_blk && I.solver != 1;             // block Jacobi, matrix in shared memory
+    const bool use_scalar = !use_blk && I.fits_scalar;            // scalar Jacobi, matrix in shared memory
+    const bool hier = !use_blk && !use_scalar;                    // two-level Jacobi, matrix in HBM
+    const bool sm = true;
+    const int hj_nb = hj_nblocks(s.max_nao), hj_nbp = hj_nb / 2, hj_rt = (s.max_nao + GT - 1) / GT;
+    const size_t hj_inner_bytes = jb_smem_bytes(HP, kHjInnerWarps), hj_apply_bytes = (size_t)HP * GLD * sizeof(double);
+    // eigen-decomposition of Asrc (+ warm start from Zm when allowed) by the two-level block Jacobi: Zm, emo
+    auto hjacobi = [&](const double* Asrc, int allow_warm, int kid) {
+        KL(kid, k_hj_begin<<<(nmol + 127) / 128, 128, 0, st>>>(d));
+        KL(kid, k_hj_sigma<<<nmol, 256, 0, st>>>(d, Asrc));
+        KL(kid, k_hj_load<<<grid2((long long)s.max_nao * s.max_nao, 256, nmol), 256, 0, st>>>(d, Asrc, allow_warm));
+        int sweep = 0, still = 1;
+        for (; sweep < 40 && still; ++sweep) {
+            for (int step = 0; step < hj_nb - 1; ++step) {
+                KL(kid, k_hj_gram<<<dim3(4, hj_nbp, nmol), 128, 0, st>>>(d, step));
+                KL(kid, k_hj_inner<<<dim3(hj_nbp, nmol), 32 * kHjInnerWarps, hj_inner_bytes, st>>>(d, step));
+                KL(kid, k_hj_apply<<<dim3(hj_rt, hj_nbp, nmol), 128, hj_apply_bytes, st>>>(d, step));
+            }
+            XTB_CUDA_CHECK(cudaMemsetAsync(I.d_active, 0, sizeof(int), st));
+            KL(kid, k_hj_sweep_end<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.d_active));
+            XTB_CUDA_CHECK(cudaMemcpyAsync(&still, I.d_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            XTB_CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+        KL(kid, k_hj_norms<<<grid2((long long)s.max_nao * 32, 256, nmol), 256, 0, st>>>(d));
+        KL(kid, k_hj_rank<<<grid2(s.max_nao, 128, nmol), 128, 0, st>>>(d));
+        KL(kid, k_hj_write<<<grid2((long long)s.max_nao * s.max_nao, 256, nmol), 256, 0, st>>>(d, still ? 1 : 0));
+    };
+    if (!hier) {
+        const size_t chol_bytes = (size_t)s.max_nao * (s.max_nao | 1) * sizeof(double);
+        KL(K_CHOL, k_chol_inv<true><<<nmol, 512, chol_bytes, st>>>(d));
+    } else {
+        hjacobi(d.S, 0, K_CHOL);                                  // S = V s V^T
+        KL(K_CHOL, k_hj_xscale<<<grid2((long long)s.max_nao * s.max_nao, 256, nmol), 256, 0, st>>>(d));   // X = V s^-1/2
+    }
     cudaEventRecord(ev[1], st);
     // ---- SCC iterations
     const int tiles = (s.max_nao + GT - 1) / GT;
@@ -362,7 +408,6 @@ int Batch::singlepoint(bool restart) {
     // ensemble-sized matrices: block Jacobi on the FP64 tensor path, matrix resident in shared memory
     const int jb_warps = std::max(1, std::min(20, jb_dims(s.max_nao).nb / 2));   // k_jacobi_blk: __launch_bounds__(640)
     const size_t jb_bytes = jb_smem_bytes(s.max_nao, jb_warps);
-    const bool jb = jb_bytes <= (size_t)(227 * 1024 - 1024) && I.solver != 1;
     int active = nmol;
     int iters = 0;
     for (int it = 0; it < I.maxiter && active > 0; ++it) {
@@ -376,7 +421,8 @@ int Batch::singlepoint(bool restart) {
         KL(K_GEMM_XHX, k_gemm<true, false><<<ggrid, 128, 0, st>>>(d, d.X, d.T, d.W, 0, 1));       // W = X^T T
         if (it > 0 || (restart && I.have_wfn))
             KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.W, d.Zm, d.T, 0, 2));   // T = A' Z_prev
-        if (jb) KL(K_JACOBI, k_jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d));
+        if (use_blk) KL(K_JACOBI, k_jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d));
+        else if (hier) hjacobi(d.W, 1, K_JACOBI);
         else if (npairs * 32 <= 1024) KL(K_JACOBI, launch_jacobi<32>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 16 <= 1024) KL(K_JACOBI, launch_jacobi<16>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 8 <= 1024) KL(K_JACOBI, launch_jacobi<8>(d, nmol, s.max_nao, sm, st));

@@ -364,65 +364,20 @@ inline size_t jb_smem_bytes(int n, int nwarps) {
 #else
 #define JB_T(k)
 #endif
-__global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
+// The sweep loop of the block Jacobi solver on a matrix G resident in shared memory (layout of jb_dims(n)); every
+// thread of the CTA calls it.  Msh: this warp's 8x9 + 8x9 scratch; ver: 64 ints of shared memory.  Returns the number
+// of sweeps executed (the last one is the verification sweep when converged; == maxsweeps means not converged).
+__device__ __forceinline__ int jb_sweeps(double* G, double* Msh, volatile int* ver, int n, double tol, int inner, int maxsweeps
 #ifdef XTBB200_JB_TIMING
-    long long jbt[6] = {0, 0, 0, 0, 0, 0}, jbt0 = clock64();
+                                         , long long* jbt, long long& jbt0
 #endif
-    const int im = blockIdx.x;
-    const MolDesc m = d.mol[im];
-    MolState& st = d.st[im];
-    if (st.done) return;
-    const int n = m.nao;
+) {
     const JbDims dm = jb_dims(n);
     const int nr = dm.nr, ld = dm.ld, nb = dm.nb;
-    extern __shared__ double smem[];
-    double* G = smem;
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-    double* Msh = smem + (size_t)ld * nb * 4 + (size_t)warp * kJbScratch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     double* Jsh = Msh + 72;
-    __shared__ double red[32];
-    __shared__ double s_sigma;
-    // ver[b] = number of tournament steps column block b has completed.  Warps synchronise on the two blocks they are
-    // about to rotate instead of a CTA-wide barrier per step, so the DMMA phases (Gram, apply) of some warps overlap
-    // the latency-bound inner solves of others.
-    __shared__ volatile int ver[64];
-    const double* A = d.W + m.mat0;
-    // Gershgorin bound -> shift that makes G positive definite
-    double mx = 0.0;
-    for (int i = tid; i < n; i += nt) {
-        double s = 0;
-        for (int j = 0; j < n; ++j) s += fabs(A[i + (long long)n * j]);
-        mx = fmax(mx, s);
-    }
-    mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    if (tid == 0) {
-        double v = 0;
-        for (int w = 0; w < nwarps; ++w) v = fmax(v, red[w]);
-        s_sigma = 1.05 * v + 1.0;
-    }
-    __syncthreads();
-    const double sigma = s_sigma;
-    const int ncolp = nb * 4;
-    const bool warm = st.zvalid != 0;
-    {
-        const double* T = d.T + m.mat0;
-        const double* Zp = d.Zm + m.mat0;
-        for (int t = tid; t < ld * ncolp; t += nt) {
-            const int i = t % ld, j = t / ld;
-            double v = 0.0;
-            if (i < n && j < n) {
-                const long long a = i + (long long)n * j;
-                if (warm) v = T[a] + sigma * Zp[a];
-                else v = 0.5 * (A[a] + A[j + (long long)n * i]) + (i == j ? sigma : 0.0);
-            }
-            G[t] = v;
-        }
-    }
     if (tid < 64) ver[tid] = 0;
     __syncthreads();
-    const double tol = d.jb_tol > 0.0 ? d.jb_tol : 8.0 * sqrt((double)n) * 2.220446049250313e-16;
     const double tol2 = tol * tol;
     const double tol_in2 = 2.220446049250313e-16 * 2.220446049250313e-16;
     const int nbp = nb / 2;
@@ -438,7 +393,7 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
     }
     int sweep = 0;
     int tstep = 0;     // tournament steps completed so far (all sweeps)
-    for (; sweep < 40; ++sweep) {
+    for (; sweep < maxsweeps; ++sweep) {
         int rotated = 0;
         for (int step = 0; step < nb - 1; ++step, ++tstep) {
             for (int pr = warp; pr < nbp; pr += nwarps) {
@@ -482,7 +437,7 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
                 // A bounded number of inner sweeps is enough: the outer loop re-forms every Gram matrix, so the inner
                 // solve only sets the convergence rate, never the final accuracy.  M and J have row stride 9
                 // (conflict-free column access).
-                for (int isw = 0; isw < d.jb_inner; ++isw) {
+                for (int isw = 0; isw < inner; ++isw) {
                     int anyrot = 0;
 #pragma unroll
                     for (int s7 = 0; s7 < 7; ++s7) {
@@ -548,6 +503,71 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
         }
         if (!__syncthreads_or(rotated)) { ++sweep; break; }
     }
+    return sweep;
+}
+
+__global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
+#ifdef XTBB200_JB_TIMING
+    long long jbt[6] = {0, 0, 0, 0, 0, 0}, jbt0 = clock64();
+#endif
+    const int im = blockIdx.x;
+    const MolDesc m = d.mol[im];
+    MolState& st = d.st[im];
+    if (st.done) return;
+    const int n = m.nao;
+    const JbDims dm = jb_dims(n);
+    const int nr = dm.nr, ld = dm.ld, nb = dm.nb;
+    extern __shared__ double smem[];
+    double* G = smem;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    double* Msh = smem + (size_t)ld * nb * 4 + (size_t)warp * kJbScratch;
+    double* Jsh = Msh + 72;
+    __shared__ double red[32];
+    __shared__ double s_sigma;
+    // ver[b] = number of tournament steps column block b has completed.  Warps synchronise on the two blocks they are
+    // about to rotate instead of a CTA-wide barrier per step, so the DMMA phases (Gram, apply) of some warps overlap
+    // the latency-bound inner solves of others.
+    __shared__ volatile int ver[64];
+    const double* A = d.W + m.mat0;
+    // Gershgorin bound -> shift that makes G positive definite
+    double mx = 0.0;
+    for (int i = tid; i < n; i += nt) {
+        double s = 0;
+        for (int j = 0; j < n; ++j) s += fabs(A[i + (long long)n * j]);
+        mx = fmax(mx, s);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        double v = 0;
+        for (int w = 0; w < nwarps; ++w) v = fmax(v, red[w]);
+        s_sigma = 1.05 * v + 1.0;
+    }
+    __syncthreads();
+    const double sigma = s_sigma;
+    const int ncolp = nb * 4;
+    const bool warm = st.zvalid != 0;
+    {
+        const double* T = d.T + m.mat0;
+        const double* Zp = d.Zm + m.mat0;
+        for (int t = tid; t < ld * ncolp; t += nt) {
+            const int i = t % ld, j = t / ld;
+            double v = 0.0;
+            if (i < n && j < n) {
+                const long long a = i + (long long)n * j;
+                if (warm) v = T[a] + sigma * Zp[a];
+                else v = 0.5 * (A[a] + A[j + (long long)n * i]) + (i == j ? sigma : 0.0);
+            }
+            G[t] = v;
+        }
+    }
+    const double tol = d.jb_tol > 0.0 ? d.jb_tol : 8.0 * sqrt((double)n) * 2.220446049250313e-16;
+#ifdef XTBB200_JB_TIMING
+    const int sweep = jb_sweeps(G, Msh, ver, n, tol, d.jb_inner, 40, jbt, jbt0);
+#else
+    const int sweep = jb_sweeps(G, Msh, ver, n, tol, d.jb_inner, 40);
+#endif
     // eigenvalues, ordering, normalised eigenvectors
     double* nrm = d.nrm + m.ao0;
     for (int j = tid; j < n; j += nt) {

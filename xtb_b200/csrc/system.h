@@ -38,6 +38,7 @@ struct MolDesc {
     long long dd0;                  // ndim*ndim matrices
     long long br0;                  // Broyden history (maxhist*nbr)
     long long q0;                   // Broyden vector offset (nbr)
+    long long hj0;                  // two-level Jacobi: first panel Gram matrix (128*128 doubles per block pair)
     double charge;
 };
 
@@ -178,7 +179,7 @@ struct BatchSystem {
     std::vector<int> ao2sh, ao2at;      // per AO (indices within molecule)
     std::vector<int> etypes;            // element numbers of the dense types
     std::vector<double> c6ref;          // [ntype][ntype][7][7]
-    long long tot_mat = 0, tot_nn = 0, tot_ss = 0, tot_dd = 0, tot_br = 0, tot_q = 0;
+    long long tot_mat = 0, tot_nn = 0, tot_ss = 0, tot_dd = 0, tot_br = 0, tot_q = 0, tot_hj = 0;
     int max_nat = 0, max_nsh = 0, max_nao = 0, max_ndim = 0, max_nbr = 0;
     int maxhist = 0;
 
@@ -265,6 +266,12 @@ struct BatchSystem {
         m.dd0 = tot_dd; tot_dd += (long long)ndim * ndim;
         m.br0 = tot_br; tot_br += (long long)maxhist * m.nbr;
         m.q0 = tot_q; tot_q += m.nbr;
+        {
+            int nb64 = (nao + 63) / 64;
+            if (nb64 & 1) nb64++;
+            if (nb64 < 2) nb64 = 2;
+            m.hj0 = tot_hj; tot_hj += (long long)(nb64 / 2) * 128 * 128;
+        }
         max_nat = std::max(max_nat, nat); max_nsh = std::max(max_nsh, nsh); max_nao = std::max(max_nao, nao);
         max_ndim = std::max(max_ndim, ndim); max_nbr = std::max(max_nbr, m.nbr);
         mol.push_back(m);
