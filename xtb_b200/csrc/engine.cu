@@ -234,6 +234,7 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         cudaFuncSetAttribute(k_chol_inv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_jacobi_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_hj_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        cudaFuncSetAttribute(k_grad_atm, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_hj_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, HP * GLD * (int)sizeof(double));
         cudaFuncSetAttribute(k_jacobi<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_jacobi<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
@@ -354,7 +355,16 @@ int Batch::singlepoint(bool restart) {
     if (!(restart && I.have_wfn)) {
         if (I.guess == 0) {
             KL(K_EEQ, k_eeq_build<<<grid2((long long)(s.max_nat + 1) * (s.max_nat + 2), 256, nmol), 256, 0, st>>>(d));
-            KL(K_EEQ, k_eeq_solve<<<nmol, 256, 0, st>>>(d));
+            if (s.max_nat <= 320) {
+                KL(K_EEQ, k_eeq_solve<<<nmol, 256, 0, st>>>(d));
+            } else {   // large molecules: the same elimination spread over the GPU, two launches per column
+                for (int k = 0; k < s.max_nat + 1; ++k) {
+                    KL(K_EEQ, k_eeq_pivot<<<nmol, 1024, 0, st>>>(d, k));
+                    const long long el = (long long)(s.max_nat - k) * (s.max_nat + 1 - k);
+                    if (el > 0) KL(K_EEQ, k_eeq_elim<<<grid2(el, 256, nmol), 256, 0, st>>>(d, k));
+                }
+                KL(K_EEQ, k_eeq_finish<<<nmol, 1024, 0, st>>>(d));
+            }
         } else {
             KL(K_EEQ, k_guess_uniform<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
         }
@@ -455,7 +465,7 @@ int Batch::singlepoint(bool restart) {
     KL(K_GRAD_D4, k_d4_weights<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
     KL(K_GRAD_D4, k_d4_c6<<<grid2((long long)s.max_nat * s.max_nat, 128, nmol), 128, 0, st>>>(d));
     KL(K_GRAD_D4, k_grad_pairs<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
-    KL(K_GRAD_ATM, k_grad_atm<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+    KL(K_GRAD_ATM, k_grad_atm<<<dim3(s.max_nat, nmol), 128, (size_t)s.max_nat * sizeof(double), st>>>(d));
     KL(K_GRAD_MISC, k_grad_cn<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
     // ---- properties: bond orders and dipole
     bool any_open = false;

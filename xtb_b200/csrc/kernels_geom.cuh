@@ -233,6 +233,31 @@ __global__ void k_eeq_build(Dev d) {
     A[i + (long long)n1 * j] = v;
 }
 
+// back substitution on the eliminated augmented system and the charge guess derived from it (one CTA)
+__device__ __forceinline__ void eeq_backsub_and_guess(Dev& d, const MolDesc& m, double* A, int n1) {
+    // back substitution (serial in k, parallel in rows)
+    double* x = A + (long long)n1 * n1;
+    for (int k = n1 - 1; k >= 0; --k) {
+        if (threadIdx.x == 0) x[k] = x[k] / A[k + (long long)n1 * k];
+        __syncthreads();
+        double xk = x[k];
+        for (int i = threadIdx.x; i < k; i += blockDim.x) x[i] -= A[i + (long long)n1 * k] * xk;
+        __syncthreads();
+    }
+    // charges -> shell charges by reference-occupation fractions; multipoles start at zero
+    for (int i = threadIdx.x; i < m.nat; i += blockDim.x) {
+        const AtomPar& a = d.atoms[m.at0 + i];
+        double qi = x[i];
+        d.q[m.at0 + i] = qi;
+        for (int s = 0; s < a.nsh; ++s) {
+            const ShellPar& sp = d.shells[m.sh0 + a.sh0 + s];
+            d.qsh[m.sh0 + a.sh0 + s] = sp.refocc / a.zval * qi;
+        }
+        for (int k = 0; k < 3; ++k) d.dipm[3 * (m.at0 + i) + k] = 0.0;
+        for (int k = 0; k < 6; ++k) d.qp[6 * (m.at0 + i) + k] = 0.0;
+    }
+}
+
 // Gaussian elimination with partial pivoting on the augmented system (one CTA per molecule).
 // Replaces the dsysv call of src/eeq_model.f90:858-862; then iniqshell (scc_core.f90:1475-1506).
 __global__ void k_eeq_solve(Dev d) {
@@ -282,27 +307,64 @@ __global__ void k_eeq_solve(Dev d) {
         }
         __syncthreads();
     }
-    // back substitution (serial in k, parallel in rows)
-    double* x = A + (long long)n1 * n1;
-    for (int k = n1 - 1; k >= 0; --k) {
-        if (threadIdx.x == 0) x[k] = x[k] / A[k + (long long)n1 * k];
-        __syncthreads();
-        double xk = x[k];
-        for (int i = threadIdx.x; i < k; i += blockDim.x) x[i] -= A[i + (long long)n1 * k] * xk;
-        __syncthreads();
+    eeq_backsub_and_guess(d, m, A, n1);
+}
+
+// ---- the same elimination for large molecules, spread over the GPU: per column one pivot kernel (one CTA per
+// molecule: search + row swap) and one elimination kernel (thread per trailing element).  Same arithmetic and pivoting
+// as k_eeq_solve, so both give identical charges.
+__global__ void __launch_bounds__(1024) k_eeq_pivot(Dev d, int k) {
+    const MolDesc m = d.mol[blockIdx.x];
+    const int n1 = m.nat + 1, nc = n1 + 1;
+    if (k >= n1) return;
+    double* A = d.eeqA + d.eeq0[blockIdx.x];
+    __shared__ int s_piv;
+    __shared__ double s_red[32];
+    __shared__ int s_idx[32];
+    double best = -1.0; int bi = k;
+    for (int i = k + threadIdx.x; i < n1; i += blockDim.x) {
+        double v = fabs(A[i + (long long)n1 * k]);
+        if (v > best) { best = v; bi = i; }
     }
-    // charges -> shell charges by reference-occupation fractions; multipoles start at zero
-    for (int i = threadIdx.x; i < m.nat; i += blockDim.x) {
-        const AtomPar& a = d.atoms[m.at0 + i];
-        double qi = x[i];
-        d.q[m.at0 + i] = qi;
-        for (int s = 0; s < a.nsh; ++s) {
-            const ShellPar& sp = d.shells[m.sh0 + a.sh0 + s];
-            d.qsh[m.sh0 + a.sh0 + s] = sp.refocc / a.zval * qi;
+    for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        double b = s_red[0]; int ix = s_idx[0];
+        for (int w = 1; w < nw; ++w) if (s_red[w] > b || (s_red[w] == b && s_idx[w] < ix)) { b = s_red[w]; ix = s_idx[w]; }
+        s_piv = ix;
+        if (b == 0.0) d.st[blockIdx.x].fail = 10;
+    }
+    __syncthreads();
+    const int p = s_piv;
+    if (p != k)
+        for (int j = k + threadIdx.x; j < nc; j += blockDim.x) {
+            double t = A[k + (long long)n1 * j];
+            A[k + (long long)n1 * j] = A[p + (long long)n1 * j];
+            A[p + (long long)n1 * j] = t;
         }
-        for (int k = 0; k < 3; ++k) d.dipm[3 * (m.at0 + i) + k] = 0.0;
-        for (int k = 0; k < 6; ++k) d.qp[6 * (m.at0 + i) + k] = 0.0;
-    }
+}
+__global__ void k_eeq_elim(Dev d, int k) {
+    const MolDesc m = d.mol[blockIdx.y];
+    const int n1 = m.nat + 1, nc = n1 + 1;
+    if (k >= n1) return;
+    const int nr = n1 - k - 1, ncol = nc - k - 1;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)nr * ncol) return;
+    double* A = d.eeqA + d.eeq0[blockIdx.y];
+    const double pinv = 1.0 / A[k + (long long)n1 * k];
+    const int i = k + 1 + (int)(t % nr), j = k + 1 + (int)(t / nr);
+    const double f = A[i + (long long)n1 * k] * pinv;
+    A[i + (long long)n1 * j] -= f * A[k + (long long)n1 * j];
+}
+__global__ void __launch_bounds__(1024) k_eeq_finish(Dev d) {
+    const MolDesc m = d.mol[blockIdx.x];
+    eeq_backsub_and_guess(d, m, d.eeqA + d.eeq0[blockIdx.x], m.nat + 1);
 }
 
 }  // namespace xtbb200

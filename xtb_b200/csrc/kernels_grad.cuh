@@ -427,28 +427,35 @@ __global__ void k_grad_pairs(Dev d) {
 }
 
 // Axilrod-Teller-Muto three-body term with neutral reference weights (atm_gradient_latp,
-// deriv_atm_triple): thread per atom a, loops over partner pairs (b < c); each triple is visited
-// from its three atoms, every thread accumulates only its own gradient / dE/dCN (no atomics).
-__global__ void k_grad_atm(Dev d) {
+// deriv_atm_triple): one CTA per atom a, threads over partner pairs (b strided over the CTA, c < b); each triple is
+// visited from its three atoms, every CTA accumulates only its own gradient / dE/dCN and reduces in a fixed order
+// (no atomics).  dynamic shared memory: nat doubles (row a of dC6/dCN, strided in HBM).
+__global__ void __launch_bounds__(128) k_grad_atm(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = blockIdx.x;
     if (a >= m.nat) return;
+    extern __shared__ double s_dc6a[];
+    __shared__ double red[32];
     const double* xyz = d.xyz + 3 * m.at0;
     const double ra[3] = {xyz[3 * a], xyz[3 * a + 1], xyz[3 * a + 2]};
     const double r4a = d.atoms[m.at0 + a].r4r2;
     const double* c60 = d.c60 + m.nn0;
     const double* dc60 = d.dc60 + m.nn0;
     const int n = m.nat;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) s_dc6a[c] = dc60[a + (long long)n * c];
+    __syncthreads();
+    const double* c6a = c60 + (long long)n * a;     // C6(a, .) ; the matrix is symmetric
     double g[3] = {0, 0, 0}, dcn = 0, e3 = 0;
-    for (int b = 0; b < n; ++b) {
+    for (int b = threadIdx.x; b < n; b += blockDim.x) {
         if (b == a) continue;
         const double rij[3] = {xyz[3 * b] - ra[0], xyz[3 * b + 1] - ra[1], xyz[3 * b + 2] - ra[2]};
         const double r2ij = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
         if (r2ij > 1600.0) continue;
         const double r4b = d.atoms[m.at0 + b].r4r2;
-        const double c6ij = c60[a + (long long)n * b];
+        const double c6ij = c6a[b];
         const double cij = 0.52 * sqrt(3.0 * r4a * r4b) + 5.0;
-        const double dc6ij = dc60[a + (long long)n * b];
+        const double dc6ij = s_dc6a[b];
+        const double* c6b = c60 + (long long)n * b;
         for (int c = 0; c < b; ++c) {
             if (c == a) continue;
             const double rik[3] = {xyz[3 * c] - ra[0], xyz[3 * c + 1] - ra[1], xyz[3 * c + 2] - ra[2]};
@@ -458,7 +465,7 @@ __global__ void k_grad_atm(Dev d) {
             const double r2jk = rjk[0] * rjk[0] + rjk[1] * rjk[1] + rjk[2] * rjk[2];
             if (r2jk > 1600.0) continue;
             const double r4c = d.atoms[m.at0 + c].r4r2;
-            const double c6ik = c60[a + (long long)n * c], c6jk = c60[b + (long long)n * c];
+            const double c6ik = c6a[c], c6jk = c6b[c];
             const double cik = 0.52 * sqrt(3.0 * r4a * r4c) + 5.0, cjk = 0.52 * sqrt(3.0 * r4b * r4c) + 5.0;
             const double c9 = -sqrt(c6ij * c6ik * c6jk);
             const double ccc1 = cij * cjk * cik;
@@ -480,12 +487,17 @@ __global__ void k_grad_atm(Dev d) {
             const double scale = 5.0;   // s9
             for (int k = 0; k < 3; ++k) g[k] += (-dGr1 * rij[k] - dGr2 * rik[k]) * scale;
             e3 += dE * scale / 3.0;
-            dcn += -ang * fdmp * (0.5 * c9 * (dc6ij / c6ij + dc60[a + (long long)n * c] / c6ik)) * scale;
+            dcn += -ang * fdmp * (0.5 * c9 * (dc6ij / c6ij + s_dc6a[c] / c6ik)) * scale;
         }
     }
-    for (int k = 0; k < 3; ++k) d.grad[3 * (m.at0 + a) + k] += g[k];
-    d.dEdcn[m.at0 + a] += dcn;
-    d.e_atom[4 * (m.at0 + a) + 2] = e3;
+    for (int k = 0; k < 3; ++k) g[k] = block_sum(g[k], red);
+    dcn = block_sum(dcn, red);
+    e3 = block_sum(e3, red);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 3; ++k) d.grad[3 * (m.at0 + a) + k] += g[k];
+        d.dEdcn[m.at0 + a] += dcn;
+        d.e_atom[4 * (m.at0 + a) + 2] = e3;
+    }
 }
 
 // CN chain rule: g_i += sum_j dCN-pair(i,j) * (v_i + v_j) for the gfn CN (v = dE/dCN from H0 + AES radii)
