@@ -32,6 +32,12 @@ void xtbb200_delBatch(xtbb200_TBatch* batch);
  * xtb_setMaxIter); guess: 0 = EEQ charges (reference default), 1 = uniform charges */
 int xtbb200_setOptions(xtbb200_TBatch batch, double accuracy, double etemp, int maxiter, int guess);
 
+/* Restart wavefunction of the whole batch (the reference's chk%wfn: shell charges qsh[nshell], atomic dipoles
+ * dipm[natoms][3], quadrupoles qp[natoms][6], concatenated over molecules; src/type/restart.F90, used as SCC start by
+ * src/scf_module.F90 when restart is requested).  NULL pointers drop the stored wavefunction (next call starts from
+ * the EEQ guess).  The converged values are read back with xtbb200_getArray("qsh" | "dipm" | "qp"). */
+int xtbb200_setWavefunction(xtbb200_TBatch batch, const double* qsh, const double* dipm, const double* qp);
+
 /* eigensolver selection: 0 = automatic (block Jacobi on the FP64 tensor path when the matrix fits in shared memory),
  * 1 = scalar one-sided Jacobi.  Both give the same spectrum to rounding; used by the parity tests. */
 int xtbb200_setSolver(xtbb200_TBatch batch, int mode);

@@ -434,6 +434,14 @@ int xtbb200_setOptions(xtbb200_TBatch batch, double accuracy, double etemp, int 
     return 0;
     XTBB_CATCH(-1)
 }
+int xtbb200_setWavefunction(xtbb200_TBatch batch, const double* qsh, const double* dipm, const double* qp) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    if (!qsh || !dipm || !qp) { batch->b->invalidate_wavefunction(); return 0; }
+    batch->b->set_wavefunction(qsh, dipm, qp);
+    return 0;
+    XTBB_CATCH(-1)
+}
 int xtbb200_setSolver(xtbb200_TBatch batch, int mode) {
     XTBB_TRY
     if (!batch) throw std::runtime_error("batch is not allocated");

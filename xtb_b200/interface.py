@@ -69,6 +69,7 @@ def load_library():
         "xtbb200_delBatch": (None, [ctypes.POINTER(vp)]),
         "xtbb200_setOptions": (ci, [vp, cd, cd, ci, ci]),
         "xtbb200_setSolver": (ci, [vp, ci]),
+        "xtbb200_setWavefunction": (ci, [vp, _c_double_p, _c_double_p, _c_double_p]),
         "xtbb200_singlepoint": (ci, [vp, _c_double_p, ci, _c_double_p, _c_double_p, _c_double_p, _c_int_p, _c_int_p]),
         "xtbb200_singlepointDevice": (ci, [vp, vp, ci, vp]),
         "xtbb200_getNMol": (ci, [vp]), "xtbb200_getSizes": (ci, [vp, ci, _c_int_p, _c_int_p, _c_int_p]),
@@ -359,6 +360,14 @@ class BatchCalculator:
     def set_options(self, accuracy=1.0, etemp=300.0, maxiter=250, guess="eeq"):
         self._check(self._lib.xtbb200_setOptions(self._b, float(accuracy), float(etemp), int(maxiter),
                                                  {"eeq": 0, "sad": 1}[guess]))
+
+    def set_wavefunction(self, qsh=None, dipm=None, qp=None):
+        """Restart wavefunction for the next singlepoint(restart=True); None drops the stored one."""
+        if qsh is None:
+            self._check(self._lib.xtbb200_setWavefunction(self._b, None, None, None))
+            return
+        a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (qsh, dipm, qp))
+        self._check(self._lib.xtbb200_setWavefunction(self._b, _dp(a), _dp(b), _dp(c)))
 
     def set_solver(self, mode):
         """0: automatic, 1: scalar Jacobi kernel."""
