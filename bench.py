@@ -341,7 +341,7 @@ def run_engine(args):
 
     # -- CPU baseline on a bounded sample of the same workload
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # reported at N=1 only
         from oracle.oracle import build
         build()
         cores = host_cores()
