@@ -42,6 +42,23 @@ int xtbb200_setWavefunction(xtbb200_TBatch batch, const double* qsh, const doubl
  * 1 = scalar one-sided Jacobi.  Both give the same spectrum to rounding; used by the parity tests. */
 int xtbb200_setSolver(xtbb200_TBatch batch, int mode);
 
+/* Split of ONE large system over the GPUs of a box (one process per GPU; every process creates the SAME batch on its
+ * own device).  The shell-pair blocks of the integral build (build_SDQH0, src/xtb/hamiltonian.F90:261-412) and of its
+ * derivative (build_dSDQH0, :575-792) are dealt to the ranks CTA by CTA, the per-atom gradient terms (AES, D4 two- and
+ * three-body, Coulomb derivative, CN chain rule) in chunks of 32 atoms; the contributions are summed with NCCL
+ * allreduce over NVLink: S/D/Q/H0 (12 n^2 doubles, disjoint blocks: bit-identical to one GPU), the dE/dCN vectors
+ * (4 N) and the gradient (3 N).  The SCC iterations, i.e. the eigensolver, run replicated on every rank (they stay on
+ * one GPU by design), so every rank ends with the complete result.
+ *   xtbb200_shardUniqueId: rank 0 creates the 128-byte NCCL id; the caller ships it to the other ranks (MPI,
+ *                          torch.distributed, a file ...).
+ *   xtbb200_setShard:      collective over all ranks; nranks == 1 switches the split off again.
+ *   xtbb200_shardOwner:    ownership rule (pure function): kind 0 = atom index, kind 1 = shell-pair CTA index. */
+int xtbb200_shardUniqueId(char* id128, size_t len);
+int xtbb200_setShard(xtbb200_TBatch batch, int rank, int nranks, const char* id128, size_t len);
+int xtbb200_shardOwner(int kind, long long index, int nranks);
+/* device time [ms] spent in the exchanges of the last call (0 when not split) */
+int xtbb200_getCommTime(xtbb200_TBatch batch, float* ms);
+
 /* GFN2-xTB single point + gradient for every molecule of the batch (batched xtb_singlepoint).
  * positions: concatenated [natoms][3] in Bohr (host memory). restart != 0 reuses the converged
  * wavefunction of the previous call as SCC start (src/api/interface.f90:82-101).

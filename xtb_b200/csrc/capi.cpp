@@ -449,6 +449,34 @@ int xtbb200_setSolver(xtbb200_TBatch batch, int mode) {
     return 0;
     XTBB_CATCH(-1)
 }
+int xtbb200_shardUniqueId(char* id128, size_t len) {
+    XTBB_TRY
+    if (!id128 || len < 128) throw std::runtime_error("need a 128-byte buffer for the NCCL unique id");
+    xtbb200::shard_unique_id(id128);
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_setShard(xtbb200_TBatch batch, int rank, int nranks, const char* id128, size_t len) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    if (nranks > 1 && (!id128 || len < 128)) throw std::runtime_error("need the 128-byte NCCL unique id of rank 0");
+    batch->b->set_shard(rank, nranks, id128);
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_shardOwner(int kind, long long index, int nranks) {
+    if (nranks < 1 || index < 0) return -1;
+    if (kind == 0) return xtbb200::shard_atom_owner_host((int)index, nranks);
+    if (kind == 1) return xtbb200::shard_pair_cta_owner_host(index, nranks);
+    return -1;
+}
+int xtbb200_getCommTime(xtbb200_TBatch batch, float* ms) {
+    XTBB_TRY
+    if (!batch || !ms) throw std::runtime_error("batch is not allocated");
+    *ms = batch->b->comm_ms();
+    return 0;
+    XTBB_CATCH(-1)
+}
 int xtbb200_singlepoint(xtbb200_TBatch batch, const double* positions, int restart, double* energies, double* gradients,
                         double* charges, int* niter, int* status) {
     XTBB_TRY

@@ -47,6 +47,8 @@ struct Dev {
     int ntype;
     int nmol;
     int maxhist;
+    // split of one large system over GPUs: this process is `rank` of `nranks` (1: not split)
+    int srank, snranks;
     // options
     double intcut, neglect, scfconv, qconv, etemp, broydamp;
     int maxiter;
@@ -106,6 +108,12 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     for (int i = 0; i < nw; ++i) r += red[i];
     return r;
 }
+
+// Ownership rules of the multi-GPU split: atoms are owned in warp-sized chunks (whole warps of the thread-per-atom
+// kernels drop out), shell-pair CTAs are interleaved over the ranks (neighbouring CTAs have similar cost).
+__host__ __device__ __forceinline__ int shard_atom_owner(int i, int nranks) { return nranks <= 1 ? 0 : (i >> 5) % nranks; }
+__device__ __forceinline__ bool shard_owns_atom(const Dev& d, int i) { return shard_atom_owner(i, d.snranks) == d.srank; }
+__device__ __forceinline__ long long shard_pair_cta(const Dev& d) { return (long long)blockIdx.x * d.snranks + d.srank; }
 
 __device__ __forceinline__ int lin0(int a, int b) {  // packed index, 0-based (src/lin_mod.f90:28-36)
     int mx = a > b ? a : b, mn = a > b ? b : a;

@@ -6,6 +6,9 @@
 // (src/xtb/calculator.f90:195-350, src/scf_module.F90:74-920, src/scc_core.f90:255-640).
 #include "engine.h"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -40,15 +43,70 @@ __global__ void k_count_active(Dev d, int* out) {
 // kernel classes for the per-kernel device timers (bench.py roofline, profiles/)
 enum KernelId { K_SETUP = 0, K_EEQ, K_SDQH0, K_DQMASK, K_CHOL, K_POT, K_D4SCC, K_FOCK, K_GEMM_XHX, K_JACOBI, K_GEMM_C,
                 K_FERMI, K_DENSITY, K_POP, K_ENERGY, K_SCCFIN, K_GRAD_H0, K_GRAD_AES, K_GRAD_D4, K_GRAD_ATM, K_GRAD_MISC,
-                K_WBO, K_FINISH, K_COUNT };
+                K_WBO, K_FINISH, K_COMM, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {
     "setup(cn,gab,jmat,dispmat,rep)", "eeq_guess", "k_sdqh0", "k_dqmask", "k_chol_inv", "potentials(shell,aes)",
     "d4_scc(zeta,matvec,shift)", "k_fock", "k_gemm(X^T H X)", "k_jacobi", "k_gemm(C=XZ)", "k_fermi",
     "density(scale+k_gemm)", "populations(k_pop_rows,k_pop_atoms)", "energies(es,aes)", "k_scc_finish(broyden)",
     "k_grad_h0(+W build,collect)", "k_grad_aes", "grad_d4(weights,c6,pairs)", "k_grad_atm", "k_grad_cn", "wbo(PS gemm,k_wbo)",
-    "k_finish"};
+    "k_finish", "nccl_allreduce(S,D,Q,H0 | dE/dCN | gradient)"};
+
+// NCCL is needed only when one large system is split over GPUs; it is resolved at run time so that the
+// single-GPU library has no link dependency on it.  Inside a PyTorch process the already loaded torch-bundled
+// libnccl.so.2 is picked up (same SONAME); XTBB200_NCCL_LIB overrides the name.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    static NcclApi& get() {
+        static NcclApi api;
+        if (api.handle) return api;
+        const char* name = std::getenv("XTBB200_NCCL_LIB");
+        void* h = dlopen(name ? name : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) throw std::runtime_error(std::string("xtb_b200: cannot load NCCL for the multi-GPU split: ") + dlerror());
+        auto sym = [&](const char* n) {
+            void* p = dlsym(h, n);
+            if (!p) throw std::runtime_error(std::string("xtb_b200: NCCL symbol missing: ") + n);
+            return p;
+        };
+        api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+        api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+        api.handle = h;
+        return api;
+    }
+    void check(ncclResult_t r, const char* what) const {
+        if (r != ncclSuccess) throw std::runtime_error(std::string("NCCL error in ") + what + ": " + GetErrorString(r));
+    }
+};
+
+void shard_unique_id(char* out128) {
+    NcclApi& n = NcclApi::get();
+    ncclUniqueId id;
+    n.check(n.GetUniqueId(&id), "ncclGetUniqueId");
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out128, &id, sizeof(id));
+}
+int shard_atom_owner_host(int iatom, int nranks) { return shard_atom_owner(iatom, nranks); }
+int shard_pair_cta_owner_host(long long cta, int nranks) { return nranks <= 1 ? 0 : (int)(cta % nranks); }
 
 struct Batch::Impl {
+    ncclComm_t comm = nullptr;
+    double* xbuf = nullptr;   // exchange buffer of the gradient phase, 4 * natoms doubles
+    float t_comm = 0;
+    void allreduce(double* p, size_t count, cudaStream_t st) {
+        NcclApi& n = NcclApi::get();
+        n.check(n.AllReduce(p, p, count, ncclDouble, ncclSum, comm, st), "ncclAllReduce");
+    }
     // per-kernel-class timers: events bracket every launch whose class bit is set in prof_mask
     unsigned long long prof_mask = 0;
     std::vector<cudaEvent_t> ev_pool;
@@ -105,6 +163,8 @@ struct Batch::Impl {
     int scc_passes = 0;
     cudaEvent_t ev_phase[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_call[2] = {nullptr, nullptr};
+    cudaEvent_t ev_comm[4] = {nullptr, nullptr, nullptr, nullptr};   // integral exchange begin/end, gradient exchange begin/end
+    long long pair_total = 0;
     float t_call = 0;
 
     template <class T>
@@ -128,6 +188,8 @@ struct Batch::Impl {
         for (auto& e : ev_pool) cudaEventDestroy(e);
         for (auto& e : ev_phase) if (e) cudaEventDestroy(e);
         for (auto& e : ev_call) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_comm) if (e) cudaEventDestroy(e);
+        if (comm) NcclApi::get().CommDestroy(comm);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -162,6 +224,7 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         Dev& d = I.d;
         std::memset(&d, 0, sizeof(d));
         d.nmol = nmol; d.ntype = (int)s.etypes.size(); d.maxhist = maxhist;
+        d.srank = 0; d.snranks = 1;
         d.mol = I.upload(s.mol);
         d.atoms = I.upload(s.atoms);
         d.shells = I.upload(s.shells);
@@ -208,6 +271,7 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         d.eeqA = I.dalloc<double>((size_t)te);
         d.eeq0 = I.upload(I.eeq0);
         d.gpair = I.dalloc<double>(4 * (size_t)tp);
+        I.pair_total = tp;
         d.pair0 = I.upload(I.pair0);
         d.bdf = I.dalloc<double>((size_t)s.tot_br); d.bu = I.dalloc<double>((size_t)s.tot_br);
         d.ba = I.dalloc<double>((size_t)nmol * maxhist * maxhist); d.bbeta = I.dalloc<double>((size_t)nmol * maxhist * maxhist);
@@ -269,6 +333,30 @@ void Batch::set_options(double accuracy, double etemp, int maxiter) {
 }
 void Batch::set_guess(int mode) { p_->guess = mode; }
 void Batch::set_solver(int mode) { p_->solver = mode; }
+
+void Batch::set_shard(int rank, int nranks, const char* id128) {
+    Impl& I = *p_;
+    if (nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("set_shard: need 0 <= rank < nranks");
+    XTB_CUDA_CHECK(cudaSetDevice(I.device));
+    NcclApi* n = nranks > 1 || I.comm ? &NcclApi::get() : nullptr;
+    if (I.comm) { n->CommDestroy(I.comm); I.comm = nullptr; }
+    I.d.srank = 0; I.d.snranks = 1;
+    if (nranks == 1) return;
+    if (!id128) throw std::runtime_error("set_shard: the NCCL unique id of rank 0 is required");
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    n->check(n->CommInitRank(&I.comm, nranks, id, rank), "ncclCommInitRank");
+    if (!I.xbuf) I.xbuf = I.dalloc<double>(4 * I.sys.atoms.size());
+    I.d.srank = rank; I.d.snranks = nranks;
+    I.have_wfn = false;
+    // first collective of a communicator sets up its channels (hundreds of ms): pay that here, not in the first call
+    XTB_CUDA_CHECK(cudaMemsetAsync(I.xbuf, 0, 4 * I.sys.atoms.size() * sizeof(double), I.stream));
+    I.allreduce(I.xbuf, 4 * I.sys.atoms.size(), I.stream);
+    XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+}
+int Batch::shard_rank() const { return p_->d.srank; }
+int Batch::shard_nranks() const { return p_->d.snranks; }
+float Batch::comm_ms() const { return p_->t_comm; }
 
 void Batch::set_positions(const double* xyz_host) {
     Impl& I = *p_;
@@ -338,6 +426,7 @@ int Batch::singlepoint(bool restart) {
     if (const char* e = std::getenv("XTBB200_JB_TOL")) d.jb_tol = std::atof(e);   // tuning knob
     if (const char* e = std::getenv("XTBB200_JB_INNER")) d.jb_inner = std::max(1, std::atoi(e));   // tuning knob
     if (!I.ev_phase[0]) for (auto& e : I.ev_phase) cudaEventCreate(&e);
+    if (!I.ev_comm[0]) for (auto& e : I.ev_comm) cudaEventCreate(&e);
     cudaEvent_t* ev = I.ev_phase;
     int nl = 0;
     const int B = 128;
@@ -372,7 +461,34 @@ int Batch::singlepoint(bool restart) {
     KL(K_EEQ, k_qsh2qat<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
     // ---- integrals
     const long long max_pairs = (long long)s.max_nsh * (s.max_nsh + 1) / 2;
-    KL(K_SDQH0, k_sdqh0<<<grid2(max_pairs, kIntWarps, nmol), kIntWarps * 32, 0, st>>>(d));
+    // one large system split over GPUs: every rank evaluates an interleaved subset of the shell-pair CTAs into zeroed
+    // matrices; the NCCL allreduce(sum) of disjoint blocks reproduces the single-GPU matrices bit for bit
+    const int R = d.snranks;
+    const long long pair_ctas = (max_pairs + kIntWarps - 1) / kIntWarps;
+    const dim3 pair_grid((unsigned)std::max<long long>(1, (pair_ctas + R - 1) / R), nmol);
+    const size_t tmb = (size_t)s.tot_mat * sizeof(double);
+    if (R > 1) {
+        XTB_CUDA_CHECK(cudaMemsetAsync(d.S, 0, tmb, st));
+        XTB_CUDA_CHECK(cudaMemsetAsync(d.D, 0, 3 * tmb, st));
+        XTB_CUDA_CHECK(cudaMemsetAsync(d.Q, 0, 6 * tmb, st));
+        XTB_CUDA_CHECK(cudaMemsetAsync(d.H0, 0, tmb, st));
+        XTB_CUDA_CHECK(cudaMemsetAsync(d.H0n, 0, tmb, st));
+    }
+    KL(K_SDQH0, k_sdqh0<<<pair_grid, kIntWarps * 32, 0, st>>>(d));
+    if (R > 1) {
+        NcclApi& n = NcclApi::get();
+        I.prof_begin(K_COMM, st);
+        cudaEventRecord(I.ev_comm[0], st);
+        n.check(n.GroupStart(), "ncclGroupStart");
+        I.allreduce(d.S, (size_t)s.tot_mat, st);
+        I.allreduce(d.D, 3 * (size_t)s.tot_mat, st);
+        I.allreduce(d.Q, 6 * (size_t)s.tot_mat, st);
+        I.allreduce(d.H0, (size_t)s.tot_mat, st);
+        I.allreduce(d.H0n, (size_t)s.tot_mat, st);
+        n.check(n.GroupEnd(), "ncclGroupEnd");
+        cudaEventRecord(I.ev_comm[1], st);
+        I.prof_end(K_COMM, st);
+    }
     const long long nn2 = (long long)s.max_nao * s.max_nao;
     KL(K_DQMASK, k_dqmask<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
     // ---- solver selection and overlap factorisation
@@ -459,14 +575,34 @@ int Batch::singlepoint(bool restart) {
     KL(K_GRAD_H0, k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 1));                     // T = C (f e)
     KL(K_GRAD_H0, k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.H, 1, 0));            // H <- energy weighted density
     KL(K_GRAD_AES, k_pot_aes<false><<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
-    KL(K_GRAD_H0, k_grad_h0<<<grid2(max_pairs, kIntWarps, nmol), kIntWarps * 32, 0, st>>>(d));
+    if (R > 1) {   // partial gradients: repulsion stays on rank 0, unowned shell pairs contribute zeros
+        if (d.srank != 0) XTB_CUDA_CHECK(cudaMemsetAsync(d.grad, 0, 3 * s.atoms.size() * sizeof(double), st));
+        XTB_CUDA_CHECK(cudaMemsetAsync(d.gpair, 0, 4 * (size_t)I.pair_total * sizeof(double), st));
+    }
+    KL(K_GRAD_H0, k_grad_h0<<<pair_grid, kIntWarps * 32, 0, st>>>(d));
     KL(K_GRAD_H0, k_grad_h0_collect<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
     KL(K_GRAD_AES, k_grad_aes<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
     KL(K_GRAD_D4, k_d4_weights<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
     KL(K_GRAD_D4, k_d4_c6<<<grid2((long long)s.max_nat * s.max_nat, 128, nmol), 128, 0, st>>>(d));
     KL(K_GRAD_D4, k_grad_pairs<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
     KL(K_GRAD_ATM, k_grad_atm<<<dim3(s.max_nat, nmol), 128, (size_t)s.max_nat * sizeof(double), st>>>(d));
+    const int na_tot = (int)s.atoms.size();
+    if (R > 1) {   // dE/dCN vectors and ATM energies: owned / partial -> complete on every rank
+        I.prof_begin(K_COMM, st);
+        cudaEventRecord(I.ev_comm[2], st);
+        k_shard_pack<<<(na_tot + 127) / 128, 128, 0, st>>>(d, I.xbuf, na_tot);
+        I.allreduce(I.xbuf, 4 * (size_t)na_tot, st);
+        k_shard_unpack<<<(na_tot + 127) / 128, 128, 0, st>>>(d, I.xbuf, na_tot);
+        I.prof_end(K_COMM, st);
+        nl += 2;
+    }
     KL(K_GRAD_MISC, k_grad_cn<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+    if (R > 1) {
+        I.prof_begin(K_COMM, st);
+        I.allreduce(d.grad, 3 * (size_t)na_tot, st);
+        cudaEventRecord(I.ev_comm[3], st);
+        I.prof_end(K_COMM, st);
+    }
     // ---- properties: bond orders and dipole
     bool any_open = false;
     for (auto& m : s.mol) any_open |= (m.nopen != 0);
@@ -490,6 +626,13 @@ int Batch::singlepoint(bool restart) {
     cudaEventElapsedTime(&I.t_setup, ev[0], ev[1]);
     cudaEventElapsedTime(&I.t_scc, ev[1], ev[2]);
     cudaEventElapsedTime(&I.t_grad, ev[2], ev[3]);
+    I.t_comm = 0;
+    if (R > 1) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, I.ev_comm[0], I.ev_comm[1]);
+        cudaEventElapsedTime(&b, I.ev_comm[2], I.ev_comm[3]);   // includes k_grad_cn between the two exchanges
+        I.t_comm = a + b;
+    }
     I.prof_collect();
     I.launches = nl;
     I.scc_passes = iters;

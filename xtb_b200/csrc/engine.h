@@ -11,6 +11,10 @@ struct MolResult {
 };
 
 int device_count();
+// multi-GPU split of one large system: NCCL unique id (128 bytes) created on rank 0, ownership rules
+void shard_unique_id(char* out128);
+int shard_atom_owner_host(int iatom, int nranks);
+int shard_pair_cta_owner_host(long long cta, int nranks);
 
 class Batch {
  public:
@@ -23,6 +27,12 @@ class Batch {
     void set_options(double accuracy, double etemp, int maxiter);
     void set_guess(int mode);                      // 0: EEQ (default), 1: uniform charges
     void set_solver(int mode);                     // 0: automatic, 1: force the scalar Jacobi kernel
+    // this process becomes rank `rank` of `nranks` working on the SAME molecules: shell-pair integral / gradient blocks
+    // and the per-atom gradient terms are split, NCCL allreduce of the contributions; nranks == 1 switches it off
+    void set_shard(int rank, int nranks, const char* nccl_unique_id128);
+    int shard_rank() const;
+    int shard_nranks() const;
+    float comm_ms() const;                         // device time of the exchanges of the last call
     void set_positions(const double* xyz_host);    // concatenated (3, natoms) in bohr, host memory
     void set_positions_device(const double* xyz_dev);
     void set_wavefunction(const double* qsh, const double* dipm, const double* qp);

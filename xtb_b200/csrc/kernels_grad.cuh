@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kIntWarps * 32) k_grad_h0(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long npair = (long long)m.nsh * (m.nsh + 1) / 2;
-    const long long p = (long long)blockIdx.x * kIntWarps + warp;
+    const long long p = shard_pair_cta(d) * kIntWarps + warp;
     __shared__ double s_alp[kIntWarps][2][6], s_cont[kIntWarps][2][6];
     __shared__ double s_wf[kIntWarps][25], s_wp[kIntWarps][25];
     if (p >= npair) return;
@@ -235,10 +235,11 @@ __global__ void k_grad_h0_collect(Dev d) {
             g[0] += sgn * o[0]; g[1] += sgn * o[1]; g[2] += sgn * o[2];
             dh += o[3] * dse;
         }
-        for (int k = 0; k < c_nsph[sp.l]; ++k) {
-            const long long ao = sp.ao0 + k;
-            dh += d.P[m.mat0 + ao + (long long)m.nao * ao] * dse * kEVtoAU;
-        }
+        if (d.srank == 0)   // on-site term: counted once when the shell pairs are split over ranks
+            for (int k = 0; k < c_nsph[sp.l]; ++k) {
+                const long long ao = sp.ao0 + k;
+                dh += d.P[m.mat0 + ao + (long long)m.nao * ao] * dse * kEVtoAU;
+            }
     }
     for (int k = 0; k < 3; ++k) d.grad[3 * (m.at0 + i) + k] += g[k];
     d.dhdcn[m.at0 + i] = dh;
@@ -248,7 +249,7 @@ __global__ void k_grad_h0_collect(Dev d) {
 __global__ void k_grad_aes(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nat) return;
+    if (i >= m.nat || !shard_owns_atom(d, i)) return;
     const double* xyz = d.xyz + 3 * m.at0;
     const double* q = d.q + m.at0;
     const double* dipm = d.dipm + 3 * m.at0;
@@ -387,7 +388,7 @@ __global__ void k_d4_c6(Dev d) {
 __global__ void k_grad_pairs(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nat) return;
+    if (i >= m.nat || !shard_owns_atom(d, i)) return;
     const AtomPar ai = d.atoms[m.at0 + i];
     const double* xi = d.xyz + 3 * (m.at0 + i);
     double g[3] = {0, 0, 0}, dE = 0;
@@ -433,7 +434,7 @@ __global__ void k_grad_pairs(Dev d) {
 __global__ void __launch_bounds__(128) k_grad_atm(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     const int a = blockIdx.x;
-    if (a >= m.nat) return;
+    if (a >= m.nat || !shard_owns_atom(d, a)) return;
     extern __shared__ double s_dc6a[];
     __shared__ double red[32];
     const double* xyz = d.xyz + 3 * m.at0;
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(128) k_grad_atm(Dev d) {
 __global__ void k_grad_cn(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nat) return;
+    if (i >= m.nat || !shard_owns_atom(d, i)) return;
     const AtomPar ai = d.atoms[m.at0 + i];
     const double* xi = d.xyz + 3 * (m.at0 + i);
     const double vi = d.dhdcn[m.at0 + i] + d.w_aes[m.at0 + i], wi = d.dEdcn[m.at0 + i];
@@ -526,6 +527,30 @@ __global__ void k_grad_cn(Dev d) {
         for (int k = 0; k < 3; ++k) g[k] += f * rij[k];
     }
     for (int k = 0; k < 3; ++k) d.grad[3 * (m.at0 + i) + k] += g[k];
+}
+
+// Multi-GPU split: exchange buffer xbuf[4][natoms_total] = (dE/dCN of H0: partial sums over this rank's shell pairs |
+// AES radius weight | D4 dE/dCN | ATM energy: owned atoms only, zero elsewhere).  One NCCL allreduce(sum) of xbuf turns
+// it into the full vectors on every rank; k_shard_unpack writes them back.  thread per atom of the whole batch
+__global__ void k_shard_pack(Dev d, double* xbuf, int na) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= na) return;
+    // molecule of atom t: batches that are split hold one (or a few) large molecules
+    int im = 0;
+    while (im + 1 < d.nmol && d.mol[im + 1].at0 <= t) ++im;
+    const bool own = shard_owns_atom(d, t - d.mol[im].at0);
+    xbuf[t] = d.dhdcn[t];
+    xbuf[na + t] = own ? d.w_aes[t] : 0.0;
+    xbuf[2 * (long long)na + t] = own ? d.dEdcn[t] : 0.0;
+    xbuf[3 * (long long)na + t] = own ? d.e_atom[4 * (long long)t + 2] : 0.0;
+}
+__global__ void k_shard_unpack(Dev d, const double* xbuf, int na) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= na) return;
+    d.dhdcn[t] = xbuf[t];
+    d.w_aes[t] = xbuf[na + t];
+    d.dEdcn[t] = xbuf[2 * (long long)na + t];
+    d.e_atom[4 * (long long)t + 2] = xbuf[3 * (long long)na + t];
 }
 
 // Wiberg/Mayer bond orders from PS (get_wiberg / get_unrestricted_wiberg, scc_core.f90:1208-1295);

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kIntWarps * 32) k_sdqh0(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long npair = (long long)m.nsh * (m.nsh + 1) / 2;
-    long long p = (long long)blockIdx.x * kIntWarps + warp;
+    long long p = shard_pair_cta(d) * kIntWarps + warp;
     __shared__ double s_blk[kIntWarps][10][36];
     __shared__ double s_part[kIntWarps][10][33];
     __shared__ double s_alp[kIntWarps][2][6], s_cont[kIntWarps][2][6];

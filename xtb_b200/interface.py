@@ -70,6 +70,10 @@ def load_library():
         "xtbb200_setOptions": (ci, [vp, cd, cd, ci, ci]),
         "xtbb200_setSolver": (ci, [vp, ci]),
         "xtbb200_setWavefunction": (ci, [vp, _c_double_p, _c_double_p, _c_double_p]),
+        "xtbb200_shardUniqueId": (ci, [ctypes.c_char_p, ctypes.c_size_t]),
+        "xtbb200_setShard": (ci, [vp, ci, ci, ctypes.c_char_p, ctypes.c_size_t]),
+        "xtbb200_shardOwner": (ci, [ci, ctypes.c_longlong, ci]),
+        "xtbb200_getCommTime": (ci, [vp, ctypes.POINTER(ctypes.c_float)]),
         "xtbb200_singlepoint": (ci, [vp, _c_double_p, ci, _c_double_p, _c_double_p, _c_double_p, _c_int_p, _c_int_p]),
         "xtbb200_singlepointDevice": (ci, [vp, vp, ci, vp]),
         "xtbb200_getNMol": (ci, [vp]), "xtbb200_getSizes": (ci, [vp, ci, _c_int_p, _c_int_p, _c_int_p]),
@@ -372,6 +376,17 @@ class BatchCalculator:
     def set_solver(self, mode):
         """0: automatic, 1: scalar Jacobi kernel."""
         self._check(self._lib.xtbb200_setSolver(self._b, int(mode)))
+
+    def set_shard(self, rank, nranks, unique_id=None):
+        """Make this batch rank `rank` of `nranks` processes that work on the SAME molecules (one per GPU): integral /
+        gradient blocks are split, contributions summed by NCCL allreduce (include/xtb_b200.h).  Collective call."""
+        uid = bytes(unique_id) if unique_id is not None else None
+        self._check(self._lib.xtbb200_setShard(self._b, int(rank), int(nranks), uid, len(uid) if uid else 0))
+
+    def comm_ms(self):
+        ms = ctypes.c_float(0)
+        self._check(self._lib.xtbb200_getCommTime(self._b, ctypes.byref(ms)))
+        return ms.value
 
     def singlepoint(self, positions, restart=False):
         """positions: (total_atoms, 3) Bohr. Returns dict(energies, gradients, charges, niter, status)."""
