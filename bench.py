@@ -406,40 +406,68 @@ def kernel_roofline(top, k_ms, nmol, nao, nsh, nat, batch, peaks, torch, dev):
 
 def run_water(args):
     """BASELINE configs[3]: one large single system, (H2O)_n cluster (default n = 1000, 3000 atoms, 6000 AOs);
-    metric = seconds per SCC iteration on one GPU (the eigensolve stays on one GPU by design)."""
+    metric = seconds per SCC iteration.  With N > 1 ranks the integral / gradient blocks are split over the GPUs
+    (xtb_b200/sharded.py, NCCL allreduce of the contributions); the SCC iterations - the eigensolve - run replicated on
+    every GPU (they stay on one GPU by design), so the per-iteration metric does not scale and the JSON line carries the
+    phase split (setup+integrals / SCC / gradient / exchanges) that shows what does."""
     import torch
+    import torch.distributed as dist
 
-    import xtb_b200
+    from xtb_b200.sharded import ShardedCalculator
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device; the engine has no CPU fallback")
     rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
     Z, xyz = make_water_cluster(args.nwat)
-    b = xtb_b200.BatchCalculator([Z])
+    sc = ShardedCalculator(Z, rank, world, local)
+    b = sc.calc
     sz = b.sizes(0)
-    clocks = ClockSampler(0)
+    clocks = ClockSampler(local)
     for _ in range(max(args.warmup, 0)):
         b.singlepoint(xyz)
+    barrier()
     clocks.start()
     b.set_profile("all")
-    per_iter, tot_ms, launches = [], [], 0
+    per_iter, tot_ms, phases, launches = [], [], [], 0
     for _ in range(args.steps):
         r = b.singlepoint(xyz)
         t = b.timings()
         prof, passes = b.kernel_times()
         per_iter.append(t["scc_ms"] * 1e-3 / max(passes, 1))
         tot_ms.append(t["setup_ms"] + t["scc_ms"] + t["grad_ms"])
+        phases.append([t["setup_ms"], t["scc_ms"], t["grad_ms"], b.comm_ms()])
         launches += t["launches"]
+    barrier()
     clk = clocks.stop()
-    n, nocc = sz["nao"], 4 * args.nwat
-    value = float(np.mean(per_iter))
+    # max over ranks of the device times
+    agg = torch.tensor([float(np.mean(per_iter)), float(np.mean(tot_ms))] + list(np.mean(np.array(phases), axis=0)),
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+    value, step_ms, ph_setup, ph_scc, ph_grad, ph_comm = [float(x) for x in agg.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n = sz["nao"]
     k = prof["k_jacobi"]
     sec_diag = k["ms"] * 1e-3 / args.steps / max(passes, 1)
     flops = (10.0 / 3.0) * n ** 3
-    peak = measure_fp64_peak(torch, torch.device("cuda", 0))
+    peak = measure_fp64_peak(torch, dev)
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         from oracle.oracle import Oracle, build
         build()
         cores = host_cores()
@@ -450,23 +478,29 @@ def run_water(args):
         cpu = {"value": ts[1] - ts[0], "unit": "s/SCC-iteration", "cores": cores, "kind": "port",
                "sample": "second SCC iteration of the same system (oracle run with maxiter 2 minus maxiter 1)"}
     line = {
-        "metric": "s/SCC-iter at 3k atoms", "value": value, "unit": "s/SCC-iteration", "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": float(np.mean(tot_ms)), "higher_is_better": False, "scaling": "strong",
+        "metric": "s/SCC-iter at 3k atoms", "value": value, "unit": "s/SCC-iteration", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "(H2O)_%d cluster single point + gradient (%d atoms, %d AOs), seed 3000" % (args.nwat, sz["natoms"], n),
                    "scc_iterations": int(r["niter"][0]), "converged": bool(r["status"][0] == 0),
+                   "parallelism": ("integral/gradient blocks split x%d + NCCL allreduce; SCC (eigensolve) replicated" % world)
+                   if world > 1 else "one GPU",
                    "l2": "matrices of %.2f GB each >> 126 MB L2" % (8.0 * n * n / 1e9)},
+        "phases_ms": {"setup+integrals(+S factorisation)": ph_setup, "scc": ph_scc, "gradient+properties": ph_grad,
+                      "of which exchanges (NCCL allreduce)": ph_comm},
         "e2e": {"value": value, "unit": "s/SCC-iteration", "h2d_bytes_per_step": int(xyz.size * 8),
-                "d2h_bytes_per_step": int(8 * (1 + 4 * sz["natoms"])), "ms_per_step": float(np.mean(tot_ms)),
+                "d2h_bytes_per_step": int(8 * (1 + 4 * sz["natoms"])), "ms_per_step": step_ms,
                 "note": "whole host-buffer call incl. H2D/D2H is ms_per_step; the per-iteration metric excludes setup and gradient"},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "two-level block Jacobi (k_hj_gram/k_hj_inner/k_hj_apply)",
                      "achieved": flops / sec_diag / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / sec_diag / 1e12 / peak,
                      "traffic": None, "note": "algorithmic flop = (4/3+2) n^3 per diagonalisation (dsyevd equivalent)",
-                     "share_of_step": k["ms"] / args.steps / float(np.mean(tot_ms))},
+                     "share_of_step": k["ms"] / args.steps / step_ms},
         "cpu_baseline": cpu, "clocks": clk, "sample_energy_Eh": float(r["energies"][0]),
     }
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

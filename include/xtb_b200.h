@@ -39,7 +39,9 @@ int xtbb200_setOptions(xtbb200_TBatch batch, double accuracy, double etemp, int 
 int xtbb200_setWavefunction(xtbb200_TBatch batch, const double* qsh, const double* dipm, const double* qp);
 
 /* eigensolver selection: 0 = automatic (block Jacobi on the FP64 tensor path when the matrix fits in shared memory),
- * 1 = scalar one-sided Jacobi.  Both give the same spectrum to rounding; used by the parity tests. */
+ * 1 = scalar one-sided Jacobi, 2 = (matrices beyond shared memory) overlap orthogonaliser X = V s^-1/2 from the
+ * eigen-decomposition of S instead of the blocked Cholesky X = L^-T.  All give the same spectrum and density to
+ * rounding; used by the parity tests. */
 int xtbb200_setSolver(xtbb200_TBatch batch, int mode);
 
 /* Split of ONE large system over the GPUs of a box (one process per GPU; every process creates the SAME batch on its

@@ -291,7 +291,7 @@ def test_block_and_scalar_eigensolvers_agree(xb, kat, name):
 @pytest.mark.parametrize("kind", ["water64", "peptide3"])
 def test_large_system_two_level_jacobi(xb, kat, kind):
     """Matrices beyond the shared-memory solvers (two-level block Jacobi in HBM, overlap orthogonaliser from the
-    eigen-decomposition of S): same energies, gradients, charges and iteration count as the oracle."""
+    blocked Cholesky factorisation of S): same energies, gradients, charges and iteration count as the oracle."""
     from bench import make_peptide_cluster, make_water_cluster
     from oracle.oracle import Oracle
     if kind == "water64":
@@ -310,6 +310,32 @@ def test_large_system_two_level_jacobi(xb, kat, kind):
     assert int(res["niter"]) == o.info["niter"]
     cnt = b.counts(0)
     assert (cnt["ndp"], cnt["nqp"]) == (o.info["ndp"], o.info["nqp"])
+
+
+@pytest.mark.parametrize("nwat", [29, 64])
+def test_blocked_cholesky_orthogonaliser(xb, nwat):
+    """Large-matrix path: X = L^-T from the blocked Cholesky S = L L^T (kernels_chol.cuh) is upper triangular and
+    satisfies X^T S X = 1; the whole single point agrees with the cross-check path that takes X = V s^-1/2 from the
+    eigen-decomposition of S (solver mode 2).  nwat = 29 gives n = 174: ragged last panel (174 = 2 * 64 + 46)."""
+    from bench import make_water_cluster
+    Z, xyz = make_water_cluster(nwat)
+    b = xb.BatchCalculator([Z])
+    r = b.singlepoint(xyz)
+    assert r["all_converged"]
+    n = b.sizes(0)["nao"]
+    assert n > 168                                        # beyond the shared-memory solvers
+    X, S = b.matrix("X", 0), b.matrix("S", 0)
+    assert np.max(np.abs(np.tril(X, -1))) == 0.0
+    assert np.max(np.abs(X.T @ S @ X - np.eye(n))) < 1e-12
+    L = np.linalg.cholesky(S)
+    assert np.max(np.abs(X - np.linalg.inv(L).T)) < 1e-11
+    b2 = xb.BatchCalculator([Z])
+    b2.set_solver(2)
+    r2 = b2.singlepoint(xyz)
+    assert np.array_equal(r["niter"], r2["niter"])
+    assert abs(r["energies"][0] - r2["energies"][0]) < 1e-9
+    assert np.max(np.abs(r["gradients"] - r2["gradients"])) < 1e-9
+    assert np.max(np.abs(r["charges"] - r2["charges"])) < 1e-9
 
 
 def test_ensemble_runner_single_rank(xb, kat):

@@ -18,6 +18,7 @@
 #include "kernels_grad.cuh"
 #include "kernels_int.cuh"
 #include "kernels_hjacobi.cuh"
+#include "kernels_chol.cuh"
 #include "kernels_linalg.cuh"
 #include "kernels_scc.cuh"
 
@@ -299,6 +300,7 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         cudaFuncSetAttribute(k_jacobi_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_hj_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_grad_atm, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        cudaFuncSetAttribute(k_bchol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBcholDiagSmem);
         cudaFuncSetAttribute(k_hj_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, HP * GLD * (int)sizeof(double));
         cudaFuncSetAttribute(k_jacobi<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_jacobi<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
@@ -522,9 +524,24 @@ int Batch::singlepoint(bool restart) {
     if (!hier) {
         const size_t chol_bytes = (size_t)s.max_nao * (s.max_nao | 1) * sizeof(double);
         KL(K_CHOL, k_chol_inv<true><<<nmol, 512, chol_bytes, st>>>(d));
-    } else {
+    } else if (I.solver == 2) {                                   // cross-check path: X = V s^-1/2 from eig(S)
         hjacobi(d.S, 0, K_CHOL);                                  // S = V s V^T
-        KL(K_CHOL, k_hj_xscale<<<grid2((long long)s.max_nao * s.max_nao, 256, nmol), 256, 0, st>>>(d));   // X = V s^-1/2
+        KL(K_CHOL, k_hj_xscale<<<grid2((long long)s.max_nao * s.max_nao, 256, nmol), 256, 0, st>>>(d));
+    } else {                                                      // blocked Cholesky S = L L^T, X = L^-T (kernels_chol.cuh)
+        XTB_CUDA_CHECK(cudaMemcpyAsync(d.W, d.S, tmb, cudaMemcpyDeviceToDevice, st));
+        XTB_CUDA_CHECK(cudaMemsetAsync(d.X, 0, tmb, st));
+        const int cnb = (s.max_nao + CB - 1) / CB;
+        for (int k = 0; k < cnb; ++k) {
+            KL(K_CHOL, k_bchol_diag<<<nmol, 256, kBcholDiagSmem, st>>>(d, k));
+            const int mt = cnb - k - 1;
+            if (mt > 0) {
+                KL(K_CHOL, k_bchol_panel<<<dim3(mt, nmol), 128, 0, st>>>(d, k));
+                KL(K_CHOL, k_bchol_update<<<dim3(mt * (mt + 1) / 2, nmol), 128, 0, st>>>(d, k));
+            }
+        }
+        if (cnb > 1) KL(K_CHOL, k_bchol_scale<<<dim3(cnb * (cnb - 1) / 2, nmol), 128, 0, st>>>(d));
+        KL(K_CHOL, k_bchol_inv_diag<<<dim3(cnb, nmol), 256, 0, st>>>(d));
+        for (int i = 1; i < cnb; ++i) KL(K_CHOL, k_bchol_inv_row<<<dim3(i, nmol), 128, 0, st>>>(d, i));
     }
     cudaEventRecord(ev[1], st);
     // ---- SCC iterations
