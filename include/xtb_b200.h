@@ -38,11 +38,18 @@ int xtbb200_setOptions(xtbb200_TBatch batch, double accuracy, double etemp, int 
  * the EEQ guess).  The converged values are read back with xtbb200_getArray("qsh" | "dipm" | "qp"). */
 int xtbb200_setWavefunction(xtbb200_TBatch batch, const double* qsh, const double* dipm, const double* qp);
 
-/* eigensolver selection: 0 = automatic (block Jacobi on the FP64 tensor path when the matrix fits in shared memory),
- * 1 = scalar one-sided Jacobi, 2 = (matrices beyond shared memory) overlap orthogonaliser X = V s^-1/2 from the
- * eigen-decomposition of S instead of the blocked Cholesky X = L^-T.  All give the same spectrum and density to
- * rounding; used by the parity tests. */
+/* eigensolver selection: 0 = automatic (block Jacobi on the FP64 tensor path when the matrix fits in shared memory,
+ * Householder tridiagonalisation + divide and conquer + back-transformation beyond), 1 = scalar one-sided Jacobi,
+ * 2 = (matrices beyond shared memory) overlap orthogonaliser X = V s^-1/2 from the eigen-decomposition of S instead of
+ * the blocked Cholesky X = L^-T, 3 = (matrices beyond shared memory) two-level block Jacobi instead of Householder +
+ * divide and conquer.  All give the same spectrum and density to rounding; used by the parity tests. */
 int xtbb200_setSolver(xtbb200_TBatch batch, int mode);
+
+/* The large-matrix symmetric eigensolver of the SCC loop on its own (what dsyevd is to the reference,
+ * src/mctc/lapack/eigensolve.F90:240): a[n*n] column-major symmetric (both triangles, host memory) -> w[n] ascending,
+ * z[n*n] eigenvectors (may be NULL).  ms3 (may be NULL): device time [ms] of tridiagonalisation, divide and conquer,
+ * back-transformation.  Returns 0 on success, > 0 = number of unconverged secular equations, < 0 on error. */
+int xtbb200_symmetricEigen(int n, const double* a, double* w, double* z, float* ms3, int device);
 
 /* Split of ONE large system over the GPUs of a box (one process per GPU; every process creates the SAME batch on its
  * own device).  The shell-pair blocks of the integral build (build_SDQH0, src/xtb/hamiltonian.F90:261-412) and of its

@@ -5,7 +5,7 @@ include/xtb.h / include/xtb_b200.h (xtb_b200/lib/libxtb_b200.so).  This package 
 host-side mirror of that ABI; there is no CPU fallback.
 """
 from .interface import (BatchCalculator, Calculator, Environment, Molecule, Param, Results, XTBException,
-                        device_count, library_path, load_library)
+                        device_count, library_path, load_library, symmetric_eigen)
 
 __all__ = ["BatchCalculator", "Calculator", "Environment", "Molecule", "Param", "Results", "XTBException",
-           "device_count", "library_path", "load_library"]
+           "device_count", "library_path", "load_library", "symmetric_eigen"]

@@ -449,6 +449,11 @@ int xtbb200_setSolver(xtbb200_TBatch batch, int mode) {
     return 0;
     XTBB_CATCH(-1)
 }
+int xtbb200_symmetricEigen(int n, const double* a, double* w, double* z, float* ms3, int device) {
+    XTBB_TRY
+    return xtbb200::symmetric_eigen(n, a, w, z, ms3, device);
+    XTBB_CATCH(-1)
+}
 int xtbb200_shardUniqueId(char* id128, size_t len) {
     XTBB_TRY
     if (!id128 || len < 128) throw std::runtime_error("need a 128-byte buffer for the NCCL unique id");

@@ -19,6 +19,7 @@
 #include "kernels_int.cuh"
 #include "kernels_hjacobi.cuh"
 #include "kernels_chol.cuh"
+#include "kernels_eigh.cuh"
 #include "kernels_linalg.cuh"
 #include "kernels_scc.cuh"
 
@@ -41,13 +42,24 @@ __global__ void k_count_active(Dev d, int* out) {
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, __popc(b));
 }
 
+// after the Householder / divide-and-conquer eigensolver: bookkeeping of the molecules that were diagonalised
+__global__ void k_eigh_finish(Dev d, const int* fail) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.nmol) return;
+    MolState& s = d.st[i];
+    if (s.done) return;
+    s.sweeps = 0;
+    s.zvalid = 1;
+    if (*fail) s.fail = 12;
+}
+
 // kernel classes for the per-kernel device timers (bench.py roofline, profiles/)
 enum KernelId { K_SETUP = 0, K_EEQ, K_SDQH0, K_DQMASK, K_CHOL, K_POT, K_D4SCC, K_FOCK, K_GEMM_XHX, K_JACOBI, K_GEMM_C,
                 K_FERMI, K_DENSITY, K_POP, K_ENERGY, K_SCCFIN, K_GRAD_H0, K_GRAD_AES, K_GRAD_D4, K_GRAD_ATM, K_GRAD_MISC,
                 K_WBO, K_FINISH, K_COMM, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {
     "setup(cn,gab,jmat,dispmat,rep)", "eeq_guess", "k_sdqh0", "k_dqmask", "k_chol_inv", "potentials(shell,aes)",
-    "d4_scc(zeta,matvec,shift)", "k_fock", "k_gemm(X^T H X)", "k_jacobi", "k_gemm(C=XZ)", "k_fermi",
+    "d4_scc(zeta,matvec,shift)", "k_fock", "k_gemm(X^T H X)", "k_jacobi",   /* = the eigensolver class, whichever kernel family runs */ "k_gemm(C=XZ)", "k_fermi",
     "density(scale+k_gemm)", "populations(k_pop_rows,k_pop_atoms)", "energies(es,aes)", "k_scc_finish(broyden)",
     "k_grad_h0(+W build,collect)", "k_grad_aes", "grad_d4(weights,c6,pairs)", "k_grad_atm", "k_grad_cn", "wbo(PS gemm,k_wbo)",
     "k_finish", "nccl_allreduce(S,D,Q,H0 | dE/dCN | gradient)"};
@@ -143,6 +155,9 @@ struct Batch::Impl {
     }
     BatchSystem sys;
     Dev d;
+    EighWork eig;             // Householder + divide-and-conquer eigensolver for matrices beyond shared memory
+    bool have_eig = false;
+    std::vector<int> h_done;  // per-molecule "left the SCC loop" flags, mirrored for the per-molecule solver loop
     std::vector<void*> allocs;
     std::vector<long long> eeq0, pair0;
     int* d_active = nullptr;
@@ -186,6 +201,7 @@ struct Batch::Impl {
     }
     ~Impl() {
         for (void* p : allocs) cudaFree(p);
+        if (have_eig) eig.release();
         for (auto& e : ev_pool) cudaEventDestroy(e);
         for (auto& e : ev_phase) if (e) cudaEventDestroy(e);
         for (auto& e : ev_call) if (e) cudaEventDestroy(e);
@@ -290,7 +306,11 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
             d.hjM = I.dalloc<double>((size_t)s.tot_hj); d.hjJ = I.dalloc<double>((size_t)s.tot_hj);
             d.hj_flag = I.dalloc<int>((size_t)(s.tot_hj / (128 * 128)));
             d.hj_count = I.dalloc<int>(nmol); d.hj_conv = I.dalloc<int>(nmol); d.hj_sigma = I.dalloc<double>(nmol);
+            I.eig.init(s.max_nao, device);
+            I.have_eig = true;
+            I.bytes += I.eig.bytes;
         }
+        I.h_done.assign(nmol, 0);
         I.d_active = I.dalloc<int>(1);
         I.h_state.resize(nmol);
         XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
@@ -496,7 +516,8 @@ int Batch::singlepoint(bool restart) {
     // ---- solver selection and overlap factorisation
     const bool use_blk = I.fits_blk && I.solver != 1;             // block Jacobi, matrix in shared memory
     const bool use_scalar = !use_blk && I.fits_scalar;            // scalar Jacobi, matrix in shared memory
-    const bool hier = !use_blk && !use_scalar;                    // two-level Jacobi, matrix in HBM
+    const bool hier = !use_blk && !use_scalar;                    // matrix in HBM
+    const bool dc = hier && I.solver != 3;                        // Householder + divide and conquer (3: two-level Jacobi)
     const bool sm = true;
     const int hj_nb = hj_nblocks(s.max_nao), hj_nbp = hj_nb / 2, hj_rt = (s.max_nao + GT - 1) / GT;
     const size_t hj_inner_bytes = jb_smem_bytes(HP, kHjInnerWarps), hj_apply_bytes = (size_t)HP * GLD * sizeof(double);
@@ -553,6 +574,7 @@ int Batch::singlepoint(bool restart) {
     const size_t jb_bytes = jb_smem_bytes(s.max_nao, jb_warps);
     int active = nmol;
     int iters = 0;
+    std::fill(I.h_done.begin(), I.h_done.end(), 0);
     for (int it = 0; it < I.maxiter && active > 0; ++it) {
         KL(K_POT, k_pot_shell<<<grid2(s.max_nsh, B, nmol), B, 0, st>>>(d));
         KL(K_POT, k_pot_aes<true><<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
@@ -562,10 +584,22 @@ int Batch::singlepoint(bool restart) {
         KL(K_FOCK, k_fock<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
         KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.H, d.X, d.T, 0, 1));      // T = H X
         KL(K_GEMM_XHX, k_gemm<true, false><<<ggrid, 128, 0, st>>>(d, d.X, d.T, d.W, 0, 1));       // W = X^T T
-        if (it > 0 || (restart && I.have_wfn))
+        if (!dc && (it > 0 || (restart && I.have_wfn)))
             KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.W, d.Zm, d.T, 0, 2));   // T = A' Z_prev
         if (use_blk) KL(K_JACOBI, k_jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d));
-        else if (hier) hjacobi(d.W, 1, K_JACOBI);
+        else if (dc) {
+            I.prof_begin(K_JACOBI, st);
+            XTB_CUDA_CHECK(cudaMemsetAsync(I.eig.fail, 0, sizeof(int), st));
+            for (int im = 0; im < nmol; ++im)
+                if (!I.h_done[im]) {
+                    const int nla = I.eig.solve(st, d.W + s.mol[im].mat0, s.mol[im].nao, d.emo + s.mol[im].ao0,
+                                                d.Zm + s.mol[im].mat0, false);
+                    nl += nla; I.k_launches[K_JACOBI] += nla;
+                }
+            k_eigh_finish<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.eig.fail);
+            I.prof_end(K_JACOBI, st);
+            I.k_launches[K_JACOBI]++; nl++;
+        } else if (hier) hjacobi(d.W, 1, K_JACOBI);
         else if (npairs * 32 <= 1024) KL(K_JACOBI, launch_jacobi<32>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 16 <= 1024) KL(K_JACOBI, launch_jacobi<16>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 8 <= 1024) KL(K_JACOBI, launch_jacobi<8>(d, nmol, s.max_nao, sm, st));
@@ -584,6 +618,9 @@ int Batch::singlepoint(bool restart) {
         XTB_CUDA_CHECK(cudaMemsetAsync(I.d_active, 0, sizeof(int), st));
         KL(K_SCCFIN, k_count_active<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.d_active));
         XTB_CUDA_CHECK(cudaMemcpyAsync(&active, I.d_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (dc && nmol > 1)
+            XTB_CUDA_CHECK(cudaMemcpy2DAsync(I.h_done.data(), sizeof(int), &d.st[0].done, sizeof(MolState), sizeof(int), nmol,
+                                             cudaMemcpyDeviceToHost, st));
         XTB_CUDA_CHECK(cudaStreamSynchronize(st));
         iters++;
     }
@@ -658,6 +695,37 @@ int Batch::singlepoint(bool restart) {
     for (int i = 0; i < nmol; ++i)
         if (I.h_state[i].fail || !I.h_state[i].converged) nfail++;
     return nfail;
+}
+
+int symmetric_eigen(int n, const double* a_host, double* w_host, double* z_host, float* ms3, int device) {
+    if (n < 1 || !a_host || !w_host) throw std::runtime_error("symmetric_eigen: invalid arguments");
+    if (device_count() < 1) throw std::runtime_error("xtb_b200: no CUDA device available (this engine has no CPU fallback)");
+    XTB_CUDA_CHECK(cudaSetDevice(device));
+    EighWork w;
+    cudaStream_t st = nullptr;
+    double *A = nullptr, *Z = nullptr, *ev = nullptr;
+    int fail = 0;
+    const size_t n2 = (size_t)n * n;
+    try {
+        w.init(n, device);
+        XTB_CUDA_CHECK(cudaStreamCreate(&st));
+        A = w.alloc<double>(n2); Z = w.alloc<double>(n2); ev = w.alloc<double>(n);
+        XTB_CUDA_CHECK(cudaMemcpyAsync(A, a_host, n2 * sizeof(double), cudaMemcpyHostToDevice, st));
+        w.solve(st, A, n, ev, Z, true);
+        XTB_CUDA_CHECK(cudaMemcpyAsync(w_host, ev, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (z_host) XTB_CUDA_CHECK(cudaMemcpyAsync(z_host, Z, n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        XTB_CUDA_CHECK(cudaMemcpyAsync(&fail, w.fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+        XTB_CUDA_CHECK(cudaStreamSynchronize(st));
+        XTB_CUDA_CHECK(cudaGetLastError());
+        if (ms3) for (int k = 0; k < 3; ++k) ms3[k] = w.ms[k];
+    } catch (...) {
+        w.release();
+        if (st) cudaStreamDestroy(st);
+        throw;
+    }
+    w.release();
+    cudaStreamDestroy(st);
+    return fail;
 }
 
 void Batch::set_profile(unsigned long long mask) {

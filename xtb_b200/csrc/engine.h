@@ -16,6 +16,12 @@ void shard_unique_id(char* out128);
 int shard_atom_owner_host(int iatom, int nranks);
 int shard_pair_cta_owner_host(long long cta, int nranks);
 
+// Eigen-decomposition of one dense symmetric matrix (column-major, both triangles) with the large-matrix solver of the
+// SCC loop (Householder tridiagonalisation, divide and conquer, back-transformation; kernels_eigh.cuh): eigenvalues
+// ascending in w[n], eigenvectors in z[n*n] (may be null).  ms3: device time of the three stages.  Returns the number
+// of secular equations that did not converge (0 = success).
+int symmetric_eigen(int n, const double* a_host, double* w_host, double* z_host, float* ms3, int device);
+
 class Batch {
  public:
     // numbers: concatenated atomic numbers of all molecules; charges/uhf may be null (0)
@@ -26,7 +32,7 @@ class Batch {
 
     void set_options(double accuracy, double etemp, int maxiter);
     void set_guess(int mode);                      // 0: EEQ (default), 1: uniform charges
-    void set_solver(int mode);                     // 0: automatic, 1: force the scalar Jacobi kernel
+    void set_solver(int mode);                     // 0: automatic, 1: scalar Jacobi kernel, 2: X from eig(S), 3: two-level Jacobi for large n
     // this process becomes rank `rank` of `nranks` working on the SAME molecules: shell-pair integral / gradient blocks
     // and the per-atom gradient terms are split, NCCL allreduce of the contributions; nranks == 1 switches it off
     void set_shard(int rank, int nranks, const char* nccl_unique_id128);

@@ -69,6 +69,7 @@ def load_library():
         "xtbb200_delBatch": (None, [ctypes.POINTER(vp)]),
         "xtbb200_setOptions": (ci, [vp, cd, cd, ci, ci]),
         "xtbb200_setSolver": (ci, [vp, ci]),
+        "xtbb200_symmetricEigen": (ci, [ci, _c_double_p, _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_float), ci]),
         "xtbb200_setWavefunction": (ci, [vp, _c_double_p, _c_double_p, _c_double_p]),
         "xtbb200_shardUniqueId": (ci, [ctypes.c_char_p, ctypes.c_size_t]),
         "xtbb200_setShard": (ci, [vp, ci, ci, ctypes.c_char_p, ctypes.c_size_t]),
@@ -102,6 +103,21 @@ EXPORTED_SYMBOLS = None  # filled lazily by tests from the headers
 
 def device_count():
     return load_library().xtbb200_deviceCount()
+
+
+def symmetric_eigen(a, vectors=True, device=0):
+    """Eigen-decomposition of a dense symmetric matrix with the engine's large-matrix solver (xtbb200_symmetricEigen):
+    returns (w ascending, Z or None, {"sytrd_ms", "dc_ms", "backtransform_ms"})."""
+    L = load_library()
+    a = np.asfortranarray(a, dtype=np.float64)
+    n = a.shape[0]
+    w = np.empty(n)
+    z = np.empty((n, n), order="F") if vectors else None
+    ms = (ctypes.c_float * 3)()
+    rc = L.xtbb200_symmetricEigen(n, _dp(a), _dp(w), _dp(z) if vectors else None, ms, device)
+    if rc != 0:
+        raise XTBException("xtbb200_symmetricEigen failed (%d): %s" % (rc, L.xtbb200_lastError().decode()))
+    return w, z, {"sytrd_ms": ms[0], "dc_ms": ms[1], "backtransform_ms": ms[2]}
 
 
 def _dp(a):
