@@ -14,7 +14,8 @@ using namespace xtbb200::eigcore;
 extern "C" int dc_tridiag_host(int n, const double* din, const double* ein, double* lam_out, double* Qout, int* stats) {
     std::vector<double> Qa((size_t)n * n, 0.0), Qb((size_t)n * n, 0.0), U((size_t)n * n, 0.0);
     std::vector<double> lam(n), lam2(n), z(n), zhat(n), dk(n), zk(n), rc(n), rs(n);
-    std::vector<int> perm(n), cols(n), ra(n), rb(n);
+    std::vector<int> perm(n), cols(n), ra(n), rb(n), ctype(n), pos(n);
+    std::vector<double> Qg((size_t)n * n, 0.0), Ug((size_t)n * n, 0.0);
     int fails = 0, total_k = 0, total_rot = 0;
     if (n == 1) { lam_out[0] = din[0]; Qout[0] = 1.0; return 0; }
     const int D = tree_depth(n);
@@ -54,8 +55,11 @@ extern "C" int dc_tridiag_host(int n, const double* din, const double* ein, doub
                 perm[r] = i;
             }
             int nrot = 0;
-            const int k = deflate_scan(m, perm.data(), &lam[lo], z.data(), rho, cols.data(), ra.data(), rb.data(), rc.data(),
-                                       rs.data(), &nrot);
+            const int n1 = mid - lo;
+            const int k = deflate_scan(m, n1, perm.data(), &lam[lo], z.data(), rho, cols.data(), ctype.data(), ra.data(),
+                                       rb.data(), rc.data(), rs.data(), &nrot);
+            int cnt[3];
+            group_columns(k, cols.data(), ctype.data(), pos.data(), cnt);
             total_k += k; total_rot += nrot;
             for (int r = 0; r < nrot; ++r)
                 for (int row = lo; row < hi; ++row) {
@@ -67,7 +71,7 @@ extern "C" int dc_tridiag_host(int n, const double* din, const double* ein, doub
             for (int i = 0; i < k; ++i) { dk[i] = lam[lo + cols[i]]; zk[i] = z[cols[i]]; }
             // secular equation: delta(i, j) stored in U[(lo+i) + n (lo+j)]
             for (int j2 = 0; j2 < k; ++j2)
-                fails += secular_root(k, j2, dk.data(), zk.data(), rho, &U[lo + (size_t)n * (lo + j2)], 1, &lam2[lo + j2]);
+                fails += secular_root(k, j2, dk.data(), zk.data(), rho, &U[lo + (size_t)n * (lo + j2)], 1, &lam2[lo + j2], SeqPar());
             for (int i = 0; i < k; ++i) {
                 double w = U[(lo + i) + (size_t)n * (lo + i)];
                 for (int j2 = 0; j2 < k; ++j2)
@@ -78,13 +82,17 @@ extern "C" int dc_tridiag_host(int n, const double* din, const double* ein, doub
                 double s = 0;
                 for (int i = 0; i < k; ++i) { double& u = U[(lo + i) + (size_t)n * (lo + j2)]; u = zhat[i] / u; s += u * u; }
                 s = 1.0 / sqrt(s);
-                for (int i = 0; i < k; ++i) U[(lo + i) + (size_t)n * (lo + j2)] *= s;
+                for (int i = 0; i < k; ++i) Ug[(lo + pos[i]) + (size_t)n * (lo + j2)] = U[(lo + i) + (size_t)n * (lo + j2)] * s;
             }
-            // Qn[lo:hi, lo:lo+k) = Qo[lo:hi, cols[0:k)] U ; deflated columns copied behind
+            // grouped copies of the non-deflated columns, then two products: top rows use the slots [0, c0 + c1),
+            // bottom rows the slots [c0, k); deflated columns copied behind
+            for (int i = 0; i < k; ++i)
+                for (int row = lo; row < hi; ++row) Qg[row + (size_t)n * (lo + pos[i])] = Qo[row + (size_t)n * (lo + cols[i])];
             for (int j2 = 0; j2 < k; ++j2)
                 for (int row = lo; row < hi; ++row) {
+                    const int s0 = row < mid ? 0 : cnt[0], s1 = row < mid ? cnt[0] + cnt[1] : k;
                     double s = 0;
-                    for (int i = 0; i < k; ++i) s += Qo[row + (size_t)n * (lo + cols[i])] * U[(lo + i) + (size_t)n * (lo + j2)];
+                    for (int i = s0; i < s1; ++i) s += Qg[row + (size_t)n * (lo + i)] * Ug[(lo + i) + (size_t)n * (lo + j2)];
                     Qn[row + (size_t)n * (lo + j2)] = s;
                 }
             for (int p = k; p < m; ++p) {

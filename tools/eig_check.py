@@ -28,6 +28,8 @@ def main():
     worst = 0.0
     for n in sizes:
         for name, a in matrices(n, rng):
+            if os.environ.get("EIG_ONLY") and name != os.environ["EIG_ONLY"]:
+                continue
             t0 = time.time()
             w, z, ms = xtb_b200.symmetric_eigen(a)
             wall = time.time() - t0

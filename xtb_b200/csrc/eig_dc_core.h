@@ -58,9 +58,12 @@ EIG_HD void sym2x2(double a, double b, double c, double& rt1, double& rt2, doubl
 // Output: cols[0..k) non-deflated columns in ascending order of d, cols[k..m) deflated columns; rotations
 // (ra[t], rb[t], rc[t], rs[t]), t < nrot, to be applied in this order to the eigenvector columns:
 //   x = Q[:, ra], y = Q[:, rb]  ->  Q[:, ra] = c x + s y,  Q[:, rb] = c y - s x.
+// ctype[c] (work array, m entries): 1 = column of the left child (non-zero in the top n1 rows only), 3 = column of the
+// right child (bottom rows only), 2 = dense after a rotation that mixed the two kinds; valid for cols[0..k) on return.
 // Returns k.
-EIG_HD int deflate_scan(int m, const int* perm, double* d, double* z, double rho, int* cols, int* ra, int* rb, double* rc,
-                        double* rs, int* nrot_out) {
+EIG_HD int deflate_scan(int m, int n1, const int* perm, double* d, double* z, double rho, int* cols, int* ctype, int* ra,
+                        int* rb, double* rc, double* rs, int* nrot_out) {
+    for (int i = 0; i < m; ++i) ctype[i] = i < n1 ? 1 : 3;
     double dmax = 0.0, zmax = 0.0;
     for (int i = 0; i < m; ++i) { dmax = fmax(dmax, fabs(d[i])); zmax = fmax(zmax, fabs(z[i])); }
     const double tol = 8.0 * kEps * fmax(dmax, zmax);
@@ -84,6 +87,7 @@ EIG_HD int deflate_scan(int m, const int* perm, double* d, double* z, double rho
             z[nj] = tau;
             z[pj] = 0.0;
             ra[nrot] = pj; rb[nrot] = nj; rc[nrot] = c; rs[nrot] = s; ++nrot;
+            if (ctype[nj] != ctype[pj]) ctype[nj] = 2;
             const double tt = d[pj] * c * c + d[nj] * s * s;
             d[nj] = d[pj] * s * s + d[nj] * c * c;
             d[pj] = tt;
@@ -99,15 +103,36 @@ EIG_HD int deflate_scan(int m, const int* perm, double* d, double* z, double rho
     return k;
 }
 
+// Grouping of the k non-deflated columns by kind (left-only, dense, right-only; stable inside a kind): pos[i] = slot
+// of the i-th column (ascending order of d) in the grouped order, cnt[0..3) = columns per kind.  With the update matrix
+// stored in grouped row order, the top n1 rows of the new eigenvectors need the slots [0, cnt0 + cnt1) only and the
+// bottom rows the slots [cnt0, k): two dense products instead of one of twice the size.
+EIG_HD void group_columns(int k, const int* cols, const int* ctype, int* pos, int* cnt) {
+    int c[3] = {0, 0, 0};
+    for (int i = 0; i < k; ++i) c[ctype[cols[i]] - 1]++;
+    int o[3] = {0, c[0], c[0] + c[1]};
+    for (int i = 0; i < k; ++i) pos[i] = o[ctype[cols[i]] - 1]++;
+    cnt[0] = c[0]; cnt[1] = c[1]; cnt[2] = c[2];
+}
+
+// how the poles of one secular equation are shared out: one thread (host, SeqPar) or the lanes of a warp (kernels)
+struct SeqPar {
+    EIG_HD int first() const { return 0; }
+    EIG_HD int step() const { return 1; }
+    EIG_HD double sum(double x) const { return x; }
+};
+
 // Root j (0-based, ascending) of the secular equation 1 + rho sum_i z_i^2 / (d_i - lambda) = 0 with d strictly
 // ascending and rho > 0.  The iteration runs in the shifted variable tau = lambda - origin, origin = the closer pole,
 // so that delta_i = d_i - lambda_j = (d_i - origin) - tau is obtained without cancellation; these differences are
 // what the eigenvector formula needs.  delta is written with the given stride.  Returns 0 when converged (secular
 // function below its rounding-error bound or bracket collapsed), 1 when the iteration limit was hit.
-EIG_HD int secular_root(int k, int j, const double* dk, const double* zk, double rho, double* delta, long long stride, double* lam_out) {
+template <class Par>
+EIG_HD int secular_root(int k, int j, const double* dk, const double* zk, double rho, double* delta, long long stride,
+                        double* lam_out, Par par) {
     if (k == 1) {
         const double z0 = zk[0], t = rho * z0 * z0;
-        delta[0] = -t;
+        if (par.first() == 0) delta[0] = -t;
         *lam_out = dk[0] + t;
         return 0;
     }
@@ -117,14 +142,16 @@ EIG_HD int secular_root(int k, int j, const double* dk, const double* zk, double
     int isplit, i1, i2;
     if (!last) {
         const double g = dk[j + 1] - dj, half = 0.5 * g;
-        double f = 1.0;
-        for (int i = 0; i < k; ++i) { const double zi = zk[i]; f += rho * zi * (zi / ((dk[i] - dj) - half)); }
+        double f = 0.0;
+        for (int i = par.first(); i < k; i += par.step()) { const double zi = zk[i]; f += zi * (zi / ((dk[i] - dj) - half)); }
+        f = 1.0 + rho * par.sum(f);
         if (f >= 0.0) { origin = dj; lo = 0.0; hi = half; tau = half; }
         else { origin = dk[j + 1]; lo = -half; hi = 0.0; tau = -half; }
         isplit = j; i1 = j; i2 = j + 1;
     } else {
         double zz = 0.0;
-        for (int i = 0; i < k; ++i) { const double zi = zk[i]; zz += zi * zi; }
+        for (int i = par.first(); i < k; i += par.step()) { const double zi = zk[i]; zz += zi * zi; }
+        zz = par.sum(zz);
         origin = dj; lo = 0.0; hi = rho * zz; tau = 0.5 * hi;
         isplit = k - 2; i1 = k - 2; i2 = k - 1;
     }
@@ -132,15 +159,12 @@ EIG_HD int secular_root(int k, int j, const double* dk, const double* zk, double
     int status = 1;
     for (int it = 0; it < 120; ++it) {
         double psi = 0.0, dpsi = 0.0, phi = 0.0, dphi = 0.0;
-        for (int i = 0; i <= isplit; ++i) {
+        for (int i = par.first(); i < k; i += par.step()) {
             const double zi = zk[i], t = zi / ((dk[i] - origin) - tau);
-            psi += zi * t; dpsi += t * t;
+            if (i <= isplit) { psi += zi * t; dpsi += t * t; }
+            else { phi += zi * t; dphi += t * t; }
         }
-        for (int i = isplit + 1; i < k; ++i) {
-            const double zi = zk[i], t = zi / ((dk[i] - origin) - tau);
-            phi += zi * t; dphi += t * t;
-        }
-        psi *= rho; dpsi *= rho; phi *= rho; dphi *= rho;
+        psi = rho * par.sum(psi); dpsi = rho * par.sum(dpsi); phi = rho * par.sum(phi); dphi = rho * par.sum(dphi);
         const double f = 1.0 + psi + phi;
         const double err = 8.0 * (fabs(psi) + fabs(phi)) + 1.0 + fabs(tau) * (dpsi + dphi);
         if (fabs(f) <= kEps * err) { status = 0; break; }
@@ -176,7 +200,7 @@ EIG_HD int secular_root(int k, int j, const double* dk, const double* zk, double
         if (tn == tau) { status = 0; break; }
         tau = tn;
     }
-    for (int i = 0; i < k; ++i) delta[(long long)i * stride] = (dk[i] - origin) - tau;
+    for (int i = par.first(); i < k; i += par.step()) delta[(long long)i * stride] = (dk[i] - origin) - tau;
     *lam_out = origin + tau;
     return status;
 }

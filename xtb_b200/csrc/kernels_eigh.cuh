@@ -6,10 +6,11 @@
 //                    dot products -- the HBM-bound part, 8 (n-j)^2 bytes per column) + rank-2*EB trailing update on the
 //                    FP64 tensor path (k_eg_gemm, DMMA m8n8k4)
 //   T = Qt L Qt^T    Cuppen divide and conquer down to 1x1 / 2x2 leaves, one batch of kernels per tree level:
-//                    rank sort, deflation scan, Givens rotations, secular equation (thread per root), Loewner update
-//                    vector, eigenvector update as one batched DMMA GEMM per level (scalar routines: eig_dc_core.h)
-//   Z = Q Qt         block reflectors I - V T V^T, the T factors assembled from the V^T v products that the
-//                    tridiagonalisation computes anyway; two DMMA GEMMs per panel
+//                    rank sort, deflation scan, Givens rotations, secular equation (warp per root), Loewner update
+//                    vector, eigenvector update as two DMMA GEMMs per node (top / bottom rows, columns grouped by
+//                    kind as in LAPACK's dlaed2/3), batched over the level (scalar routines: eig_dc_core.h)
+//   Z = Q Qt         block reflectors I - V T V^T over two panels, the T factors assembled from the V^T v products
+//                    that the tridiagonalisation computes anyway; two DMMA GEMMs per block
 //
 // Replaces dsyevd('V') inside TEigenSolver%fact_solve (src/mctc/lapack/eigensolve.F90:218-246) for large n; the
 // reduction to standard form (dsygst) and the back-substitution (dtrsm) are the X^T H X and X Z products of engine.cu.
@@ -20,7 +21,8 @@
 
 namespace xtbb200 {
 
-constexpr int EB = 64;             // panel width: tridiagonalisation panel = block reflector of the back-transformation
+constexpr int EB = 64;             // panel width of the tridiagonalisation
+constexpr int NB = 2 * EB;         // block reflector width of the back-transformation (two panels)
 constexpr int kSytrdThreads = 1024;
 constexpr int kBtSplit = 4;        // split of the long K dimension of W = V^T C
 
@@ -31,33 +33,52 @@ struct GemmTask {
     const double* A;
     const double* B;
     double* C;
-    long long lda, ldb, ldc;
+    int lda, ldb, ldc;
     int M, N, K;
     double alpha, beta;
-    const int* gA;        // optional column gather of a non-transposed A: op(A)(r,k) = A[r + lda gA[k]]
+    // two-segment K range: k >= ksegA reads K-index (k - ksegA + offA2) of A (ksegA = 0: plain); same for B.  Lets
+    // [V | W] [W | V]^T run as one product without copying the panels.
+    int ksegA, offA2, ksegB, offB2;
     int ksplit;           // > 1: blockIdx.z selects a K chunk, partial products go to C + blockIdx.z * csplit
     long long csplit;
 };
+inline GemmTask gemm_task(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
+                          double alpha, double beta) {
+    GemmTask t;
+    t.A = A; t.B = B; t.C = C; t.lda = lda; t.ldb = ldb; t.ldc = ldc; t.M = M; t.N = N; t.K = K; t.alpha = alpha; t.beta = beta;
+    t.ksegA = 0; t.offA2 = 0; t.ksegB = 0; t.offB2 = 0; t.ksplit = 1; t.csplit = 0;
+    return t;
+}
+
+__device__ __forceinline__ GemmTask gemm_task_dev(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M,
+                                                  int N, int K) {
+    GemmTask t;
+    t.A = A; t.B = B; t.C = C; t.lda = lda; t.ldb = ldb; t.ldc = ldc; t.M = M; t.N = N; t.K = K; t.alpha = 1.0; t.beta = 0.0;
+    t.ksegA = 0; t.offA2 = 0; t.ksegB = 0; t.offB2 = 0; t.ksplit = 1; t.csplit = 0;
+    return t;
+}
 
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(128) k_eg_gemm(GemmTask t0, const GemmTask* __restrict__ tasks) {
+__global__ void __launch_bounds__(128, 3) k_eg_gemm(GemmTask t0, const GemmTask* __restrict__ tasks) {
     const GemmTask t = tasks ? tasks[blockIdx.y] : t0;
     const int tm = (t.M + GT - 1) / GT, tn = (t.N + GT - 1) / GT;
     if ((int)blockIdx.x >= tm * tn) return;
     const int r0 = (blockIdx.x % tm) * GT, c0 = (blockIdx.x / tm) * GT;
     int kb = 0, ke = t.K;
-    double* C = t.C;
+    double* __restrict__ C = t.C + r0 + (long long)t.ldc * c0;
     if (t.ksplit > 1) {
         const int ch = (((t.K + t.ksplit - 1) / t.ksplit + GK - 1) / GK) * GK;
         kb = min(t.K, (int)blockIdx.z * ch);
         ke = min(t.K, kb + ch);
         C += (long long)blockIdx.z * t.csplit;
     }
-    const double* __restrict__ A = t.A;
-    const double* __restrict__ B = t.B;
-    const int* __restrict__ gA = t.gA;
-    const long long lda = t.lda, ldb = t.ldb, ldc = t.ldc;
-    const int M = t.M, N = t.N;
+    // tile-local operands: A rows / B columns start at the tile, K index 0 = first K index of the task
+    const double* __restrict__ A = TA ? t.A + (long long)t.lda * r0 : t.A + r0;
+    const double* __restrict__ B = TB ? t.B + c0 : t.B + (long long)t.ldb * c0;
+    const int lda = t.lda, ldb = t.ldb, ldc = t.ldc;
+    const int M = t.M - r0, N = t.N - c0;   // valid rows / columns of this tile (may exceed GT)
+    const int sgA = t.ksegA ? t.ksegA : 0x7fffffff, oA = t.offA2 - t.ksegA;
+    const int sgB = t.ksegB ? t.ksegB : 0x7fffffff, oB = t.offB2 - t.ksegB;
     __shared__ double As[GK][GLD], Bs[GK][GLD];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wr = (warp & 1) * 32, wc = (warp >> 1) * 32;
@@ -72,18 +93,18 @@ __global__ void __launch_bounds__(128) k_eg_gemm(GemmTask t0, const GemmTask* __
         for (int u = 0; u < GT * GK / 128; ++u) {
             const int tt = tid + 128 * u;
             if (!TA) {
-                const int r = tt % GT, kk = tt / GT, gr = r0 + r, gk = k0 + kk;
-                ra[u] = (gr < M && gk < ke) ? A[gr + lda * (gA ? gA[gk] : gk)] : 0.0;
+                const int r = tt % GT, gk = k0 + tt / GT, ka = gk >= sgA ? gk + oA : gk;
+                ra[u] = (r < M && gk < ke) ? A[r + (long long)lda * ka] : 0.0;
             } else {
-                const int kk = tt % GK, r = tt / GK, gr = r0 + r, gk = k0 + kk;
-                ra[u] = (gr < M && gk < ke) ? A[gk + lda * gr] : 0.0;
+                const int gk = k0 + tt % GK, r = tt / GK, ka = gk >= sgA ? gk + oA : gk;
+                ra[u] = (r < M && gk < ke) ? A[ka + (long long)lda * r] : 0.0;
             }
             if (!TB) {
-                const int kk = tt % GK, c = tt / GK, gc = c0 + c, gk = k0 + kk;
-                rb[u] = (gc < N && gk < ke) ? B[gk + ldb * gc] : 0.0;
+                const int gk = k0 + tt % GK, c = tt / GK, kq = gk >= sgB ? gk + oB : gk;
+                rb[u] = (c < N && gk < ke) ? B[kq + (long long)ldb * c] : 0.0;
             } else {
-                const int c = tt % GT, kk = tt / GT, gc = c0 + c, gk = k0 + kk;
-                rb[u] = (gc < N && gk < ke) ? B[gc + ldb * gk] : 0.0;
+                const int c = tt % GT, gk = k0 + tt / GT, kq = gk >= sgB ? gk + oB : gk;
+                rb[u] = (c < N && gk < ke) ? B[c + (long long)ldb * kq] : 0.0;
             }
         }
     };
@@ -119,13 +140,13 @@ __global__ void __launch_bounds__(128) k_eg_gemm(GemmTask t0, const GemmTask* __
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int gr = r0 + wr + 8 * i + (lane >> 2);
-            const int gc = c0 + wc + 8 * j + 2 * (lane & 3);
+            const int gr = wr + 8 * i + (lane >> 2);
+            const int gc = wc + 8 * j + 2 * (lane & 3);
             if (gr < M) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
                     if (gc + h < N) {
-                        double* p = C + gr + ldc * (gc + h);
+                        double* p = C + gr + (long long)ldc * (gc + h);
                         const double v = alpha * acc[i][j][h];
                         *p = (beta == 0.0) ? v : v + beta * *p;
                     }
@@ -141,6 +162,7 @@ struct SytrdArgs {
     int n, j0, ncols;   // panel columns [j0, j0 + ncols)
     double* V;          // n x EB reflectors of the panel (explicit, zero above the unit entry)
     double* W;          // n x EB
+    const double* Vprev;// reflectors of the previous panel when it belongs to the same block reflector, else null
     double* d;          // diagonal of T
     double* e;          // sub-diagonal of T
     double* tau;
@@ -149,31 +171,49 @@ struct SytrdArgs {
     double* part_vy;    // [grid] partial v^T y
     double* vtv;        // [EB]  V^T v
     double* wtv;        // [EB]  W^T v
-    double* G;          // EB x EB of this panel: G[k + EB i] = v_k^T v_i (k < i), input of the T factor
+    double* G;          // NB x NB Gram matrix of the block reflector: G[k + NB i] = v_k^T v_i (k < i), input of the T factor
+    int gq;             // offset of this panel inside the block reflector (0 or EB)
     unsigned* bar;      // grid barrier counter (zeroed before the launch)
+    long long* prof;    // optional: cycles of CTA 0 per phase section (diagnostics), else null
 };
+#define SY_T(k) do { if (a.prof && cta == 0 && tid == 0) { const long long t_ = clock64(); a.prof[k] += t_ - tprof; tprof = t_; } } while (0)
 
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, unsigned& target) {
+// Block-wide sum of v into part[blockIdx.x] followed by a barrier over all CTAs of the (cooperative) grid.  red: 32 doubles.
+__device__ __forceinline__ void grid_sum_barrier(double v, double* red, double* part, unsigned* bar, unsigned nblocks, unsigned& target) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) red[warp] = v;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        target += nblocks;
-        __threadfence();
-        atomicAdd(bar, 1u);
-        unsigned v;
-        do {
-            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-        } while (v < target);
-        __threadfence();
+    if (warp == 0) {
+        double s = lane < nw ? red[lane] : 0.0;
+        s = warp_sum(s);
+        if (lane == 0) {
+            part[blockIdx.x] = s;
+            target += nblocks;
+            __threadfence();
+            atomicAdd(bar, 1u);
+            unsigned x;
+            do {
+                asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(x) : "l"(bar) : "memory");
+            } while (x < target);
+            __threadfence();
+        }
     }
     __syncthreads();
 }
 
-// dynamic shared memory: sv[n] | sh_part[(n / grid + 4) * 8]
+constexpr int kSyRows = 64;                         // rows per CTA pass of the panel update
+constexpr int kSySlices = kSytrdThreads / kSyRows;  // threads per row, each with a slice of the panel columns
+constexpr int kSyKmax = (EB + kSySlices - 1) / kSySlices;
+
+// dynamic shared memory: sv[n] | sh_part[(n / grid + 6) * 8]
 __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
     extern __shared__ double sm_dyn[];
     __shared__ double sh_vtv[EB], sh_wtv[EB], sh_vrow[EB], sh_wrow[EB], red[32], sh_sc[4];
+    __shared__ double sh_r1[kSySlices][kSyRows], sh_r2[kSySlices][kSyRows];
     const int n = a.n, G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    const int rl = tid & (kSyRows - 1), ks = tid / kSyRows;
     const long long ld = n;
     double* __restrict__ A = a.A;
     double* __restrict__ V = a.V;
@@ -182,88 +222,130 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
     double* sh_part = sm_dyn + n;
     unsigned target = 0;
     double taup = 0.0;   // tau of the previous column
+    long long tprof = clock64();
     for (int i = 0;; ++i) {
         const int j = a.j0 + i;
         const bool fin = i > 0, upd = i < a.ncols;
         const int ip = i - 1, jp = j - 1;
-        double alpha2 = 0.0;
-        // ---------------- phase A: finish w of column j-1, update column j, partial norm
-        if (fin) {
-            for (int k = tid; k < ip; k += nthr) {
-                sh_vtv[k] = __ldcg(a.vtv + k); sh_wtv[k] = __ldcg(a.wtv + k);
-                sh_vrow[k] = __ldcg(V + j + ld * k); sh_wrow[k] = __ldcg(W + j + ld * k);
-            }
-            __syncthreads();
-            if (warp == 0) {
-                double vy = 0.0, vw = 0.0, s = 0.0;
-                for (int c = lane; c < G; c += 32) vy += __ldcg(a.part_vy + c);
-                for (int k = lane; k < ip; k += 32) { vw += sh_vtv[k] * sh_wtv[k]; s += sh_vrow[k] * sh_wtv[k] + sh_wrow[k] * sh_vtv[k]; }
-                vy = warp_sum(vy); vw = warp_sum(vw); s = warp_sum(s);
-                if (lane == 0) {
-                    const double al2 = -0.5 * taup * taup * (vy - 2.0 * vw);
-                    sh_sc[0] = al2;
-                    sh_vrow[ip] = 1.0;                                        // V[j, ip]: the unit entry of v
-                    sh_wrow[ip] = taup * (__ldcg(a.y + j) - s) + al2;          // W[j, ip]
-                }
-            }
-            __syncthreads();
-            alpha2 = sh_sc[0];
-        }
+        // ---------------- phase A: finish w of column j-1, update column j, partial norm.  A CTA pass covers kSyRows
+        // rows; the panel columns of a row are shared out over kSySlices threads so that all loads of a pass are in
+        // flight together (the panel sits in L2; a serial loop per row would pay its latency 2*ip times).
         double sq = 0.0;
-        for (long long r = (long long)j + (long long)cta * nthr + tid; r < n; r += (long long)G * nthr) {
-            double s1 = 0.0, s2 = 0.0;
+        for (int base = j + cta * kSyRows, pass = 0; base < n || pass == 0; base += G * kSyRows, ++pass) {
+            const int r = base + rl;
+            const bool rv = r < n;
+            double vk[kSyKmax], wk[kSyKmax], vr = 0.0, yr = 0.0, ar = 0.0;
             if (fin) {
-                for (int k = 0; k < ip; ++k) {
-                    const double vk = __ldcg(V + r + ld * k), wk = __ldcg(W + r + ld * k);
-                    s1 += vk * sh_wtv[k] + wk * sh_vtv[k];
-                    s2 += vk * sh_wrow[k] + wk * sh_vrow[k];
+#pragma unroll
+                for (int u = 0; u < kSyKmax; ++u) {
+                    const int k = ks + u * kSySlices;
+                    const bool ok = rv && k < ip;
+                    vk[u] = ok ? __ldcg(V + r + ld * k) : 0.0;
+                    wk[u] = ok ? __ldcg(W + r + ld * k) : 0.0;
                 }
-                const double vr = __ldcg(V + r + ld * ip);
-                const double wr = taup * (__ldcg(a.y + r) - s1) + alpha2 * vr;
-                W[r + ld * ip] = wr;
-                if (r > j) A[r + ld * jp] = vr;                               // reflector storage below the sub-diagonal
-                s2 += vr * sh_wrow[ip] + wr * sh_vrow[ip];
+                if (ks == 0 && rv) { vr = __ldcg(V + r + ld * ip); yr = __ldcg(a.y + r); }
             }
-            if (upd) {
-                const double av = __ldcg(A + r + ld * j) - s2;
-                A[r + ld * j] = av;
-                if (r == j) a.d[j] = av;
-                else if (r >= j + 2) sq += av * av;
+            if (ks == 0 && rv && upd) ar = __ldcg(A + r + ld * j);
+            double alpha2 = 0.0;
+            if (fin) {
+                if (pass == 0) {
+                    double vy = 0.0, yj = 0.0;
+                    if (warp == 0) {
+                        for (int c = lane; c < G; c += 32) vy += __ldcg(a.part_vy + c);
+                        if (lane == 0) yj = __ldcg(a.y + j);
+                    }
+                    for (int k = tid; k < ip; k += nthr) {
+                        sh_vtv[k] = __ldcg(a.vtv + k); sh_wtv[k] = __ldcg(a.wtv + k);
+                        sh_vrow[k] = __ldcg(V + j + ld * k); sh_wrow[k] = __ldcg(W + j + ld * k);
+                    }
+                    __syncthreads();
+                    if (warp == 0) {
+                        double vw = 0.0, s = 0.0;
+                        for (int k = lane; k < ip; k += 32) { vw += sh_vtv[k] * sh_wtv[k]; s += sh_vrow[k] * sh_wtv[k] + sh_wrow[k] * sh_vtv[k]; }
+                        vy = warp_sum(vy); vw = warp_sum(vw); s = warp_sum(s);
+                        if (lane == 0) {
+                            const double al2 = -0.5 * taup * taup * (vy - 2.0 * vw);
+                            sh_sc[0] = al2;
+                            sh_vrow[ip] = 1.0;                          // V[j, ip]: the unit entry of v
+                            sh_wrow[ip] = taup * (yj - s) + al2;         // W[j, ip]
+                        }
+                    }
+                    __syncthreads();
+                    SY_T(0);
+                }
+                alpha2 = sh_sc[0];
+                double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int u = 0; u < kSyKmax; ++u) {
+                    const int k = ks + u * kSySlices;
+                    if (k < ip) {
+                        s1 += vk[u] * sh_wtv[k] + wk[u] * sh_vtv[k];
+                        s2 += vk[u] * sh_wrow[k] + wk[u] * sh_vrow[k];
+                    }
+                }
+                sh_r1[ks][rl] = s1; sh_r2[ks][rl] = s2;
+                __syncthreads();
             }
+            if (ks == 0 && rv) {
+                double s2 = 0.0;
+                if (fin) {
+                    double s1 = 0.0;
+#pragma unroll
+                    for (int u = 0; u < kSySlices; ++u) { s1 += sh_r1[u][rl]; s2 += sh_r2[u][rl]; }
+                    const double wr = taup * (yr - s1) + alpha2 * vr;
+                    W[r + ld * ip] = wr;
+                    if (r > j) A[r + ld * jp] = vr;             // reflector storage below the sub-diagonal
+                    s2 += vr * sh_wrow[ip] + wr * sh_vrow[ip];
+                }
+                if (upd) {
+                    const double av = ar - s2;
+                    A[r + ld * j] = av;
+                    if (r == j) a.d[j] = av;
+                    else if (r >= j + 2) sq += av * av;
+                }
+            }
+            if (fin && base + G * kSyRows < n) __syncthreads();   // sh_r1/sh_r2 are reused by the next pass
         }
         if (!upd || j == n - 1) break;
-        sq = block_sum(sq, red);
-        if (tid == 0) a.part_n[cta] = sq;
-        grid_barrier(a.bar, G, target);
+        SY_T(1);
+        grid_sum_barrier(sq, red, a.part_n, a.bar, G, target);
+        SY_T(3);
         // ---------------- phase B: reflector, trailing-matrix product, V^T v, W^T v
         const int m = n - j - 1;
-        if (warp == 0) {
-            double s = 0.0;
-            for (int c = lane; c < G; c += 32) s += __ldcg(a.part_n + c);
-            s = warp_sum(s);
-            if (lane == 0) {
-                const double alpha = __ldcg(A + (j + 1) + ld * j);
-                double beta = alpha, tau = 0.0, scal = 0.0;
-                if (s > 0.0) {
-                    beta = -copysign(sqrt(alpha * alpha + s), alpha);
-                    tau = (beta - alpha) / beta;
-                    scal = 1.0 / (alpha - beta);
+        {   // raw column and the norm partials are loaded together; the column is scaled once the reflector is known
+            double s = 0.0, alpha = 0.0;
+            if (warp == 0) {
+                for (int c = lane; c < G; c += 32) s += __ldcg(a.part_n + c);
+                if (lane == 0) alpha = __ldcg(A + (j + 1) + ld * j);
+            }
+            for (int t = tid; t < m; t += nthr) sv[t] = __ldcg(A + (j + 1 + t) + ld * j);
+            if (warp == 0) {
+                s = warp_sum(s);
+                if (lane == 0) {
+                    double beta = alpha, tau = 0.0, scal = 0.0;
+                    if (s > 0.0) {
+                        beta = -copysign(sqrt(alpha * alpha + s), alpha);
+                        tau = (beta - alpha) / beta;
+                        scal = 1.0 / (alpha - beta);
+                    }
+                    sh_sc[1] = tau; sh_sc[2] = scal;
+                    if (cta == 0) { a.e[j] = beta; a.tau[j] = tau; }
                 }
-                sh_sc[1] = tau; sh_sc[2] = scal;
-                if (cta == 0) { a.e[j] = beta; a.tau[j] = tau; }
             }
         }
         __syncthreads();
         const double tau = sh_sc[1], scal = sh_sc[2];
-        for (int t = tid; t < m; t += nthr) sv[t] = (t == 0) ? 1.0 : __ldcg(A + (j + 1 + t) + ld * j) * scal;
+        for (int t = tid; t < m; t += nthr) sv[t] = (t == 0) ? 1.0 : sv[t] * scal;
         __syncthreads();
         for (long long t = (long long)cta * nthr + tid; t < m; t += (long long)G * nthr) V[(j + 1 + t) + ld * i] = sv[t];
-        // jobs of this CTA: its share of the trailing columns, plus V / W columns dealt round-robin
+        SY_T(4);
+        // jobs of this CTA: its share of the trailing columns, plus V / W (/ previous panel V) columns dealt round-robin
         const int cb = j + 1 + (int)(((long long)m * cta) / G), ce = j + 1 + (int)(((long long)m * (cta + 1)) / G);
         const int ncA = ce - cb;
-        int nex = 0;
+        int nex = 0, nex2 = 0;
         for (int k = cta; k < i; k += G) ++nex;
-        const int nloc = ncA + 2 * nex;
+        if (a.Vprev) for (int k = cta; k < EB; k += G) ++nex2;
+        const int nloc = ncA + 2 * nex + nex2;
         int Q = 1;
         if (nloc > 0) {
             Q = (4 * nwarp + nloc - 1) / nloc;
@@ -274,10 +356,10 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
             const int lc = job / Q, q = job - lc * Q;
             const double* col;
             if (lc < ncA) col = A + (j + 1) + ld * (cb + lc);
-            else {
+            else if (lc < ncA + 2 * nex) {
                 const int x = lc - ncA, k = cta + (x >> 1) * G;
                 col = ((x & 1) ? W : V) + (j + 1) + ld * k;
-            }
+            } else col = a.Vprev + (j + 1) + ld * (cta + (lc - ncA - 2 * nex) * G);
             const int tb = (int)(((long long)m * q) / Q), te = (int)(((long long)m * (q + 1)) / Q);
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int t = tb + lane;
@@ -292,6 +374,7 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
             if (lane == 0) sh_part[job] = s;
         }
         __syncthreads();
+        SY_T(5);
         double vyl = 0.0;
         for (int lc = tid; lc < nloc; lc += nthr) {
             double s = 0.0;
@@ -300,62 +383,63 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
                 const int c = cb + lc;
                 a.y[c] = s;
                 vyl += sv[c - (j + 1)] * s;
-            } else {
+            } else if (lc < ncA + 2 * nex) {
                 const int x = lc - ncA, k = cta + (x >> 1) * G;
                 if (x & 1) a.wtv[k] = s;
-                else { a.vtv[k] = s; a.G[k + EB * i] = s; }
-            }
+                else { a.vtv[k] = s; a.G[(a.gq + k) + NB * (a.gq + i)] = s; }
+            } else a.G[(cta + (lc - ncA - 2 * nex) * G) + NB * (a.gq + i)] = s;
         }
-        vyl = block_sum(vyl, red);
-        if (tid == 0) a.part_vy[cta] = vyl;
         taup = tau;
-        grid_barrier(a.bar, G, target);
+        SY_T(6);
+        grid_sum_barrier(vyl, red, a.part_vy, a.bar, G, target);
+        SY_T(7);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// back-transformation  Z <- (I - V T V^T) Z  per panel
+// back-transformation  Z <- (I - V T V^T) Z  per block reflector of NB columns
 // ---------------------------------------------------------------------------------------------------------------
-// explicit V of panel [jb, jb+kb): Vb[r + n k], rows absolute
+// explicit V of the block [jb, jb+kb): Vb[r + n k], rows absolute
 __global__ void k_bt_formv(const double* __restrict__ A, int n, int jb, int kb, double* __restrict__ Vb) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * kb) return;
     const int r = (int)(t % n), k = (int)(t / n), piv = jb + k + 1;
     Vb[t] = r < piv ? 0.0 : (r == piv ? 1.0 : A[r + (long long)n * (jb + k)]);
 }
-// T factors of all panels (one CTA per panel): T(0:i,i) = -tau_i T(0:i,0:i) G(0:i,i), T(i,i) = tau_i
-__global__ void __launch_bounds__(EB) k_bt_tfactor(const double* __restrict__ Gall, const double* __restrict__ tau, int n,
+// T factors of all blocks (one CTA per block): T(0:i,i) = -tau_i T(0:i,0:i) G(0:i,i), T(i,i) = tau_i
+__global__ void __launch_bounds__(NB) k_bt_tfactor(const double* __restrict__ Gall, const double* __restrict__ tau, int n,
                                                    double* __restrict__ Tall) {
-    __shared__ double T[EB][EB + 1];
-    const int p = blockIdx.x, jb = p * EB, kb = min(EB, n - 1 - jb), r = threadIdx.x;
-    const double* G = Gall + (long long)p * EB * EB;
-    for (int c = 0; c < EB; ++c) T[r][c] = 0.0;
+    extern __shared__ double sm_dyn[];
+    double (*T)[NB + 1] = (double (*)[NB + 1])sm_dyn;
+    const int b = blockIdx.x, jb = b * NB, kb = min(NB, n - 1 - jb), r = threadIdx.x;
+    const double* G = Gall + (long long)b * NB * NB;
+    for (int c = 0; c < NB; ++c) T[r][c] = 0.0;
     __syncthreads();
     for (int i = 0; i < kb; ++i) {
         const double ti = tau[jb + i];
         if (r < i) {
             double s = 0.0;
-            for (int k = r; k < i; ++k) s += T[r][k] * G[k + EB * i];
+            for (int k = r; k < i; ++k) s += T[r][k] * G[k + NB * i];
             T[r][i] = -ti * s;
         } else if (r == i) T[r][i] = ti;
         __syncthreads();
     }
-    double* To = Tall + (long long)p * EB * EB;
-    for (int c = 0; c < EB; ++c) To[r + EB * c] = T[r][c];
+    double* To = Tall + (long long)b * NB * NB;
+    for (int c = 0; c < NB; ++c) To[r + NB * c] = T[r][c];
 }
-// W2 = T * sum_z Wz  (EB x n, leading dimension EB); thread per output element
+// W2 = T * sum_z Wz  (NB x n, leading dimension NB); thread per output element
 __global__ void k_bt_tw(const double* __restrict__ T, const double* __restrict__ Wz, long long zstride, int nz, int kb, int n,
                         double* __restrict__ W2) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)EB * n) return;
-    const int i = (int)(t % EB);
-    const long long c = t / EB;
+    if (t >= (long long)NB * n) return;
+    const int i = (int)(t % NB);
+    const long long c = t / NB;
     double s = 0.0;
     if (i < kb)
         for (int k = i; k < kb; ++k) {
             double w = 0.0;
-            for (int z = 0; z < nz; ++z) w += Wz[(long long)z * zstride + k + EB * c];
-            s += T[i + EB * k] * w;
+            for (int z = 0; z < nz; ++z) w += Wz[(long long)z * zstride + k + NB * c];
+            s += T[i + NB * k] * w;
         }
     W2[t] = s;
 }
@@ -366,9 +450,10 @@ __global__ void k_bt_tw(const double* __restrict__ T, const double* __restrict__
 struct DcArgs {
     int n, depth;
     const double* e;      // sub-diagonal of T (coupling of the torn blocks)
-    double *Qo, *Qn, *U;  // eigenvector blocks of the children / of the merged nodes, delta / update matrix
+    double *Qo, *Qn;      // eigenvector blocks of the children / of the merged nodes
+    double *U, *Qg, *Ug;  // delta matrix; non-deflated columns and update matrix in grouped order
     double *lam, *lam2, *z, *zhat, *dk, *zk, *rc, *rs;
-    int *perm, *cols, *ra, *rb, *kcnt, *nrot, *fail;
+    int *perm, *cols, *pos, *tcnt, *ra, *rb, *kcnt, *nrot, *fail;
     GemmTask* tasks;
 };
 struct DcNode { int lo, mid, hi; };
@@ -379,6 +464,11 @@ __device__ __forceinline__ DcNode dc_node(const DcArgs& a, int t) {
     nd.mid = eigcore::tree_bound(a.n, a.depth + 1, 2 * t + 1);
     return nd;
 }
+struct WarpPar {
+    __device__ __forceinline__ int first() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ int step() const { return 32; }
+    __device__ __forceinline__ double sum(double x) const { return warp_sum(x); }
+};
 
 // leaves of the tearing tree: 1x1 and 2x2 blocks of the torn matrix; thread per leaf
 __global__ void k_dc_leaves(int n, int D, const double* __restrict__ d, const double* __restrict__ e, double* __restrict__ lam,
@@ -422,7 +512,7 @@ __global__ void __launch_bounds__(256) k_dc_sort(DcArgs a) {
     a.perm[nd.lo + r] = i;
 }
 
-// deflation: one CTA per node, eigenvalues / z / order staged in shared memory, sequential scan by thread 0
+// deflation: one CTA per node, eigenvalues / z / order / column kinds staged in shared memory, sequential scan by thread 0
 __global__ void __launch_bounds__(256) k_dc_deflate(DcArgs a) {
     extern __shared__ double sm_dyn[];
     const DcNode nd = dc_node(a, blockIdx.x);
@@ -430,14 +520,18 @@ __global__ void __launch_bounds__(256) k_dc_deflate(DcArgs a) {
     double* sd = sm_dyn;
     double* sz = sm_dyn + m;
     int* sp = (int*)(sm_dyn + 2 * m);
+    int* sty = sp + m;
     __shared__ int sh_k;
     for (int i = threadIdx.x; i < m; i += blockDim.x) { sd[i] = a.lam[lo + i]; sz[i] = a.z[lo + i]; sp[i] = a.perm[lo + i]; }
     __syncthreads();
     const double rho = 2.0 * fabs(a.e[nd.mid - 1]);
     if (threadIdx.x == 0) {
         int nrot = 0;
-        sh_k = eigcore::deflate_scan(m, sp, sd, sz, rho, a.cols + lo, a.ra + lo, a.rb + lo, a.rc + lo, a.rs + lo, &nrot);
-        a.kcnt[blockIdx.x] = sh_k;
+        const int k = eigcore::deflate_scan(m, nd.mid - lo, sp, sd, sz, rho, a.cols + lo, sty, a.ra + lo, a.rb + lo, a.rc + lo,
+                                            a.rs + lo, &nrot);
+        eigcore::group_columns(k, a.cols + lo, sty, a.pos + lo, a.tcnt + 3 * blockIdx.x);
+        sh_k = k;
+        a.kcnt[blockIdx.x] = k;
         a.nrot[blockIdx.x] = nrot;
     }
     __syncthreads();
@@ -466,83 +560,94 @@ __global__ void __launch_bounds__(256) k_dc_rot(DcArgs a) {
     }
 }
 
-// secular equation: thread per root; delta(i,j) = d_i - lambda_j into U
-__global__ void __launch_bounds__(64) k_dc_secular(DcArgs a) {
+// secular equation: warp per root (the lanes share the poles); delta(i,j) = d_i - lambda_j into U
+__global__ void __launch_bounds__(256) k_dc_secular(DcArgs a) {
     extern __shared__ double sm_dyn[];
     const int k = a.kcnt[blockIdx.y];
-    if ((int)(blockIdx.x * blockDim.x) >= k) return;
+    if ((int)(blockIdx.x * (blockDim.x >> 5)) >= k) return;
     const DcNode nd = dc_node(a, blockIdx.y);
     double* sd = sm_dyn;
     double* sz = sm_dyn + k;
     for (int i = threadIdx.x; i < k; i += blockDim.x) { sd[i] = a.dk[nd.lo + i]; sz[i] = a.zk[nd.lo + i]; }
     __syncthreads();
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= k) return;
     const double rho = 2.0 * fabs(a.e[nd.mid - 1]);
     double lam;
-    const int st = eigcore::secular_root(k, j, sd, sz, rho, a.U + nd.lo + (long long)a.n * (nd.lo + j), 1, &lam);
-    a.lam2[nd.lo + j] = lam;
-    if (st) atomicAdd(a.fail, 1);
+    const int st = eigcore::secular_root(k, j, sd, sz, rho, a.U + nd.lo + (long long)a.n * (nd.lo + j), 1, &lam, WarpPar());
+    if ((threadIdx.x & 31) == 0) {
+        a.lam2[nd.lo + j] = lam;
+        if (st) atomicAdd(a.fail, 1);
+    }
 }
 
-// Loewner formula for the update vector that makes the computed roots exact; thread per entry
-__global__ void __launch_bounds__(128) k_dc_zhat(DcArgs a) {
+// Loewner formula for the update vector that makes the computed roots exact.  CTA = 32 entries x 8 slices of the roots
+__global__ void __launch_bounds__(256) k_dc_zhat(DcArgs a) {
+    __shared__ double sp[8][33];
     const int k = a.kcnt[blockIdx.y];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= k) return;
+    if ((int)(blockIdx.x * 32) >= k) return;
     const DcNode nd = dc_node(a, blockIdx.y);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;
     const long long ld = a.n;
-    const double* U = a.U + (nd.lo + i) + ld * nd.lo;
     const double* dk = a.dk + nd.lo;
-    const double di = dk[i];
-    double w = U[ld * i];
-    for (int j = 0; j < k; ++j)
-        if (j != i) w *= U[ld * j] / (di - dk[j]);
-    a.zhat[nd.lo + i] = copysign(sqrt(fabs(w)), a.zk[nd.lo + i]);
+    double w = 1.0;
+    if (i < k) {
+        const double* U = a.U + (nd.lo + i) + ld * nd.lo;
+        const double di = dk[i];
+        for (int j = ty; j < k; j += 8) w *= (j == i) ? U[ld * j] : U[ld * j] / (di - dk[j]);
+    }
+    sp[ty][tx] = w;
+    __syncthreads();
+    if (ty == 0 && i < k) {
+        for (int q = 1; q < 8; ++q) w *= sp[q][tx];
+        a.zhat[nd.lo + i] = copysign(sqrt(fabs(w)), a.zk[nd.lo + i]);
+    }
 }
 
-// eigenvectors of the rank-one update: U(i,j) = zhat_i / delta(i,j), normalised; warp per column
+// eigenvectors of the rank-one update: U(i,j) = zhat_i / delta(i,j), normalised, rows stored in grouped order; warp per column
 __global__ void __launch_bounds__(256) k_dc_vec(DcArgs a) {
     const int k = a.kcnt[blockIdx.y];
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j >= k) return;
     const DcNode nd = dc_node(a, blockIdx.y);
-    double* U = a.U + nd.lo + (long long)a.n * (nd.lo + j);
+    const double* U = a.U + nd.lo + (long long)a.n * (nd.lo + j);
+    double* Ug = a.Ug + nd.lo + (long long)a.n * (nd.lo + j);
     const double* zh = a.zhat + nd.lo;
+    const int* pos = a.pos + nd.lo;
     double s = 0.0;
     for (int i = lane; i < k; i += 32) { const double u = zh[i] / U[i]; s += u * u; }
     s = warp_sum(s);
     const double sc = 1.0 / sqrt(s);
-    for (int i = lane; i < k; i += 32) U[i] = zh[i] / U[i] * sc;
+    for (int i = lane; i < k; i += 32) Ug[pos[i]] = zh[i] / U[i] * sc;
 }
 
-// GEMM tasks of the level: Qn[lo:hi, lo:lo+k) = Qo[lo:hi, cols[0:k)] U(0:k, 0:k); thread per node
+// GEMM tasks of the level, two per node: the top rows of the merged eigenvectors need the left-only and dense columns,
+// the bottom rows the dense and right-only ones; thread per node
 __global__ void k_dc_tasks(DcArgs a, int nodes) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nodes) return;
     const DcNode nd = dc_node(a, t);
-    const long long ld = a.n, off = nd.lo + ld * nd.lo;
-    GemmTask g;
-    g.A = a.Qo + off; g.B = a.U + off; g.C = a.Qn + off;
-    g.lda = ld; g.ldb = ld; g.ldc = ld;
-    g.M = nd.hi - nd.lo; g.N = a.kcnt[t]; g.K = a.kcnt[t];
-    g.alpha = 1.0; g.beta = 0.0;
-    g.gA = a.cols + nd.lo;
-    g.ksplit = 1; g.csplit = 0;
-    a.tasks[t] = g;
+    const int ld = a.n, k = a.kcnt[t], c0 = a.tcnt[3 * t], c1 = a.tcnt[3 * t + 1], c2 = a.tcnt[3 * t + 2];
+    const long long off = nd.lo + (long long)ld * nd.lo;
+    a.tasks[2 * t] = gemm_task_dev(a.Qg + off, ld, a.Ug + off, ld, a.Qn + off, ld, nd.mid - nd.lo, k, c0 + c1);
+    a.tasks[2 * t + 1] = gemm_task_dev(a.Qg + nd.mid + (long long)ld * (nd.lo + c0), ld, a.Ug + (nd.lo + c0) + (long long)ld * nd.lo, ld,
+                                       a.Qn + nd.mid + (long long)ld * nd.lo, ld, nd.hi - nd.mid, k, c1 + c2);
 }
 
-// deflated eigenvectors are carried over unchanged behind the updated ones; grid (row chunks, slot, node)
-__global__ void __launch_bounds__(256) k_dc_copy(DcArgs a) {
-    const int k = a.kcnt[blockIdx.z];
+// non-deflated eigenvectors into their grouped slots of Qg, deflated ones unchanged behind the updated ones in Qn;
+// grid (row chunks, slot, node)
+__global__ void __launch_bounds__(256) k_dc_move(DcArgs a) {
     const DcNode nd = dc_node(a, blockIdx.z);
-    const int m = nd.hi - nd.lo;
-    const int p = k + blockIdx.y;
+    const int m = nd.hi - nd.lo, p = blockIdx.y;
     if (p >= m) return;
     const int row = nd.lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nd.hi) return;
+    const int k = a.kcnt[blockIdx.z];
     const long long ld = a.n;
-    a.Qn[row + ld * (nd.lo + p)] = a.Qo[row + ld * (nd.lo + a.cols[nd.lo + p])];
+    const double v = a.Qo[row + ld * (nd.lo + a.cols[nd.lo + p])];
+    if (p < k) a.Qg[row + ld * (nd.lo + a.pos[nd.lo + p])] = v;
+    else a.Qn[row + ld * (nd.lo + p)] = v;
 }
 
 // final ascending order: rank of every eigenvalue, sorted eigenvalues
@@ -571,12 +676,14 @@ __global__ void k_dc_permute(int n, const double* __restrict__ Q, const int* __r
 // ---------------------------------------------------------------------------------------------------------------
 struct EighWork {
     int nmax = 0, nsm = 0, grid = 0;
-    double *Qa = nullptr, *Qb = nullptr, *U = nullptr;
-    double *V = nullptr, *W = nullptr, *Vb = nullptr, *Wz = nullptr, *W2 = nullptr, *Tf = nullptr, *Gf = nullptr;
+    double *Qa = nullptr, *Qb = nullptr, *U = nullptr, *Qg = nullptr, *Ug = nullptr;
+    double *PB = nullptr, *Vb = nullptr, *Wz = nullptr, *W2 = nullptr, *Tf = nullptr, *Gf = nullptr;
     double *dd = nullptr, *ee = nullptr, *tau = nullptr, *y = nullptr, *part = nullptr, *vtv = nullptr, *wtv = nullptr;
     double *lam = nullptr, *lam2 = nullptr, *z = nullptr, *zhat = nullptr, *dk = nullptr, *zk = nullptr, *rc = nullptr, *rs = nullptr;
-    int *perm = nullptr, *cols = nullptr, *ra = nullptr, *rb = nullptr, *kcnt = nullptr, *nrot = nullptr, *fail = nullptr, *rank = nullptr;
+    int *perm = nullptr, *cols = nullptr, *pos = nullptr, *tcnt = nullptr, *ra = nullptr, *rb = nullptr, *kcnt = nullptr, *nrot = nullptr,
+        *fail = nullptr, *rank = nullptr;
     unsigned* bar = nullptr;
+    long long* prof = nullptr;
     GemmTask* tasks = nullptr;
     std::vector<void*> allocs;
     size_t bytes = 0;
@@ -594,37 +701,39 @@ struct EighWork {
         bytes += b;
         return (T*)p;
     }
-    static size_t sytrd_smem(int n, int grid) { return ((size_t)n + (size_t)(n / grid + 4) * 8) * sizeof(double); }
-    // largest order the shared-memory staging of the panel kernel and of the deflation scan allows
-    static int max_order() { return 11000; }
+    static size_t sytrd_smem(int n, int grid) { return ((size_t)n + (size_t)(n / grid + 6) * 8) * sizeof(double); }
+    // largest order the shared-memory staging of the deflation scan (24 bytes per row) allows
+    static int max_order() { return 9600; }
 
     void init(int nmax_, int device) {
         nmax = nmax_;
-        if (nmax > max_order()) throw std::runtime_error("xtb_b200: eigensolver supports matrices up to order 11000");
+        if (nmax > max_order()) throw std::runtime_error("xtb_b200: eigensolver supports matrices up to order 9600");
         cudaDeviceProp prop;
         XTB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
         nsm = prop.multiProcessorCount;
         if (!prop.cooperativeLaunch) throw std::runtime_error("xtb_b200: device lacks cooperative launch");
         const size_t n = nmax, n2 = n * n;
-        Qa = alloc<double>(n2); Qb = alloc<double>(n2); U = alloc<double>(n2);
-        V = alloc<double>(n * EB); W = alloc<double>(n * EB); Vb = alloc<double>(n * EB);
-        Wz = alloc<double>((size_t)kBtSplit * EB * n); W2 = alloc<double>((size_t)EB * n);
-        const size_t npan = (n + EB - 1) / EB;
-        Tf = alloc<double>(npan * EB * EB); Gf = alloc<double>(npan * EB * EB);
+        Qa = alloc<double>(n2); Qb = alloc<double>(n2); U = alloc<double>(n2); Qg = alloc<double>(n2); Ug = alloc<double>(n2);
+        PB = alloc<double>(n * (NB + EB)); Vb = alloc<double>(n * NB);
+        Wz = alloc<double>((size_t)kBtSplit * NB * n); W2 = alloc<double>((size_t)NB * n);
+        const size_t nblk = (n + NB - 1) / NB;
+        Tf = alloc<double>(nblk * NB * NB); Gf = alloc<double>(nblk * NB * NB);
         dd = alloc<double>(n); ee = alloc<double>(n); tau = alloc<double>(n); y = alloc<double>(n);
         part = alloc<double>(2 * (size_t)nsm); vtv = alloc<double>(EB); wtv = alloc<double>(EB);
         lam = alloc<double>(n); lam2 = alloc<double>(n); z = alloc<double>(n); zhat = alloc<double>(n);
         dk = alloc<double>(n); zk = alloc<double>(n); rc = alloc<double>(n); rs = alloc<double>(n);
-        perm = alloc<int>(n); cols = alloc<int>(n); ra = alloc<int>(n); rb = alloc<int>(n);
+        perm = alloc<int>(n); cols = alloc<int>(n); pos = alloc<int>(n); tcnt = alloc<int>(3 * n); ra = alloc<int>(n); rb = alloc<int>(n);
         kcnt = alloc<int>(n); nrot = alloc<int>(n); fail = alloc<int>(1); rank = alloc<int>(n);
         bar = alloc<unsigned>(1);
-        tasks = alloc<GemmTask>(n);
+        prof = alloc<long long>(8);
+        tasks = alloc<GemmTask>(2 * n);
         grid = nsm;
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sytrd_smem(nmax, grid)));
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 8)));
-        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 20 + 16)));
+        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 24 + 16)));
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_secular, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 16)));
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 8)));
+        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_bt_tfactor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NB * (NB + 1) * 8)));
         int occ = 0;
         XTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sytrd_panel, kSytrdThreads, sytrd_smem(nmax, grid)));
         if (occ < 1) throw std::runtime_error("xtb_b200: tridiagonalisation kernel does not fit on an SM");
@@ -653,31 +762,32 @@ struct EighWork {
         const long long ld = n;
         const size_t n2 = (size_t)n * n;
         if (timed) cudaEventRecord(ev[0], st);
-        // ---- 1. tridiagonalisation
-        const int npan = (n + EB - 1) / EB;
-        XTB_CUDA_CHECK(cudaMemsetAsync(Gf, 0, (size_t)npan * EB * EB * sizeof(double), st));
+        // ---- 1. tridiagonalisation; panel buffer PB = [V of even panels | V of odd panels | W]
+        const int npan = (n + EB - 1) / EB, nblk = (n + NB - 1) / NB;
+        double* Wp = PB + (size_t)n * NB;
+        XTB_CUDA_CHECK(cudaMemsetAsync(Gf, 0, (size_t)nblk * NB * NB * sizeof(double), st));
         for (int p = 0; p < npan; ++p) {
-            const int j0 = p * EB, nc = std::min(EB, n - j0);
+            const int j0 = p * EB, nc = std::min(EB, n - j0), q = p & 1;
+            double* V = PB + (size_t)n * EB * q;
             XTB_CUDA_CHECK(cudaMemsetAsync(V, 0, (size_t)n * EB * sizeof(double), st));
-            XTB_CUDA_CHECK(cudaMemsetAsync(W, 0, (size_t)n * EB * sizeof(double), st));
+            XTB_CUDA_CHECK(cudaMemsetAsync(Wp, 0, (size_t)n * EB * sizeof(double), st));
             XTB_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
             SytrdArgs sa;
-            sa.A = A; sa.n = n; sa.j0 = j0; sa.ncols = nc; sa.V = V; sa.W = W; sa.d = dd; sa.e = ee; sa.tau = tau; sa.y = y;
-            sa.part_n = part; sa.part_vy = part + nsm; sa.vtv = vtv; sa.wtv = wtv; sa.G = Gf + (size_t)p * EB * EB; sa.bar = bar;
+            sa.A = A; sa.n = n; sa.j0 = j0; sa.ncols = nc; sa.V = V; sa.W = Wp; sa.Vprev = q ? PB : nullptr;
+            sa.d = dd; sa.e = ee; sa.tau = tau; sa.y = y; sa.part_n = part; sa.part_vy = part + nsm; sa.vtv = vtv; sa.wtv = wtv;
+            sa.G = Gf + (size_t)(p >> 1) * NB * NB; sa.gq = EB * q; sa.bar = bar;
+            sa.prof = std::getenv("XTBB200_SYTRD_PROF") ? prof : nullptr;
             void* args[] = {&sa};
             XTB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sytrd_panel, dim3(grid), dim3(kSytrdThreads), args,
                                                        sytrd_smem(n, grid), st));
             ++nl;
             const int j1 = j0 + nc, mt = n - j1;
-            if (mt > 0) {   // A22 -= V W^T + W V^T on both triangles
-                GemmTask t;
-                t.C = A + j1 + ld * j1; t.ldc = ld; t.M = mt; t.N = mt; t.K = nc; t.alpha = -1.0; t.beta = 1.0;
-                t.gA = nullptr; t.ksplit = 1; t.csplit = 0; t.lda = ld; t.ldb = ld;
-                t.A = V + j1; t.B = W + j1;
+            if (mt > 0) {   // A22 -= [V | W] [W | V]^T on both triangles (only full panels have a trailing matrix)
+                GemmTask t = gemm_task(V + j1, n, Wp + j1, n, A + j1 + ld * j1, n, mt, mt, 2 * EB, -1.0, 1.0);
+                t.ksegA = EB; t.offA2 = NB - EB * q;          // K index of W's first column relative to V
+                t.ksegB = EB; t.offB2 = -(NB - EB * q);       // K index of V's first column relative to W
                 gemm(st, false, true, t);
-                t.A = W + j1; t.B = V + j1;
-                gemm(st, false, true, t);
-                nl += 2;
+                ++nl;
             }
         }
         if (timed) cudaEventRecord(ev[1], st);
@@ -686,58 +796,56 @@ struct EighWork {
         XTB_CUDA_CHECK(cudaMemsetAsync(Qb, 0, n2 * sizeof(double), st));
         double* Qo = Qa;
         double* Qn = Qb;
+        double* la = lam;
+        double* lb = lam2;
         if (n == 1) {
-            XTB_CUDA_CHECK(cudaMemcpyAsync(lam, dd, sizeof(double), cudaMemcpyDeviceToDevice, st));
+            XTB_CUDA_CHECK(cudaMemcpyAsync(la, dd, sizeof(double), cudaMemcpyDeviceToDevice, st));
             const double one = 1.0;
             XTB_CUDA_CHECK(cudaMemcpyAsync(Qo, &one, sizeof(double), cudaMemcpyHostToDevice, st));
         } else {
             const int D = eigcore::tree_depth(n);
-            k_dc_leaves<<<((1 << D) + 127) / 128, 128, 0, st>>>(n, D, dd, ee, lam, Qo);
+            k_dc_leaves<<<((1 << D) + 127) / 128, 128, 0, st>>>(n, D, dd, ee, la, Qo);
             ++nl;
             for (int depth = D - 1; depth >= 0; --depth) {
                 const int nodes = 1 << depth, mmax = (n + nodes - 1) / nodes;
                 DcArgs a;
-                a.n = n; a.depth = depth; a.e = ee; a.Qo = Qo; a.Qn = Qn; a.U = U; a.lam = lam; a.lam2 = lam2; a.z = z; a.zhat = zhat;
-                a.dk = dk; a.zk = zk; a.rc = rc; a.rs = rs; a.perm = perm; a.cols = cols; a.ra = ra; a.rb = rb; a.kcnt = kcnt;
-                a.nrot = nrot; a.fail = fail; a.tasks = tasks;
+                a.n = n; a.depth = depth; a.e = ee; a.Qo = Qo; a.Qn = Qn; a.U = U; a.Qg = Qg; a.Ug = Ug; a.lam = la; a.lam2 = lb;
+                a.z = z; a.zhat = zhat; a.dk = dk; a.zk = zk; a.rc = rc; a.rs = rs; a.perm = perm; a.cols = cols; a.pos = pos;
+                a.tcnt = tcnt; a.ra = ra; a.rb = rb; a.kcnt = kcnt; a.nrot = nrot; a.fail = fail; a.tasks = tasks;
                 k_dc_sort<<<dim3((mmax + 255) / 256, nodes), 256, (size_t)mmax * 8, st>>>(a);
-                k_dc_deflate<<<nodes, 256, (size_t)mmax * 20 + 16, st>>>(a);
+                k_dc_deflate<<<nodes, 256, (size_t)mmax * 24 + 16, st>>>(a);
                 k_dc_rot<<<dim3((mmax + 255) / 256, nodes), 256, 0, st>>>(a);
-                k_dc_secular<<<dim3((mmax + 63) / 64, nodes), 64, (size_t)mmax * 16, st>>>(a);
-                k_dc_zhat<<<dim3((mmax + 127) / 128, nodes), 128, 0, st>>>(a);
+                k_dc_move<<<dim3((mmax + 255) / 256, mmax, nodes), 256, 0, st>>>(a);
+                k_dc_secular<<<dim3((mmax + 7) / 8, nodes), 256, (size_t)mmax * 16, st>>>(a);
+                k_dc_zhat<<<dim3((mmax + 31) / 32, nodes), 256, 0, st>>>(a);
                 k_dc_vec<<<dim3((mmax + 7) / 8, nodes), 256, 0, st>>>(a);
                 k_dc_tasks<<<(nodes + 127) / 128, 128, 0, st>>>(a, nodes);
-                const int tl = (mmax + GT - 1) / GT;
-                k_eg_gemm<false, false><<<dim3(tl * tl, nodes), 128, 0, st>>>(GemmTask(), tasks);
-                k_dc_copy<<<dim3((mmax + 255) / 256, mmax, nodes), 256, 0, st>>>(a);
+                const int th = (mmax / 2 + 1 + GT - 1) / GT, tw = (mmax + GT - 1) / GT;
+                k_eg_gemm<false, false><<<dim3(th * tw, 2 * nodes), 128, 0, st>>>(GemmTask(), tasks);
                 nl += 9;
                 std::swap(Qo, Qn);
-                std::swap(lam, lam2);
+                std::swap(la, lb);
             }
         }
-        k_dc_rank<<<(n + 255) / 256, 256, (size_t)n * 8, st>>>(n, lam, rank, w);
+        k_dc_rank<<<(n + 255) / 256, 256, (size_t)n * 8, st>>>(n, la, rank, w);
         k_dc_permute<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(n, Qo, rank, Z);
         nl += 2;
         if (timed) cudaEventRecord(ev[2], st);
-        // ---- 3. back-transformation, last panel first
+        // ---- 3. back-transformation, last block reflector first
         const int nrefl = n - 1;   // reflectors 0 .. n-2 (the last one is the identity)
         if (nrefl > 0) {
-            const int nbp = (nrefl + EB - 1) / EB;
-            k_bt_tfactor<<<nbp, EB, 0, st>>>(Gf, tau, n, Tf);
+            const int nbb = (nrefl + NB - 1) / NB;
+            k_bt_tfactor<<<nbb, NB, NB * (NB + 1) * sizeof(double), st>>>(Gf, tau, n, Tf);
             ++nl;
-            for (int p = nbp - 1; p >= 0; --p) {
-                const int jb = p * EB, kb = std::min(EB, nrefl - jb), r0 = jb + 1, mr = n - r0;
+            for (int b = nbb - 1; b >= 0; --b) {
+                const int jb = b * NB, kb = std::min(NB, nrefl - jb), r0 = jb + 1, mr = n - r0;
                 k_bt_formv<<<(unsigned)(((size_t)n * kb + 255) / 256), 256, 0, st>>>(A, n, jb, kb, Vb);
-                GemmTask t;
-                t.A = Vb + r0; t.lda = ld; t.B = Z + r0; t.ldb = ld; t.C = Wz; t.ldc = EB; t.M = kb; t.N = n; t.K = mr;
-                t.alpha = 1.0; t.beta = 0.0; t.gA = nullptr; t.ksplit = kBtSplit; t.csplit = (long long)EB * n;
+                GemmTask t = gemm_task(Vb + r0, n, Z + r0, n, Wz, NB, kb, n, mr, 1.0, 0.0);
+                t.ksplit = kBtSplit; t.csplit = (long long)NB * n;
                 gemm(st, true, false, t, kBtSplit);
-                k_bt_tw<<<(unsigned)(((size_t)EB * n + 255) / 256), 256, 0, st>>>(Tf + (size_t)p * EB * EB, Wz, (long long)EB * n,
+                k_bt_tw<<<(unsigned)(((size_t)NB * n + 255) / 256), 256, 0, st>>>(Tf + (size_t)b * NB * NB, Wz, (long long)NB * n,
                                                                                     kBtSplit, kb, n, W2);
-                GemmTask u;
-                u.A = Vb + r0; u.lda = ld; u.B = W2; u.ldb = EB; u.C = Z + r0; u.ldc = ld; u.M = mr; u.N = n; u.K = kb;
-                u.alpha = -1.0; u.beta = 1.0; u.gA = nullptr; u.ksplit = 1; u.csplit = 0;
-                gemm(st, false, false, u);
+                gemm(st, false, false, gemm_task(Vb + r0, n, W2, NB, Z + r0, n, mr, n, kb, -1.0, 1.0));
                 nl += 4;
             }
         }
@@ -745,6 +853,14 @@ struct EighWork {
             cudaEventRecord(ev[3], st);
             cudaEventSynchronize(ev[3]);
             for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
+        }
+        if (timed && std::getenv("XTBB200_SYTRD_PROF")) {
+            long long h[8];
+            cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+            static const char* nm[8] = {"A:scalars", "A:rows", "A:reduce", "barrier1", "B:reflector+v", "B:column dots", "B:collect",
+                                        "barrier2"};
+            for (int k = 0; k < 8; ++k) std::fprintf(stderr, "sytrd phase %-14s %10.3f us per column (n=%d)\n", nm[k], h[k] / 1.965e3 / n, n);
+            cudaMemset(prof, 0, sizeof(h));
         }
         launches = nl;
         return nl;
