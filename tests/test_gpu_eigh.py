@@ -1,0 +1,57 @@
+"""GPU checks of the large-matrix symmetric eigensolver (Householder tridiagonalisation + divide and conquer +
+back-transformation, xtb_b200/csrc/kernels_eigh.cuh) through the C ABI (xtbb200_symmetricEigen), against LAPACK's
+dsyevd -- the routine the reference calls at src/mctc/lapack/eigensolve.F90:240.  Tolerances in units of n*eps*|A|."""
+import numpy as np
+import pytest
+
+import xtb_b200
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+
+
+def _check(a, tol=30.0):
+    n = a.shape[0]
+    w, z, _ = xtb_b200.symmetric_eigen(a)
+    scale = max(np.abs(a).max(), 1e-300) * n * EPS
+    assert np.all(np.diff(w) >= 0)
+    assert np.max(np.abs(w - np.linalg.eigvalsh(a))) <= tol * scale
+    assert np.max(np.abs(z.T @ z - np.eye(n))) <= tol * n * EPS
+    assert np.max(np.abs(a @ z - z * w)) <= tol * scale
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 63, 64, 65, 127, 128, 129, 200, 515])
+def test_random_symmetric(n):
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n))
+    _check((a + a.T) / 2)
+
+
+def test_clustered_spectrum_of_weakly_coupled_identical_blocks():
+    """The spectrum of a cluster of identical molecules: bands of nearly degenerate levels (heavy deflation)."""
+    rng = np.random.default_rng(11)
+    b = rng.standard_normal((6, 6))
+    a = np.kron(np.eye(80), b + b.T) + 1e-4 * rng.standard_normal((480, 480))
+    _check((a + a.T) / 2)
+
+
+def test_exactly_degenerate_and_diagonal():
+    _check(np.eye(150))
+    _check(np.diag(np.repeat([1.0, -2.0, 3.0], 60)))
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((170, 170))
+    _check(np.diag(np.arange(170.0)) + 1e-11 * (a + a.T))
+
+
+def test_graded_matrix():
+    rng = np.random.default_rng(4)
+    n = 220
+    s = 10.0 ** (-6 * rng.random(n))
+    a = rng.standard_normal((n, n))
+    _check(s[:, None] * (a + a.T) * s[None, :])
+
+
+def test_larger_than_one_l2_slice():
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((1500, 1500))
+    _check((a + a.T) / 2)

@@ -56,13 +56,14 @@ __global__ void k_eigh_finish(Dev d, const int* fail) {
 // kernel classes for the per-kernel device timers (bench.py roofline, profiles/)
 enum KernelId { K_SETUP = 0, K_EEQ, K_SDQH0, K_DQMASK, K_CHOL, K_POT, K_D4SCC, K_FOCK, K_GEMM_XHX, K_JACOBI, K_GEMM_C,
                 K_FERMI, K_DENSITY, K_POP, K_ENERGY, K_SCCFIN, K_GRAD_H0, K_GRAD_AES, K_GRAD_D4, K_GRAD_ATM, K_GRAD_MISC,
-                K_WBO, K_FINISH, K_COMM, K_COUNT };
+                K_WBO, K_FINISH, K_COMM, K_EIG_PANEL, K_EIG_TRAIL, K_EIG_DC, K_EIG_BT, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {
     "setup(cn,gab,jmat,dispmat,rep)", "eeq_guess", "k_sdqh0", "k_dqmask", "k_chol_inv", "potentials(shell,aes)",
     "d4_scc(zeta,matvec,shift)", "k_fock", "k_gemm(X^T H X)", "k_jacobi",   /* = the eigensolver class, whichever kernel family runs */ "k_gemm(C=XZ)", "k_fermi",
     "density(scale+k_gemm)", "populations(k_pop_rows,k_pop_atoms)", "energies(es,aes)", "k_scc_finish(broyden)",
     "k_grad_h0(+W build,collect)", "k_grad_aes", "grad_d4(weights,c6,pairs)", "k_grad_atm", "k_grad_cn", "wbo(PS gemm,k_wbo)",
-    "k_finish", "nccl_allreduce(S,D,Q,H0 | dE/dCN | gradient)"};
+    "k_finish", "nccl_allreduce(S,D,Q,H0 | dE/dCN | gradient)", "eig:k_sytrd_panel", "eig:trailing update(k_eg_gemm)",
+    "eig:divide and conquer", "eig:back-transformation"};
 
 // NCCL is needed only when one large system is split over GPUs; it is resolved at run time so that the
 // single-GPU library has no link dependency on it.  Inside a PyTorch process the already loaded torch-bundled
@@ -518,6 +519,7 @@ int Batch::singlepoint(bool restart) {
     const bool use_scalar = !use_blk && I.fits_scalar;            // scalar Jacobi, matrix in shared memory
     const bool hier = !use_blk && !use_scalar;                    // matrix in HBM
     const bool dc = hier && I.solver != 3;                        // Householder + divide and conquer (3: two-level Jacobi)
+    const bool xtri = !(hier && I.solver == 2);                   // X = L^-T is upper triangular (dense when taken from eig(S))
     const bool sm = true;
     const int hj_nb = hj_nblocks(s.max_nao), hj_nbp = hj_nb / 2, hj_rt = (s.max_nao + GT - 1) / GT;
     const size_t hj_inner_bytes = jb_smem_bytes(HP, kHjInnerWarps), hj_apply_bytes = (size_t)HP * GLD * sizeof(double);
@@ -582,29 +584,29 @@ int Batch::singlepoint(bool restart) {
         KL(K_D4SCC, k_d4_matvec<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d));
         KL(K_D4SCC, k_d4_shift<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
         KL(K_FOCK, k_fock<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
-        KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.H, d.X, d.T, 0, 1));      // T = H X
-        KL(K_GEMM_XHX, k_gemm<true, false><<<ggrid, 128, 0, st>>>(d, d.X, d.T, d.W, 0, 1));       // W = X^T T
+        KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.H, d.X, d.T, xtri ? 2 : 0, 1));   // T = H X
+        KL(K_GEMM_XHX, k_gemm<true, false><<<ggrid, 128, 0, st>>>(d, d.X, d.T, d.W, xtri ? 3 : 0, 1));    // W = X^T T
         if (!dc && (it > 0 || (restart && I.have_wfn)))
             KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.W, d.Zm, d.T, 0, 2));   // T = A' Z_prev
         if (use_blk) KL(K_JACOBI, k_jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d));
         else if (dc) {
-            I.prof_begin(K_JACOBI, st);
             XTB_CUDA_CHECK(cudaMemsetAsync(I.eig.fail, 0, sizeof(int), st));
+            // stage hooks of the solver -> kernel classes (stage 0: panel kernel, 1: trailing update, 2: D&C, 3: back-transformation)
+            auto hook = [&](int stage, int end, int launches) {
+                const int id = K_EIG_PANEL + stage;
+                if (!end) I.prof_begin(id, st);
+                else { I.prof_end(id, st); I.k_launches[id] += launches; nl += launches; }
+            };
             for (int im = 0; im < nmol; ++im)
-                if (!I.h_done[im]) {
-                    const int nla = I.eig.solve(st, d.W + s.mol[im].mat0, s.mol[im].nao, d.emo + s.mol[im].ao0,
-                                                d.Zm + s.mol[im].mat0, false);
-                    nl += nla; I.k_launches[K_JACOBI] += nla;
-                }
-            k_eigh_finish<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.eig.fail);
-            I.prof_end(K_JACOBI, st);
-            I.k_launches[K_JACOBI]++; nl++;
+                if (!I.h_done[im])
+                    I.eig.solve(st, d.W + s.mol[im].mat0, s.mol[im].nao, d.emo + s.mol[im].ao0, d.Zm + s.mol[im].mat0, false, hook);
+            KL(K_EIG_BT, k_eigh_finish<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.eig.fail));
         } else if (hier) hjacobi(d.W, 1, K_JACOBI);
         else if (npairs * 32 <= 1024) KL(K_JACOBI, launch_jacobi<32>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 16 <= 1024) KL(K_JACOBI, launch_jacobi<16>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 8 <= 1024) KL(K_JACOBI, launch_jacobi<8>(d, nmol, s.max_nao, sm, st));
         else KL(K_JACOBI, launch_jacobi<4>(d, nmol, s.max_nao, sm, st));
-        KL(K_GEMM_C, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.Zm, d.C, 0, 1));       // C = X Z
+        KL(K_GEMM_C, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.Zm, d.C, xtri ? 4 : 0, 1));   // C = X Z
         KL(K_FERMI, k_fermi<<<nmol, 32, 0, st>>>(d));
         KL(K_DENSITY, k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 0));                // T = C f
         KL(K_DENSITY, k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.P, 1, 1));       // P = T C^T
@@ -711,7 +713,7 @@ int symmetric_eigen(int n, const double* a_host, double* w_host, double* z_host,
         XTB_CUDA_CHECK(cudaStreamCreate(&st));
         A = w.alloc<double>(n2); Z = w.alloc<double>(n2); ev = w.alloc<double>(n);
         XTB_CUDA_CHECK(cudaMemcpyAsync(A, a_host, n2 * sizeof(double), cudaMemcpyHostToDevice, st));
-        w.solve(st, A, n, ev, Z, true);
+        w.solve(st, A, n, ev, Z, true, [](int, int, int) {});
         XTB_CUDA_CHECK(cudaMemcpyAsync(w_host, ev, n * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (z_host) XTB_CUDA_CHECK(cudaMemcpyAsync(z_host, Z, n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
         XTB_CUDA_CHECK(cudaMemcpyAsync(&fail, w.fail, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -757,7 +757,10 @@ struct EighWork {
 
     // A (n x n, leading dimension n, both triangles; destroyed) -> eigenvalues w[n] ascending, eigenvectors Z (n x n).
     // *fail (device int) is incremented when a secular equation did not converge.  Returns the number of launches.
-    int solve(cudaStream_t st, double* A, int n, double* w, double* Z, bool timed) {
+    // hook(stage, end, launches) brackets the stages for the caller's timers: 0 panel kernel, 1 trailing update,
+    // 2 divide and conquer, 3 back-transformation.
+    template <class Hook>
+    int solve(cudaStream_t st, double* A, int n, double* w, double* Z, bool timed, Hook hook) {
         int nl = 0;
         const long long ld = n;
         const size_t n2 = (size_t)n * n;
@@ -778,19 +781,25 @@ struct EighWork {
             sa.G = Gf + (size_t)(p >> 1) * NB * NB; sa.gq = EB * q; sa.bar = bar;
             sa.prof = std::getenv("XTBB200_SYTRD_PROF") ? prof : nullptr;
             void* args[] = {&sa};
+            hook(0, 0, 0);
             XTB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sytrd_panel, dim3(grid), dim3(kSytrdThreads), args,
                                                        sytrd_smem(n, grid), st));
+            hook(0, 1, 1);
             ++nl;
             const int j1 = j0 + nc, mt = n - j1;
             if (mt > 0) {   // A22 -= [V | W] [W | V]^T on both triangles (only full panels have a trailing matrix)
                 GemmTask t = gemm_task(V + j1, n, Wp + j1, n, A + j1 + ld * j1, n, mt, mt, 2 * EB, -1.0, 1.0);
                 t.ksegA = EB; t.offA2 = NB - EB * q;          // K index of W's first column relative to V
                 t.ksegB = EB; t.offB2 = -(NB - EB * q);       // K index of V's first column relative to W
+                hook(1, 0, 0);
                 gemm(st, false, true, t);
+                hook(1, 1, 1);
                 ++nl;
             }
         }
         if (timed) cudaEventRecord(ev[1], st);
+        hook(2, 0, 0);
+        const int nl_dc0 = nl;
         // ---- 2. divide and conquer
         XTB_CUDA_CHECK(cudaMemsetAsync(Qa, 0, n2 * sizeof(double), st));
         XTB_CUDA_CHECK(cudaMemsetAsync(Qb, 0, n2 * sizeof(double), st));
@@ -830,7 +839,10 @@ struct EighWork {
         k_dc_rank<<<(n + 255) / 256, 256, (size_t)n * 8, st>>>(n, la, rank, w);
         k_dc_permute<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(n, Qo, rank, Z);
         nl += 2;
+        hook(2, 1, nl - nl_dc0);
         if (timed) cudaEventRecord(ev[2], st);
+        hook(3, 0, 0);
+        const int nl_bt0 = nl;
         // ---- 3. back-transformation, last block reflector first
         const int nrefl = n - 1;   // reflectors 0 .. n-2 (the last one is the identity)
         if (nrefl > 0) {
@@ -849,6 +861,7 @@ struct EighWork {
                 nl += 4;
             }
         }
+        hook(3, 1, nl - nl_bt0);
         if (timed) {
             cudaEventRecord(ev[3], st);
             cudaEventSynchronize(ev[3]);

@@ -26,6 +26,10 @@ constexpr int GK = 16;     // k tile
 constexpr int GLD = GT + 4;
 
 // kmode: 0 -> K = nao ; 1 -> K = st.kocc (density build over occupied columns)
+//        2 -> B is upper triangular (T = H X): K stops at the last row of the tile's columns
+//        3 -> op(A) = X^T with X upper triangular and the product is symmetric (W = X^T T): K stops at the last row
+//             index of the tile, only tiles on or below the diagonal are computed and mirrored into the upper triangle
+//        4 -> A is upper triangular (C = X Z): K starts at the first row of the tile
 // skip_done: 1 = skip molecules that already left the SCC loop; 2 = additionally skip molecules without a valid
 // eigenvector guess (warm-start product A' Z_prev)
 template <bool TA, bool TB>
@@ -38,7 +42,12 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
     const int tiles = (n + GT - 1) / GT;
     if ((int)blockIdx.x >= tiles * tiles) return;
     const int r0 = (blockIdx.x % tiles) * GT, c0 = (blockIdx.x / tiles) * GT;
-    const int K = kmode == 1 ? d.st[blockIdx.y].kocc : n;
+    if (kmode == 3 && r0 < c0) return;
+    int K = n, kbeg = 0;
+    if (kmode == 1) K = d.st[blockIdx.y].kocc;
+    else if (kmode == 2) K = min(n, c0 + GT);
+    else if (kmode == 3) K = min(n, r0 + GT);
+    else if (kmode == 4) kbeg = r0;
     const double* A = Ag + m.mat0;
     const double* B = Bg + m.mat0;
     double* C = Cg + m.mat0;
@@ -80,8 +89,8 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
             if (!TB) Bs[t % GK][t / GK] = rb[u]; else Bs[t / GT][t % GT] = rb[u];
         }
     };
-    if (K > 0) fetch(0);
-    for (int k0 = 0; k0 < K; k0 += GK) {
+    if (K > kbeg) fetch(kbeg);
+    for (int k0 = kbeg; k0 < K; k0 += GK) {
         stage();
         __syncthreads();
         if (k0 + GK < K) fetch(k0 + GK);
@@ -99,6 +108,7 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
         }
         __syncthreads();
     }
+    const bool mirror = kmode == 3 && r0 > c0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -108,6 +118,10 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
             if (gr < n) {
                 if (gc < n) C[gr + (long long)n * gc] = acc[i][j][0];
                 if (gc + 1 < n) C[gr + (long long)n * (gc + 1)] = acc[i][j][1];
+                if (mirror) {
+                    if (gc < n) C[gc + (long long)n * gr] = acc[i][j][0];
+                    if (gc + 1 < n) C[gc + 1 + (long long)n * gr] = acc[i][j][1];
+                }
             }
         }
 }
