@@ -38,6 +38,14 @@ int xtbb200_setOptions(xtbb200_TBatch batch, double accuracy, double etemp, int 
  * the EEQ guess).  The converged values are read back with xtbb200_getArray("qsh" | "dipm" | "qp"). */
 int xtbb200_setWavefunction(xtbb200_TBatch batch, const double* qsh, const double* dipm, const double* qp);
 
+/* External point charges for every molecule of the batch (batched xtb_setExternalCharges / xtb_releaseExternalCharges,
+ * src/api/calculator.f90:470-580): npc[nmol] charges per molecule; numbers (element whose chemical hardness damps the
+ * interaction, src/api/calculator.f90:533), charges, positions [npc][3] in Bohr, concatenated over molecules.
+ * npc == NULL (or all zero) releases them.  After a single point the gradient on the charges is
+ * xtbb200_getArray("pcgradient") (3 doubles per charge; xtb_getPCGradient). */
+int xtbb200_setExternalCharges(xtbb200_TBatch batch, const int* npc, const int* numbers, const double* charges,
+                               const double* positions);
+
 /* eigensolver selection: 0 = automatic (block Jacobi on the FP64 tensor path when the matrix fits in shared memory,
  * Householder tridiagonalisation + divide and conquer + back-transformation beyond), 1 = scalar one-sided Jacobi,
  * 2 = (matrices beyond shared memory) overlap orthogonaliser X = V s^-1/2 from the eigen-decomposition of S instead of

@@ -456,6 +456,9 @@ struct Oracle {
     int maxiter = 250;
     int guess = 0;  // 0 EEQ, 1 zero charges, 2 restart arrays
     double broydamp = 0.4;  // src/setparam.f90:226
+    // external point charges (src/type/pcem.f90; set through xtb_setExternalCharges, src/api/calculator.f90:470-540):
+    // positions [npc][3] in bohr, charges, hardness gam = chemical hardness of the element given for the charge
+    dvec pc_xyz, pc_q, pc_gam;
 
     Basis bas;
     // results / intermediates, by name
@@ -1316,10 +1319,26 @@ int singlepoint(Oracle& o) {
     const int ione = 1;
     const double g_a = 3.0, g_c = 2.0;
     double t_eig = 0;
+    // potential of the external point charges on the shells: jpot_pcem_gfn2, src/embedding.f90:225-256
+    const int npc = (int)o.pc_q.size();
+    dvec Vpc(nsh, 0.0);
+    double epcem = 0.0;
+    for (int s = 0; s < nsh && npc > 0; ++s) {
+        const double* ri = R(o, b.sh[s].atom);
+        double eh1 = 0.0;
+        for (int kk = 0; kk < npc; ++kk) {
+            double r2 = 0;
+            for (int k = 0; k < 3; ++k) { double dx = o.pc_xyz[3 * kk + k] - ri[k]; r2 += dx * dx; }
+            const double xj = 0.5 * (hard[s] + o.pc_gam[kk]);
+            eh1 += o.pc_q[kk] / std::sqrt(r2 + 1.0 / (xj * xj));
+        }
+        Vpc[s] = eh1;
+    }
     for (iter = 1; iter <= o.maxiter; ++iter) {
         // potentials: thirdorder.f90:100-131, coulomb.f90:89-114
         for (int i = 0; i < n; ++i) atomicShift[i] = 0.0;
-        for (int s = 0; s < nsh; ++s) shellShift[s] = 0.0 + qsh[s] * qsh[s] * gam3[s];
+        // shellShift(:) = externShift, scc_core.f90:438
+        for (int s = 0; s < nsh; ++s) shellShift[s] = Vpc[s] + qsh[s] * qsh[s] * gam3[s];
         scipy_dsymv_("L", &nsh, &one, jmat.data(), &nsh, qsh.data(), &ione, &one, shellShift.data(), &ione);
         setvsdq(o, true, q, dipm, qp, gab3, gab5, vs, vd, vq);
         // disppot, dftd4.F90:735-818
@@ -1454,6 +1473,12 @@ int singlepoint(Oracle& o) {
         ed = 0;
         for (int k = 0; k < ndim; ++k) ed += dumvec[k] * zetavec[k];
         eel = eel + ed;
+        // electro_pcem, src/embedding.f90:261-280, called at scc_core.f90:539-541
+        if (npc > 0) {
+            epcem = 0.0;
+            for (int s = 0; s < nsh; ++s) epcem += qsh[s] * Vpc[s];
+            eel += epcem;
+        }
         eel = eel + ga + gb;
 
         bool econverged = std::fabs(eel - eold) < scfconv;
@@ -1840,6 +1865,23 @@ int singlepoint(Oracle& o) {
         cn_chain(covpairs, dEdcn, grad);
     }
     D["grad_d4"] = grad;
+    if (npc > 0) {
+        // pcem_grad_gfn2, src/embedding.f90:329-365 (scf_module.F90:790-798): wfn%qsh = the mixed shell charges
+        dvec gpc(3 * npc, 0.0);
+        for (int s = 0; s < nsh; ++s) {
+            const int iat = b.sh[s].atom;
+            for (int j = 0; j < npc; ++j) {
+                double dr[3], r2 = 0;
+                for (int k = 0; k < 3; ++k) { dr[k] = R(o, iat)[k] - o.pc_xyz[3 * j + k]; r2 += dr[k] * dr[k]; }
+                double rr = 0.5 * (hard[s] + o.pc_gam[j]);
+                rr = 1.0 / (rr * rr);
+                const double yy = qsh[s] * o.pc_q[j] * std::pow(r2 + rr, -1.5);
+                for (int k = 0; k < 3; ++k) { grad[3 * iat + k] -= dr[k] * yy; gpc[3 * j + k] += dr[k] * yy; }
+            }
+        }
+        D["pcgradient"] = gpc;
+        D["e_pcem"] = dvec(1, epcem);
+    }
     {
         // getCoulombDerivsCluster + gemv, klopmanohno.F90:471-573, scf_module.F90:781-785
         int nth = o.nthreads;
@@ -1962,6 +2004,14 @@ void orc_set_threads(void* h, int nthreads) {
     scipy_openblas_set_num_threads(nthreads);
 }
 void orc_set_guess(void* h, int mode) { ((Oracle*)h)->guess = mode; }
+// external point charges: numbers -> hardness as in setExternalCharges_api (src/api/calculator.f90:530-535); npc = 0 releases
+void orc_set_pcem(void* h, int npc, const int* numbers, const double* q, const double* xyz) {
+    Oracle* o = (Oracle*)h;
+    o->pc_q.assign(q, q + npc);
+    o->pc_xyz.assign(xyz, xyz + 3 * npc);
+    o->pc_gam.resize(npc);
+    for (int i = 0; i < npc; ++i) o->pc_gam[i] = gfn2_chemical_hardness[numbers[i] - 1];
+}
 void orc_set_xyz(void* h, const double* xyz) { Oracle* o = (Oracle*)h; o->xyz.assign(xyz, xyz + 3 * o->nat); }
 void orc_set_restart(void* h, const double* qsh, int nsh, const double* dipm, const double* qp) {
     Oracle* o = (Oracle*)h;

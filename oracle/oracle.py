@@ -30,6 +30,7 @@ def lib():
         L.orc_set_threads.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.orc_set_guess.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.orc_set_xyz.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_set_pcem.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_set_restart.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_singlepoint.argtypes = [ctypes.c_void_p]
         L.orc_len64.restype = ctypes.c_long
@@ -71,6 +72,13 @@ class Oracle:
     def set_positions(self, positions):
         self.positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
         lib().orc_set_xyz(self.h, self.positions.ctypes.data)
+
+    def set_external_charges(self, numbers, charges, positions):
+        """xtb_setExternalCharges: element numbers (-> hardness), charges, positions [npc][3] in bohr; empty = release."""
+        numbers = np.ascontiguousarray(numbers, dtype=np.int32)
+        charges = np.ascontiguousarray(charges, dtype=np.float64)
+        positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+        lib().orc_set_pcem(self.h, len(numbers), numbers.ctypes.data, charges.ctypes.data, positions.ctypes.data)
 
     def set_restart(self, qsh, dipm, qp):
         qsh = np.ascontiguousarray(qsh, dtype=np.float64)

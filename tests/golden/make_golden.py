@@ -6,7 +6,7 @@ Run in the build container only (needs /root/reference):
     python tests/golden/make_golden.py
 
 Sources: test/unit/molstock.f90 (geometries), test/unit/test_gfn2.f90:48-235,667-742,831-901,
-987-1091, test/api/c_api_example.c:30-112, test/unit/test_coulomb.f90:828-1079,
+987-1091, test/api/c_api_example.c:30-112,298-419, test/unit/test_coulomb.f90:828-1079,
 test/unit/test_repulsion.f90, test/unit/test_eeq.f90.
 """
 import json
@@ -87,6 +87,21 @@ out["c3h4_api"] = dict(
              g_2_1=0.0, g_0_2=-0.74649908147372E-03, g_3_0=-0.28433755158510E-03, g_6_2=0.99750545315944E-02,
              q5=0.05184019996829, dipole2=-0.298279305689518, wbo9=2.89823984265213, tol=1e-9,
              source="test/unit/test_gfn2.f90:226-233; test/api/c_api_example.c:87-112"))
+# water dimer in the field of a second dimer given as external point charges: test/api/c_api_example.c:298-419
+out["h2o2_pcem_api"] = dict(
+    numbers=[8, 1, 1, 8, 1, 1],
+    xyz=[-2.75237178376284, 2.43247309226225, -0.01392519847964, -0.93157260886974, 2.79621404458590, -0.01863384029005,
+         -3.43820531288547, 3.30583608421060, 1.42134539425148, -2.43247309226225, -2.75237178376284, 0.01392519847964,
+         -2.79621404458590, -0.93157260886974, 0.01863384029005, -3.30583608421060, -3.43820531288547, -1.42134539425148],
+    charge=0.0, uhf=0,
+    pc_numbers=[8, 1, 1, 8, 1, 1],
+    pc_charges=[-0.69645733, 0.36031084, 0.33614649, -0.69645733, 0.36031084, 0.33614649],
+    pc_xyz=[2.75237178376284, -2.43247309226225, -0.01392519847964, 0.93157260886974, -2.79621404458590, -0.01863384029005,
+            3.43820531288547, -3.30583608421060, 1.42134539425148, 2.43247309226225, 2.75237178376284, 0.01392519847964,
+            2.79621404458590, 0.93157260886974, 0.01863384029005, 3.30583608421060, 3.43820531288547, -1.42134539425148],
+    kat=dict(energy=-10.160927754235, g_4_0=-2.0326750053811E-03, g_1_1=3.3125460324302E-03, g_3_0=-1.1929405354823E-03,
+             g_5_2=-1.6607683158587E-03, pcg_4_0=-0.000248319582, pcg_1_1=0.001420844475, pcg_3_0=0.003746685275,
+             pcg_5_2=0.000651613444, tol_energy=1e-9, tol_grad=1e-8, source="test/api/c_api_example.c:298-419"))
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_kat.json"), "w") as f:
     json.dump(out, f, indent=1)
 print("wrote", len(out), "systems")

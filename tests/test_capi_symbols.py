@@ -89,3 +89,32 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")) and "tables" not in dp:
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.lower() or f == "interface.py" and "oracle" not in txt, (dp, f)
+
+
+def test_external_charges_error_convention(lib):
+    """src/api/calculator.f90:470-540: errors go to the environment log, nothing is returned; releasing on a calculator
+    without charges is not an error (545-580)."""
+    vp = ctypes.c_void_p
+    env, calc = vp(lib.xtb_newEnvironment()), vp(lib.xtb_newCalculator())
+    n = ctypes.c_int(1)
+    nu, q, x = np.array([8], dtype=np.int32), np.array([0.5]), np.zeros(3)
+    ip, dp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
+    lib.xtb_setExternalCharges(env, calc, ctypes.byref(n), nu.ctypes.data_as(ip), q.ctypes.data_as(dp), x.ctypes.data_as(dp))
+    assert lib.xtb_checkEnvironment(env) == 1           # no parametrisation loaded
+    buf, ln = ctypes.create_string_buffer(512), ctypes.c_int(512)
+    lib.xtb_getError(env, buf, ctypes.byref(ln))
+    assert b"No calculator loaded" in buf.value
+    n0 = ctypes.c_int(0)
+    lib.xtb_setExternalCharges(env, calc, ctypes.byref(n0), nu.ctypes.data_as(ip), q.ctypes.data_as(dp), x.ctypes.data_as(dp))
+    assert lib.xtb_checkEnvironment(env) == 1
+    lib.xtb_getError(env, buf, ctypes.byref(ln))
+    lib.xtb_releaseExternalCharges(env, calc)
+    assert lib.xtb_checkEnvironment(env) == 0
+    res = vp(lib.xtb_newResults())
+    g = np.zeros(3)
+    lib.xtb_getPCGradient(env, res, g.ctypes.data_as(dp))
+    assert lib.xtb_checkEnvironment(env) == 1
+    lib.xtb_getError(env, buf, ctypes.byref(ln))
+    lib.xtb_delResults(ctypes.byref(res))
+    lib.xtb_delCalculator(ctypes.byref(calc))
+    lib.xtb_delEnvironment(ctypes.byref(env))

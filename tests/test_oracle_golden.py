@@ -105,3 +105,54 @@ def test_restart_converges_immediately(kat):
     assert o.singlepoint() == 0
     assert o.info["niter"] <= 3 < n1
     assert abs(o.energies["e_total"] - e1) < 1e-7
+
+
+def test_external_point_charges_api_kat(kat):
+    # test/api/c_api_example.c:298-419: water dimer embedded in the point charges of a second dimer;
+    # energy 1e-9, gradient and point-charge gradient components 1e-8 (the reference's own tolerances)
+    s = kat["h2o2_pcem_api"]
+    k = s["kat"]
+    o = Oracle(s["numbers"], s["xyz"])
+    o.set_external_charges(s["pc_numbers"], s["pc_charges"], np.array(s["pc_xyz"]).reshape(-1, 3))
+    assert o.singlepoint() == 0
+    assert abs(o.energies["e_total"] - k["energy"]) < k["tol_energy"]
+    g = o.get("gradient").reshape(-1, 3)
+    pg = o.get("pcgradient").reshape(-1, 3)
+    for key, val in k.items():
+        if key.startswith("g_"):
+            i, c = map(int, key[2:].split("_"))
+            assert abs(g[i, c] - val) < k["tol_grad"], key
+        if key.startswith("pcg_"):
+            i, c = map(int, key[4:].split("_"))
+            assert abs(pg[i, c] - val) < k["tol_grad"], key
+    # releasing the charges gives back the gas-phase dimer
+    o.set_external_charges([], [], np.zeros((0, 3)))
+    assert o.singlepoint() == 0
+    o2 = Oracle(s["numbers"], s["xyz"])
+    assert o2.singlepoint() == 0
+    assert abs(o.energies["e_total"] - o2.energies["e_total"]) < 1e-12
+
+
+def test_external_point_charges_gradient_is_consistent(kat):
+    # finite differences of the embedded energy with respect to an atom and to a point charge position
+    s = kat["h2o2_pcem_api"]
+    pcx = np.array(s["pc_xyz"]).reshape(-1, 3)
+
+    def run(xyz, pc):
+        o = Oracle(s["numbers"], xyz, acc=0.01)
+        o.set_external_charges(s["pc_numbers"], s["pc_charges"], pc)
+        assert o.singlepoint() == 0
+        return o
+
+    o = run(s["xyz"], pcx)
+    g = o.get("gradient").reshape(-1, 3)
+    pg = o.get("pcgradient").reshape(-1, 3)
+    h = 1e-4
+    for which, i, c in [("atom", 1, 1), ("pc", 3, 0)]:
+        e = []
+        for sgn in (+1, -1):
+            x, p = s["xyz"].copy(), pcx.copy()
+            (x if which == "atom" else p)[i, c] += sgn * h
+            e.append(run(x, p).energies["e_total"])
+        fd = (e[0] - e[1]) / (2 * h)
+        assert abs(fd - (g if which == "atom" else pg)[i, c]) < 2e-7

@@ -55,9 +55,13 @@ struct _xtb_TCalculator {
     double accuracy = 1.0, etemp = 300.0;
     int maxiter = 250;
     bool loaded = false;
+    // external point charges (src/type/pcem.f90): element numbers (-> hardness), charges, positions in bohr
+    std::vector<int> pc_numbers;
+    std::vector<double> pc_q, pc_xyz;
 };
 struct _xtb_TResults {
-    bool has_energy = false, has_gradient = false, has_wfn = false, has_dipole = false;
+    bool has_energy = false, has_gradient = false, has_wfn = false, has_dipole = false, has_pcgradient = false;
+    std::vector<double> pcgradient;
     int n = 0, nao = 0, nshell = 0;
     double energy = 0, egap = 0;
     std::vector<double> gradient, q, qsh, dipm, qp, wbo, emo, focc, C;
@@ -233,10 +237,25 @@ void xtb_releaseSolvent(xtb_TEnvironment env, xtb_TCalculator calc) {
     if (!check_env(env)) return;
     if (!calc) env->error("Calculator object is not allocated", "xtb_api_releaseSolvent");
 }
-void xtb_setExternalCharges(xtb_TEnvironment env, xtb_TCalculator, int*, int*, double*, double*) { unsupported(env, "Point charge embedding", "xtb_api_setExternalCharges"); }
+// src/api/calculator.f90:470-540
+void xtb_setExternalCharges(xtb_TEnvironment env, xtb_TCalculator calc, int* n, int* numbers, double* charges, double* positions) {
+    const char* source = "xtb_api_setExternalCharges";
+    if (!check_env(env)) return;
+    if (!n || !numbers || !charges || !positions) { env->error("External charges are not fully specified", source); return; }
+    if (*n <= 0) { env->error("Negative number of point charges provided", source); return; }
+    if (!calc) { env->error("Singlepoint calculator is not allocated", source); return; }
+    if (!calc->loaded) { env->error("No calculator loaded to add external potential", source); return; }
+    for (int i = 0; i < *n; ++i)
+        if (numbers[i] < 1 || numbers[i] > 86) { env->error("Element of an external charge is not parametrised in GFN2-xTB", source); return; }
+    calc->pc_numbers.assign(numbers, numbers + *n);
+    calc->pc_q.assign(charges, charges + *n);
+    calc->pc_xyz.assign(positions, positions + 3 * (size_t)*n);
+}
+// src/api/calculator.f90:545-580: no errors on calculators without point charges
 void xtb_releaseExternalCharges(xtb_TEnvironment env, xtb_TCalculator calc) {
     if (!check_env(env)) return;
-    if (!calc) env->error("Calculator object is not allocated", "xtb_api_releaseExternalCharges");
+    if (!calc) { env->error("Singlepoint calculator is not allocated", "xtb_api_releaseExternalCharges"); return; }
+    calc->pc_numbers.clear(); calc->pc_q.clear(); calc->pc_xyz.clear();
 }
 void xtb_setAccuracy(xtb_TEnvironment env, xtb_TCalculator calc, double accuracy) {
     const char* source = "xtb_api_setAccuracy";
@@ -283,6 +302,9 @@ void xtb_singlepoint(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator ca
         b.set_options(calc->accuracy, calc->etemp, calc->maxiter);
         b.set_guess(0);
         b.set_positions(mol->xyz.data());
+        const int npc = (int)calc->pc_q.size();
+        if (npc > 0) b.set_external_charges(&npc, calc->pc_numbers.data(), calc->pc_q.data(), calc->pc_xyz.data());
+        else if (b.external_charge_count() > 0) b.release_external_charges();
         if (cached) b.set_wavefunction(res->qsh.data(), res->dipm.data(), res->qp.data());
         else b.invalidate_wavefunction();
         int nfail = b.singlepoint(true);
@@ -299,6 +321,9 @@ void xtb_singlepoint(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator ca
         res->focc.resize(nao); b.fetch("focc", res->focc.data());
         res->C.resize((size_t)nao * nao); b.fetch("C", res->C.data());
         for (int k = 0; k < 3; ++k) res->dipole[k] = r.dipole[k];
+        res->has_pcgradient = npc > 0;   // src/api/interface.f90:111-113,148-150
+        res->pcgradient.clear();
+        if (npc > 0) { res->pcgradient.resize(3 * (size_t)npc); b.fetch("pcgradient", res->pcgradient.data()); }
         res->has_energy = res->has_gradient = res->has_wfn = res->has_dipole = true;
         if (env->verbosity > 0) {
             FILE* f = env->out();
@@ -347,9 +372,10 @@ void xtb_getGradient(xtb_TEnvironment env, xtb_TResults res, double* gradient) {
     if (!res->has_gradient) { env->error("Gradient is not available in results", source); return; }
     if (gradient) std::memcpy(gradient, res->gradient.data(), res->gradient.size() * sizeof(double));
 }
-void xtb_getPCGradient(xtb_TEnvironment env, xtb_TResults res, double*) {
+void xtb_getPCGradient(xtb_TEnvironment env, xtb_TResults res, double* gradient) {
     XTB_GETTER_PROLOGUE("xtb_api_getPCGradient")
-    env->error("Gradient on external charges is not available in results", source);
+    if (!res->has_pcgradient) { env->error("Gradient on external charges is not available in results", source); return; }
+    if (gradient) std::copy(res->pcgradient.begin(), res->pcgradient.end(), gradient);
 }
 void xtb_getVirial(xtb_TEnvironment env, xtb_TResults res, double* virial) {
     XTB_GETTER_PROLOGUE("xtb_api_getVirial")
@@ -439,6 +465,13 @@ int xtbb200_setWavefunction(xtbb200_TBatch batch, const double* qsh, const doubl
     if (!batch) throw std::runtime_error("batch is not allocated");
     if (!qsh || !dipm || !qp) { batch->b->invalidate_wavefunction(); return 0; }
     batch->b->set_wavefunction(qsh, dipm, qp);
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_setExternalCharges(xtbb200_TBatch batch, const int* npc, const int* numbers, const double* charges, const double* positions) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    batch->b->set_external_charges(npc, numbers, charges, positions);
     return 0;
     XTBB_CATCH(-1)
 }

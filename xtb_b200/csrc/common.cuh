@@ -30,6 +30,7 @@ struct MolState {
     int pad0;
     double eel, eold, ees, eaes, epol, ed, egap, ga, gb, efa, efb, rmsq;
     double ep, embd, eh0;
+    double epcem;    // interaction energy of the shell charges with the external point charges
     double energy, gnorm;
     double dipole[3];
 };
@@ -82,6 +83,11 @@ struct Dev {
     // two-level Jacobi (large matrices): G in HBM, per block pair Gram matrix / rotation, flags and counters
     double *hjG, *hjM, *hjJ, *hj_sigma;
     int *hj_flag, *hj_count, *hj_conv;
+    // external point charges (xtb_setExternalCharges): per molecule the range [pc0[im], pc0[im+1]) of the concatenated
+    // arrays; pc0 == nullptr: none.  vpc: their potential on the shells, pc_grad: gradient on the charges
+    const long long* pc0;
+    const double *pc_xyz, *pc_q, *pc_gam;
+    double *pc_grad, *vpc;
     // shell-pair gradient partials
     double *gpair;   // [npair][4] : gx,gy,gz,dCN
     const long long* pair0;

@@ -158,6 +158,11 @@ struct Batch::Impl {
     Dev d;
     EighWork eig;             // Householder + divide-and-conquer eigensolver for matrices beyond shared memory
     bool have_eig = false;
+    std::vector<long long> h_pc0;  // external point charges: per-molecule ranges (empty: none)
+    int max_npc = 0;
+    long long pc_cap = 0;          // capacity (charges) of the device buffers below
+    long long* pc0_dev = nullptr;
+    double* pc_buf = nullptr;      // [gam | q | xyz(3) | grad(3)] x pc_cap
     std::vector<int> h_done;  // per-molecule "left the SCC loop" flags, mirrored for the per-molecule solver loop
     std::vector<void*> allocs;
     std::vector<long long> eeq0, pair0;
@@ -202,6 +207,7 @@ struct Batch::Impl {
     }
     ~Impl() {
         for (void* p : allocs) cudaFree(p);
+        if (pc_buf) cudaFree(pc_buf);
         if (have_eig) eig.release();
         for (auto& e : ev_pool) cudaEventDestroy(e);
         for (auto& e : ev_phase) if (e) cudaEventDestroy(e);
@@ -405,6 +411,47 @@ void Batch::set_wavefunction(const double* qsh, const double* dipm, const double
     I.have_wfn = true;
 }
 
+void Batch::set_external_charges(const int* npc, const int* numbers, const double* charges, const double* xyz) {
+    Impl& I = *p_;
+    XTB_CUDA_CHECK(cudaSetDevice(I.device));
+    XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+    const int nmol = I.d.nmol;
+    long long tot = 0;
+    if (npc) for (int i = 0; i < nmol; ++i) { if (npc[i] < 0) throw std::runtime_error("negative number of point charges"); tot += npc[i]; }
+    I.d.pc0 = nullptr; I.d.pc_xyz = I.d.pc_q = I.d.pc_gam = nullptr; I.d.pc_grad = nullptr;
+    I.h_pc0.clear(); I.max_npc = 0;
+    if (tot == 0) return;
+    if (!numbers || !charges || !xyz) throw std::runtime_error("external charges: numbers, charges and positions are required");
+    I.h_pc0.assign(nmol + 1, 0);
+    for (int i = 0; i < nmol; ++i) { I.h_pc0[i + 1] = I.h_pc0[i] + npc[i]; I.max_npc = std::max(I.max_npc, npc[i]); }
+    std::vector<double> gam(tot);
+    for (long long k = 0; k < tot; ++k) {
+        if (numbers[k] < 1 || numbers[k] > 86) throw std::runtime_error("external charges: element number outside 1..86");
+        gam[k] = gfn2_chemical_hardness[numbers[k] - 1];   // src/api/calculator.f90:533
+    }
+    if (!I.pc0_dev) I.pc0_dev = I.dalloc<long long>(nmol + 1);
+    if (!I.d.vpc) I.d.vpc = I.dalloc<double>(I.sys.shells.size());
+    if (tot > I.pc_cap) {   // grow-only buffer, so that per-step updates (QM/MM) do not allocate
+        if (I.pc_buf) cudaFree(I.pc_buf);
+        I.pc_buf = nullptr;
+        XTB_CUDA_CHECK(cudaMalloc((void**)&I.pc_buf, (size_t)tot * 8 * sizeof(double)));
+        I.pc_cap = tot;
+    }
+    double* gam_d = I.pc_buf;
+    double* q_d = I.pc_buf + I.pc_cap;
+    double* xyz_d = I.pc_buf + 2 * I.pc_cap;
+    double* grd_d = I.pc_buf + 5 * I.pc_cap;
+    XTB_CUDA_CHECK(cudaMemcpyAsync(I.pc0_dev, I.h_pc0.data(), (nmol + 1) * sizeof(long long), cudaMemcpyHostToDevice, I.stream));
+    XTB_CUDA_CHECK(cudaMemcpyAsync(gam_d, gam.data(), tot * sizeof(double), cudaMemcpyHostToDevice, I.stream));
+    XTB_CUDA_CHECK(cudaMemcpyAsync(q_d, charges, tot * sizeof(double), cudaMemcpyHostToDevice, I.stream));
+    XTB_CUDA_CHECK(cudaMemcpyAsync(xyz_d, xyz, 3 * tot * sizeof(double), cudaMemcpyHostToDevice, I.stream));
+    XTB_CUDA_CHECK(cudaMemsetAsync(grd_d, 0, 3 * tot * sizeof(double), I.stream));
+    XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+    I.d.pc0 = I.pc0_dev; I.d.pc_gam = gam_d; I.d.pc_q = q_d; I.d.pc_xyz = xyz_d; I.d.pc_grad = grd_d;
+}
+void Batch::release_external_charges() { set_external_charges(nullptr, nullptr, nullptr, nullptr); }
+long long Batch::external_charge_count() const { return p_->h_pc0.empty() ? 0 : p_->h_pc0.back(); }
+
 template <int TG>
 static void launch_jacobi(Dev& d, int nmol, int max_nao, bool sm, cudaStream_t st) {
     const int npairs = (max_nao + 1) / 2;
@@ -463,6 +510,7 @@ int Batch::singlepoint(bool restart) {
     KL(K_SETUP, k_jmat<<<grid2((long long)s.max_nsh * s.max_nsh, 256, nmol), 256, 0, st>>>(d));
     KL(K_SETUP, k_dispmat<<<grid2((long long)s.max_ndim * s.max_ndim, 256, nmol), 256, 0, st>>>(d));
     KL(K_SETUP, k_repulsion<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
+    if (d.pc0) KL(K_SETUP, k_pcem_pot<<<grid2(s.max_nsh, B, nmol), B, 0, st>>>(d));
     // ---- guess (src/api/interface.f90:82-101: reuse the cached wavefunction when present)
     if (!(restart && I.have_wfn)) {
         if (I.guess == 0) {
@@ -642,6 +690,10 @@ int Batch::singlepoint(bool restart) {
     KL(K_GRAD_D4, k_d4_c6<<<grid2((long long)s.max_nat * s.max_nat, 128, nmol), 128, 0, st>>>(d));
     KL(K_GRAD_D4, k_grad_pairs<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
     KL(K_GRAD_ATM, k_grad_atm<<<dim3(s.max_nat, nmol), 128, (size_t)s.max_nat * sizeof(double), st>>>(d));
+    if (d.pc0) {
+        KL(K_GRAD_MISC, k_grad_pcem_atoms<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+        KL(K_GRAD_MISC, k_grad_pcem_charges<<<grid2(std::max(I.max_npc, 1), 64, nmol), 64, 0, st>>>(d));
+    }
     const int na_tot = (int)s.atoms.size();
     if (R > 1) {   // dE/dCN vectors and ATM energies: owned / partial -> complete on every rank
         I.prof_begin(K_COMM, st);
@@ -765,6 +817,7 @@ MolResult Batch::result(int i) const {
     MolResult r;
     r.energy = s.energy; r.e_elec = s.eel + s.embd; r.e_rep = s.ep; r.e_es = s.ees; r.e_aes = s.eaes; r.e_axc = s.epol;
     r.e_disp = s.ed + s.embd; r.hl_gap = s.egap; r.gnorm = s.gnorm; r.e_atm = s.embd;
+    r.e_pcem = s.epcem;
     r.niter = s.iter; r.converged = s.converged; r.fail = s.fail; r.ndp = s.ndp; r.nqp = s.nqp; r.sweeps = s.sweeps_total;
     for (int k = 0; k < 3; ++k) r.dipole[k] = s.dipole[k];
     return r;
@@ -784,6 +837,7 @@ void Batch::fetch(const char* name, double* out) const {
         {"gab3", d.gab3, tn}, {"gab5", d.gab5, tn}, {"jmat", d.jmat, (size_t)I.sys.tot_ss},
         {"dispmat", d.dispmat, (size_t)I.sys.tot_dd}, {"gw", d.gw, nr}, {"selfenergy", d.selfE, ns}, {"xyz", d.xyz, 3 * na},
         {"vs", d.vs, na}, {"vd", d.vd, 3 * na}, {"vq", d.vq, 6 * na}, {"q_out", d.q_out, na}, {"qsh_out", d.qsh_out, ns},
+        {"pcgradient", d.pc_grad, 3 * (size_t)external_charge_count()},
     };
     XTB_CUDA_CHECK(cudaSetDevice(I.device));
     for (const E& e : tab)
@@ -811,6 +865,7 @@ size_t Batch::fetch_len(const char* name) const {
     if (n == "jmat") return (size_t)I.sys.tot_ss;
     if (n == "dispmat") return (size_t)I.sys.tot_dd;
     if (n == "gw") return nr;
+    if (n == "pcgradient") return 3 * (size_t)external_charge_count();
     throw std::runtime_error(std::string("unknown array: ") + name);
 }
 void Batch::fetch_mask(unsigned char* out) const {

@@ -7,6 +7,7 @@ namespace xtbb200 {
 struct MolResult {
     double energy, e_elec, e_rep, e_es, e_aes, e_axc, e_disp, hl_gap, gnorm, e_atm;
     double dipole[3];
+    double e_pcem;   // interaction with external point charges (part of e_elec)
     int niter, converged, fail, ndp, nqp, sweeps;
 };
 
@@ -42,6 +43,12 @@ class Batch {
     void set_positions(const double* xyz_host);    // concatenated (3, natoms) in bohr, host memory
     void set_positions_device(const double* xyz_dev);
     void set_wavefunction(const double* qsh, const double* dipm, const double* qp);
+    // external point charges (xtb_setExternalCharges, src/api/calculator.f90:470-540): npc[nmol] charges per molecule,
+    // concatenated element numbers (-> chemical hardness), charges, positions [npc][3] in bohr; all null / zero: release.
+    // The gradient on the charges of the last single point is fetch("pcgradient").
+    void set_external_charges(const int* npc, const int* numbers, const double* charges, const double* xyz);
+    void release_external_charges();
+    long long external_charge_count() const;
     void invalidate_wavefunction();
     bool has_wavefunction() const;
     // runs SP + gradient for every molecule; returns the number of molecules that failed / did not converge

@@ -427,6 +427,44 @@ __global__ void k_grad_pairs(Dev d) {
     d.dEdcn[m.at0 + i] = dE;
 }
 
+// gradient of the point charge embedding (pcem_grad_gfn2, src/embedding.f90:329-365) with the mixed shell charges.
+// Two passes without atomics: thread per atom for the molecular gradient, thread per point charge for theirs.
+__global__ void k_grad_pcem_atoms(Dev d) {
+    const MolDesc m = d.mol[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.nat || !shard_owns_atom(d, i)) return;
+    const AtomPar ai = d.atoms[m.at0 + i];
+    const double* xi = d.xyz + 3 * (m.at0 + i);
+    double g[3] = {0, 0, 0};
+    for (int s = 0; s < ai.nsh; ++s) {
+        const double hs = d.shells[m.sh0 + ai.sh0 + s].hard, qs = d.qsh[m.sh0 + ai.sh0 + s];
+        for (long long j = d.pc0[blockIdx.y]; j < d.pc0[blockIdx.y + 1]; ++j) {
+            const double dr[3] = {xi[0] - d.pc_xyz[3 * j], xi[1] - d.pc_xyz[3 * j + 1], xi[2] - d.pc_xyz[3 * j + 2]};
+            double rr = 0.5 * (hs + d.pc_gam[j]);
+            rr = 1.0 / (rr * rr);
+            const double yy = qs * d.pc_q[j] * pow(dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2] + rr, -1.5);
+            for (int k = 0; k < 3; ++k) g[k] -= dr[k] * yy;
+        }
+    }
+    for (int k = 0; k < 3; ++k) d.grad[3 * (m.at0 + i) + k] += g[k];
+}
+__global__ void k_grad_pcem_charges(Dev d) {
+    const MolDesc m = d.mol[blockIdx.y];
+    const long long j = d.pc0[blockIdx.y] + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d.pc0[blockIdx.y + 1]) return;
+    double g[3] = {0, 0, 0};
+    for (int s = 0; s < m.nsh; ++s) {
+        const ShellPar& sp = d.shells[m.sh0 + s];
+        const double* xi = d.xyz + 3 * (m.at0 + sp.atom);
+        const double dr[3] = {xi[0] - d.pc_xyz[3 * j], xi[1] - d.pc_xyz[3 * j + 1], xi[2] - d.pc_xyz[3 * j + 2]};
+        double rr = 0.5 * (sp.hard + d.pc_gam[j]);
+        rr = 1.0 / (rr * rr);
+        const double yy = d.qsh[m.sh0 + s] * d.pc_q[j] * pow(dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2] + rr, -1.5);
+        for (int k = 0; k < 3; ++k) g[k] += dr[k] * yy;
+    }
+    for (int k = 0; k < 3; ++k) d.pc_grad[3 * j + k] = g[k];
+}
+
 // Axilrod-Teller-Muto three-body term with neutral reference weights (atm_gradient_latp,
 // deriv_atm_triple): one CTA per atom a, threads over partner pairs (b strided over the CTA, c < b); each triple is
 // visited from its three atoms, every CTA accumulates only its own gradient / dE/dCN and reduces in a fixed order

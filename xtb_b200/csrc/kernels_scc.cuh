@@ -45,7 +45,25 @@ __global__ void k_pot_shell(Dev d) {
     const double* q = d.qsh + m.sh0;
     double acc = 0;
     for (int t = 0; t < m.nsh; ++t) acc += J[s + (long long)m.nsh * t] * q[t];
-    d.sshift[m.sh0 + s] = q[s] * q[s] * d.shells[m.sh0 + s].gam3 + acc;
+    // shellShift(:) = externShift (scc_core.f90:438): the potential of the external point charges, if any
+    const double ext = d.pc0 ? d.vpc[m.sh0 + s] : 0.0;
+    d.sshift[m.sh0 + s] = ext + q[s] * q[s] * d.shells[m.sh0 + s].gam3 + acc;
+}
+
+// potential of the external point charges on the shells (jpot_pcem_gfn2, src/embedding.f90:225-256); thread per shell
+__global__ void k_pcem_pot(Dev d) {
+    const MolDesc m = d.mol[blockIdx.y];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m.nsh) return;
+    const ShellPar& sp = d.shells[m.sh0 + s];
+    const double* ri = d.xyz + 3 * (m.at0 + sp.atom);
+    double eh1 = 0.0;
+    for (long long kk = d.pc0[blockIdx.y]; kk < d.pc0[blockIdx.y + 1]; ++kk) {
+        const double dx = d.pc_xyz[3 * kk] - ri[0], dy = d.pc_xyz[3 * kk + 1] - ri[1], dz = d.pc_xyz[3 * kk + 2] - ri[2];
+        const double xj = 0.5 * (sp.hard + d.pc_gam[kk]);
+        eh1 += d.pc_q[kk] * (1.0 / sqrt(dx * dx + dy * dy + dz * dz + 1.0 / (xj * xj)));
+    }
+    d.vpc[m.sh0 + s] = eh1;
 }
 
 // anisotropic potentials vs, vd, vq; SHIFT = true: setvsdq (SCC), false: setdvsdq (gradient). thread per atom
@@ -493,10 +511,17 @@ __global__ void __launch_bounds__(256) k_scc_finish(Dev d) {
     p = 0;
     for (int k = tid; k < m.ndim; k += nt) p += 0.5 * d.dvec[m.ref0 + k] * d.zeta[m.ref0 + k];
     const double ed = block_sum(p, red);
+    double epcem = 0.0;
+    if (d.pc0) {   // electro_pcem, src/embedding.f90:261-280 (scc_core.f90:539-541)
+        p = 0;
+        for (int s = tid; s < m.nsh; s += nt) p += d.qsh_out[m.sh0 + s] * d.vpc[m.sh0 + s];
+        epcem = block_sum(p, red);
+    }
     const double eold = st.eel;
     double eel = ees + eh0 * kEVtoAU;
     eel = eel + eaes + epol;
     eel = eel + ed;
+    eel = eel + epcem;
     eel = eel + st.ga + st.gb;
     const bool econv = fabs(eel - eold) < d.scfconv;
     // --- charge difference vector (gfn2broyden_save/diff, aespot.F90:1360-1425)
@@ -612,7 +637,7 @@ __global__ void __launch_bounds__(256) k_scc_finish(Dev d) {
         d.q[m.at0 + i] = s;
     }
     if (tid == 0) {
-        st.eold = eold; st.eel = eel; st.ees = ees; st.eaes = eaes; st.epol = epol; st.ed = ed; st.eh0 = eh0;
+        st.eold = eold; st.eel = eel; st.ees = ees; st.eaes = eaes; st.epol = epol; st.ed = ed; st.eh0 = eh0; st.epcem = epcem;
         st.rmsq = rmsq;
         st.iter = iter;
         if (econv && qconv) {

@@ -69,6 +69,7 @@ def load_library():
         "xtbb200_delBatch": (None, [ctypes.POINTER(vp)]),
         "xtbb200_setOptions": (ci, [vp, cd, cd, ci, ci]),
         "xtbb200_setSolver": (ci, [vp, ci]),
+        "xtbb200_setExternalCharges": (ci, [vp, _c_int_p, _c_int_p, _c_double_p, _c_double_p]),
         "xtbb200_symmetricEigen": (ci, [ci, _c_double_p, _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_float), ci]),
         "xtbb200_setWavefunction": (ci, [vp, _c_double_p, _c_double_p, _c_double_p]),
         "xtbb200_shardUniqueId": (ci, [ctypes.c_char_p, ctypes.c_size_t]),
@@ -258,6 +259,10 @@ class Results(Environment):
     def get_gradient(self):
         return self._array(self._lib.xtb_getGradient, (self._natoms, 3), "Gradient is not available")
 
+    def get_pc_gradient(self, npc):
+        """Gradient on the external point charges of the last single point (xtb_getPCGradient), shape (npc, 3)."""
+        return self._array(self._lib.xtb_getPCGradient, (int(npc), 3), "Gradient on external charges is not available")
+
     def get_virial(self):
         return self._array(self._lib.xtb_getVirial, (3, 3), "Virial is not available")
 
@@ -334,6 +339,12 @@ class Calculator(Molecule):
         po = np.ascontiguousarray(positions, dtype=np.float64)
         self._lib.xtb_setExternalCharges(self._env, self._calc, ctypes.byref(n), _ip(nu), _dp(ch), _dp(po))
         self.raise_on_error("Failed to set external charges")
+        self._npc = len(nu)
+
+    def release_external_charges(self):
+        self._lib.xtb_releaseExternalCharges(self._env, self._calc)
+        self.raise_on_error("Failed to release external charges")
+        self._npc = 0
 
     def singlepoint(self, res=None, copy=False):
         _res = Results(self) if res is None else (Results(res) if copy else res)
@@ -389,8 +400,21 @@ class BatchCalculator:
         a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (qsh, dipm, qp))
         self._check(self._lib.xtbb200_setWavefunction(self._b, _dp(a), _dp(b), _dp(c)))
 
+    def set_external_charges(self, npc=None, numbers=None, charges=None, positions=None):
+        """Point charges per molecule (xtbb200_setExternalCharges): npc[nmol], concatenated numbers / charges / positions
+        (bohr); None releases them.  Gradient on the charges after a single point: array("pcgradient")."""
+        if npc is None:
+            self._check(self._lib.xtbb200_setExternalCharges(self._b, None, None, None, None))
+            return
+        n = np.ascontiguousarray(npc, dtype=np.int32)
+        nu = np.ascontiguousarray(numbers, dtype=np.int32)
+        ch = np.ascontiguousarray(charges, dtype=np.float64)
+        po = np.ascontiguousarray(positions, dtype=np.float64)
+        assert len(nu) == int(n.sum()) == len(ch) and po.size == 3 * len(ch)
+        self._check(self._lib.xtbb200_setExternalCharges(self._b, _ip(n), _ip(nu), _dp(ch), _dp(po)))
+
     def set_solver(self, mode):
-        """0: automatic, 1: scalar Jacobi kernel."""
+        """0: automatic, 1: scalar Jacobi kernel, 2: X from eig(S), 3: two-level Jacobi for large matrices."""
         self._check(self._lib.xtbb200_setSolver(self._b, int(mode)))
 
     def set_shard(self, rank, nranks, unique_id=None):
