@@ -1,0 +1,193 @@
+"""Thin command line front end: `python -m xtb_b200 mol.xyz --gfn 2 --grad` (the `xtb mol.xyz --gfn 2 --grad` call of
+BASELINE configs[0]) on the CUDA engine, through the xtb.h C ABI.
+
+Covers what the single point path of the reference's driver needs (src/prog/main.F90:224-399,721,1020-1048): geometry
+readers for xyz and Turbomole coord files (the reference delegates them to mctc-lib, which is not part of its tree; the
+formats are the published ones), the run-type flags of a single point with gradient, and the result files `energy`,
+`gradient` (src/io/writer/turbomole.f90:32-123), `charges` (src/main/property.F90:189-192, one f14.8 per atom) and `wbo`
+(src/main/property.F90:228-231,869-881, pairs above 0.1).  Everything else the reference's CLI offers (optimisation, MD,
+hessian, solvation, other Hamiltonians) is refused with an error instead of being ignored.
+"""
+import argparse
+import sys
+import time
+
+import numpy as np
+
+SYMBOLS = ("H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr "
+           "Rb Sr Y Zr Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe Cs Ba La Ce Pr Nd Pm Sm Eu Gd Tb Dy Ho Er Tm Yb Lu "
+           "Hf Ta W Re Os Ir Pt Au Hg Tl Pb Bi Po At Rn").split()
+AATOAU = 1.0 / 0.529177210903   # mctc-lib's conversion (CODATA 2018), used by its geometry readers
+
+
+def _number(sym):
+    s = sym.strip().capitalize()
+    if s.isdigit():
+        return int(s)
+    s = "".join(ch for ch in s if ch.isalpha())
+    if s not in SYMBOLS:
+        raise ValueError("unknown element symbol '%s'" % sym)
+    return SYMBOLS.index(s) + 1
+
+
+def read_xyz(text):
+    """Xmol xyz: atom count, comment line, then `symbol x y z` in Angstrom."""
+    lines = text.splitlines()
+    n = int(lines[0].split()[0])
+    numbers, xyz = [], []
+    for ln in lines[2:2 + n]:
+        t = ln.split()
+        numbers.append(_number(t[0]))
+        xyz.append([float(x.replace("d", "e").replace("D", "e")) for x in t[1:4]])
+    if len(numbers) != n:
+        raise ValueError("xyz file ends before %d atoms were read" % n)
+    return np.array(numbers, dtype=np.int32), np.array(xyz) * AATOAU
+
+
+def read_coord(text):
+    """Turbomole coord: `$coord [angs]` block of `x y z symbol` lines (bohr unless `angs`), ended by the next `$` group."""
+    numbers, xyz, scale, inside = [], [], 1.0, False
+    for ln in text.splitlines():
+        s = ln.strip()
+        if not s or s.startswith("#"):
+            continue
+        if s.startswith("$"):
+            if inside:
+                break
+            if s.lower().startswith("$coord"):
+                inside = True
+                if "angs" in s.lower():
+                    scale = AATOAU
+                elif "frac" in s.lower():
+                    raise ValueError("fractional coordinates need a lattice: periodic systems are outside the engine's scope")
+            continue
+        if inside:
+            t = s.split()
+            xyz.append([float(x) for x in t[:3]])
+            numbers.append(_number(t[3]))
+    if not numbers:
+        raise ValueError("no $coord block found")
+    return np.array(numbers, dtype=np.int32), np.array(xyz) * scale
+
+
+def read_geometry(path):
+    with open(path) as f:
+        text = f.read()
+    if path.lower().endswith(".xyz"):
+        return read_xyz(text)
+    if "$coord" in text.lower():
+        return read_coord(text)
+    return read_xyz(text)
+
+
+def _fortran_e(x, width, digits):
+    """Fortran ESw.d: one non-zero digit before the point (Python's %E gives the same normalisation)."""
+    return ("%" + "%d.%dE" % (width, digits)) % x
+
+
+def write_turbomole(numbers, xyz, energy, gradient, iter_number=1, energy_file="energy", gradient_file="gradient"):
+    """src/io/writer/turbomole.f90:96-123: `$energy` and `$grad` groups, each closed by `$end`."""
+    with open(energy_file, "w") as f:
+        f.write("$energy\n")
+        f.write("%6d%18.11f%18.11f%18.11f\n" % (1, energy, energy, energy))
+        f.write("$end\n")
+    if gradient is None:
+        return
+    with open(gradient_file, "w") as f:
+        f.write("$grad\n")
+        f.write("  cycle = %6d    SCF energy =%18.11f   |dE/dxyz| =%10.6f\n" % (iter_number, energy, np.linalg.norm(gradient)))
+        for z, r in zip(numbers, xyz):
+            f.write("%20.14f  %20.14f  %20.14f      %-2s\n" % (r[0], r[1], r[2], SYMBOLS[z - 1].lower()))
+        for g in gradient:
+            f.write("".join(_fortran_e(v, 22, 13) for v in g) + "\n")
+        f.write("$end\n")
+
+
+def read_turbomole_gradient(path):
+    """Inverse of write_turbomole for the last `cycle` of a gradient file: (energy, xyz, gradient)."""
+    with open(path) as f:
+        lines = [ln for ln in f.read().splitlines() if ln.strip() and not ln.startswith("$")]
+    energy = float(lines[0].split("SCF energy =")[1].split()[0])
+    body = lines[1:]
+    n = len(body) // 2
+    xyz = np.array([[float(x) for x in ln.split()[:3]] for ln in body[:n]])
+    grad = np.array([[float(x.replace("D", "E")) for x in ln.split()[:3]] for ln in body[n:2 * n]])
+    return energy, xyz, grad
+
+
+def write_charges(q, path="charges"):
+    with open(path, "w") as f:
+        for v in q:
+            f.write("%14.8f\n" % v)
+
+
+def write_wbo(wbo, path="wbo", thr=0.1):
+    n = wbo.shape[0]
+    with open(path, "w") as f:
+        for i in range(n):
+            for j in range(i):
+                if wbo[j, i] > thr:
+                    f.write("%12d%12d   %.15f\n" % (j + 1, i + 1, wbo[j, i]))
+
+
+UNSUPPORTED = ["--opt", "--ohess", "--hess", "--md", "--omd", "--metadyn", "--alpb", "--gbsa", "--cosmo", "--gff", "--gfnff",
+               "--vipea", "--vip", "--vea", "--path", "--modef", "--scan", "--esp", "--stm", "--tblite", "--cpcmx", "--oniom",
+               "--dipro", "--siman", "--screen", "--bhess", "--vfukui", "--vomega", "--pcem"]
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    for flag in argv:
+        if flag.split("=")[0] in UNSUPPORTED:
+            print("xtb_b200: %s is not available in the B200 GFN2-xTB single point engine" % flag, file=sys.stderr)
+            return 2
+    ap = argparse.ArgumentParser(prog="xtb_b200", description="GFN2-xTB single point (+ gradient) on the B200 engine")
+    ap.add_argument("geometry")
+    ap.add_argument("--gfn", type=int, default=2)
+    ap.add_argument("--sp", "--scc", action="store_true", help="single point (the default run type)")
+    ap.add_argument("--grad", action="store_true", help="write the Turbomole gradient file")
+    ap.add_argument("-c", "--chrg", type=float, default=0.0)
+    ap.add_argument("-u", "--uhf", type=int, default=0)
+    ap.add_argument("-a", "--acc", type=float, default=1.0)
+    ap.add_argument("--etemp", type=float, default=300.0)
+    ap.add_argument("--iterations", type=int, default=250)
+    ap.add_argument("-v", "--verbose", action="store_true")
+    ap.add_argument("--silent", action="store_true")
+    args = ap.parse_args(argv)
+    if args.gfn != 2:
+        print("xtb_b200: only --gfn 2 is implemented", file=sys.stderr)
+        return 2
+    import xtb_b200
+    numbers, xyz = read_geometry(args.geometry)
+    t0 = time.perf_counter()
+    calc = xtb_b200.Calculator(xtb_b200.Param.GFN2xTB, numbers, xyz, charge=args.chrg, uhf=args.uhf)
+    calc.set_verbosity(0 if args.silent else (2 if args.verbose else 1))
+    calc.set_accuracy(args.acc)
+    calc.set_electronic_temperature(args.etemp)
+    calc.set_max_iterations(args.iterations)
+    res = calc.singlepoint()
+    wall = time.perf_counter() - t0
+    energy, grad = res.get_energy(), res.get_gradient()
+    q, wbo, dip = res.get_charges(), res.get_bond_orders(), res.get_dipole()
+    eps, occ = res.get_orbital_eigenvalues(), res.get_orbital_occupations()
+    homo = int(np.nonzero(occ > 1e-6)[0].max()) if np.any(occ > 1e-6) else 0
+    gap = (eps[homo + 1] - eps[homo]) * 27.21138505 if homo + 1 < len(eps) else 0.0
+    write_turbomole(numbers, xyz, energy, grad if args.grad else None)
+    write_charges(q)
+    write_wbo(wbo)
+    if not args.silent:
+        print("         :::::::::::::::::::::::::::::::::::::::::::::::::::::")
+        print("         ::                     SUMMARY                     ::")
+        print("         :::::::::::::::::::::::::::::::::::::::::::::::::::::")
+        print("         :: total energy        %18.12f Eh    ::" % energy)
+        print("         :: gradient norm       %18.12f Eh/a0 ::" % np.linalg.norm(grad))
+        print("         :: HOMO-LUMO gap       %18.12f eV    ::" % gap)
+        print("         :::::::::::::::::::::::::::::::::::::::::::::::::::::")
+        print("molecular dipole (au): %12.6f %12.6f %12.6f" % tuple(dip))
+        print(" * wall-time: %.3f s (device: GFN2-xTB engine on B200)" % wall)
+        print("normal termination of xtb_b200")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
