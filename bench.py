@@ -543,6 +543,92 @@ def run_water(args):
         dist.destroy_process_group()
 
 
+def run_single(args):
+    """BASELINE configs[0] / configs[1]: wall time of ONE GFN2-xTB single point + gradient through the xtb.h C ABI
+    (xtb_newMolecule / xtb_loadGFN2xTB / xtb_singlepoint / xtb_getEnergy / xtb_getGradient), fresh results handle (EEQ
+    guess) per step.  --molecule caffeine: the 24-atom molecule of `xtb caffeine.xyz --gfn 2 --grad`; --molecule
+    protein: stand-in of crambin's size (its coordinates are not available offline): 6 copies of taxol
+    (test/unit/molstock.f90, 113 atoms each = 678 atoms) 20 bohr apart.  (Clusters of the zwitterionic peptide pdb-4qxx
+    were tried first; their SCC needs > 100 iterations in the oracle and in the engine alike and the iteration count is
+    not reproducible between any two eigensolvers, so they make a poor benchmark.)"""
+    import torch
+
+    import xtb_b200
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the engine has no CPU fallback")
+    if int(os.environ.get("RANK", "0")) != 0:
+        return                                            # does not shard: one molecule, one GPU
+    torch.cuda.set_device(0)
+    if args.molecule == "protein":
+        Z, xyz = make_peptide_cluster(load_kat("taxol"), 6, gap=20.0)
+        label = "6 x taxol, 20 bohr apart (stand-in of crambin's size)"
+    else:
+        s = load_kat(args.molecule)
+        Z, xyz = s["numbers"], s["xyz"]
+        label = args.molecule
+    calc = xtb_b200.Calculator(xtb_b200.Param.GFN2xTB, Z, xyz)
+    calc.set_verbosity(0)
+    for _ in range(max(args.warmup, 1)):
+        res = calc.singlepoint()
+    clocks = ClockSampler(0)
+    clocks.start()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        res = calc.singlepoint()                          # new results handle: no restart
+        e = res.get_energy()
+        g = res.get_gradient()
+        ts.append(time.perf_counter() - t0)
+    clk = clocks.stop()
+    # device-side split of the same calculation through the batched ABI (positions resident on the device)
+    b = xtb_b200.BatchCalculator([Z])
+    pos_dev = torch.from_numpy(np.ascontiguousarray(xyz)).cuda()
+    b.set_profile("all")
+    dev_ms = []
+    for _ in range(max(args.warmup, 1) + args.steps):
+        b.singlepoint_device(pos_dev.data_ptr())
+        t = b.timings()
+        dev_ms.append(t["setup_ms"] + t["scc_ms"] + t["grad_ms"])
+    dev_ms = dev_ms[-args.steps:]
+    prof, passes = b.kernel_times()
+    tot = sum(v["ms"] for v in prof.values())
+    share = {kk: round(v["ms"] / tot, 4) for kk, v in sorted(prof.items(), key=lambda x: -x[1]["ms"]) if v["ms"] / tot >= 0.01}
+    r = b.result(0)
+    sz = b.sizes(0)
+    cpu = None
+    if not args.no_cpu:
+        from oracle.oracle import Oracle, build
+        build()
+        cores = host_cores()
+        best = None
+        for nth in sorted({1, cores}):           # tiny molecules run fastest on one thread, large ones on all cores
+            for _ in range(2):
+                o = Oracle(Z, xyz, threads=nth)
+                t0 = time.perf_counter(); st = o.singlepoint(); dt = time.perf_counter() - t0
+                if best is None or dt < best[0]:
+                    best = (dt, nth)
+        cpu = {"value": 1e3 * best[0], "unit": "ms/single point", "cores": best[1], "kind": "port",
+               "sample": "the same molecule, OpenMP + OpenBLAS with 1 and with %d threads, best of 2 x 2" % cores,
+               "dE_vs_gpu": float(e - o.energies["e_total"]), "niter": int(o.info["niter"])}
+    line = {
+        "metric": "wall time per GFN2 SP+gradient (single molecule)", "value": float(np.mean(dev_ms)), "unit": "ms/single point",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(dev_ms)), "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %d atoms, %d AOs, xtb.h C API, EEQ guess every call" % (label, sz["natoms"], sz["nao"]),
+                   "scc_iterations": int(r["niter"]), "l2": "single small system: launch/latency bound, working set in L2"},
+        "e2e": {"value": 1e3 * float(np.mean(ts)), "unit": "ms/single point", "h2d_bytes_per_step": int(np.asarray(xyz).size * 8),
+                "d2h_bytes_per_step": int(8 * (1 + 3 * sz["natoms"])),
+                "note": "xtb_singlepoint + xtb_getEnergy + xtb_getGradient, host buffers, wall clock around the blocking calls"},
+        "gpu_launches": int(b.timings()["launches"]) * args.steps,
+        "roofline": {"bound": "latency", "kernel": max(prof, key=lambda k: prof[k]["ms"]), "achieved": None, "peak": None, "unit": None,
+                     "frac": None, "traffic": None,
+                     "note": "one small molecule cannot fill the GPU; see the ensemble workload for throughput"},
+        "share_all_kernels": share, "cpu_baseline": cpu, "clocks": clk, "sample_energy_Eh": float(e),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -552,14 +638,19 @@ def main():
     ap.add_argument("--nmol", type=int, default=4096, help="conformers per GPU")
     ap.add_argument("--molecule", default="rivaroxaban")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "water"],
-                    help="ensemble: BASELINE configs[2] (default, the headline metric); water: configs[3], s/SCC-iteration")
+    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "water", "single"],
+                    help="ensemble: BASELINE configs[2] (default, the headline metric); water: configs[3], s/SCC-iteration; "
+                         "single: configs[0]/[1], one molecule (--molecule caffeine | protein) through the xtb.h C API")
     ap.add_argument("--nwat", type=int, default=1000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "water":
         run_water(args)
+    elif args.workload == "single":
+        if args.molecule == "rivaroxaban":
+            args.molecule = "caffeine"
+        run_single(args)
     else:
         run_engine(args)
 
