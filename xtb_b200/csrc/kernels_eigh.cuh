@@ -24,7 +24,7 @@ namespace xtbb200 {
 constexpr int EB = 64;             // panel width of the tridiagonalisation
 constexpr int NB = 2 * EB;         // block reflector width of the back-transformation (two panels)
 constexpr int kSytrdThreads = 1024;
-constexpr int kBtSplit = 4;        // split of the long K dimension of W = V^T C
+constexpr int kBtSplit = 4;        // largest split of the long K dimension of W = V^T Z (small matrices: too few tiles otherwise)
 
 // ---------------------------------------------------------------------------------------------------------------
 // general GEMM  C = alpha op(A) op(B) + beta C  on 64x64 tiles (128 threads, 4 warps of 32x32, DMMA m8n8k4)
@@ -427,21 +427,13 @@ __global__ void __launch_bounds__(NB) k_bt_tfactor(const double* __restrict__ Ga
     double* To = Tall + (long long)b * NB * NB;
     for (int c = 0; c < NB; ++c) To[r + NB * c] = T[r][c];
 }
-// W2 = T * sum_z Wz  (NB x n, leading dimension NB); thread per output element
-__global__ void k_bt_tw(const double* __restrict__ T, const double* __restrict__ Wz, long long zstride, int nz, int kb, int n,
-                        double* __restrict__ W2) {
+// W = sum_z Wz (partial products of the K-split W = V^T Z); thread per element
+__global__ void k_bt_sum(double* __restrict__ Wz, long long zstride, int nz, long long count) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)NB * n) return;
-    const int i = (int)(t % NB);
-    const long long c = t / NB;
-    double s = 0.0;
-    if (i < kb)
-        for (int k = i; k < kb; ++k) {
-            double w = 0.0;
-            for (int z = 0; z < nz; ++z) w += Wz[(long long)z * zstride + k + NB * c];
-            s += T[i + NB * k] * w;
-        }
-    W2[t] = s;
+    if (t >= count) return;
+    double w = Wz[t];
+    for (int z = 1; z < nz; ++z) w += Wz[(long long)z * zstride + t];
+    Wz[t] = w;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -677,7 +669,7 @@ __global__ void k_dc_permute(int n, const double* __restrict__ Q, const int* __r
 struct EighWork {
     int nmax = 0, nsm = 0, grid = 0;
     double *Qa = nullptr, *Qb = nullptr, *U = nullptr, *Qg = nullptr, *Ug = nullptr;
-    double *PB = nullptr, *Vb = nullptr, *Wz = nullptr, *W2 = nullptr, *Tf = nullptr, *Gf = nullptr;
+    double *PB = nullptr, *Vb = nullptr, *Wz = nullptr, *VT = nullptr, *Tf = nullptr, *Gf = nullptr;
     double *dd = nullptr, *ee = nullptr, *tau = nullptr, *y = nullptr, *part = nullptr, *vtv = nullptr, *wtv = nullptr;
     double *lam = nullptr, *lam2 = nullptr, *z = nullptr, *zhat = nullptr, *dk = nullptr, *zk = nullptr, *rc = nullptr, *rs = nullptr;
     int *perm = nullptr, *cols = nullptr, *pos = nullptr, *tcnt = nullptr, *ra = nullptr, *rb = nullptr, *kcnt = nullptr, *nrot = nullptr,
@@ -715,7 +707,7 @@ struct EighWork {
         const size_t n = nmax, n2 = n * n;
         Qa = alloc<double>(n2); Qb = alloc<double>(n2); U = alloc<double>(n2); Qg = alloc<double>(n2); Ug = alloc<double>(n2);
         PB = alloc<double>(n * (NB + EB)); Vb = alloc<double>(n * NB);
-        Wz = alloc<double>((size_t)kBtSplit * NB * n); W2 = alloc<double>((size_t)NB * n);
+        Wz = alloc<double>((size_t)kBtSplit * NB * n); VT = alloc<double>((size_t)NB * n);
         const size_t nblk = (n + NB - 1) / NB;
         Tf = alloc<double>(nblk * NB * NB); Gf = alloc<double>(nblk * NB * NB);
         dd = alloc<double>(n); ee = alloc<double>(n); tau = alloc<double>(n); y = alloc<double>(n);
@@ -852,13 +844,16 @@ struct EighWork {
             for (int b = nbb - 1; b >= 0; --b) {
                 const int jb = b * NB, kb = std::min(NB, nrefl - jb), r0 = jb + 1, mr = n - r0;
                 k_bt_formv<<<(unsigned)(((size_t)n * kb + 255) / 256), 256, 0, st>>>(A, n, jb, kb, Vb);
+                // (I - V T V^T) Z = Z - (V T) (V^T Z): W = V^T Z (K split only while there are too few tiles), VT = V T, Z -= VT W
+                const int tiles = ((kb + GT - 1) / GT) * ((n + GT - 1) / GT);
+                const int split = std::max(1, std::min(kBtSplit, (2 * nsm + tiles - 1) / tiles));
                 GemmTask t = gemm_task(Vb + r0, n, Z + r0, n, Wz, NB, kb, n, mr, 1.0, 0.0);
-                t.ksplit = kBtSplit; t.csplit = (long long)NB * n;
-                gemm(st, true, false, t, kBtSplit);
-                k_bt_tw<<<(unsigned)(((size_t)NB * n + 255) / 256), 256, 0, st>>>(Tf + (size_t)b * NB * NB, Wz, (long long)NB * n,
-                                                                                    kBtSplit, kb, n, W2);
-                gemm(st, false, false, gemm_task(Vb + r0, n, W2, NB, Z + r0, n, mr, n, kb, -1.0, 1.0));
-                nl += 4;
+                t.ksplit = split; t.csplit = (long long)NB * n;
+                gemm(st, true, false, t, split);
+                if (split > 1) k_bt_sum<<<(unsigned)(((size_t)NB * n + 255) / 256), 256, 0, st>>>(Wz, (long long)NB * n, split, (long long)NB * n);
+                gemm(st, false, false, gemm_task(Vb + r0, n, Tf + (size_t)b * NB * NB, NB, VT + r0, n, mr, kb, kb, 1.0, 0.0));
+                gemm(st, false, false, gemm_task(VT + r0, n, Wz, NB, Z + r0, n, mr, n, kb, -1.0, 1.0));
+                nl += split > 1 ? 5 : 4;
             }
         }
         hook(3, 1, nl - nl_bt0);
