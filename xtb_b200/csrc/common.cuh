@@ -55,6 +55,8 @@ struct Dev {
     int maxiter;
     int jb_inner;     // inner sweeps per Gram block of the block Jacobi solver
     double jb_tol;    // relative orthogonality threshold of the block Jacobi solver (0: 8 sqrt(n) eps)
+    double jb_qtol;   // quadratic stop of the block Jacobi solver: skip the verification sweep after a sweep whose largest
+                      // relative off-diagonal was below this (0: always verify)
     // per atom
     double *xyz, *cn, *cn_cov, *cn_d4, *cn_erf, *radcn;
     double *q, *q_out, *dipm, *dipm_out, *qp, *qp_out;

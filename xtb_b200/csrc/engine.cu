@@ -494,6 +494,8 @@ int Batch::singlepoint(bool restart) {
     d.jb_inner = kJbInnerSweeps;
     d.jb_tol = 0.0;
     if (const char* e = std::getenv("XTBB200_JB_TOL")) d.jb_tol = std::atof(e);   // tuning knob
+    d.jb_qtol = kJbQuadraticStop;
+    if (const char* e = std::getenv("XTBB200_JB_QTOL")) d.jb_qtol = std::atof(e);   // tuning knob
     if (const char* e = std::getenv("XTBB200_JB_INNER")) d.jb_inner = std::max(1, std::atoi(e));   // tuning knob
     if (!I.ev_phase[0]) for (auto& e : I.ev_phase) cudaEventCreate(&e);
     if (!I.ev_comm[0]) for (auto& e : I.ev_comm) cudaEventCreate(&e);

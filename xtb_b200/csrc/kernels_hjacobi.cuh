@@ -190,9 +190,9 @@ __global__ void __launch_bounds__(32 * kHjInnerWarps) k_hj_inner(Dev d, int step
     const double tol_inner = 2.0 * sqrt((double)HP) * 2.220446049250313e-16;
 #ifdef XTBB200_JB_TIMING
     long long jbt[6] = {0, 0, 0, 0, 0, 0}, jbt0 = clock64();
-    jb_sweeps(G, Msh, ver, HP, tol_inner, 1, 60, jbt, jbt0);
+    jb_sweeps(G, Msh, ver, HP, tol_inner, 1, 60, 0.0, jbt, jbt0);
 #else
-    jb_sweeps(G, Msh, ver, HP, tol_inner, 1, 60);
+    jb_sweeps(G, Msh, ver, HP, tol_inner, 1, 60, 0.0);
 #endif
     __syncthreads();
     for (int j = tid; j < HP; j += nt) {

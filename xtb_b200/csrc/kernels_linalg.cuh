@@ -355,6 +355,7 @@ __device__ __forceinline__ void jb_publish(volatile int* ver, int P, int Q, int 
     if (lane == 0) { ver[P] = v; ver[Q] = v; }
 }
 
+constexpr double kJbQuadraticStop = 1.0e-8;   // default of Dev::jb_qtol: columns orthogonal to ~1e-16 after the last sweep
 constexpr int kJbInnerSweeps = 1;  // inner sweeps per Gram block (early exit when a sweep rotates nothing)
 constexpr int kJbScratch = 144;   // doubles of per-warp scratch: M[8][9], J[8][9]
 
@@ -381,7 +382,8 @@ inline size_t jb_smem_bytes(int n, int nwarps) {
 // The sweep loop of the block Jacobi solver on a matrix G resident in shared memory (layout of jb_dims(n)); every
 // thread of the CTA calls it.  Msh: this warp's 8x9 + 8x9 scratch; ver: 64 ints of shared memory.  Returns the number
 // of sweeps executed (the last one is the verification sweep when converged; == maxsweeps means not converged).
-__device__ __forceinline__ int jb_sweeps(double* G, double* Msh, volatile int* ver, int n, double tol, int inner, int maxsweeps
+__device__ __forceinline__ int jb_sweeps(double* G, double* Msh, volatile int* ver, int n, double tol, int inner, int maxsweeps,
+                                         double qtol
 #ifdef XTBB200_JB_TIMING
                                          , long long* jbt, long long& jbt0
 #endif
@@ -393,6 +395,9 @@ __device__ __forceinline__ int jb_sweeps(double* G, double* Msh, volatile int* v
     if (tid < 64) ver[tid] = 0;
     __syncthreads();
     const double tol2 = tol * tol;
+    // quadratic stop: a sweep in which no pair was further from orthogonality than qtol leaves the columns orthogonal
+    // to ~qtol^2 (cyclic Jacobi converges quadratically), so the verification sweep can be skipped.  0: off.
+    const double qtol2 = qtol * qtol;
     const double tol_in2 = 2.220446049250313e-16 * 2.220446049250313e-16;
     const int nbp = nb / 2;
     const int l4 = lane >> 2, l3 = lane & 3;
@@ -408,7 +413,7 @@ __device__ __forceinline__ int jb_sweeps(double* G, double* Msh, volatile int* v
     int sweep = 0;
     int tstep = 0;     // tournament steps completed so far (all sweeps)
     for (; sweep < maxsweeps; ++sweep) {
-        int rotated = 0;
+        int rotated = 0, rotbig = 0;
         for (int step = 0; step < nb - 1; ++step, ++tstep) {
             for (int pr = warp; pr < nbp; pr += nwarps) {
                 int P, Q;
@@ -447,6 +452,14 @@ __device__ __forceinline__ int jb_sweeps(double* G, double* Msh, volatile int* v
                 }
                 if (!__any_sync(0xffffffffu, need)) { jb_publish(ver, P, Q, tstep + 1, lane); continue; }
                 rotated = 1;
+                if (qtol2 > 0.0) {
+                    const double dii = Msh[l4 * 10];
+                    const int j0 = 2 * l3, j1 = 2 * l3 + 1;
+                    int big = 0;
+                    if (j0 != l4) big |= (m0 * m0 > qtol2 * dii * Msh[j0 * 10]) ? 1 : 0;
+                    if (j1 != l4) big |= (m1 * m1 > qtol2 * dii * Msh[j1 * 10]) ? 1 : 0;
+                    if (__any_sync(0xffffffffu, big)) rotbig = 1;
+                } else rotbig = 1;
                 // ---- two-sided Jacobi on the 8x8 Gram matrix; lane = (pair slot, row/column index).
                 // A bounded number of inner sweeps is enough: the outer loop re-forms every Gram matrix, so the inner
                 // solve only sets the convergence rate, never the final accuracy.  M and J have row stride 9
@@ -516,6 +529,7 @@ __device__ __forceinline__ int jb_sweeps(double* G, double* Msh, volatile int* v
             }
         }
         if (!__syncthreads_or(rotated)) { ++sweep; break; }
+        if (!__syncthreads_or(rotbig)) { ++sweep; break; }
     }
     return sweep;
 }
@@ -578,9 +592,9 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
     }
     const double tol = d.jb_tol > 0.0 ? d.jb_tol : 8.0 * sqrt((double)n) * 2.220446049250313e-16;
 #ifdef XTBB200_JB_TIMING
-    const int sweep = jb_sweeps(G, Msh, ver, n, tol, d.jb_inner, 40, jbt, jbt0);
+    const int sweep = jb_sweeps(G, Msh, ver, n, tol, d.jb_inner, 40, d.jb_qtol, jbt, jbt0);
 #else
-    const int sweep = jb_sweeps(G, Msh, ver, n, tol, d.jb_inner, 40);
+    const int sweep = jb_sweeps(G, Msh, ver, n, tol, d.jb_inner, 40, d.jb_qtol);
 #endif
     // eigenvalues, ordering, normalised eigenvectors
     double* nrm = d.nrm + m.ao0;
