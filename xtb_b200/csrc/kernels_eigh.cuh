@@ -178,6 +178,32 @@ struct SytrdArgs {
 };
 #define SY_T(k) do { if (a.prof && cta == 0 && tid == 0) { const long long t_ = clock64(); a.prof[k] += t_ - tprof; tprof = t_; } } while (0)
 
+// barrier over all CTAs of a cooperative grid; bar is zeroed before the launch, target is the caller's running count
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += nblocks;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned x;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(x) : "l"(bar) : "memory");
+        } while (x < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// deterministic block sum, result in all threads; second stage by shuffles in every warp (red: 32 doubles)
+__device__ __forceinline__ double block_sum_sh(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    return warp_sum(lane < nw ? red[lane] : 0.0);
+}
+
 // Block-wide sum of v into part[blockIdx.x] followed by a barrier over all CTAs of the (cooperative) grid.  red: 32 doubles.
 __device__ __forceinline__ void grid_sum_barrier(double v, double* red, double* part, unsigned* bar, unsigned nblocks, unsigned& target) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -393,6 +419,147 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
         SY_T(6);
         grid_sum_barrier(vyl, red, a.part_vy, a.bar, G, target);
         SY_T(7);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tridiagonalisation with the trailing matrix resident in shared memory (order up to ~1860 on 148 SMs)
+// ---------------------------------------------------------------------------------------------------------------
+// The columns of the (trailing) matrix are dealt cyclically to the CTAs of a cooperative grid and stay in their shared
+// memory for the whole reduction, so the unblocked two-sided update A -= v w^T + w v^T (dsytd2) costs no HBM or L2
+// traffic at all; only v and y = A v travel through L2 between the CTAs (two grid barriers per column).  Below that
+// order the panel kernel above is bound by L2 round trips (~12 us per column); this form needs about half.
+struct SytrdSmemArgs {
+    double* A;          // n x n; the reduction covers A[j0:, j0:]; reflectors are stored below the sub-diagonal
+    int n, j0;          // j0 must be a multiple of NB
+    double *d, *e, *tau;
+    double* vbuf;       // [n] current reflector, rows relative to j0
+    double* ybuf;       // [n] y = A v
+    double* sc;         // [2] tau of the current column (double buffered)
+    double* Gf;         // Gram matrices of the block reflectors (as written by the panel kernel)
+    unsigned* bar;
+};
+inline size_t sytrd_smem_resident_bytes(int m0, int grid) {
+    const size_t slots = (size_t)(m0 + grid - 1) / grid;
+    return (slots * m0 + 2 * (size_t)m0 + 128) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a) {
+    extern __shared__ double sm_dyn[];
+    __shared__ double red[32], sh_tau;
+    const int n = a.n, j0 = a.j0, m0 = n - j0, G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    const long long ld = n;
+    const int maxslot = (m0 + G - 1) / G;
+    const int nslot = cta < m0 ? (m0 - cta + G - 1) / G : 0;   // owned columns c = cta + s G
+    double* cols = sm_dyn;
+    double* sv = sm_dyn + (size_t)maxslot * m0;
+    double* sw = sv + m0;
+    double* part = sw + m0;                                    // 128 doubles
+    for (int s = 0; s < nslot; ++s) {
+        const double* src = a.A + j0 + ld * (j0 + cta + s * G);
+        for (int r = tid; r < m0; r += nthr) cols[(size_t)s * m0 + r] = src[r];
+    }
+    __syncthreads();
+    unsigned target = 0;
+    double sqnext = 0.0;   // sum of squares below the sub-diagonal of the next column, formed while it is updated
+    for (int jj = 0; jj < m0; ++jj) {
+        const int j = j0 + jj, owner = jj % G, mm = m0 - jj - 1;
+        // ---- reflector of column jj by its owner (the column is up to date in its shared memory)
+        if (cta == owner) {
+            double* col = cols + (size_t)(jj / G) * m0;
+            double sq = sqnext;
+            if (jj == 0) {
+                for (int r = 2 + tid; r < m0; r += nthr) sq += col[r] * col[r];
+                sq = block_sum_sh(sq, red);
+            }
+            if (tid == 0) a.d[j] = col[jj];
+            if (mm > 0) {
+                const double alpha = col[jj + 1];
+                double beta = alpha, tau = 0.0, scal = 0.0;
+                if (sq > 0.0) {
+                    beta = -copysign(sqrt(alpha * alpha + sq), alpha);
+                    tau = (beta - alpha) / beta;
+                    scal = 1.0 / (alpha - beta);
+                }
+                if (tid == 0) { a.e[j] = beta; a.tau[j] = tau; a.sc[jj & 1] = tau; }
+                for (int r = jj + 1 + tid; r < m0; r += nthr) {
+                    const double v = (r == jj + 1) ? 1.0 : col[r] * scal;
+                    a.vbuf[r] = v;
+                    if (r >= jj + 2) a.A[(j0 + r) + ld * j] = v;
+                }
+            }
+        }
+        if (mm == 0) break;
+        grid_barrier(a.bar, G, target);
+        // ---- y = A v on the owned columns; Gram entries of the block reflector (v_k^T v_i, k < i in the same block)
+        if (tid == 0) sh_tau = __ldcg(a.sc + (jj & 1));
+        for (int r = jj + 1 + tid; r < m0; r += nthr) sv[r] = __ldcg(a.vbuf + r);
+        __syncthreads();
+        const double tau = sh_tau;
+        const int s0 = (jj + 1 - cta + G - 1) / G;            // first owned slot with column > jj (cta + s G >= jj + 1)
+        const int sfirst = cta >= jj + 1 ? 0 : s0;
+        const int nact = nslot - sfirst;
+        const int blk0 = (j / NB) * NB;                       // first reflector of the current block reflector
+        const int kg = blk0 + cta;                            // Gram job of this CTA: previous reflector kg (if any)
+        const bool gram = kg < j;
+        const int njobcols = max(nact, 0) + (gram ? 1 : 0);
+        int Q = 1;
+        if (njobcols > 0) Q = max(1, min(8, min((nwarp + njobcols - 1) / njobcols, max(mm / 64, 1))));
+        const int njobs = njobcols * Q;
+        for (int job = warp; job < njobs; job += nwarp) {
+            const int lc = job / Q, q = job - lc * Q;
+            const int tb = jj + 1 + (int)(((long long)mm * q) / Q), te = jj + 1 + (int)(((long long)mm * (q + 1)) / Q);
+            double s = 0.0;
+            if (lc < nact) {
+                const double* col = cols + (size_t)(sfirst + lc) * m0;
+                double s1 = 0.0;
+                int r = tb + lane;
+                for (; r + 32 < te; r += 64) { s += col[r] * sv[r]; s1 += col[r + 32] * sv[r + 32]; }
+                if (r < te) s += col[r] * sv[r];
+                s += s1;
+            } else {
+                const double* col = a.A + j0 + ld * kg;       // reflector kg: stored entries from row kg + 2 <= jj + 1
+                for (int r = tb + lane; r < te; r += 32) s += __ldcg(col + r) * sv[r];
+            }
+            s = warp_sum(s);
+            if (lane == 0) part[job] = s;
+        }
+        __syncthreads();
+        for (int lc = tid; lc < njobcols; lc += nthr) {
+            double s = 0.0;
+            for (int q = 0; q < Q; ++q) s += part[lc * Q + q];
+            if (lc < nact) a.ybuf[cta + (sfirst + lc) * G] = s;
+            else a.Gf[(size_t)(j / NB) * NB * NB + (kg - blk0) + NB * (j - blk0)] = s;
+        }
+        grid_barrier(a.bar, G, target);
+        // ---- w = tau y - tau^2/2 (v^T y) v, then A -= v w^T + w v^T on the owned columns (rows and columns > jj)
+        double vy = 0.0;
+        for (int r = jj + 1 + tid; r < m0; r += nthr) { const double y = __ldcg(a.ybuf + r); sw[r] = y; vy += sv[r] * y; }
+        vy = block_sum_sh(vy, red);
+        const double coef = -0.5 * tau * tau * vy;
+        for (int r = jj + 1 + tid; r < m0; r += nthr) sw[r] = tau * sw[r] + coef * sv[r];
+        __syncthreads();
+        // the owner of the next column comes first so that its norm is ready when the others are still updating
+        const bool own_next = (jj + 1) % G == cta;
+        double sq = 0.0;
+        if (own_next) {
+            double* col = cols + (size_t)((jj + 1) / G) * m0;
+            const double wc = sw[jj + 1], vc = sv[jj + 1];
+            for (int r = jj + 1 + tid; r < m0; r += nthr) {
+                const double x = col[r] - (sv[r] * wc + sw[r] * vc);
+                col[r] = x;
+                if (r >= jj + 3) sq += x * x;
+            }
+        }
+        const int sskip = own_next ? 1 : 0;   // the next column is the first active slot of its owner
+        for (int idx = tid; idx < (nact - sskip) * mm; idx += nthr) {
+            const int s = idx / mm + sskip, r = jj + 1 + (idx - (s - sskip) * mm);
+            const int c = cta + (sfirst + s) * G;
+            cols[(size_t)(sfirst + s) * m0 + r] -= sv[r] * sw[c] + sw[r] * sv[c];
+        }
+        if (own_next) sqnext = block_sum_sh(sq, red);
+        else __syncthreads();
     }
 }
 
@@ -675,6 +842,8 @@ struct EighWork {
     int *perm = nullptr, *cols = nullptr, *pos = nullptr, *tcnt = nullptr, *ra = nullptr, *rb = nullptr, *kcnt = nullptr, *nrot = nullptr,
         *fail = nullptr, *rank = nullptr;
     unsigned* bar = nullptr;
+    double *vbuf = nullptr, *ybuf = nullptr, *scbuf = nullptr;
+    int resident_max = 0;      // largest trailing order the shared-memory resident tridiagonalisation takes
     long long* prof = nullptr;
     GemmTask* tasks = nullptr;
     std::vector<void*> allocs;
@@ -717,6 +886,7 @@ struct EighWork {
         perm = alloc<int>(n); cols = alloc<int>(n); pos = alloc<int>(n); tcnt = alloc<int>(3 * n); ra = alloc<int>(n); rb = alloc<int>(n);
         kcnt = alloc<int>(n); nrot = alloc<int>(n); fail = alloc<int>(1); rank = alloc<int>(n);
         bar = alloc<unsigned>(1);
+        vbuf = alloc<double>(n); ybuf = alloc<double>(n); scbuf = alloc<double>(2);
         prof = alloc<long long>(8);
         tasks = alloc<GemmTask>(2 * n);
         grid = nsm;
@@ -726,6 +896,13 @@ struct EighWork {
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_secular, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 16)));
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 8)));
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_bt_tfactor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NB * (NB + 1) * 8)));
+        resident_max = 0;
+        const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin - 2048;   // static shared memory of the kernel
+        for (int m = 1; m <= nmax; ++m) if (sytrd_smem_resident_bytes(m, grid) <= smem_cap) resident_max = m;
+        if (std::getenv("XTBB200_NO_RESIDENT_SYTRD")) resident_max = 0;
+        if (resident_max > 0)
+            XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)sytrd_smem_resident_bytes(std::min(resident_max, nmax), grid)));
         int occ = 0;
         XTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sytrd_panel, kSytrdThreads, sytrd_smem(nmax, grid)));
         if (occ < 1) throw std::runtime_error("xtb_b200: tridiagonalisation kernel does not fit on an SM");
@@ -761,8 +938,10 @@ struct EighWork {
         const int npan = (n + EB - 1) / EB, nblk = (n + NB - 1) / NB;
         double* Wp = PB + (size_t)n * NB;
         XTB_CUDA_CHECK(cudaMemsetAsync(Gf, 0, (size_t)nblk * NB * NB * sizeof(double), st));
+        int jres = -1;   // column from which the shared-memory resident kernel takes over (block reflector boundary)
         for (int p = 0; p < npan; ++p) {
             const int j0 = p * EB, nc = std::min(EB, n - j0), q = p & 1;
+            if (q == 0 && n - j0 <= resident_max) { jres = j0; break; }
             double* V = PB + (size_t)n * EB * q;
             XTB_CUDA_CHECK(cudaMemsetAsync(V, 0, (size_t)n * EB * sizeof(double), st));
             XTB_CUDA_CHECK(cudaMemsetAsync(Wp, 0, (size_t)n * EB * sizeof(double), st));
@@ -788,6 +967,18 @@ struct EighWork {
                 hook(1, 1, 1);
                 ++nl;
             }
+        }
+        if (jres >= 0) {
+            XTB_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+            SytrdSmemArgs ra;
+            ra.A = A; ra.n = n; ra.j0 = jres; ra.d = dd; ra.e = ee; ra.tau = tau; ra.vbuf = vbuf; ra.ybuf = ybuf; ra.sc = scbuf;
+            ra.Gf = Gf; ra.bar = bar;
+            void* args[] = {&ra};
+            hook(0, 0, 0);
+            XTB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sytrd_smem, dim3(grid), dim3(kSytrdThreads), args,
+                                                       sytrd_smem_resident_bytes(n - jres, grid), st));
+            hook(0, 1, 1);
+            ++nl;
         }
         if (timed) cudaEventRecord(ev[1], st);
         hook(2, 0, 0);
