@@ -628,10 +628,10 @@ int Batch::singlepoint(bool restart) {
     int iters = 0;
     std::fill(I.h_done.begin(), I.h_done.end(), 0);
     for (int it = 0; it < I.maxiter && active > 0; ++it) {
-        KL(K_POT, k_pot_shell<<<grid2(s.max_nsh, B, nmol), B, 0, st>>>(d));
-        KL(K_POT, k_pot_aes<true><<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+        KL(K_POT, k_pot_shell<<<grid2(8LL * s.max_nsh, 256, nmol), 256, 0, st>>>(d));
+        KL(K_POT, k_pot_aes<true><<<grid2(8LL * s.max_nat, 256, nmol), 256, 0, st>>>(d));
         KL(K_D4SCC, k_d4_zeta<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d, 0));
-        KL(K_D4SCC, k_d4_matvec<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d));
+        KL(K_D4SCC, k_d4_matvec<<<grid2(8LL * s.max_ndim, 256, nmol), 256, 0, st>>>(d));
         KL(K_D4SCC, k_d4_shift<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
         KL(K_FOCK, k_fock<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
         KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.H, d.X, d.T, xtri ? 2 : 0, 1));   // T = H X
@@ -662,10 +662,10 @@ int Batch::singlepoint(bool restart) {
         KL(K_DENSITY, k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.P, 1, 1));       // P = T C^T
         KL(K_POP, k_pop_rows<<<grid2((long long)s.max_nao * 32, 256, nmol), 256, 0, st>>>(d));
         KL(K_POP, k_pop_atoms<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
-        KL(K_ENERGY, k_es_rows<<<grid2(s.max_nsh, B, nmol), B, 0, st>>>(d));
+        KL(K_ENERGY, k_es_rows<<<grid2(8LL * s.max_nsh, 256, nmol), 256, 0, st>>>(d));
         KL(K_ENERGY, k_aes_rows<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
         KL(K_D4SCC, k_d4_zeta<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d, 1));
-        KL(K_D4SCC, k_d4_matvec<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d));
+        KL(K_D4SCC, k_d4_matvec<<<grid2(8LL * s.max_ndim, 256, nmol), 256, 0, st>>>(d));
         KL(K_SCCFIN, k_scc_finish<<<nmol, 256, 0, st>>>(d));
         XTB_CUDA_CHECK(cudaMemsetAsync(I.d_active, 0, sizeof(int), st));
         KL(K_SCCFIN, k_count_active<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.d_active));
@@ -680,7 +680,7 @@ int Batch::singlepoint(bool restart) {
     // ---- gradient
     KL(K_GRAD_H0, k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 1));                     // T = C (f e)
     KL(K_GRAD_H0, k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.H, 1, 0));            // H <- energy weighted density
-    KL(K_GRAD_AES, k_pot_aes<false><<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+    KL(K_GRAD_AES, k_pot_aes<false><<<grid2(8LL * s.max_nat, 256, nmol), 256, 0, st>>>(d));
     if (R > 1) {   // partial gradients: repulsion stays on rank 0, unowned shell pairs contribute zeros
         if (d.srank != 0) XTB_CUDA_CHECK(cudaMemsetAsync(d.grad, 0, 3 * s.atoms.size() * sizeof(double), st));
         XTB_CUDA_CHECK(cudaMemsetAsync(d.gpair, 0, 4 * (size_t)I.pair_total * sizeof(double), st));

@@ -35,16 +35,43 @@ __global__ void k_qsh2qat(Dev d) {
 }
 
 // ---- potentials -------------------------------------------------------------------------------
-// shell potential: Gamma_sh q_sh^2 + (J q)_sh ; thread per shell (row of the symmetric J, coalesced)
-__global__ void k_pot_shell(Dev d) {
+// Row of y = M x for a dense symmetric column-major n x n matrix.  CTA = 32 rows x kMvSlices column slices (256
+// threads, launched with grid2(8 n, 256, nmol)): lanes read 32 consecutive rows (coalesced), the slices share the columns
+// so that 8 times more loads are in flight than with one thread per row; partial sums are combined in a fixed order.
+// Returns the row index (or -1) and the sum in the threads of slice 0.
+constexpr int kMvSlices = 8;
+__device__ __forceinline__ int matvec_row(const double* __restrict__ M, int n, const double* __restrict__ x, double& out) {
+    __shared__ double sp[kMvSlices][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int row = blockIdx.x * 32 + lane;
+    double a0 = 0.0, a1 = 0.0;
+    if (row < n) {
+        int t = w;
+        for (; t + kMvSlices < n; t += 2 * kMvSlices) {
+            a0 += M[row + (long long)n * t] * x[t];
+            a1 += M[row + (long long)n * (t + kMvSlices)] * x[t + kMvSlices];
+        }
+        if (t < n) a0 += M[row + (long long)n * t] * x[t];
+    }
+    sp[w][lane] = a0 + a1;
+    __syncthreads();
+    if (w != 0 || row >= n) return -1;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kMvSlices; ++k) s += sp[k][lane];
+    out = s;
+    return row;
+}
+
+// shell potential: Gamma_sh q_sh^2 + (J q)_sh
+__global__ void __launch_bounds__(32 * kMvSlices) k_pot_shell(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     if (d.st[blockIdx.y].done) return;
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= m.nsh) return;
-    const double* J = d.jmat + m.ss0;
+    if ((int)blockIdx.x * 32 >= m.nsh) return;
     const double* q = d.qsh + m.sh0;
     double acc = 0;
-    for (int t = 0; t < m.nsh; ++t) acc += J[s + (long long)m.nsh * t] * q[t];
+    const int s = matvec_row(d.jmat + m.ss0, m.nsh, q, acc);
+    if (s < 0) return;
     // shellShift(:) = externShift (scc_core.f90:438): the potential of the external point charges, if any
     const double ext = d.pc0 ? d.vpc[m.sh0 + s] : 0.0;
     d.sshift[m.sh0 + s] = ext + q[s] * q[s] * d.shells[m.sh0 + s].gam3 + acc;
@@ -66,20 +93,24 @@ __global__ void k_pcem_pot(Dev d) {
     d.vpc[m.sh0 + s] = eh1;
 }
 
-// anisotropic potentials vs, vd, vq; SHIFT = true: setvsdq (SCC), false: setdvsdq (gradient). thread per atom
+// anisotropic potentials vs, vd, vq; SHIFT = true: setvsdq (SCC), false: setdvsdq (gradient).  CTA = 32 atoms x
+// kMvSlices slices of the partner loop (launched with grid2(8 nat, 256, nmol)); partial sums combined in a fixed order
 template <bool SHIFT>
-__global__ void k_pot_aes(Dev d) {
+__global__ void __launch_bounds__(32 * kMvSlices) k_pot_aes(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     if (SHIFT && d.st[blockIdx.y].done) return;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nat) return;
+    if ((int)blockIdx.x * 32 >= m.nat) return;
+    __shared__ double sp[kMvSlices][10][33];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int i = min(blockIdx.x * 32 + lane, m.nat - 1);
+    const bool valid = (int)(blockIdx.x * 32 + lane) < m.nat;
     const double* xyz = d.xyz + 3 * m.at0;
     const double* q = d.q + m.at0;
     const double* dipm = d.dipm + 3 * m.at0;
     const double* qp = d.qp + 6 * m.at0;
     const double ra[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
     double stmp = 0, dtmp[3] = {0, 0, 0}, qtmp[6] = {0, 0, 0, 0, 0, 0};
-    for (int j = 0; j < m.nat; ++j) {
+    for (int j = slice; j < m.nat; j += kMvSlices) {
         const double g3 = d.gab3[m.nn0 + i + (long long)m.nat * j], g5 = d.gab5[m.nn0 + i + (long long)m.nat * j];
         const double dra[3] = {ra[0] - xyz[3 * j], ra[1] - xyz[3 * j + 1], ra[2] - xyz[3 * j + 2]};
         const double qj = q[j];
@@ -115,9 +146,21 @@ __global__ void k_pot_aes(Dev d) {
             qtmp[l1] += 0.50 * r2ab * qj * g5;
         }
     }
-    double vs = stmp, vd[3] = {dtmp[0], dtmp[1], dtmp[2]}, vq[6];
+    sp[slice][0][lane] = stmp;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) vq[k] = qtmp[k];
+    for (int k = 0; k < 3; ++k) sp[slice][1 + k][lane] = dtmp[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sp[slice][4 + k][lane] = qtmp[k];
+    __syncthreads();
+    if (slice != 0 || !valid) return;
+    double vs = 0.0, vd[3] = {0.0, 0.0, 0.0}, vq[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int w = 0; w < kMvSlices; ++w) {
+        vs += sp[w][0][lane];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) vd[k] += sp[w][1 + k][lane];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) vq[k] += sp[w][4 + k][lane];
+    }
     const AtomPar& a = d.atoms[m.at0 + i];
     const double qs1 = a.dipk * 2.0, qs2 = a.quadk * 6.0;
     double t3a = 0, t2a = 0;
@@ -173,17 +216,14 @@ __global__ void k_d4_zeta(Dev d, int use_out) {
     d.zeta[m.ref0 + k] = z;
     d.dzeta[m.ref0 + k] = dz;
 }
-// dvec = dispmat * zeta ; thread per reference row
-__global__ void k_d4_matvec(Dev d) {
+// dvec = dispmat * zeta
+__global__ void __launch_bounds__(32 * kMvSlices) k_d4_matvec(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     if (d.st[blockIdx.y].done) return;
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= m.ndim) return;
-    const double* M = d.dispmat + m.dd0;
-    const double* z = d.zeta + m.ref0;
+    if ((int)blockIdx.x * 32 >= m.ndim) return;
     double acc = 0;
-    for (int l = 0; l < m.ndim; ++l) acc += M[k + (long long)m.ndim * l] * z[l];
-    d.dvec[m.ref0 + k] = acc;
+    const int k = matvec_row(d.dispmat + m.dd0, m.ndim, d.zeta + m.ref0, acc);
+    if (k >= 0) d.dvec[m.ref0 + k] = acc;
 }
 // atomic shift from dispersion: sum_ref dvec*dzeta (dftd4.F90:805-811); thread per atom
 __global__ void k_d4_shift(Dev d) {
@@ -388,16 +428,13 @@ __global__ void k_pop_atoms(Dev d) {
 }
 
 // (J q_out) per shell for the ES energy; thread per shell
-__global__ void k_es_rows(Dev d) {
+__global__ void __launch_bounds__(32 * kMvSlices) k_es_rows(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     if (d.st[blockIdx.y].done) return;
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= m.nsh) return;
-    const double* J = d.jmat + m.ss0;
-    const double* q = d.qsh_out + m.sh0;
+    if ((int)blockIdx.x * 32 >= m.nsh) return;
     double acc = 0;
-    for (int t = 0; t < m.nsh; ++t) acc += J[s + (long long)m.nsh * t] * q[t];
-    d.jq[m.sh0 + s] = acc;
+    const int s = matvec_row(d.jmat + m.ss0, m.nsh, d.qsh_out + m.sh0, acc);
+    if (s >= 0) d.jq[m.sh0 + s] = acc;
 }
 
 // anisotropic ES energy rows (aniso_electro, aespot.F90:569-662): per atom i, sum over j < i
