@@ -44,6 +44,7 @@ struct Dev {
     const RefPar* refs;
     const int* ao2sh;
     const int* ao2at;
+    const int* leader;   // per molecule: first molecule of the batch with the same atoms in the same order (itself if none before)
     const double* c6ref;
     int ntype;
     int nmol;

@@ -158,6 +158,7 @@ struct Batch::Impl {
     Dev d;
     EighWork eig;             // Householder + divide-and-conquer eigensolver for matrices beyond shared memory
     bool have_eig = false;
+    bool has_followers = false;    // some molecules share their composition with an earlier one (conformer ensemble)
     std::vector<long long> h_pc0;  // external point charges: per-molecule ranges (empty: none)
     int max_npc = 0;
     long long pc_cap = 0;          // capacity (charges) of the device buffers below
@@ -318,6 +319,22 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
             I.bytes += I.eig.bytes;
         }
         I.h_done.assign(nmol, 0);
+        {   // leaders of the groups of identical compositions (warm start of the first diagonalisation, k_lead_copy)
+            std::vector<int> lead(nmol);
+            std::map<std::vector<int>, int> first;
+            int o2 = 0;
+            for (int i = 0; i < nmol; ++i) {
+                std::vector<int> key(numbers + o2, numbers + o2 + natoms[i]);
+                key.push_back((int)std::lround(100 * (charges ? charges[i] : 0.0)));
+                key.push_back(uhf ? uhf[i] : 0);
+                auto it = first.find(key);
+                if (it == first.end()) { first[key] = i; lead[i] = i; }
+                else { lead[i] = it->second; I.has_followers = true; }
+                o2 += natoms[i];
+            }
+            d.leader = I.upload(lead);
+            XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+        }
         I.d_active = I.dalloc<int>(1);
         I.h_state.resize(nmol);
         XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
@@ -638,7 +655,13 @@ int Batch::singlepoint(bool restart) {
         KL(K_GEMM_XHX, k_gemm<true, false><<<ggrid, 128, 0, st>>>(d, d.X, d.T, d.W, xtri ? 3 : 0, 1));    // W = X^T T
         if (!dc && (it > 0 || (restart && I.have_wfn)))
             KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.W, d.Zm, d.T, 0, 2));   // T = A' Z_prev
-        if (use_blk) KL(K_JACOBI, k_jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d));
+        if (use_blk && it == 0 && I.has_followers && !(restart && I.have_wfn) && I.solver == 0) {
+            // first diagonalisation of an ensemble: leaders cold, followers warm from their leader's eigenvectors
+            KL(K_JACOBI, k_jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d, 1));
+            KL(K_JACOBI, k_lead_copy<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
+            KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.W, d.Zm, d.T, 0, 3));
+            KL(K_JACOBI, k_jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d, 2));
+        } else if (use_blk) KL(K_JACOBI, k_jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d, 0));
         else if (dc) {
             XTB_CUDA_CHECK(cudaMemsetAsync(I.eig.fail, 0, sizeof(int), st));
             // stage hooks of the solver -> kernel classes (stage 0: panel kernel, 1: trailing update, 2: D&C, 3: back-transformation)

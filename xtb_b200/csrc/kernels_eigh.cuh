@@ -389,6 +389,12 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
             const int tb = (int)(((long long)m * q) / Q), te = (int)(((long long)m * (q + 1)) / Q);
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int t = tb + lane;
+            for (; t + 224 < te; t += 256) {   // eight loads in flight per lane: the L2 / HBM latency is the limit here
+                const double a0 = __ldcg(col + t), a1 = __ldcg(col + t + 32), a2 = __ldcg(col + t + 64), a3 = __ldcg(col + t + 96);
+                const double a4 = __ldcg(col + t + 128), a5 = __ldcg(col + t + 160), a6 = __ldcg(col + t + 192), a7 = __ldcg(col + t + 224);
+                s0 += a0 * sv[t]; s1 += a1 * sv[t + 32]; s2 += a2 * sv[t + 64]; s3 += a3 * sv[t + 96];
+                s0 += a4 * sv[t + 128]; s1 += a5 * sv[t + 160]; s2 += a6 * sv[t + 192]; s3 += a7 * sv[t + 224];
+            }
             for (; t + 96 < te; t += 128) {
                 s0 += __ldcg(col + t) * sv[t];
                 s1 += __ldcg(col + t + 32) * sv[t + 32];

@@ -31,13 +31,15 @@ constexpr int GLD = GT + 4;
 //             index of the tile, only tiles on or below the diagonal are computed and mirrored into the upper triangle
 //        4 -> A is upper triangular (C = X Z): K starts at the first row of the tile
 // skip_done: 1 = skip molecules that already left the SCC loop; 2 = additionally skip molecules without a valid
-// eigenvector guess (warm-start product A' Z_prev)
+// eigenvector guess (warm-start product A' Z_prev); 3 = as 2, and only molecules that follow a leader (first
+// diagonalisation of an ensemble, see k_lead_copy)
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ Ag, const double* __restrict__ Bg,
                                               double* __restrict__ Cg, int kmode, int skip_done) {
     const MolDesc m = d.mol[blockIdx.y];
     if (skip_done && d.st[blockIdx.y].done) return;
-    if (skip_done == 2 && !d.st[blockIdx.y].zvalid) return;
+    if (skip_done >= 2 && !d.st[blockIdx.y].zvalid) return;
+    if (skip_done == 3 && d.leader[blockIdx.y] == (int)blockIdx.y) return;
     const int n = m.nao;
     const int tiles = (n + GT - 1) / GT;
     if ((int)blockIdx.x >= tiles * tiles) return;
@@ -534,7 +536,24 @@ __device__ __forceinline__ int jb_sweeps(double* G, double* Msh, volatile int* v
     return sweep;
 }
 
-__global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
+// Conformer ensembles: the first diagonalisation of a molecule has no eigenvectors of its own to start from, but the
+// converged ones of another conformer of the same molecule are a far better start than the unit matrix (any orthogonal
+// Z is a valid start of the one-sided method).  The first molecule of every group of identical compositions (its
+// "leader") is solved cold, its Z is copied to the followers, and they start warm.  thread per matrix element
+__global__ void k_lead_copy(Dev d) {
+    const int im = blockIdx.y, L = d.leader[im];
+    if (L == im) return;
+    const MolState& sl = d.st[L];
+    if (!sl.zvalid || sl.fail) return;
+    const MolDesc m = d.mol[im];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)m.nao * m.nao) return;
+    d.Zm[m.mat0 + t] = d.Zm[d.mol[L].mat0 + t];
+    if (t == 0) d.st[im].zvalid = 1;
+}
+
+// phase: 0 all molecules, 1 leaders only, 2 followers only
+__global__ void __launch_bounds__(640) k_jacobi_blk(Dev d, int phase) {
 #ifdef XTBB200_JB_TIMING
     long long jbt[6] = {0, 0, 0, 0, 0, 0}, jbt0 = clock64();
 #endif
@@ -542,6 +561,7 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d) {
     const MolDesc m = d.mol[im];
     MolState& st = d.st[im];
     if (st.done) return;
+    if (phase && (d.leader[im] == im) != (phase == 1)) return;
     const int n = m.nao;
     const JbDims dm = jb_dims(n);
     const int nr = dm.nr, ld = dm.ld, nb = dm.nb;
