@@ -393,7 +393,10 @@ def kernel_roofline(top, k_ms, nmol, nao, nsh, nat, batch, peaks, torch, dev):
             note = "2 n^3 flop per launch and matrix (upper bound; density uses occupied columns only)"
         peak = measure_fp64_peak(torch, dev)
         ach = flops / (k_ms * 1e-3) / 1e12
-        return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+        # DRAM traffic of k_jacobi_blk per launch, scaled from the committed ncu capture (profiles/r01_ncu_k_jacobi_blk_v4.txt:
+        # 295.0 MB read + 66.1 MB written for 592 molecules of this size; algorithmic: T, Z in and Z out = 3 n^2 doubles)
+        traffic = (295.0e6 + 66.1e6) / 592 * nmol if ("jacobi" in top and n == 144) else None
+        return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (FP64 DMMA; MEASURED_PEAKS.json has no FP64 entry)",
                 "note": note}
     per_mol = {"k_sdqh0": 88 * n * n, "k_fock": 8 * (2.5 * n * n), "populations": 8 * 11 * n * n,

@@ -55,3 +55,33 @@ def test_larger_than_one_l2_slice():
     rng = np.random.default_rng(5)
     a = rng.standard_normal((1500, 1500))
     _check((a + a.T) / 2)
+
+
+def test_panel_kernel_hands_over_to_the_resident_kernel():
+    """n = 2100: the first panels run through k_sytrd_panel, the trailing matrix then fits into shared memory."""
+    rng = np.random.default_rng(6)
+    a = rng.standard_normal((2100, 2100))
+    _check((a + a.T) / 2)
+
+
+def test_order_beyond_the_shared_memory_deflation_scan():
+    """n = 9700 (deflation scan of the top levels in global memory): matrix with a known spectrum, A = H3 H2 H1 D H1 H2 H3
+    with three Householder reflectors, so that no LAPACK call of this size is needed; sampled residuals."""
+    n = 9700
+    rng = np.random.default_rng(8)
+    dvals = np.sort(rng.standard_normal(n) * 3.0)
+    dvals[100:140] = dvals[100]                      # a cluster of exactly degenerate levels
+    a = np.diag(dvals)
+    for _ in range(3):
+        v = rng.standard_normal(n)
+        v /= np.linalg.norm(v)
+        a -= 2.0 * np.outer(v, v @ a)
+        a -= 2.0 * np.outer(a @ v, v)
+    a = (a + a.T) / 2
+    w, z, ms = xtb_b200.symmetric_eigen(a)
+    scale = np.abs(a).max() * n * EPS
+    assert np.max(np.abs(w - np.sort(dvals))) <= 30 * scale
+    cols = rng.choice(n, 64, replace=False)
+    zs = z[:, cols]
+    assert np.max(np.abs(a @ zs - zs * w[cols])) <= 30 * scale
+    assert np.max(np.abs(zs.T @ z - np.eye(n)[cols])) <= 30 * n * EPS

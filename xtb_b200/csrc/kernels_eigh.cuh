@@ -618,7 +618,7 @@ struct DcArgs {
     double *Qo, *Qn;      // eigenvector blocks of the children / of the merged nodes
     double *U, *Qg, *Ug;  // delta matrix; non-deflated columns and update matrix in grouped order
     double *lam, *lam2, *z, *zhat, *dk, *zk, *rc, *rs;
-    int *perm, *cols, *pos, *tcnt, *ra, *rb, *kcnt, *nrot, *fail;
+    int *perm, *cols, *pos, *tcnt, *ctype, *ra, *rb, *kcnt, *nrot, *fail;
     GemmTask* tasks;
 };
 struct DcNode { int lo, mid, hi; };
@@ -677,17 +677,20 @@ __global__ void __launch_bounds__(256) k_dc_sort(DcArgs a) {
     a.perm[nd.lo + r] = i;
 }
 
-// deflation: one CTA per node, eigenvalues / z / order / column kinds staged in shared memory, sequential scan by thread 0
-__global__ void __launch_bounds__(256) k_dc_deflate(DcArgs a) {
+// deflation: one CTA per node, sequential scan by thread 0 over eigenvalues / z / order / column kinds staged in shared
+// memory (use_smem) or, for nodes too large for it, in place in global memory
+__global__ void __launch_bounds__(256) k_dc_deflate(DcArgs a, int use_smem) {
     extern __shared__ double sm_dyn[];
     const DcNode nd = dc_node(a, blockIdx.x);
     const int m = nd.hi - nd.lo, lo = nd.lo;
-    double* sd = sm_dyn;
-    double* sz = sm_dyn + m;
-    int* sp = (int*)(sm_dyn + 2 * m);
-    int* sty = sp + m;
+    double* sd = use_smem ? sm_dyn : a.lam + lo;
+    double* sz = use_smem ? sm_dyn + m : a.z + lo;
+    int* sp = use_smem ? (int*)(sm_dyn + 2 * m) : a.perm + lo;
+    int* sty = use_smem ? sp + m : a.ctype + lo;
     __shared__ int sh_k;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) { sd[i] = a.lam[lo + i]; sz[i] = a.z[lo + i]; sp[i] = a.perm[lo + i]; }
+    if (use_smem) {
+        for (int i = threadIdx.x; i < m; i += blockDim.x) { sd[i] = a.lam[lo + i]; sz[i] = a.z[lo + i]; sp[i] = a.perm[lo + i]; }
+    }
     __syncthreads();
     const double rho = 2.0 * fabs(a.e[nd.mid - 1]);
     if (threadIdx.x == 0) {
@@ -845,10 +848,11 @@ struct EighWork {
     double *PB = nullptr, *Vb = nullptr, *Wz = nullptr, *VT = nullptr, *Tf = nullptr, *Gf = nullptr;
     double *dd = nullptr, *ee = nullptr, *tau = nullptr, *y = nullptr, *part = nullptr, *vtv = nullptr, *wtv = nullptr;
     double *lam = nullptr, *lam2 = nullptr, *z = nullptr, *zhat = nullptr, *dk = nullptr, *zk = nullptr, *rc = nullptr, *rs = nullptr;
-    int *perm = nullptr, *cols = nullptr, *pos = nullptr, *tcnt = nullptr, *ra = nullptr, *rb = nullptr, *kcnt = nullptr, *nrot = nullptr,
+    int *perm = nullptr, *cols = nullptr, *pos = nullptr, *tcnt = nullptr, *ctype = nullptr, *ra = nullptr, *rb = nullptr, *kcnt = nullptr, *nrot = nullptr,
         *fail = nullptr, *rank = nullptr;
     unsigned* bar = nullptr;
     double *vbuf = nullptr, *ybuf = nullptr, *scbuf = nullptr;
+    size_t smem_limit = 0;
     int resident_max = 0;      // largest trailing order the shared-memory resident tridiagonalisation takes
     long long* prof = nullptr;
     GemmTask* tasks = nullptr;
@@ -869,12 +873,12 @@ struct EighWork {
         return (T*)p;
     }
     static size_t sytrd_smem(int n, int grid) { return ((size_t)n + (size_t)(n / grid + 6) * 8) * sizeof(double); }
-    // largest order the shared-memory staging of the deflation scan (24 bytes per row) allows
-    static int max_order() { return 9600; }
+    // largest order: shared-memory staging of the secular solver (16 bytes per root) and of the panel kernel's vector
+    static int max_order() { return 14000; }
 
     void init(int nmax_, int device) {
         nmax = nmax_;
-        if (nmax > max_order()) throw std::runtime_error("xtb_b200: eigensolver supports matrices up to order 9600");
+        if (nmax > max_order()) throw std::runtime_error("xtb_b200: eigensolver supports matrices up to order 14000");
         cudaDeviceProp prop;
         XTB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
         nsm = prop.multiProcessorCount;
@@ -889,7 +893,7 @@ struct EighWork {
         part = alloc<double>(2 * (size_t)nsm); vtv = alloc<double>(EB); wtv = alloc<double>(EB);
         lam = alloc<double>(n); lam2 = alloc<double>(n); z = alloc<double>(n); zhat = alloc<double>(n);
         dk = alloc<double>(n); zk = alloc<double>(n); rc = alloc<double>(n); rs = alloc<double>(n);
-        perm = alloc<int>(n); cols = alloc<int>(n); pos = alloc<int>(n); tcnt = alloc<int>(3 * n); ra = alloc<int>(n); rb = alloc<int>(n);
+        perm = alloc<int>(n); cols = alloc<int>(n); pos = alloc<int>(n); tcnt = alloc<int>(3 * n); ctype = alloc<int>(n); ra = alloc<int>(n); rb = alloc<int>(n);
         kcnt = alloc<int>(n); nrot = alloc<int>(n); fail = alloc<int>(1); rank = alloc<int>(n);
         bar = alloc<unsigned>(1);
         vbuf = alloc<double>(n); ybuf = alloc<double>(n); scbuf = alloc<double>(2);
@@ -898,7 +902,9 @@ struct EighWork {
         grid = nsm;
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sytrd_smem(nmax, grid)));
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 8)));
-        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 24 + 16)));
+        smem_limit = (size_t)prop.sharedMemPerBlockOptin - 1024;
+        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)std::min(n * 24 + 16, smem_limit)));
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_secular, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 16)));
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 8)));
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_bt_tfactor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NB * (NB + 1) * 8)));
@@ -1009,9 +1015,13 @@ struct EighWork {
                 DcArgs a;
                 a.n = n; a.depth = depth; a.e = ee; a.Qo = Qo; a.Qn = Qn; a.U = U; a.Qg = Qg; a.Ug = Ug; a.lam = la; a.lam2 = lb;
                 a.z = z; a.zhat = zhat; a.dk = dk; a.zk = zk; a.rc = rc; a.rs = rs; a.perm = perm; a.cols = cols; a.pos = pos;
-                a.tcnt = tcnt; a.ra = ra; a.rb = rb; a.kcnt = kcnt; a.nrot = nrot; a.fail = fail; a.tasks = tasks;
+                a.tcnt = tcnt; a.ctype = ctype; a.ra = ra; a.rb = rb; a.kcnt = kcnt; a.nrot = nrot; a.fail = fail; a.tasks = tasks;
                 k_dc_sort<<<dim3((mmax + 255) / 256, nodes), 256, (size_t)mmax * 8, st>>>(a);
-                k_dc_deflate<<<nodes, 256, (size_t)mmax * 24 + 16, st>>>(a);
+                {
+                    const size_t need = (size_t)mmax * 24 + 16;
+                    if (need <= smem_limit) k_dc_deflate<<<nodes, 256, need, st>>>(a, 1);
+                    else k_dc_deflate<<<nodes, 256, 0, st>>>(a, 0);
+                }
                 k_dc_rot<<<dim3((mmax + 255) / 256, nodes), 256, 0, st>>>(a);
                 k_dc_move<<<dim3((mmax + 255) / 256, mmax, nodes), 256, 0, st>>>(a);
                 k_dc_secular<<<dim3((mmax + 7) / 8, nodes), 256, (size_t)mmax * 16, st>>>(a);
