@@ -288,9 +288,30 @@ def test_block_and_scalar_eigensolvers_agree(xb, kat, name):
     assert np.max(np.abs(p0 - p1)) < 1e-8
 
 
+def test_ragged_batch_of_large_molecules(xb, kat):
+    """Batch whose matrices are beyond the shared-memory solvers: the Householder / divide-and-conquer solver is looped
+    over the molecules on the host and skips those that already left the SCC loop (they converge at different
+    iterations); a small molecule in the same batch rides along.  The two-level Jacobi (solver 3) must agree."""
+    names = ["taxol", "caffeine", "remdesivir", "rivaroxaban"]   # 299, 66, 208, 144 AOs: 66 < 91 once overflowed the Cholesky scratch
+    mols = [kat[n] for n in names]
+    b = xb.BatchCalculator([m["numbers"] for m in mols])
+    pos = np.concatenate([m["xyz"] for m in mols])
+    r = b.singlepoint(pos)
+    assert r["all_converged"]
+    assert len(set(int(x) for x in r["niter"])) > 1          # they do leave the loop at different iterations
+    for i, m in enumerate(mols):
+        _compare(xb, m, _oracle(m), b, r, i)
+    b3 = xb.BatchCalculator([m["numbers"] for m in mols])
+    b3.set_solver(3)
+    r3 = b3.singlepoint(pos)
+    assert np.array_equal(r["niter"], r3["niter"])
+    assert np.max(np.abs(r["energies"] - r3["energies"])) < 1e-9
+    assert np.max(np.abs(r["gradients"] - r3["gradients"])) < 1e-8
+
+
 @pytest.mark.parametrize("kind", ["water64", "peptide3"])
 def test_large_system_two_level_jacobi(xb, kat, kind):
-    """Matrices beyond the shared-memory solvers (two-level block Jacobi in HBM, overlap orthogonaliser from the
+    """Matrices beyond the shared-memory solvers (Householder + divide and conquer in HBM, overlap orthogonaliser from the
     blocked Cholesky factorisation of S): same energies, gradients, charges and iteration count as the oracle."""
     from bench import make_peptide_cluster, make_water_cluster
     from oracle.oracle import Oracle

@@ -91,6 +91,10 @@ struct Dev {
     const long long* pc0;
     const double *pc_xyz, *pc_q, *pc_gam;
     double *pc_grad, *vpc;
+    // blocked Cholesky of the overlap matrix (kernels_chol.cuh): inverse diagonal blocks, chol_stride doubles per molecule
+    // (their number of 64-blocks times 64 x 64 can exceed nao^2 for small members of a batch, so they have their own buffer)
+    double* cholD;
+    long long chol_stride;
     // shell-pair gradient partials
     double *gpair;   // [npair][4] : gx,gy,gz,dCN
     const long long* pair0;

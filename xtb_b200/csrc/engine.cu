@@ -314,6 +314,8 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
             d.hjM = I.dalloc<double>((size_t)s.tot_hj); d.hjJ = I.dalloc<double>((size_t)s.tot_hj);
             d.hj_flag = I.dalloc<int>((size_t)(s.tot_hj / (128 * 128)));
             d.hj_count = I.dalloc<int>(nmol); d.hj_conv = I.dalloc<int>(nmol); d.hj_sigma = I.dalloc<double>(nmol);
+            d.chol_stride = (long long)((s.max_nao + CB - 1) / CB) * CB * CB;
+            d.cholD = I.dalloc<double>((size_t)nmol * d.chol_stride);
             I.eig.init(s.max_nao, device);
             I.have_eig = true;
             I.bytes += I.eig.bytes;

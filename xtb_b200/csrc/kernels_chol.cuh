@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_bchol_diag(Dev d, int k) {
         }
     }
     __syncthreads();
-    double* Dk = d.T + m.mat0 + (long long)k * CB * CB;
+    double* Dk = d.cholD + (long long)im * d.chol_stride + (long long)k * CB * CB;
     for (int t = tid; t < CB * CB; t += nt) {
         const int r = t % CB, c = t / CB;
         if (r < b && c < b) W[(c0 + r) + (long long)n * (c0 + c)] = (r >= c) ? A[r][c] : 0.0;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(128) k_bchol_panel(Dev d, int k) {
     const int b = min(CB, n - c0), mr = min(CB, n - r0);
     __shared__ double As[GK][GLD], Bs[GK][GLD];
     double* W = d.W + m.mat0;
-    const double* Dk = d.T + m.mat0 + (long long)k * CB * CB;
+    const double* Dk = d.cholD + (long long)blockIdx.y * d.chol_stride + (long long)k * CB * CB;
     double acc[4][4][2];
     bchol_zero(acc);
     // op(B)(kk, c) = D_k(c, kk) = Dk[c + 64 kk]
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128) k_bchol_scale(Dev d) {
     const int mr = min(CB, n - r0);
     __shared__ double As[GK][GLD], Bs[GK][GLD];
     double* W = d.W + m.mat0;
-    const double* Di = d.T + m.mat0 + (long long)i * CB * CB;
+    const double* Di = d.cholD + (long long)blockIdx.y * d.chol_stride + (long long)i * CB * CB;
     double acc[4][4][2];
     bchol_zero(acc);
     gemm64_acc<false, false>(acc, Di, CB, W + r0 + (long long)n * c0, n, mr, CB, mr, As, Bs);
@@ -165,7 +165,7 @@ __global__ void k_bchol_inv_diag(Dev d) {
     const int n = m.nao, j = blockIdx.x, c0 = CB * j;
     if (c0 >= n) return;
     const int b = min(CB, n - c0);
-    const double* Dj = d.T + m.mat0 + (long long)j * CB * CB;
+    const double* Dj = d.cholD + (long long)blockIdx.y * d.chol_stride + (long long)j * CB * CB;
     double* X = d.X + m.mat0;
     for (int t = threadIdx.x; t < CB * CB; t += blockDim.x) {
         const int r = t % CB, c = t / CB;
