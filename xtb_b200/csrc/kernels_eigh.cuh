@@ -433,18 +433,20 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
 // ---------------------------------------------------------------------------------------------------------------
 // The columns of the (trailing) matrix are dealt cyclically to the CTAs of a cooperative grid and stay in their shared
 // memory for the whole reduction, so the unblocked two-sided update A -= v w^T + w v^T (dsytd2) costs no HBM or L2
-// traffic at all; only v and y = A v travel through L2 between the CTAs (two grid barriers per column).  Below that
-// order the panel kernel above is bound by L2 round trips (~12 us per column); this form needs about half.
+// traffic at all.  One grid barrier per column: before it every CTA publishes its entries of y = A v and the owner of
+// the next column publishes that column as it stands; after it every CTA forms w, updates its columns and forms the
+// NEXT reflector itself from the published column (redundantly, O(m) work), so no second exchange is needed.  The
+// panel kernel above is bound by L2 round trips below this order (~12 us per column); this form needs ~6.
 struct SytrdSmemArgs {
     double* A;          // n x n; the reduction covers A[j0:, j0:]; reflectors are stored below the sub-diagonal
     int n, j0;          // j0 must be a multiple of NB
     double *d, *e, *tau;
-    double* vbuf;       // [n] current reflector, rows relative to j0
-    double* ybuf;       // [n] y = A v
-    double* sc;         // [2] tau of the current column (double buffered)
+    double* cbuf;       // [2][n] next column as published by its owner (double buffered by the parity of the column)
+    double* ybuf;       // [2][n] y = A v
     double* Gf;         // Gram matrices of the block reflectors (as written by the panel kernel)
     unsigned* bar;
 };
+constexpr int kResRows = 2;   // rows of a column per thread: the resident kernel takes orders up to kResRows * kSytrdThreads
 inline size_t sytrd_smem_resident_bytes(int m0, int grid) {
     const size_t slots = (size_t)(m0 + grid - 1) / grid;
     return (slots * m0 + 2 * (size_t)m0 + 128) * sizeof(double);
@@ -452,7 +454,7 @@ inline size_t sytrd_smem_resident_bytes(int m0, int grid) {
 
 __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a) {
     extern __shared__ double sm_dyn[];
-    __shared__ double red[32], sh_tau;
+    __shared__ double red[32], sh_d, sh_alpha;
     const int n = a.n, j0 = a.j0, m0 = n - j0, G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const long long ld = n;
@@ -468,41 +470,58 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
     }
     __syncthreads();
     unsigned target = 0;
-    double sqnext = 0.0;   // sum of squares below the sub-diagonal of the next column, formed while it is updated
-    for (int jj = 0; jj < m0; ++jj) {
-        const int j = j0 + jj, owner = jj % G, mm = m0 - jj - 1;
-        // ---- reflector of column jj by its owner (the column is up to date in its shared memory)
-        if (cta == owner) {
-            double* col = cols + (size_t)(jj / G) * m0;
-            double sq = sqnext;
-            if (jj == 0) {
-                for (int r = 2 + tid; r < m0; r += nthr) sq += col[r] * col[r];
-                sq = block_sum_sh(sq, red);
-            }
-            if (tid == 0) a.d[j] = col[jj];
-            if (mm > 0) {
-                const double alpha = col[jj + 1];
-                double beta = alpha, tau = 0.0, scal = 0.0;
-                if (sq > 0.0) {
-                    beta = -copysign(sqrt(alpha * alpha + sq), alpha);
-                    tau = (beta - alpha) / beta;
-                    scal = 1.0 / (alpha - beta);
-                }
-                if (tid == 0) { a.e[j] = beta; a.tau[j] = tau; a.sc[jj & 1] = tau; }
-                for (int r = jj + 1 + tid; r < m0; r += nthr) {
-                    const double v = (r == jj + 1) ? 1.0 : col[r] * scal;
-                    a.vbuf[r] = v;
-                    if (r >= jj + 2) a.A[(j0 + r) + ld * j] = v;
-                }
+    double tau = 0.0;
+    // Reflector of column jn from its up-to-date entries cn[k] (row jn + tid + k nthr) held in registers by every CTA:
+    // v -> sv, tau; CTA jn % G stores d, e, tau and the reflector.  Ends with a CTA barrier.
+    auto form_reflector = [&](int jn, const double (&cn)[kResRows]) {
+        double sq = 0.0;
+#pragma unroll
+        for (int k = 0; k < kResRows; ++k) {
+            const int r = jn + tid + k * nthr;
+            if (r == jn) sh_d = cn[k];
+            else if (r == jn + 1) sh_alpha = cn[k];
+            else if (r < m0) sq += cn[k] * cn[k];
+        }
+        sq = block_sum_sh(sq, red);
+        const bool writer = cta == jn % G;
+        if (jn == m0 - 1) {
+            if (writer && tid == 0) a.d[j0 + jn] = sh_d;
+            tau = 0.0;
+            return;
+        }
+        const double alpha = sh_alpha;
+        double beta = alpha, scal = 0.0;
+        tau = 0.0;
+        if (sq > 0.0) {
+            beta = -copysign(sqrt(alpha * alpha + sq), alpha);
+            tau = (beta - alpha) / beta;
+            scal = 1.0 / (alpha - beta);
+        }
+        if (writer && tid == 0) { a.d[j0 + jn] = sh_d; a.e[j0 + jn] = beta; a.tau[j0 + jn] = tau; }
+#pragma unroll
+        for (int k = 0; k < kResRows; ++k) {
+            const int r = jn + tid + k * nthr;
+            if (r > jn && r < m0) {
+                const double v = (r == jn + 1) ? 1.0 : cn[k] * scal;
+                sv[r] = v;
+                if (writer && r >= jn + 2) a.A[(j0 + r) + ld * (j0 + jn)] = v;
             }
         }
-        if (mm == 0) break;
-        grid_barrier(a.bar, G, target);
-        // ---- y = A v on the owned columns; Gram entries of the block reflector (v_k^T v_i, k < i in the same block)
-        if (tid == 0) sh_tau = __ldcg(a.sc + (jj & 1));
-        for (int r = jj + 1 + tid; r < m0; r += nthr) sv[r] = __ldcg(a.vbuf + r);
         __syncthreads();
-        const double tau = sh_tau;
+    };
+    {   // first column: published by its owner, reflector formed by everybody
+        if (cta == 0) for (int r = tid; r < m0; r += nthr) a.cbuf[ld + r] = cols[r];
+        grid_barrier(a.bar, G, target);
+        double cn[kResRows];
+#pragma unroll
+        for (int k = 0; k < kResRows; ++k) { const int r = tid + k * nthr; cn[k] = r < m0 ? __ldcg(a.cbuf + ld + r) : 0.0; }
+        form_reflector(0, cn);
+    }
+    for (int jj = 0; jj < m0 - 1; ++jj) {
+        const int j = j0 + jj, mm = m0 - jj - 1;
+        double* ybuf = a.ybuf + (jj & 1) * ld;
+        double* cbuf = a.cbuf + (jj & 1) * ld;
+        // ---- y = A v on the owned columns; Gram entries of the block reflector (v_k^T v_i, k < i in the same block)
         const int s0 = (jj + 1 - cta + G - 1) / G;            // first owned slot with column > jj (cta + s G >= jj + 1)
         const int sfirst = cta >= jj + 1 ? 0 : s0;
         const int nact = nslot - sfirst;
@@ -531,41 +550,60 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
             s = warp_sum(s);
             if (lane == 0) part[job] = s;
         }
+        if ((jj + 1) % G == cta) {                            // the next column as it stands (its update comes after the barrier)
+            const double* col = cols + (size_t)((jj + 1) / G) * m0;
+            for (int r = jj + 1 + tid; r < m0; r += nthr) cbuf[r] = col[r];
+        }
         __syncthreads();
         for (int lc = tid; lc < njobcols; lc += nthr) {
             double s = 0.0;
             for (int q = 0; q < Q; ++q) s += part[lc * Q + q];
-            if (lc < nact) a.ybuf[cta + (sfirst + lc) * G] = s;
+            if (lc < nact) ybuf[cta + (sfirst + lc) * G] = s;
             else a.Gf[(size_t)(j / NB) * NB * NB + (kg - blk0) + NB * (j - blk0)] = s;
         }
         grid_barrier(a.bar, G, target);
-        // ---- w = tau y - tau^2/2 (v^T y) v, then A -= v w^T + w v^T on the owned columns (rows and columns > jj)
-        double vy = 0.0;
-        for (int r = jj + 1 + tid; r < m0; r += nthr) { const double y = __ldcg(a.ybuf + r); sw[r] = y; vy += sv[r] * y; }
+        // ---- w = tau y - tau^2/2 (v^T y) v;  A -= v w^T + w v^T on the owned columns and on the published next column
+        double vy = 0.0, cn[kResRows];
+#pragma unroll
+        for (int k = 0; k < kResRows; ++k) {
+            const int r = jj + 1 + tid + k * nthr;
+            cn[k] = 0.0;
+            if (r < m0) { const double y = __ldcg(ybuf + r); cn[k] = __ldcg(cbuf + r); sw[r] = y; vy += sv[r] * y; }
+        }
         vy = block_sum_sh(vy, red);
         const double coef = -0.5 * tau * tau * vy;
-        for (int r = jj + 1 + tid; r < m0; r += nthr) sw[r] = tau * sw[r] + coef * sv[r];
+#pragma unroll
+        for (int k = 0; k < kResRows; ++k) {
+            const int r = jj + 1 + tid + k * nthr;
+            if (r < m0) sw[r] = tau * sw[r] + coef * sv[r];
+        }
         __syncthreads();
-        // the owner of the next column comes first so that its norm is ready when the others are still updating
-        const bool own_next = (jj + 1) % G == cta;
-        double sq = 0.0;
-        if (own_next) {
-            double* col = cols + (size_t)((jj + 1) / G) * m0;
-            const double wc = sw[jj + 1], vc = sv[jj + 1];
-            for (int r = jj + 1 + tid; r < m0; r += nthr) {
-                const double x = col[r] - (sv[r] * wc + sw[r] * vc);
-                col[r] = x;
-                if (r >= jj + 3) sq += x * x;
+        {   // thread = (row, slot parity): rows fastest so that the shared-memory accesses are conflict free
+            double vr[kResRows], wr[kResRows];
+#pragma unroll
+            for (int k = 0; k < kResRows; ++k) {
+                const int r = jj + 1 + tid + k * nthr;
+                vr[k] = r < m0 ? sv[r] : 0.0;
+                wr[k] = r < m0 ? sw[r] : 0.0;
+            }
+            for (int s = 0; s < nact; ++s) {
+                const int c = cta + (sfirst + s) * G;
+                const double wc = sw[c], vc = sv[c];
+                double* col = cols + (size_t)(sfirst + s) * m0;
+#pragma unroll
+                for (int k = 0; k < kResRows; ++k) {
+                    const int r = jj + 1 + tid + k * nthr;
+                    if (r < m0) col[r] -= vr[k] * wc + wr[k] * vc;
+                }
             }
         }
-        const int sskip = own_next ? 1 : 0;   // the next column is the first active slot of its owner
-        for (int idx = tid; idx < (nact - sskip) * mm; idx += nthr) {
-            const int s = idx / mm + sskip, r = jj + 1 + (idx - (s - sskip) * mm);
-            const int c = cta + (sfirst + s) * G;
-            cols[(size_t)(sfirst + s) * m0 + r] -= sv[r] * sw[c] + sw[r] * sv[c];
+        const double wn = sw[jj + 1], vn = sv[jj + 1];
+#pragma unroll
+        for (int k = 0; k < kResRows; ++k) {
+            const int r = jj + 1 + tid + k * nthr;
+            if (r < m0) cn[k] -= sv[r] * wn + sw[r] * vn;
         }
-        if (own_next) sqnext = block_sum_sh(sq, red);
-        else __syncthreads();
+        form_reflector(jj + 1, cn);
     }
 }
 
@@ -851,7 +889,7 @@ struct EighWork {
     int *perm = nullptr, *cols = nullptr, *pos = nullptr, *tcnt = nullptr, *ctype = nullptr, *ra = nullptr, *rb = nullptr, *kcnt = nullptr, *nrot = nullptr,
         *fail = nullptr, *rank = nullptr;
     unsigned* bar = nullptr;
-    double *vbuf = nullptr, *ybuf = nullptr, *scbuf = nullptr;
+    double *cbuf = nullptr, *ybuf = nullptr;
     size_t smem_limit = 0;
     int resident_max = 0;      // largest trailing order the shared-memory resident tridiagonalisation takes
     long long* prof = nullptr;
@@ -896,7 +934,7 @@ struct EighWork {
         perm = alloc<int>(n); cols = alloc<int>(n); pos = alloc<int>(n); tcnt = alloc<int>(3 * n); ctype = alloc<int>(n); ra = alloc<int>(n); rb = alloc<int>(n);
         kcnt = alloc<int>(n); nrot = alloc<int>(n); fail = alloc<int>(1); rank = alloc<int>(n);
         bar = alloc<unsigned>(1);
-        vbuf = alloc<double>(n); ybuf = alloc<double>(n); scbuf = alloc<double>(2);
+        cbuf = alloc<double>(2 * n); ybuf = alloc<double>(2 * n);
         prof = alloc<long long>(8);
         tasks = alloc<GemmTask>(2 * n);
         grid = nsm;
@@ -909,8 +947,9 @@ struct EighWork {
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 8)));
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_bt_tfactor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NB * (NB + 1) * 8)));
         resident_max = 0;
-        const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin - 2048;   // static shared memory of the kernel
-        for (int m = 1; m <= nmax; ++m) if (sytrd_smem_resident_bytes(m, grid) <= smem_cap) resident_max = m;
+        const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin - 1024;   // static shared memory of the kernel
+        for (int m = 1; m <= std::min(nmax, kResRows * kSytrdThreads); ++m)
+            if (sytrd_smem_resident_bytes(m, grid) <= smem_cap) resident_max = m;
         if (std::getenv("XTBB200_NO_RESIDENT_SYTRD")) resident_max = 0;
         if (resident_max > 0)
             XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -983,7 +1022,7 @@ struct EighWork {
         if (jres >= 0) {
             XTB_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
             SytrdSmemArgs ra;
-            ra.A = A; ra.n = n; ra.j0 = jres; ra.d = dd; ra.e = ee; ra.tau = tau; ra.vbuf = vbuf; ra.ybuf = ybuf; ra.sc = scbuf;
+            ra.A = A; ra.n = n; ra.j0 = jres; ra.d = dd; ra.e = ee; ra.tau = tau; ra.cbuf = cbuf; ra.ybuf = ybuf;
             ra.Gf = Gf; ra.bar = bar;
             void* args[] = {&ra};
             hook(0, 0, 0);
