@@ -53,7 +53,7 @@ __constant__ int c_ord[10][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {2,
 // Hamiltonian gradient: one warp per off-site shell pair (is > js, different atoms, r^2 <= 1600).
 // The spherical weights are transformed to the Cartesian basis so that each lane contracts its own
 // Cartesian component pair; result per pair: gpair[p] = (gx, gy, gz, dCN).
-__global__ void __launch_bounds__(kIntWarps * 32) k_grad_h0(Dev d) {
+__global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long npair = (long long)m.nsh * (m.nsh + 1) / 2;

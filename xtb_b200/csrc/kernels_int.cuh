@@ -91,7 +91,7 @@ __device__ __forceinline__ double h0scal(int li, int lj, double eni, double enj)
 constexpr int kIntWarps = 4;
 
 // S, D, Q, H0, H0_noovlp for all shell pairs (is >= js).  grid = (ceil(npair/kIntWarps), nmol)
-__global__ void __launch_bounds__(kIntWarps * 32) k_sdqh0(Dev d) {
+__global__ void __launch_bounds__(kIntWarps * 32, 6) k_sdqh0(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long npair = (long long)m.nsh * (m.nsh + 1) / 2;
