@@ -50,7 +50,9 @@ int xtbb200_setExternalCharges(xtbb200_TBatch batch, const int* npc, const int* 
  * Householder tridiagonalisation + divide and conquer + back-transformation beyond), 1 = scalar one-sided Jacobi,
  * 2 = (matrices beyond shared memory) overlap orthogonaliser X = V s^-1/2 from the eigen-decomposition of S instead of
  * the blocked Cholesky X = L^-T, 3 = (matrices beyond shared memory) two-level block Jacobi instead of Householder +
- * divide and conquer.  All give the same spectrum and density to rounding; used by the parity tests. */
+ * divide and conquer, 4 = (ensembles whose matrices all have one order <= 160) batched Householder + divide and conquer
+ * instead of the block Jacobi (an independent cross-check; measured 2.3x slower than the warm-started Jacobi at 144 AOs).
+ * All give the same spectrum and density to rounding; used by the parity tests. */
 int xtbb200_setSolver(xtbb200_TBatch batch, int mode);
 
 /* The large-matrix symmetric eigensolver of the SCC loop on its own (what dsyevd is to the reference,

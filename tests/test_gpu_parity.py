@@ -288,6 +288,27 @@ def test_block_and_scalar_eigensolvers_agree(xb, kat, name):
     assert np.max(np.abs(p0 - p1)) < 1e-8
 
 
+def test_batched_householder_solver_agrees_with_block_jacobi(xb, kat):
+    """Solver mode 4: ensembles of one matrix order through the batched Householder + divide-and-conquer path (one CTA per
+    matrix tridiagonalises in shared memory, D&C and back-transformation batched over the ensemble) -- an independent
+    algorithm for the same eigenproblems as the block Jacobi of mode 0."""
+    s = kat["caffeine"]
+    rng = np.random.default_rng(3)
+    nmol = 24
+    pos = np.concatenate([s["xyz"] + 0.05 * rng.standard_normal(s["xyz"].shape) for _ in range(nmol)])
+    out = []
+    for mode in (0, 4):
+        b = xb.BatchCalculator([s["numbers"]] * nmol)
+        b.set_solver(mode)
+        r = b.singlepoint(pos)
+        assert r["all_converged"]
+        out.append(r)
+    assert np.array_equal(out[0]["niter"], out[1]["niter"])
+    assert np.max(np.abs(out[0]["energies"] - out[1]["energies"])) < 1e-10
+    assert np.max(np.abs(out[0]["gradients"] - out[1]["gradients"])) < 1e-9
+    assert np.max(np.abs(out[0]["charges"] - out[1]["charges"])) < 1e-9
+
+
 def test_ragged_batch_of_large_molecules(xb, kat):
     """Batch whose matrices are beyond the shared-memory solvers: the Householder / divide-and-conquer solver is looped
     over the molecules on the host and skips those that already left the SCC loop (they converge at different

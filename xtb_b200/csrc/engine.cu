@@ -43,14 +43,14 @@ __global__ void k_count_active(Dev d, int* out) {
 }
 
 // after the Householder / divide-and-conquer eigensolver: bookkeeping of the molecules that were diagonalised
-__global__ void k_eigh_finish(Dev d, const int* fail) {
+__global__ void k_eigh_finish(Dev d, const int* fail, int fail_stride) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.nmol) return;
     MolState& s = d.st[i];
     if (s.done) return;
     s.sweeps = 0;
     s.zvalid = 1;
-    if (*fail) s.fail = 12;
+    if (fail[(long long)i * fail_stride]) s.fail = 12;
 }
 
 // kernel classes for the per-kernel device timers (bench.py roofline, profiles/)
@@ -158,6 +158,7 @@ struct Batch::Impl {
     Dev d;
     EighWork eig;             // Householder + divide-and-conquer eigensolver for matrices beyond shared memory
     bool have_eig = false;
+    bool cta_eig = false;          // batched Householder + divide and conquer for ensembles of one matrix order (solver mode 4)
     bool has_followers = false;    // some molecules share their composition with an earlier one (conformer ensemble)
     std::vector<long long> h_pc0;  // external point charges: per-molecule ranges (empty: none)
     int max_npc = 0;
@@ -513,6 +514,7 @@ int Batch::singlepoint(bool restart) {
     d.jb_inner = kJbInnerSweeps;
     d.jb_tol = 0.0;
     if (const char* e = std::getenv("XTBB200_JB_TOL")) d.jb_tol = std::atof(e);   // tuning knob
+    if (const char* e = std::getenv("XTBB200_SOLVER")) I.solver = std::atoi(e);    // tuning knob: overrides xtbb200_setSolver
     d.jb_qtol = kJbQuadraticStop;
     if (const char* e = std::getenv("XTBB200_JB_QTOL")) d.jb_qtol = std::atof(e);   // tuning knob
     if (const char* e = std::getenv("XTBB200_JB_INNER")) d.jb_inner = std::max(1, std::atoi(e));   // tuning knob
@@ -588,6 +590,19 @@ int Batch::singlepoint(bool restart) {
     const bool use_scalar = !use_blk && I.fits_scalar;            // scalar Jacobi, matrix in shared memory
     const bool hier = !use_blk && !use_scalar;                    // matrix in HBM
     const bool dc = hier && I.solver != 3;                        // Householder + divide and conquer (3: two-level Jacobi)
+    bool bdc = false;                                             // the same for a batch of small matrices of one order
+    if (use_blk && I.solver == 4) {
+        bool uniform = true;
+        for (auto& m : s.mol) uniform = uniform && m.nao == s.max_nao;
+        if (uniform && s.max_nao > 1 && s.max_nao <= kCtaEigMax) {
+            if (!I.cta_eig) {
+                if (!I.have_eig) { I.eig.init(s.max_nao, I.device); I.have_eig = true; }
+                I.eig.init_batch(nmol, s.max_nao);
+                I.cta_eig = true;
+            }
+            bdc = true;
+        }
+    }
     const bool xtri = !(hier && I.solver == 2);                   // X = L^-T is upper triangular (dense when taken from eig(S))
     const bool sm = true;
     const int hj_nb = hj_nblocks(s.max_nao), hj_nbp = hj_nb / 2, hj_rt = (s.max_nao + GT - 1) / GT;
@@ -655,9 +670,16 @@ int Batch::singlepoint(bool restart) {
         KL(K_FOCK, k_fock<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
         KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.H, d.X, d.T, xtri ? 2 : 0, 1));   // T = H X
         KL(K_GEMM_XHX, k_gemm<true, false><<<ggrid, 128, 0, st>>>(d, d.X, d.T, d.W, xtri ? 3 : 0, 1));    // W = X^T T
-        if (!dc && (it > 0 || (restart && I.have_wfn)))
+        if (!dc && !bdc && (it > 0 || (restart && I.have_wfn)))
             KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.W, d.Zm, d.T, 0, 2));   // T = A' Z_prev
-        if (use_blk && it == 0 && I.has_followers && !(restart && I.have_wfn) && I.solver == 0) {
+        if (bdc) {
+            I.prof_begin(K_JACOBI, st);
+            k_eig_skip_b<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.eig.bskip);
+            const int nla = I.eig.solve_batch(st, d.W, d.emo, d.Zm) + 2;
+            k_eigh_finish<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.eig.bfail, 1);
+            I.prof_end(K_JACOBI, st);
+            I.k_launches[K_JACOBI] += nla; nl += nla;
+        } else if (use_blk && it == 0 && I.has_followers && !(restart && I.have_wfn) && I.solver == 0) {
             // first diagonalisation of an ensemble: leaders cold, followers warm from their leader's eigenvectors
             KL(K_JACOBI, k_jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d, 1));
             KL(K_JACOBI, k_lead_copy<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
@@ -675,7 +697,7 @@ int Batch::singlepoint(bool restart) {
             for (int im = 0; im < nmol; ++im)
                 if (!I.h_done[im])
                     I.eig.solve(st, d.W + s.mol[im].mat0, s.mol[im].nao, d.emo + s.mol[im].ao0, d.Zm + s.mol[im].mat0, false, hook);
-            KL(K_EIG_BT, k_eigh_finish<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.eig.fail));
+            KL(K_EIG_BT, k_eigh_finish<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.eig.fail, 0));
         } else if (hier) hjacobi(d.W, 1, K_JACOBI);
         else if (npairs * 32 <= 1024) KL(K_JACOBI, launch_jacobi<32>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 16 <= 1024) KL(K_JACOBI, launch_jacobi<16>(d, nmol, s.max_nao, sm, st));

@@ -58,9 +58,12 @@ __device__ __forceinline__ GemmTask gemm_task_dev(const double* A, int lda, cons
     return t;
 }
 
+// tasks != null: task = tasks[blockIdx.y + zstride * blockIdx.z] (zstride > 0: batch of matrices along z, no K split)
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(128, 3) k_eg_gemm(GemmTask t0, const GemmTask* __restrict__ tasks) {
-    const GemmTask t = tasks ? tasks[blockIdx.y] : t0;
+__global__ void __launch_bounds__(128, 3) k_eg_gemm(GemmTask t0, const GemmTask* __restrict__ tasks, int zstride = 0,
+                                                  const int* __restrict__ skip = nullptr) {
+    if (skip && skip[blockIdx.z]) return;
+    const GemmTask t = tasks ? tasks[blockIdx.y + (long long)zstride * blockIdx.z] : t0;
     const int tm = (t.M + GT - 1) / GT, tn = (t.N + GT - 1) / GT;
     if ((int)blockIdx.x >= tm * tn) return;
     const int r0 = (blockIdx.x % tm) * GT, c0 = (blockIdx.x / tm) * GT;
@@ -652,13 +655,30 @@ __global__ void k_bt_sum(double* __restrict__ Wz, long long zstride, int nz, lon
 // ---------------------------------------------------------------------------------------------------------------
 struct DcArgs {
     int n, depth;
+    const double* d;      // diagonal of T
     const double* e;      // sub-diagonal of T (coupling of the torn blocks)
+    // batch of matrices of the same order along blockIdx.z (0 strides: single matrix): vectors are vs apart, matrices
+    // ms, skip[matrix] != 0 leaves a matrix out
+    long long vs, ms;
+    const int* skip;
     double *Qo, *Qn;      // eigenvector blocks of the children / of the merged nodes
     double *U, *Qg, *Ug;  // delta matrix; non-deflated columns and update matrix in grouped order
     double *lam, *lam2, *z, *zhat, *dk, *zk, *rc, *rs;
     int *perm, *cols, *pos, *tcnt, *ctype, *ra, *rb, *kcnt, *nrot, *fail;
     GemmTask* tasks;
 };
+// select the matrix of the batch this CTA works on; false: skipped
+__device__ __forceinline__ bool dc_select(DcArgs& a) {
+    const long long ib = blockIdx.z;
+    if (a.skip && a.skip[ib]) return false;
+    const long long v = ib * a.vs, m = ib * a.ms;
+    a.d += v; a.e += v; a.Qo += m; a.Qn += m; a.U += m; a.Qg += m; a.Ug += m;
+    a.lam += v; a.lam2 += v; a.z += v; a.zhat += v; a.dk += v; a.zk += v; a.rc += v; a.rs += v;
+    a.perm += v; a.cols += v; a.pos += v; a.tcnt += 3 * v; a.ctype += v; a.ra += v; a.rb += v; a.kcnt += v; a.nrot += v;
+    a.tasks += 2 * v;
+    if (a.vs) a.fail += ib;
+    return true;
+}
 struct DcNode { int lo, mid, hi; };
 __device__ __forceinline__ DcNode dc_node(const DcArgs& a, int t) {
     DcNode nd;
@@ -673,22 +693,27 @@ struct WarpPar {
     __device__ __forceinline__ double sum(double x) const { return warp_sum(x); }
 };
 
-// leaves of the tearing tree: 1x1 and 2x2 blocks of the torn matrix; thread per leaf
-__global__ void k_dc_leaves(int n, int D, const double* __restrict__ d, const double* __restrict__ e, double* __restrict__ lam,
-                            double* __restrict__ Q) {
+// leaves of the tearing tree: 1x1 and 2x2 blocks of the torn matrix; thread per leaf (a.depth = depth of the leaves)
+__global__ void k_dc_leaves(DcArgs a) {
+    if (!dc_select(a)) return;
+    const int n = a.n, D = a.depth;
+    const double* __restrict__ d = a.d;
+    const double* __restrict__ e = a.e;
+    double* __restrict__ lam = a.lam;
+    double* __restrict__ Q = a.Qo;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (1 << D)) return;
     const int lo = eigcore::tree_bound(n, D, t), hi = eigcore::tree_bound(n, D, t + 1);
     const long long ld = n;
-    double a = d[lo] - (lo > 0 ? fabs(e[lo - 1]) : 0.0);
+    double av = d[lo] - (lo > 0 ? fabs(e[lo - 1]) : 0.0);
     if (hi - lo == 1) {
-        a -= (hi < n ? fabs(e[hi - 1]) : 0.0);
-        lam[lo] = a;
+        av -= (hi < n ? fabs(e[hi - 1]) : 0.0);
+        lam[lo] = av;
         Q[lo + ld * lo] = 1.0;
     } else {
         const double c = d[lo + 1] - (hi < n ? fabs(e[hi - 1]) : 0.0), b = e[lo];
         double rt1, rt2, cs, sn;
-        eigcore::sym2x2(a, b, c, rt1, rt2, cs, sn);
+        eigcore::sym2x2(av, b, c, rt1, rt2, cs, sn);
         lam[lo] = rt1; lam[lo + 1] = rt2;
         Q[lo + ld * lo] = cs; Q[lo + 1 + ld * lo] = sn;
         Q[lo + ld * (lo + 1)] = -sn; Q[lo + 1 + ld * (lo + 1)] = cs;
@@ -697,6 +722,7 @@ __global__ void k_dc_leaves(int n, int D, const double* __restrict__ d, const do
 
 // update vector z (last row of the left block, first row of the right block) and ascending order of the eigenvalues
 __global__ void __launch_bounds__(256) k_dc_sort(DcArgs a) {
+    if (!dc_select(a)) return;
     extern __shared__ double sm_dyn[];
     const DcNode nd = dc_node(a, blockIdx.y);
     const int m = nd.hi - nd.lo;
@@ -718,6 +744,7 @@ __global__ void __launch_bounds__(256) k_dc_sort(DcArgs a) {
 // deflation: one CTA per node, sequential scan by thread 0 over eigenvalues / z / order / column kinds staged in shared
 // memory (use_smem) or, for nodes too large for it, in place in global memory
 __global__ void __launch_bounds__(256) k_dc_deflate(DcArgs a, int use_smem) {
+    if (!dc_select(a)) return;
     extern __shared__ double sm_dyn[];
     const DcNode nd = dc_node(a, blockIdx.x);
     const int m = nd.hi - nd.lo, lo = nd.lo;
@@ -751,6 +778,7 @@ __global__ void __launch_bounds__(256) k_dc_deflate(DcArgs a, int use_smem) {
 
 // Givens rotations of the deflation applied to the eigenvector columns; thread per row
 __global__ void __launch_bounds__(256) k_dc_rot(DcArgs a) {
+    if (!dc_select(a)) return;
     const int nr = a.nrot[blockIdx.y];
     if (nr == 0) return;
     const DcNode nd = dc_node(a, blockIdx.y);
@@ -768,6 +796,7 @@ __global__ void __launch_bounds__(256) k_dc_rot(DcArgs a) {
 
 // secular equation: warp per root (the lanes share the poles); delta(i,j) = d_i - lambda_j into U
 __global__ void __launch_bounds__(256) k_dc_secular(DcArgs a) {
+    if (!dc_select(a)) return;
     extern __shared__ double sm_dyn[];
     const int k = a.kcnt[blockIdx.y];
     if ((int)(blockIdx.x * (blockDim.x >> 5)) >= k) return;
@@ -789,6 +818,7 @@ __global__ void __launch_bounds__(256) k_dc_secular(DcArgs a) {
 
 // Loewner formula for the update vector that makes the computed roots exact.  CTA = 32 entries x 8 slices of the roots
 __global__ void __launch_bounds__(256) k_dc_zhat(DcArgs a) {
+    if (!dc_select(a)) return;
     __shared__ double sp[8][33];
     const int k = a.kcnt[blockIdx.y];
     if ((int)(blockIdx.x * 32) >= k) return;
@@ -813,6 +843,7 @@ __global__ void __launch_bounds__(256) k_dc_zhat(DcArgs a) {
 
 // eigenvectors of the rank-one update: U(i,j) = zhat_i / delta(i,j), normalised, rows stored in grouped order; warp per column
 __global__ void __launch_bounds__(256) k_dc_vec(DcArgs a) {
+    if (!dc_select(a)) return;
     const int k = a.kcnt[blockIdx.y];
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j >= k) return;
@@ -831,6 +862,7 @@ __global__ void __launch_bounds__(256) k_dc_vec(DcArgs a) {
 // GEMM tasks of the level, two per node: the top rows of the merged eigenvectors need the left-only and dense columns,
 // the bottom rows the dense and right-only ones; thread per node
 __global__ void k_dc_tasks(DcArgs a, int nodes) {
+    if (!dc_select(a)) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nodes) return;
     const DcNode nd = dc_node(a, t);
@@ -875,6 +907,164 @@ __global__ void k_dc_permute(int n, const double* __restrict__ Q, const int* __r
     if (t >= (long long)n * n) return;
     const int r = (int)(t % n), j = (int)(t / n);
     Z[r + (long long)n * rank[j]] = Q[t];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// batch of small matrices of one order (conformer ensembles, n <= kCtaEigMax): the same three stages, every launch
+// covering all matrices (blockIdx.z or .x = matrix).  The tridiagonalisation runs with one CTA per matrix, the matrix
+// resident in its shared memory (k_sytrd_smem with a single owner: no grid barrier at all).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kCtaEigMax = 160;
+
+// A: matrices ms apart (n x n, both triangles; on exit the reflectors below the sub-diagonal); d, e, tau: vs apart
+__global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_cta(double* __restrict__ Aall, long long ms, int n, double* __restrict__ dall,
+                                                                double* __restrict__ eall, double* __restrict__ tauall, long long vs,
+                                                                const int* __restrict__ skip) {
+    const long long ib = blockIdx.x;
+    if (skip && skip[ib]) return;
+    extern __shared__ double sm_dyn[];
+    __shared__ double red[32];
+    double* cols = sm_dyn;                 // n x n, column-major
+    double* sv = sm_dyn + (size_t)n * n;
+    double* sw = sv + n;
+    double* A = Aall + ib * ms;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    for (int t = tid; t < n * n; t += nthr) cols[t] = A[t];
+    __syncthreads();
+    for (int jj = 0; jj < n; ++jj) {
+        const int mm = n - jj - 1;
+        double* col = cols + (size_t)jj * n;
+        double sq = 0.0;
+        for (int r = jj + 2 + tid; r < n; r += nthr) sq += col[r] * col[r];
+        sq = block_sum_sh(sq, red);
+        if (tid == 0) dall[ib * vs + jj] = col[jj];
+        if (mm == 0) break;
+        const double alpha = col[jj + 1];
+        double beta = alpha, tau = 0.0, scal = 0.0;
+        if (sq > 0.0) {
+            beta = -copysign(sqrt(alpha * alpha + sq), alpha);
+            tau = (beta - alpha) / beta;
+            scal = 1.0 / (alpha - beta);
+        }
+        if (tid == 0) { eall[ib * vs + jj] = beta; tauall[ib * vs + jj] = tau; }
+        for (int r = jj + 1 + tid; r < n; r += nthr) {
+            const double v = (r == jj + 1) ? 1.0 : col[r] * scal;
+            sv[r] = v;
+            if (r >= jj + 2) col[r] = v;             // reflector storage (this column is not touched again)
+        }
+        __syncthreads();
+        // y = A v over the trailing block: warp per column
+        for (int c = jj + 1 + warp; c < n; c += nwarp) {
+            const double* cc = cols + (size_t)c * n;
+            double s = 0.0;
+            for (int r = jj + 1 + lane; r < n; r += 32) s += cc[r] * sv[r];
+            s = warp_sum(s);
+            if (lane == 0) sw[c] = s;
+        }
+        __syncthreads();
+        double vy = 0.0;
+        for (int r = jj + 1 + tid; r < n; r += nthr) vy += sv[r] * sw[r];
+        vy = block_sum_sh(vy, red);
+        const double coef = -0.5 * tau * tau * vy;
+        __syncthreads();
+        for (int r = jj + 1 + tid; r < n; r += nthr) sw[r] = tau * sw[r] + coef * sv[r];
+        __syncthreads();
+        for (int t = tid; t < mm * mm; t += nthr) {
+            const int r = jj + 1 + t % mm, c = jj + 1 + t / mm;
+            cols[(size_t)c * n + r] -= sv[r] * sw[c] + sw[r] * sv[c];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int t = tid; t < n * n; t += nthr) A[t] = cols[t];
+}
+
+// grouped copies of the non-deflated eigenvectors / deflated ones behind (k_dc_move for the batch): grid (slot, node,
+// matrix), the threads run over the rows
+__global__ void __launch_bounds__(64) k_dc_move_b(DcArgs a) {
+    if (!dc_select(a)) return;
+    const DcNode nd = dc_node(a, blockIdx.y);
+    const int m = nd.hi - nd.lo, p = blockIdx.x;
+    if (p >= m) return;
+    const int k = a.kcnt[blockIdx.y];
+    const long long ld = a.n;
+    const double* src = a.Qo + ld * (nd.lo + a.cols[nd.lo + p]);
+    double* dst = p < k ? a.Qg + ld * (nd.lo + a.pos[nd.lo + p]) : a.Qn + ld * (nd.lo + p);
+    for (int row = nd.lo + threadIdx.x; row < nd.hi; row += blockDim.x) dst[row] = src[row];
+}
+// final order of the batch: rank, sorted eigenvalues into w (stride ws), Z[:, rank[j]] = Q[:, j]; CTA per matrix
+__global__ void __launch_bounds__(256) k_dc_finish_b(DcArgs a, int* __restrict__ rankall, double* __restrict__ wall, long long ws,
+                                                     double* __restrict__ Zall) {
+    const long long ib = blockIdx.z;
+    if (!dc_select(a)) return;
+    extern __shared__ double sm_dyn[];
+    const int n = a.n;
+    int* rank = rankall + ib * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm_dyn[i] = a.lam[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = sm_dyn[i];
+        int r = 0;
+        for (int k = 0; k < n; ++k) { const double w = sm_dyn[k]; r += (w < v || (w == v && k < i)) ? 1 : 0; }
+        rank[i] = r;
+        wall[ib * ws + r] = v;
+    }
+    __syncthreads();
+    double* Z = Zall + ib * a.ms;
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) Z[t % n + (long long)n * rank[t / n]] = a.Qo[t];
+}
+// explicit V of block [jb, jb + kb) for every matrix; grid (elements, 1, matrix)
+__global__ void k_bt_formv_b(const double* __restrict__ Aall, long long ms, int n, int jb, int kb, double* __restrict__ Vball,
+                             long long vbs, const int* __restrict__ skip) {
+    const long long ib = blockIdx.z;
+    if (skip && skip[ib]) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * kb) return;
+    const int r = t % n, k = t / n, piv = jb + k + 1;
+    Vball[ib * vbs + t] = r < piv ? 0.0 : (r == piv ? 1.0 : Aall[ib * ms + r + (long long)n * (jb + k)]);
+}
+// T factor of one block for every matrix from G = V^T V (full kb x kb product, only k < i is used); CTA per matrix
+__global__ void __launch_bounds__(NB) k_bt_tfactor_b(const double* __restrict__ Gall, const double* __restrict__ tauall, long long vs,
+                                                     int jb, int kb, double* __restrict__ Tall, const int* __restrict__ skip) {
+    const long long ib = blockIdx.x;
+    if (skip && skip[ib]) return;
+    extern __shared__ double sm_dyn[];
+    double (*T)[NB + 1] = (double (*)[NB + 1])sm_dyn;
+    const int r = threadIdx.x;
+    const double* G = Gall + ib * NB * NB;
+    const double* tau = tauall + ib * vs;
+    for (int c = 0; c < NB; ++c) T[r][c] = 0.0;
+    __syncthreads();
+    for (int i = 0; i < kb; ++i) {
+        const double ti = tau[jb + i];
+        if (r < i) {
+            double s = 0.0;
+            for (int k = r; k < i; ++k) s += T[r][k] * G[k + NB * i];
+            T[r][i] = -ti * s;
+        } else if (r == i) T[r][i] = ti;
+        __syncthreads();
+    }
+    double* To = Tall + ib * NB * NB;
+    for (int c = 0; c < NB; ++c) To[r + NB * c] = T[r][c];
+}
+// GEMM tasks of one back-transformation step for every matrix; which: 0 G = V^T V, 1 W = V^T Z, 2 VT = V T, 3 Z -= VT W
+__global__ void k_bt_tasks_b(GemmTask* __restrict__ tasks, int nb, int which, int n, int jb, int kb, double* Vb, long long vbs,
+                             double* G, double* T, double* Wz, double* VT, double* Z, long long ms) {
+    const long long ib = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ib >= nb) return;
+    const int r0 = jb + 1, mr = n - r0;
+    double* V = Vb + ib * vbs;
+    GemmTask t;
+    if (which == 0) t = gemm_task_dev(V + r0, n, V + r0, n, G + ib * NB * NB, NB, kb, kb, mr);
+    else if (which == 1) t = gemm_task_dev(V + r0, n, Z + ib * ms + r0, n, Wz + ib * vbs, NB, kb, n, mr);
+    else if (which == 2) t = gemm_task_dev(V + r0, n, T + ib * NB * NB, NB, VT + ib * vbs + r0, n, mr, kb, kb);
+    else { t = gemm_task_dev(VT + ib * vbs + r0, n, Wz + ib * vbs, NB, Z + ib * ms + r0, n, mr, n, kb); t.alpha = -1.0; t.beta = 1.0; }
+    tasks[ib] = t;
+}
+// per-matrix "leave out" flags of the batch from the SCC state
+__global__ void k_eig_skip_b(Dev d, int* __restrict__ skip) {
+    const int im = blockIdx.x * blockDim.x + threadIdx.x;
+    if (im < d.nmol) skip[im] = d.st[im].done ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -965,6 +1155,91 @@ struct EighWork {
         for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     }
 
+    // ---- batch of nb matrices of one small order n (conformer ensembles): own scratch, every launch covers the batch
+    int bnb = 0, bn = 0;
+    double *bQa = nullptr, *bQb = nullptr, *bU = nullptr, *bQg = nullptr, *bUg = nullptr, *bVb = nullptr, *bVT = nullptr, *bWz = nullptr,
+           *bG = nullptr, *bT = nullptr, *bvec = nullptr;
+    int *bint = nullptr, *bskip = nullptr, *bfail = nullptr;
+    GemmTask *btasks = nullptr, *bbt = nullptr;
+    void init_batch(int nb, int n) {
+        if (n > kCtaEigMax) throw std::runtime_error("xtb_b200: batched eigensolver takes orders up to 160");
+        bnb = nb; bn = n;
+        const size_t n2 = (size_t)n * n, m = (size_t)nb * n2, v = (size_t)nb * n;
+        bQa = alloc<double>(m); bQb = alloc<double>(m); bU = alloc<double>(m); bQg = alloc<double>(m); bUg = alloc<double>(m);
+        bVb = alloc<double>((size_t)nb * n * NB); bVT = alloc<double>((size_t)nb * n * NB); bWz = alloc<double>((size_t)nb * n * NB);
+        bG = alloc<double>((size_t)nb * NB * NB); bT = alloc<double>((size_t)nb * NB * NB);
+        bvec = alloc<double>(11 * v);
+        bint = alloc<int>(12 * v);
+        bskip = alloc<int>(nb); bfail = alloc<int>(nb);
+        btasks = alloc<GemmTask>(2 * v); bbt = alloc<GemmTask>(nb);
+        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((n2 + 2 * n) * sizeof(double))));
+        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_bt_tfactor_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NB * (NB + 1) * 8)));
+    }
+    // A: nb matrices n^2 apart (destroyed), w: eigenvalues n apart, Z: eigenvectors n^2 apart; bskip[] selects (k_eig_skip_b)
+    int solve_batch(cudaStream_t st, double* A, double* w, double* Z) {
+        const int nb = bnb, n = bn;
+        const long long vs = n, ms = (long long)n * n, vbs = (long long)n * NB;
+        const size_t v = (size_t)nb * n;
+        int nl = 0;
+        double *dd_ = bvec, *ee_ = bvec + v, *tau_ = bvec + 2 * v;
+        XTB_CUDA_CHECK(cudaMemsetAsync(bfail, 0, nb * sizeof(int), st));
+        k_sytrd_cta<<<nb, kSytrdThreads, ((size_t)n * n + 2 * n) * sizeof(double), st>>>(A, ms, n, dd_, ee_, tau_, vs, bskip);
+        ++nl;
+        XTB_CUDA_CHECK(cudaMemsetAsync(bQa, 0, (size_t)nb * ms * sizeof(double), st));
+        XTB_CUDA_CHECK(cudaMemsetAsync(bQb, 0, (size_t)nb * ms * sizeof(double), st));
+        DcArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.n = n; a.d = dd_; a.e = ee_; a.vs = vs; a.ms = ms; a.skip = bskip;
+        a.Qo = bQa; a.Qn = bQb; a.U = bU; a.Qg = bQg; a.Ug = bUg;
+        a.lam = bvec + 3 * v; a.lam2 = bvec + 4 * v; a.z = bvec + 5 * v; a.zhat = bvec + 6 * v; a.dk = bvec + 7 * v; a.zk = bvec + 8 * v;
+        a.rc = bvec + 9 * v; a.rs = bvec + 10 * v;
+        a.perm = bint; a.cols = bint + v; a.pos = bint + 2 * v; a.tcnt = bint + 3 * v; a.ctype = bint + 6 * v; a.ra = bint + 7 * v;
+        a.rb = bint + 8 * v; a.kcnt = bint + 9 * v; a.nrot = bint + 10 * v;
+        int* rank_ = bint + 11 * v;
+        a.fail = bfail; a.tasks = btasks;
+        if (n < 2) throw std::runtime_error("xtb_b200: batched eigensolver needs n > 1");
+        const int D = eigcore::tree_depth(n);
+        a.depth = D;
+        k_dc_leaves<<<dim3(((1 << D) + 127) / 128, 1, nb), 128, 0, st>>>(a);
+        ++nl;
+        for (int depth = D - 1; depth >= 0; --depth) {
+            const int nodes = 1 << depth, mmax = (n + nodes - 1) / nodes;
+            a.depth = depth;
+            k_dc_sort<<<dim3((mmax + 255) / 256, nodes, nb), 256, (size_t)mmax * 8, st>>>(a);
+            k_dc_deflate<<<dim3(nodes, 1, nb), 256, (size_t)mmax * 24 + 16, st>>>(a, 1);
+            k_dc_rot<<<dim3((mmax + 255) / 256, nodes, nb), 256, 0, st>>>(a);
+            k_dc_move_b<<<dim3(mmax, nodes, nb), 64, 0, st>>>(a);
+            k_dc_secular<<<dim3((mmax + 7) / 8, nodes, nb), 256, (size_t)mmax * 16, st>>>(a);
+            k_dc_zhat<<<dim3((mmax + 31) / 32, nodes, nb), 256, 0, st>>>(a);
+            k_dc_vec<<<dim3((mmax + 7) / 8, nodes, nb), 256, 0, st>>>(a);
+            k_dc_tasks<<<dim3((nodes + 127) / 128, 1, nb), 128, 0, st>>>(a, nodes);
+            const int th = (mmax / 2 + 1 + GT - 1) / GT, tw = (mmax + GT - 1) / GT;
+            k_eg_gemm<false, false><<<dim3(th * tw, 2 * nodes, nb), 128, 0, st>>>(GemmTask(), btasks, 2 * n, bskip);
+            nl += 9;
+            std::swap(a.Qo, a.Qn);
+            std::swap(a.lam, a.lam2);
+        }
+        k_dc_finish_b<<<dim3(1, 1, nb), 256, (size_t)n * 8, st>>>(a, rank_, w, vs, Z);
+        ++nl;
+        const int nrefl = n - 1, nbb = (nrefl + NB - 1) / NB;
+        const int tz = (n + GT - 1) / GT;
+        for (int b = nbb - 1; b >= 0; --b) {
+            const int jb = b * NB, kb = std::min(NB, nrefl - jb), tk = (kb + GT - 1) / GT;
+            k_bt_formv_b<<<dim3((n * kb + 255) / 256, 1, nb), 256, 0, st>>>(A, ms, n, jb, kb, bVb, vbs, bskip);
+            k_bt_tasks_b<<<(nb + 127) / 128, 128, 0, st>>>(bbt, nb, 0, n, jb, kb, bVb, vbs, bG, bT, bWz, bVT, Z, ms);
+            k_eg_gemm<true, false><<<dim3(tk * tk, 1, nb), 128, 0, st>>>(GemmTask(), bbt, 1, bskip);
+            k_bt_tfactor_b<<<nb, NB, NB * (NB + 1) * sizeof(double), st>>>(bG, tau_, vs, jb, kb, bT, bskip);
+            k_bt_tasks_b<<<(nb + 127) / 128, 128, 0, st>>>(bbt, nb, 1, n, jb, kb, bVb, vbs, bG, bT, bWz, bVT, Z, ms);
+            k_eg_gemm<true, false><<<dim3(tk * tz, 1, nb), 128, 0, st>>>(GemmTask(), bbt, 1, bskip);
+            k_bt_tasks_b<<<(nb + 127) / 128, 128, 0, st>>>(bbt, nb, 2, n, jb, kb, bVb, vbs, bG, bT, bWz, bVT, Z, ms);
+            k_eg_gemm<false, false><<<dim3(tz * tk, 1, nb), 128, 0, st>>>(GemmTask(), bbt, 1, bskip);
+            k_bt_tasks_b<<<(nb + 127) / 128, 128, 0, st>>>(bbt, nb, 3, n, jb, kb, bVb, vbs, bG, bT, bWz, bVT, Z, ms);
+            k_eg_gemm<false, false><<<dim3(tz * tz, 1, nb), 128, 0, st>>>(GemmTask(), bbt, 1, bskip);
+            nl += 10;
+        }
+        return nl;
+    }
+
     static void gemm(cudaStream_t st, bool ta, bool tb, const GemmTask& t, int nz = 1) {
         const int tm = (t.M + GT - 1) / GT, tn = (t.N + GT - 1) / GT;
         if (tm * tn == 0) return;
@@ -1047,11 +1322,17 @@ struct EighWork {
             XTB_CUDA_CHECK(cudaMemcpyAsync(Qo, &one, sizeof(double), cudaMemcpyHostToDevice, st));
         } else {
             const int D = eigcore::tree_depth(n);
-            k_dc_leaves<<<((1 << D) + 127) / 128, 128, 0, st>>>(n, D, dd, ee, la, Qo);
+            {
+                DcArgs a;
+                std::memset(&a, 0, sizeof(a));
+                a.n = n; a.depth = D; a.d = dd; a.e = ee; a.lam = la; a.Qo = Qo;
+                k_dc_leaves<<<((1 << D) + 127) / 128, 128, 0, st>>>(a);
+            }
             ++nl;
             for (int depth = D - 1; depth >= 0; --depth) {
                 const int nodes = 1 << depth, mmax = (n + nodes - 1) / nodes;
                 DcArgs a;
+                a.d = dd; a.vs = 0; a.ms = 0; a.skip = nullptr;
                 a.n = n; a.depth = depth; a.e = ee; a.Qo = Qo; a.Qn = Qn; a.U = U; a.Qg = Qg; a.Ug = Ug; a.lam = la; a.lam2 = lb;
                 a.z = z; a.zhat = zhat; a.dk = dk; a.zk = zk; a.rc = rc; a.rs = rs; a.perm = perm; a.cols = cols; a.pos = pos;
                 a.tcnt = tcnt; a.ctype = ctype; a.ra = ra; a.rb = rb; a.kcnt = kcnt; a.nrot = nrot; a.fail = fail; a.tasks = tasks;
