@@ -309,6 +309,23 @@ def test_batched_householder_solver_agrees_with_block_jacobi(xb, kat):
     assert np.max(np.abs(out[0]["charges"] - out[1]["charges"])) < 1e-9
 
 
+def test_large_matrix_solver_with_degenerate_levels(xb, kat):
+    """Four Fe(CO)5 molecules far apart as ONE system (196 AOs, d shells): every level is (nearly) four-fold degenerate,
+    which is the regime where the divide and conquer deflates heavily and where the density must not depend on the
+    arbitrary basis inside a degenerate subspace.  Same energy, gradient, charges and iteration count as the oracle."""
+    from bench import make_peptide_cluster
+    Z, xyz = make_peptide_cluster(kat["feco5"], 4, gap=30.0)
+    s = dict(numbers=Z, xyz=xyz, charge=0.0, uhf=0)
+    o = _oracle(s)
+    b = xb.BatchCalculator([Z])
+    assert b.sizes(0)["nao"] > 168
+    r = b.singlepoint(xyz)
+    assert r["all_converged"]
+    _compare(xb, s, o, b, r, 0)
+    e1 = _oracle(kat["feco5"]).energies["e_total"]
+    assert abs(r["energies"][0] - 4 * e1) < 5e-3          # four weakly interacting copies (dispersion, electrostatics)
+
+
 def test_ragged_batch_of_large_molecules(xb, kat):
     """Batch whose matrices are beyond the shared-memory solvers: the Householder / divide-and-conquer solver is looped
     over the molecules on the host and skips those that already left the SCC loop (they converge at different
