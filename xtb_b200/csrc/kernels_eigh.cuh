@@ -524,14 +524,11 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
         const int j = j0 + jj, mm = m0 - jj - 1;
         double* ybuf = a.ybuf + (jj & 1) * ld;
         double* cbuf = a.cbuf + (jj & 1) * ld;
-        // ---- y = A v on the owned columns; Gram entries of the block reflector (v_k^T v_i, k < i in the same block)
+        // ---- y = A v on the owned columns (the Gram matrices of the block reflectors follow from one batched GEMM afterwards)
         const int s0 = (jj + 1 - cta + G - 1) / G;            // first owned slot with column > jj (cta + s G >= jj + 1)
         const int sfirst = cta >= jj + 1 ? 0 : s0;
         const int nact = nslot - sfirst;
-        const int blk0 = (j / NB) * NB;                       // first reflector of the current block reflector
-        const int kg = blk0 + cta;                            // Gram job of this CTA: previous reflector kg (if any)
-        const bool gram = kg < j;
-        const int njobcols = max(nact, 0) + (gram ? 1 : 0);
+        const int njobcols = max(nact, 0);
         int Q = 1;
         if (njobcols > 0) Q = max(1, min(8, min((nwarp + njobcols - 1) / njobcols, max(mm / 64, 1))));
         const int njobs = njobcols * Q;
@@ -539,16 +536,13 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
             const int lc = job / Q, q = job - lc * Q;
             const int tb = jj + 1 + (int)(((long long)mm * q) / Q), te = jj + 1 + (int)(((long long)mm * (q + 1)) / Q);
             double s = 0.0;
-            if (lc < nact) {
+            {
                 const double* col = cols + (size_t)(sfirst + lc) * m0;
                 double s1 = 0.0;
                 int r = tb + lane;
                 for (; r + 32 < te; r += 64) { s += col[r] * sv[r]; s1 += col[r + 32] * sv[r + 32]; }
                 if (r < te) s += col[r] * sv[r];
                 s += s1;
-            } else {
-                const double* col = a.A + j0 + ld * kg;       // reflector kg: stored entries from row kg + 2 <= jj + 1
-                for (int r = tb + lane; r < te; r += 32) s += __ldcg(col + r) * sv[r];
             }
             s = warp_sum(s);
             if (lane == 0) part[job] = s;
@@ -561,8 +555,7 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
         for (int lc = tid; lc < njobcols; lc += nthr) {
             double s = 0.0;
             for (int q = 0; q < Q; ++q) s += part[lc * Q + q];
-            if (lc < nact) ybuf[cta + (sfirst + lc) * G] = s;
-            else a.Gf[(size_t)(j / NB) * NB * NB + (kg - blk0) + NB * (j - blk0)] = s;
+            ybuf[cta + (sfirst + lc) * G] = s;
         }
         grid_barrier(a.bar, G, target);
         // ---- w = tau y - tau^2/2 (v^T y) v;  A -= v w^T + w v^T on the owned columns and on the published next column
@@ -608,6 +601,23 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
         }
         form_reflector(jj + 1, cn);
     }
+}
+
+// Gram matrices G_b = V_b^T V_b of the block reflectors whose columns were reduced by the resident kernel: explicit V of all
+// those blocks side by side (Vall: n x (n - jres), column jb + k - jres), then one task per block for k_eg_gemm<true,false>
+__global__ void k_gram_formv(const double* __restrict__ A, int n, int jres, double* __restrict__ Vall) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nc = n - 1 - jres;                              // reflectors jres .. n-2
+    if (t >= (long long)n * nc) return;
+    const int r = (int)(t % n), c = jres + (int)(t / n), piv = c + 1;
+    Vall[t] = r < piv ? 0.0 : (r == piv ? 1.0 : A[r + (long long)n * c]);
+}
+__global__ void k_gram_tasks(GemmTask* __restrict__ tasks, int n, int jres, double* Vall, double* Gf) {
+    const int b = jres / NB + blockIdx.x * blockDim.x + threadIdx.x, jb = b * NB;
+    if (jb >= n - 1) return;
+    const int kb = min(NB, n - 1 - jb), r0 = jb + 1;
+    double* V = Vall + (long long)n * (jb - jres) + r0;
+    tasks[b - jres / NB] = gemm_task_dev(V, n, V, n, Gf + (long long)b * NB * NB, NB, kb, kb, n - r0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1305,6 +1315,15 @@ struct EighWork {
                                                        sytrd_smem_resident_bytes(n - jres, grid), st));
             hook(0, 1, 1);
             ++nl;
+            const int nrb = (n - 1 - jres + NB - 1) / NB;    // block reflectors of the resident range
+            if (nrb > 0) {
+                hook(1, 0, 0);
+                k_gram_formv<<<(unsigned)(((size_t)n * (n - 1 - jres) + 255) / 256), 256, 0, st>>>(A, n, jres, Qg);
+                k_gram_tasks<<<(nrb + 63) / 64, 64, 0, st>>>(tasks, n, jres, Qg, Gf);
+                k_eg_gemm<true, false><<<dim3(4, nrb), 128, 0, st>>>(GemmTask(), tasks);
+                hook(1, 1, 3);
+                nl += 3;
+            }
         }
         if (timed) cudaEventRecord(ev[1], st);
         hook(2, 0, 0);
