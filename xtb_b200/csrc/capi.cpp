@@ -58,6 +58,9 @@ struct _xtb_TCalculator {
     // external point charges (src/type/pcem.f90): element numbers (-> hardness), charges, positions in bohr
     std::vector<int> pc_numbers;
     std::vector<double> pc_q, pc_xyz;
+    // ensemble of displaced copies of the molecule for xtb_hessian (created on first use, reused)
+    std::shared_ptr<Batch> hess_batch;
+    int hess_copies = 0;
 };
 struct _xtb_TResults {
     bool has_energy = false, has_gradient = false, has_wfn = false, has_dipole = false, has_pcgradient = false;
@@ -281,8 +284,103 @@ void xtb_setElectronicTemp(xtb_TEnvironment env, xtb_TCalculator calc, double te
     calc->etemp = temperature < 1.e-6 ? 1.e-6 : temperature;
 }
 void xtb_cpcmx_calc(xtb_TEnvironment env, xtb_TMolecule, xtb_TCalculator, xtb_TResults) { unsupported(env, "CPCM-X", "xtb_api_cpcmx_calc"); }
-void xtb_hessian(xtb_TEnvironment env, xtb_TMolecule, xtb_TCalculator, xtb_TResults, double*, int*, int*, double*, double*) {
-    unsupported(env, "Numerical Hessian", "xtb_api_hessian");
+// Numerical Hessian by central differences of analytical gradients (src/api/interface.f90:312-456 ->
+// TCalculator%hessian, src/type/calculator.f90:116-229).  The reference loops over 6 N displaced single points (OpenMP over
+// the points); here they are one conformer ensemble: every displaced geometry is a member of a batch, all of them start
+// from the wavefunction cached on the results handle (or from the EEQ guess when there is none, as newWavefunction does),
+// and the batch runs through the same kernels as xtbb200_singlepoint.  hessian: (3N x 3N) symmetrised as in
+// interface.f90:438-444; dipole_gradient (3, 3N) optional.  atom_index_list / step_size: NULL = all atoms / 0.005 bohr
+// (the reference's defaults); a non-NULL step_size is read as a double, which is what the reference's Fortran side does
+// with this argument (interface.f90:330).  Polarizabilities are not available for GFN2-xTB: a non-NULL
+// polarizability_gradient is an error.
+void xtb_hessian(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator calc, xtb_TResults res, double* hess, int* atom_list,
+                 int* step_size, double* dipgrad, double* polgrad) {
+    const char* source = "xtb_api_hessian";
+    if (!check_env(env)) return;
+    if (!mol) { env->error("Molecular structure data is not allocated", source); return; }
+    if (!calc) { env->error("Singlepoint calculator is not allocated", source); return; }
+    if (!calc->loaded || !calc->batch) { env->error("No calculator loaded for single point", source); return; }
+    if (!res) { env->error("Calculation results are not allocated", source); return; }
+    if (!hess) { env->error("Hessian array is not allocated", source); return; }
+    if (atom_list) { env->error("Atom index lists are not supported, pass NULL to displace all atoms", source); return; }
+    if (polgrad) { env->error("Polarizability gradients are not available for GFN2-xTB", source); return; }
+    if (calc->at != mol->at) { env->error("Calculator was loaded for a different molecule", source); return; }
+    try {
+        const int n = mol->n, n3 = 3 * n;
+        const double step = step_size ? *reinterpret_cast<const double*>(step_size) : 0.005;
+        if (!(step > 0.0)) { env->error("Step size for numerical differentiation must be positive", source); return; }
+        const int nao = calc->batch->nao(0), nsh = calc->batch->nshell(0);
+        const bool cached = res->has_wfn && res->n == n && res->nao == nao && res->nshell == nsh;   // interface.f90:369-388
+        // points per pass: bounded by a memory estimate of ~40 nao^2 doubles per member
+        const double per = 40.0 * 8.0 * (double)nao * nao + 1.0e6;
+        const int chunk = (int)std::max(1.0, std::min((double)(2 * n3), std::floor(6.0e9 / per)));
+        if (!calc->hess_batch || calc->hess_copies != chunk) {
+            std::vector<int> nat(chunk, n), num;
+            std::vector<double> chg(chunk, calc->chrg);
+            std::vector<int> uhf(chunk, calc->uhf);
+            num.reserve((size_t)chunk * n);
+            for (int c = 0; c < chunk; ++c) num.insert(num.end(), mol->at.begin(), mol->at.end());
+            calc->hess_batch.reset(new Batch(chunk, nat.data(), num.data(), chg.data(), uhf.data(), 0));
+            calc->hess_copies = chunk;
+        }
+        Batch& b = *calc->hess_batch;
+        b.set_options(calc->accuracy, calc->etemp, calc->maxiter);
+        b.set_guess(0);
+        const int npc = (int)calc->pc_q.size();
+        if (npc > 0) {
+            std::vector<int> cnt(chunk, npc), pnum;
+            std::vector<double> pq, px;
+            for (int c = 0; c < chunk; ++c) {
+                pnum.insert(pnum.end(), calc->pc_numbers.begin(), calc->pc_numbers.end());
+                pq.insert(pq.end(), calc->pc_q.begin(), calc->pc_q.end());
+                px.insert(px.end(), calc->pc_xyz.begin(), calc->pc_xyz.end());
+            }
+            b.set_external_charges(cnt.data(), pnum.data(), pq.data(), px.data());
+        } else if (b.external_charge_count() > 0) b.release_external_charges();
+        std::vector<double> H((size_t)n3 * n3, 0.0), dg((size_t)3 * n3, 0.0);
+        std::vector<double> pos((size_t)chunk * n3), grad((size_t)chunk * n3), qsh, dipm, qp;
+        if (cached) {
+            for (int c = 0; c < chunk; ++c) {
+                qsh.insert(qsh.end(), res->qsh.begin(), res->qsh.end());
+                dipm.insert(dipm.end(), res->dipm.begin(), res->dipm.end());
+                qp.insert(qp.end(), res->qp.begin(), res->qp.end());
+            }
+        }
+        const double step2 = 0.5 / step;
+        int nbad = 0;
+        // point index p = 2 * ii + (0: +step, 1: -step), ii = 3 * iat + ic
+        for (int p0 = 0; p0 < 2 * n3; p0 += chunk) {
+            const int np = std::min(chunk, 2 * n3 - p0);
+            for (int c = 0; c < chunk; ++c) {
+                const int p = std::min(p0 + c, 2 * n3 - 1);          // members beyond the last point repeat it
+                std::copy(mol->xyz.begin(), mol->xyz.end(), pos.begin() + (size_t)c * n3);
+                pos[(size_t)c * n3 + p / 2] += (p & 1) ? -step : step;
+            }
+            b.set_positions(pos.data());
+            if (cached) b.set_wavefunction(qsh.data(), dipm.data(), qp.data());
+            else b.invalidate_wavefunction();
+            b.singlepoint(true);
+            b.fetch("gradient", grad.data());
+            for (int c = 0; c < np; ++c) {
+                const int p = p0 + c, ii = p / 2;
+                const double sgn = (p & 1) ? -step2 : step2;
+                MolResult r = b.result(c);
+                if (r.fail || !r.converged) ++nbad;
+                for (int jj = 0; jj < n3; ++jj) H[jj + (size_t)n3 * ii] += sgn * grad[(size_t)c * n3 + jj];
+                for (int k = 0; k < 3; ++k) dg[k + (size_t)3 * ii] += sgn * r.dipole[k];
+            }
+        }
+        for (int i = 0; i < n3; ++i)                                 // interface.f90:438-444
+            for (int j = i + 1; j < n3; ++j) {
+                const double v = 0.5 * (H[i + (size_t)n3 * j] + H[j + (size_t)n3 * i]);
+                H[i + (size_t)n3 * j] = v; H[j + (size_t)n3 * i] = v;
+            }
+        std::copy(H.begin(), H.end(), hess);
+        if (dipgrad) std::copy(dg.begin(), dg.end(), dipgrad);
+        if (nbad) env->error("Self consistent charge iterator did not converge in " + std::to_string(nbad) + " displaced geometries", "scf");
+    } catch (const std::exception& e) {
+        env->error(std::string("Hessian calculation failed: ") + e.what(), source);
+    }
 }
 
 void xtb_singlepoint(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator calc, xtb_TResults res) {

@@ -346,6 +346,20 @@ class Calculator(Molecule):
         self.raise_on_error("Failed to release external charges")
         self._npc = 0
 
+    def hessian(self, res=None, step=None):
+        """Numerical Hessian (xtb_hessian): central differences of analytical gradients, the 6 N displaced geometries run
+        as one ensemble on the GPU.  Returns (hessian (3N, 3N), dipole gradient (3N, 3)).  `res`: results of a previous
+        single point whose wavefunction is the SCC start of every point (None: EEQ guess)."""
+        _res = Results(self) if res is None else res
+        n3 = 3 * len(self)
+        hess = np.zeros((n3, n3))
+        dipgrad = np.zeros((n3, 3))
+        st = ctypes.c_double(step) if step is not None else None
+        self._lib.xtb_hessian(self._env, self._mol, self._calc, _res._res, _dp(hess), None,
+                              ctypes.cast(ctypes.byref(st), _c_int_p) if st is not None else None, _dp(dipgrad), None)
+        self.raise_on_error("Hessian calculation failed")
+        return hess, dipgrad
+
     def singlepoint(self, res=None, copy=False):
         _res = Results(self) if res is None else (Results(res) if copy else res)
         self._lib.xtb_singlepoint(self._env, self._mol, self._calc, _res._res)
