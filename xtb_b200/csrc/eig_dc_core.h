@@ -80,10 +80,13 @@ EIG_HD int deflate_scan(int m, int n1, const int* perm, double* d, double* z, do
         if (rho * fabs(z[nj]) <= tol) { cols[m - 1 - ndf++] = nj; continue; }
         if (pj < 0) { pj = nj; continue; }
         double s = z[pj], c = z[nj];
-        const double tau = hypot(c, s), t = d[nj] - d[pj];
-        c /= tau;
-        s = -s / tau;
-        if (fabs(t * c * s) <= tol) {
+        const double t = d[nj] - d[pj];
+        // |t c s| / (c^2 + s^2) <= tol is the test of dlaed2 (there with c, s already divided by hypot(c, s)); in this
+        // form the square root and the divisions are only paid for the pairs that do deflate
+        if (fabs(t * c * s) <= tol * (c * c + s * s)) {
+            const double tau = hypot(c, s);
+            c /= tau;
+            s = -s / tau;
             z[nj] = tau;
             z[pj] = 0.0;
             ra[nrot] = pj; rb[nrot] = nj; rc[nrot] = c; rs[nrot] = s; ++nrot;
