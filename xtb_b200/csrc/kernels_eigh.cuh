@@ -4,13 +4,18 @@
 //   A = Q T Q^T      k_sytrd_panel (persistent cooperative kernel, one launch per panel of EB columns: column update,
 //                    reflector, w = tau (A v - V W^T v - W V^T v) with the trailing-matrix product as warp-per-column
 //                    dot products -- the HBM-bound part, 8 (n-j)^2 bytes per column) + rank-2*EB trailing update on the
-//                    FP64 tensor path (k_eg_gemm, DMMA m8n8k4)
+//                    FP64 tensor path (k_eg_gemm, DMMA m8n8k4); once the trailing matrix fits into the shared memory
+//                    of all SMs together (order <= ~1920) k_sytrd_smem finishes the reduction: columns resident in
+//                    shared memory, unblocked rank-2 updates, one grid barrier per column
 //   T = Qt L Qt^T    Cuppen divide and conquer down to 1x1 / 2x2 leaves, one batch of kernels per tree level:
 //                    rank sort, deflation scan, Givens rotations, secular equation (warp per root), Loewner update
 //                    vector, eigenvector update as two DMMA GEMMs per node (top / bottom rows, columns grouped by
 //                    kind as in LAPACK's dlaed2/3), batched over the level (scalar routines: eig_dc_core.h)
-//   Z = Q Qt         block reflectors I - V T V^T over two panels, the T factors assembled from the V^T v products
-//                    that the tridiagonalisation computes anyway; two DMMA GEMMs per block
+//   Z = Q Qt         block reflectors I - V T V^T over two panels; T factors from the Gram matrices V^T V (the V^T v
+//                    products of the panel kernel, one batched GEMM for the resident range); three DMMA GEMMs per block
+//
+// The same stages batched over an ensemble of small matrices of one order (k_sytrd_cta, blockIdx.z = matrix) are kept
+// as a cross-check of the block Jacobi solver (solver mode 4).
 //
 // Replaces dsyevd('V') inside TEigenSolver%fact_solve (src/mctc/lapack/eigensolve.F90:218-246) for large n; the
 // reduction to standard form (dsygst) and the back-substitution (dtrsm) are the X^T H X and X Z products of engine.cu.
