@@ -158,6 +158,7 @@ struct Batch::Impl {
     Dev d;
     EighWork eig;             // Householder + divide-and-conquer eigensolver for matrices beyond shared memory
     bool have_eig = false;
+    bool blocked_chol = false;     // S = L L^T, X = L^-T by the blocked DMMA kernels instead of one CTA per molecule
     bool cta_eig = false;          // batched Householder + divide and conquer for ensembles of one matrix order (solver mode 4)
     bool has_followers = false;    // some molecules share their composition with an earlier one (conformer ensemble)
     std::vector<long long> h_pc0;  // external point charges: per-molecule ranges (empty: none)
@@ -315,11 +316,15 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
             d.hjM = I.dalloc<double>((size_t)s.tot_hj); d.hjJ = I.dalloc<double>((size_t)s.tot_hj);
             d.hj_flag = I.dalloc<int>((size_t)(s.tot_hj / (128 * 128)));
             d.hj_count = I.dalloc<int>(nmol); d.hj_conv = I.dalloc<int>(nmol); d.hj_sigma = I.dalloc<double>(nmol);
-            d.chol_stride = (long long)((s.max_nao + CB - 1) / CB) * CB * CB;
-            d.cholD = I.dalloc<double>((size_t)nmol * d.chol_stride);
             I.eig.init(s.max_nao, device);
             I.have_eig = true;
             I.bytes += I.eig.bytes;
+        }
+        // blocked Cholesky (kernels_chol.cuh) from kBlockedCholMin AOs on, also when the eigensolver runs in shared memory
+        I.blocked_chol = (!I.fits_blk || !I.fits_scalar) || s.max_nao >= kBlockedCholMin;
+        if (I.blocked_chol) {
+            d.chol_stride = (long long)((s.max_nao + CB - 1) / CB) * CB * CB;
+            d.cholD = I.dalloc<double>((size_t)nmol * d.chol_stride);
         }
         I.h_done.assign(nmol, 0);
         {   // leaders of the groups of identical compositions (warm start of the first diagonalisation, k_lead_copy)
@@ -628,10 +633,10 @@ int Batch::singlepoint(bool restart) {
         KL(kid, k_hj_rank<<<grid2(s.max_nao, 128, nmol), 128, 0, st>>>(d));
         KL(kid, k_hj_write<<<grid2((long long)s.max_nao * s.max_nao, 256, nmol), 256, 0, st>>>(d, still ? 1 : 0));
     };
-    if (!hier) {
+    if (!hier && !(I.blocked_chol && !std::getenv("XTBB200_CTA_CHOL"))) {
         const size_t chol_bytes = (size_t)s.max_nao * (s.max_nao | 1) * sizeof(double);
         KL(K_CHOL, k_chol_inv<true><<<nmol, 512, chol_bytes, st>>>(d));
-    } else if (I.solver == 2) {                                   // cross-check path: X = V s^-1/2 from eig(S)
+    } else if (hier && I.solver == 2) {                           // cross-check path: X = V s^-1/2 from eig(S)
         hjacobi(d.S, 0, K_CHOL);                                  // S = V s V^T
         KL(K_CHOL, k_hj_xscale<<<grid2((long long)s.max_nao * s.max_nao, 256, nmol), 256, 0, st>>>(d));
     } else {                                                      // blocked Cholesky S = L L^T, X = L^-T (kernels_chol.cuh)

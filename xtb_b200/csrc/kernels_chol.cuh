@@ -21,6 +21,7 @@
 namespace xtbb200 {
 
 constexpr int CB = 64;   // panel width = gemm64_acc tile
+constexpr int kBlockedCholMin = 97;   // smaller matrices: one CTA per molecule in shared memory (k_chol_inv) is faster
 constexpr size_t kBcholDiagSmem = 2 * CB * (CB + 1) * sizeof(double);
 
 __device__ __forceinline__ void bchol_zero(double (&acc)[4][4][2]) {
