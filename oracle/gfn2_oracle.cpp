@@ -32,6 +32,7 @@
 #include "../xtb_b200/csrc/tables/slater_tables.h"
 #include "../xtb_b200/csrc/tables/eeq_tables.h"
 #include "../xtb_b200/csrc/tables/d4_tables.h"
+#include "../xtb_b200/csrc/tables/solv_tables.h"
 
 extern "C" {
 void scipy_dpotrf_(const char*, const int*, double*, const int*, int*);
@@ -459,6 +460,13 @@ struct Oracle {
     // external point charges (src/type/pcem.f90; set through xtb_setExternalCharges, src/api/calculator.f90:470-540):
     // positions [npc][3] in bohr, charges, hardness gam = chemical hardness of the element given for the charge
     dvec pc_xyz, pc_q, pc_gam;
+    // implicit solvation (xtb_setSolvent -> TSolvInput, src/solv/input.F90:30-66): solv_on, normalised solvent name,
+    // ALPB flag, kernel (1 Still, 2 P16), reference state (1 gsolv, 2 reference, 3 mol1bar), temperature, ion strength / radius
+    bool solv_on = false;
+    std::string solv_name;
+    bool solv_alpb = false;
+    int solv_kernel = 2, solv_state = 1;
+    double solv_temp = 298.15, solv_ionst = 0.0, solv_ionrad = 0.0;
 
     Basis bas;
     // results / intermediates, by name
@@ -986,6 +994,387 @@ void mmompop(const Oracle& o, const double* P, const double* S, const double* D,
 // ------------------------------------------------------------------------------------
 // the single point, src/scf_module.F90:74-920 (scf) + src/scc_core.f90:255-640 (scc)
 // ------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------
+// implicit solvation: GBSA / ALPB (src/solv/{model,gbsa,born,sasa,kernel,state}.f90)
+// ------------------------------------------------------------------------------------
+struct Solv {
+    int n = 0, kernel = 2;
+    bool lsalt = false, lhb = false;
+    double keps = 0, alpbet = 0, gshift = 0, born_scale = 1, eps = 1, kappa = 0, ion_rad = 0, lrcut = 0, srcut = 0;
+    dvec vdwr, rho, svdw, vdwsa, wrp, trj2, gamsasa, hbmag;
+    // geometry dependent
+    dvec brad, brdr /* [i][j][3]: d brad(i) / d R_j */, sasa, dsdrt /* [i][j][3]: d sasa(i) / d R_j */, dsdr, hbw, dhbdw;
+    dvec ionscr, discr, bornmat;
+    double gsasa = 0, adet = 0;
+};
+
+const double KCALTOAU = 1.0 / 627.50947428;   // src/mctc/convert.f90:31-32
+
+// initSolvModel + loadInternalParam + paramToModel + initBorn: src/solv/model.f90:185-207,250-474,498-528,
+// src/solv/gbsa.f90:197-388.  Returns false when the solvent has no internal GFN2 parameter set for the kernel.
+bool solv_init(const Oracle& o, Solv& sv) {
+    const SolvParamSet* ps = nullptr;
+    for (int i = 0; i < solv_nsets; ++i)
+        if (solv_param_sets[i].kernel == o.solv_kernel && o.solv_name == solv_param_sets[i].name) ps = &solv_param_sets[i];
+    if (!ps) return false;
+    const int n = o.nat;
+    sv.n = n; sv.kernel = o.solv_kernel;
+    const double molcm3toau = 8.92388e-2, surfaceTension = 1.0e-5;
+    const double eps = ps->epsv, density = ps->rhos / ps->smass * molcm3toau;
+    double gshift = ps->gshift * KCALTOAU;
+    const double born_offset = ps->soset * 0.1 * AATOAU, probe = ps->rprobe * AATOAU;
+    // getStateShift, src/solv/state.f90:55-85
+    const double ideal = 24.79, ambient = 298.15;
+    if (o.solv_state == 2)
+        gshift += o.solv_temp * KB * (std::log(ideal * o.solv_temp / ambient) + std::log(density / 1.0e-3 * 1.0 / ps->smass));
+    else if (o.solv_state == 3)
+        gshift += o.solv_temp * KB * std::log(ideal * o.solv_temp / ambient);
+    bool anyhb = false;
+    for (int k = 0; k < 94; ++k) anyhb = anyhb || std::fabs(ps->tmp[k]) > 1.e-3;
+    sv.gshift = gshift; sv.eps = eps; sv.born_scale = ps->c1;
+    sv.alpbet = o.solv_alpb ? 0.571412 / eps : 0.0;
+    sv.keps = (1.0 / eps - 1.0) / (1.0 + sv.alpbet);
+    sv.lsalt = o.solv_ionst > 0.0;
+    if (sv.lsalt) {
+        const double kappaConst = 0.7897e-3;
+        sv.ion_rad = o.solv_ionrad;
+        sv.kappa = 1.0 / (std::sqrt(eps * o.solv_temp * kappaConst / o.solv_ionst) * AATOAU);
+    }
+    sv.lrcut = 35.0 * AATOAU;
+    const double w = 0.3 * AATOAU, w3 = w * (w * w), ah3 = -1.0 / (4.0 * w3);
+    sv.vdwr.resize(n); sv.rho.resize(n); sv.svdw.resize(n); sv.vdwsa.resize(n); sv.wrp.resize(n); sv.trj2.resize(2 * n);
+    sv.gamsasa.resize(n); sv.hbmag.resize(n);
+    double maxsa = 0;
+    for (int i = 0; i < n; ++i) {
+        const int z = o.Z[i] - 1;
+        sv.vdwr[i] = AATOAU * solv_vdw_rad_d3_aa[z];
+        sv.rho[i] = sv.vdwr[i] * ps->sx[z];
+        sv.svdw[i] = sv.vdwr[i] - born_offset;
+        sv.vdwsa[i] = sv.vdwr[i] + probe;
+        maxsa = std::max(maxsa, sv.vdwsa[i]);
+        sv.trj2[2 * i] = (sv.vdwsa[i] - w) * (sv.vdwsa[i] - w);
+        sv.trj2[2 * i + 1] = (sv.vdwsa[i] + w) * (sv.vdwsa[i] + w);
+        const double v = sv.vdwsa[i];
+        double r = v + w;
+        double wr = (0.25 / w + 3.0 * ah3 * (0.2 * r * r - 0.5 * r * v + v * v / 3.0)) * r * r * r;
+        r = v - w;
+        wr -= (0.25 / w + 3.0 * ah3 * (0.2 * r * r - 0.5 * r * v + v * v / 3.0)) * r * r * r;
+        sv.wrp[i] = wr;
+        sv.gamsasa[i] = ps->gamscale[z] * (4.0 * PI) * surfaceTension;
+        sv.hbmag[i] = anyhb ? -(ps->tmp[z] * ps->tmp[z]) * KCALTOAU : 0.0;
+        sv.lhb = sv.lhb || sv.hbmag[i] < 0.0;
+    }
+    sv.srcut = 2.0 * (w + maxsa) + 2.0 * AATOAU;
+    return true;
+}
+
+// one descreening term psi_i <- j and its radial derivative factor (d psi / d r) / r: src/solv/born.f90:130-330
+inline bool born_psi_term(double r, double rho_j, double vdw_i, double& g, double& dg) {
+    const double r1 = 1.0 / r;
+    if (r >= vdw_i + rho_j) {   // no overlap
+        const double ap = r + rho_j, am = r - rho_j, ab = ap * am, rhab = rho_j / ab, lnab = 0.5 * std::log(am / ap) * r1;
+        g = rhab + lnab;
+        dg = -2.0 * rhab / ab + (rhab - lnab) * r1 * r1;
+        return true;
+    }
+    if (r + rho_j > vdw_i) {    // partial overlap
+        const double r12 = 0.5 * r1, r24 = r12 * r12, ap = r + rho_j, am = r - rho_j, rh1 = 1.0 / vdw_i, rhr1 = 1.0 / ap,
+                     aprh1 = ap * rh1, lnab = std::log(aprh1);
+        g = rh1 - rhr1 + r12 * (0.5 * am * (rhr1 - rh1 * aprh1) - lnab);
+        dg = rhr1 * rhr1 * (1.0 - 0.25 * am * r1 * (1.0 + aprh1 * aprh1)) + rho_j * r24 * (rhr1 - rh1 * aprh1) + r12 * (r1 * lnab - rhr1);
+        dg = dg * r1;
+        return true;
+    }
+    return false;               // sphere j inside the van der Waals sphere of i
+}
+
+// update: src/solv/gbsa.f90:391-432 (neighbour lists 826-1010 are implied by the cutoffs lrcut / srcut)
+void solv_update(const Oracle& o, Solv& sv) {
+    const int n = sv.n;
+    const size_t nn = (size_t)n * n;
+    // ---- compute_psi / compute_bornr (GBOBC II): src/solv/born.f90:36-84,87-345
+    // (the reference re-uses 1/r of the preceding pair when only the j <- i term of an i-overlaps-j pair exists,
+    //  born.f90:224-262; the restatement always takes 1/r of the pair itself)
+    sv.brad.assign(n, 0.0); sv.brdr.assign(3 * nn, 0.0);
+    const double lr2 = sv.lrcut * sv.lrcut;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j) {
+            double dr[3], r2 = 0;
+            for (int k = 0; k < 3; ++k) { dr[k] = R(o, i)[k] - R(o, j)[k]; r2 += dr[k] * dr[k]; }
+            if (!(r2 < lr2)) continue;
+            const double r = std::sqrt(r2);
+            double g, dg;
+            if (born_psi_term(r, sv.rho[j], sv.vdwr[i], g, dg)) {
+                sv.brad[i] += g;
+                for (int k = 0; k < 3; ++k) { sv.brdr[3 * ((size_t)i * n + i) + k] += dg * dr[k]; sv.brdr[3 * ((size_t)i * n + j) + k] -= dg * dr[k]; }
+            }
+            if (born_psi_term(r, sv.rho[i], sv.vdwr[j], g, dg)) {
+                sv.brad[j] += g;
+                for (int k = 0; k < 3; ++k) { sv.brdr[3 * ((size_t)j * n + j) + k] -= dg * dr[k]; sv.brdr[3 * ((size_t)j * n + i) + k] += dg * dr[k]; }
+            }
+        }
+    const double alp = 1.0, bet = 0.8, gam = 4.85;   // src/solv/born.f90:28-30
+    for (int i = 0; i < n; ++i) {
+        double br = sv.brad[i];
+        const double s1 = 1.0 / sv.svdw[i], v1 = 1.0 / sv.vdwr[i], s2 = 0.5 * sv.svdw[i];
+        br = br * s2;
+        double arg2 = br * (gam * br - bet);
+        const double arg = br * (alp + arg2);
+        arg2 = 2.0 * arg2 + alp + gam * br * br;
+        const double th = std::tanh(arg), ch = std::cosh(arg);
+        br = sv.born_scale / (s1 - v1 * th);
+        double dpsi = ch * (s1 - v1 * th);
+        dpsi = sv.born_scale * s2 * v1 * arg2 / (dpsi * dpsi);
+        sv.brad[i] = br;
+        for (size_t t = 3 * (size_t)i * n; t < 3 * (size_t)(i + 1) * n; ++t) sv.brdr[t] *= dpsi;
+    }
+    // ---- compute_numsa / compute_w_sp: src/solv/sasa.f90:41-125,128-204
+    const double w = 0.3 * AATOAU, w3 = w * (w * w), ah0 = 0.5, ah1 = 3.0 / (4.0 * w), ah3 = -1.0 / (4.0 * w3), tolsesp = 1.e-6;
+    sv.sasa.assign(n, 0.0); sv.dsdrt.assign(3 * nn, 0.0);
+    const double sr2 = sv.srcut * sv.srcut;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(o.nthreads)
+    for (int i = 0; i < n; ++i) {
+        ivec nb;
+        for (int j = 0; j < n; ++j) {
+            if (j == i) continue;
+            double r2 = 0;
+            for (int k = 0; k < 3; ++k) { const double t = R(o, i)[k] - R(o, j)[k]; r2 += t * t; }
+            if (r2 < sr2) nb.push_back(j);
+        }
+        dvec grds(3 * nb.size());
+        ivec grdi(nb.size());
+        double sasai = 0;
+        double* gi = &sv.dsdrt[3 * (size_t)i * n];
+        for (int ip = 0; ip < solv_nang; ++ip) {
+            double xyzp[3];
+            for (int k = 0; k < 3; ++k) xyzp[k] = R(o, i)[k] + sv.vdwsa[i] * solv_leb230[ip][k];
+            int nni = 0;
+            double sasap = 1.0;
+            for (size_t t = 0; t < nb.size(); ++t) {
+                const int ia = nb[t];
+                double tj[3], tj2 = 0;
+                for (int k = 0; k < 3; ++k) { tj[k] = xyzp[k] - R(o, ia)[k]; tj2 += tj[k] * tj[k]; }
+                if (tj2 < sv.trj2[2 * ia + 1]) {
+                    if (tj2 <= sv.trj2[2 * ia]) { sasap = 0.0; break; }
+                    const double sqtj = std::sqrt(tj2), uj = sqtj - sv.vdwsa[ia], ah3uj2 = ah3 * uj * uj;
+                    double dsasaij = ah1 + 3.0 * ah3uj2, sasaij = ah0 + (ah1 + ah3uj2) * uj;
+                    sasaij = std::max(0.0, std::min(sasaij, 1.0));
+                    if (sasaij < 2.2250738585072014e-308) { sasap = 0.0; break; }
+                    sasap *= sasaij;
+                    dsasaij = dsasaij / (sasaij * sqtj);
+                    grdi[nni] = ia;
+                    for (int k = 0; k < 3; ++k) grds[3 * nni + k] = dsasaij * tj[k];
+                    nni++;
+                }
+            }
+            if (sasap > tolsesp) {
+                const double wsa = solv_leb230[ip][3] * sv.wrp[i] * sasap;
+                sasai += wsa;
+                for (int jj = 0; jj < nni; ++jj)
+                    for (int k = 0; k < 3; ++k) {
+                        const double dd = wsa * grds[3 * jj + k];
+                        gi[3 * i + k] += dd;
+                        gi[3 * grdi[jj] + k] -= dd;
+                    }
+            }
+        }
+        sv.sasa[i] = sasai;
+    }
+    // dsdr = dsdrt . gamsasa, gsasa (gbsa.f90:419-420)
+    sv.dsdr.assign(3 * n, 0.0);
+    sv.gsasa = 0;
+    for (int i = 0; i < n; ++i) {
+        sv.gsasa += sv.sasa[i] * sv.gamsasa[i];
+        for (int j = 0; j < n; ++j) for (int k = 0; k < 3; ++k) sv.dsdr[3 * j + k] += sv.dsdrt[3 * ((size_t)i * n + j) + k] * sv.gamsasa[i];
+    }
+    // getDebyeHueckel, gbsa.f90:794-821
+    if (sv.lsalt) {
+        sv.ionscr.resize(n); sv.discr.resize(n);
+        const double aa = 0.5 / sv.eps;
+        for (int i = 0; i < n; ++i) {
+            const double gg = sv.kappa * (sv.brad[i] + sv.ion_rad);
+            sv.ionscr[i] = aa * std::exp(gg) / (1.0 + gg);
+            sv.discr[i] = sv.ionscr[i] * sv.kappa * gg / (1.0 + gg);
+        }
+    }
+    // compute_fhb, gbsa.f90:1013-1046
+    sv.hbw.assign(n, 0.0); sv.dhbdw.assign(n, 0.0);
+    if (sv.lhb)
+        for (int i = 0; i < n; ++i) {
+            const double smaxd = 1.0 / (sv.vdwsa[i] * sv.vdwsa[i]);
+            sv.hbw[i] = sv.hbmag[i] * sv.sasa[i] * smaxd;
+            sv.dhbdw[i] = sv.hbmag[i] * smaxd;
+        }
+}
+
+// inertia tensor of the van der Waals spheres and the shape descriptor of ALPB: getADet, gbsa.f90:643-687
+void solv_inertia(const Oracle& o, const Solv& sv, double center[3], double inertia[3][3], double& totRad3, double& adet) {
+    const double tof = 2.0 / 5.0;
+    totRad3 = 0;
+    for (int k = 0; k < 3; ++k) center[k] = 0;
+    for (int i = 0; i < sv.n; ++i) {
+        const double rad3 = sv.vdwr[i] * sv.vdwr[i] * sv.vdwr[i];
+        totRad3 += rad3;
+        for (int k = 0; k < 3; ++k) center[k] += R(o, i)[k] * rad3;
+    }
+    for (int k = 0; k < 3; ++k) center[k] /= totRad3;
+    for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) inertia[a][c] = 0;
+    for (int i = 0; i < sv.n; ++i) {
+        const double rad2 = sv.vdwr[i] * sv.vdwr[i], rad3 = rad2 * sv.vdwr[i];
+        double vec[3], r2 = 0;
+        for (int k = 0; k < 3; ++k) { vec[k] = R(o, i)[k] - center[k]; r2 += vec[k] * vec[k]; }
+        for (int a = 0; a < 3; ++a) {
+            inertia[a][a] += rad3 * (r2 + tof * rad2);
+            for (int c = 0; c < 3; ++c) inertia[a][c] -= rad3 * vec[a] * vec[c];
+        }
+    }
+    const double det = inertia[0][0] * (inertia[1][1] * inertia[2][2] - inertia[1][2] * inertia[2][1]) -
+                       inertia[0][1] * (inertia[1][0] * inertia[2][2] - inertia[1][2] * inertia[2][0]) +
+                       inertia[0][2] * (inertia[1][0] * inertia[2][1] - inertia[1][1] * inertia[2][0]);
+    adet = std::sqrt(std::pow(det, 1.0 / 3.0) / (tof * totRad3));
+}
+
+// addBornMatrix: gbsa.f90:435-479 with the kernels of src/solv/kernel.f90:620-760
+void solv_born_matrix(const Oracle& o, Solv& sv) {
+    const int n = sv.n;
+    sv.bornmat.assign((size_t)n * n, 0.0);
+    const double zetaP16o16 = 1.028 / 16.0;
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < i; ++j) {
+            double r2 = 0;
+            for (int k = 0; k < 3; ++k) { const double t = R(o, i)[k] - R(o, j)[k]; r2 += t * t; }
+            double v;
+            if (sv.kernel == 1) {
+                const double aa = sv.brad[i] * sv.brad[j], dd = 0.25 * r2 / aa, expd = std::exp(-dd), fgb2 = r2 + aa * expd;
+                if (sv.lsalt) {
+                    const double fgb = std::sqrt(fgb2), gg = sv.ionscr[i] + sv.ionscr[j];
+                    v = (std::exp(-sv.kappa * fgb) * gg - 1.0) / fgb;
+                } else v = sv.keps / std::sqrt(fgb2);
+            } else {
+                const double r1 = std::sqrt(r2), ab = std::sqrt(sv.brad[i] * sv.brad[j]);
+                double arg = ab / (ab + zetaP16o16 * r1);
+                arg = arg * arg; arg = arg * arg; arg = arg * arg; arg = arg * arg;
+                v = sv.keps / (r1 + ab * arg);
+            }
+            sv.bornmat[i + (size_t)n * j] += v; sv.bornmat[j + (size_t)n * i] += v;
+        }
+        if (sv.kernel == 1 && sv.lsalt) sv.bornmat[i + (size_t)n * i] += (std::exp(-sv.kappa * sv.brad[i]) * sv.ionscr[i] * 2.0 - 1.0) / sv.brad[i];
+        else sv.bornmat[i + (size_t)n * i] += sv.keps / sv.brad[i];
+        if (sv.lhb) sv.bornmat[i + (size_t)n * i] += 2.0 * sv.hbw[i];
+    }
+    if (sv.alpbet > 0.0) {
+        double c[3], in[3][3], tr;
+        solv_inertia(o, sv, c, in, tr, sv.adet);
+        for (auto& v : sv.bornmat) v += sv.keps * sv.alpbet / sv.adet;
+    }
+}
+
+// addGradient: gbsa.f90:573-640 (kernels: src/solv/kernel.f90:47-330; hydrogen bonds gbsa.f90:1049-1090; ALPB shape
+// term gbsa.f90:690-791).  Returns gborn (incl. the ALPB term) and ghb.
+void solv_gradient(const Oracle& o, const Solv& sv, const dvec& q, dvec& grad, double& gborn, double& ghb) {
+    const int n = sv.n;
+    dvec grddb(n, 0.0);
+    double egb = 0;
+    const double zetaP16 = 1.028, zetaP16o16 = zetaP16 / 16.0;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j) {
+            double dr[3], r2 = 0;
+            for (int k = 0; k < 3; ++k) { dr[k] = R(o, i)[k] - R(o, j)[k]; r2 += dr[k] * dr[k]; }
+            const double qq = q[i] * q[j];
+            if (sv.kernel == 1 && sv.lsalt) {
+                double aa = sv.brad[i] * sv.brad[j];
+                const double dd = 0.25 * r2 / aa, expd = std::exp(-dd), dfgb = r2 + aa * expd, fgb = std::sqrt(dfgb);
+                aa = sv.kappa * fgb;
+                const double expa = std::exp(-aa), gg = (sv.ionscr[i] + sv.ionscr[j]) * expa;
+                double qfg = qq / fgb;
+                egb += qfg * (gg - 1.0);
+                const double dfgb3 = qfg * (gg * (1.0 + aa) - 1.0) / dfgb, ap = (1.0 - 0.25 * expd) * dfgb3;
+                for (int k = 0; k < 3; ++k) { grad[3 * i + k] -= ap * dr[k]; grad[3 * j + k] += ap * dr[k]; }
+                qfg = qfg * expa;
+                const double bp = -0.5 * expd * (1.0 + dd) * dfgb3;
+                grddb[i] += sv.brad[j] * bp + qfg * sv.discr[i];
+                grddb[j] += sv.brad[i] * bp + qfg * sv.discr[j];
+            } else if (sv.kernel == 1) {
+                const double aa = sv.brad[i] * sv.brad[j], dd = 0.25 * r2 / aa, expd = std::exp(-dd), fgb2 = r2 + aa * expd,
+                             dfgb2 = 1.0 / fgb2, dfgb = std::sqrt(dfgb2), dfgb3 = dfgb2 * dfgb * sv.keps;
+                egb += qq * sv.keps * dfgb;
+                const double ap = (1.0 - 0.25 * expd) * dfgb3;
+                for (int k = 0; k < 3; ++k) { grad[3 * i + k] -= ap * dr[k] * qq; grad[3 * j + k] += ap * dr[k] * qq; }
+                const double bp = -0.5 * expd * (1.0 + dd) * dfgb3;
+                grddb[i] += sv.brad[j] * bp * qq;
+                grddb[j] += sv.brad[i] * bp * qq;
+            } else {
+                const double r1 = std::sqrt(r2), ab = std::sqrt(sv.brad[i] * sv.brad[j]), arg1 = ab / (ab + zetaP16o16 * r1);
+                double arg16 = arg1 * arg1;
+                arg16 = arg16 * arg16; arg16 = arg16 * arg16; arg16 = arg16 * arg16;
+                const double fgb = r1 + ab * arg16, dfgb = 1.0 / fgb, dfgb2 = dfgb * dfgb;
+                egb += qq * sv.keps * dfgb;
+                const double ap = (1.0 - zetaP16 * arg1 * arg16) * dfgb2;
+                for (int k = 0; k < 3; ++k) {
+                    const double dG = ap * dr[k] * sv.keps / r1 * qq;
+                    grad[3 * i + k] -= dG; grad[3 * j + k] += dG;
+                }
+                const double bp = -0.5 * (r1 * zetaP16 / ab * arg1 + 1.0) / ab * arg16 * dfgb2;
+                grddb[i] += sv.brad[j] * bp * sv.keps * qq;
+                grddb[j] += sv.brad[i] * bp * sv.keps * qq;
+            }
+        }
+    for (int i = 0; i < n; ++i) {   // self-energy part
+        if (sv.kernel == 1 && sv.lsalt) {
+            const double gg = std::exp(-sv.kappa * sv.brad[i]), aa = 2.0 * sv.ionscr[i] * gg - 1.0, qq = q[i] / sv.brad[i];
+            egb += 0.5 * qq * q[i] * aa;
+            const double ap = aa - sv.brad[i] * 2.0 * (sv.discr[i] + sv.ionscr[i] * sv.kappa) * gg;
+            grddb[i] += -0.5 * qq * qq * ap;
+        } else {
+            const double bp = 1.0 / sv.brad[i], qq = q[i] * bp;
+            egb += 0.5 * q[i] * qq * sv.keps;
+            grddb[i] += -0.5 * sv.keps * qq * bp * q[i];
+        }
+    }
+    // contract with the Born radii derivatives: gradient += brdr . grddb
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+            for (int k = 0; k < 3; ++k) grad[3 * j + k] += sv.brdr[3 * ((size_t)i * n + j) + k] * grddb[i];
+    gborn = egb;
+    for (int k = 0; k < 3 * n; ++k) grad[k] += sv.dsdr[k];
+    ghb = 0;
+    if (sv.lhb) {
+        for (int i = 0; i < n; ++i) ghb += sv.hbw[i] * q[i] * q[i];
+        for (int i = 0; i < n; ++i) {
+            if (sv.dhbdw[i] == 0.0) continue;
+            const double dhbed = sv.dhbdw[i] * q[i] * q[i];
+            for (int j = 0; j < n; ++j) for (int k = 0; k < 3; ++k) grad[3 * j + k] += sv.dsdrt[3 * ((size_t)i * n + j) + k] * dhbed;
+        }
+    }
+    if (sv.alpbet > 0.0) {
+        double qtot = 0;
+        for (int i = 0; i < n; ++i) qtot += q[i];
+        gborn += qtot * qtot * sv.alpbet / sv.adet * sv.keps;
+        // addADetDeriv, gbsa.f90:690-791
+        double c[3], in[3][3], tr, adet;
+        solv_inertia(o, sv, c, in, tr, adet);
+        const double kE = sv.keps * sv.alpbet;
+        const double f = (250.0 / (48.0 * tr * tr * tr * std::pow(adet, 5))) * (-0.5 * kE * qtot * qtot / (adet * adet));
+        double ad[3][3];
+        ad[0][0] = in[0][0] * (in[1][1] + in[2][2]) - in[0][1] * in[0][1] - in[0][2] * in[0][2];
+        ad[0][1] = ad[1][0] = in[0][1] * in[2][2] - in[0][2] * in[1][2];
+        ad[0][2] = ad[2][0] = in[0][2] * in[1][1] - in[0][1] * in[2][1];
+        ad[1][1] = in[1][1] * (in[0][0] + in[2][2]) - in[0][1] * in[0][1] - in[1][2] * in[1][2];
+        ad[1][2] = ad[2][1] = in[0][0] * in[1][2] - in[0][1] * in[0][2];
+        ad[2][2] = in[2][2] * (in[0][0] + in[1][1]) - in[0][2] * in[0][2] - in[1][2] * in[1][2];
+        for (int i = 0; i < n; ++i) {
+            const double rad3 = sv.vdwr[i] * sv.vdwr[i] * sv.vdwr[i];
+            double vec[3];
+            for (int k = 0; k < 3; ++k) vec[k] = R(o, i)[k] - c[k];
+            for (int a = 0; a < 3; ++a) {
+                double s = 0;
+                for (int k = 0; k < 3; ++k) s += ad[a][k] * f * vec[k];
+                grad[3 * i + a] += rad3 * s;
+            }
+        }
+    }
+}
+
 int singlepoint(Oracle& o) {
     const int n = o.nat;
     build_basis(n, o.Z.data(), o.bas);
@@ -1334,6 +1723,14 @@ int singlepoint(Oracle& o) {
         }
         Vpc[s] = eh1;
     }
+    // implicit solvation: solvation%update, scf_module.F90:299-320 (GFN2: cm5a = 0, the model sees the Mulliken charges)
+    Solv sv;
+    double gsolv_scc = 0.0;
+    if (o.solv_on) {
+        if (!solv_init(o, sv)) return 7;
+        solv_update(o, sv);
+        solv_born_matrix(o, sv);
+    }
     for (iter = 1; iter <= o.maxiter; ++iter) {
         // potentials: thirdorder.f90:100-131, coulomb.f90:89-114
         for (int i = 0; i < n; ++i) atomicShift[i] = 0.0;
@@ -1341,6 +1738,13 @@ int singlepoint(Oracle& o) {
         for (int s = 0; s < nsh; ++s) shellShift[s] = Vpc[s] + qsh[s] * qsh[s] * gam3[s];
         scipy_dsymv_("L", &nsh, &one, jmat.data(), &nsh, qsh.data(), &ione, &one, shellShift.data(), &ione);
         setvsdq(o, true, q, dipm, qp, gab3, gab5, vs, vd, vq);
+        // solvation%addShift, scc_core.f90:444-448 -> gbsa.f90:482-507: atomicShift += bornMat q
+        if (o.solv_on)
+            for (int i = 0; i < n; ++i) {
+                double t = 0;
+                for (int j = 0; j < n; ++j) t += sv.bornmat[i + (size_t)n * j] * q[j];
+                atomicShift[i] += t;
+            }
         // disppot, dftd4.F90:735-818
         for (int i = 0; i < n; ++i) {
             int ati = o.Z[i] - 1;
@@ -1478,6 +1882,17 @@ int singlepoint(Oracle& o) {
             epcem = 0.0;
             for (int s = 0; s < nsh; ++s) epcem += qsh[s] * Vpc[s];
             eel += epcem;
+        }
+        // solvation%getEnergy, scc_core.f90:543-548 -> gbsa.f90:510-535 (output charges of this iteration)
+        if (o.solv_on) {
+            double e = 0;
+            for (int i = 0; i < n; ++i) {
+                double t = 0;
+                for (int j = 0; j < n; ++j) t += 0.5 * sv.bornmat[i + (size_t)n * j] * q[j];
+                e += q[i] * t;
+            }
+            gsolv_scc = e + sv.gsasa + sv.gshift;
+            eel += gsolv_scc;
         }
         eel = eel + ga + gb;
 
@@ -1865,6 +2280,20 @@ int singlepoint(Oracle& o) {
         cn_chain(covpairs, dEdcn, grad);
     }
     D["grad_d4"] = grad;
+    if (o.solv_on) {
+        // solvation%addGradient + getEnergyParts with the mixed charges wfn%q, scf_module.F90:759-777
+        double gborn = 0, ghb = 0;
+        solv_gradient(o, sv, q, grad, gborn, ghb);
+        // getEnergyParts, gbsa.f90:538-570: gborn = 1/2 q B q - ghb
+        double e = 0;
+        for (int i = 0; i < n; ++i) {
+            double t = 0;
+            for (int j = 0; j < n; ++j) t += 0.5 * sv.bornmat[i + (size_t)n * j] * q[j];
+            e += q[i] * t;
+        }
+        D["solvation"] = dvec{(e - ghb) + sv.gsasa + ghb + sv.gshift, e - ghb, sv.gsasa, ghb, sv.gshift, gsolv_scc, gborn, sv.adet};
+        D["brad"] = sv.brad; D["sasa"] = sv.sasa; D["bornmat"] = sv.bornmat; D["dsdr"] = sv.dsdr;
+    }
     if (npc > 0) {
         // pcem_grad_gfn2, src/embedding.f90:329-365 (scf_module.F90:790-798): wfn%qsh = the mixed shell charges
         dvec gpc(3 * npc, 0.0);
@@ -2013,6 +2442,23 @@ void orc_set_pcem(void* h, int npc, const int* numbers, const double* q, const d
     for (int i = 0; i < npc; ++i) o->pc_gam[i] = gfn2_chemical_hardness[numbers[i] - 1];
 }
 void orc_set_xyz(void* h, const double* xyz) { Oracle* o = (Oracle*)h; o->xyz.assign(xyz, xyz + 3 * o->nat); }
+// implicit solvation (xtb_setSolvent, src/api/calculator.f90:341-445): solvent name as given by the caller (normalised
+// here as normalizeSolventName does, src/solv/model.f90:211-246), alpb 0/1, kernel 1 Still / 2 P16; name == NULL releases
+void orc_set_solvent(void* h, const char* name, int alpb, int kernel, int state, double temperature, double ion_strength,
+                     double ion_rad) {
+    Oracle* o = (Oracle*)h;
+    if (!name) { o->solv_on = false; return; }
+    std::string s(name);
+    for (auto& c : s) c = (char)std::tolower((unsigned char)c);
+    static const char* alias[][2] = {{"methylcyanide", "acetonitrile"}, {"methylenechloride", "ch2cl2"}, {"dichloromethane", "ch2cl2"},
+        {"dcm", "ch2cl2"}, {"chloroform", "chcl3"}, {"trichloromethane", "chcl3"}, {"tcm", "chcl3"}, {"carbondisulfide", "cs2"},
+        {"diethylether", "ether"}, {"dimethylformamide", "dmf"}, {"dimethylsulfoxide", "dmso"}, {"furan", "furane"},
+        {"nhexan", "hexane"}, {"n-hexan", "hexane"}, {"nhexane", "hexane"}, {"n-hexane", "hexane"}, {"tetrahydrofuran", "thf"},
+        {"h2o", "water"}};
+    for (auto& a : alias) if (s == a[0]) s = a[1];
+    o->solv_on = true; o->solv_name = s; o->solv_alpb = alpb != 0; o->solv_kernel = kernel; o->solv_state = state;
+    o->solv_temp = temperature; o->solv_ionst = ion_strength; o->solv_ionrad = ion_rad;
+}
 void orc_set_restart(void* h, const double* qsh, int nsh, const double* dipm, const double* qp) {
     Oracle* o = (Oracle*)h;
     o->d["restart_qsh"].assign(qsh, qsh + nsh);

@@ -31,6 +31,8 @@ def lib():
         L.orc_set_guess.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.orc_set_xyz.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.orc_set_pcem.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_set_solvent.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_double, ctypes.c_double, ctypes.c_double]
         L.orc_set_restart.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_singlepoint.argtypes = [ctypes.c_void_p]
         L.orc_len64.restype = ctypes.c_long
@@ -79,6 +81,21 @@ class Oracle:
         charges = np.ascontiguousarray(charges, dtype=np.float64)
         positions = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
         lib().orc_set_pcem(self.h, len(numbers), numbers.ctypes.data, charges.ctypes.data, positions.ctypes.data)
+
+    def set_solvent(self, solvent, model="gbsa", kernel=None, state=1, temperature=298.15, ion_strength=0.0, ion_rad=0.0):
+        """xtb_setSolvent: model "gbsa" (Still kernel) or "alpb" (P16 kernel) as the C API chooses them
+        (src/api/calculator.f90:411-419); kernel "still"/"p16" overrides (the reference's unit tests combine
+        alpb=True with the Still kernel); solvent None releases the model."""
+        if solvent is None:
+            lib().orc_set_solvent(self.h, None, 0, 0, 1, 298.15, 0.0, 0.0)
+            return
+        alpb = 1 if model == "alpb" else 0
+        if kernel is None:
+            kernel = "still" if model == "gbsa" else "p16"
+        lib().orc_set_solvent(self.h, solvent.encode(), alpb, {"still": 1, "p16": 2}[kernel], int(state), float(temperature),
+                              float(ion_strength), float(ion_rad))
+
+    SOLVATION = ["g_solv", "g_born", "g_sasa", "g_hb", "g_shift", "g_scc", "g_born_grad", "adet"]
 
     def set_restart(self, qsh, dipm, qp):
         qsh = np.ascontiguousarray(qsh, dtype=np.float64)

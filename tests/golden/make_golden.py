@@ -6,7 +6,8 @@ Run in the build container only (needs /root/reference):
     python tests/golden/make_golden.py
 
 Sources: test/unit/molstock.f90 (geometries), test/unit/test_gfn2.f90:48-235,667-742,831-901,
-987-1091, test/api/c_api_example.c:30-112,298-419, test/unit/test_coulomb.f90:828-1079,
+987-1091 and (implicit solvation) 237-385,745-828,
+862-900, test/api/c_api_example.c:30-163,298-419, test/unit/test_coulomb.f90:828-1079,
 test/unit/test_repulsion.f90, test/unit/test_eeq.f90.
 """
 import json
@@ -102,6 +103,54 @@ out["h2o2_pcem_api"] = dict(
     kat=dict(energy=-10.160927754235, g_4_0=-2.0326750053811E-03, g_1_1=3.3125460324302E-03, g_3_0=-1.1929405354823E-03,
              g_5_2=-1.6607683158587E-03, pcg_4_0=-0.000248319582, pcg_1_1=0.001420844475, pcg_3_0=0.003746685275,
              pcg_5_2=0.000651613444, tol_energy=1e-9, tol_grad=1e-8, source="test/api/c_api_example.c:298-419"))
+# ---- implicit solvation (GBSA / ALPB), SURVEY 8f row f2
+# C API sequence on the allene molecule above: gas phase, then GBSA(h2o), then ALPB(h2o), each restarted from the
+# previous wavefunction (test/api/c_api_example.c:114-163)
+out["c3h4_api"]["kat_solv"] = dict(
+    gbsa=dict(solvent="h2o", energy=-8.38393864716134, q5=0.06090868805034, dipole2=-0.35455233974705, wbo9=2.89453979224265),
+    alpb=dict(solvent="h2o", energy=-8.384076843892, q5=0.0644849340, dipole2=-0.3641866008, wbo9=2.8932146955),
+    tol_energy=1e-9, tol_q=1e-8, tol_dipole=1e-6, tol_wbo=1e-8, source="test/api/c_api_example.c:114-163")
+out["gbsa_h2o_api"] = dict(
+    numbers=[7, 1, 1, 1, 15, 6, 6, 6, 7, 7, 7],
+    xyz=[4.84112686339230, -1.15671648374837, 0.00000000000000, 5.87217277985151, -0.70323701391366, 1.54511189584035,
+         5.87217277985151, -0.70323701391366, -1.54511189584035, 4.61871932563459, -3.05696083228965, 0.00000000000000,
+         0.23751589819013, 1.28722286021158, 0.00000000000000, 0.00161949529588, -0.89075264835377, 2.57562301980395,
+         -3.06580664031769, 2.16487781673832, 0.00000000000000, 0.00161949529588, -0.89075264835377, -2.57562301980395,
+         -5.06585309511506, 3.00827014874972, 0.00000000000000, 0.00161949529588, -2.15043086045241, 4.34183098346579,
+         0.00161949529588, -2.15043086045241, -4.34183098346579],
+    charge=0.0, uhf=0, maxiter=30, solvent="h2o", model="gbsa", kernel="still",
+    kat=dict(hl_gap=3.408607724814, energy=-22.002501380096, gnorm=0.19366866479022E-01, g_0_0=.9038674439127e-02,
+             g_1_2=-.1394693523214e-02, g_7_0=0.17878350605942E-02, tol=5e-7, tol_gap=1e-5,
+             source="test/unit/test_gfn2.f90:237-311"))
+out["gbsa_salt_api"] = dict(
+    numbers=[7, 7, 9, 1, 1, 1, 1, 1],
+    xyz=[0.00000000000000, 1.30633555031959, 0.00000000000000, -1.26402080275201, -4.06871453465823, 0.00000000000000,
+         1.42937939828404, 3.57212474255400, 0.00000000000000, -2.92500314615638, -3.12058224200551, 0.00000000000000,
+         0.71133449039308, 0.35812010971703, 1.51289962417918, -1.25697212427635, -5.20406577474818, -1.53711646457211,
+         0.71133449039308, 0.35812010971703, -1.51289962417918, -1.25697212427635, -5.20406577474818, 1.53711646457211],
+    charge=0.0, uhf=0, maxiter=30, solvent="ch2cl2", model="gbsa", kernel="still", ion_strength=1.0e-3,
+    ion_rad_angstrom=1.0,
+    kat=dict(hl_gap=6.895830675032, energy=-13.027106170796, gnorm=0.014655633557, g_0_0=-0.6696141112967e-02,
+             g_3_1=-0.7608884457863e-03, g_4_0=0.2359793849677e-02, g_6_2=0.6882248903260e-02, tol=5e-7, tol_gap=5e-5,
+             source="test/unit/test_gfn2.f90:313-385"))
+# ten "mindless" molecules in ten solvents, GBSA parameter sets with the Still kernel, ALPB switched on for every second
+# molecule (test/unit/test_gfn2.f90:745-828)
+ms_solv = ["h2o", "chcl3", "thf", "acetonitrile", "toluene", "ch2cl2", "ether", "methanol", "cs2", "dmso"]
+ms_e = [-30.384994095620, -24.092790321708, -23.760000587724, -22.759033676135, -27.755756860587, -18.578906535415,
+        -33.448544467530, -29.993777657049, -20.567481283491, -25.665458003353]
+ms_g = [0.064382736361151, 0.055824257363022, 0.040696787567357, 0.073197307180171, 0.049852029310233,
+        0.053051084845551, 0.046463198340453, 0.057936724779824, 0.055081716352177, 0.045339090185313]
+ms_h = [2.5109978045214, 1.3559515037838, 0.1719065524538, 1.2428812469179, 2.1428443722148, 2.2548300583012,
+        2.6935601499212, 0.83100059690964, 3.3270919380043, 0.3859217429034]
+for i in range(10):
+    out["mindless%02d" % (i + 1)]["kat_solv"] = dict(
+        solvent=ms_solv[i], model="alpb" if (i + 1) % 2 == 0 else "gbsa", kernel="still", energy=ms_e[i], gnorm=ms_g[i],
+        hl_gap=ms_h[i], tol=1e-8, source="test/unit/test_gfn2.f90:745-828")
+# Fe(CO)5 in CH2Cl2: GBSA and ALPB, both with the Still kernel (test/unit/test_gfn2.f90:831-901)
+out["feco5"]["kat_solv"] = dict(
+    solvent="ch2cl2", kernel="still", tol=1e-8, source="test/unit/test_gfn2.f90:862-900",
+    gbsa=dict(energy=-34.078580189077, gnorm=0.26591831790033, hl_gap=2.9163891345974),
+    alpb=dict(energy=-34.078529449408, gnorm=0.26613440125774, hl_gap=2.9168589130125))
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_kat.json"), "w") as f:
     json.dump(out, f, indent=1)
 print("wrote", len(out), "systems")

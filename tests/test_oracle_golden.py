@@ -156,3 +156,101 @@ def test_external_point_charges_gradient_is_consistent(kat):
             e.append(run(x, p).energies["e_total"])
         fd = (e[0] - e[1]) / (2 * h)
         assert abs(fd - (g if which == "atom" else pg)[i, c]) < 2e-7
+
+
+# ---- implicit solvation (GBSA / ALPB), SURVEY 8f row f2 ----
+
+AATOAU = 1.0 / 0.52917726
+
+
+def test_c3h4_api_gbsa_alpb(kat):
+    # test/api/c_api_example.c:114-163: gas phase, GBSA(h2o), ALPB(h2o), each restarted from the previous results
+    s = kat["c3h4_api"]
+    ks = s["kat_solv"]
+    o = _run(s)
+    for model in ("gbsa", "alpb"):
+        k = ks[model]
+        o.set_restart(o.get("qsh"), o.get("dipm"), o.get("qp"))
+        o.set_solvent(k["solvent"], model)
+        assert o.singlepoint() == 0
+        assert abs(o.energies["e_total"] - k["energy"]) < ks["tol_energy"]
+        assert abs(o.get("q")[5] - k["q5"]) < ks["tol_q"]
+        assert abs(o.get("dipole")[2] - k["dipole2"]) < ks["tol_dipole"]
+        assert abs(o.get("wbo")[9] - k["wbo9"]) < ks["tol_wbo"]
+    # releasing the solvent gives the gas phase again
+    o.set_solvent(None)
+    o.set_restart(o.get("qsh"), o.get("dipm"), o.get("qp"))
+    assert o.singlepoint() == 0
+    assert abs(o.energies["e_total"] - s["kat"]["energy"]) < 1e-8
+
+
+@pytest.mark.parametrize("name", ["gbsa_h2o_api", "gbsa_salt_api"])
+def test_gbsa_energy_and_gradient(kat, name):
+    # test/unit/test_gfn2.f90:237-311 (GBSA water) and 313-385 (GBSA CH2Cl2 with salt screening)
+    s = kat[name]
+    k = s["kat"]
+    o = Oracle(s["numbers"], s["xyz"], maxiter=s["maxiter"])
+    o.set_solvent(s["solvent"], s["model"], s["kernel"], ion_strength=s.get("ion_strength", 0.0),
+                  ion_rad=s.get("ion_rad_angstrom", 0.0) * AATOAU)
+    assert o.singlepoint() == 0
+    e = o.energies
+    g = o.get("gradient").reshape(-1, 3)
+    assert abs(e["e_total"] - k["energy"]) < k["tol"]
+    assert abs(e["gnorm"] - k["gnorm"]) < k["tol"]
+    assert abs(e["hl_gap"] - k["hl_gap"]) < k["tol_gap"]
+    for key, val in k.items():
+        if key.startswith("g_"):
+            _, i, c = key.split("_")
+            assert abs(g[int(i), int(c)] - val) < k["tol"]
+    if name == "gbsa_h2o_api":
+        assert abs(g[10, 2] + g[9, 2]) < k["tol"]   # gradient(3,11) = -gradient(3,10)
+
+
+@pytest.mark.parametrize("i", range(1, 11))
+def test_mindless_solvation(kat, i):
+    # test/unit/test_gfn2.f90:745-828: ten molecules, ten solvents, GBSA / ALPB alternating, Still kernel
+    s = kat["mindless%02d" % i]
+    k = s["kat_solv"]
+    o = Oracle(s["numbers"], s["xyz"], charge=s["charge"], uhf=s["uhf"])
+    o.set_solvent(k["solvent"], k["model"], k["kernel"])
+    assert o.singlepoint() == 0
+    e = o.energies
+    assert abs(e["e_total"] - k["energy"]) < k["tol"]
+    assert abs(e["gnorm"] - k["gnorm"]) < k["tol"]
+    assert abs(e["hl_gap"] - k["hl_gap"]) < k["tol"]
+
+
+@pytest.mark.parametrize("model", ["gbsa", "alpb"])
+def test_feco5_solvation(kat, model):
+    # test/unit/test_gfn2.f90:862-900
+    s = kat["feco5"]
+    k = s["kat_solv"]
+    o = Oracle(s["numbers"], s["xyz"])
+    o.set_solvent(k["solvent"], model, k["kernel"])
+    assert o.singlepoint() == 0
+    e = o.energies
+    assert abs(e["e_total"] - k[model]["energy"]) < k["tol"]
+    assert abs(e["gnorm"] - k[model]["gnorm"]) < k["tol"]
+    assert abs(e["hl_gap"] - k[model]["hl_gap"]) < k["tol"]
+
+
+def test_alpb_p16_gradient_is_consistent(kat):
+    # ALPB with the P16 kernel (what xtb_setSolvent(..., "alpb") selects): analytic gradient against central differences
+    s = kat["gbsa_h2o_api"]
+    x0 = np.array(s["xyz"]).reshape(-1, 3)
+
+    def run(xyz):
+        o = Oracle(s["numbers"], xyz, acc=0.01)
+        o.set_solvent("water", "alpb")
+        assert o.singlepoint() == 0
+        return o
+
+    g = run(x0).get("gradient").reshape(-1, 3)
+    h = 1e-4
+    for i, c in [(0, 0), (4, 1), (9, 2)]:
+        e = []
+        for sgn in (+1, -1):
+            x = x0.copy()
+            x[i, c] += sgn * h
+            e.append(run(x).energies["e_total"])
+        assert abs((e[0] - e[1]) / (2 * h) - g[i, c]) < 3e-7
