@@ -46,6 +46,16 @@ int xtbb200_setWavefunction(xtbb200_TBatch batch, const double* qsh, const doubl
 int xtbb200_setExternalCharges(xtbb200_TBatch batch, const int* npc, const int* numbers, const double* charges,
                                const double* positions);
 
+/* Implicit solvation for every molecule of the batch (batched form of xtb_setSolvent / xtb_releaseSolvent,
+ * reference: src/api/calculator.f90:341-476 -> src/solv/model.f90, gbsa.f90).  solvent: name as xtb accepts it ("h2o",
+ * "water", "ch2cl2", "dmso" ...), NULL releases the model.  alpb: 0 = GBSA, 1 = ALPB.  kernel: 1 = Still (GBSA parameter
+ * sets; what xtb_setSolvent(..., "gbsa") selects), 2 = P16 (ALPB parameter sets; xtb_setSolvent(..., "alpb")).
+ * state: 1 gsolv, 2 reference, 3 mol1bar.  temperature in K (298.15).  ion_strength > 0 switches Debye-Hueckel salt
+ * screening on (Still kernel), ion_rad in bohr.  Energy parts of the last single point: xtbb200_getArray("solvation") =
+ * g_solv, g_born, g_sasa, g_hb, g_shift per molecule; Born radii "brad", atomic surfaces "sasa". */
+int xtbb200_setSolvent(xtbb200_TBatch batch, const char* solvent, int alpb, int kernel, int state, double temperature,
+                       double ion_strength, double ion_rad);
+
 /* eigensolver selection: 0 = automatic (block Jacobi on the FP64 tensor path when the matrix fits in shared memory,
  * Householder tridiagonalisation + divide and conquer + back-transformation beyond), 1 = scalar one-sided Jacobi,
  * 2 = (matrices beyond shared memory) overlap orthogonaliser X = V s^-1/2 from the eigen-decomposition of S instead of

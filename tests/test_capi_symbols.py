@@ -118,3 +118,20 @@ def test_external_charges_error_convention(lib):
     lib.xtb_delResults(ctypes.byref(res))
     lib.xtb_delCalculator(ctypes.byref(calc))
     lib.xtb_delEnvironment(ctypes.byref(env))
+
+
+def test_solvent_calls_without_calculator(lib):
+    """src/api/calculator.f90:341-476: xtb_setSolvent on an unloaded calculator is an environment error; xtb_releaseSolvent
+    on a calculator without a solvation model is not."""
+    vp = ctypes.c_void_p
+    lib.xtb_setSolvent.argtypes = [vp, vp, ctypes.c_char_p, vp, vp, vp, ctypes.c_char_p]
+    env, calc = vp(lib.xtb_newEnvironment()), vp(lib.xtb_newCalculator())
+    lib.xtb_setSolvent(env, calc, b"h2o", None, None, None, None)
+    assert lib.xtb_checkEnvironment(env) == 1
+    buf, ln = ctypes.create_string_buffer(512), ctypes.c_int(512)
+    lib.xtb_getError(env, buf, ctypes.byref(ln))
+    assert b"No calculator loaded to add solvation model" in buf.value
+    lib.xtb_releaseSolvent(env, calc)
+    assert lib.xtb_checkEnvironment(env) == 0
+    lib.xtb_delCalculator(ctypes.byref(calc))
+    lib.xtb_delEnvironment(ctypes.byref(env))

@@ -1,0 +1,178 @@
+"""GPU parity of the implicit solvation models GBSA / ALPB (xtb_setSolvent / xtb_releaseSolvent;
+src/solv/{model,gbsa,born,sasa,kernel}.f90) through the C ABI: against the reference's own golden values
+(test/api/c_api_example.c:114-163; test/unit/test_gfn2.f90:237-385,745-828,862-900, tolerances as stated there) and
+against the CPU oracle (energy 1e-7 Eh, gradient 1e-6 Eh/bohr, charges 1e-6 e, identical iteration counts)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+AATOAU = 1.0 / 0.52917726
+
+
+@pytest.fixture(scope="module")
+def xb():
+    import xtb_b200
+    if xtb_b200.device_count() < 1:
+        pytest.fail("no CUDA device: the engine has no CPU fallback")
+    return xtb_b200
+
+
+def test_c_api_example_gbsa_alpb(xb, kat):
+    """testFirst() of the reference's C API example: gas phase, GBSA(h2o), ALPB(h2o) on one calculator / results pair."""
+    s = kat["c3h4_api"]
+    ks = s["kat_solv"]
+    calc = xb.Calculator(xb.Param.GFN2xTB, s["numbers"], s["xyz"])
+    calc.set_verbosity(0)
+    calc.set_max_iterations(30)
+    res = calc.singlepoint()
+    assert abs(res.get_energy() - s["kat"]["energy"]) < 1e-9
+    for model in ("gbsa", "alpb"):
+        k = ks[model]
+        if model == "alpb":
+            calc.set_solvent(None)
+        calc.set_solvent(k["solvent"], model=None if model == "gbsa" else model)   # NULL model = "gbsa"
+        res = calc.singlepoint(res)
+        assert abs(res.get_energy() - k["energy"]) < ks["tol_energy"], model
+        assert abs(res.get_charges()[5] - k["q5"]) < ks["tol_q"], model
+        assert abs(res.get_dipole()[2] - k["dipole2"]) < ks["tol_dipole"], model
+        assert abs(res.get_bond_orders().ravel()[9] - k["wbo9"]) < ks["tol_wbo"], model
+    # release: gas phase again
+    calc.set_solvent(None)
+    res = calc.singlepoint(res)
+    assert abs(res.get_energy() - s["kat"]["energy"]) < 1e-8
+    # errors of xtb_setSolvent are environment errors, not crashes
+    with pytest.raises(xb.XTBException):
+        calc.set_solvent("unobtainium")
+    with pytest.raises(xb.XTBException):
+        calc.set_solvent("h2o", model="pcm")
+    with pytest.raises(xb.XTBException):
+        calc.set_solvent("h2o", model="cosmo")
+    with pytest.raises(xb.XTBException):
+        calc.set_solvent("h2o", grid=110)
+
+
+def _run_batch(xb, mols, **solv):
+    b = xb.BatchCalculator([m["numbers"] for m in mols], charges=[m["charge"] for m in mols], uhf=[m["uhf"] for m in mols],
+                           maxiter=solv.pop("maxiter", 250))
+    b.set_solvent(**solv)
+    r = b.singlepoint(np.concatenate([m["xyz"] for m in mols]))
+    return b, r
+
+
+@pytest.mark.parametrize("name", ["gbsa_h2o_api", "gbsa_salt_api"])
+def test_gbsa_reference_values(xb, kat, name):
+    """GBSA water and GBSA CH2Cl2 with salt screening: energy, gradient norm and components of the reference's tests."""
+    s = kat[name]
+    k = s["kat"]
+    b, r = _run_batch(xb, [s], solvent=s["solvent"], model=s["model"], kernel=s["kernel"], maxiter=s["maxiter"],
+                      ion_strength=s.get("ion_strength", 0.0), ion_rad=s.get("ion_rad_angstrom", 0.0) * AATOAU)
+    assert r["all_converged"]
+    g = r["gradients"]
+    assert abs(r["energies"][0] - k["energy"]) < k["tol"]
+    assert abs(np.linalg.norm(g) - k["gnorm"]) < k["tol"]
+    assert abs(b.result(0)["hl_gap"] - k["hl_gap"]) < k["tol_gap"]
+    for key, val in k.items():
+        if key.startswith("g_"):
+            _, i, c = key.split("_")
+            assert abs(g[int(i), int(c)] - val) < k["tol"], key
+
+
+def test_mindless_solvation_batches(xb, kat):
+    """The ten mindless molecules in ten solvents (test_gfn2.f90:745-828); one batch per solvent model, compared with the
+    reference values (1e-8) and with the oracle, including Born radii, surfaces and the energy parts."""
+    from oracle.oracle import Oracle
+    for i in range(1, 11):
+        s = kat["mindless%02d" % i]
+        k = s["kat_solv"]
+        b, r = _run_batch(xb, [s], solvent=k["solvent"], model=k["model"], kernel=k["kernel"])
+        assert r["all_converged"]
+        res = b.result(0)
+        assert abs(r["energies"][0] - k["energy"]) < 1e-7, i
+        assert abs(np.linalg.norm(r["gradients"]) - k["gnorm"]) < 1e-7, i
+        assert abs(res["hl_gap"] - k["hl_gap"]) < 1e-6, i
+        o = Oracle(s["numbers"], s["xyz"], charge=s["charge"], uhf=s["uhf"])
+        o.set_solvent(k["solvent"], k["model"], k["kernel"])
+        assert o.singlepoint() == 0
+        assert abs(r["energies"][0] - o.energies["e_total"]) < 1e-7
+        assert np.max(np.abs(r["gradients"] - o.get("gradient").reshape(-1, 3))) < 1e-6
+        assert np.max(np.abs(r["charges"] - o.get("q"))) < 1e-6
+        assert int(res["niter"]) == o.info["niter"]
+        assert np.max(np.abs(b.array("brad") - o.get("brad"))) < 1e-10
+        assert np.max(np.abs(b.array("sasa") - o.get("sasa"))) < 1e-9
+        n = len(s["numbers"])
+        assert np.max(np.abs(b.array("bornmat").reshape(n, n) - o.get("bornmat").reshape(n, n))) < 1e-11
+        assert np.max(np.abs(b.array("solvation") - o.get("solvation")[:5])) < 1e-8
+
+
+def test_ragged_ensemble_alpb_p16(xb, kat):
+    """Ragged batch with the model xtb_setSolvent(..., "alpb") selects (P16 kernel, ALPB parameter sets) against the oracle;
+    conformers of one molecule share the batch with other molecules."""
+    from oracle.oracle import Oracle
+    rng = np.random.default_rng(5)
+    riv = kat["rivaroxaban"]
+    mols = [kat["caffeine"], riv, dict(riv, xyz=riv["xyz"] + rng.normal(0.0, 0.05, riv["xyz"].shape)), kat["gbsa_h2o_api"],
+            kat["feco5"]]
+    b, r = _run_batch(xb, mols, solvent="water", model="alpb")
+    assert r["all_converged"]
+    solv = b.array("solvation").reshape(-1, 5)
+    off = 0
+    for i, m in enumerate(mols):
+        o = Oracle(m["numbers"], m["xyz"], charge=m["charge"], uhf=m["uhf"])
+        o.set_solvent("water", "alpb")
+        assert o.singlepoint() == 0
+        n = len(m["numbers"])
+        assert abs(r["energies"][i] - o.energies["e_total"]) < 1e-7, i
+        assert np.max(np.abs(r["gradients"][off:off + n] - o.get("gradient").reshape(-1, 3))) < 1e-6, i
+        assert np.max(np.abs(r["charges"][off:off + n] - o.get("q"))) < 1e-6, i
+        assert int(b.result(i)["niter"]) == o.info["niter"], i
+        assert np.max(np.abs(solv[i] - o.get("solvation")[:5])) < 1e-8, i
+        off += n
+    # release: gas phase energies again
+    b.set_solvent(None)
+    r2 = b.singlepoint(np.concatenate([m["xyz"] for m in mols]))
+    o = Oracle(mols[0]["numbers"], mols[0]["xyz"])
+    assert o.singlepoint() == 0
+    assert abs(r2["energies"][0] - o.energies["e_total"]) < 1e-7
+
+
+def test_solvation_gradient_is_derivative_of_energy(xb, kat):
+    """Size-independent property: the analytic gradient with GBSA(dmso) + Still kernel and with ALPB(water) + P16 equals
+    central differences of the energy; all displaced geometries run as one ensemble."""
+    s = kat["caffeine"]
+    x0 = s["xyz"]
+    h = 1e-3
+    picks = [(0, 0), (5, 1), (13, 2), (23, 0)]
+    for solv in (dict(solvent="dmso", model="gbsa"), dict(solvent="water", model="alpb")):
+        geos = [x0]
+        for (i, c) in picks:
+            for sg in (+1, -1):
+                x = x0.copy(); x[i, c] += sg * h
+                geos.append(x)
+        b = xb.BatchCalculator([s["numbers"]] * len(geos), accuracy=0.01)
+        b.set_solvent(**solv)
+        r = b.singlepoint(np.concatenate(geos))
+        assert r["all_converged"]
+        g = r["gradients"][:len(x0)]
+        for k, (i, c) in enumerate(picks):
+            fd = (r["energies"][1 + 2 * k] - r["energies"][2 + 2 * k]) / (2 * h)
+            assert abs(fd - g[i, c]) < 2e-6, (solv, i, c)
+
+
+def test_large_system_solvation(xb, kat):
+    """3 x taxol far apart (339 atoms, 897 AOs: large-matrix eigensolver path): ALPB(water) against the oracle."""
+    from oracle.oracle import Oracle
+    t = kat["taxol"]
+    n = len(t["numbers"])
+    numbers = np.concatenate([t["numbers"]] * 3)
+    xyz = np.concatenate([t["xyz"] + np.array([60.0 * k, 0.0, 0.0]) for k in range(3)])
+    b = xb.BatchCalculator([numbers])
+    b.set_solvent("water", model="alpb")
+    r = b.singlepoint(xyz)
+    assert r["all_converged"]
+    o = Oracle(numbers, xyz, threads=8)
+    o.set_solvent("water", "alpb")
+    assert o.singlepoint() == 0
+    assert abs(r["energies"][0] - o.energies["e_total"]) < 3e-7
+    assert np.max(np.abs(r["gradients"] - o.get("gradient").reshape(-1, 3))) < 1e-6
+    assert np.max(np.abs(b.array("sasa") - o.get("sasa"))) < 1e-8

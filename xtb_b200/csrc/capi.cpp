@@ -58,6 +58,11 @@ struct _xtb_TCalculator {
     // external point charges (src/type/pcem.f90): element numbers (-> hardness), charges, positions in bohr
     std::vector<int> pc_numbers;
     std::vector<double> pc_q, pc_xyz;
+    // implicit solvation (xtb_setSolvent): applied to the engine at once, kept here for the Hessian ensemble
+    bool solv_on = false, solv_alpb = false;
+    std::string solv_name;
+    int solv_kernel = 2, solv_state = 1;
+    double solv_temp = 298.15;
     // ensemble of displaced copies of the molecule for xtb_hessian (created on first use, reused)
     std::shared_ptr<Batch> hess_batch;
     int hess_copies = 0;
@@ -235,10 +240,41 @@ void xtb_loadGFN2xTB(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator ca
 void xtb_loadGFN0xTB(xtb_TEnvironment env, xtb_TMolecule, xtb_TCalculator, char*) { unsupported(env, "GFN0-xTB", "xtb_api_loadGFN0xTB"); }
 void xtb_loadGFN1xTB(xtb_TEnvironment env, xtb_TMolecule, xtb_TCalculator, char*) { unsupported(env, "GFN1-xTB", "xtb_api_loadGFN1xTB"); }
 void xtb_loadGFNFF(xtb_TEnvironment env, xtb_TMolecule, xtb_TCalculator, char*) { unsupported(env, "GFN-FF", "xtb_api_loadGFNFF"); }
-void xtb_setSolvent(xtb_TEnvironment env, xtb_TCalculator, char*, int*, double*, int*, char*) { unsupported(env, "Implicit solvation", "xtb_api_setSolvent"); }
+// src/api/calculator.f90:341-445: solvent name, optional reference state (1 gsolv, 2 reference [X=1], 3 mol1bar),
+// temperature [K], angular grid size (only the default 230 point Lebedev grid is built in), model "gbsa" (default; Still
+// kernel, GBSA parameter sets) or "alpb" (P16 kernel, ALPB parameter sets).  COSMO, TM-COSMO and CPCM-X are refused.
+void xtb_setSolvent(xtb_TEnvironment env, xtb_TCalculator calc, char* solvent, int* state, double* temperature, int* grid, char* model) {
+    const char* source = "xtb_api_setSolvent";
+    if (!check_env(env)) return;
+    if (!calc) { env->error("Singlepoint calculator is not allocated", source); return; }
+    if (!calc->loaded || !calc->batch) { env->error("No calculator loaded to add solvation model", source); return; }
+    if (!solvent) { env->error("Solvent name is not given", source); return; }
+    const int st = state ? *state : 1;
+    const double temp = temperature ? *temperature : 298.15;
+    const int nang = grid ? *grid : 230;
+    const std::string mdl = model ? std::string(model) : std::string("gbsa");
+    bool alpb = false;
+    int kernel = 2;
+    if (mdl == "gbsa") kernel = 1;
+    else if (mdl == "alpb") alpb = true;
+    else if (mdl == "cosmo" || mdl == "tmcosmo" || mdl == "cpcmx") { unsupported(env, "The COSMO family of solvation models", source); return; }
+    else { env->error("Unknown solvation model", source); return; }
+    if (nang != 230) { env->error("Only the 230 point angular grid is available for the surface integration", source); return; }
+    try {
+        calc->batch->set_solvent(solvent, alpb, kernel, st, temp, 0.0, 0.0);
+        calc->solv_on = true; calc->solv_alpb = alpb; calc->solv_name = solvent; calc->solv_kernel = kernel; calc->solv_state = st;
+        calc->solv_temp = temp;
+    } catch (const std::exception& e) {
+        env->error(e.what(), "solv_model_loadInternalParam");
+        env->error(std::string("Could not add solvation model for '") + solvent + "'", source);
+    }
+}
+// src/api/calculator.f90:449-476: no error on calculators without a solvation model
 void xtb_releaseSolvent(xtb_TEnvironment env, xtb_TCalculator calc) {
     if (!check_env(env)) return;
-    if (!calc) env->error("Calculator object is not allocated", "xtb_api_releaseSolvent");
+    if (!calc) { env->error("Singlepoint calculator is not allocated", "xtb_api_setRelease"); return; }
+    calc->solv_on = false;
+    if (calc->batch) calc->batch->release_solvent();
 }
 // src/api/calculator.f90:470-540
 void xtb_setExternalCharges(xtb_TEnvironment env, xtb_TCalculator calc, int* n, int* numbers, double* charges, double* positions) {
@@ -326,6 +362,8 @@ void xtb_hessian(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator calc, 
         Batch& b = *calc->hess_batch;
         b.set_options(calc->accuracy, calc->etemp, calc->maxiter);
         b.set_guess(0);
+        if (calc->solv_on) b.set_solvent(calc->solv_name.c_str(), calc->solv_alpb, calc->solv_kernel, calc->solv_state, calc->solv_temp, 0.0, 0.0);
+        else if (b.has_solvent()) b.release_solvent();
         const int npc = (int)calc->pc_q.size();
         if (npc > 0) {
             std::vector<int> cnt(chunk, npc), pnum;
@@ -570,6 +608,15 @@ int xtbb200_setExternalCharges(xtbb200_TBatch batch, const int* npc, const int* 
     XTBB_TRY
     if (!batch) throw std::runtime_error("batch is not allocated");
     batch->b->set_external_charges(npc, numbers, charges, positions);
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_setSolvent(xtbb200_TBatch batch, const char* solvent, int alpb, int kernel, int state, double temperature,
+                       double ion_strength, double ion_rad) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    if (!solvent) { batch->b->release_solvent(); return 0; }
+    batch->b->set_solvent(solvent, alpb != 0, kernel, state, temperature, ion_strength, ion_rad);
     return 0;
     XTBB_CATCH(-1)
 }

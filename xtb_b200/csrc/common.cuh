@@ -95,6 +95,14 @@ struct Dev {
     // (their number of 64-blocks times 64 x 64 can exceed nao^2 for small members of a batch, so they have their own buffer)
     double* cholD;
     long long chol_stride;
+    // implicit solvation, GBSA / ALPB (kernels_solv.cuh; xtb_setSolvent): solv_on == 0: none.  One model per batch.
+    int solv_on, solv_kernel /* 1 Still, 2 P16 */, solv_salt, solv_hb;
+    double solv_keps, solv_alpbet, solv_gshift, solv_c1, solv_eps, solv_kappa, solv_ionrad;
+    const double* sv_par;   // [8] per atom: vdwr, rho, svdw, vdwsa, wrp, gamsasa, hbmag, vdwr^3
+    double *sv_brad, *sv_dbr, *sv_sasa, *sv_ion /* [2]: ionscr, discr */, *sv_grddb, *sv_bq, *sv_shift;
+    double *sv_bmat;        // Born interaction matrix, nat^2 per molecule (offsets nn0)
+    double *sv_dsdrt;       // d sasa_i / d R_j, [i][j][3], 3 nat^2 per molecule
+    double *sv_mol;         // [24] per molecule: surface energy, shape descriptor, inertia tensor, energy parts
     // shell-pair gradient partials
     double *gpair;   // [npair][4] : gx,gy,gz,dCN
     const long long* pair0;

@@ -22,6 +22,8 @@
 #include "kernels_eigh.cuh"
 #include "kernels_linalg.cuh"
 #include "kernels_scc.cuh"
+#include "kernels_solv.cuh"
+#include "solvation.h"
 
 namespace xtbb200 {
 
@@ -56,14 +58,15 @@ __global__ void k_eigh_finish(Dev d, const int* fail, int fail_stride) {
 // kernel classes for the per-kernel device timers (bench.py roofline, profiles/)
 enum KernelId { K_SETUP = 0, K_EEQ, K_SDQH0, K_DQMASK, K_CHOL, K_POT, K_D4SCC, K_FOCK, K_GEMM_XHX, K_JACOBI, K_GEMM_C,
                 K_FERMI, K_DENSITY, K_POP, K_ENERGY, K_SCCFIN, K_GRAD_H0, K_GRAD_AES, K_GRAD_D4, K_GRAD_ATM, K_GRAD_MISC,
-                K_WBO, K_FINISH, K_COMM, K_EIG_PANEL, K_EIG_TRAIL, K_EIG_DC, K_EIG_BT, K_COUNT };
+                K_WBO, K_FINISH, K_COMM, K_EIG_PANEL, K_EIG_TRAIL, K_EIG_DC, K_EIG_BT, K_SOLV_SETUP, K_SOLV_SCC, K_SOLV_GRAD, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {
     "setup(cn,gab,jmat,dispmat,rep)", "eeq_guess", "k_sdqh0", "k_dqmask", "k_chol_inv", "potentials(shell,aes)",
     "d4_scc(zeta,matvec,shift)", "k_fock", "k_gemm(X^T H X)", "k_jacobi",   /* = the eigensolver class, whichever kernel family runs */ "k_gemm(C=XZ)", "k_fermi",
     "density(scale+k_gemm)", "populations(k_pop_rows,k_pop_atoms)", "energies(es,aes)", "k_scc_finish(broyden)",
     "k_grad_h0(+W build,collect)", "k_grad_aes", "grad_d4(weights,c6,pairs)", "k_grad_atm", "k_grad_cn", "wbo(PS gemm,k_wbo)",
     "k_finish", "nccl_allreduce(S,D,Q,H0 | dE/dCN | gradient)", "eig:k_sytrd_panel", "eig:trailing update(k_eg_gemm)",
-    "eig:divide and conquer", "eig:back-transformation"};
+    "eig:divide and conquer", "eig:back-transformation", "solv:setup(born,sasa,shape,bornmat)", "solv:scc(k_solv_matvec)",
+    "solv:gradient(pairs,energy,chain)"};
 
 // NCCL is needed only when one large system is split over GPUs; it is resolved at run time so that the
 // single-GPU library has no link dependency on it.  Inside a PyTorch process the already loaded torch-bundled
@@ -166,6 +169,9 @@ struct Batch::Impl {
     long long pc_cap = 0;          // capacity (charges) of the device buffers below
     long long* pc0_dev = nullptr;
     double* pc_buf = nullptr;      // [gam | q | xyz(3) | grad(3)] x pc_cap
+    SolvModel solv;           // implicit solvation model (solv.on == false: none)
+    double* sv_par_dev = nullptr;
+    bool leb_uploaded = false;
     std::vector<int> h_done;  // per-molecule "left the SCC loop" flags, mirrored for the per-molecule solver loop
     std::vector<void*> allocs;
     std::vector<long long> eeq0, pair0;
@@ -474,6 +480,40 @@ void Batch::set_external_charges(const int* npc, const int* numbers, const doubl
     XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
     I.d.pc0 = I.pc0_dev; I.d.pc_gam = gam_d; I.d.pc_q = q_d; I.d.pc_xyz = xyz_d; I.d.pc_grad = grd_d;
 }
+void Batch::set_solvent(const char* solvent, bool alpb, int kernel, int state, double temperature, double ion_strength,
+                        double ion_rad) {
+    Impl& I = *p_;
+    Dev& d = I.d;
+    if (kernel != 1 && kernel != 2) throw std::runtime_error("solvation: kernel must be 1 (Still) or 2 (P16)");
+    SolvModel sm = make_solv_model(solvent, alpb, kernel, state, temperature, ion_strength, ion_rad);   // throws: unknown solvent
+    XTB_CUDA_CHECK(cudaSetDevice(I.device));
+    XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+    const size_t na = I.sys.atoms.size(), tn = (size_t)I.sys.tot_nn;
+    std::vector<double> par(8 * na);
+    bool hb = false;
+    for (size_t i = 0; i < na; ++i) { solv_atom_par(sm, I.sys.atoms[i].Z, &par[8 * i]); hb = hb || par[8 * i + 6] < 0.0; }
+    if (!I.sv_par_dev) {
+        I.sv_par_dev = I.dalloc<double>(8 * na);
+        d.sv_brad = I.dalloc<double>(na); d.sv_dbr = I.dalloc<double>(na); d.sv_sasa = I.dalloc<double>(na);
+        d.sv_ion = I.dalloc<double>(2 * na); d.sv_grddb = I.dalloc<double>(na); d.sv_bq = I.dalloc<double>(na);
+        d.sv_shift = I.dalloc<double>(na);
+        d.sv_bmat = I.dalloc<double>(tn); d.sv_dsdrt = I.dalloc<double>(3 * tn);
+        d.sv_mol = I.dalloc<double>((size_t)SVM_STRIDE * d.nmol);
+    }
+    if (!I.leb_uploaded) {
+        XTB_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_leb230, solv_leb230, sizeof(double) * kSolvNang * 4, 0, cudaMemcpyHostToDevice, I.stream));
+        I.leb_uploaded = true;
+    }
+    XTB_CUDA_CHECK(cudaMemcpyAsync(I.sv_par_dev, par.data(), par.size() * sizeof(double), cudaMemcpyHostToDevice, I.stream));
+    XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+    d.sv_par = I.sv_par_dev;
+    d.solv_on = 1; d.solv_kernel = kernel; d.solv_salt = sm.salt ? 1 : 0; d.solv_hb = hb ? 1 : 0;
+    d.solv_keps = sm.keps; d.solv_alpbet = sm.alpbet; d.solv_gshift = sm.gshift; d.solv_c1 = sm.c1; d.solv_eps = sm.eps;
+    d.solv_kappa = sm.kappa; d.solv_ionrad = sm.ion_rad;
+    I.solv = sm;
+}
+void Batch::release_solvent() { p_->d.solv_on = 0; p_->solv.on = false; }
+bool Batch::has_solvent() const { return p_->d.solv_on != 0; }
 void Batch::release_external_charges() { set_external_charges(nullptr, nullptr, nullptr, nullptr); }
 long long Batch::external_charge_count() const { return p_->h_pc0.empty() ? 0 : p_->h_pc0.back(); }
 
@@ -539,6 +579,13 @@ int Batch::singlepoint(bool restart) {
     KL(K_SETUP, k_dispmat<<<grid2((long long)s.max_ndim * s.max_ndim, 256, nmol), 256, 0, st>>>(d));
     KL(K_SETUP, k_repulsion<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
     if (d.pc0) KL(K_SETUP, k_pcem_pot<<<grid2(s.max_nsh, B, nmol), B, 0, st>>>(d));
+    if (d.solv_on) {   // solvation%update, src/scf_module.F90:299-320 (every rank of a split system computes all of it)
+        XTB_CUDA_CHECK(cudaMemsetAsync(d.sv_dsdrt, 0, 3 * (size_t)s.tot_nn * sizeof(double), st));
+        KL(K_SOLV_SETUP, k_solv_born<<<dim3(s.max_nat, nmol), 128, 0, st>>>(d));
+        KL(K_SOLV_SETUP, k_solv_sasa<<<dim3(s.max_nat, nmol), 256, 0, st>>>(d));
+        KL(K_SOLV_SETUP, k_solv_shape<<<nmol, 256, 0, st>>>(d));
+        KL(K_SOLV_SETUP, k_solv_bornmat<<<grid2((long long)s.max_nat * s.max_nat, 256, nmol), 256, 0, st>>>(d));
+    }
     // ---- guess (src/api/interface.f90:82-101: reuse the cached wavefunction when present)
     if (!(restart && I.have_wfn)) {
         if (I.guess == 0) {
@@ -671,6 +718,7 @@ int Batch::singlepoint(bool restart) {
         KL(K_POT, k_pot_aes<true><<<grid2(8LL * s.max_nat, 256, nmol), 256, 0, st>>>(d));
         KL(K_D4SCC, k_d4_zeta<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d, 0));
         KL(K_D4SCC, k_d4_matvec<<<grid2(8LL * s.max_ndim, 256, nmol), 256, 0, st>>>(d));
+        if (d.solv_on) KL(K_SOLV_SCC, k_solv_matvec<<<dim3((s.max_nat + 31) / 32, nmol), 256, 0, st>>>(d, 0));
         KL(K_D4SCC, k_d4_shift<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
         KL(K_FOCK, k_fock<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
         KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.H, d.X, d.T, xtri ? 2 : 0, 1));   // T = H X
@@ -718,6 +766,7 @@ int Batch::singlepoint(bool restart) {
         KL(K_ENERGY, k_aes_rows<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
         KL(K_D4SCC, k_d4_zeta<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d, 1));
         KL(K_D4SCC, k_d4_matvec<<<grid2(8LL * s.max_ndim, 256, nmol), 256, 0, st>>>(d));
+        if (d.solv_on) KL(K_SOLV_SCC, k_solv_matvec<<<dim3((s.max_nat + 31) / 32, nmol), 256, 0, st>>>(d, 1));
         KL(K_SCCFIN, k_scc_finish<<<nmol, 256, 0, st>>>(d));
         XTB_CUDA_CHECK(cudaMemsetAsync(I.d_active, 0, sizeof(int), st));
         KL(K_SCCFIN, k_count_active<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.d_active));
@@ -744,6 +793,12 @@ int Batch::singlepoint(bool restart) {
     KL(K_GRAD_D4, k_d4_c6<<<grid2((long long)s.max_nat * s.max_nat, 128, nmol), 128, 0, st>>>(d));
     KL(K_GRAD_D4, k_grad_pairs<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
     KL(K_GRAD_ATM, k_grad_atm<<<dim3(s.max_nat, nmol), 128, (size_t)s.max_nat * sizeof(double), st>>>(d));
+    if (d.solv_on) {   // solvation%addGradient + getEnergyParts with the mixed charges, src/scf_module.F90:759-777
+        KL(K_SOLV_GRAD, k_solv_matvec<<<dim3((s.max_nat + 31) / 32, nmol), 256, 0, st>>>(d, -1));
+        KL(K_SOLV_GRAD, k_solv_energy<<<nmol, 256, 0, st>>>(d));
+        KL(K_SOLV_GRAD, k_solv_grad_pairs<<<dim3(s.max_nat, nmol), 64, 0, st>>>(d));
+        KL(K_SOLV_GRAD, k_solv_grad_chain<<<dim3(s.max_nat, nmol), 64, 0, st>>>(d));
+    }
     if (d.pc0) {
         KL(K_GRAD_MISC, k_grad_pcem_atoms<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
         KL(K_GRAD_MISC, k_grad_pcem_charges<<<grid2(std::max(I.max_npc, 1), 64, nmol), 64, 0, st>>>(d));
@@ -892,7 +947,23 @@ void Batch::fetch(const char* name, double* out) const {
         {"dispmat", d.dispmat, (size_t)I.sys.tot_dd}, {"gw", d.gw, nr}, {"selfenergy", d.selfE, ns}, {"xyz", d.xyz, 3 * na},
         {"vs", d.vs, na}, {"vd", d.vd, 3 * na}, {"vq", d.vq, 6 * na}, {"q_out", d.q_out, na}, {"qsh_out", d.qsh_out, ns},
         {"pcgradient", d.pc_grad, 3 * (size_t)external_charge_count()},
+        {"brad", d.sv_brad, na}, {"sasa", d.sv_sasa, na}, {"bornmat", d.sv_bmat, tn}, {"solv_mol", d.sv_mol, (size_t)SVM_STRIDE * d.nmol},
     };
+    if (std::strcmp(name, "solvation") == 0) {   // per molecule: g_solv, g_born, g_sasa, g_hb, g_shift
+        if (!d.solv_on) throw std::runtime_error("no solvation model set");
+        std::vector<double> tmp((size_t)SVM_STRIDE * d.nmol);
+        XTB_CUDA_CHECK(cudaSetDevice(I.device));
+        XTB_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), d.sv_mol, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, I.stream));
+        XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+        for (int i = 0; i < d.nmol; ++i) {
+            const double* t = &tmp[(size_t)SVM_STRIDE * i];
+            out[5 * i] = t[SVM_GSOLV]; out[5 * i + 1] = t[SVM_GBORN]; out[5 * i + 2] = t[SVM_GSASA]; out[5 * i + 3] = t[SVM_GHB];
+            out[5 * i + 4] = t[SVM_GSHIFT];
+        }
+        return;
+    }
+    if (!d.solv_on && (!std::strcmp(name, "brad") || !std::strcmp(name, "sasa") || !std::strcmp(name, "bornmat") || !std::strcmp(name, "solv_mol")))
+        throw std::runtime_error("no solvation model set");
     XTB_CUDA_CHECK(cudaSetDevice(I.device));
     for (const E& e : tab)
         if (std::strcmp(e.n, name) == 0) {
@@ -920,6 +991,10 @@ size_t Batch::fetch_len(const char* name) const {
     if (n == "dispmat") return (size_t)I.sys.tot_dd;
     if (n == "gw") return nr;
     if (n == "pcgradient") return 3 * (size_t)external_charge_count();
+    if (n == "brad" || n == "sasa") return na;
+    if (n == "bornmat") return tn;
+    if (n == "solvation") return 5 * (size_t)I.d.nmol;
+    if (n == "solv_mol") return (size_t)SVM_STRIDE * I.d.nmol;
     throw std::runtime_error(std::string("unknown array: ") + name);
 }
 void Batch::fetch_mask(unsigned char* out) const {

@@ -49,6 +49,14 @@ class Batch {
     void set_external_charges(const int* npc, const int* numbers, const double* charges, const double* xyz);
     void release_external_charges();
     long long external_charge_count() const;
+    // implicit solvation (xtb_setSolvent, src/api/calculator.f90:341-445): one model for all molecules of the batch.
+    // kernel 1 = Still (GBSA parameter sets), 2 = P16 (ALPB parameter sets); state 1 gsolv, 2 reference, 3 mol1bar;
+    // throws when the solvent has no internal GFN2-xTB parameter set.  fetch("solvation") gives per molecule
+    // g_solv, g_born, g_sasa, g_hb, g_shift; fetch("brad") / fetch("sasa") the Born radii and atomic surfaces.
+    void set_solvent(const char* solvent, bool alpb, int kernel, int state, double temperature, double ion_strength,
+                     double ion_rad);
+    void release_solvent();
+    bool has_solvent() const;
     void invalidate_wavefunction();
     bool has_wavefunction() const;
     // runs SP + gradient for every molecule; returns the number of molecules that failed / did not converge

@@ -233,6 +233,7 @@ __global__ void k_d4_shift(Dev d) {
     if (i >= m.nat) return;
     const AtomPar& a = d.atoms[m.at0 + i];
     double s = 0;
+    if (d.solv_on) s = d.sv_shift[m.at0 + i];   // solvation%addShift precedes scD4%addShift, scc_core.f90:444-452
     for (int r = 0; r < a.nref; ++r) s += d.dvec[m.ref0 + a.ref0 + r] * d.dzeta[m.ref0 + a.ref0 + r];
     d.ashift[m.at0 + i] = s;
 }
@@ -554,11 +555,18 @@ __global__ void __launch_bounds__(256) k_scc_finish(Dev d) {
         for (int s = tid; s < m.nsh; s += nt) p += d.qsh_out[m.sh0 + s] * d.vpc[m.sh0 + s];
         epcem = block_sum(p, red);
     }
+    double gsolv = 0.0;
+    if (d.solv_on) {   // solvation%getEnergy with the output charges, scc_core.f90:543-548 -> gbsa.f90:510-535
+        p = 0;
+        for (int i = tid; i < m.nat; i += nt) p += d.q_out[m.at0 + i] * (0.5 * d.sv_bq[m.at0 + i]);
+        gsolv = block_sum(p, red) + d.sv_mol[24 * (size_t)im] + d.solv_gshift;
+    }
     const double eold = st.eel;
     double eel = ees + eh0 * kEVtoAU;
     eel = eel + eaes + epol;
     eel = eel + ed;
     eel = eel + epcem;
+    eel = eel + gsolv;
     eel = eel + st.ga + st.gb;
     const bool econv = fabs(eel - eold) < d.scfconv;
     // --- charge difference vector (gfn2broyden_save/diff, aespot.F90:1360-1425)

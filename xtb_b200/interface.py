@@ -69,6 +69,7 @@ def load_library():
         "xtbb200_delBatch": (None, [ctypes.POINTER(vp)]),
         "xtbb200_setOptions": (ci, [vp, cd, cd, ci, ci]),
         "xtbb200_setSolver": (ci, [vp, ci]),
+        "xtbb200_setSolvent": (ci, [vp, cp, ci, ci, ci, cd, cd, cd]),
         "xtbb200_setExternalCharges": (ci, [vp, _c_int_p, _c_int_p, _c_double_p, _c_double_p]),
         "xtbb200_symmetricEigen": (ci, [ci, _c_double_p, _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_float), ci]),
         "xtbb200_setWavefunction": (ci, [vp, _c_double_p, _c_double_p, _c_double_p]),
@@ -325,11 +326,16 @@ class Calculator(Molecule):
         self._lib.xtb_setElectronicTemp(self._env, self._calc, float(etemp))
         self.raise_on_error("Could not set electronic temperature")
 
-    def set_solvent(self, solvent=None):
+    def set_solvent(self, solvent=None, model=None, state=None, temperature=None, grid=None):
+        """xtb_setSolvent / xtb_releaseSolvent: implicit solvation, model "gbsa" (default) or "alpb"; None releases it."""
         if solvent is None:
             self._lib.xtb_releaseSolvent(self._env, self._calc)
         else:
-            self._lib.xtb_setSolvent(self._env, self._calc, str(solvent).encode(), None, None, None, None)
+            st = ctypes.byref(ctypes.c_int(int(state))) if state is not None else None
+            te = ctypes.byref(ctypes.c_double(float(temperature))) if temperature is not None else None
+            gr = ctypes.byref(ctypes.c_int(int(grid))) if grid is not None else None
+            self._lib.xtb_setSolvent(self._env, self._calc, str(solvent).encode(), st, te, gr,
+                                     model.encode() if model is not None else None)
         self.raise_on_error("Failed to set solvent model")
 
     def set_external_charges(self, numbers, charges, positions):
@@ -426,6 +432,19 @@ class BatchCalculator:
         po = np.ascontiguousarray(positions, dtype=np.float64)
         assert len(nu) == int(n.sum()) == len(ch) and po.size == 3 * len(ch)
         self._check(self._lib.xtbb200_setExternalCharges(self._b, _ip(n), _ip(nu), _dp(ch), _dp(po)))
+
+    def set_solvent(self, solvent=None, model="gbsa", kernel=None, state=1, temperature=298.15, ion_strength=0.0, ion_rad=0.0):
+        """Implicit solvation for all molecules (xtbb200_setSolvent): model "gbsa" or "alpb"; kernel "still" / "p16"
+        (default: what xtb_setSolvent selects for the model); None releases it.  Energy parts after a single point:
+        array("solvation").reshape(nmol, 5) = g_solv, g_born, g_sasa, g_hb, g_shift."""
+        if solvent is None:
+            self._check(self._lib.xtbb200_setSolvent(self._b, None, 0, 2, 1, 298.15, 0.0, 0.0))
+            return
+        if kernel is None:
+            kernel = "still" if model == "gbsa" else "p16"
+        self._check(self._lib.xtbb200_setSolvent(self._b, str(solvent).encode(), 1 if model == "alpb" else 0,
+                                                 {"still": 1, "p16": 2}[kernel], int(state), float(temperature),
+                                                 float(ion_strength), float(ion_rad)))
 
     def set_solver(self, mode):
         """0: automatic, 1: scalar Jacobi kernel, 2: X from eig(S), 3: two-level Jacobi for large matrices."""
