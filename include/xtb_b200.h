@@ -46,6 +46,24 @@ int xtbb200_setWavefunction(xtbb200_TBatch batch, const double* qsh, const doubl
 int xtbb200_setExternalCharges(xtbb200_TBatch batch, const int* npc, const int* numbers, const double* charges,
                                const double* positions);
 
+/* Molecular dynamics of every molecule of the batch as independent replicas (reference: src/dynamic.f90:140-702 md,
+ * src/shake_module.f90 init_shake / do_shake, src/rmrottr.f90): leap-frog with Berendsen thermostat (thermostat != 0,
+ * tau = 500 fs), SHAKE (shake_mode 0 off, 1 X-H bonds, 2 all bonds with a Wiberg bond order above 0.5; xtb's default is 2),
+ * hydrogen mass hmass amu (0 = physical; xtb's default is 4) and removal of the overall translation / rotation every
+ * step.  The potential is whatever the batch is set up with (solvent, external charges, accuracy).
+ *   xtbb200_mdInit: positions [natoms][3] in bohr; runs the single point that provides the bond orders (restart != 0:
+ *     from the stored wavefunction); velocities [natoms][3] in atomic units or NULL = the reference's start (every
+ *     component +-sqrt(2 e / m), hydrogens doubled, signs drawn from `seed`).  xtb's defaults: tstep_fs 4, 298.15 K.
+ *   xtbb200_mdRun: nsteps steps; positions, velocities and forces stay on the device, per step only 4 doubles per molecule
+ *     are read back.  epot / ekin / temperature: [nsteps][nmol] (Hartree, Hartree, K), any may be NULL.  Returns the
+ *     number of steps done (less than nsteps when a replica blew up), -1 on error.  Positions and velocities:
+ *     xtbb200_getArray("xyz" | "velocities").
+ *   xtbb200_mdConstraints: number of SHAKE constraints of the whole batch. */
+int xtbb200_mdInit(xtbb200_TBatch batch, const double* positions, double tstep_fs, double temperature, int thermostat,
+                   int shake_mode, int hmass, const double* velocities, unsigned long long seed, int restart);
+int xtbb200_mdRun(xtbb200_TBatch batch, int nsteps, double* epot, double* ekin, double* temperature);
+long long xtbb200_mdConstraints(xtbb200_TBatch batch);
+
 /* Implicit solvation for every molecule of the batch (batched form of xtb_setSolvent / xtb_releaseSolvent,
  * reference: src/api/calculator.f90:341-476 -> src/solv/model.f90, gbsa.f90).  solvent: name as xtb accepts it ("h2o",
  * "water", "ch2cl2", "dmso" ...), NULL releases the model.  alpb: 0 = GBSA, 1 = ALPB.  kernel: 1 = Still (GBSA parameter

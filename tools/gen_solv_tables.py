@@ -10,6 +10,9 @@ Sources (file:line of the reference):
   src/param/vdwradd3.f90:37-61       vanDerWaalsRadD3 (Angstrom)
   src/solv/lebedev.f90:542-577       ld0230: orbit parameters of the 230 point Lebedev-Laikov grid; the points are
                                      expanded here in the order of genOh1..genOh6 (lebedev.f90:126-317)
+and, for the molecular dynamics driver (md_tables.h):
+  src/param/atomicmass.f90:37-67     atomicMass (amu)
+  src/shake_module.f90:36-41         metal(1:86) flags of init_shake
 """
 import glob
 import math
@@ -125,6 +128,24 @@ def lebedev230(ref):
     return pts
 
 
+def md_tables(ref, outdir):
+    text = open(os.path.join(ref, 'src', 'param', 'atomicmass.f90')).read()
+    m = re.search(r'atomicMass\(1:118\) = amutoau \* \[(.*?)\]', text, re.S)
+    mass = numbers(m.group(1))
+    assert len(mass) == 118
+    text = open(os.path.join(ref, 'src', 'shake_module.f90')).read()
+    m = re.search(r'metal\(1:86\) = \[(.*?)\]', text, re.S)
+    metal = [int(t) for t in re.findall(r'\b[01]\b', m.group(1))]
+    assert len(metal) == 86
+    with open(os.path.join(outdir, 'md_tables.h'), 'w') as f:
+        f.write('// GENERATED by tools/gen_solv_tables.py from grimme-lab/xtb v6.7.1 parameter data. Do not edit.\n')
+        f.write('#pragma once\n\n// atomic masses in amu (src/param/atomicmass.f90)\n')
+        f.write('static const double md_atomic_mass_amu[118] = {%s};\n\n' % ', '.join(fmt(x) for x in mass))
+        f.write('// metal flags of the SHAKE bond selection (src/shake_module.f90:36-41)\n')
+        f.write('static const int md_metal[86] = {%s};\n' % ', '.join(str(x) for x in metal))
+    print('wrote md_tables.h')
+
+
 def fmt(v):
     return repr(float(v))
 
@@ -161,6 +182,7 @@ def main():
             f.write('  {%s},\n' % ', '.join(fmt(x) for x in p))
         f.write('};\n')
     print('wrote solv_tables.h: %d GBSA sets, %d ALPB sets' % (len(gbsa), len(alpb)))
+    md_tables(ref, outdir)
 
 
 if __name__ == '__main__':

@@ -620,6 +620,28 @@ int xtbb200_setSolvent(xtbb200_TBatch batch, const char* solvent, int alpb, int 
     return 0;
     XTBB_CATCH(-1)
 }
+int xtbb200_mdInit(xtbb200_TBatch batch, const double* positions, double tstep_fs, double temperature, int thermostat,
+                   int shake_mode, int hmass, const double* velocities, unsigned long long seed, int restart) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    if (!positions) throw std::runtime_error("positions are required");
+    batch->b->md_init(positions, tstep_fs, temperature, thermostat != 0, shake_mode, hmass, velocities, seed, restart != 0);
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_mdRun(xtbb200_TBatch batch, int nsteps, double* epot, double* ekin, double* temperature) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    if (nsteps < 0) throw std::runtime_error("negative number of steps");
+    return batch->b->md_run(nsteps, epot, ekin, temperature);
+    XTBB_CATCH(-1)
+}
+long long xtbb200_mdConstraints(xtbb200_TBatch batch) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    return batch->b->md_constraints();
+    XTBB_CATCH(-1)
+}
 int xtbb200_setSolver(xtbb200_TBatch batch, int mode) {
     XTBB_TRY
     if (!batch) throw std::runtime_error("batch is not allocated");

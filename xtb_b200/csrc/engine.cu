@@ -23,6 +23,8 @@
 #include "kernels_linalg.cuh"
 #include "kernels_scc.cuh"
 #include "kernels_solv.cuh"
+#include "kernels_md.cuh"
+#include "tables/md_tables.h"
 #include "solvation.h"
 
 namespace xtbb200 {
@@ -58,7 +60,7 @@ __global__ void k_eigh_finish(Dev d, const int* fail, int fail_stride) {
 // kernel classes for the per-kernel device timers (bench.py roofline, profiles/)
 enum KernelId { K_SETUP = 0, K_EEQ, K_SDQH0, K_DQMASK, K_CHOL, K_POT, K_D4SCC, K_FOCK, K_GEMM_XHX, K_JACOBI, K_GEMM_C,
                 K_FERMI, K_DENSITY, K_POP, K_ENERGY, K_SCCFIN, K_GRAD_H0, K_GRAD_AES, K_GRAD_D4, K_GRAD_ATM, K_GRAD_MISC,
-                K_WBO, K_FINISH, K_COMM, K_EIG_PANEL, K_EIG_TRAIL, K_EIG_DC, K_EIG_BT, K_SOLV_SETUP, K_SOLV_SCC, K_SOLV_GRAD, K_COUNT };
+                K_WBO, K_FINISH, K_COMM, K_EIG_PANEL, K_EIG_TRAIL, K_EIG_DC, K_EIG_BT, K_SOLV_SETUP, K_SOLV_SCC, K_SOLV_GRAD, K_MD, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {
     "setup(cn,gab,jmat,dispmat,rep)", "eeq_guess", "k_sdqh0", "k_dqmask", "k_chol_inv", "potentials(shell,aes)",
     "d4_scc(zeta,matvec,shift)", "k_fock", "k_gemm(X^T H X)", "k_jacobi",   /* = the eigensolver class, whichever kernel family runs */ "k_gemm(C=XZ)", "k_fermi",
@@ -66,7 +68,7 @@ static const char* const kKernelNames[K_COUNT] = {
     "k_grad_h0(+W build,collect)", "k_grad_aes", "grad_d4(weights,c6,pairs)", "k_grad_atm", "k_grad_cn", "wbo(PS gemm,k_wbo)",
     "k_finish", "nccl_allreduce(S,D,Q,H0 | dE/dCN | gradient)", "eig:k_sytrd_panel", "eig:trailing update(k_eg_gemm)",
     "eig:divide and conquer", "eig:back-transformation", "solv:setup(born,sasa,shape,bornmat)", "solv:scc(k_solv_matvec)",
-    "solv:gradient(pairs,energy,chain)"};
+    "solv:gradient(pairs,energy,chain)", "k_md_update"};
 
 // NCCL is needed only when one large system is split over GPUs; it is resolved at run time so that the
 // single-GPU library has no link dependency on it.  Inside a PyTorch process the already loaded torch-bundled
@@ -169,6 +171,10 @@ struct Batch::Impl {
     long long pc_cap = 0;          // capacity (charges) of the device buffers below
     long long* pc0_dev = nullptr;
     double* pc_buf = nullptr;      // [gam | q | xyz(3) | grad(3)] x pc_cap
+    MdDev md;                 // molecular dynamics state (md_ready == false: md_init not called)
+    bool md_ready = false, md_first = true;
+    long long md_ncons = 0;
+    std::vector<double> md_out;
     SolvModel solv;           // implicit solvation model (solv.on == false: none)
     double* sv_par_dev = nullptr;
     bool leb_uploaded = false;
@@ -516,6 +522,146 @@ void Batch::release_solvent() { p_->d.solv_on = 0; p_->solv.on = false; }
 bool Batch::has_solvent() const { return p_->d.solv_on != 0; }
 void Batch::release_external_charges() { set_external_charges(nullptr, nullptr, nullptr, nullptr); }
 long long Batch::external_charge_count() const { return p_->h_pc0.empty() ? 0 : p_->h_pc0.back(); }
+
+// ---- molecular dynamics (kernels_md.cuh) ----
+void Batch::md_init(const double* xyz_host, double tstep_fs, double temperature, bool thermostat, int shake_mode, int hmass,
+                    const double* velocities, unsigned long long seed, bool restart) {
+    Impl& I = *p_;
+    Dev& d = I.d;
+    if (!(tstep_fs > 0.0) || !(temperature > 0.0)) throw std::runtime_error("md: time step and temperature must be positive");
+    if (shake_mode < 0 || shake_mode > 2) throw std::runtime_error("md: shake mode must be 0, 1 or 2");
+    const double amutoau = 1.660539040e-27 * (1.0 / 9.10938356e-31);   // src/mctc/convert.f90:51-55
+    const double fstoau = 1.0e-15 / 2.4188843265857e-17;               // src/mctc/convert.f90:58-60
+    const int nmol = d.nmol;
+    const size_t na = I.sys.atoms.size();
+    set_positions(xyz_host);
+    singlepoint(restart);   // the single point of the main program: wavefunction and bond orders (src/prog/main.F90:1147)
+    std::vector<double> wbo((size_t)I.sys.tot_nn), mass(na), velo(3 * na), nfree(nmol);
+    fetch("wbo", wbo.data());
+    // masses, dynamic.f90:237-252
+    for (size_t a = 0; a < na; ++a) {
+        const int Z = I.sys.atoms[a].Z;
+        mass[a] = md_atomic_mass_amu[Z - 1] * amutoau;
+        if (Z == 1 && hmass > 0) mass[a] = (double)hmass * amutoau;
+    }
+    // SHAKE constraints, init_shake (src/shake_module.f90:50-148)
+    std::vector<long long> cons0(nmol + 1, 0), adj0(na + 1, 0);
+    std::vector<int> cons, adj;
+    std::vector<double> dist2;
+    for (int im = 0; im < nmol; ++im) {
+        const MolDesc& m = I.sys.mol[im];
+        const double* x = xyz_host + 3 * (size_t)m.at0;
+        const double* w = wbo.data() + m.nn0;
+        std::vector<std::pair<int, int>> list;
+        auto r2 = [&](int i, int j) { double s = 0; for (int k = 0; k < 3; ++k) { const double t = x[3 * i + k] - x[3 * j + k]; s += t * t; } return s; };
+        if (shake_mode == 1) {   // every hydrogen to its nearest neighbour
+            for (int i = 0; i < m.nat; ++i) {
+                if (I.sys.atoms[m.at0 + i].Z != 1) continue;
+                double minr = 1000.0; int jmin = -1;
+                for (int j = 0; j < m.nat; ++j) if (j != i && r2(i, j) < minr) { minr = r2(i, j); jmin = j; }
+                if (jmin < 0) continue;
+                if (I.sys.atoms[m.at0 + jmin].Z == 1) { if (jmin > i) list.push_back({i, jmin}); }
+                else list.push_back({i, jmin});
+            }
+        } else if (shake_mode == 2) {   // all bonds: close contacts with a Wiberg bond order above the threshold, metals excluded
+            for (int i = 0; i < m.nat; ++i)
+                for (int j = i + 1; j < m.nat; ++j) {
+                    const int zi = I.sys.atoms[m.at0 + i].Z, zj = I.sys.atoms[m.at0 + j].Z;
+                    const double rco = (I.sys.atoms[m.at0 + i].rad + I.sys.atoms[m.at0 + j].rad) * kAutoAA;
+                    if (!(0.52917726 * std::sqrt(r2(i, j)) < 1.2 * rco)) continue;
+                    bool metalbond = md_metal[zi - 1] == 1 || md_metal[zj - 1] == 1;
+                    const double wthr = metalbond ? 0.1 : 0.5;
+                    if (!(w[i + (size_t)m.nat * j] > wthr)) continue;
+                    if (zi == 3 || zi == 4 || zj == 3 || zj == 4) metalbond = false;
+                    if (!metalbond) list.push_back({i, j});
+                }
+        }
+        std::vector<std::vector<int>> per_atom(m.nat);
+        for (size_t c = 0; c < list.size(); ++c) {
+            cons.push_back(list[c].first); cons.push_back(list[c].second);
+            dist2.push_back(r2(list[c].first, list[c].second));
+            per_atom[list[c].first].push_back(2 * (int)c);
+            per_atom[list[c].second].push_back(2 * (int)c + 1);
+        }
+        cons0[im + 1] = cons0[im] + (long long)list.size();
+        for (int i = 0; i < m.nat; ++i) {
+            adj.insert(adj.end(), per_atom[i].begin(), per_atom[i].end());
+            adj0[m.at0 + i + 1] = (long long)adj.size();
+        }
+        nfree[im] = 3.0 * m.nat - (shake_mode ? (double)list.size() : 0.0);   // dynamic.f90:277-280
+    }
+    I.md_ncons = cons0[nmol];
+    // velocities, mdinitu (dynamic.f90:850-890): every component +-sqrt(2 e / m), hydrogens twice that; e = Ekin / (3 n)
+    if (velocities) velo.assign(velocities, velocities + 3 * na);
+    else {
+        unsigned long long sdm = seed ? seed : 0x9E3779B97F4A7C15ull;
+        auto next = [&]() {   // splitmix64
+            sdm += 0x9E3779B97F4A7C15ull;
+            unsigned long long z = sdm;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            return z ^ (z >> 31);
+        };
+        for (int im = 0; im < nmol; ++im) {
+            const MolDesc& m = I.sys.mol[im];
+            const double f = thermostat ? 1.0 : 2.0;
+            const double eperat = f * temperature * 0.5 * kBoltz * nfree[im] / (3.0 * m.nat);
+            for (int i = 0; i < m.nat; ++i) {
+                const size_t a = m.at0 + i;
+                const double v = std::sqrt(2.0 * eperat / mass[a]) * (I.sys.atoms[a].Z == 1 ? 2.0 : 1.0);
+                for (int k = 0; k < 3; ++k) velo[3 * a + k] = (next() >> 63) ? -v : v;
+            }
+        }
+    }
+    MdDev& md = I.md;
+    if (!I.md_ready) {
+        md.velo = I.dalloc<double>(3 * na); md.vel = I.dalloc<double>(3 * na); md.mass = I.dalloc<double>(na);
+        md.xyzo = I.dalloc<double>(3 * na); md.acc = I.dalloc<double>(3 * na); md.xyzt = I.dalloc<double>(3 * na);
+        md.out = I.dalloc<double>(4 * (size_t)nmol);
+    }
+    // constraint tables change with every md_init: fresh uploads (freed with the batch)
+    md.cons0 = I.upload(cons0); md.cons = I.upload(cons); md.dist2 = I.upload(dist2);
+    md.dro = I.dalloc<double>(3 * dist2.size()); md.gc = I.dalloc<double>(dist2.size());
+    md.adj0 = I.upload(adj0); md.adj = I.upload(adj); md.nfree = I.upload(nfree);
+    XTB_CUDA_CHECK(cudaMemcpyAsync(md.velo, velo.data(), velo.size() * sizeof(double), cudaMemcpyHostToDevice, I.stream));
+    XTB_CUDA_CHECK(cudaMemcpyAsync(md.mass, mass.data(), mass.size() * sizeof(double), cudaMemcpyHostToDevice, I.stream));
+    XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+    md.tstep0 = tstep_fs; md.tstep = tstep_fs * fstoau; md.taut = 500.0; md.tinit = temperature;
+    md.thermostat = thermostat ? 1 : 0; md.shake = shake_mode ? 1 : 0;
+    I.md_out.assign(4 * (size_t)nmol, 0.0);
+    I.md_ready = true; I.md_first = true;
+}
+long long Batch::md_constraints() const { return p_->md_ncons; }
+
+int Batch::md_run(int nsteps, double* epot, double* ekin, double* temp) {
+    Impl& I = *p_;
+    if (!I.md_ready) throw std::runtime_error("md_run: md_init has not been called");
+    const int nmol = I.d.nmol;
+    if (I.md_first) { singlepoint(true); I.md_first = false; }   // the single point before the MD loop, dynamic.f90:383-385
+    int done = 0;
+    for (int k = 0; k < nsteps; ++k) {
+        singlepoint(true);
+        I.prof_begin(K_MD, I.stream);
+        k_md_update<<<nmol, 256, 0, I.stream>>>(I.d, I.md);
+        I.prof_end(K_MD, I.stream);
+        I.k_launches[K_MD]++;
+        I.launches++;
+        XTB_CUDA_CHECK(cudaMemcpyAsync(I.md_out.data(), I.md.out, 4 * (size_t)nmol * sizeof(double), cudaMemcpyDeviceToHost, I.stream));
+        XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+        XTB_CUDA_CHECK(cudaGetLastError());
+        I.prof_collect();
+        bool bad = false;
+        for (int i = 0; i < nmol; ++i) {
+            const double* o = &I.md_out[4 * (size_t)i];
+            if (epot) epot[(size_t)k * nmol + i] = o[0];
+            if (ekin) ekin[(size_t)k * nmol + i] = o[1];
+            if (temp) temp[(size_t)k * nmol + i] = o[2];
+            if (!(o[0] == o[0]) || o[0] > 1.e5 || o[0] < -1.e5 || o[2] > 10000.0) bad = true;   // dynamic.f90:424-431
+        }
+        done = k + 1;
+        if (bad) break;
+    }
+    return done;
+}
 
 template <int TG>
 static void launch_jacobi(Dev& d, int nmol, int max_nao, bool sm, cudaStream_t st) {
@@ -947,6 +1093,7 @@ void Batch::fetch(const char* name, double* out) const {
         {"dispmat", d.dispmat, (size_t)I.sys.tot_dd}, {"gw", d.gw, nr}, {"selfenergy", d.selfE, ns}, {"xyz", d.xyz, 3 * na},
         {"vs", d.vs, na}, {"vd", d.vd, 3 * na}, {"vq", d.vq, 6 * na}, {"q_out", d.q_out, na}, {"qsh_out", d.qsh_out, ns},
         {"pcgradient", d.pc_grad, 3 * (size_t)external_charge_count()},
+        {"velocities", I.md.velo, 3 * na}, {"md_mass", I.md.mass, na}, {"md_out", I.md.out, 4 * (size_t)d.nmol},
         {"brad", d.sv_brad, na}, {"sasa", d.sv_sasa, na}, {"bornmat", d.sv_bmat, tn}, {"solv_mol", d.sv_mol, (size_t)SVM_STRIDE * d.nmol},
     };
     if (std::strcmp(name, "solvation") == 0) {   // per molecule: g_solv, g_born, g_sasa, g_hb, g_shift
@@ -962,6 +1109,8 @@ void Batch::fetch(const char* name, double* out) const {
         }
         return;
     }
+    if (!I.md_ready && (!std::strcmp(name, "velocities") || !std::strcmp(name, "md_mass") || !std::strcmp(name, "md_out")))
+        throw std::runtime_error("molecular dynamics has not been initialised");
     if (!d.solv_on && (!std::strcmp(name, "brad") || !std::strcmp(name, "sasa") || !std::strcmp(name, "bornmat") || !std::strcmp(name, "solv_mol")))
         throw std::runtime_error("no solvation model set");
     XTB_CUDA_CHECK(cudaSetDevice(I.device));
@@ -991,6 +1140,9 @@ size_t Batch::fetch_len(const char* name) const {
     if (n == "dispmat") return (size_t)I.sys.tot_dd;
     if (n == "gw") return nr;
     if (n == "pcgradient") return 3 * (size_t)external_charge_count();
+    if (n == "velocities") return 3 * na;
+    if (n == "md_mass") return na;
+    if (n == "md_out") return 4 * (size_t)I.d.nmol;
     if (n == "brad" || n == "sasa") return na;
     if (n == "bornmat") return tn;
     if (n == "solvation") return 5 * (size_t)I.d.nmol;

@@ -57,6 +57,17 @@ class Batch {
                      double ion_rad);
     void release_solvent();
     bool has_solvent() const;
+    // Molecular dynamics of every molecule of the batch as independent replicas (src/dynamic.f90:140-702): leap-frog
+    // with Berendsen thermostat (tau = 500 fs), SHAKE (0 off, 1 X-H bonds, 2 all bonds with a Wiberg bond order > 0.5,
+    // src/shake_module.f90:50-148) and removal of overall translation / rotation; hydrogen mass hmass amu (0: physical).
+    // md_init runs the single point that provides the bond orders; velocities [natoms][3] in atomic units, or null:
+    // mdinitu (dynamic.f90:850-890) with random signs from `seed`.  md_run propagates nsteps steps, positions, velocities
+    // and forces stay on the device; epot / ekin / temp: [nsteps][nmol] (Hartree, Hartree, K), any may be null.  Returns
+    // the number of steps done (fewer than nsteps when a replica blew up: energy not finite or T > 10000 K).
+    void md_init(const double* xyz_host, double tstep_fs, double temperature, bool thermostat, int shake_mode, int hmass,
+                 const double* velocities, unsigned long long seed, bool restart);
+    int md_run(int nsteps, double* epot, double* ekin, double* temp);
+    long long md_constraints() const;
     void invalidate_wavefunction();
     bool has_wavefunction() const;
     // runs SP + gradient for every molecule; returns the number of molecules that failed / did not converge

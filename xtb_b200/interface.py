@@ -70,6 +70,9 @@ def load_library():
         "xtbb200_setOptions": (ci, [vp, cd, cd, ci, ci]),
         "xtbb200_setSolver": (ci, [vp, ci]),
         "xtbb200_setSolvent": (ci, [vp, cp, ci, ci, ci, cd, cd, cd]),
+        "xtbb200_mdInit": (ci, [vp, _c_double_p, cd, cd, ci, ci, ci, _c_double_p, ctypes.c_ulonglong, ci]),
+        "xtbb200_mdRun": (ci, [vp, ci, _c_double_p, _c_double_p, _c_double_p]),
+        "xtbb200_mdConstraints": (ctypes.c_longlong, [vp]),
         "xtbb200_setExternalCharges": (ci, [vp, _c_int_p, _c_int_p, _c_double_p, _c_double_p]),
         "xtbb200_symmetricEigen": (ci, [ci, _c_double_p, _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_float), ci]),
         "xtbb200_setWavefunction": (ci, [vp, _c_double_p, _c_double_p, _c_double_p]),
@@ -445,6 +448,25 @@ class BatchCalculator:
         self._check(self._lib.xtbb200_setSolvent(self._b, str(solvent).encode(), 1 if model == "alpb" else 0,
                                                  {"still": 1, "p16": 2}[kernel], int(state), float(temperature),
                                                  float(ion_strength), float(ion_rad)))
+
+    def md_init(self, positions, tstep_fs=4.0, temperature=298.15, thermostat=True, shake=2, hmass=4, velocities=None,
+                seed=1, restart=False):
+        """Start molecular dynamics of all molecules as independent replicas (xtbb200_mdInit; defaults as xtb's $md block:
+        4 fs, 298.15 K, Berendsen thermostat, SHAKE on all bonds, hydrogen mass 4 amu).  Returns the number of constraints."""
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        assert pos.size == 3 * self.total_atoms
+        vel = np.ascontiguousarray(velocities, dtype=np.float64) if velocities is not None else None
+        self._check(self._lib.xtbb200_mdInit(self._b, _dp(pos), float(tstep_fs), float(temperature), int(bool(thermostat)),
+                                             int(shake), int(hmass), _dp(vel) if vel is not None else None, int(seed),
+                                             int(bool(restart))))
+        return int(self._lib.xtbb200_mdConstraints(self._b))
+
+    def md_run(self, nsteps):
+        """Propagate nsteps MD steps (xtbb200_mdRun).  Returns dict(steps, epot, ekin, temperature) with [steps][nmol] arrays;
+        positions / velocities afterwards: array("xyz") / array("velocities")."""
+        ep, ek, te = (np.zeros((int(nsteps), self.nmol)) for _ in range(3))
+        n = self._check(self._lib.xtbb200_mdRun(self._b, int(nsteps), _dp(ep), _dp(ek), _dp(te)))
+        return dict(steps=n, epot=ep[:n], ekin=ek[:n], temperature=te[:n])
 
     def set_solver(self, mode):
         """0: automatic, 1: scalar Jacobi kernel, 2: X from eig(S), 3: two-level Jacobi for large matrices."""
