@@ -244,6 +244,9 @@ def run_engine(args):
     Z, pos = make_ensemble(s, nmol, first=rank * nmol)
     nat = len(Z)
     batch = xtb_b200.BatchCalculator([Z] * nmol, device=local)
+    if args.solvent:
+        batch.set_solvent(args.solvent, model=args.solvent_model)
+        args.no_cpu = True     # the cpu_baseline leg of this workload is the gas-phase ensemble
     sizes = batch.sizes(0)
     nao, nsh = sizes["nao"], sizes["nshell"]
     # pinned host buffers for the end-to-end leg; device-resident positions for the kernel leg
@@ -359,7 +362,8 @@ def run_engine(args):
         "ms_per_step": t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "ensemble of %d %s conformers per GPU (%d atoms, %d shells, %d AOs), sigma=0.05 bohr, "
-                               "EEQ guess, SP+gradient" % (nmol, args.molecule, nat, nsh, nao),
+                               "EEQ guess, SP+gradient%s" % (nmol, args.molecule, nat, nsh, nao,
+                                                             (", %s(%s)" % (args.solvent_model.upper(), args.solvent)) if args.solvent else ""),
                    "molecules_per_gpu": nmol, "parallelism": "molecule-sharded x%d, no collective" % world,
                    "l2": "per-step working set %.1f GB of HBM-resident matrices >> 126 MB L2 (no flush needed)" % (batch.device_bytes() / 1e9),
                    "mean_scc_iterations": mean_iter, "scc_passes": passes, "converged": "%d/%d" % (n_conv, nmol)},
@@ -632,6 +636,129 @@ def run_single(args):
     print(json.dumps(line), flush=True)
 
 
+def run_md(args):
+    """BASELINE configs[4]: GFN2-xTB molecular dynamics of a ~200-atom peptide in ALPB(water), MD steps per second.
+    System: 3 copies of the 76-atom peptide pdb-4qxx (test/unit/molstock.f90:739-909) 8 bohr apart = 228 atoms (SURVEY 8(d)
+    C5); xtb's default $md settings (4 fs, Berendsen 298.15 K, SHAKE on all bonds, hydrogen mass 4 amu).  A step = one
+    restarted single point + gradient and one propagation kernel.  MD does not shard (replicas only): with
+    --gpus N every rank runs its own replica (other start velocities) and the value is the sum over ranks.
+    value: xtbb200_mdRun, positions / velocities / forces resident on the device; e2e: the loop a user of the reference's
+    API drives from the host (positions H2D, energy + gradient D2H every step, leap-frog + thermostat on the host)."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    import xtb_b200
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    Z, xyz = make_peptide_cluster(load_kat("pdb_4qxx"), 3, gap=8.0)
+    nat = len(Z)
+    solvent = dict(solvent="water", model="alpb")
+    b = xtb_b200.BatchCalculator([Z], device=local)
+    b.set_solvent(**solvent)
+    ncons = b.md_init(xyz, seed=1 + rank)
+    sz = b.sizes(0)
+    steps = max(args.steps, 1) * 20                       # a "step" of the bench contract = 20 MD steps
+    b.set_profile("all")
+    b.md_run(max(args.warmup, 3) * 5)
+    prof, passes = b.kernel_times()
+    tot = sum(v["ms"] for v in prof.values())
+    share = {kk: round(v["ms"] / tot, 4) for kk, v in sorted(prof.items(), key=lambda x: -x[1]["ms"]) if v["ms"] / tot >= 0.01}
+    top = max(prof, key=lambda k: prof[k]["ms"])
+    b.set_profile([])
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    t0 = time.perf_counter()
+    r = b.md_run(steps)
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0                       # md_run blocks on the engine's stream after every step
+    clk = clocks.stop()
+    launches = int(b.timings()["launches"]) * steps
+    barrier()
+    # ---- end to end: host-driven loop through the host-buffer C ABI (restart = 1), unconstrained leap-frog on the host
+    L = xtb_b200.load_library()
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    pos_pin = torch.from_numpy(b.array("xyz").copy()).pin_memory()
+    e_pin = torch.empty(1, dtype=torch.float64).pin_memory()
+    g_pin = torch.empty(nat * 3, dtype=torch.float64).pin_memory()
+    q_pin = torch.empty(nat, dtype=torch.float64).pin_memory()
+    it_pin = torch.empty(1, dtype=torch.int32).pin_memory()
+    st_pin = torch.empty(1, dtype=torch.int32).pin_memory()
+    mass = b.array("md_mass")[:, None]
+    vel = b.array("velocities").reshape(-1, 3).copy()
+    x = pos_pin.numpy().reshape(-1, 3)
+    dt = 1.0 * 1.0e-15 / 2.4188843265857e-17              # 1 fs without constraints
+    nh = max(args.steps, 1) * 10
+    t0 = time.perf_counter()
+    for _ in range(nh):
+        rc = L.xtbb200_singlepoint(b._b, ctypes.cast(pos_pin.data_ptr(), dp), 1, ctypes.cast(e_pin.data_ptr(), dp),
+                                   ctypes.cast(g_pin.data_ptr(), dp), ctypes.cast(q_pin.data_ptr(), dp),
+                                   ctypes.cast(it_pin.data_ptr(), ip), ctypes.cast(st_pin.data_ptr(), ip))
+        if rc < 0:
+            raise RuntimeError(L.xtbb200_lastError().decode())
+        vel += -g_pin.numpy().reshape(-1, 3) / mass * dt
+        x += vel * dt
+    wall_host = time.perf_counter() - t0
+    rate, rate_host = steps / wall, nh / wall_host
+    if world > 1:
+        t = torch.tensor([rate, rate_host, wall], dtype=torch.float64, device=dev)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        rate, rate_host, wall = float(tsum[0]), float(tsum[1]), float(tmax[2])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if not args.no_cpu:
+        from oracle.md_oracle import MDOracle
+        from oracle.oracle import build
+        build()
+        cores = host_cores()
+        sg = np.where(np.random.default_rng(1).random((nat, 3)) > 0.5, -1.0, 1.0)
+        mo = MDOracle(Z, xyz, signs=sg, solvent=solvent, threads=cores)
+        mo.run(1)
+        t0 = time.perf_counter(); mo.run(4); dtc = time.perf_counter() - t0
+        cpu = {"value": 4 / dtc, "unit": "MD steps/s", "cores": cores, "kind": "port",
+               "sample": "4 MD steps of the same system and settings with the CPU oracle (OpenMP + OpenBLAS)"}
+    line = {
+        "metric": "GFN2-xTB MD steps/sec (228-atom peptide cluster, ALPB water)", "value": rate, "unit": "MD steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "MD, 3 x pdb-4qxx (%d atoms, %d AOs), ALPB(water), 4 fs, NVT 298.15 K, SHAKE on %d bonds, H mass 4; "
+                               "one replica per GPU; %d MD steps timed" % (nat, sz["nao"], ncons, steps),
+                   "scc_iterations_last_step": int(b.result(0)["niter"]),
+                   "l2": "one small system: latency bound, working set in L2"},
+        "e2e": {"value": rate_host, "unit": "MD steps/s", "h2d_bytes_per_step": int(nat * 24), "d2h_bytes_per_step": int(8 * (1 + 4 * nat) + 8),
+                "note": "host-driven loop: xtbb200_singlepoint(host positions, restart) + leap-frog on the host, %d steps" % nh},
+        "gpu_launches": launches,
+        "roofline": {"bound": "latency", "kernel": top, "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                     "note": "a 228-atom system cannot fill the GPU; kernel-class shares below"},
+        "share_all_kernels": share, "cpu_baseline": cpu, "clocks": clk,
+        "trajectory": {"epot_first": float(r["epot"][0, 0]), "epot_last": float(r["epot"][-1, 0]),
+                       "T_mean": float(r["temperature"][:, 0].mean()), "steps_done": int(r["steps"])},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -641,15 +768,20 @@ def main():
     ap.add_argument("--nmol", type=int, default=4096, help="conformers per GPU")
     ap.add_argument("--molecule", default="rivaroxaban")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "water", "single"],
+    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "water", "single", "md"],
                     help="ensemble: BASELINE configs[2] (default, the headline metric); water: configs[3], s/SCC-iteration; "
-                         "single: configs[0]/[1], one molecule (--molecule caffeine | protein) through the xtb.h C API")
+                         "single: configs[0]/[1], one molecule (--molecule caffeine | protein) through the xtb.h C API; "
+                         "md: configs[4], MD steps/s of a 228-atom peptide cluster in ALPB water")
+    ap.add_argument("--solvent", default=None, help="ensemble workload: implicit solvent (e.g. water) instead of the gas phase")
+    ap.add_argument("--solvent-model", default="alpb", choices=["gbsa", "alpb"])
     ap.add_argument("--nwat", type=int, default=1000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "water":
         run_water(args)
+    elif args.workload == "md":
+        run_md(args)
     elif args.workload == "single":
         if args.molecule == "rivaroxaban":
             args.molecule = "caffeine"

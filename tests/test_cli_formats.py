@@ -55,7 +55,8 @@ def test_turbomole_writers_layout_and_round_trip(kat, tmp_path):
 
 def test_unsupported_run_types_are_refused():
     assert cli.main(["mol.xyz", "--opt"]) == 2
-    assert cli.main(["mol.xyz", "--alpb", "water"]) == 2
+    assert cli.main(["mol.xyz", "--cosmo", "water"]) == 2
+    assert cli.main(["mol.xyz", "--alpb", "water", "--gbsa", "water", "--gfn", "1"]) == 2
     assert cli.main(["mol.xyz", "--gfn", "1"]) == 2
 
 
@@ -79,3 +80,23 @@ def test_cli_single_point_with_gradient(kat, tmp_path):
     q = np.loadtxt(tmp_path / "charges")
     assert np.max(np.abs(q - o.get("q"))) < 1e-6
     assert os.path.exists(tmp_path / "wbo") and os.path.exists(tmp_path / "energy")
+
+
+@pytest.mark.gpu
+def test_cli_alpb_single_point(kat, tmp_path):
+    """`xtb caffeine.xyz --gfn 2 --grad --alpb water` on the engine against the oracle."""
+    from oracle.oracle import Oracle
+    s = kat["caffeine"]
+    xyz_aa = s["xyz"] * 0.52917726
+    (tmp_path / "caffeine.xyz").write_text("%d\n\n" % len(s["numbers"]) + "".join(
+        "%-2s %20.14f %20.14f %20.14f\n" % (cli.SYMBOLS[z - 1], r[0], r[1], r[2]) for z, r in zip(s["numbers"], xyz_aa)))
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-m", "xtb_b200", "caffeine.xyz", "--gfn", "2", "--grad", "--alpb", "water"],
+                         cwd=tmp_path, env=env, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    o = Oracle(s["numbers"], s["xyz"])
+    o.set_solvent("water", "alpb")
+    assert o.singlepoint() == 0
+    e, x, g = cli.read_turbomole_gradient(str(tmp_path / "gradient"))
+    assert abs(e - o.energies["e_total"]) < 1e-7
+    assert np.max(np.abs(g - o.get("gradient").reshape(-1, 3))) < 1e-6

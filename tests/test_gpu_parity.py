@@ -205,7 +205,7 @@ def test_error_behaviour(xb):
     calc = xb.Calculator(xb.Param.GFN2xTB, [1, 1], [[0, 0, 0], [0, 0, 1.4]])
     calc.set_verbosity(0)
     with pytest.raises(xb.XTBException):
-        calc.set_solvent("water")                         # not on this path: raises, never silently ignored
+        calc.set_solvent("water", model="cosmo")          # not on this path: raises, never silently ignored
     calc.set_max_iterations(1)
     with pytest.raises(xb.XTBException):
         calc.singlepoint()                                # not converged is an error (src/scf_module.F90:806-808)

@@ -130,7 +130,7 @@ def write_wbo(wbo, path="wbo", thr=0.1):
                     f.write("%12d%12d   %.15f\n" % (j + 1, i + 1, wbo[j, i]))
 
 
-UNSUPPORTED = ["--opt", "--ohess", "--hess", "--md", "--omd", "--metadyn", "--alpb", "--gbsa", "--cosmo", "--gff", "--gfnff",
+UNSUPPORTED = ["--opt", "--ohess", "--hess", "--md", "--omd", "--metadyn", "--cosmo", "--gff", "--gfnff",
                "--vipea", "--vip", "--vea", "--path", "--modef", "--scan", "--esp", "--stm", "--tblite", "--cpcmx", "--oniom",
                "--dipro", "--siman", "--screen", "--bhess", "--vfukui", "--vomega", "--pcem"]
 
@@ -151,6 +151,8 @@ def main(argv=None):
     ap.add_argument("-a", "--acc", type=float, default=1.0)
     ap.add_argument("--etemp", type=float, default=300.0)
     ap.add_argument("--iterations", type=int, default=250)
+    ap.add_argument("--alpb", metavar="SOLVENT", default=None, help="ALPB implicit solvation (src/prog/argparser / set_gbsa)")
+    ap.add_argument("-g", "--gbsa", metavar="SOLVENT", default=None, help="GBSA implicit solvation")
     ap.add_argument("-v", "--verbose", action="store_true")
     ap.add_argument("--silent", action="store_true")
     args = ap.parse_args(argv)
@@ -165,6 +167,13 @@ def main(argv=None):
     calc.set_accuracy(args.acc)
     calc.set_electronic_temperature(args.etemp)
     calc.set_max_iterations(args.iterations)
+    if args.alpb and args.gbsa:
+        print("xtb_b200: --alpb and --gbsa are mutually exclusive", file=sys.stderr)
+        return 2
+    if args.alpb:
+        calc.set_solvent(args.alpb, model="alpb")
+    elif args.gbsa:
+        calc.set_solvent(args.gbsa, model="gbsa")
     res = calc.singlepoint()
     wall = time.perf_counter() - t0
     energy, grad = res.get_energy(), res.get_gradient()
