@@ -454,12 +454,15 @@ struct SytrdSmemArgs {
     double* Gf;         // Gram matrices of the block reflectors (as written by the panel kernel)
     unsigned* bar;
 };
+constexpr int kResGridMin = 148;   // smallest grid of the resident kernel (see EighWork::solve): fewer CTAs were slower at
+                                   // every order tried (n = 552: 3.09 ms with 148 CTAs, 3.71 with 32, 4.84 with 12)
 constexpr int kResRows = 2;   // rows of a column per thread: the resident kernel takes orders up to kResRows * kSytrdThreads
 inline size_t sytrd_smem_resident_bytes(int m0, int grid) {
     const size_t slots = (size_t)(m0 + grid - 1) / grid;
     return (slots * m0 + 2 * (size_t)m0 + 128) * sizeof(double);
 }
 
+template <int RR>   // RR = rows of a column per thread (the CTA has at least m0 / RR threads)
 __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a) {
     extern __shared__ double sm_dyn[];
     __shared__ double red[32], sh_d, sh_alpha;
@@ -481,10 +484,10 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
     double tau = 0.0;
     // Reflector of column jn from its up-to-date entries cn[k] (row jn + tid + k nthr) held in registers by every CTA:
     // v -> sv, tau; CTA jn % G stores d, e, tau and the reflector.  Ends with a CTA barrier.
-    auto form_reflector = [&](int jn, const double (&cn)[kResRows]) {
+    auto form_reflector = [&](int jn, const double (&cn)[RR]) {
         double sq = 0.0;
 #pragma unroll
-        for (int k = 0; k < kResRows; ++k) {
+        for (int k = 0; k < RR; ++k) {
             const int r = jn + tid + k * nthr;
             if (r == jn) sh_d = cn[k];
             else if (r == jn + 1) sh_alpha = cn[k];
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
         }
         if (writer && tid == 0) { a.d[j0 + jn] = sh_d; a.e[j0 + jn] = beta; a.tau[j0 + jn] = tau; }
 #pragma unroll
-        for (int k = 0; k < kResRows; ++k) {
+        for (int k = 0; k < RR; ++k) {
             const int r = jn + tid + k * nthr;
             if (r > jn && r < m0) {
                 const double v = (r == jn + 1) ? 1.0 : cn[k] * scal;
@@ -520,9 +523,9 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
     {   // first column: published by its owner, reflector formed by everybody
         if (cta == 0) for (int r = tid; r < m0; r += nthr) a.cbuf[ld + r] = cols[r];
         grid_barrier(a.bar, G, target);
-        double cn[kResRows];
+        double cn[RR];
 #pragma unroll
-        for (int k = 0; k < kResRows; ++k) { const int r = tid + k * nthr; cn[k] = r < m0 ? __ldcg(a.cbuf + ld + r) : 0.0; }
+        for (int k = 0; k < RR; ++k) { const int r = tid + k * nthr; cn[k] = r < m0 ? __ldcg(a.cbuf + ld + r) : 0.0; }
         form_reflector(0, cn);
     }
     for (int jj = 0; jj < m0 - 1; ++jj) {
@@ -564,9 +567,9 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
         }
         grid_barrier(a.bar, G, target);
         // ---- w = tau y - tau^2/2 (v^T y) v;  A -= v w^T + w v^T on the owned columns and on the published next column
-        double vy = 0.0, cn[kResRows];
+        double vy = 0.0, cn[RR];
 #pragma unroll
-        for (int k = 0; k < kResRows; ++k) {
+        for (int k = 0; k < RR; ++k) {
             const int r = jj + 1 + tid + k * nthr;
             cn[k] = 0.0;
             if (r < m0) { const double y = __ldcg(ybuf + r); cn[k] = __ldcg(cbuf + r); sw[r] = y; vy += sv[r] * y; }
@@ -574,15 +577,15 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
         vy = block_sum_sh(vy, red);
         const double coef = -0.5 * tau * tau * vy;
 #pragma unroll
-        for (int k = 0; k < kResRows; ++k) {
+        for (int k = 0; k < RR; ++k) {
             const int r = jj + 1 + tid + k * nthr;
             if (r < m0) sw[r] = tau * sw[r] + coef * sv[r];
         }
         __syncthreads();
         {   // thread = (row, slot parity): rows fastest so that the shared-memory accesses are conflict free
-            double vr[kResRows], wr[kResRows];
+            double vr[RR], wr[RR];
 #pragma unroll
-            for (int k = 0; k < kResRows; ++k) {
+            for (int k = 0; k < RR; ++k) {
                 const int r = jj + 1 + tid + k * nthr;
                 vr[k] = r < m0 ? sv[r] : 0.0;
                 wr[k] = r < m0 ? sw[r] : 0.0;
@@ -592,7 +595,7 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
                 const double wc = sw[c], vc = sv[c];
                 double* col = cols + (size_t)(sfirst + s) * m0;
 #pragma unroll
-                for (int k = 0; k < kResRows; ++k) {
+                for (int k = 0; k < RR; ++k) {
                     const int r = jj + 1 + tid + k * nthr;
                     if (r < m0) col[r] -= vr[k] * wc + wr[k] * vc;
                 }
@@ -600,7 +603,7 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
         }
         const double wn = sw[jj + 1], vn = sv[jj + 1];
 #pragma unroll
-        for (int k = 0; k < kResRows; ++k) {
+        for (int k = 0; k < RR; ++k) {
             const int r = jj + 1 + tid + k * nthr;
             if (r < m0) cn[k] -= sv[r] * wn + sw[r] * vn;
         }
@@ -1095,6 +1098,8 @@ struct EighWork {
         *fail = nullptr, *rank = nullptr;
     unsigned* bar = nullptr;
     double *cbuf = nullptr, *ybuf = nullptr;
+    size_t res_smem_cap = 0;
+    int res_grid_want = 0;   // CTAs of the resident tridiagonalisation (0: automatic)
     size_t smem_limit = 0;
     int resident_max = 0;      // largest trailing order the shared-memory resident tridiagonalisation takes
     long long* prof = nullptr;
@@ -1156,9 +1161,14 @@ struct EighWork {
         for (int m = 1; m <= std::min(nmax, kResRows * kSytrdThreads); ++m)
             if (sytrd_smem_resident_bytes(m, grid) <= smem_cap) resident_max = m;
         if (std::getenv("XTBB200_NO_RESIDENT_SYTRD")) resident_max = 0;
-        if (resident_max > 0)
-            XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)sytrd_smem_resident_bytes(std::min(resident_max, nmax), grid)));
+        res_smem_cap = smem_cap;
+        if (resident_max > 0)   // smaller grids than one CTA per SM hold more columns per CTA: allow the full capacity
+        {
+            XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+            XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+            XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        }
+        if (const char* e = std::getenv("XTBB200_RES_GRID")) res_grid_want = std::max(1, std::atoi(e));   // tuning knob
         int occ = 0;
         XTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sytrd_panel, kSytrdThreads, sytrd_smem(nmax, grid)));
         if (occ < 1) throw std::runtime_error("xtb_b200: tridiagonalisation kernel does not fit on an SM");
@@ -1316,8 +1326,25 @@ struct EighWork {
             ra.Gf = Gf; ra.bar = bar;
             void* args[] = {&ra};
             hook(0, 0, 0);
-            XTB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sytrd_smem, dim3(grid), dim3(kSytrdThreads), args,
-                                                       sytrd_smem_resident_bytes(n - jres, grid), st));
+            // Grid of the resident kernel: the grid barrier per column costs more the more CTAs take part, and a mid-size
+            // matrix does not need the shared memory of all SMs: the smallest grid that holds it, but at least kResGridMin
+            int gres = grid;
+            {
+                int gmin = 1;
+                while (gmin < grid && (sytrd_smem_resident_bytes(n - jres, gmin) > res_smem_cap || (n - jres + gmin - 1) / gmin > 96)) ++gmin;   // 96: job slots of the CTA's partial sums
+                gres = std::min(grid, std::max(gmin, res_grid_want > 0 ? res_grid_want : kResGridMin));
+            }
+            // threads: every thread owns kResRows rows of a column; fewer warps make the CTA barriers of a column step cheaper
+            // measured on B200 (tools/res_grid_sweep.sh, sytrd ms): n = 552: 3.09 (1024 threads) -> 2.61 (2 rows x 512);
+            // n = 900: 5.55 -> 4.70; n = 1400: 9.56 (2 x 1024) -> 9.01 (4 x 512); 8 rows per thread lose everywhere
+            int rr = (n - jres > 1024) ? 4 : kResRows, tmin = 256;
+            if (const char* e = std::getenv("XTBB200_RES_RR")) rr = std::atoi(e);            // tuning knobs
+            if (const char* e = std::getenv("XTBB200_RES_TMIN")) tmin = std::atoi(e);
+            while (rr * kSytrdThreads < n - jres) rr *= 2;
+            int tres = kSytrdThreads;
+            while (tres > tmin && rr * (tres / 2) >= n - jres) tres /= 2;
+            void* fn = rr == 2 ? (void*)k_sytrd_smem<2> : rr == 4 ? (void*)k_sytrd_smem<4> : (void*)k_sytrd_smem<8>;
+            XTB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(gres), dim3(tres), args, sytrd_smem_resident_bytes(n - jres, gres), st));
             hook(0, 1, 1);
             ++nl;
             const int nrb = (n - 1 - jres + NB - 1) / NB;    // block reflectors of the resident range
