@@ -188,16 +188,16 @@ struct SytrdArgs {
 
 // barrier over all CTAs of a cooperative grid; bar is zeroed before the launch, target is the caller's running count
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, unsigned& target) {
+    // arrive with a release reduction (cumulative over the CTA's writes ordered before it by the CTA barrier), wait with
+    // acquire loads: one L2 round trip less than fence + atomic + fence
     __syncthreads();
     if (threadIdx.x == 0) {
         target += nblocks;
-        __threadfence();
-        atomicAdd(bar, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         unsigned x;
         do {
             asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(x) : "l"(bar) : "memory");
         } while (x < target);
-        __threadfence();
     }
     __syncthreads();
 }
@@ -224,13 +224,11 @@ __device__ __forceinline__ void grid_sum_barrier(double v, double* red, double* 
         if (lane == 0) {
             part[blockIdx.x] = s;
             target += nblocks;
-            __threadfence();
-            atomicAdd(bar, 1u);
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
             unsigned x;
             do {
                 asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(x) : "l"(bar) : "memory");
             } while (x < target);
-            __threadfence();
         }
     }
     __syncthreads();
