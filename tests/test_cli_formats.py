@@ -100,3 +100,50 @@ def test_cli_alpb_single_point(kat, tmp_path):
     e, x, g = cli.read_turbomole_gradient(str(tmp_path / "gradient"))
     assert abs(e - o.energies["e_total"]) < 1e-7
     assert np.max(np.abs(g - o.get("gradient").reshape(-1, 3))) < 1e-6
+
+
+def test_md_restart_and_trajectory_formats(tmp_path):
+    """mdrestart (src/dynamic.f90:814-844: '-1.0' + 6D22.14 per atom) round trip and the xyz frames of xtb.trj."""
+    rng = np.random.default_rng(0)
+    x, v = rng.normal(size=(5, 3)) * 4.0, rng.normal(size=(5, 3)) * 1e-3
+    x[0, 0], v[1, 2] = 0.0, -0.099999999999999999
+    p = tmp_path / "mdrestart"
+    cli.write_mdrestart(x, v, str(p))
+    lines = p.read_text().splitlines()
+    assert lines[0].strip() == "-1.0" and len(lines) == 6 and all(len(ln) == 132 for ln in lines[1:])
+    assert lines[1][:22] == "  0.00000000000000D+00"
+    assert cli._fortran_d(-0.0377190663280180, 22, 14) == " -0.37719066328018D-01"
+    assert cli._fortran_d(0.99999999999999999, 22, 14) == "  0.10000000000000D+01"
+    x2, v2 = cli.read_mdrestart(str(p))
+    assert np.max(np.abs(x - x2)) < 1e-13 and np.max(np.abs(v - v2)) < 1e-16
+    with open(tmp_path / "xtb.trj", "w") as f:
+        cli.write_trj_frame(f, [8, 1, 1], x[:3], -5.0704513551, 0.0064574201)
+        cli.write_trj_frame(f, [8, 1, 1], x[:3] + 0.1, -5.07, 0.007)
+    text = (tmp_path / "xtb.trj").read_text().splitlines()
+    assert text[0].strip() == "3" and text[1].startswith(" energy: -5.070451355100 gnorm: 0.006457420100 xtb:")
+    assert len(text) == 10 and text[2].split()[0] == "O"
+    z, xyz = cli.read_xyz("\n".join(text[:5]) + "\n")
+    assert list(z) == [8, 1, 1] and np.max(np.abs(xyz - x[:3])) < 1e-12
+
+
+@pytest.mark.gpu
+def test_cli_md_run(kat, tmp_path):
+    """`xtb caffeine.xyz --md` with a short $md block: trajectory frames, mdrestart, xtbmdok; restart continues."""
+    s = kat["caffeine"]
+    (tmp_path / "caffeine.xyz").write_text("%d\n\n" % len(s["numbers"]) + "".join(
+        "%-2s %20.14f %20.14f %20.14f\n" % (cli.SYMBOLS[z - 1], r[0], r[1], r[2]) for z, r in zip(s["numbers"], s["xyz"] / cli.AATOAU)))
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    cmd = [sys.executable, "-m", "xtb_b200", "caffeine.xyz", "--md", "--time", "0.04", "--dump", "16", "--alpb", "water"]
+    out = subprocess.run(cmd, cwd=tmp_path, env=env, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "normal exit of md()" in out.stdout and "SHAKE on. # bonds  : 25" in out.stdout
+    assert (tmp_path / "xtbmdok").exists()
+    frames = (tmp_path / "xtb.trj").read_text().splitlines()
+    assert len(frames) == 3 * 26                                  # steps 1, 5, 9 of 10
+    e = [float(frames[26 * k + 1].split()[1]) for k in range(3)]
+    assert all(-42.3 < x < -42.0 for x in e)
+    x1, v1 = cli.read_mdrestart(str(tmp_path / "mdrestart"))
+    out = subprocess.run(cmd + ["--restart", "--time", "0.008"], cwd=tmp_path, env=env, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    x2, v2 = cli.read_mdrestart(str(tmp_path / "mdrestart"))
+    assert 1e-4 < np.max(np.abs(x2 - x1)) < 0.5

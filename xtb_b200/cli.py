@@ -5,8 +5,12 @@ Covers what the single point path of the reference's driver needs (src/prog/main
 readers for xyz and Turbomole coord files (the reference delegates them to mctc-lib, which is not part of its tree; the
 formats are the published ones), the run-type flags of a single point with gradient, and the result files `energy`,
 `gradient` (src/io/writer/turbomole.f90:32-123), `charges` (src/main/property.F90:189-192, one f14.8 per atom) and `wbo`
-(src/main/property.F90:228-231,869-881, pairs above 0.1).  Everything else the reference's CLI offers (optimisation, MD,
-hessian, solvation, other Hamiltonians) is refused with an error instead of being ignored.
+(src/main/property.F90:228-231,869-881, pairs above 0.1); implicit solvation (`--alpb / --gbsa SOLVENT`); and molecular
+dynamics (`--md`, the $md block's time / step / temp / dump / shake / hmass / nvt as flags): trajectory `xtb.trj` (xyz frames
+with the energy in the comment line, src/dynamic.f90:536-545, src/io/writer.f90:64-75), `mdrestart`
+(src/dynamic.f90:814-827), the screen table (src/dynamic.f90:522-533) and the `xtbmdok` marker.  Everything else the
+reference's CLI offers (optimisation, hessian, other Hamiltonians, metadynamics) is refused with an error instead of being
+ignored.
 """
 import argparse
 import sys
@@ -130,7 +134,106 @@ def write_wbo(wbo, path="wbo", thr=0.1):
                     f.write("%12d%12d   %.15f\n" % (j + 1, i + 1, wbo[j, i]))
 
 
-UNSUPPORTED = ["--opt", "--ohess", "--hess", "--md", "--omd", "--metadyn", "--cosmo", "--gff", "--gfnff",
+def _fortran_d(x, width, digits):
+    """Fortran Dw.d: mantissa in [0.1, 1), e.g. 0.37719066328018D+00."""
+    if x == 0.0:
+        return ("0." + "0" * digits + "D+00").rjust(width)
+    e = int(np.floor(np.log10(abs(x)))) + 1
+    ms = "%.*f" % (digits, abs(x) / 10.0 ** e)
+    if ms.startswith("1."):      # rounded up to 1.0
+        e += 1
+        ms = "%.*f" % (digits, abs(x) / 10.0 ** e)
+    return (("-" if x < 0 else "") + ms + "D%+03d" % e).rjust(width)
+
+
+def write_trj_frame(f, numbers, xyz_bohr, energy, gnorm):
+    """One xyz frame of xtb.trj (positions in Angstrom; comment line as writeMolecule builds it, src/io/writer.f90:64-75)."""
+    f.write("%d\n energy: %s gnorm: %s xtb: b200\n" % (len(numbers), ("%20.12f" % energy).strip(), ("%20.12f" % gnorm).strip()))
+    for z, r in zip(numbers, np.asarray(xyz_bohr) / AATOAU):
+        f.write("%-4s %20.14f %20.14f %20.14f\n" % (SYMBOLS[z - 1], r[0], r[1], r[2]))
+    f.flush()
+
+
+def write_mdrestart(xyz, velo, path="mdrestart"):
+    """src/dynamic.f90:814-827: '-1.0', then positions and velocities (atomic units) as 6D22.14 per atom."""
+    with open(path, "w") as f:
+        f.write(" -1.0\n")
+        for r, v in zip(xyz, velo):
+            f.write("".join(_fortran_d(x, 22, 14) for x in (*r, *v)) + "\n")
+
+
+def read_mdrestart(path="mdrestart"):
+    """src/dynamic.f90:829-844."""
+    with open(path) as f:
+        lines = f.read().splitlines()[1:]
+    vals = np.array([[float(ln[22 * k:22 * (k + 1)].replace("D", "E").replace("d", "e")) for k in range(6)] for ln in lines if ln.strip()])
+    return vals[:, :3].copy(), vals[:, 3:].copy()
+
+
+def run_md(args, numbers, xyz, out=sys.stdout):
+    """The MD run type (src/dynamic.f90:140-702 through xtbb200_mdInit / xtbb200_mdRun): one replica, frames every
+    --dump fs starting with the first step, screen line every 200 steps, mdrestart and xtbmdok at the end."""
+    import os
+
+    import xtb_b200
+    b = xtb_b200.BatchCalculator([numbers], charges=[args.chrg], uhf=[args.uhf], accuracy=args.acc, etemp=args.etemp,
+                                 maxiter=args.iterations)
+    if args.alpb:
+        b.set_solvent(args.alpb, model="alpb")
+    elif args.gbsa:
+        b.set_solvent(args.gbsa, model="gbsa")
+    velo = None
+    if args.restart:
+        xyz, velo = read_mdrestart()
+    if os.path.exists("xtbmdok"):
+        os.remove("xtbmdok")
+    ncons = b.md_init(xyz, tstep_fs=args.step, temperature=args.temp, thermostat=not args.nve, shake=args.shake, hmass=args.hmass,
+                      velocities=velo, seed=args.seed)
+    nmax = int(args.time * 1000.0 / args.step)
+    dumpstep = max(1, int(args.dump / args.step))
+    if not args.silent:
+        out.write(" MD time /ps        :%8.2f\n dt /fs             :%8.2f\n temperature /K     :%8.2f\n max steps          :%6d\n"
+                  % (args.time, args.step, args.temp, nmax))
+        out.write(" dumpstep(trj) /fs  :%8.2f%6d\n" % (args.dump, dumpstep))
+        if args.hmass > 0:
+            out.write(" H atoms mass (amu) :%6d\n" % args.hmass)
+        out.write(" SHAKE %s\n" % ("on. # bonds  : %d all: %s" % (ncons, args.shake == 2) if args.shake else "off"))
+        if not args.nve:
+            out.write(" Berendsen THERMOSTAT on\n")
+        out.write("   step   time/ps    <Epot>      Ekin   <T>   T     Etot\n")
+    k, epav, tav, blown = 0, 0.0, 0.0, False
+    with open("xtb.trj", "w") as trj:
+        while k < nmax and not blown:
+            frame_xyz = b.array("xyz").reshape(-1, 3)          # geometry of step k + 1: dumped with its energy
+            chunk = min(dumpstep, nmax - k)
+            r = b.md_run(1)
+            blown = r["steps"] < 1
+            if r["steps"]:
+                write_trj_frame(trj, numbers, frame_xyz, r["epot"][0, 0], b.result(0)["gnorm"])
+                rest = b.md_run(chunk - 1) if chunk > 1 else dict(steps=0, epot=np.zeros((0, 1)), ekin=np.zeros((0, 1)),
+                                                                     temperature=np.zeros((0, 1)))
+                blown = rest["steps"] < chunk - 1
+                for part in (r, rest):
+                    for i in range(part["steps"]):
+                        k += 1
+                        epav += part["epot"][i, 0]
+                        tav += part["temperature"][i, 0]
+                        if not args.silent and (k == 1 or k % 200 == 0):
+                            out.write("%7d%8.2f%13.5f%9.4f%6.0f%6.0f%12.5f\n" % (
+                                k, 0.001 * k * args.step, epav / k, part["ekin"][i, 0], tav / k, part["temperature"][i, 0],
+                                part["epot"][i, 0] + part["ekin"][i, 0]))
+    write_mdrestart(b.array("xyz").reshape(-1, 3), b.array("velocities").reshape(-1, 3))
+    if blown:
+        print("xtb_b200: MD is unstable, emergency exit", file=sys.stderr)
+        return 1
+    if not args.silent:
+        out.write(" average properties\n Epot               :%16.8f\n T                  :%16.8f\n" % (epav / max(k, 1), tav / max(k, 1)))
+        out.write("normal exit of md()\n")
+    open("xtbmdok", "w").close()
+    return 0
+
+
+UNSUPPORTED = ["--opt", "--ohess", "--hess", "--omd", "--metadyn", "--cosmo", "--gff", "--gfnff",
                "--vipea", "--vip", "--vea", "--path", "--modef", "--scan", "--esp", "--stm", "--tblite", "--cpcmx", "--oniom",
                "--dipro", "--siman", "--screen", "--bhess", "--vfukui", "--vomega", "--pcem"]
 
@@ -153,6 +256,16 @@ def main(argv=None):
     ap.add_argument("--iterations", type=int, default=250)
     ap.add_argument("--alpb", metavar="SOLVENT", default=None, help="ALPB implicit solvation (src/prog/argparser / set_gbsa)")
     ap.add_argument("-g", "--gbsa", metavar="SOLVENT", default=None, help="GBSA implicit solvation")
+    ap.add_argument("--md", action="store_true", help="molecular dynamics (defaults of the reference's $md block)")
+    ap.add_argument("--time", type=float, default=50.0, help="MD: simulation time / ps")
+    ap.add_argument("--step", type=float, default=4.0, help="MD: time step / fs")
+    ap.add_argument("--temp", type=float, default=298.15, help="MD: thermostat temperature / K")
+    ap.add_argument("--dump", type=float, default=50.0, help="MD: trajectory dump interval / fs")
+    ap.add_argument("--shake", type=int, default=2, choices=[0, 1, 2], help="MD: 0 off, 1 X-H bonds, 2 all bonds")
+    ap.add_argument("--hmass", type=int, default=4, help="MD: hydrogen mass / amu (0: physical)")
+    ap.add_argument("--nve", action="store_true", help="MD: no thermostat (nvt=false)")
+    ap.add_argument("--seed", type=int, default=1, help="MD: seed of the start velocities' signs")
+    ap.add_argument("--restart", action="store_true", help="MD: positions and velocities from ./mdrestart")
     ap.add_argument("-v", "--verbose", action="store_true")
     ap.add_argument("--silent", action="store_true")
     args = ap.parse_args(argv)
@@ -161,15 +274,17 @@ def main(argv=None):
         return 2
     import xtb_b200
     numbers, xyz = read_geometry(args.geometry)
+    if args.alpb and args.gbsa:
+        print("xtb_b200: --alpb and --gbsa are mutually exclusive", file=sys.stderr)
+        return 2
+    if args.md:
+        return run_md(args, numbers, xyz)
     t0 = time.perf_counter()
     calc = xtb_b200.Calculator(xtb_b200.Param.GFN2xTB, numbers, xyz, charge=args.chrg, uhf=args.uhf)
     calc.set_verbosity(0 if args.silent else (2 if args.verbose else 1))
     calc.set_accuracy(args.acc)
     calc.set_electronic_temperature(args.etemp)
     calc.set_max_iterations(args.iterations)
-    if args.alpb and args.gbsa:
-        print("xtb_b200: --alpb and --gbsa are mutually exclusive", file=sys.stderr)
-        return 2
     if args.alpb:
         calc.set_solvent(args.alpb, model="alpb")
     elif args.gbsa:
