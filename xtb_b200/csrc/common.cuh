@@ -118,6 +118,18 @@ __device__ __forceinline__ double warp_max(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// Atom loops of the O(N^2) pair kernels: kAS consecutive lanes share one atom i and stride over its partners j, the
+// partial sums are combined by xor shuffles in a fixed order (bit-reproducible).  A single 200-atom molecule then spreads
+// over 8x more threads than with one thread per atom; ensembles lose nothing (their atoms already fill the GPU).
+// No thread may leave such a kernel before the shuffles: inactive groups run empty loops.
+constexpr int kAS = 8;
+__device__ __forceinline__ double slice_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
 // deterministic block reduction (sum); result valid in all threads. red: >= 32 doubles of shared memory
 __device__ __forceinline__ double block_sum(double v, double* red) {
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;

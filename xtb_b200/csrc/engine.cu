@@ -717,13 +717,13 @@ int Batch::singlepoint(bool restart) {
     cudaEventRecord(ev[0], st);
     KL(K_SETUP, k_reset_state<<<(nmol + 127) / 128, 128, 0, st>>>(d, (restart && I.have_wfn) ? 1 : 0));
     // ---- geometry dependent setup
-    KL(K_SETUP, k_cn<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
+    KL(K_SETUP, k_cn<<<grid2((long long)kAS * s.max_nat, B, nmol), B, 0, st>>>(d));
     const int mx = std::max(s.max_nat, std::max(s.max_nsh, s.max_ndim));
     KL(K_SETUP, k_cn_dependent<<<grid2(mx, B, nmol), B, 0, st>>>(d));
     KL(K_SETUP, k_gab<<<grid2((long long)s.max_nat * s.max_nat, 256, nmol), 256, 0, st>>>(d));
     KL(K_SETUP, k_jmat<<<grid2((long long)s.max_nsh * s.max_nsh, 256, nmol), 256, 0, st>>>(d));
     KL(K_SETUP, k_dispmat<<<grid2((long long)s.max_ndim * s.max_ndim, 256, nmol), 256, 0, st>>>(d));
-    KL(K_SETUP, k_repulsion<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
+    KL(K_SETUP, k_repulsion<<<grid2((long long)kAS * s.max_nat, B, nmol), B, 0, st>>>(d));
     if (d.pc0) KL(K_SETUP, k_pcem_pot<<<grid2(s.max_nsh, B, nmol), B, 0, st>>>(d));
     if (d.solv_on) {   // solvation%update, src/scf_module.F90:299-320 (every rank of a split system computes all of it)
         XTB_CUDA_CHECK(cudaMemsetAsync(d.sv_dsdrt, 0, 3 * (size_t)s.tot_nn * sizeof(double), st));
@@ -909,7 +909,7 @@ int Batch::singlepoint(bool restart) {
         KL(K_POP, k_pop_rows<<<grid2((long long)s.max_nao * 32, 256, nmol), 256, 0, st>>>(d));
         KL(K_POP, k_pop_atoms<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
         KL(K_ENERGY, k_es_rows<<<grid2(8LL * s.max_nsh, 256, nmol), 256, 0, st>>>(d));
-        KL(K_ENERGY, k_aes_rows<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+        KL(K_ENERGY, k_aes_rows<<<grid2((long long)kAS * s.max_nat, 64, nmol), 64, 0, st>>>(d));
         KL(K_D4SCC, k_d4_zeta<<<grid2(s.max_ndim, B, nmol), B, 0, st>>>(d, 1));
         KL(K_D4SCC, k_d4_matvec<<<grid2(8LL * s.max_ndim, 256, nmol), 256, 0, st>>>(d));
         if (d.solv_on) KL(K_SOLV_SCC, k_solv_matvec<<<dim3((s.max_nat + 31) / 32, nmol), 256, 0, st>>>(d, 1));
@@ -933,11 +933,11 @@ int Batch::singlepoint(bool restart) {
         XTB_CUDA_CHECK(cudaMemsetAsync(d.gpair, 0, 4 * (size_t)I.pair_total * sizeof(double), st));
     }
     KL(K_GRAD_H0, k_grad_h0<<<pair_grid, kIntWarps * 32, 0, st>>>(d));
-    KL(K_GRAD_H0, k_grad_h0_collect<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
-    KL(K_GRAD_AES, k_grad_aes<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+    KL(K_GRAD_H0, k_grad_h0_collect<<<grid2((long long)kAS * s.max_nat, 64, nmol), 64, 0, st>>>(d));
+    KL(K_GRAD_AES, k_grad_aes<<<grid2((long long)kAS * s.max_nat, 64, nmol), 64, 0, st>>>(d));
     KL(K_GRAD_D4, k_d4_weights<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
     KL(K_GRAD_D4, k_d4_c6<<<grid2((long long)s.max_nat * s.max_nat, 128, nmol), 128, 0, st>>>(d));
-    KL(K_GRAD_D4, k_grad_pairs<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+    KL(K_GRAD_D4, k_grad_pairs<<<grid2((long long)kAS * s.max_nat, 64, nmol), 64, 0, st>>>(d));
     KL(K_GRAD_ATM, k_grad_atm<<<dim3(s.max_nat, nmol), 128, (size_t)s.max_nat * sizeof(double), st>>>(d));
     if (d.solv_on) {   // solvation%addGradient + getEnergyParts with the mixed charges, src/scf_module.F90:759-777
         KL(K_SOLV_GRAD, k_solv_matvec<<<dim3((s.max_nat + 31) / 32, nmol), 256, 0, st>>>(d, -1));
@@ -959,7 +959,7 @@ int Batch::singlepoint(bool restart) {
         I.prof_end(K_COMM, st);
         nl += 2;
     }
-    KL(K_GRAD_MISC, k_grad_cn<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
+    KL(K_GRAD_MISC, k_grad_cn<<<grid2((long long)kAS * s.max_nat, 64, nmol), 64, 0, st>>>(d));
     if (R > 1) {
         I.prof_begin(K_COMM, st);
         I.allreduce(d.grad, 3 * (size_t)na_tot, st);

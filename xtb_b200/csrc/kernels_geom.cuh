@@ -22,12 +22,13 @@ __device__ __forceinline__ double en_den(double eni, double enj) {  // k4*exp(-(
 // CN(gfn), CN(cov) [coordinationnumber.F90:351-479], ncoord_d4 / ncoord_erf [src/disp/ncoord.f90:469-617]
 __global__ void k_cn(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nat) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, sl = t % kAS;
+    const bool active = t / kAS < m.nat;
+    const int i = active ? t / kAS : 0;
     const AtomPar ai = d.atoms[m.at0 + i];
     const double* xi = d.xyz + 3 * (m.at0 + i);
     double cg = 0, cc = 0, c4 = 0, ce = 0;
-    for (int j = 0; j < m.nat; ++j) {
+    for (int j = sl; j < (active ? m.nat : 0); j += kAS) {
         if (j == i) continue;
         const AtomPar& aj = d.atoms[m.at0 + j];
         const double* xj = d.xyz + 3 * (m.at0 + j);
@@ -45,6 +46,8 @@ __global__ void k_cn(Dev d) {
         ce += ec;
         c4 += en_den(ai.nc_en, aj.nc_en) * ec;
     }
+    cg = slice_sum(cg); cc = slice_sum(cc); c4 = slice_sum(c4); ce = slice_sum(ce);
+    if (!active || sl) return;
     d.cn[m.at0 + i] = cg; d.cn_cov[m.at0 + i] = cc; d.cn_d4[m.at0 + i] = c4; d.cn_erf[m.at0 + i] = ce;
 }
 
@@ -172,12 +175,13 @@ __global__ void k_dispmat(Dev d) {
 // classical repulsion energy + gradient, src/xtb/repulsion.F90:41-158 ; thread per atom
 __global__ void k_repulsion(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nat) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, sl = t % kAS;
+    const bool active = t / kAS < m.nat;
+    const int i = active ? t / kAS : 0;
     const AtomPar ai = d.atoms[m.at0 + i];
     const double* xi = d.xyz + 3 * (m.at0 + i);
     double e = 0, g[3] = {0, 0, 0};
-    for (int j = 0; j < m.nat; ++j) {
+    for (int j = sl; j < (active ? m.nat : 0); j += kAS) {
         if (j == i) continue;
         const AtomPar& aj = d.atoms[m.at0 + j];
         const double* xj = d.xyz + 3 * (m.at0 + j);
@@ -194,6 +198,9 @@ __global__ void k_repulsion(Dev d) {
         for (int k = 0; k < 3; ++k) g[k] += f * rij[k];
         e += 0.5 * dE;
     }
+    e = slice_sum(e);
+    for (int k = 0; k < 3; ++k) g[k] = slice_sum(g[k]);
+    if (!active || sl) return;
     d.e_atom[4 * (m.at0 + i) + 0] = e;
     for (int k = 0; k < 3; ++k) d.grad[3 * (m.at0 + i) + k] = g[k];  // first gradient contribution: overwrite
 }

@@ -219,15 +219,16 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
 // (hamiltonian.F90:741-771); thread per atom
 __global__ void k_grad_h0_collect(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nat) return;
+    const int tg = blockIdx.x * blockDim.x + threadIdx.x, sl = tg % kAS;
+    const bool active = tg / kAS < m.nat;
+    const int i = active ? tg / kAS : 0;
     const AtomPar& a = d.atoms[m.at0 + i];
     const double* gp = d.gpair + 4 * d.pair0[blockIdx.y];
     double g[3] = {0, 0, 0}, dh = 0;
-    for (int s = a.sh0; s < a.sh0 + a.nsh; ++s) {
+    for (int s = a.sh0; s < (active ? a.sh0 + a.nsh : 0); ++s) {
         const ShellPar& sp = d.shells[m.sh0 + s];
         const double dse = -sp.kcn;
-        for (int t = 0; t < m.nsh; ++t) {
+        for (int t = sl; t < m.nsh; t += kAS) {
             if (t >= a.sh0 && t < a.sh0 + a.nsh) continue;
             const int hi = s > t ? s : t, lo = s > t ? t : s;
             const double* o = gp + 4 * ((long long)hi * (hi + 1) / 2 + lo);
@@ -235,12 +236,15 @@ __global__ void k_grad_h0_collect(Dev d) {
             g[0] += sgn * o[0]; g[1] += sgn * o[1]; g[2] += sgn * o[2];
             dh += o[3] * dse;
         }
-        if (d.srank == 0)   // on-site term: counted once when the shell pairs are split over ranks
+        if (d.srank == 0 && sl == 0)   // on-site term: counted once when the shell pairs are split over ranks
             for (int k = 0; k < c_nsph[sp.l]; ++k) {
                 const long long ao = sp.ao0 + k;
                 dh += d.P[m.mat0 + ao + (long long)m.nao * ao] * dse * kEVtoAU;
             }
     }
+    dh = slice_sum(dh);
+    for (int k = 0; k < 3; ++k) g[k] = slice_sum(g[k]);
+    if (!active || sl) return;
     for (int k = 0; k < 3; ++k) d.grad[3 * (m.at0 + i) + k] += g[k];
     d.dhdcn[m.at0 + i] = dh;
 }
@@ -248,8 +252,9 @@ __global__ void k_grad_h0_collect(Dev d) {
 // anisotropic electrostatics gradient (aniso_grad, aespot.F90:1070-1165) + dradcn factor; thread per atom
 __global__ void k_grad_aes(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nat || !shard_owns_atom(d, i)) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, sl = t % kAS;
+    const bool active = t / kAS < m.nat && shard_owns_atom(d, t / kAS);
+    const int i = active ? t / kAS : 0;
     const double* xyz = d.xyz + 3 * m.at0;
     const double* q = d.q + m.at0;
     const double* dipm = d.dipm + 3 * m.at0;
@@ -260,7 +265,7 @@ __global__ void k_grad_aes(Dev d) {
     double qp1[6];
     for (int k = 0; k < 6; ++k) qp1[k] = qp[6 * i + k];
     double gi[3] = {0, 0, 0}, tmp2 = 0;
-    for (int j = 0; j < m.nat; ++j) {
+    for (int j = sl; j < (active ? m.nat : 0); j += kAS) {
         if (j == i) continue;
         const double rij[3] = {xyz[3 * j] - xyz[3 * i], xyz[3 * j + 1] - xyz[3 * i + 1], xyz[3 * j + 2] - xyz[3 * i + 2]};
         const double r2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
@@ -310,6 +315,9 @@ __global__ void k_grad_aes(Dev d) {
         tmp2 += ed * 3.0 * g3 * (damp1 / rab) * pow(rab * rabi, 3.0);
         tmp2 += (eq + edd) * 4.0 * g5 * (damp2 / rab) * pow(rab * rabi, 4.0);
     }
+    tmp2 = slice_sum(tmp2);
+    for (int k = 0; k < 3; ++k) gi[k] = slice_sum(gi[k]);
+    if (!active || sl) return;
     tmp2 = 3.0 * tmp2;
     const AtomPar& a = d.atoms[m.at0 + i];
     const double t1 = exp(-4.0 * (d.cn[m.at0 + i] - a.valcn - 1.2));
@@ -387,12 +395,13 @@ __global__ void k_d4_c6(Dev d) {
 // (getCoulombDerivsCluster + gemv); thread per atom, loops over partners
 __global__ void k_grad_pairs(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nat || !shard_owns_atom(d, i)) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, sl = t % kAS;
+    const bool active = t / kAS < m.nat && shard_owns_atom(d, t / kAS);
+    const int i = active ? t / kAS : 0;
     const AtomPar ai = d.atoms[m.at0 + i];
     const double* xi = d.xyz + 3 * (m.at0 + i);
     double g[3] = {0, 0, 0}, dE = 0;
-    for (int j = 0; j < m.nat; ++j) {
+    for (int j = sl; j < (active ? m.nat : 0); j += kAS) {
         if (j == i) continue;
         const AtomPar& aj = d.atoms[m.at0 + j];
         const double* xj = d.xyz + 3 * (m.at0 + j);
@@ -423,6 +432,9 @@ __global__ void k_grad_pairs(Dev d) {
         // -dG*q_i*q_j with vec = -rij :  -(-(-rij) * f) = -rij*f
         for (int k = 0; k < 3; ++k) g[k] -= rij[k] * acc;
     }
+    dE = slice_sum(dE);
+    for (int k = 0; k < 3; ++k) g[k] = slice_sum(g[k]);
+    if (!active || sl) return;
     for (int k = 0; k < 3; ++k) d.grad[3 * (m.at0 + i) + k] += g[k];
     d.dEdcn[m.at0 + i] = dE;
 }
@@ -543,14 +555,15 @@ __global__ void __launch_bounds__(128) k_grad_atm(Dev d) {
 // and the covalent CN (v = D4 dE/dCN); replaces the dense gemv with dcndr (scf_module.F90:726, dftd4.F90:1723)
 __global__ void k_grad_cn(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nat || !shard_owns_atom(d, i)) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, sl = t % kAS;
+    const bool active = t / kAS < m.nat && shard_owns_atom(d, t / kAS);
+    const int i = active ? t / kAS : 0;
     const AtomPar ai = d.atoms[m.at0 + i];
     const double* xi = d.xyz + 3 * (m.at0 + i);
     const double vi = d.dhdcn[m.at0 + i] + d.w_aes[m.at0 + i], wi = d.dEdcn[m.at0 + i];
     const double sqrtpi = sqrt(kPi);
     double g[3] = {0, 0, 0};
-    for (int j = 0; j < m.nat; ++j) {
+    for (int j = sl; j < (active ? m.nat : 0); j += kAS) {
         if (j == i) continue;
         const AtomPar& aj = d.atoms[m.at0 + j];
         const double* xj = d.xyz + 3 * (m.at0 + j);
@@ -564,6 +577,8 @@ __global__ void k_grad_cn(Dev d) {
         const double f = (dgfn * (vi + vj) + dcov * (wi + wj)) / r1;
         for (int k = 0; k < 3; ++k) g[k] += f * rij[k];
     }
+    for (int k = 0; k < 3; ++k) g[k] = slice_sum(g[k]);
+    if (!active || sl) return;
     for (int k = 0; k < 3; ++k) d.grad[3 * (m.at0 + i) + k] += g[k];
 }
 

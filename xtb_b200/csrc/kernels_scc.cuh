@@ -443,8 +443,9 @@ __global__ void __launch_bounds__(32 * kMvSlices) k_es_rows(Dev d) {
 __global__ void k_aes_rows(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     if (d.st[blockIdx.y].done) return;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nat) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, sl = t % kAS;
+    const bool active = t / kAS < m.nat;
+    const int i = active ? t / kAS : 0;
     const int idx[3][3] = {{0, 1, 3}, {1, 2, 4}, {3, 4, 5}};
     const double* xyz = d.xyz + 3 * m.at0;
     const double* q = d.q_out + m.at0;
@@ -455,7 +456,7 @@ __global__ void k_aes_rows(Dev d) {
     double qp1[6];
     for (int k = 0; k < 6; ++k) qp1[k] = qp[6 * i + k];
     double e01 = 0, e02 = 0, e11 = 0;
-    for (int j = 0; j < i; ++j) {
+    for (int j = sl; j < (active ? i : 0); j += kAS) {
         const double rij[3] = {xyz[3 * j] - xyz[3 * i], xyz[3 * j + 1] - xyz[3 * i + 1], xyz[3 * j + 2] - xyz[3 * i + 2]};
         const double r2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
         double ed = 0, eq = 0, edd = 0;
@@ -476,6 +477,8 @@ __global__ void k_aes_rows(Dev d) {
         const double g3 = d.gab3[m.nn0 + j + (long long)m.nat * i], g5 = d.gab5[m.nn0 + j + (long long)m.nat * i];
         e01 += ed * g3; e02 += eq * g5; e11 += edd * g5;
     }
+    e01 = slice_sum(e01); e02 = slice_sum(e02); e11 = slice_sum(e11);
+    if (!active || sl) return;
     const AtomPar& a = d.atoms[m.at0 + i];
     double tt = dp1[0] * dp1[0] + dp1[1] * dp1[1] + dp1[2] * dp1[2], tt3 = 0;
 #pragma unroll
