@@ -637,25 +637,36 @@ __global__ void k_bt_formv(const double* __restrict__ A, int n, int jb, int kb, 
     Vb[t] = r < piv ? 0.0 : (r == piv ? 1.0 : A[r + (long long)n * (jb + k)]);
 }
 // T factors of all blocks (one CTA per block): T(0:i,i) = -tau_i T(0:i,0:i) G(0:i,i), T(i,i) = tau_i
-__global__ void __launch_bounds__(NB) k_bt_tfactor(const double* __restrict__ Gall, const double* __restrict__ tau, int n,
-                                                   double* __restrict__ Tall) {
+// Row r of T depends on nothing but itself and G; kTfParts threads share a row and split the k range of its dot products
+// (the column-by-column recurrence is serial in i: 128 steps of <= 128 / kTfParts terms instead of <= 128).
+constexpr int kTfParts = 8;
+__global__ void __launch_bounds__(NB * kTfParts) k_bt_tfactor(const double* __restrict__ Gall, const double* __restrict__ tau, int n,
+                                                              double* __restrict__ Tall) {
     extern __shared__ double sm_dyn[];
-    double (*T)[NB + 1] = (double (*)[NB + 1])sm_dyn;
-    const int b = blockIdx.x, jb = b * NB, kb = min(NB, n - 1 - jb), r = threadIdx.x;
+    double (*T)[NB + 1] = (double (*)[NB + 1])sm_dyn;                   // NB x (NB + 1)
+    double (*part)[NB] = (double (*)[NB])(sm_dyn + NB * (NB + 1));     // kTfParts x NB
+    const int b = blockIdx.x, jb = b * NB, kb = min(NB, n - 1 - jb), r = threadIdx.x % NB, pt = threadIdx.x / NB;
     const double* G = Gall + (long long)b * NB * NB;
-    for (int c = 0; c < NB; ++c) T[r][c] = 0.0;
+    for (int c = pt; c < NB; c += kTfParts) T[r][c] = 0.0;
     __syncthreads();
     for (int i = 0; i < kb; ++i) {
-        const double ti = tau[jb + i];
-        if (r < i) {
-            double s = 0.0;
-            for (int k = r; k < i; ++k) s += T[r][k] * G[k + NB * i];
-            T[r][i] = -ti * s;
-        } else if (r == i) T[r][i] = ti;
+        double s = 0.0;
+        if (r < i)
+            for (int k = r + pt; k < i; k += kTfParts) s += T[r][k] * G[k + NB * i];
+        part[pt][r] = s;
+        __syncthreads();
+        if (pt == 0) {
+            if (r < i) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < kTfParts; ++q) t += part[q][r];
+                T[r][i] = -tau[jb + i] * t;
+            } else if (r == i) T[r][i] = tau[jb + i];
+        }
         __syncthreads();
     }
     double* To = Tall + (long long)b * NB * NB;
-    for (int c = 0; c < NB; ++c) To[r + NB * c] = T[r][c];
+    for (int c = pt; c < NB; c += kTfParts) To[r + NB * c] = T[r][c];
 }
 // W = sum_z Wz (partial products of the K-split W = V^T Z); thread per element
 __global__ void k_bt_sum(double* __restrict__ Wz, long long zstride, int nz, long long count) {
@@ -1153,7 +1164,7 @@ struct EighWork {
                                             (int)std::min(n * 24 + 16, smem_limit)));
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_secular, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 16)));
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 8)));
-        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_bt_tfactor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NB * (NB + 1) * 8)));
+        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_bt_tfactor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((NB * (NB + 1) + kTfParts * NB) * 8)));
         resident_max = 0;
         const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin - 1024;   // static shared memory of the kernel
         for (int m = 1; m <= std::min(nmax, kResRows * kSytrdThreads); ++m)
@@ -1415,7 +1426,7 @@ struct EighWork {
         const int nrefl = n - 1;   // reflectors 0 .. n-2 (the last one is the identity)
         if (nrefl > 0) {
             const int nbb = (nrefl + NB - 1) / NB;
-            k_bt_tfactor<<<nbb, NB, NB * (NB + 1) * sizeof(double), st>>>(Gf, tau, n, Tf);
+            k_bt_tfactor<<<nbb, NB * kTfParts, (NB * (NB + 1) + kTfParts * NB) * sizeof(double), st>>>(Gf, tau, n, Tf);
             ++nl;
             for (int b = nbb - 1; b >= 0; --b) {
                 const int jb = b * NB, kb = std::min(NB, nrefl - jb), r0 = jb + 1, mr = n - r0;
