@@ -46,6 +46,12 @@ int xtbb200_setWavefunction(xtbb200_TBatch batch, const double* qsh, const doubl
 int xtbb200_setExternalCharges(xtbb200_TBatch batch, const int* npc, const int* numbers, const double* charges,
                                const double* positions);
 
+/* Host-side query of the solvation model xtbb200_setSolvent / xtb_setSolvent would build (no GPU needed): out8 = dielectric
+ * constant, keps = (1/eps - 1) / (1 + alpha beta), ALPB alpha * beta (0 for GBSA), free energy shift incl. the reference
+ * state [Eh], Born radius scaling c1, Born offset [bohr], probe radius [bohr], 1.0 if the set has a hydrogen bond term.
+ * Returns -1 (xtbb200_lastError: "solvent: '...' is not parametrized") for solvents without an internal GFN2 set. */
+int xtbb200_solventParameters(const char* solvent, int alpb, int kernel, int state, double temperature, double* out8);
+
 /* Molecular dynamics of every molecule of the batch as independent replicas (reference: src/dynamic.f90:140-702 md,
  * src/shake_module.f90 init_shake / do_shake, src/rmrottr.f90): leap-frog with Berendsen thermostat (thermostat != 0,
  * tau = 500 fs), SHAKE (shake_mode 0 off, 1 X-H bonds, 2 all bonds with a Wiberg bond order above 0.5; xtb's default is 2),

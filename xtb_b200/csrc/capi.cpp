@@ -19,6 +19,7 @@
 #include "../../include/xtb.h"
 #include "../../include/xtb_b200.h"
 #include "engine.h"
+#include "solvation.h"
 
 using xtbb200::Batch;
 using xtbb200::MolResult;
@@ -617,6 +618,16 @@ int xtbb200_setSolvent(xtbb200_TBatch batch, const char* solvent, int alpb, int 
     if (!batch) throw std::runtime_error("batch is not allocated");
     if (!solvent) { batch->b->release_solvent(); return 0; }
     batch->b->set_solvent(solvent, alpb != 0, kernel, state, temperature, ion_strength, ion_rad);
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_solventParameters(const char* solvent, int alpb, int kernel, int state, double temperature, double* out8) {
+    XTBB_TRY
+    if (!solvent || !out8) throw std::runtime_error("solvent name and output buffer are required");
+    if (kernel != 1 && kernel != 2) throw std::runtime_error("solvation: kernel must be 1 (Still) or 2 (P16)");
+    const xtbb200::SolvModel sm = xtbb200::make_solv_model(solvent, alpb != 0, kernel, state, temperature, 0.0, 0.0);
+    out8[0] = sm.eps; out8[1] = sm.keps; out8[2] = sm.alpbet; out8[3] = sm.gshift; out8[4] = sm.c1; out8[5] = sm.born_offset;
+    out8[6] = sm.probe; out8[7] = sm.any_hb ? 1.0 : 0.0;
     return 0;
     XTBB_CATCH(-1)
 }
