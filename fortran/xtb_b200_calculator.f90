@@ -14,6 +14,7 @@ module xtb_b200_calculator
    use xtb_type_environment, only : TEnvironment
    use xtb_type_molecule, only : TMolecule
    use xtb_type_restart, only : TRestart
+   use xtb_solv_input, only : TSolvInput
    implicit none
    private
 
@@ -28,6 +29,8 @@ module xtb_b200_calculator
    contains
       procedure :: singlepoint
       procedure :: writeInfo
+      procedure :: setSolvent
+      procedure :: releaseSolvent
       final :: delB200Calculator
    end type TB200Calculator
 
@@ -86,6 +89,23 @@ module xtb_b200_calculator
          integer(c_size_t), value :: len
          integer(c_int) :: stat
       end function xtbb200_getArray
+      function xtbb200_setSolvent(batch, solvent, alpb, kernel, state, temperature, ion_strength, ion_rad) result(stat) &
+            & bind(C, name="xtbb200_setSolvent")
+         import :: c_ptr, c_int, c_double, c_char
+         type(c_ptr), value :: batch
+         character(kind=c_char), intent(in) :: solvent(*)
+         integer(c_int), value :: alpb, kernel, state
+         real(c_double), value :: temperature, ion_strength, ion_rad
+         integer(c_int) :: stat
+      end function xtbb200_setSolvent
+      function xtbb200_releaseSolvent(batch, solvent, alpb, kernel, state, temperature, ion_strength, ion_rad) result(stat) &
+            & bind(C, name="xtbb200_setSolvent")
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: batch, solvent   ! solvent = c_null_ptr releases the model
+         integer(c_int), value :: alpb, kernel, state
+         real(c_double), value :: temperature, ion_strength, ion_rad
+         integer(c_int) :: stat
+      end function xtbb200_releaseSolvent
       function xtbb200_lastError() result(msg) bind(C, name="xtbb200_lastError")
          import :: c_ptr
          type(c_ptr) :: msg
@@ -169,6 +189,36 @@ subroutine singlepoint(self, env, mol, chk, printlevel, restart, energy, gradien
    stat = xtbb200_getArray(self%batch, "qp"//c_null_char, chk%wfn%qp, int(size(chk%wfn%qp), c_size_t))
    if (status(1) /= 0) call env%error("Self consistent charge iterator did not converge", "scf")
 end subroutine singlepoint
+
+!> Implicit solvation: what addSolvationModel (src/main/setup.f90) does for TxTBCalculator with a TSolvInput
+!> (src/solv/input.F90:30-66); a maintainer adds a `type is (TB200Calculator)` branch there that calls this routine.
+!> input%kernel is the reference's gbKernel enumerator (1 Still, 2 P16), which is what the C ABI takes.
+subroutine setSolvent(self, env, input)
+   character(len=*), parameter :: source = 'xtb_b200_setSolvent'
+   class(TB200Calculator), intent(inout) :: self
+   type(TEnvironment), intent(inout) :: env
+   type(TSolvInput), intent(in) :: input
+   integer(c_int) :: stat
+   if (input%cosmo .or. input%tmcosmo) then
+      call env%error("COSMO is not available in the B200 GFN2-xTB engine", source)
+      return
+   end if
+   stat = xtbb200_setSolvent(self%batch, input%solvent//c_null_char, merge(1_c_int, 0_c_int, input%alpb), &
+      & int(input%kernel, c_int), int(input%state, c_int), real(input%temperature, c_double), &
+      & real(input%ionStrength, c_double), real(input%ionRad, c_double))
+   if (stat < 0) then
+      call env%error("solvent: '"//input%solvent//"' is not parametrized", source)
+      return
+   end if
+   self%lSolv = .true.
+end subroutine setSolvent
+
+subroutine releaseSolvent(self)
+   class(TB200Calculator), intent(inout) :: self
+   integer(c_int) :: stat
+   stat = xtbb200_releaseSolvent(self%batch, c_null_ptr, 0_c_int, 2_c_int, 1_c_int, 298.15_c_double, 0.0_c_double, 0.0_c_double)
+   self%lSolv = .false.
+end subroutine releaseSolvent
 
 subroutine writeInfo(self, unit, mol)
    class(TB200Calculator), intent(in) :: self
