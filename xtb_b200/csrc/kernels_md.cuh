@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) k_md_update(Dev d, MdDev md) {
     }
     double ekin = 0.5 * block_sum(ek, red);
     double T = 2.0 * ekin / nfree / kBoltz;
-    const double xlam2 = sqrt(1.0 + (md.tstep0 / md.taut) * (md.tinit / T - 1.0));
+    const double xlam2 = T > 0.0 ? sqrt(1.0 + (md.tstep0 / md.taut) * (md.tinit / T - 1.0)) : 1.0;   // start from rest: no scaling
     // ---- velocity and position update (dynamic.f90:577-600)
     ek = 0;
     for (int i = tid; i < m.nat; i += nt) {
@@ -172,8 +172,10 @@ __global__ void __launch_bounds__(256) k_md_update(Dev d, MdDev md) {
     const double c00 = iyy * izz - iyz * iyz, c01 = ixz * iyz - ixy * izz, c02 = ixy * iyz - ixz * iyy;
     const double c11 = ixx * izz - ixz * ixz, c12 = ixy * ixz - ixx * iyz, c22 = ixx * iyy - ixy * ixy;
     const double det = ixx * c00 + ixy * c01 + ixz * c02;
-    const double ox = (c00 * q[0] + c01 * q[1] + c02 * q[2]) / det, oy = (c01 * q[0] + c11 * q[1] + c12 * q[2]) / det,
-                 oz = (c02 * q[0] + c12 * q[1] + c22 * q[2]) / det;
+    // atoms, diatomics and exactly linear molecules have a singular inertia tensor: only the translation is removed
+    const double scale = ixx + iyy + izz, rdet = fabs(det) > 1.0e-12 * scale * scale * scale ? 1.0 / det : 0.0;
+    const double ox = (c00 * q[0] + c01 * q[1] + c02 * q[2]) * rdet, oy = (c01 * q[0] + c11 * q[1] + c12 * q[2]) * rdet,
+                 oz = (c02 * q[0] + c12 * q[1] + c22 * q[2]) * rdet;
     for (int i = tid; i < m.nat; i += nt) {
         const int a = m.at0 + i;
         const double x = d.xyz[3 * a] - cx, y = d.xyz[3 * a + 1] - cy, z = d.xyz[3 * a + 2] - cz;
