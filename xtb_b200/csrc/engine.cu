@@ -789,12 +789,17 @@ int Batch::singlepoint(bool restart) {
     const bool hier = !use_blk && !use_scalar;                    // matrix in HBM
     const bool dc = hier && I.solver != 3;                        // Householder + divide and conquer (3: two-level Jacobi)
     bool bdc = false;                                             // the same for a batch of small matrices of one order
-    if (use_blk && I.solver == 4) {
+    // (a) solver mode 4 for ensemble-sized matrices (cross-check of the block Jacobi); (b) batches of mid-size matrices of one
+    // order (conformers of a 60-150 atom molecule): instead of one matrix after the other through the GPU-wide solver, all
+    // of them at once with one thread-block cluster per matrix in the tridiagonalisation
+    const bool clu_batch = dc && nmol >= 2 && (I.solver == 4 || (I.solver == 0 && !std::getenv("XTBB200_NO_CLUSTER_EIG")));
+    if ((use_blk && I.solver == 4) || clu_batch) {
         bool uniform = true;
         for (auto& m : s.mol) uniform = uniform && m.nao == s.max_nao;
-        if (uniform && s.max_nao > 1 && s.max_nao <= kCtaEigMax) {
+        if (!I.have_eig) { I.eig.init(s.max_nao, I.device); I.have_eig = true; }
+        const int nmaxb = use_blk ? kCtaEigMax : I.eig.cluster_max();
+        if (uniform && s.max_nao > 1 && s.max_nao <= nmaxb) {
             if (!I.cta_eig) {
-                if (!I.have_eig) { I.eig.init(s.max_nao, I.device); I.have_eig = true; }
                 I.eig.init_batch(nmol, s.max_nao);
                 I.cta_eig = true;
             }

@@ -451,7 +451,17 @@ struct SytrdSmemArgs {
     double* ybuf;       // [2][n] y = A v
     double* Gf;         // Gram matrices of the block reflectors (as written by the panel kernel)
     unsigned* bar;
+    // cluster form (k_sytrd_smem<RR, true>): a batch of matrices of one order, one thread-block cluster of `clu` CTAs per
+    // matrix (blockIdx.x / clu); matrices ms apart, d / e / tau vs apart, cbuf / ybuf 2 n apart; skip[matrix] != 0: left out
+    int clu;
+    long long ms, vs;
+    const int* skip;
 };
+// barrier over the CTAs of a thread-block cluster (hardware barrier; release / acquire at cluster scope also orders the
+// global-memory exchange buffers, which are read back with ld.cg)
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 constexpr int kResGridMin = 148;   // smallest grid of the resident kernel (see EighWork::solve): fewer CTAs were slower at
                                    // every order tried (n = 552: 3.09 ms with 148 CTAs, 3.71 with 32, 4.84 with 12)
 constexpr int kResRows = 2;   // rows of a column per thread: the resident kernel takes orders up to kResRows * kSytrdThreads
@@ -460,11 +470,20 @@ inline size_t sytrd_smem_resident_bytes(int m0, int grid) {
     return (slots * m0 + 2 * (size_t)m0 + 128) * sizeof(double);
 }
 
-template <int RR>   // RR = rows of a column per thread (the CTA has at least m0 / RR threads)
+template <int RR, bool CLU = false>   // RR = rows of a column per thread (the CTA has at least m0 / RR threads)
 __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a) {
     extern __shared__ double sm_dyn[];
     __shared__ double red[32], sh_d, sh_alpha;
-    const int n = a.n, j0 = a.j0, m0 = n - j0, G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    int G = gridDim.x, cta = blockIdx.x;
+    if (CLU) {   // one cluster per matrix of the batch: the cluster's CTAs take the role of the cooperative grid
+        G = a.clu;
+        cta = blockIdx.x % G;
+        const long long ib = blockIdx.x / G;
+        if (a.skip && a.skip[ib]) return;   // the same for every CTA of the cluster
+        a.A += ib * a.ms; a.d += ib * a.vs; a.e += ib * a.vs; a.tau += ib * a.vs;
+        a.cbuf += ib * 2 * a.n; a.ybuf += ib * 2 * a.n;
+    }
+    const int n = a.n, j0 = a.j0, m0 = n - j0, tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const long long ld = n;
     const int maxslot = (m0 + G - 1) / G;
@@ -520,7 +539,7 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
     };
     {   // first column: published by its owner, reflector formed by everybody
         if (cta == 0) for (int r = tid; r < m0; r += nthr) a.cbuf[ld + r] = cols[r];
-        grid_barrier(a.bar, G, target);
+        if (CLU) cluster_barrier(); else grid_barrier(a.bar, G, target);
         double cn[RR];
 #pragma unroll
         for (int k = 0; k < RR; ++k) { const int r = tid + k * nthr; cn[k] = r < m0 ? __ldcg(a.cbuf + ld + r) : 0.0; }
@@ -563,7 +582,7 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
             for (int q = 0; q < Q; ++q) s += part[lc * Q + q];
             ybuf[cta + (sfirst + lc) * G] = s;
         }
-        grid_barrier(a.bar, G, target);
+        if (CLU) cluster_barrier(); else grid_barrier(a.bar, G, target);
         // ---- w = tau y - tau^2/2 (v^T y) v;  A -= v w^T + w v^T on the owned columns and on the published next column
         double vy = 0.0, cn[RR];
 #pragma unroll
@@ -942,6 +961,7 @@ __global__ void k_dc_permute(int n, const double* __restrict__ Q, const int* __r
 // resident in its shared memory (k_sytrd_smem with a single owner: no grid barrier at all).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kCtaEigMax = 160;
+constexpr int kCluSize = 8;        // CTAs per cluster of the batched mid-size tridiagonalisation (portable maximum)
 
 // A: matrices ms apart (n x n, both triangles; on exit the reflectors below the sub-diagonal); d, e, tau: vs apart
 __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_cta(double* __restrict__ Aall, long long ms, int n, double* __restrict__ dall,
@@ -1176,6 +1196,7 @@ struct EighWork {
             XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
             XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
             XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+            XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
         }
         if (const char* e = std::getenv("XTBB200_RES_GRID")) res_grid_want = std::max(1, std::atoi(e));   // tuning knob
         int occ = 0;
@@ -1191,12 +1212,13 @@ struct EighWork {
 
     // ---- batch of nb matrices of one small order n (conformer ensembles): own scratch, every launch covers the batch
     int bnb = 0, bn = 0;
+    double *bcbuf = nullptr, *bybuf = nullptr;   // exchange buffers of the cluster tridiagonalisation, 2 n per matrix each
     double *bQa = nullptr, *bQb = nullptr, *bU = nullptr, *bQg = nullptr, *bUg = nullptr, *bVb = nullptr, *bVT = nullptr, *bWz = nullptr,
            *bG = nullptr, *bT = nullptr, *bvec = nullptr;
     int *bint = nullptr, *bskip = nullptr, *bfail = nullptr;
     GemmTask *btasks = nullptr, *bbt = nullptr;
     void init_batch(int nb, int n) {
-        if (n > kCtaEigMax) throw std::runtime_error("xtb_b200: batched eigensolver takes orders up to 160");
+        if (n > cluster_max()) throw std::runtime_error("xtb_b200: batched eigensolver: matrix order beyond the cluster-resident tridiagonalisation");
         bnb = nb; bn = n;
         const size_t n2 = (size_t)n * n, m = (size_t)nb * n2, v = (size_t)nb * n;
         bQa = alloc<double>(m); bQb = alloc<double>(m); bU = alloc<double>(m); bQg = alloc<double>(m); bUg = alloc<double>(m);
@@ -1206,8 +1228,19 @@ struct EighWork {
         bint = alloc<int>(12 * v);
         bskip = alloc<int>(nb); bfail = alloc<int>(nb);
         btasks = alloc<GemmTask>(2 * v); bbt = alloc<GemmTask>(nb);
-        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((n2 + 2 * n) * sizeof(double))));
+        if (n <= kCtaEigMax)
+            XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((n2 + 2 * n) * sizeof(double))));
+        else { bcbuf = alloc<double>(2 * v); bybuf = alloc<double>(2 * v); }
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_bt_tfactor_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NB * (NB + 1) * 8)));
+    }
+    // largest order of the batched solver: up to kCtaEigMax one CTA holds a matrix (k_sytrd_cta); beyond, a cluster of
+    // kCluSize CTAs holds it in their shared memories (k_sytrd_smem<2, true>: the resident kernel with the cluster's hardware
+    // barrier in place of the grid barrier), 148 / kCluSize matrices at a time
+    int cluster_max() const {
+        int m = kCtaEigMax;
+        for (int t = kCtaEigMax + 1; t <= 1024; ++t)
+            if (sytrd_smem_resident_bytes(t, kCluSize) <= res_smem_cap && (t + kCluSize - 1) / kCluSize <= 96) m = t; else break;
+        return m;
     }
     // A: nb matrices n^2 apart (destroyed), w: eigenvalues n apart, Z: eigenvectors n^2 apart; bskip[] selects (k_eig_skip_b)
     int solve_batch(cudaStream_t st, double* A, double* w, double* Z) {
@@ -1217,7 +1250,25 @@ struct EighWork {
         int nl = 0;
         double *dd_ = bvec, *ee_ = bvec + v, *tau_ = bvec + 2 * v;
         XTB_CUDA_CHECK(cudaMemsetAsync(bfail, 0, nb * sizeof(int), st));
-        k_sytrd_cta<<<nb, kSytrdThreads, ((size_t)n * n + 2 * n) * sizeof(double), st>>>(A, ms, n, dd_, ee_, tau_, vs, bskip);
+        if (n <= kCtaEigMax) {
+            k_sytrd_cta<<<nb, kSytrdThreads, ((size_t)n * n + 2 * n) * sizeof(double), st>>>(A, ms, n, dd_, ee_, tau_, vs, bskip);
+        } else {
+            SytrdSmemArgs ra;
+            std::memset(&ra, 0, sizeof(ra));
+            ra.A = A; ra.n = n; ra.j0 = 0; ra.d = dd_; ra.e = ee_; ra.tau = tau_; ra.cbuf = bcbuf; ra.ybuf = bybuf;
+            ra.clu = kCluSize; ra.ms = ms; ra.vs = vs; ra.skip = bskip;
+            int tres = kSytrdThreads;
+            while (tres > 256 && kResRows * (tres / 2) >= n) tres /= 2;
+            cudaLaunchConfig_t cfg;
+            std::memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)nb * kCluSize); cfg.blockDim = dim3(tres);
+            cfg.dynamicSmemBytes = sytrd_smem_resident_bytes(n, kCluSize); cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = kCluSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            XTB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_sytrd_smem<2, true>, ra));
+        }
         ++nl;
         XTB_CUDA_CHECK(cudaMemsetAsync(bQa, 0, (size_t)nb * ms * sizeof(double), st));
         XTB_CUDA_CHECK(cudaMemsetAsync(bQb, 0, (size_t)nb * ms * sizeof(double), st));
