@@ -1071,28 +1071,37 @@ __global__ void k_bt_formv_b(const double* __restrict__ Aall, long long ms, int 
     Vball[ib * vbs + t] = r < piv ? 0.0 : (r == piv ? 1.0 : Aall[ib * ms + r + (long long)n * (jb + k)]);
 }
 // T factor of one block for every matrix from G = V^T V (full kb x kb product, only k < i is used); CTA per matrix
-__global__ void __launch_bounds__(NB) k_bt_tfactor_b(const double* __restrict__ Gall, const double* __restrict__ tauall, long long vs,
-                                                     int jb, int kb, double* __restrict__ Tall, const int* __restrict__ skip) {
+__global__ void __launch_bounds__(NB * kTfParts) k_bt_tfactor_b(const double* __restrict__ Gall, const double* __restrict__ tauall,
+                                                                long long vs, int jb, int kb, double* __restrict__ Tall,
+                                                                const int* __restrict__ skip) {
     const long long ib = blockIdx.x;
     if (skip && skip[ib]) return;
     extern __shared__ double sm_dyn[];
-    double (*T)[NB + 1] = (double (*)[NB + 1])sm_dyn;
-    const int r = threadIdx.x;
+    double (*T)[NB + 1] = (double (*)[NB + 1])sm_dyn;                   // NB x (NB + 1)
+    double (*part)[NB] = (double (*)[NB])(sm_dyn + NB * (NB + 1));     // kTfParts x NB
+    const int r = threadIdx.x % NB, pt = threadIdx.x / NB;             // kTfParts threads per row, as in k_bt_tfactor
     const double* G = Gall + ib * NB * NB;
     const double* tau = tauall + ib * vs;
-    for (int c = 0; c < NB; ++c) T[r][c] = 0.0;
+    for (int c = pt; c < NB; c += kTfParts) T[r][c] = 0.0;
     __syncthreads();
     for (int i = 0; i < kb; ++i) {
-        const double ti = tau[jb + i];
-        if (r < i) {
-            double s = 0.0;
-            for (int k = r; k < i; ++k) s += T[r][k] * G[k + NB * i];
-            T[r][i] = -ti * s;
-        } else if (r == i) T[r][i] = ti;
+        double s = 0.0;
+        if (r < i)
+            for (int k = r + pt; k < i; k += kTfParts) s += T[r][k] * G[k + NB * i];
+        part[pt][r] = s;
+        __syncthreads();
+        if (pt == 0) {
+            if (r < i) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < kTfParts; ++q) t += part[q][r];
+                T[r][i] = -tau[jb + i] * t;
+            } else if (r == i) T[r][i] = tau[jb + i];
+        }
         __syncthreads();
     }
     double* To = Tall + ib * NB * NB;
-    for (int c = 0; c < NB; ++c) To[r + NB * c] = T[r][c];
+    for (int c = pt; c < NB; c += kTfParts) To[r + NB * c] = T[r][c];
 }
 // GEMM tasks of one back-transformation step for every matrix; which: 0 G = V^T V, 1 W = V^T Z, 2 VT = V T, 3 Z -= VT W
 __global__ void k_bt_tasks_b(GemmTask* __restrict__ tasks, int nb, int which, int n, int jb, int kb, double* Vb, long long vbs,
@@ -1231,7 +1240,7 @@ struct EighWork {
         if (n <= kCtaEigMax)
             XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((n2 + 2 * n) * sizeof(double))));
         else { bcbuf = alloc<double>(2 * v); bybuf = alloc<double>(2 * v); }
-        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_bt_tfactor_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NB * (NB + 1) * 8)));
+        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_bt_tfactor_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((NB * (NB + 1) + kTfParts * NB) * 8)));
     }
     // largest order of the batched solver: up to kCtaEigMax one CTA holds a matrix (k_sytrd_cta); beyond, a cluster of
     // kCluSize CTAs holds it in their shared memories (k_sytrd_smem<2, true>: the resident kernel with the cluster's hardware
@@ -1313,7 +1322,7 @@ struct EighWork {
             k_bt_formv_b<<<dim3((n * kb + 255) / 256, 1, nb), 256, 0, st>>>(A, ms, n, jb, kb, bVb, vbs, bskip);
             k_bt_tasks_b<<<(nb + 127) / 128, 128, 0, st>>>(bbt, nb, 0, n, jb, kb, bVb, vbs, bG, bT, bWz, bVT, Z, ms);
             k_eg_gemm<true, false><<<dim3(tk * tk, 1, nb), 128, 0, st>>>(GemmTask(), bbt, 1, bskip);
-            k_bt_tfactor_b<<<nb, NB, NB * (NB + 1) * sizeof(double), st>>>(bG, tau_, vs, jb, kb, bT, bskip);
+            k_bt_tfactor_b<<<nb, NB * kTfParts, (NB * (NB + 1) + kTfParts * NB) * sizeof(double), st>>>(bG, tau_, vs, jb, kb, bT, bskip);
             k_bt_tasks_b<<<(nb + 127) / 128, 128, 0, st>>>(bbt, nb, 1, n, jb, kb, bVb, vbs, bG, bT, bWz, bVT, Z, ms);
             k_eg_gemm<true, false><<<dim3(tk * tz, 1, nb), 128, 0, st>>>(GemmTask(), bbt, 1, bskip);
             k_bt_tasks_b<<<(nb + 127) / 128, 128, 0, st>>>(bbt, nb, 2, n, jb, kb, bVb, vbs, bG, bT, bWz, bVT, Z, ms);
