@@ -51,3 +51,34 @@ def test_cluster_batch_matches_sequential_solver_and_oracle(xb, kat, name, nconf
     assert abs(rc["energies"][1] - o.energies["e_total"]) < 1e-7
     assert np.max(np.abs(rc["gradients"][n:2 * n] - o.get("gradient").reshape(-1, 3))) < 1e-6
     assert res["cluster"][2][1] == o.info["niter"]
+
+
+def test_cluster16_batch(xb, kat):
+    """Orders between 473 and ~670 AOs with clusters of 16 CTAs (non-portable cluster size; XTBB200_NO_CLUSTER16 switches
+    them off): four replicas of the 228-atom peptide cluster (552 AOs) in ALPB water against the one-matrix-at-a-time
+    solver."""
+    import bench
+    Z, xyz = bench.make_peptide_cluster(bench.load_kat("pdb_4qxx"), 3, gap=8.0)
+    rng = np.random.default_rng(9)
+    nrep = 4
+    pos = np.concatenate([xyz + (rng.normal(0.0, 0.02, xyz.shape) if k else 0.0) for k in range(nrep)])
+    res = {}
+    for mode in ("cluster16", "sequential"):
+        if mode == "sequential":
+            os.environ["XTBB200_NO_CLUSTER_EIG"] = "1"
+        try:
+            b = xb.BatchCalculator([Z] * nrep)
+            b.set_solvent("water", model="alpb")
+            b.singlepoint(pos)
+            t0 = time.perf_counter()
+            r = b.singlepoint(pos)
+            res[mode] = (r, time.perf_counter() - t0, [int(b.result(i)["niter"]) for i in range(nrep)])
+        finally:
+            os.environ.pop("XTBB200_NO_CLUSTER_EIG", None)
+    rc, rs = res["cluster16"][0], res["sequential"][0]
+    assert rc["all_converged"] and rs["all_converged"]
+    print("\npeptide cluster x %d (552 AOs): cluster16 path %.1f ms, sequential %.1f ms" % (
+        nrep, 1e3 * res["cluster16"][1], 1e3 * res["sequential"][1]))
+    assert np.max(np.abs(rc["energies"] - rs["energies"])) < 1e-7
+    assert np.max(np.abs(rc["gradients"] - rs["gradients"])) < 1e-6
+    assert res["cluster16"][2] == res["sequential"][2]

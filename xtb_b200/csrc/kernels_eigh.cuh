@@ -1206,6 +1206,20 @@ struct EighWork {
             XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
             XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
             XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+            clu16_ok = false;
+            if (!std::getenv("XTBB200_NO_CLUSTER16") &&
+                cudaFuncSetAttribute(k_sytrd_smem<2, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+                cudaLaunchConfig_t cfg;
+                std::memset(&cfg, 0, sizeof(cfg));
+                cfg.gridDim = dim3(2 * kCluSize); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem_cap;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = 2 * kCluSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                int ncl = 0;
+                if (cudaOccupancyMaxActiveClusters(&ncl, k_sytrd_smem<2, true>, &cfg) == cudaSuccess && ncl >= 1) clu16_ok = true;
+                cudaGetLastError();
+            }
         }
         if (const char* e = std::getenv("XTBB200_RES_GRID")) res_grid_want = std::max(1, std::atoi(e));   // tuning knob
         int occ = 0;
@@ -1221,6 +1235,7 @@ struct EighWork {
 
     // ---- batch of nb matrices of one small order n (conformer ensembles): own scratch, every launch covers the batch
     int bnb = 0, bn = 0;
+    bool clu16_ok = false;                       // clusters of 2 kCluSize CTAs can be scheduled (checked in init)
     double *bcbuf = nullptr, *bybuf = nullptr;   // exchange buffers of the cluster tridiagonalisation, 2 n per matrix each
     double *bQa = nullptr, *bQb = nullptr, *bU = nullptr, *bQg = nullptr, *bUg = nullptr, *bVb = nullptr, *bVT = nullptr, *bWz = nullptr,
            *bG = nullptr, *bT = nullptr, *bvec = nullptr;
@@ -1245,10 +1260,18 @@ struct EighWork {
     // largest order of the batched solver: up to kCtaEigMax one CTA holds a matrix (k_sytrd_cta); beyond, a cluster of
     // kCluSize CTAs holds it in their shared memories (k_sytrd_smem<2, true>: the resident kernel with the cluster's hardware
     // barrier in place of the grid barrier), 148 / kCluSize matrices at a time
+    // CTAs per cluster for order n: kCluSize (portable) while the matrix fits (n <= 472), 2 kCluSize beyond (n <= ~670;
+    // non-portable cluster size: used only when the device can schedule such a cluster with this shared-memory footprint;
+    // XTBB200_NO_CLUSTER16 switches it off); 0: does not fit
+    int cluster_size(int n) const {
+        for (int c = kCluSize; c <= (clu16_ok ? 2 * kCluSize : kCluSize); c *= 2)
+            if (sytrd_smem_resident_bytes(n, c) <= res_smem_cap && (n + c - 1) / c <= 96 && n <= 1024) return c;
+        return 0;
+    }
     int cluster_max() const {
         int m = kCtaEigMax;
         for (int t = kCtaEigMax + 1; t <= 1024; ++t)
-            if (sytrd_smem_resident_bytes(t, kCluSize) <= res_smem_cap && (t + kCluSize - 1) / kCluSize <= 96) m = t; else break;
+            if (cluster_size(t)) m = t; else break;
         return m;
     }
     // A: nb matrices n^2 apart (destroyed), w: eigenvalues n apart, Z: eigenvectors n^2 apart; bskip[] selects (k_eig_skip_b)
@@ -1265,16 +1288,17 @@ struct EighWork {
             SytrdSmemArgs ra;
             std::memset(&ra, 0, sizeof(ra));
             ra.A = A; ra.n = n; ra.j0 = 0; ra.d = dd_; ra.e = ee_; ra.tau = tau_; ra.cbuf = bcbuf; ra.ybuf = bybuf;
-            ra.clu = kCluSize; ra.ms = ms; ra.vs = vs; ra.skip = bskip;
+            const int clu = cluster_size(n);
+            ra.clu = clu; ra.ms = ms; ra.vs = vs; ra.skip = bskip;
             int tres = kSytrdThreads;
             while (tres > 256 && kResRows * (tres / 2) >= n) tres /= 2;
             cudaLaunchConfig_t cfg;
             std::memset(&cfg, 0, sizeof(cfg));
-            cfg.gridDim = dim3((unsigned)nb * kCluSize); cfg.blockDim = dim3(tres);
-            cfg.dynamicSmemBytes = sytrd_smem_resident_bytes(n, kCluSize); cfg.stream = st;
+            cfg.gridDim = dim3((unsigned)nb * clu); cfg.blockDim = dim3(tres);
+            cfg.dynamicSmemBytes = sytrd_smem_resident_bytes(n, clu); cfg.stream = st;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = kCluSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            at[0].val.clusterDim.x = clu; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             XTB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_sytrd_smem<2, true>, ra));
         }
