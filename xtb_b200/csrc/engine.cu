@@ -175,6 +175,7 @@ struct Batch::Impl {
     bool md_ready = false, md_first = true;
     long long md_ncons = 0;
     std::vector<double> md_out;
+    std::vector<void*> md_allocs;   // device buffers of the current constraint tables (subset of allocs)
     SolvModel solv;           // implicit solvation model (solv.on == false: none)
     double* sv_par_dev = nullptr;
     bool leb_uploaded = false;
@@ -618,10 +619,18 @@ void Batch::md_init(const double* xyz_host, double tstep_fs, double temperature,
         md.xyzo = I.dalloc<double>(3 * na); md.acc = I.dalloc<double>(3 * na); md.xyzt = I.dalloc<double>(3 * na);
         md.out = I.dalloc<double>(4 * (size_t)nmol);
     }
-    // constraint tables change with every md_init: fresh uploads (freed with the batch)
+    // constraint tables change with every md_init: the ones of an earlier call are released first
+    XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+    for (void* p : I.md_allocs) {
+        auto it = std::find(I.allocs.begin(), I.allocs.end(), p);
+        if (it != I.allocs.end()) { I.allocs.erase(it); cudaFree(p); }
+    }
+    I.md_allocs.clear();
+    const size_t first_md_alloc = I.allocs.size();
     md.cons0 = I.upload(cons0); md.cons = I.upload(cons); md.dist2 = I.upload(dist2);
     md.dro = I.dalloc<double>(3 * dist2.size()); md.gc = I.dalloc<double>(dist2.size());
     md.adj0 = I.upload(adj0); md.adj = I.upload(adj); md.nfree = I.upload(nfree);
+    I.md_allocs.assign(I.allocs.begin() + first_md_alloc, I.allocs.end());
     XTB_CUDA_CHECK(cudaMemcpyAsync(md.velo, velo.data(), velo.size() * sizeof(double), cudaMemcpyHostToDevice, I.stream));
     XTB_CUDA_CHECK(cudaMemcpyAsync(md.mass, mass.data(), mass.size() * sizeof(double), cudaMemcpyHostToDevice, I.stream));
     XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
