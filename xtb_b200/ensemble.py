@@ -31,9 +31,11 @@ class EnsembleRunner:
     numbers_list : atomic numbers of every molecule of the WHOLE ensemble (same on all ranks)
     compute      : None -> BatchCalculator on `device` (CUDA engine); otherwise a callable
                    compute(numbers_list_local, positions_local) -> dict(energies, gradients, charges, niter, status)
+    solvent      : None (gas phase) or the keyword arguments of BatchCalculator.set_solvent, e.g.
+                   dict(solvent="water", model="alpb"): every rank sets the same implicit solvation model
     """
 
-    def __init__(self, numbers_list, rank=0, world=1, device=0, compute=None, **options):
+    def __init__(self, numbers_list, rank=0, world=1, device=0, compute=None, solvent=None, **options):
         self.rank, self.world = int(rank), int(world)
         self.numbers_list = [np.asarray(z, dtype=np.int32) for z in numbers_list]
         self.nmol = len(self.numbers_list)
@@ -46,6 +48,8 @@ class EnsembleRunner:
         if compute is None and self.last > self.first:
             from .interface import BatchCalculator
             self._calc = BatchCalculator(self.numbers_list[self.first:self.last], device=device, **options)
+            if solvent:
+                self._calc.set_solvent(**solvent)
 
     def local_positions(self, positions):
         """Slice of the concatenated (total_atoms, 3) positions that belongs to this rank."""
