@@ -65,6 +65,12 @@ int xtbb200_solventParameters(const char* solvent, int alpb, int kernel, int sta
  *     number of steps done (less than nsteps when a replica blew up), -1 on error.  Positions and velocities:
  *     xtbb200_getArray("xyz" | "velocities").
  *   xtbb200_mdConstraints: number of SHAKE constraints of the whole batch. */
+/* Host-side query (no GPU needed) of what xtbb200_mdInit sets up for one molecule: the SHAKE constraint pairs in the order
+ * of the reference's init_shake (src/shake_module.f90:50-148; 0-based atom indices, pairs[2 * capacity]) from positions
+ * [natoms][3] in bohr and the Wiberg bond orders wbo[natoms * natoms] (mode 2 only), and the masses in atomic units with
+ * hydrogens at hmass amu (masses[natoms], may be NULL).  Returns the number of constraints, -1 on error. */
+long long xtbb200_shakeList(int natoms, const int* numbers, const double* positions, const double* wbo, int mode, int hmass,
+                            int* pairs, long long capacity, double* masses);
 int xtbb200_mdInit(xtbb200_TBatch batch, const double* positions, double tstep_fs, double temperature, int thermostat,
                    int shake_mode, int hmass, const double* velocities, unsigned long long seed, int restart);
 int xtbb200_mdRun(xtbb200_TBatch batch, int nsteps, double* epot, double* ekin, double* temperature);

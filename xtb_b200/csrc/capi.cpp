@@ -20,6 +20,7 @@
 #include "../../include/xtb_b200.h"
 #include "engine.h"
 #include "solvation.h"
+#include "md_host.h"
 
 using xtbb200::Batch;
 using xtbb200::MolResult;
@@ -629,6 +630,22 @@ int xtbb200_solventParameters(const char* solvent, int alpb, int kernel, int sta
     out8[0] = sm.eps; out8[1] = sm.keps; out8[2] = sm.alpbet; out8[3] = sm.gshift; out8[4] = sm.c1; out8[5] = sm.born_offset;
     out8[6] = sm.probe; out8[7] = sm.any_hb ? 1.0 : 0.0;
     return 0;
+    XTBB_CATCH(-1)
+}
+long long xtbb200_shakeList(int natoms, const int* numbers, const double* positions, const double* wbo, int mode, int hmass,
+                            int* pairs, long long capacity, double* masses) {
+    XTBB_TRY
+    if (natoms < 1 || !numbers || !positions) throw std::runtime_error("atoms and positions are required");
+    if (mode < 0 || mode > 2) throw std::runtime_error("md: shake mode must be 0, 1 or 2");
+    if (mode == 2 && !wbo) throw std::runtime_error("shake mode 2 needs the bond orders");
+    for (int i = 0; i < natoms; ++i)
+        if (numbers[i] < 1 || numbers[i] > 86) throw std::runtime_error("element outside 1..86");
+    const auto list = xtbb200::shake_constraint_list(natoms, numbers, positions, wbo, mode);
+    if (pairs)
+        for (size_t c = 0; c < list.size() && (long long)c < capacity; ++c) { pairs[2 * c] = list[c].first; pairs[2 * c + 1] = list[c].second; }
+    if (masses)
+        for (int i = 0; i < natoms; ++i) masses[i] = xtbb200::md_mass(numbers[i], hmass);
+    return (long long)list.size();
     XTBB_CATCH(-1)
 }
 int xtbb200_mdInit(xtbb200_TBatch batch, const double* positions, double tstep_fs, double temperature, int thermostat,

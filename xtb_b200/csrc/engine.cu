@@ -24,7 +24,7 @@
 #include "kernels_scc.cuh"
 #include "kernels_solv.cuh"
 #include "kernels_md.cuh"
-#include "tables/md_tables.h"
+#include "md_host.h"
 #include "solvation.h"
 
 namespace xtbb200 {
@@ -531,8 +531,7 @@ void Batch::md_init(const double* xyz_host, double tstep_fs, double temperature,
     Dev& d = I.d;
     if (!(tstep_fs > 0.0) || !(temperature > 0.0)) throw std::runtime_error("md: time step and temperature must be positive");
     if (shake_mode < 0 || shake_mode > 2) throw std::runtime_error("md: shake mode must be 0, 1 or 2");
-    const double amutoau = 1.660539040e-27 * (1.0 / 9.10938356e-31);   // src/mctc/convert.f90:51-55
-    const double fstoau = 1.0e-15 / 2.4188843265857e-17;               // src/mctc/convert.f90:58-60
+    const double fstoau = kFsToAU;
     const int nmol = d.nmol;
     const size_t na = I.sys.atoms.size();
     set_positions(xyz_host);
@@ -540,11 +539,7 @@ void Batch::md_init(const double* xyz_host, double tstep_fs, double temperature,
     std::vector<double> wbo((size_t)I.sys.tot_nn), mass(na), velo(3 * na), nfree(nmol);
     fetch("wbo", wbo.data());
     // masses, dynamic.f90:237-252
-    for (size_t a = 0; a < na; ++a) {
-        const int Z = I.sys.atoms[a].Z;
-        mass[a] = md_atomic_mass_amu[Z - 1] * amutoau;
-        if (Z == 1 && hmass > 0) mass[a] = (double)hmass * amutoau;
-    }
+    for (size_t a = 0; a < na; ++a) mass[a] = md_mass(I.sys.atoms[a].Z, hmass);
     // SHAKE constraints, init_shake (src/shake_module.f90:50-148)
     std::vector<long long> cons0(nmol + 1, 0), adj0(na + 1, 0);
     std::vector<int> cons, adj;
@@ -553,30 +548,10 @@ void Batch::md_init(const double* xyz_host, double tstep_fs, double temperature,
         const MolDesc& m = I.sys.mol[im];
         const double* x = xyz_host + 3 * (size_t)m.at0;
         const double* w = wbo.data() + m.nn0;
-        std::vector<std::pair<int, int>> list;
+        std::vector<int> zs(m.nat);
+        for (int i = 0; i < m.nat; ++i) zs[i] = I.sys.atoms[m.at0 + i].Z;
+        const std::vector<std::pair<int, int>> list = shake_constraint_list(m.nat, zs.data(), x, w, shake_mode);
         auto r2 = [&](int i, int j) { double s = 0; for (int k = 0; k < 3; ++k) { const double t = x[3 * i + k] - x[3 * j + k]; s += t * t; } return s; };
-        if (shake_mode == 1) {   // every hydrogen to its nearest neighbour
-            for (int i = 0; i < m.nat; ++i) {
-                if (I.sys.atoms[m.at0 + i].Z != 1) continue;
-                double minr = 1000.0; int jmin = -1;
-                for (int j = 0; j < m.nat; ++j) if (j != i && r2(i, j) < minr) { minr = r2(i, j); jmin = j; }
-                if (jmin < 0) continue;
-                if (I.sys.atoms[m.at0 + jmin].Z == 1) { if (jmin > i) list.push_back({i, jmin}); }
-                else list.push_back({i, jmin});
-            }
-        } else if (shake_mode == 2) {   // all bonds: close contacts with a Wiberg bond order above the threshold, metals excluded
-            for (int i = 0; i < m.nat; ++i)
-                for (int j = i + 1; j < m.nat; ++j) {
-                    const int zi = I.sys.atoms[m.at0 + i].Z, zj = I.sys.atoms[m.at0 + j].Z;
-                    const double rco = (I.sys.atoms[m.at0 + i].rad + I.sys.atoms[m.at0 + j].rad) * kAutoAA;
-                    if (!(0.52917726 * std::sqrt(r2(i, j)) < 1.2 * rco)) continue;
-                    bool metalbond = md_metal[zi - 1] == 1 || md_metal[zj - 1] == 1;
-                    const double wthr = metalbond ? 0.1 : 0.5;
-                    if (!(w[i + (size_t)m.nat * j] > wthr)) continue;
-                    if (zi == 3 || zi == 4 || zj == 3 || zj == 4) metalbond = false;
-                    if (!metalbond) list.push_back({i, j});
-                }
-        }
         std::vector<std::vector<int>> per_atom(m.nat);
         for (size_t c = 0; c < list.size(); ++c) {
             cons.push_back(list[c].first); cons.push_back(list[c].second);
