@@ -147,3 +147,29 @@ def test_cli_md_run(kat, tmp_path):
     assert out.returncode == 0, out.stderr
     x2, v2 = cli.read_mdrestart(str(tmp_path / "mdrestart"))
     assert 1e-4 < np.max(np.abs(x2 - x1)) < 0.5
+
+
+def test_xcontrol_md_block():
+    """`$md` block of an xcontrol file (keys of set_md, src/set_module.f90:1975-2072)."""
+    text = """$chrg 0
+$md
+   temp=350.0 # in K
+   time= 10.0
+   dumptrj = 20.0
+   step=  2.0
+   velo=false
+   nvt =false
+   hmass=2
+   shake=1
+   sccacc=2.0
+   time=99.0
+$end
+$scc
+   temp=300
+$end
+"""
+    blk = cli.read_xcontrol_md(text)
+    assert blk == dict(temp=350.0, time=10.0, dump=20.0, step=2.0, nvt=False, hmass=2, shake=1, ignored=["velo", "sccacc"])
+    assert cli.read_xcontrol_md("$opt\n maxcycle=5\n$end\n") == dict(ignored=[])
+    with pytest.raises(ValueError):
+        cli.read_xcontrol_md("$md\n shake=3\n$end\n")

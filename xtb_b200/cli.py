@@ -170,6 +170,49 @@ def read_mdrestart(path="mdrestart"):
     return vals[:, :3].copy(), vals[:, 3:].copy()
 
 
+def read_xcontrol_md(text):
+    """The `$md` block of an xcontrol input (keys of set_md, src/set_module.f90:1975-2072: temp, time, dump / dumpxyz /
+    dumptrj, step, hmass, shake, nvt, restart; `key=value`, `#` comments, first occurrence wins as in the reference).
+    Returns a dict with the argparse destination names; keys this driver does not implement are reported in 'ignored'."""
+    keys = {"temp": ("temp", float), "time": ("time", float), "dump": ("dump", float), "dumpxyz": ("dump", float),
+            "dumptrj": ("dump", float), "step": ("step", float), "hmass": ("hmass", int), "shake": ("shake", int),
+            "nvt": ("nvt", None), "restart": ("restart", None)}
+    out, ignored, inside = {}, [], False
+    for raw in text.splitlines():
+        line = raw.split("#", 1)[0].strip()
+        if not line:
+            continue
+        if line.startswith("$"):
+            inside = line[1:].split()[0].lower() == "md" if len(line) > 1 else False
+            continue
+        if not inside:
+            continue
+        key, sep, val = line.replace(":", "=", 1).partition("=")
+        key, val = key.strip().lower(), val.strip()
+        if not sep or not val:
+            continue
+        if key not in keys:
+            ignored.append(key)
+            continue
+        dest, conv = keys[key]
+        if dest in out:
+            continue
+        if conv is None:
+            v = val.lower()
+            if v in ("true", "yes", "on", "1", ".true."):
+                out[dest] = True
+            elif v in ("false", "no", "off", "0", ".false."):
+                out[dest] = False
+            else:
+                raise ValueError("$md: '%s' is not a boolean for %s" % (val, key))
+        else:
+            out[dest] = conv(float(val)) if conv is int else conv(val)
+    if "shake" in out and out["shake"] not in (0, 1, 2):
+        raise ValueError("$md: shake=%d is not available (0, 1, 2)" % out["shake"])
+    out["ignored"] = ignored
+    return out
+
+
 def run_md(args, numbers, xyz, out=sys.stdout):
     """The MD run type (src/dynamic.f90:140-702 through xtbb200_mdInit / xtbb200_mdRun): one replica, frames every
     --dump fs starting with the first step, screen line every 200 steps, mdrestart and xtbmdok at the end."""
@@ -266,6 +309,7 @@ def main(argv=None):
     ap.add_argument("--nve", action="store_true", help="MD: no thermostat (nvt=false)")
     ap.add_argument("--seed", type=int, default=1, help="MD: seed of the start velocities' signs")
     ap.add_argument("--restart", action="store_true", help="MD: positions and velocities from ./mdrestart")
+    ap.add_argument("-I", "--input", default=None, help="xcontrol file: its $md block sets the MD parameters not given as flags")
     ap.add_argument("-v", "--verbose", action="store_true")
     ap.add_argument("--silent", action="store_true")
     args = ap.parse_args(argv)
@@ -278,6 +322,20 @@ def main(argv=None):
         print("xtb_b200: --alpb and --gbsa are mutually exclusive", file=sys.stderr)
         return 2
     if args.md:
+        if args.input:
+            with open(args.input) as f:
+                blk = read_xcontrol_md(f.read())
+            for key in blk.pop("ignored"):
+                print("xtb_b200: $md key '%s' is not used by this driver" % key, file=sys.stderr)
+            given = {a.split("=")[0] for a in argv if a.startswith("--")}
+            for dest, val in blk.items():
+                if dest == "nvt":
+                    if "--nve" not in given:
+                        args.nve = not val
+                elif dest == "restart":
+                    args.restart = args.restart or val
+                elif "--" + dest not in given:
+                    setattr(args, dest, val)
         return run_md(args, numbers, xyz)
     t0 = time.perf_counter()
     calc = xtb_b200.Calculator(xtb_b200.Param.GFN2xTB, numbers, xyz, charge=args.chrg, uhf=args.uhf)
