@@ -144,7 +144,9 @@ int xtbb200_getResult(xtbb200_TBatch batch, int imol, double* out16);
 int xtbb200_getCounts(xtbb200_TBatch batch, int imol, int* ndp, int* nqp, int* sweeps);
 
 /* copy a named device array of the whole batch to the host; names: gradient q qsh dipm qp cn emo
- * focc S dpint qpint H0 H0_noovlp P C wbo gab3 gab5 jmat dispmat gw ...; len = number of doubles */
+ * focc S dpint qpint H0 H0_noovlp P C wbo gab3 gab5 jmat dispmat gw xyz pcgradient ...; with a solvation model:
+ * solvation (5 per molecule: g_solv g_born g_sasa g_hb g_shift) brad sasa bornmat; after xtbb200_mdInit: velocities
+ * md_mass; len = number of doubles */
 int xtbb200_getArrayLen(xtbb200_TBatch batch, const char* name, size_t* len);
 int xtbb200_getArray(xtbb200_TBatch batch, const char* name, double* out, size_t len);
 /* offsets of molecule imol inside the concatenated arrays: atoms, shells, AOs, nao^2, natoms^2 */
