@@ -52,6 +52,13 @@ int xtbb200_setExternalCharges(xtbb200_TBatch batch, const int* npc, const int* 
  * Returns -1 (xtbb200_lastError: "solvent: '...' is not parametrized") for solvents without an internal GFN2 set. */
 int xtbb200_solventParameters(const char* solvent, int alpb, int kernel, int state, double temperature, double* out8);
 
+/* Host-side query (no GPU needed) of what xtbb200_mdInit sets up for one molecule: the SHAKE constraint pairs in the order
+ * of the reference's init_shake (src/shake_module.f90:50-148; 0-based atom indices, pairs[2 * capacity]) from positions
+ * [natoms][3] in bohr and the Wiberg bond orders wbo[natoms * natoms] (mode 2 only), and the masses in atomic units with
+ * hydrogens at hmass amu (masses[natoms], may be NULL).  Returns the number of constraints, -1 on error. */
+long long xtbb200_shakeList(int natoms, const int* numbers, const double* positions, const double* wbo, int mode, int hmass,
+                            int* pairs, long long capacity, double* masses);
+
 /* Molecular dynamics of every molecule of the batch as independent replicas (reference: src/dynamic.f90:140-702 md,
  * src/shake_module.f90 init_shake / do_shake, src/rmrottr.f90): leap-frog with Berendsen thermostat (thermostat != 0,
  * tau = 500 fs), SHAKE (shake_mode 0 off, 1 X-H bonds, 2 all bonds with a Wiberg bond order above 0.5; xtb's default is 2),
@@ -65,12 +72,6 @@ int xtbb200_solventParameters(const char* solvent, int alpb, int kernel, int sta
  *     number of steps done (less than nsteps when a replica blew up), -1 on error.  Positions and velocities:
  *     xtbb200_getArray("xyz" | "velocities").
  *   xtbb200_mdConstraints: number of SHAKE constraints of the whole batch. */
-/* Host-side query (no GPU needed) of what xtbb200_mdInit sets up for one molecule: the SHAKE constraint pairs in the order
- * of the reference's init_shake (src/shake_module.f90:50-148; 0-based atom indices, pairs[2 * capacity]) from positions
- * [natoms][3] in bohr and the Wiberg bond orders wbo[natoms * natoms] (mode 2 only), and the masses in atomic units with
- * hydrogens at hmass amu (masses[natoms], may be NULL).  Returns the number of constraints, -1 on error. */
-long long xtbb200_shakeList(int natoms, const int* numbers, const double* positions, const double* wbo, int mode, int hmass,
-                            int* pairs, long long capacity, double* masses);
 int xtbb200_mdInit(xtbb200_TBatch batch, const double* positions, double tstep_fs, double temperature, int thermostat,
                    int shake_mode, int hmass, const double* velocities, unsigned long long seed, int restart);
 int xtbb200_mdRun(xtbb200_TBatch batch, int nsteps, double* epot, double* ekin, double* temperature);
@@ -87,7 +88,9 @@ int xtbb200_setSolvent(xtbb200_TBatch batch, const char* solvent, int alpb, int 
                        double ion_strength, double ion_rad);
 
 /* eigensolver selection: 0 = automatic (block Jacobi on the FP64 tensor path when the matrix fits in shared memory,
- * Householder tridiagonalisation + divide and conquer + back-transformation beyond), 1 = scalar one-sided Jacobi,
+ * Householder tridiagonalisation + divide and conquer + back-transformation beyond: one matrix at a time with GPU-wide
+ * kernels, or - batches of one order up to ~670 - all matrices at once with one thread-block cluster per matrix),
+ * 1 = scalar one-sided Jacobi,
  * 2 = (matrices beyond shared memory) overlap orthogonaliser X = V s^-1/2 from the eigen-decomposition of S instead of
  * the blocked Cholesky X = L^-T, 3 = (matrices beyond shared memory) two-level block Jacobi instead of Householder +
  * divide and conquer, 4 = (ensembles whose matrices all have one order <= 160) batched Householder + divide and conquer
