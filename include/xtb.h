@@ -79,6 +79,10 @@ void xtb_setMaxIter(xtb_TEnvironment env, xtb_TCalculator calc, int iterations);
 void xtb_setElectronicTemp(xtb_TEnvironment env, xtb_TCalculator calc, double temperature);
 void xtb_cpcmx_calc(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator calc, xtb_TResults res);
 void xtb_singlepoint(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator calc, xtb_TResults res);
+/* Argument order as in the reference's C header (include/xtb.h:244-252).  The reference's Fortran side declares
+ * (hessian, step_size, atom_index_list) (src/api/interface.f90:310-311), so its binary reads the 6th pointer as the step
+ * and the 7th as the list; this library follows the header.  Portable callers pass NULL for both (all atoms, 0.005 bohr);
+ * a non-NULL atom_index_list is refused with an environment error, a non-NULL step_size is read as a double. */
 void xtb_hessian(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator calc, xtb_TResults res,
                  double* hessian, int* atom_index_list, int* step_size, double* dipole_gradient,
                  double* polarizability_gradient);

@@ -94,7 +94,9 @@ int xtbb200_setSolvent(xtbb200_TBatch batch, const char* solvent, int alpb, int 
  * 2 = (matrices beyond shared memory) overlap orthogonaliser X = V s^-1/2 from the eigen-decomposition of S instead of
  * the blocked Cholesky X = L^-T, 3 = (matrices beyond shared memory) two-level block Jacobi instead of Householder +
  * divide and conquer, 4 = (ensembles whose matrices all have one order <= 160) batched Householder + divide and conquer
- * instead of the block Jacobi (an independent cross-check; measured 2.3x slower than the warm-started Jacobi at 144 AOs).
+ * instead of the block Jacobi (an independent cross-check; measured 2.3x slower than the warm-started Jacobi at 144 AOs),
+ * 5 = (matrices beyond shared memory) Householder + divide and conquer one matrix at a time also for batches of one
+ * order (cross-check of the cluster-per-matrix path).
  * All give the same spectrum and density to rounding; used by the parity tests. */
 int xtbb200_setSolver(xtbb200_TBatch batch, int mode);
 
@@ -143,6 +145,10 @@ size_t xtbb200_getDeviceBytes(xtbb200_TBatch batch);
  * out[16] = energy, e_elec, e_rep, e_es, e_aes, e_axc, e_disp, hl_gap, gnorm, e_atm, dipole(3),
  *           niter, converged, fail */
 int xtbb200_getResult(xtbb200_TBatch batch, int imol, double* out16);
+/* What the reference prints but does not return through xtb.h: HOMO-LUMO gap [eV] (scc_results%hl_gap,
+ * src/scf_module.F90:894) and the number of SCC iterations (src/scc_core.f90:628-638) of the single point stored on an
+ * xtb.h results handle (xtb_TResults passed as void*).  Either output may be NULL. */
+int xtbb200_getResultsInfo(void* xtb_results, double* hl_gap_eV, int* scc_iterations);
 /* screening list lengths ndp, nqp and total Jacobi sweeps of one molecule */
 int xtbb200_getCounts(xtbb200_TBatch batch, int imol, int* ndp, int* nqp, int* sweeps);
 

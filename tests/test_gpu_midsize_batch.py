@@ -1,6 +1,6 @@
 """Batches of mid-size matrices of one order (conformers of a 60-150 atom molecule, 153-472 AOs): the batched Householder +
 divide and conquer path with one thread-block cluster per matrix in the tridiagonalisation (k_sytrd_smem<2, true>) against
-the one-matrix-at-a-time GPU-wide solver (XTBB200_NO_CLUSTER_EIG) and against the CPU oracle."""
+the one-matrix-at-a-time GPU-wide solver (set_solver(5)) and against the CPU oracle."""
 import os
 import time
 
@@ -27,17 +27,14 @@ def test_cluster_batch_matches_sequential_solver_and_oracle(xb, kat, name, nconf
     pos = np.concatenate(geos)
     res = {}
     for mode in ("cluster", "sequential"):
+        b = xb.BatchCalculator([s["numbers"]] * nconf)
         if mode == "sequential":
-            os.environ["XTBB200_NO_CLUSTER_EIG"] = "1"
-        try:
-            b = xb.BatchCalculator([s["numbers"]] * nconf)
-            assert 152 < b.sizes(0)["nao"] <= 472
-            b.singlepoint(pos)                      # warm-up (allocations)
-            t0 = time.perf_counter()
-            r = b.singlepoint(pos)
-            res[mode] = (r, time.perf_counter() - t0, [int(b.result(i)["niter"]) for i in range(nconf)])
-        finally:
-            os.environ.pop("XTBB200_NO_CLUSTER_EIG", None)
+            b.set_solver(5)                         # Householder + D&C, one matrix at a time through the GPU-wide kernels
+        assert 152 < b.sizes(0)["nao"] <= 472
+        b.singlepoint(pos)                          # warm-up (allocations)
+        t0 = time.perf_counter()
+        r = b.singlepoint(pos)
+        res[mode] = (r, time.perf_counter() - t0, [int(b.result(i)["niter"]) for i in range(nconf)])
     rc, rs = res["cluster"][0], res["sequential"][0]
     assert rc["all_converged"] and rs["all_converged"]
     assert np.max(np.abs(rc["energies"] - rs["energies"])) < 1e-8
@@ -54,8 +51,7 @@ def test_cluster_batch_matches_sequential_solver_and_oracle(xb, kat, name, nconf
 
 
 def test_cluster16_batch(xb, kat):
-    """Orders between 473 and ~670 AOs with clusters of 16 CTAs (non-portable cluster size; XTBB200_NO_CLUSTER16 switches
-    them off): four replicas of the 228-atom peptide cluster (552 AOs) in ALPB water against the one-matrix-at-a-time
+    """Orders between 473 and ~670 AOs with clusters of 16 CTAs (non-portable cluster size): four replicas of the 228-atom peptide cluster (552 AOs) in ALPB water against the one-matrix-at-a-time
     solver."""
     import bench
     Z, xyz = bench.make_peptide_cluster(bench.load_kat("pdb_4qxx"), 3, gap=8.0)
@@ -64,17 +60,14 @@ def test_cluster16_batch(xb, kat):
     pos = np.concatenate([xyz + (rng.normal(0.0, 0.02, xyz.shape) if k else 0.0) for k in range(nrep)])
     res = {}
     for mode in ("cluster16", "sequential"):
+        b = xb.BatchCalculator([Z] * nrep)
         if mode == "sequential":
-            os.environ["XTBB200_NO_CLUSTER_EIG"] = "1"
-        try:
-            b = xb.BatchCalculator([Z] * nrep)
-            b.set_solvent("water", model="alpb")
-            b.singlepoint(pos)
-            t0 = time.perf_counter()
-            r = b.singlepoint(pos)
-            res[mode] = (r, time.perf_counter() - t0, [int(b.result(i)["niter"]) for i in range(nrep)])
-        finally:
-            os.environ.pop("XTBB200_NO_CLUSTER_EIG", None)
+            b.set_solver(5)
+        b.set_solvent("water", model="alpb")
+        b.singlepoint(pos)
+        t0 = time.perf_counter()
+        r = b.singlepoint(pos)
+        res[mode] = (r, time.perf_counter() - t0, [int(b.result(i)["niter"]) for i in range(nrep)])
     rc, rs = res["cluster16"][0], res["sequential"][0]
     assert rc["all_converged"] and rs["all_converged"]
     print("\npeptide cluster x %d (552 AOs): cluster16 path %.1f ms, sequential %.1f ms" % (

@@ -352,8 +352,7 @@ def main(argv=None):
     energy, grad = res.get_energy(), res.get_gradient()
     q, wbo, dip = res.get_charges(), res.get_bond_orders(), res.get_dipole()
     eps, occ = res.get_orbital_eigenvalues(), res.get_orbital_occupations()
-    homo = int(np.nonzero(occ > 1e-6)[0].max()) if np.any(occ > 1e-6) else 0
-    gap = (eps[homo + 1] - eps[homo]) * 27.21138505 if homo + 1 < len(eps) else 0.0
+    gap = res.get_info()["hl_gap"]   # the engine's egap from ihomoa (src/scc_core.f90:501), not re-derived from occupations
     write_turbomole(numbers, xyz, energy, grad if args.grad else None)
     write_charges(q)
     write_wbo(wbo)

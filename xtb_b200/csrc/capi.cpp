@@ -222,9 +222,14 @@ void xtb_loadGFN2xTB(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator ca
     if (!calc) { env->error("Calculator object is not allocated", source); return; }
     // parameter files are not parsed: the compiled-in GFN2-xTB tables are the reference's own fallback
     // (src/xtb/calculator.f90:147-160); a custom file would change the arithmetic, so refuse it loudly
-    if (filename && filename[0] != '\0' && std::strstr(filename, "param_gfn2-xtb.txt") == nullptr) {
-        env->error("Custom parameter files are not supported, only the built-in GFN2-xTB parametrisation", source);
-        return;
+    if (filename && filename[0] != '\0') {
+        if (std::strstr(filename, "param_gfn2-xtb.txt") == nullptr) {
+            env->error("Custom parameter files are not supported, only the built-in GFN2-xTB parametrisation", source);
+            return;
+        }
+        // the distributed param_gfn2-xtb.txt holds the same numbers as the compiled-in tables; it is not read, say so
+        env->warning(std::string("Parameter file '") + filename + "' is not read: the built-in GFN2-xTB tables "
+                     "(identical to the distributed param_gfn2-xtb.txt) are used", source);
     }
     try {
         double chrg = mol->chrg;
@@ -329,7 +334,10 @@ void xtb_cpcmx_calc(xtb_TEnvironment env, xtb_TMolecule, xtb_TCalculator, xtb_TR
 // and the batch runs through the same kernels as xtbb200_singlepoint.  hessian: (3N x 3N) symmetrised as in
 // interface.f90:438-444; dipole_gradient (3, 3N) optional.  atom_index_list / step_size: NULL = all atoms / 0.005 bohr
 // (the reference's defaults); a non-NULL step_size is read as a double, which is what the reference's Fortran side does
-// with this argument (interface.f90:330).  Polarizabilities are not available for GFN2-xTB: a non-NULL
+// with this argument (interface.f90:330).  Deliberate deviation, documented in include/xtb.h and INTEGRATION.md: the
+// argument ORDER follows the C header (include/xtb.h:244-252: hessian, atom_index_list, step_size), whereas the
+// reference's Fortran binding declares (c_hess, c_step, c_list) (interface.f90:310-311), i.e. its binary reads the 6th
+// pointer as the step and the 7th as the list.  Callers that pass NULL for both (the only portable use) are unaffected.  Polarizabilities are not available for GFN2-xTB: a non-NULL
 // polarizability_gradient is an error.
 void xtb_hessian(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator calc, xtb_TResults res, double* hess, int* atom_list,
                  int* step_size, double* dipgrad, double* polgrad) {
@@ -758,6 +766,15 @@ int xtbb200_getResult(xtbb200_TBatch batch, int imol, double* out16) {
     const double v[16] = {r.energy, r.e_elec, r.e_rep, r.e_es, r.e_aes, r.e_axc, r.e_disp, r.hl_gap, r.gnorm, r.e_atm,
                           r.dipole[0], r.dipole[1], r.dipole[2], (double)r.niter, (double)r.converged, (double)r.fail};
     std::memcpy(out16, v, sizeof(v));
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_getResultsInfo(void* xtb_results, double* hl_gap_eV, int* scc_iterations) {
+    XTBB_TRY
+    const _xtb_TResults* res = (const _xtb_TResults*)xtb_results;
+    if (!res || !res->has_energy) throw std::runtime_error("results handle holds no single point");
+    if (hl_gap_eV) *hl_gap_eV = res->egap;
+    if (scc_iterations) *scc_iterations = res->niter;
     return 0;
     XTBB_CATCH(-1)
 }

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "system.h"
 
 namespace xtbb200 {
@@ -14,6 +16,13 @@ namespace xtbb200 {
             throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " + \
                                      __FILE__ + ":" + std::to_string(__LINE__));                       \
     } while (0)
+
+// Diagnostic / tuning switches ("Diagnostic switches") are honoured only when the master switch
+// XTBB200_TUNING=1 is set, so that a stray variable in a user's shell cannot change the solver or its thresholds.
+inline const char* tuning_env(const char* name) {
+    static const bool on = [] { const char* e = std::getenv("XTBB200_TUNING"); return e && e[0] == '1'; }();
+    return on ? std::getenv(name) : nullptr;
+}
 
 // per-molecule SCC state, lives on the device, mirrored to the host for convergence polling
 struct MolState {

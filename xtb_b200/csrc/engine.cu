@@ -194,6 +194,10 @@ struct Batch::Impl {
     int guess = 0;
     int solver = 0;     // 0: automatic, 1: scalar one-sided Jacobi (k_jacobi) even where the block kernel fits
     bool fits_blk = false, fits_scalar = false;
+    // diagnostic knobs, read once at construction and only under XTBB200_TUNING=1 (common.cuh: tuning_env)
+    double knob_jb_tol = 0.0, knob_jb_qtol = kJbQuadraticStop;
+    int knob_jb_inner = kJbInnerSweeps;
+    bool knob_no_cluster_eig = false, knob_cta_chol = false;
     size_t bytes = 0;
     // timing (ms) of the last single point
     float t_setup = 0, t_scc = 0, t_grad = 0;
@@ -253,6 +257,12 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         I.device = device;
         XTB_CUDA_CHECK(cudaSetDevice(device));
         XTB_CUDA_CHECK(cudaStreamCreate(&I.stream));
+        if (const char* e = tuning_env("XTBB200_JB_TOL")) I.knob_jb_tol = std::atof(e);
+        if (const char* e = tuning_env("XTBB200_JB_QTOL")) I.knob_jb_qtol = std::atof(e);
+        if (const char* e = tuning_env("XTBB200_JB_INNER")) I.knob_jb_inner = std::max(1, std::atoi(e));
+        if (const char* e = tuning_env("XTBB200_SOLVER")) I.solver = std::atoi(e);   // initial value only: set_solver() wins
+        I.knob_no_cluster_eig = tuning_env("XTBB200_NO_CLUSTER_EIG") != nullptr;
+        I.knob_cta_chol = tuning_env("XTBB200_CTA_CHOL") != nullptr;
         const int maxhist = 120;
         int off = 0;
         for (int i = 0; i < nmol; ++i) {
@@ -686,13 +696,9 @@ int Batch::singlepoint(bool restart) {
     d.etemp = I.etemp;
     d.broydamp = 0.4;   // src/setparam.f90:226
     d.maxiter = I.maxiter;
-    d.jb_inner = kJbInnerSweeps;
-    d.jb_tol = 0.0;
-    if (const char* e = std::getenv("XTBB200_JB_TOL")) d.jb_tol = std::atof(e);   // tuning knob
-    if (const char* e = std::getenv("XTBB200_SOLVER")) I.solver = std::atoi(e);    // tuning knob: overrides xtbb200_setSolver
-    d.jb_qtol = kJbQuadraticStop;
-    if (const char* e = std::getenv("XTBB200_JB_QTOL")) d.jb_qtol = std::atof(e);   // tuning knob
-    if (const char* e = std::getenv("XTBB200_JB_INNER")) d.jb_inner = std::max(1, std::atoi(e));   // tuning knob
+    d.jb_inner = I.knob_jb_inner;
+    d.jb_tol = I.knob_jb_tol;
+    d.jb_qtol = I.knob_jb_qtol;
     if (!I.ev_phase[0]) for (auto& e : I.ev_phase) cudaEventCreate(&e);
     if (!I.ev_comm[0]) for (auto& e : I.ev_comm) cudaEventCreate(&e);
     cudaEvent_t* ev = I.ev_phase;
@@ -776,7 +782,7 @@ int Batch::singlepoint(bool restart) {
     // (a) solver mode 4 for ensemble-sized matrices (cross-check of the block Jacobi); (b) batches of mid-size matrices of one
     // order (conformers of a 60-150 atom molecule): instead of one matrix after the other through the GPU-wide solver, all
     // of them at once with one thread-block cluster per matrix in the tridiagonalisation
-    const bool clu_batch = dc && nmol >= 2 && (I.solver == 4 || (I.solver == 0 && !std::getenv("XTBB200_NO_CLUSTER_EIG")));
+    const bool clu_batch = dc && nmol >= 2 && (I.solver == 4 || (I.solver == 0 && !I.knob_no_cluster_eig));
     if ((use_blk && I.solver == 4) || clu_batch) {
         bool uniform = true;
         for (auto& m : s.mol) uniform = uniform && m.nao == s.max_nao;
@@ -815,7 +821,7 @@ int Batch::singlepoint(bool restart) {
         KL(kid, k_hj_rank<<<grid2(s.max_nao, 128, nmol), 128, 0, st>>>(d));
         KL(kid, k_hj_write<<<grid2((long long)s.max_nao * s.max_nao, 256, nmol), 256, 0, st>>>(d, still ? 1 : 0));
     };
-    if (!hier && !(I.blocked_chol && !std::getenv("XTBB200_CTA_CHOL"))) {
+    if (!hier && !(I.blocked_chol && !I.knob_cta_chol)) {
         const size_t chol_bytes = (size_t)s.max_nao * (s.max_nao | 1) * sizeof(double);
         KL(K_CHOL, k_chol_inv<true><<<nmol, 512, chol_bytes, st>>>(d));
     } else if (hier && I.solver == 2) {                           // cross-check path: X = V s^-1/2 from eig(S)
@@ -967,7 +973,7 @@ int Batch::singlepoint(bool restart) {
         KL(K_WBO, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.S, d.W, 0, 0));
         KL(K_WBO, k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 3));
         KL(K_WBO, k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.X, 0, 0));
-        KL(K_WBO, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.S, d.Zm, 0, 0));
+        KL(K_WBO, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.S, d.H, 0, 0));   // not Zm: it is the warm start of the next call
     }
     KL(K_WBO, k_wbo<<<grid2((long long)s.max_nat * s.max_nat, 128, nmol), 128, 0, st>>>(d, any_open ? 1 : 0));
     KL(K_FINISH, k_finish<<<nmol, 256, 0, st>>>(d));
@@ -988,10 +994,17 @@ int Batch::singlepoint(bool restart) {
     I.prof_collect();
     I.launches = nl;
     I.scc_passes = iters;
-    I.have_wfn = true;
+    // The cached wavefunction seeds the next restarted call (MD, repeated xtb_singlepoint on one results handle): keep it
+    // only when no molecule broke down (error code or non-finite energy); a molecule that merely ran out of iterations
+    // keeps its last charges like the reference does (src/scf_module.F90:806-808 raises after storing the results).
     int nfail = 0;
-    for (int i = 0; i < nmol; ++i)
-        if (I.h_state[i].fail || !I.h_state[i].converged) nfail++;
+    bool wfn_ok = true;
+    for (int i = 0; i < nmol; ++i) {
+        const MolState& hs = I.h_state[i];
+        if (hs.fail || !hs.converged) nfail++;
+        if (hs.fail || !(hs.energy == hs.energy) || std::fabs(hs.energy) > 1.0e300) wfn_ok = false;
+    }
+    I.have_wfn = wfn_ok;
     return nfail;
 }
 

@@ -33,7 +33,7 @@ class Batch {
 
     void set_options(double accuracy, double etemp, int maxiter);
     void set_guess(int mode);                      // 0: EEQ (default), 1: uniform charges
-    void set_solver(int mode);                     // 0: automatic, 1: scalar Jacobi kernel, 2: X from eig(S), 3: two-level Jacobi for large n
+    void set_solver(int mode);                     // 0: automatic, 1: scalar Jacobi, 2: X from eig(S), 3: two-level Jacobi, 4: batched D&C, 5: D&C one matrix at a time
     // this process becomes rank `rank` of `nranks` working on the SAME molecules: shell-pair integral / gradient blocks
     // and the per-atom gradient terms are split, NCCL allreduce of the contributions; nranks == 1 switches it off
     void set_shard(int rank, int nranks, const char* nccl_unique_id128);

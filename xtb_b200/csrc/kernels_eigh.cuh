@@ -1198,7 +1198,7 @@ struct EighWork {
         const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin - 1024;   // static shared memory of the kernel
         for (int m = 1; m <= std::min(nmax, kResRows * kSytrdThreads); ++m)
             if (sytrd_smem_resident_bytes(m, grid) <= smem_cap) resident_max = m;
-        if (std::getenv("XTBB200_NO_RESIDENT_SYTRD")) resident_max = 0;
+        if (tuning_env("XTBB200_NO_RESIDENT_SYTRD")) resident_max = 0;
         res_smem_cap = smem_cap;
         if (resident_max > 0)   // smaller grids than one CTA per SM hold more columns per CTA: allow the full capacity
         {
@@ -1207,7 +1207,7 @@ struct EighWork {
             XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
             XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_smem<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
             clu16_ok = false;
-            if (!std::getenv("XTBB200_NO_CLUSTER16") &&
+            if (!tuning_env("XTBB200_NO_CLUSTER16") &&
                 cudaFuncSetAttribute(k_sytrd_smem<2, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
                 cudaLaunchConfig_t cfg;
                 std::memset(&cfg, 0, sizeof(cfg));
@@ -1221,7 +1221,7 @@ struct EighWork {
                 cudaGetLastError();
             }
         }
-        if (const char* e = std::getenv("XTBB200_RES_GRID")) res_grid_want = std::max(1, std::atoi(e));   // tuning knob
+        if (const char* e = tuning_env("XTBB200_RES_GRID")) res_grid_want = std::max(1, std::atoi(e));   // tuning knob
         int occ = 0;
         XTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sytrd_panel, kSytrdThreads, sytrd_smem(nmax, grid)));
         if (occ < 1) throw std::runtime_error("xtb_b200: tridiagonalisation kernel does not fit on an SM");
@@ -1394,7 +1394,7 @@ struct EighWork {
             sa.A = A; sa.n = n; sa.j0 = j0; sa.ncols = nc; sa.V = V; sa.W = Wp; sa.Vprev = q ? PB : nullptr;
             sa.d = dd; sa.e = ee; sa.tau = tau; sa.y = y; sa.part_n = part; sa.part_vy = part + nsm; sa.vtv = vtv; sa.wtv = wtv;
             sa.G = Gf + (size_t)(p >> 1) * NB * NB; sa.gq = EB * q; sa.bar = bar;
-            sa.prof = std::getenv("XTBB200_SYTRD_PROF") ? prof : nullptr;
+            sa.prof = tuning_env("XTBB200_SYTRD_PROF") ? prof : nullptr;
             void* args[] = {&sa};
             hook(0, 0, 0);
             XTB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sytrd_panel, dim3(grid), dim3(kSytrdThreads), args,
@@ -1431,8 +1431,8 @@ struct EighWork {
             // measured on B200 (tools/res_grid_sweep.sh, sytrd ms): n = 552: 3.09 (1024 threads) -> 2.61 (2 rows x 512);
             // n = 900: 5.55 -> 4.70; n = 1400: 9.56 (2 x 1024) -> 9.01 (4 x 512); 8 rows per thread lose everywhere
             int rr = (n - jres > 1024) ? 4 : kResRows, tmin = 256;
-            if (const char* e = std::getenv("XTBB200_RES_RR")) rr = std::atoi(e);            // tuning knobs
-            if (const char* e = std::getenv("XTBB200_RES_TMIN")) tmin = std::atoi(e);
+            if (const char* e = tuning_env("XTBB200_RES_RR")) rr = std::atoi(e);            // tuning knobs
+            if (const char* e = tuning_env("XTBB200_RES_TMIN")) tmin = std::atoi(e);
             while (rr * kSytrdThreads < n - jres) rr *= 2;
             int tres = kSytrdThreads;
             while (tres > tmin && rr * (tres / 2) >= n - jres) tres /= 2;
@@ -1533,7 +1533,7 @@ struct EighWork {
             cudaEventSynchronize(ev[3]);
             for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
         }
-        if (timed && std::getenv("XTBB200_SYTRD_PROF")) {
+        if (timed && tuning_env("XTBB200_SYTRD_PROF")) {
             long long h[8];
             cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
             static const char* nm[8] = {"A:scalars", "A:rows", "A:reduce", "barrier1", "B:reflector+v", "B:column dots", "B:collect",

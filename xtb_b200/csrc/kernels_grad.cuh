@@ -622,7 +622,7 @@ __global__ void k_wbo(Dev d, int open_path) {
             const AtomPar& a = d.atoms[m.at0 + i];
             const AtomPar& b = d.atoms[m.at0 + j];
             const double* PS = d.W + m.mat0;
-            const double* PSb = d.Zm + m.mat0;
+            const double* PSb = d.H + m.mat0;   // beta P S (engine.cu; H is dead after the gradient, Zm keeps the eigenvectors)
             const int n = m.nao;
             for (int k = a.ao0; k < a.ao0 + a.nao; ++k)
                 for (int l = b.ao0; l < b.ao0 + b.nao; ++l) {

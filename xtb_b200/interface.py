@@ -84,6 +84,7 @@ def load_library():
         "xtbb200_singlepointDevice": (ci, [vp, vp, ci, vp]),
         "xtbb200_getNMol": (ci, [vp]), "xtbb200_getSizes": (ci, [vp, ci, _c_int_p, _c_int_p, _c_int_p]),
         "xtbb200_getDeviceBytes": (ctypes.c_size_t, [vp]),
+        "xtbb200_getResultsInfo": (ci, [vp, _c_double_p, _c_int_p]),
         "xtbb200_getResult": (ci, [vp, ci, _c_double_p]), "xtbb200_getCounts": (ci, [vp, ci, _c_int_p, _c_int_p, _c_int_p]),
         "xtbb200_getArrayLen": (ci, [vp, cp, ctypes.POINTER(ctypes.c_size_t)]),
         "xtbb200_getArray": (ci, [vp, cp, _c_double_p, ctypes.c_size_t]),
@@ -259,6 +260,14 @@ class Results(Environment):
 
     def get_energy(self):
         return self._scalar(self._lib.xtb_getEnergy, "Energy is not available")
+
+    def get_info(self):
+        """HOMO-LUMO gap [eV] and number of SCC iterations of the stored single point (xtbb200_getResultsInfo; the
+        reference prints both but xtb.h has no getter for them)."""
+        gap, nit = ctypes.c_double(0.0), ctypes.c_int(0)
+        if self._lib.xtbb200_getResultsInfo(self._res, ctypes.byref(gap), ctypes.byref(nit)) != 0:
+            raise XTBException(self._lib.xtbb200_lastError().decode())
+        return dict(hl_gap=gap.value, niter=nit.value)
 
     def get_gradient(self):
         return self._array(self._lib.xtb_getGradient, (self._natoms, 3), "Gradient is not available")
@@ -469,7 +478,8 @@ class BatchCalculator:
         return dict(steps=n, epot=ep[:n], ekin=ek[:n], temperature=te[:n])
 
     def set_solver(self, mode):
-        """0: automatic, 1: scalar Jacobi kernel, 2: X from eig(S), 3: two-level Jacobi for large matrices."""
+        """0: automatic, 1: scalar Jacobi kernel, 2: X from eig(S), 3: two-level Jacobi for large matrices, 4: batched
+        Householder + D&C for ensemble-sized matrices, 5: Householder + D&C one matrix at a time (include/xtb_b200.h)."""
         self._check(self._lib.xtbb200_setSolver(self._b, int(mode)))
 
     def set_shard(self, rank, nranks, unique_id=None):
