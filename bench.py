@@ -14,7 +14,13 @@ conformers (weak scaling), there is no data-path collective; ranks only meet at 
            events on the engine's stream, max over ranks.
 `e2e`    : molecules/s through xtbb200_singlepoint with pinned HOST buffers: positions H2D and energies, gradients,
            charges, iteration counts D2H inside the timed region.
-`--workload water`: BASELINE configs[3] style large single system ((H2O)_n cluster), metric s/SCC-iteration.
+`secondary`: the default run also carries, nested under this key, one line each for the other BASELINE configs, every one
+           with its own roofline / cpu_baseline / e2e: "water" (configs[3], the second half of the metric: s/SCC-iteration
+           at 3000 atoms; with N ranks the integral / gradient blocks are split over the N GPUs and the line reports the
+           phase split, the exchange time and whether the split energy is bit-identical to one GPU), "caffeine"
+           (configs[0]), "protein" (configs[1]), "md" (configs[4]).  Their step counts are fixed and small, so the default
+           run stays within a few minutes; `--secondary off` drops them.
+`--workload water | single | md`: the same secondary workloads on their own with --steps / --warmup as given.
 """
 import argparse
 import json
@@ -198,6 +204,70 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+class Ctx:
+    """One process per GPU (torchrun env); the NCCL process group is only the timing barrier / max-over-ranks plumbing
+    (and, for the split of one large system, the carrier of rank 0's NCCL unique id)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py: no CUDA device; the engine has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self._peak64 = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def reduce(self, vals, op="max"):
+        t = self.torch.tensor([float(v) for v in vals], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    def fp64_peak(self):
+        if self._peak64 is None:
+            self._peak64 = measure_fp64_peak(self.torch, self.dev)
+        return self._peak64
+
+    def close(self):
+        if self.world > 1:
+            self.barrier()
+            self.dist.destroy_process_group()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def ncu_traffic(kernel, nao):
+    """DRAM bytes per molecule of a kernel from the committed `ncu --set full` capture (profiles/traffic.json, written by
+    tools/ncu_summary.py from dram__bytes_read.sum + dram__bytes_write.sum); None when there is no capture of this size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        e = t.get(kernel)
+        if e and int(e.get("nao", -1)) == int(nao):
+            return e
+    except Exception:
+        pass
+    return None
+
+
 def measure_fp64_peak(torch, dev):
     """cuBLAS DGEMM 4096^3 on this GPU: the FP64 (DMMA) denominator that MEASURED_PEAKS.json does not carry."""
     n = 4096
@@ -217,28 +287,11 @@ def measure_fp64_peak(torch, dev):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def run_engine(args):
-    import torch
-    import torch.distributed as dist
+def run_engine(ctx, args):
+    import ctypes
 
     import xtb_b200
-
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py: no CUDA device; the engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
+    torch, dev, rank, local, world = ctx.torch, ctx.dev, ctx.rank, ctx.local, ctx.world
     s = load_kat(args.molecule)
     nmol = args.nmol
     Z, pos = make_ensemble(s, nmol, first=rank * nmol)
@@ -271,7 +324,7 @@ def run_engine(args):
 
     # -- timed region 1: device-resident inputs
     clocks = ClockSampler(local)
-    barrier()
+    ctx.barrier()
     clocks.start()
     dev_ms, launches = [], 0
     t_wall0 = time.perf_counter()
@@ -284,7 +337,7 @@ def run_engine(args):
     prof_top, passes = batch.kernel_times()
     res = [batch.result(i) for i in (0, nmol - 1)]
     batch.array("gradient")  # results stay readable after the timed region (D2H not timed in this leg)
-    barrier()
+    ctx.barrier()
 
     # -- timed region 2: end to end through the host-buffer C ABI
     e_pin = torch.empty(nmol, dtype=torch.float64).pin_memory()
@@ -292,7 +345,6 @@ def run_engine(args):
     q_pin = torch.empty(nmol * nat, dtype=torch.float64).pin_memory()
     it_pin = torch.empty(nmol, dtype=torch.int32).pin_memory()
     st_pin = torch.empty(nmol, dtype=torch.int32).pin_memory()
-    import ctypes
     L = xtb_b200.load_library()
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
 
@@ -306,36 +358,25 @@ def run_engine(args):
 
     batch.set_profile(None)
     step_host()
-    barrier()
+    ctx.barrier()
     e2e_ms = [step_host() for _ in range(args.steps)]
-    barrier()
+    ctx.barrier()
     clk = clocks.stop()
     n_conv = int((st_pin.numpy() == 0).sum())
     mean_iter = float(it_pin.numpy().mean())
 
     # -- max over ranks
-    tot_dev = torch.tensor([sum(dev_ms), sum(e2e_ms), wall_dev * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot_dev, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e, t_wall = [float(x) for x in tot_dev.tolist()]
+    t_dev, t_e2e, t_wall = ctx.reduce([sum(dev_ms), sum(e2e_ms), wall_dev * 1e3], "max")
     value = world * nmol * args.steps / (t_dev * 1e-3)
     e2e = world * nmol * args.steps / (t_e2e * 1e-3)
-
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        del batch
+        return None
 
     # -- roofline of the dominant kernel
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
     k = prof_top[top]
     k_ms = k["ms"] / max(k["timed_launches"], 1)
-    roof = kernel_roofline(top, k_ms, nmol, nao, nsh, nat, batch, peaks, torch, dev)
+    roof = kernel_roofline(ctx, top, k_ms, nmol, nao, nsh, nat, batch, load_peaks())
     roof["kernel"] = top
     roof["avg_launch_ms"] = k_ms
     roof["share_of_step"] = k["ms"] / sum(dev_ms)
@@ -373,12 +414,11 @@ def run_engine(args):
         "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
         "sample_energy_Eh": res[0]["energy"],
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    del batch
+    return line
 
 
-def kernel_roofline(top, k_ms, nmol, nao, nsh, nat, batch, peaks, torch, dev):
+def kernel_roofline(ctx, top, k_ms, nmol, nao, nsh, nat, batch, peaks):
     """Algorithmic bytes / flops per launch of the dominant kernel class (DESIGN.md, section "Kernels")."""
     hbm = peaks.get("hbm_gbs")
     n = nao
@@ -388,21 +428,25 @@ def kernel_roofline(top, k_ms, nmol, nao, nsh, nat, batch, peaks, torch, dev):
         sweeps = np.mean([batch.counts(i)["sweeps"] for i in range(0, nmol, max(1, nmol // 64))])
         if "jacobi" in top:
             flops = nmol * (10.0 / 3.0) * n ** 3
-            note = "algorithmic flop = (4/3+2) n^3 per matrix (dsyevd equivalent); Jacobi executes ~%.1f sweeps x 3 n^3" % sweeps
+            note = "algorithmic flop = (4/3+2) n^3 per matrix (dsyevd equivalent); Jacobi executes ~%.1f sweeps x 8 n^3 DMMA flop per single point" % sweeps
         elif "X^T H X" in top:
             flops = nmol * 2 * 2.0 * n ** 3 / 2   # two GEMM launches per timed pair; per launch 2 n^3
             note = "2 n^3 flop per launch and matrix"
         else:
             flops = nmol * 2.0 * n ** 3
             note = "2 n^3 flop per launch and matrix (upper bound; density uses occupied columns only)"
-        peak = measure_fp64_peak(torch, dev)
+        peak = ctx.fp64_peak()
         ach = flops / (k_ms * 1e-3) / 1e12
-        # DRAM traffic of k_jacobi_blk per launch, scaled from the committed ncu capture (profiles/r01_ncu_k_jacobi_blk_v4.txt:
-        # 295.0 MB read + 66.1 MB written for 592 molecules of this size; algorithmic: T, Z in and Z out = 3 n^2 doubles)
-        traffic = (295.0e6 + 66.1e6) / 592 * nmol if ("jacobi" in top and n == 144) else None
-        return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
-                "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (FP64 DMMA; MEASURED_PEAKS.json has no FP64 entry)",
-                "note": note}
+        # DRAM traffic per launch from the committed ncu capture of this kernel at this matrix order (None: no capture)
+        tr = ncu_traffic("k_jacobi_blk", n) if "jacobi" in top else None
+        out = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+               "traffic": tr["bytes_per_molecule"] * nmol if tr else None,
+               "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (FP64 DMMA; MEASURED_PEAKS.json has no FP64 entry)",
+               "note": note}
+        if tr:
+            out["traffic_source"] = tr.get("source")
+            out["algorithmic_bytes"] = 3 * 8 * n * n * nmol   # T and Z in, Z out
+        return out
     per_mol = {"k_sdqh0": 88 * n * n, "k_fock": 8 * (2.5 * n * n), "populations": 8 * 11 * n * n,
                "k_grad_h0": 8 * 4 * n * n}
     b = next((v for kk, v in per_mol.items() if kk in top), 8 * n * n)
@@ -411,177 +455,199 @@ def kernel_roofline(top, k_ms, nmol, nao, nsh, nat, batch, peaks, torch, dev):
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)"}
 
 
-def run_water(args):
+def run_water(ctx, args, steps=None, warmup=None):
     """BASELINE configs[3]: one large single system, (H2O)_n cluster (default n = 1000, 3000 atoms, 6000 AOs);
-    metric = seconds per SCC iteration.  With N > 1 ranks the integral / gradient blocks are split over the GPUs
-    (xtb_b200/sharded.py, NCCL allreduce of the contributions); the SCC iterations - the eigensolve - run replicated on
-    every GPU (they stay on one GPU by design), so the per-iteration metric does not scale and the JSON line carries the
-    phase split (setup+integrals / SCC / gradient / exchanges) that shows what does."""
-    import torch
-    import torch.distributed as dist
-
+    metric = seconds per SCC iteration as the reference's "iterations" timer slot defines it (src/scf_module.F90:606-663:
+    solver init + Cholesky of S + all SCC iterations) divided by the iteration count.  With N > 1 ranks the integral /
+    gradient blocks are split over the GPUs (xtb_b200/sharded.py, NCCL allreduce of the contributions); the SCC iterations
+    - the eigensolve - run replicated on every GPU (they stay on one GPU by design), so the per-iteration metric does not
+    scale and the line carries the phase split (setup+integrals / SCC / gradient / exchanges) that shows what does, and
+    the result of the split's parity check against the same system on one GPU (energy bit-identical)."""
     from xtb_b200.sharded import ShardedCalculator
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py: no CUDA device; the engine has no CPU fallback")
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
+    import xtb_b200
+    torch, dev, rank, local, world = ctx.torch, ctx.dev, ctx.rank, ctx.local, ctx.world
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
     Z, xyz = make_water_cluster(args.nwat)
     sc = ShardedCalculator(Z, rank, world, local)
     b = sc.calc
     sz = b.sizes(0)
     clocks = ClockSampler(local)
-    for _ in range(max(args.warmup, 0)):
+    for _ in range(max(warmup, 0)):
         b.singlepoint(xyz)
-    barrier()
+    ctx.barrier()
     clocks.start()
     b.set_profile("all")
-    per_iter, tot_ms, phases, launches = [], [], [], 0
-    for _ in range(args.steps):
+    per_iter, per_iter_ref, tot_ms, phases, launches, call_ms = [], [], [], [], 0, []
+    for _ in range(steps):
         r = b.singlepoint(xyz)
         t = b.timings()
         prof, passes = b.kernel_times()
         per_iter.append(t["scc_ms"] * 1e-3 / max(passes, 1))
+        per_iter_ref.append((t["scc_ms"] + t["factorisation_ms"]) * 1e-3 / max(passes, 1))
         tot_ms.append(t["setup_ms"] + t["scc_ms"] + t["grad_ms"])
-        phases.append([t["setup_ms"], t["scc_ms"], t["grad_ms"], b.comm_ms()])
+        phases.append([t["setup_ms"], t["scc_ms"], t["grad_ms"], b.comm_ms(), t["factorisation_ms"]])
+        call_ms.append(b.call_ms())
         launches += t["launches"]
-    barrier()
+    ctx.barrier()
     clk = clocks.stop()
+    e_split = float(r["energies"][0])
+    g_split = r["gradients"].copy()
     # max over ranks of the device times
-    agg = torch.tensor([float(np.mean(per_iter)), float(np.mean(tot_ms))] + list(np.mean(np.array(phases), axis=0)),
-                       dtype=torch.float64, device=dev)
+    agg = ctx.reduce([float(np.mean(per_iter_ref)), float(np.mean(tot_ms))] + list(np.mean(np.array(phases), axis=0))
+                     + [float(np.mean(per_iter)), float(np.mean(call_ms))], "max")
+    value, step_ms, ph_setup, ph_scc, ph_grad, ph_comm, ph_fact, value_pure, e2e_ms = agg
+    # parity of the split inside the bench run (pytest on a 1-GPU box can only skip it): the same system on ONE GPU
+    shard_check = None
     if world > 1:
-        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
-    value, step_ms, ph_setup, ph_scc, ph_grad, ph_comm = [float(x) for x in agg.tolist()]
+        if rank == 0:
+            b1 = xtb_b200.BatchCalculator([Z], device=local)
+            r1 = b1.singlepoint(xyz)
+            shard_check = {"ranks": world, "energy_identical": bool(float(r1["energies"][0]) == e_split),
+                           "dE": float(r1["energies"][0]) - e_split,
+                           "max_abs_dgradient": float(np.max(np.abs(r1["gradients"] - g_split))),
+                           "niter_identical": bool(int(r1["niter"][0]) == int(r["niter"][0])),
+                           "ndp_nqp_identical": bool(b1.counts(0)["ndp"] == b.counts(0)["ndp"] and b1.counts(0)["nqp"] == b.counts(0)["nqp"])}
+            del b1
+        ctx.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        del sc, b
+        return None
     n = sz["nao"]
-    ndiag = args.steps * max(passes, 1)
-    peak = measure_fp64_peak(torch, dev)
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    hbm = peaks.get("hbm_gbs")
+    ndiag = steps * max(passes, 1)
+    peak = ctx.fp64_peak()
+    hbm = load_peaks().get("hbm_gbs")
     eig = {kk: v for kk, v in prof.items() if kk.startswith("eig:") and v["launches"]}
-    if eig:
-        # Householder + divide and conquer + back-transformation (kernels_eigh.cuh).  Dominant kernel: k_sytrd_panel, whose
-        # trailing-matrix product A v is HBM-bound.  Algorithmic bytes (DESIGN.md section 4): the lower triangle of the
-        # trailing matrix once per column, 8 (n-j-1)^2 / 2, summed over the columns = 4 (n-1) n (2n-1) / 6 per
-        # diagonalisation; the kernel reads whole columns (both triangles), i.e. twice that, which `traffic` states.
-        pk = prof["eig:k_sytrd_panel"]
-        alg = 4.0 * (n - 1) * n * (2 * n - 1) / 6.0
-        sec_panel = pk["ms"] * 1e-3 / ndiag
-        npan = (n + 63) // 64
-        stage_ms = {kk: v["ms"] / ndiag for kk, v in eig.items()}
-        gemm_flops = {"eig:trailing update(k_eg_gemm)": 4.0 * n ** 3 / 3.0, "eig:back-transformation": 2.0 * n ** 3}
-        roofline = {"bound": "hbm", "kernel": "k_sytrd_panel (Householder tridiagonalisation: column update, reflector, "
-                                              "trailing-matrix product)",
-                    "achieved": alg / sec_panel / 1e9, "peak": hbm, "unit": "GB/s",
-                    "frac": (alg / sec_panel / 1e9 / hbm) if hbm else None,
-                    "traffic": 2.0 * alg / npan,
-                    "algorithmic_bytes_per_launch": alg / npan, "avg_launch_ms": 1e3 * sec_panel / npan,
-                    "launches_per_diagonalisation": npan,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (kernel timed inside a long step)",
-                    "note": "achieved = sum of algorithmic bytes of the %d panel launches / sum of their durations; traffic = "
-                            "bytes the kernel reads by construction (full columns of the symmetric trailing matrix), confirmed "
-                            "by the ncu capture in profiles/" % npan,
-                    "share_of_step": pk["ms"] / args.steps / step_ms,
-                    "eigensolver_ms_per_diagonalisation": stage_ms,
-                    "dmma_tflops": {kk: gemm_flops[kk] / (stage_ms[kk] * 1e-3) / 1e12 for kk in gemm_flops if kk in stage_ms},
-                    "fp64_tensor_peak_tflops(cuBLAS DGEMM 4096^3, this run)": peak,
-                    "dsyevd_equivalent_tflops": (10.0 / 3.0) * n ** 3 / (sum(stage_ms.values()) * 1e-3) / 1e12}
-    else:
-        k = prof["k_jacobi"]
-        sec_diag = k["ms"] * 1e-3 / ndiag
-        flops = (10.0 / 3.0) * n ** 3
-        roofline = {"bound": "tensor", "kernel": "two-level block Jacobi (k_hj_gram/k_hj_inner/k_hj_apply)",
-                    "achieved": flops / sec_diag / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / sec_diag / 1e12 / peak,
-                    "traffic": None, "note": "algorithmic flop = (4/3+2) n^3 per diagonalisation (dsyevd equivalent)",
-                    "share_of_step": k["ms"] / args.steps / step_ms}
-    share = {kk: round(v["ms"] / args.steps / step_ms, 4) for kk, v in sorted(prof.items(), key=lambda x: -x[1]["ms"])
-             if v["ms"] / args.steps / step_ms >= 0.005}
+    stage_ms = {kk: v["ms"] / ndiag for kk, v in eig.items()}
+    topk = max(prof, key=lambda kk: prof[kk]["ms"])
+    roofline = eig_roofline(prof, topk, n, ndiag, steps, step_ms, stage_ms, peak, hbm)
+    share = {kk: round(v["ms"] / steps / step_ms, 4) for kk, v in sorted(prof.items(), key=lambda x: -x[1]["ms"])
+             if v["ms"] / steps / step_ms >= 0.005}
     cpu = None
     if not args.no_cpu and world == 1:
         from oracle.oracle import Oracle, build
         build()
         cores = host_cores()
-        ts = []
-        for mi in (1, 2):
-            o = Oracle(Z, xyz, maxiter=mi, threads=cores)
-            t0 = time.perf_counter(); o.singlepoint(); ts.append(time.perf_counter() - t0)
-        cpu = {"value": ts[1] - ts[0], "unit": "s/SCC-iteration", "cores": cores, "kind": "port",
-               "sample": "second SCC iteration of the same system (oracle run with maxiter 2 minus maxiter 1)"}
+        # one oracle run limited to two SCC iterations; its timer slot 5 is the reference's "iterations" slot
+        # (src/scf_module.F90:606-663: dpotrf + all iterations), the same quantity `value` reports for the GPU
+        o = Oracle(Z, xyz, maxiter=2, threads=cores)
+        t0 = time.perf_counter(); o.singlepoint(); t_all = time.perf_counter() - t0
+        eo = o.energies["e_total"]
+        t_it = float(o.get("timers")[5])
+        # the same two iterations on the GPU: the energy after iteration 2 is a deterministic function of the algorithm
+        b.set_options(maxiter=2)
+        r2 = b.singlepoint(xyz)
+        b.set_options(maxiter=250)
+        cpu = {"value": t_it / 2.0, "unit": "s/SCC-iteration", "cores": cores, "kind": "port",
+               "sample": "the first two SCC iterations of the same system: the oracle's 'iterations' timer slot (dpotrf + iterations) / 2; "
+                         "whole oracle call incl. integrals and gradient %.1f s" % t_all,
+               "dE_vs_gpu_after_2_iterations": float(r2["energies"][0]) - eo,
+               "note": "full converged parity (E, gradient, charges, niter, ndp/nqp) of this system: tests/test_gpu_large_parity.py"}
     line = {
-        "metric": "s/SCC-iter at 3k atoms", "value": value, "unit": "s/SCC-iteration", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong",
+        "metric": "s/SCC-iter at 3k atoms", "value": value, "unit": "s/SCC-iteration", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "(H2O)_%d cluster single point + gradient (%d atoms, %d AOs), seed 3000" % (args.nwat, sz["natoms"], n),
                    "scc_iterations": int(r["niter"][0]), "converged": bool(r["status"][0] == 0),
                    "parallelism": ("integral/gradient blocks split x%d + NCCL allreduce; SCC (eigensolve) replicated" % world)
                    if world > 1 else "one GPU",
+                   "value_definition": "(overlap factorisation + all SCC iterations) / iterations = the reference's 'iterations' "
+                                       "timer slot (src/scf_module.F90:606-663) per iteration; iterations alone: value_scc_only",
                    "l2": "matrices of %.2f GB each >> 126 MB L2" % (8.0 * n * n / 1e9)},
-        "phases_ms": {"setup+integrals(+S factorisation)": ph_setup, "scc": ph_scc, "gradient+properties": ph_grad,
-                      "of which exchanges (NCCL allreduce)": ph_comm},
+        "value_scc_only": value_pure,
+        "phases_ms": {"setup+integrals+S factorisation": ph_setup, "of which S factorisation": ph_fact, "scc": ph_scc,
+                      "gradient+properties": ph_grad, "of which exchanges (NCCL allreduce)": ph_comm},
+        "comm_ms": ph_comm, "shard_check": shard_check,
         "e2e": {"value": value, "unit": "s/SCC-iteration", "h2d_bytes_per_step": int(xyz.size * 8),
-                "d2h_bytes_per_step": int(8 * (1 + 4 * sz["natoms"])), "ms_per_step": step_ms,
-                "note": "whole host-buffer call incl. H2D/D2H is ms_per_step; the per-iteration metric excludes setup and gradient"},
+                "d2h_bytes_per_step": int(8 * (1 + 4 * sz["natoms"]) + 8), "ms_per_call": e2e_ms,
+                "note": "xtbb200_singlepoint with host buffers: ms_per_call is the whole call incl. H2D/D2H; the per-iteration "
+                        "metric is taken from the same calls (all timed steps go through the host-buffer ABI)"},
         "gpu_launches": launches,
         "roofline": roofline, "share_all_kernels": share,
-        "cpu_baseline": cpu, "clocks": clk, "sample_energy_Eh": float(r["energies"][0]),
+        "cpu_baseline": cpu, "clocks": clk, "sample_energy_Eh": e_split,
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    del sc, b
+    return line
 
 
-def run_single(args):
+def eig_roofline(prof, topk, n, ndiag, steps, step_ms, stage_ms, peak, hbm):
+    """Roofline of the dominant kernel class of a large single system."""
+    gemm_flops = {"eig:trailing update(k_eg_gemm)": 4.0 * n ** 3 / 3.0, "eig:back-transformation": 2.0 * n ** 3,
+                  "eig:band reduction(DMMA)": 4.0 * n ** 3 / 3.0}
+    common = {"eigensolver_ms_per_diagonalisation": stage_ms,
+              "dmma_tflops": {kk: gemm_flops[kk] / (stage_ms[kk] * 1e-3) / 1e12 for kk in gemm_flops if stage_ms.get(kk)},
+              "fp64_tensor_peak_tflops(cuBLAS DGEMM 4096^3, this run)": peak}
+    if stage_ms:
+        common["dsyevd_equivalent_tflops"] = (10.0 / 3.0) * n ** 3 / (sum(stage_ms.values()) * 1e-3) / 1e12
+    if topk == "eig:k_sytrd_panel":
+        # Householder tridiagonalisation: the trailing-matrix product A v is HBM-bound.  Algorithmic bytes (DESIGN.md
+        # section 4): the lower triangle of the trailing matrix once per column, 8 (n-j-1)^2 / 2, summed over the columns
+        # = 4 (n-1) n (2n-1) / 6 per diagonalisation.
+        pk = prof[topk]
+        alg = 4.0 * (n - 1) * n * (2 * n - 1) / 6.0
+        sec_panel = pk["ms"] * 1e-3 / ndiag
+        npan = (n + 63) // 64
+        r = {"bound": "hbm", "kernel": "k_sytrd_panel (Householder tridiagonalisation: column update, reflector, trailing-matrix product)",
+             "achieved": alg / sec_panel / 1e9, "peak": hbm, "unit": "GB/s", "frac": (alg / sec_panel / 1e9 / hbm) if hbm else None,
+             "traffic": None, "algorithmic_bytes_per_launch": alg / npan, "avg_launch_ms": 1e3 * sec_panel / npan,
+             "launches_per_diagonalisation": npan, "peak_source": "MEASURED_PEAKS.json hbm_gbs (kernel timed inside a long step)",
+             "note": "achieved = sum of algorithmic bytes of the %d panel launches / sum of their durations" % npan,
+             "share_of_step": pk["ms"] / steps / step_ms}
+        tr = ncu_traffic("k_sytrd_panel", n)
+        if tr:
+            r["traffic"] = tr["bytes_per_launch"]
+            r["traffic_source"] = tr.get("source")
+        r.update(common)
+        return r
+    k = prof[topk]
+    flops = gemm_flops.get(topk, (10.0 / 3.0) * n ** 3)
+    sec = k["ms"] * 1e-3 / ndiag
+    r = {"bound": "tensor", "kernel": topk, "achieved": flops / sec / 1e12, "peak": peak, "unit": "TFLOP/s",
+         "frac": flops / sec / 1e12 / peak, "traffic": None, "avg_ms_per_diagonalisation": 1e3 * sec,
+         "note": "algorithmic flop of this stage per diagonalisation / its device time",
+         "peak_source": "cuBLAS DGEMM 4096^3 measured in this run", "share_of_step": k["ms"] / steps / step_ms}
+    r.update(common)
+    return r
+
+
+def single_system(name):
+    if name == "protein" and not os.path.exists(os.path.join(ROOT, "xtb_b200", "polypeptide.py")):
+        name = "taxol6"
+    if name == "protein":
+        from xtb_b200.polypeptide import make_polypeptide
+        Z, xyz, info = make_polypeptide()
+        return Z, xyz, "synthetic polypeptide %s, %d atoms, seed %d (stand-in of crambin: same composition, SURVEY 8(d) C2)" % (
+            info["formula"], len(Z), info["seed"])
+    if name == "taxol6":
+        Z, xyz = make_peptide_cluster(load_kat("taxol"), 6, gap=20.0)
+        return Z, xyz, "6 x taxol, 20 bohr apart"
+    s = load_kat(name)
+    return s["numbers"], s["xyz"], name
+
+
+def run_single(ctx, args, molecule=None, steps=None, warmup=None):
     """BASELINE configs[0] / configs[1]: wall time of ONE GFN2-xTB single point + gradient through the xtb.h C ABI
     (xtb_newMolecule / xtb_loadGFN2xTB / xtb_singlepoint / xtb_getEnergy / xtb_getGradient), fresh results handle (EEQ
     guess) per step.  --molecule caffeine: the 24-atom molecule of `xtb caffeine.xyz --gfn 2 --grad`; --molecule
-    protein: stand-in of crambin's size (its coordinates are not available offline): 6 copies of taxol
-    (test/unit/molstock.f90, 113 atoms each = 678 atoms) 20 bohr apart.  (Clusters of the zwitterionic peptide pdb-4qxx
-    were tried first; their SCC needs > 100 iterations in the oracle and in the engine alike and the iteration count is
-    not reproducible between any two eigensolvers, so they make a poor benchmark.)"""
-    import torch
-
+    protein: a seeded, covalently connected 642-atom polypeptide of crambin's composition C202H315N55O64S6
+    (xtb_b200/polypeptide.py; crambin's coordinates are not available offline)."""
     import xtb_b200
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py: no CUDA device; the engine has no CPU fallback")
-    if int(os.environ.get("RANK", "0")) != 0:
-        return                                            # does not shard: one molecule, one GPU
-    torch.cuda.set_device(0)
-    if args.molecule == "protein":
-        Z, xyz = make_peptide_cluster(load_kat("taxol"), 6, gap=20.0)
-        label = "6 x taxol, 20 bohr apart (stand-in of crambin's size)"
-    else:
-        s = load_kat(args.molecule)
-        Z, xyz = s["numbers"], s["xyz"]
-        label = args.molecule
+    torch = ctx.torch
+    if ctx.rank != 0:
+        return None                                       # does not shard: one molecule, one GPU
+    molecule = molecule or args.molecule
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
+    Z, xyz, label = single_system(molecule)
     calc = xtb_b200.Calculator(xtb_b200.Param.GFN2xTB, Z, xyz)
     calc.set_verbosity(0)
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(max(warmup, 1)):
         res = calc.singlepoint()
-    clocks = ClockSampler(0)
+    clocks = ClockSampler(ctx.local)
     clocks.start()
     torch.cuda.synchronize()
     ts = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         t0 = time.perf_counter()
         res = calc.singlepoint()                          # new results handle: no restart
         e = res.get_energy()
@@ -589,54 +655,65 @@ def run_single(args):
         ts.append(time.perf_counter() - t0)
     clk = clocks.stop()
     # device-side split of the same calculation through the batched ABI (positions resident on the device)
-    b = xtb_b200.BatchCalculator([Z])
-    pos_dev = torch.from_numpy(np.ascontiguousarray(xyz)).cuda()
+    b = xtb_b200.BatchCalculator([Z], device=ctx.local)
+    pos_dev = torch.from_numpy(np.ascontiguousarray(xyz)).to(ctx.dev)
     b.set_profile("all")
     dev_ms = []
-    for _ in range(max(args.warmup, 1) + args.steps):
+    for _ in range(max(warmup, 1) + steps):
         b.singlepoint_device(pos_dev.data_ptr())
         t = b.timings()
         dev_ms.append(t["setup_ms"] + t["scc_ms"] + t["grad_ms"])
-    dev_ms = dev_ms[-args.steps:]
+    dev_ms = dev_ms[-steps:]
     prof, passes = b.kernel_times()
     tot = sum(v["ms"] for v in prof.values())
     share = {kk: round(v["ms"] / tot, 4) for kk, v in sorted(prof.items(), key=lambda x: -x[1]["ms"]) if v["ms"] / tot >= 0.01}
     r = b.result(0)
     sz = b.sizes(0)
+    n = sz["nao"]
+    topk = max(prof, key=lambda k: prof[k]["ms"])
+    if n > 152:     # Householder + divide and conquer path: same roofline bookkeeping as the water workload
+        ncall = max(warmup, 1) + steps
+        ndiag = ncall * max(passes, 1)
+        stage_ms = {kk: v["ms"] / ndiag for kk, v in prof.items() if kk.startswith("eig:") and v["launches"]}
+        roof = eig_roofline(prof, topk, n, ndiag, ncall, float(np.mean(dev_ms)), stage_ms, ctx.fp64_peak(), load_peaks().get("hbm_gbs"))
+    else:
+        roof = {"bound": "latency", "kernel": topk, "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                "note": "one small molecule cannot fill the GPU; see the ensemble workload for throughput"}
     cpu = None
     if not args.no_cpu:
         from oracle.oracle import Oracle, build
         build()
         cores = host_cores()
         best = None
-        for nth in sorted({1, cores}):           # tiny molecules run fastest on one thread, large ones on all cores
-            for _ in range(2):
+        for nth in sorted({1, cores}) if len(Z) < 200 else [cores]:   # tiny molecules run fastest on one thread
+            for _ in range(2 if len(Z) < 200 else 1):
                 o = Oracle(Z, xyz, threads=nth)
                 t0 = time.perf_counter(); st = o.singlepoint(); dt = time.perf_counter() - t0
                 if best is None or dt < best[0]:
                     best = (dt, nth)
         cpu = {"value": 1e3 * best[0], "unit": "ms/single point", "cores": best[1], "kind": "port",
-               "sample": "the same molecule, OpenMP + OpenBLAS with 1 and with %d threads, best of 2 x 2" % cores,
-               "dE_vs_gpu": float(e - o.energies["e_total"]), "niter": int(o.info["niter"])}
+               "sample": "the same molecule, OpenMP + OpenBLAS, best of the runs with 1 / %d threads" % cores,
+               "dE_vs_gpu": float(e - o.energies["e_total"]), "niter": int(o.info["niter"]),
+               "niter_identical": bool(int(o.info["niter"]) == int(r["niter"])),
+               "max_abs_dgradient_vs_gpu": float(np.max(np.abs(g - o.get("gradient").reshape(-1, 3))))}
     line = {
         "metric": "wall time per GFN2 SP+gradient (single molecule)", "value": float(np.mean(dev_ms)), "unit": "ms/single point",
-        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(dev_ms)), "higher_is_better": False,
+        "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": float(np.mean(dev_ms)), "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: %d atoms, %d AOs, xtb.h C API, EEQ guess every call" % (label, sz["natoms"], sz["nao"]),
-                   "scc_iterations": int(r["niter"]), "l2": "single small system: launch/latency bound, working set in L2"},
+                   "scc_iterations": int(r["niter"]), "l2": "single system: working set %.0f MB" % (b.device_bytes() / 1e6)},
         "e2e": {"value": 1e3 * float(np.mean(ts)), "unit": "ms/single point", "h2d_bytes_per_step": int(np.asarray(xyz).size * 8),
                 "d2h_bytes_per_step": int(8 * (1 + 3 * sz["natoms"])),
                 "note": "xtb_singlepoint + xtb_getEnergy + xtb_getGradient, host buffers, wall clock around the blocking calls"},
-        "gpu_launches": int(b.timings()["launches"]) * args.steps,
-        "roofline": {"bound": "latency", "kernel": max(prof, key=lambda k: prof[k]["ms"]), "achieved": None, "peak": None, "unit": None,
-                     "frac": None, "traffic": None,
-                     "note": "one small molecule cannot fill the GPU; see the ensemble workload for throughput"},
+        "gpu_launches": int(b.timings()["launches"]) * steps,
+        "roofline": roof,
         "share_all_kernels": share, "cpu_baseline": cpu, "clocks": clk, "sample_energy_Eh": float(e),
     }
-    print(json.dumps(line), flush=True)
+    del b, calc
+    return line
 
 
-def run_md(args):
+def run_md(ctx, args, steps=None, warmup=None):
     """BASELINE configs[4]: GFN2-xTB molecular dynamics of a ~200-atom peptide in ALPB(water), MD steps per second.
     System: 3 copies of the 76-atom peptide pdb-4qxx (test/unit/molstock.f90:739-909) 8 bohr apart = 228 atoms (SURVEY 8(d)
     C5); xtb's default $md settings (4 fs, Berendsen 298.15 K, SHAKE on all bonds, hydrogen mass 4 amu).  A step = one
@@ -646,26 +723,10 @@ def run_md(args):
     API drives from the host (positions H2D, energy + gradient D2H every step, leap-frog + thermostat on the host)."""
     import ctypes
 
-    import torch
-    import torch.distributed as dist
-
     import xtb_b200
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py: no CUDA device; the engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
+    torch, dev, rank, local, world = ctx.torch, ctx.dev, ctx.rank, ctx.local, ctx.world
+    steps_arg = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
     Z, xyz = make_peptide_cluster(load_kat("pdb_4qxx"), 3, gap=8.0)
     nat = len(Z)
     solvent = dict(solvent="water", model="alpb")
@@ -673,24 +734,24 @@ def run_md(args):
     b.set_solvent(**solvent)
     ncons = b.md_init(xyz, seed=1 + rank)
     sz = b.sizes(0)
-    steps = max(args.steps, 1) * 20                       # a "step" of the bench contract = 20 MD steps
+    steps = max(steps_arg, 1) * 20                        # a "step" of the bench contract = 20 MD steps
     b.set_profile("all")
-    b.md_run(max(args.warmup, 3) * 5)
+    b.md_run(max(warmup, 3) * 5)
     prof, passes = b.kernel_times()
     tot = sum(v["ms"] for v in prof.values())
     share = {kk: round(v["ms"] / tot, 4) for kk, v in sorted(prof.items(), key=lambda x: -x[1]["ms"]) if v["ms"] / tot >= 0.01}
     top = max(prof, key=lambda k: prof[k]["ms"])
     b.set_profile([])
     clocks = ClockSampler(local)
-    barrier()
+    ctx.barrier()
     clocks.start()
     t0 = time.perf_counter()
     r = b.md_run(steps)
     torch.cuda.synchronize(dev)
-    wall = time.perf_counter() - t0                       # md_run blocks on the engine's stream after every step
+    wall = time.perf_counter() - t0                       # md_run blocks on the engine's stream
     clk = clocks.stop()
     launches = int(b.timings()["launches"]) * steps
-    barrier()
+    ctx.barrier()
     # ---- end to end: host-driven loop through the host-buffer C ABI (restart = 1), unconstrained leap-frog on the host
     L = xtb_b200.load_library()
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
@@ -704,7 +765,7 @@ def run_md(args):
     vel = b.array("velocities").reshape(-1, 3).copy()
     x = pos_pin.numpy().reshape(-1, 3)
     dt = 1.0 * 1.0e-15 / 2.4188843265857e-17              # 1 fs without constraints
-    nh = max(args.steps, 1) * 10
+    nh = max(steps_arg, 1) * 10
     t0 = time.perf_counter()
     for _ in range(nh):
         rc = L.xtbb200_singlepoint(b._b, ctypes.cast(pos_pin.data_ptr(), dp), 1, ctypes.cast(e_pin.data_ptr(), dp),
@@ -717,16 +778,13 @@ def run_md(args):
     wall_host = time.perf_counter() - t0
     rate, rate_host = steps / wall, nh / wall_host
     if world > 1:
-        t = torch.tensor([rate, rate_host, wall], dtype=torch.float64, device=dev)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        rate, rate_host, wall = float(tsum[0]), float(tsum[1]), float(tmax[2])
+        rate, rate_host = ctx.reduce([rate, rate_host], "sum")
+        wall = ctx.reduce([wall], "max")[0]
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        del b
+        return None
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         from oracle.md_oracle import MDOracle
         from oracle.oracle import build
         build()
@@ -739,10 +797,10 @@ def run_md(args):
                "sample": "4 MD steps of the same system and settings with the CPU oracle (OpenMP + OpenBLAS)"}
     line = {
         "metric": "GFN2-xTB MD steps/sec (228-atom peptide cluster, ALPB water)", "value": rate, "unit": "MD steps/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
+        "n_gpus": world, "steps": steps_arg, "warmup": warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "MD, 3 x pdb-4qxx (%d atoms, %d AOs), ALPB(water), 4 fs, NVT 298.15 K, SHAKE on %d bonds, H mass 4; "
-                               "one replica per GPU; %d MD steps timed" % (nat, sz["nao"], ncons, steps),
+                               "one replica per GPU (replicas only, SURVEY 8e); %d MD steps timed" % (nat, sz["nao"], ncons, steps),
                    "scc_iterations_last_step": int(b.result(0)["niter"]),
                    "l2": "one small system: latency bound, working set in L2"},
         "e2e": {"value": rate_host, "unit": "MD steps/s", "h2d_bytes_per_step": int(nat * 24), "d2h_bytes_per_step": int(8 * (1 + 4 * nat) + 8),
@@ -754,9 +812,31 @@ def run_md(args):
         "trajectory": {"epot_first": float(r["epot"][0, 0]), "epot_last": float(r["epot"][-1, 0]),
                        "T_mean": float(r["temperature"][:, 0].mean()), "steps_done": int(r["steps"])},
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    del b
+    return line
+
+
+def run_secondary(ctx, args):
+    """The other BASELINE configs, bounded: every entry is a complete line of its own workload (or {"error": ...})."""
+    out = {}
+    plan = [("water", lambda: run_water(ctx, args, steps=2, warmup=1)),
+            ("caffeine", lambda: run_single(ctx, args, molecule="caffeine", steps=20, warmup=3)),
+            ("protein", lambda: run_single(ctx, args, molecule="protein", steps=3, warmup=1)),
+            ("md", lambda: run_md(ctx, args, steps=3, warmup=3))]
+    for name, fn in plan:
+        t0 = time.perf_counter()
+        try:
+            line = fn()
+        except Exception as ex:   # a secondary workload must never take the headline line down with it
+            line = {"error": "%s: %s" % (type(ex).__name__, ex)}
+            if ctx.world > 1:
+                raise             # ... but ranks must not diverge inside collectives
+        ctx.barrier()
+        if ctx.rank == 0:
+            if line is not None:
+                line["bench_wall_s"] = time.perf_counter() - t0
+            out[name] = line
+    return out
 
 
 def main():
@@ -769,25 +849,39 @@ def main():
     ap.add_argument("--molecule", default="rivaroxaban")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="ensemble", choices=["ensemble", "water", "single", "md"],
-                    help="ensemble: BASELINE configs[2] (default, the headline metric); water: configs[3], s/SCC-iteration; "
-                         "single: configs[0]/[1], one molecule (--molecule caffeine | protein) through the xtb.h C API; "
-                         "md: configs[4], MD steps/s of a 228-atom peptide cluster in ALPB water")
+                    help="ensemble: BASELINE configs[2] (default, the headline metric, with the other configs nested under "
+                         "`secondary`); water: configs[3], s/SCC-iteration; single: configs[0]/[1], one molecule (--molecule "
+                         "caffeine | protein) through the xtb.h C API; md: configs[4], MD steps/s of a 228-atom peptide cluster "
+                         "in ALPB water")
+    ap.add_argument("--secondary", default="auto", choices=["auto", "on", "off"],
+                    help="nest the water / caffeine / protein / md lines into the ensemble line (auto: for the default workload)")
     ap.add_argument("--solvent", default=None, help="ensemble workload: implicit solvent (e.g. water) instead of the gas phase")
     ap.add_argument("--solvent-model", default="alpb", choices=["gbsa", "alpb"])
     ap.add_argument("--nwat", type=int, default=1000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "water":
-        run_water(args)
+        return
+    ctx = Ctx()
+    if args.workload == "water":
+        line = run_water(ctx, args)
     elif args.workload == "md":
-        run_md(args)
+        line = run_md(ctx, args)
     elif args.workload == "single":
         if args.molecule == "rivaroxaban":
             args.molecule = "caffeine"
-        run_single(args)
+        line = run_single(ctx, args)
     else:
-        run_engine(args)
+        line = run_engine(ctx, args)
+        default_wl = args.molecule == "rivaroxaban" and not args.solvent
+        if args.secondary == "on" or (args.secondary == "auto" and default_wl):
+            ctx.torch.cuda.empty_cache()
+            sec = run_secondary(ctx, args)
+            if line is not None:
+                line["secondary"] = sec
+    if ctx.rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+    ctx.close()
 
 
 if __name__ == "__main__":

@@ -165,6 +165,9 @@ int xtbb200_getMask(xtbb200_TBatch batch, unsigned char* out, size_t len);
 
 /* device timings [ms] of the last call (setup+integrals, SCC, gradient+properties) and kernel launches */
 int xtbb200_getTimings(xtbb200_TBatch batch, float* ms3, int* launches);
+/* device time [ms] of the overlap factorisation S = L L^T, X = L^-T inside ms3[0].  The reference's "iterations" timer
+ * slot (src/scf_module.F90:606-663) covers solver init + dpotrf + all SCC iterations, i.e. this time + ms3[1]. */
+int xtbb200_getFactorisationTime(xtbb200_TBatch batch, float* ms);
 
 /* device time [ms] of the last xtbb200_singlepoint call from the first host->device copy to the last device->host
  * copy (CUDA events on the engine's stream) */

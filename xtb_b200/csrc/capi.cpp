@@ -827,6 +827,13 @@ int xtbb200_getTimings(xtbb200_TBatch batch, float* ms3, int* launches) {
     return 0;
     XTBB_CATCH(-1)
 }
+int xtbb200_getFactorisationTime(xtbb200_TBatch batch, float* ms) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    *ms = batch->b->factorisation_ms();
+    return 0;
+    XTBB_CATCH(-1)
+}
 int xtbb200_getCallTime(xtbb200_TBatch batch, float* ms) {
     XTBB_TRY
     if (!batch) throw std::runtime_error("batch is not allocated");

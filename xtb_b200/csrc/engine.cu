@@ -200,10 +200,10 @@ struct Batch::Impl {
     bool knob_no_cluster_eig = false, knob_cta_chol = false;
     size_t bytes = 0;
     // timing (ms) of the last single point
-    float t_setup = 0, t_scc = 0, t_grad = 0;
+    float t_setup = 0, t_scc = 0, t_grad = 0, t_fact = 0;   // t_fact: overlap factorisation, part of t_setup
     int launches = 0;
     int scc_passes = 0;
-    cudaEvent_t ev_phase[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_phase[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [4]: begin of the overlap factorisation
     cudaEvent_t ev_call[2] = {nullptr, nullptr};
     cudaEvent_t ev_comm[4] = {nullptr, nullptr, nullptr, nullptr};   // integral exchange begin/end, gradient exchange begin/end
     long long pair_total = 0;
@@ -821,6 +821,7 @@ int Batch::singlepoint(bool restart) {
         KL(kid, k_hj_rank<<<grid2(s.max_nao, 128, nmol), 128, 0, st>>>(d));
         KL(kid, k_hj_write<<<grid2((long long)s.max_nao * s.max_nao, 256, nmol), 256, 0, st>>>(d, still ? 1 : 0));
     };
+    cudaEventRecord(ev[4], st);
     if (!hier && !(I.blocked_chol && !I.knob_cta_chol)) {
         const size_t chol_bytes = (size_t)s.max_nao * (s.max_nao | 1) * sizeof(double);
         KL(K_CHOL, k_chol_inv<true><<<nmol, 512, chol_bytes, st>>>(d));
@@ -984,6 +985,7 @@ int Batch::singlepoint(bool restart) {
     cudaEventElapsedTime(&I.t_setup, ev[0], ev[1]);
     cudaEventElapsedTime(&I.t_scc, ev[1], ev[2]);
     cudaEventElapsedTime(&I.t_grad, ev[2], ev[3]);
+    cudaEventElapsedTime(&I.t_fact, ev[4], ev[1]);
     I.t_comm = 0;
     if (R > 1) {
         float a = 0, b = 0;
@@ -1068,6 +1070,7 @@ int Batch::scc_passes() const { return p_->scc_passes; }
 
 int Batch::launches() const { return p_->launches; }
 void Batch::timings(float* t3) const { t3[0] = p_->t_setup; t3[1] = p_->t_scc; t3[2] = p_->t_grad; }
+float Batch::factorisation_ms() const { return p_->t_fact; }
 
 MolResult Batch::result(int i) const {
     const MolState& s = p_->h_state[i];

@@ -89,6 +89,7 @@ class Batch {
     void* stream() const;
     int launches() const;
     void timings(float* t3) const;   // ms: setup+integrals, SCC, gradient+properties
+    float factorisation_ms() const;  // part of the setup time: S = L L^T, X = L^-T (the reference times it with the iterations)
     // per-kernel-class device timers: launches whose class bit is set in mask are bracketed by CUDA events on the
     // engine's stream; times accumulate over singlepoint calls until the next set_profile
     void set_profile(unsigned long long mask);

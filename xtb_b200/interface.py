@@ -92,6 +92,7 @@ def load_library():
         "xtbb200_getMask": (ci, [vp, ctypes.c_void_p, ctypes.c_size_t]),
         "xtbb200_getTimings": (ci, [vp, ctypes.POINTER(ctypes.c_float), _c_int_p]),
         "xtbb200_getCallTime": (ci, [vp, ctypes.POINTER(ctypes.c_float)]),
+        "xtbb200_getFactorisationTime": (ci, [vp, ctypes.POINTER(ctypes.c_float)]),
         "xtbb200_setProfile": (ci, [vp, ctypes.c_ulonglong]), "xtbb200_kernelClassCount": (ci, []),
         "xtbb200_kernelClassName": (cp, [ci]),
         "xtbb200_getKernelTimes": (ci, [vp, ctypes.POINTER(ctypes.c_float), _c_int_p, _c_int_p, _c_int_p]),
@@ -559,7 +560,9 @@ class BatchCalculator:
         t = (ctypes.c_float * 3)()
         n = ctypes.c_int()
         self._check(self._lib.xtbb200_getTimings(self._b, t, ctypes.byref(n)))
-        return dict(setup_ms=t[0], scc_ms=t[1], grad_ms=t[2], launches=n.value)
+        f = ctypes.c_float()
+        self._check(self._lib.xtbb200_getFactorisationTime(self._b, ctypes.byref(f)))
+        return dict(setup_ms=t[0], scc_ms=t[1], grad_ms=t[2], launches=n.value, factorisation_ms=f.value)
 
     def call_ms(self):
         """Device time of the last host-buffer singlepoint call, H2D of positions through D2H of results."""
