@@ -57,7 +57,9 @@ def test_open_shell_md_short(xb, kat):
     assert r["steps"] == 6
     etot = r["epot"][:, 0] + r["ekin"][:, 0]
     assert np.all(np.isfinite(etot))
-    assert np.max(np.abs(etot - etot[0])) < 5e-4
+    # the first entry holds the start velocities (t = 0), the later ones the leap-frog half-step average: conservation is
+    # judged from the second step on
+    assert np.max(np.abs(etot[1:] - etot[1])) < 1e-4
 
 
 def test_mixed_batch_open_and_closed_restart(xb, kat):

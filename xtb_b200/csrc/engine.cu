@@ -197,6 +197,7 @@ struct Batch::Impl {
     // diagnostic knobs, read once at construction and only under XTBB200_TUNING=1 (common.cuh: tuning_env)
     double knob_jb_tol = 0.0, knob_jb_qtol = kJbQuadraticStop;
     int knob_jb_inner = kJbInnerSweeps;
+    int knob_jb_variant = 1;    // 1: jb_sweeps2 (cross-block Gram, unnormalised rotations), 0: jb_sweeps
     bool knob_no_cluster_eig = false, knob_cta_chol = false;
     size_t bytes = 0;
     // timing (ms) of the last single point
@@ -260,6 +261,7 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         if (const char* e = tuning_env("XTBB200_JB_TOL")) I.knob_jb_tol = std::atof(e);
         if (const char* e = tuning_env("XTBB200_JB_QTOL")) I.knob_jb_qtol = std::atof(e);
         if (const char* e = tuning_env("XTBB200_JB_INNER")) I.knob_jb_inner = std::max(1, std::atoi(e));
+        if (const char* e = tuning_env("XTBB200_JB_VARIANT")) I.knob_jb_variant = std::atoi(e) ? 1 : 0;
         if (const char* e = tuning_env("XTBB200_SOLVER")) I.solver = std::atoi(e);   // initial value only: set_solver() wins
         I.knob_no_cluster_eig = tuning_env("XTBB200_NO_CLUSTER_EIG") != nullptr;
         I.knob_cta_chol = tuning_env("XTBB200_CTA_CHOL") != nullptr;
@@ -372,7 +374,8 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         // opt in to large dynamic shared memory for the in-SM solvers
         const int smax = 227 * 1024 - 2048;
         cudaFuncSetAttribute(k_chol_inv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-        cudaFuncSetAttribute(k_jacobi_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        cudaFuncSetAttribute(k_jacobi_blk<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        cudaFuncSetAttribute(k_jacobi_blk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_hj_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_grad_atm, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_bchol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBcholDiagSmem);
@@ -852,6 +855,7 @@ int Batch::singlepoint(bool restart) {
     // ensemble-sized matrices: block Jacobi on the FP64 tensor path, matrix resident in shared memory
     const int jb_warps = std::max(1, std::min(20, jb_dims(s.max_nao).nb / 2));   // k_jacobi_blk: __launch_bounds__(640)
     const size_t jb_bytes = jb_smem_bytes(s.max_nao, jb_warps);
+    auto jacobi_blk = I.knob_jb_variant ? k_jacobi_blk<1> : k_jacobi_blk<0>;
     int active = nmol;
     int iters = 0;
     std::fill(I.h_done.begin(), I.h_done.end(), 0);
@@ -876,11 +880,11 @@ int Batch::singlepoint(bool restart) {
             I.k_launches[K_JACOBI] += nla; nl += nla;
         } else if (use_blk && it == 0 && I.has_followers && !(restart && I.have_wfn) && I.solver == 0) {
             // first diagonalisation of an ensemble: leaders cold, followers warm from their leader's eigenvectors
-            KL(K_JACOBI, k_jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d, 1));
+            KL(K_JACOBI, jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d, 1));
             KL(K_JACOBI, k_lead_copy<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
             KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.W, d.Zm, d.T, 0, 3));
-            KL(K_JACOBI, k_jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d, 2));
-        } else if (use_blk) KL(K_JACOBI, k_jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d, 0));
+            KL(K_JACOBI, jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d, 2));
+        } else if (use_blk) KL(K_JACOBI, jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d, 0));
         else if (dc) {
             XTB_CUDA_CHECK(cudaMemsetAsync(I.eig.fail, 0, sizeof(int), st));
             // stage hooks of the solver -> kernel classes (stage 0: panel kernel, 1: trailing update, 2: D&C, 3: back-transformation)

@@ -357,7 +357,7 @@ __device__ __forceinline__ void jb_publish(volatile int* ver, int P, int Q, int 
     if (lane == 0) { ver[P] = v; ver[Q] = v; }
 }
 
-constexpr double kJbQuadraticStop = 1.0e-8;   // default of Dev::jb_qtol: columns orthogonal to ~1e-16 after the last sweep
+constexpr double kJbQuadraticStop = 1.0e-5;   // default of Dev::jb_qtol: columns orthogonal to ~1e-10 after the last sweep
 constexpr int kJbInnerSweeps = 1;  // inner sweeps per Gram block (early exit when a sweep rotates nothing)
 constexpr int kJbScratch = 144;   // doubles of per-warp scratch: M[8][9], J[8][9]
 
@@ -373,7 +373,8 @@ __host__ __device__ inline JbDims jb_dims(int n) {
 }
 inline size_t jb_smem_bytes(int n, int nwarps) {
     JbDims g = jb_dims(n);
-    return ((size_t)g.ld * g.nb * 4 + (size_t)nwarps * kJbScratch) * sizeof(double);
+    // matrix + per-warp scratch + the tracked 4x4 Gram matrix of every column block (jb_sweeps2)
+    return ((size_t)g.ld * g.nb * 4 + (size_t)nwarps * kJbScratch + (size_t)16 * g.nb) * sizeof(double);
 }
 
 #ifdef XTBB200_JB_TIMING
@@ -536,6 +537,213 @@ __device__ __forceinline__ int jb_sweeps(double* G, double* Msh, volatile int* v
     return sweep;
 }
 
+// ---------------------------------------------------------------------------------------------
+// jb_sweeps2: the sweep loop of k_jacobi_blk, second form.  Same tournament, same dataflow synchronisation, same
+// convergence logic as jb_sweeps; three changes that cut the work per block pair:
+//   * Gram matrix: only the 4x4 cross block W_P^T W_Q is formed (18 DMMAs at n = 144 instead of 36: rows 0-3 of the A
+//     fragment and columns 0-3 of the B fragment take one half of the k range, rows / columns 4-7 the other half, so
+//     the two diagonal quadrants of the accumulator are the two half sums).  The 4x4 Gram matrix of each block with
+//     itself is tracked in shared memory (Tsh): it is the corresponding corner of J^T M J of the block's previous
+//     rotation.  The first tournament step of every sweep forms the full 8x8 Gram matrix and refreshes the tracked ones.
+//   * inner solve: away from the first step of a sweep only the 16 rotations between a column of P and a column of Q
+//     are done (4 rounds of 4 disjoint rotations instead of the 7 rounds of the full 8x8 tournament): the columns of a
+//     block were orthogonalised against each other when the block was last rotated, what the later rotations put back
+//     is of second order and is removed by the full tournament of the next sweep's first step.  Sweep counts are
+//     unchanged (checked on the SCC sequences of the ensemble and on random matrices).
+//   * rotation parameters: the kernel is bound by shared-memory wavefronts and by the FP64 pipe, which DMMA and the
+//     scalar FP64 instructions share at the same flop rate (tools/microbench/fp64_pipes.cu: a DMMA occupies it 16
+//     cycles per SM sub-partition, a DFMA 2.2).  The angle is evaluated in single precision and only the final
+//     normalisation of (c, s) to unit length is done in double precision (7 FP64 instructions instead of 33): the
+//     rotation is orthogonal to rounding for any angle, and an angle with 2^-22 relative error leaves 1e-7 of the
+//     eliminated element, far below what the other rotations of the sweep put back.
+// G must be scaled so that its column norms are O(1) (k_jacobi_blk divides by sigma): the angles are formed in float.
+// Msh: this warp's kJbScratch doubles; Tsh: 16 doubles per column block.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void jb_rotation(double app, double aqq, double apq, double& c, double& s) {
+    c = 1.0; s = 0.0;
+    const float appf = (float)app, aqqf = (float)aqq, apqf = (float)apq;
+    if (apqf * apqf > 4.930380657631324e-32f * appf * aqqf) {     // |apq| > eps sqrt(app aqq)
+        // rotation angle (|theta| <= pi/4) in single precision: t = sgn(tau) 2 apq / (|tau| + hypot(tau, 2 apq))
+        const float tf = (float)(aqq - app), af = 2.0f * apqf;
+        const float s2 = fmaf(tf, tf, af * af);
+        const float t = __fdividef(tf >= 0.0f ? af : -af, fabsf(tf) + s2 * rsqrtf(s2));
+        const float cf = rsqrtf(fmaf(t, t, 1.0f));
+        // (c, s) of unit length to double precision: c0^2 + s0^2 = 1 + e with |e| ~ 1e-7, scale by (1 + e)^(-1/2) to O(e^3)
+        const double c0 = (double)cf, s0 = (double)(t * cf);
+        const double e = fma(c0, c0, fma(s0, s0, -1.0));
+        const double k = fma(e, fma(e, 0.375, -0.5), 1.0);
+        c = c0 * k; s = s0 * k;
+    }
+}
+
+__device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, volatile int* ver, int n, double tol, int inner,
+                                          int maxsweeps, double qtol
+#ifdef XTBB200_JB_TIMING
+                                          , long long* jbt, long long& jbt0
+#endif
+) {
+    const JbDims dm = jb_dims(n);
+    const int nr = dm.nr, ld = dm.ld, nb = dm.nb;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    double* Jsh = Msh + 72;
+    if (tid < 64) ver[tid] = 0;
+    __syncthreads();
+    const double tol2 = tol * tol;
+    const double qtol2 = qtol * qtol;
+    const int nbp = nb / 2;
+    const int l4 = lane >> 2, l3 = lane & 3;
+    // inner rotations: lane = (slot, idx).  pairtab: slot's pair in round s7 of the full tournament of the 8 panel columns
+    // (6 bits per round); crosstab: slot's pair (slot, 4 + (slot + r) % 4) in round r of the P x Q rotations
+    const int slot = lane >> 3, idx = lane & 7;
+    unsigned long long pairtab = 0;
+    unsigned int crosstab = 0;
+    for (int s7 = 0; s7 < 7; ++s7) {
+        int p, q;
+        if (slot == 0) { p = s7; q = 7; }
+        else { const int a = (s7 + slot) % 7, b = (s7 - slot + 7) % 7; p = a < b ? a : b; q = a < b ? b : a; }
+        pairtab |= (unsigned long long)(p | (q << 3)) << (6 * s7);
+    }
+    for (int r = 0; r < 4; ++r) crosstab |= (unsigned int)(slot | ((4 + (slot + r) % 4) << 3)) << (6 * r);
+    // tracked block Gram: lane e -> block (e >> 4 ? Q : P), element (i, j)
+    const int tb = lane >> 4, ti = (lane >> 2) & 3, tj = lane & 3;
+    const int tm = (4 * tb + ti) * 9 + 4 * tb + tj;
+    int sweep = 0;
+    int tstep = 0;
+    for (; sweep < maxsweeps; ++sweep) {
+        int rotated = 0, rotbig = 0;
+        for (int step = 0; step < nb - 1; ++step, ++tstep) {
+            const bool full = step == 0;
+            for (int pr = warp; pr < nbp; pr += nwarps) {
+                int P, Q;
+                jb_block_pair(step, pr, nb, P, Q);
+                if (lane == 0) { while (ver[P] < tstep || ver[Q] < tstep) {} }
+                __syncwarp();
+                __threadfence_block();
+                JB_T(5);
+                if (4 * Q >= n && !full) { jb_publish(ver, P, Q, tstep + 1, lane); continue; }   // dummy block
+                double* Tb = Tsh + 16 * (tb ? Q : P) + 4 * ti + tj;
+                if (full) {
+                    // ---- full 8x8 Gram matrix (A and B fragment are the same element)
+                    const int gcol = l4 < 4 ? 4 * P + l4 : 4 * Q + l4 - 4;
+                    const double* wp = G + (size_t)ld * gcol + l3;
+                    double a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, e0 = 0, e1 = 0;
+                    int k0 = 0;
+                    for (; k0 + 16 <= nr; k0 += 16) {
+                        const double w0 = wp[k0], w1 = wp[k0 + 4], w2 = wp[k0 + 8], w3 = wp[k0 + 12];
+                        dmma_884(a0, a1, w0, w0); dmma_884(b0, b1, w1, w1);
+                        dmma_884(c0, c1, w2, w2); dmma_884(e0, e1, w3, w3);
+                    }
+                    for (; k0 < nr; k0 += 4) { const double w0 = wp[k0]; dmma_884(a0, a1, w0, w0); }
+                    __syncwarp();
+                    Msh[l4 * 9 + 2 * l3] = (a0 + b0) + (c0 + e0); Msh[l4 * 9 + 2 * l3 + 1] = (a1 + b1) + (c1 + e1);
+                } else {
+                    // ---- cross block only: lanes l4 < 4 take rows k0..k0+3, lanes l4 >= 4 rows k0+4..k0+7
+                    const int cc = l4 & 3, hh = (l4 >> 2) * 4;
+                    const double* pa = G + (size_t)ld * (4 * P + cc) + hh + l3;
+                    const double* pb = G + (size_t)ld * (4 * Q + cc) + hh + l3;
+                    double a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0;
+                    int k0 = 0;
+                    for (; k0 + 24 <= nr; k0 += 24) {
+                        const double x0 = pa[k0], y0 = pb[k0], x1 = pa[k0 + 8], y1 = pb[k0 + 8], x2 = pa[k0 + 16], y2 = pb[k0 + 16];
+                        dmma_884(a0, a1, x0, y0); dmma_884(b0, b1, x1, y1); dmma_884(c0, c1, x2, y2);
+                    }
+                    for (; k0 < nr; k0 += 8) { const double x0 = pa[k0], y0 = pb[k0]; dmma_884(a0, a1, x0, y0); }
+                    double m0 = (a0 + b0) + c0, m1 = (a1 + b1) + c1;
+                    m0 += __shfl_down_sync(0xffffffffu, m0, 18);
+                    m1 += __shfl_down_sync(0xffffffffu, m1, 18);
+                    const double tv = *Tb;
+                    __syncwarp();
+                    if (l4 < 4 && l3 < 2) {
+                        Msh[l4 * 9 + 4 + 2 * l3] = m0; Msh[l4 * 9 + 5 + 2 * l3] = m1;
+                        Msh[(4 + 2 * l3) * 9 + l4] = m0; Msh[(5 + 2 * l3) * 9 + l4] = m1;
+                    }
+                    Msh[tm] = tv;
+                }
+                __syncwarp();
+                JB_T(1);
+                // ---- needs work?  (squared form of |M_pq| > tol sqrt(M_pp M_qq))
+                const int j0 = 2 * l3, j1 = 2 * l3 + 1;
+                const double dii = Msh[l4 * 10], dj0 = Msh[j0 * 10], dj1 = Msh[j1 * 10];
+                const double m0 = Msh[l4 * 9 + j0], m1 = Msh[l4 * 9 + j1];
+                int need = 0, big = 0;
+                {
+                    const double d0 = dii * dj0, d1 = dii * dj1;
+                    if (j0 != l4) { need |= (m0 * m0 > tol2 * d0) ? 1 : 0; big |= (m0 * m0 > qtol2 * d0) ? 1 : 0; }
+                    if (j1 != l4) { need |= (m1 * m1 > tol2 * d1) ? 1 : 0; big |= (m1 * m1 > qtol2 * d1) ? 1 : 0; }
+                }
+                if (!__any_sync(0xffffffffu, need)) {
+                    if (full) *Tb = Msh[tm];
+                    jb_publish(ver, P, Q, tstep + 1, lane);
+                    continue;
+                }
+                rotated = 1;
+                if (qtol2 > 0.0) { if (__any_sync(0xffffffffu, big)) rotbig = 1; }
+                else rotbig = 1;
+                // ---- two-sided Jacobi on the 8x8 Gram matrix; lane = (pair slot, row/column index)
+                __syncwarp();
+                Jsh[l4 * 9 + j0] = (l4 == j0) ? 1.0 : 0.0; Jsh[l4 * 9 + j1] = (l4 == j1) ? 1.0 : 0.0;
+                __syncwarp();
+                {
+                    const unsigned long long tab = full ? pairtab : (unsigned long long)crosstab;
+                    const int nround = full ? 7 : 4;
+#pragma unroll 1
+                    for (int s7 = 0; s7 < nround; ++s7) {
+                        const int p = (int)(tab >> (6 * s7)) & 7, q = (int)(tab >> (6 * s7 + 3)) & 7;
+                        double c, sn;
+                        jb_rotation(Msh[p * 10], Msh[q * 10], Msh[p * 9 + q], c, sn);
+                        __syncwarp();
+                        {   // columns p,q of M and J (row idx)
+                            const double mp = Msh[idx * 9 + p], mq = Msh[idx * 9 + q];
+                            const double jp = Jsh[idx * 9 + p], jq = Jsh[idx * 9 + q];
+                            Msh[idx * 9 + p] = c * mp - sn * mq; Msh[idx * 9 + q] = sn * mp + c * mq;
+                            Jsh[idx * 9 + p] = c * jp - sn * jq; Jsh[idx * 9 + q] = sn * jp + c * jq;
+                        }
+                        __syncwarp();
+                        {   // rows p,q of M (column idx)
+                            const double mp = Msh[p * 9 + idx], mq = Msh[q * 9 + idx];
+                            Msh[p * 9 + idx] = c * mp - sn * mq; Msh[q * 9 + idx] = sn * mp + c * mq;
+                        }
+                        __syncwarp();
+                    }
+                }
+                JB_T(2);
+                // ---- tracked Gram matrices of the two blocks
+                *Tb = Msh[tm];
+                // ---- W <- W J
+                {
+                    const double bj0 = Jsh[l3 * 9 + l4], bj1 = Jsh[(4 + l3) * 9 + l4];
+                    const double* ap0 = G + (size_t)ld * (4 * P + l3) + l4;
+                    const double* ap1 = G + (size_t)ld * (4 * Q + l3) + l4;
+                    const int oc = (l3 < 2) ? 4 * P + 2 * l3 : 4 * Q + 2 * l3 - 4;
+                    double* op = G + (size_t)ld * oc + l4;
+                    for (int r0 = 0; r0 < nr; r0 += 32) {
+                        double xa[4], xb[4], y0[4], y1[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const bool on = r0 + 8 * u < nr;
+                            xa[u] = on ? ap0[r0 + 8 * u] : 0.0;
+                            xb[u] = on ? ap1[r0 + 8 * u] : 0.0;
+                            y0[u] = 0.0; y1[u] = 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) dmma_884(y0[u], y1[u], xa[u], bj0);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) dmma_884(y0[u], y1[u], xb[u], bj1);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (r0 + 8 * u < nr) { op[r0 + 8 * u] = y0[u]; op[r0 + 8 * u + ld] = y1[u]; }
+                    }
+                }
+                jb_publish(ver, P, Q, tstep + 1, lane);
+                JB_T(3);
+            }
+        }
+        if (!__syncthreads_or(rotated)) { ++sweep; break; }
+        if (!__syncthreads_or(rotbig)) { ++sweep; break; }
+    }
+    return sweep;
+}
+
 // Conformer ensembles: the first diagonalisation of a molecule has no eigenvectors of its own to start from, but the
 // converged ones of another conformer of the same molecule are a far better start than the unit matrix (any orthogonal
 // Z is a valid start of the one-sided method).  The first molecule of every group of identical compositions (its
@@ -552,7 +760,8 @@ __global__ void k_lead_copy(Dev d) {
     if (t == 0) d.st[im].zvalid = 1;
 }
 
-// phase: 0 all molecules, 1 leaders only, 2 followers only
+// phase: 0 all molecules, 1 leaders only, 2 followers only.  V: 0 = jb_sweeps, 1 = jb_sweeps2 (G scaled by 1/sigma)
+template <int V>
 __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d, int phase) {
 #ifdef XTBB200_JB_TIMING
     long long jbt[6] = {0, 0, 0, 0, 0, 0}, jbt0 = clock64();
@@ -594,6 +803,7 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d, int phase) {
     }
     __syncthreads();
     const double sigma = s_sigma;
+    const double gscale = V == 1 ? 1.0 / sigma : 1.0;    // V = 1: columns of G of norm O(1), eigenvalue = sigma (norm - 1)
     const int ncolp = nb * 4;
     const bool warm = st.zvalid != 0;
     {
@@ -606,16 +816,27 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d, int phase) {
                 const long long a = i + (long long)n * j;
                 if (warm) v = T[a] + sigma * Zp[a];
                 else v = 0.5 * (A[a] + A[j + (long long)n * i]) + (i == j ? sigma : 0.0);
+                v *= gscale;
             }
             G[t] = v;
         }
     }
     const double tol = d.jb_tol > 0.0 ? d.jb_tol : 8.0 * sqrt((double)n) * 2.220446049250313e-16;
+    int sweep;
+    if (V == 1) {
+        double* Tsh = smem + (size_t)ld * nb * 4 + (size_t)nwarps * kJbScratch;
 #ifdef XTBB200_JB_TIMING
-    const int sweep = jb_sweeps(G, Msh, ver, n, tol, d.jb_inner, 40, d.jb_qtol, jbt, jbt0);
+        sweep = jb_sweeps2(G, Msh, Tsh, ver, n, tol, d.jb_inner, 40, d.jb_qtol, jbt, jbt0);
 #else
-    const int sweep = jb_sweeps(G, Msh, ver, n, tol, d.jb_inner, 40, d.jb_qtol);
+        sweep = jb_sweeps2(G, Msh, Tsh, ver, n, tol, d.jb_inner, 40, d.jb_qtol);
 #endif
+    } else {
+#ifdef XTBB200_JB_TIMING
+        sweep = jb_sweeps(G, Msh, ver, n, tol, d.jb_inner, 40, d.jb_qtol, jbt, jbt0);
+#else
+        sweep = jb_sweeps(G, Msh, ver, n, tol, d.jb_inner, 40, d.jb_qtol);
+#endif
+    }
     // eigenvalues, ordering, normalised eigenvectors
     double* nrm = d.nrm + m.ao0;
     for (int j = tid; j < n; j += nt) {
@@ -632,7 +853,7 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d, int phase) {
         const double v = nrm[j];
         int rk = 0;
         for (int k = 0; k < n; ++k) { const double w = nrm[k]; rk += (w < v || (w == v && k < j)) ? 1 : 0; }
-        emo[rk] = v - sigma;
+        emo[rk] = V == 1 ? sigma * (v - 1.0) : v - sigma;
         rank[j] = rk;
     }
     __syncthreads();
