@@ -357,9 +357,13 @@ __device__ __forceinline__ void jb_publish(volatile int* ver, int P, int Q, int 
     if (lane == 0) { ver[P] = v; ver[Q] = v; }
 }
 
-constexpr double kJbQuadraticStop = 1.0e-5;   // default of Dev::jb_qtol: columns orthogonal to ~1e-10 after the last sweep
+// default of Dev::jb_qtol.  The columns of G are then orthogonal to ~1e-14 after the last sweep, but the rotation angle between
+// two eigenvectors is larger than the non-orthogonality of their columns by (lambda + sigma) / (2 gap): at 1e-5 the density
+// matrix carried errors of 1e-6 (energy still right to 3e-12, gradients only to 1e-7, numerical Hessians to 1e-5)
+constexpr double kJbQuadraticStop = 1.0e-7;
 constexpr int kJbInnerSweeps = 1;  // inner sweeps per Gram block (early exit when a sweep rotates nothing)
-constexpr int kJbScratch = 144;   // doubles of per-warp scratch: M[8][9], J[8][9]
+constexpr int kJbScratch = 192;   // doubles of per-warp scratch: M and J, 8 x 8 with row stride 9 (jb_sweeps) or kJs (jb_sweeps2)
+constexpr int kJs = 12;           // jb_sweeps2: with lane = (idx = lane >> 2, slot = lane & 3) the P x Q rounds are free of bank conflicts
 
 struct JbDims { int nr, ld, nb; };
 __host__ __device__ inline JbDims jb_dims(int n) {
@@ -585,7 +589,7 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
     const JbDims dm = jb_dims(n);
     const int nr = dm.nr, ld = dm.ld, nb = dm.nb;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    double* Jsh = Msh + 72;
+    double* Jsh = Msh + 8 * kJs;
     if (tid < 64) ver[tid] = 0;
     __syncthreads();
     const double tol2 = tol * tol;
@@ -594,7 +598,7 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
     const int l4 = lane >> 2, l3 = lane & 3;
     // inner rotations: lane = (slot, idx).  pairtab: slot's pair in round s7 of the full tournament of the 8 panel columns
     // (6 bits per round); crosstab: slot's pair (slot, 4 + (slot + r) % 4) in round r of the P x Q rotations
-    const int slot = lane >> 3, idx = lane & 7;
+    const int slot = lane & 3, idx = lane >> 2;
     unsigned long long pairtab = 0;
     unsigned int crosstab = 0;
     for (int s7 = 0; s7 < 7; ++s7) {
@@ -606,7 +610,7 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
     for (int r = 0; r < 4; ++r) crosstab |= (unsigned int)(slot | ((4 + (slot + r) % 4) << 3)) << (6 * r);
     // tracked block Gram: lane e -> block (e >> 4 ? Q : P), element (i, j)
     const int tb = lane >> 4, ti = (lane >> 2) & 3, tj = lane & 3;
-    const int tm = (4 * tb + ti) * 9 + 4 * tb + tj;
+    const int tm = (4 * tb + ti) * kJs + 4 * tb + tj;
     int sweep = 0;
     int tstep = 0;
     for (; sweep < maxsweeps; ++sweep) {
@@ -635,7 +639,7 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                     }
                     for (; k0 < nr; k0 += 4) { const double w0 = wp[k0]; dmma_884(a0, a1, w0, w0); }
                     __syncwarp();
-                    Msh[l4 * 9 + 2 * l3] = (a0 + b0) + (c0 + e0); Msh[l4 * 9 + 2 * l3 + 1] = (a1 + b1) + (c1 + e1);
+                    Msh[l4 * kJs + 2 * l3] = (a0 + b0) + (c0 + e0); Msh[l4 * kJs + 2 * l3 + 1] = (a1 + b1) + (c1 + e1);
                 } else {
                     // ---- cross block only: lanes l4 < 4 take rows k0..k0+3, lanes l4 >= 4 rows k0+4..k0+7
                     const int cc = l4 & 3, hh = (l4 >> 2) * 4;
@@ -654,8 +658,8 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                     const double tv = *Tb;
                     __syncwarp();
                     if (l4 < 4 && l3 < 2) {
-                        Msh[l4 * 9 + 4 + 2 * l3] = m0; Msh[l4 * 9 + 5 + 2 * l3] = m1;
-                        Msh[(4 + 2 * l3) * 9 + l4] = m0; Msh[(5 + 2 * l3) * 9 + l4] = m1;
+                        Msh[l4 * kJs + 4 + 2 * l3] = m0; Msh[l4 * kJs + 5 + 2 * l3] = m1;
+                        Msh[(4 + 2 * l3) * kJs + l4] = m0; Msh[(5 + 2 * l3) * kJs + l4] = m1;
                     }
                     Msh[tm] = tv;
                 }
@@ -663,8 +667,8 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                 JB_T(1);
                 // ---- needs work?  (squared form of |M_pq| > tol sqrt(M_pp M_qq))
                 const int j0 = 2 * l3, j1 = 2 * l3 + 1;
-                const double dii = Msh[l4 * 10], dj0 = Msh[j0 * 10], dj1 = Msh[j1 * 10];
-                const double m0 = Msh[l4 * 9 + j0], m1 = Msh[l4 * 9 + j1];
+                const double dii = Msh[l4 * (kJs + 1)], dj0 = Msh[j0 * (kJs + 1)], dj1 = Msh[j1 * (kJs + 1)];
+                const double m0 = Msh[l4 * kJs + j0], m1 = Msh[l4 * kJs + j1];
                 int need = 0, big = 0;
                 {
                     const double d0 = dii * dj0, d1 = dii * dj1;
@@ -681,7 +685,7 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                 else rotbig = 1;
                 // ---- two-sided Jacobi on the 8x8 Gram matrix; lane = (pair slot, row/column index)
                 __syncwarp();
-                Jsh[l4 * 9 + j0] = (l4 == j0) ? 1.0 : 0.0; Jsh[l4 * 9 + j1] = (l4 == j1) ? 1.0 : 0.0;
+                Jsh[l4 * kJs + j0] = (l4 == j0) ? 1.0 : 0.0; Jsh[l4 * kJs + j1] = (l4 == j1) ? 1.0 : 0.0;
                 __syncwarp();
                 {
                     const unsigned long long tab = full ? pairtab : (unsigned long long)crosstab;
@@ -690,18 +694,18 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                     for (int s7 = 0; s7 < nround; ++s7) {
                         const int p = (int)(tab >> (6 * s7)) & 7, q = (int)(tab >> (6 * s7 + 3)) & 7;
                         double c, sn;
-                        jb_rotation(Msh[p * 10], Msh[q * 10], Msh[p * 9 + q], c, sn);
+                        jb_rotation(Msh[p * (kJs + 1)], Msh[q * (kJs + 1)], Msh[p * kJs + q], c, sn);
                         __syncwarp();
                         {   // columns p,q of M and J (row idx)
-                            const double mp = Msh[idx * 9 + p], mq = Msh[idx * 9 + q];
-                            const double jp = Jsh[idx * 9 + p], jq = Jsh[idx * 9 + q];
-                            Msh[idx * 9 + p] = c * mp - sn * mq; Msh[idx * 9 + q] = sn * mp + c * mq;
-                            Jsh[idx * 9 + p] = c * jp - sn * jq; Jsh[idx * 9 + q] = sn * jp + c * jq;
+                            const double mp = Msh[idx * kJs + p], mq = Msh[idx * kJs + q];
+                            const double jp = Jsh[idx * kJs + p], jq = Jsh[idx * kJs + q];
+                            Msh[idx * kJs + p] = c * mp - sn * mq; Msh[idx * kJs + q] = sn * mp + c * mq;
+                            Jsh[idx * kJs + p] = c * jp - sn * jq; Jsh[idx * kJs + q] = sn * jp + c * jq;
                         }
                         __syncwarp();
                         {   // rows p,q of M (column idx)
-                            const double mp = Msh[p * 9 + idx], mq = Msh[q * 9 + idx];
-                            Msh[p * 9 + idx] = c * mp - sn * mq; Msh[q * 9 + idx] = sn * mp + c * mq;
+                            const double mp = Msh[p * kJs + idx], mq = Msh[q * kJs + idx];
+                            Msh[p * kJs + idx] = c * mp - sn * mq; Msh[q * kJs + idx] = sn * mp + c * mq;
                         }
                         __syncwarp();
                     }
@@ -711,7 +715,7 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                 *Tb = Msh[tm];
                 // ---- W <- W J
                 {
-                    const double bj0 = Jsh[l3 * 9 + l4], bj1 = Jsh[(4 + l3) * 9 + l4];
+                    const double bj0 = Jsh[l3 * kJs + l4], bj1 = Jsh[(4 + l3) * kJs + l4];
                     const double* ap0 = G + (size_t)ld * (4 * P + l3) + l4;
                     const double* ap1 = G + (size_t)ld * (4 * Q + l3) + l4;
                     const int oc = (l3 < 2) ? 4 * P + 2 * l3 : 4 * Q + 2 * l3 - 4;
@@ -729,9 +733,14 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                         for (int u = 0; u < 4; ++u) dmma_884(y0[u], y1[u], xa[u], bj0);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) dmma_884(y0[u], y1[u], xb[u], bj1);
+                        // lanes l3 < 2 store their first column while lanes l3 >= 2 store their second one and vice versa: the
+                        // columns of P and Q start in the same bank, so this keeps every store free of bank conflicts
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
-                            if (r0 + 8 * u < nr) { op[r0 + 8 * u] = y0[u]; op[r0 + 8 * u + ld] = y1[u]; }
+                            if (r0 + 8 * u < nr) {
+                                op[r0 + 8 * u + (l3 < 2 ? 0 : ld)] = l3 < 2 ? y0[u] : y1[u];
+                                op[r0 + 8 * u + (l3 < 2 ? ld : 0)] = l3 < 2 ? y1[u] : y0[u];
+                            }
                     }
                 }
                 jb_publish(ver, P, Q, tstep + 1, lane);
