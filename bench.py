@@ -616,8 +616,8 @@ def single_system(name):
     if name == "protein":
         from xtb_b200.polypeptide import make_polypeptide
         Z, xyz, info = make_polypeptide()
-        return Z, xyz, "synthetic polypeptide %s, %d atoms, seed %d (stand-in of crambin: same composition, SURVEY 8(d) C2)" % (
-            info["formula"], len(Z), info["seed"])
+        return Z, xyz, ("synthetic polypeptide %s, %d atoms, seed %d: covalently connected random coil with crambin's sequence, "
+                        "free thiols (crambin C202H315N55O64S6 + 6 H; SURVEY 8(d) C2)" % (info["formula"], len(Z), info["seed"]))
     if name == "taxol6":
         Z, xyz = make_peptide_cluster(load_kat("taxol"), 6, gap=20.0)
         return Z, xyz, "6 x taxol, 20 bohr apart"
@@ -629,8 +629,8 @@ def run_single(ctx, args, molecule=None, steps=None, warmup=None):
     """BASELINE configs[0] / configs[1]: wall time of ONE GFN2-xTB single point + gradient through the xtb.h C ABI
     (xtb_newMolecule / xtb_loadGFN2xTB / xtb_singlepoint / xtb_getEnergy / xtb_getGradient), fresh results handle (EEQ
     guess) per step.  --molecule caffeine: the 24-atom molecule of `xtb caffeine.xyz --gfn 2 --grad`; --molecule
-    protein: a seeded, covalently connected 642-atom polypeptide of crambin's composition C202H315N55O64S6
-    (xtb_b200/polypeptide.py; crambin's coordinates are not available offline)."""
+    protein: a seeded, covalently connected 648-atom polypeptide with crambin's sequence, C202H321N55O64S6 = crambin's
+    composition with free thiols (xtb_b200/polypeptide.py; crambin's coordinates are not available offline)."""
     import xtb_b200
     torch = ctx.torch
     if ctx.rank != 0:

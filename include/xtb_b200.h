@@ -151,6 +151,19 @@ int xtbb200_getResult(xtbb200_TBatch batch, int imol, double* out16);
 int xtbb200_getResultsInfo(void* xtb_results, double* hl_gap_eV, int* scc_iterations);
 /* screening list lengths ndp, nqp and total Jacobi sweeps of one molecule */
 int xtbb200_getCounts(xtbb200_TBatch batch, int imol, int* ndp, int* nqp, int* sweeps);
+/* diagnostic (parity of the discrete decisions): when switched on, the kernels of the following
+ * single points count every cutoff / screening decision where they take it.  counts12, per molecule, unordered pairs:
+ * [0] shell pairs of build_SDQH0 with r^2 <= 2000 (src/intgrad.f90:904), [1] their primitive pairs with
+ * alpha_i alpha_j r^2 <= intcut (alpha_i + alpha_j) (intgrad.f90:917-928), [2] off-site shell pairs of build_dSDQH0 with
+ * r^2 <= 1600 (src/xtb/hamiltonian.F90:634,672), [3] their surviving primitive pairs (intgrad.f90:981-1004), [4] pairs of
+ * the GFN / covalent coordination numbers (1e-12 <= r^2 <= 1600, src/disp/coordinationnumber.F90:427), [5] pairs of the
+ * erf / D4 coordination numbers (r^2 <= 1600, src/disp/ncoord.f90:46,495,601), [6] repulsion pairs (1e-8 <= r^2 <= 1600,
+ * src/xtb/repulsion.F90:107), [7] non-zero reference pairs of the D4 self-consistent matrix (r^2 <= 72^2 and
+ * gw_i gw_j >= 1e-7, src/disp/dftd4.F90:674-713), [8] D4 gradient pairs (1e-10 <= r^2 <= 60^2, dftd4.F90:1894), [9] ATM
+ * triples with all edges r^2 <= 40^2 (dftd4.F90:2126-2140), [10] bond-order pairs r^2 < 100 (src/scc_core.f90:1232),
+ * [11] reserved.  Not defined for a batch split over several GPUs. */
+int xtbb200_setDecisionCounting(xtbb200_TBatch batch, int on);
+int xtbb200_getDecisionCounts(xtbb200_TBatch batch, int imol, long long* counts12);
 
 /* copy a named device array of the whole batch to the host; names: gradient q qsh dipm qp cn emo
  * focc S dpint qpint H0 H0_noovlp P C wbo gab3 gab5 jmat dispmat gw xyz pcgradient ...; with a solvation model:

@@ -305,6 +305,14 @@ inline void cao2sao(double blk[6][6], int li, int lj) {
     }
 }
 
+// Counters of the discrete decisions of one single point (same numbering as
+// include/xtb_b200.h xtbb200_getDecisionCounts), incremented where the decisions are taken; unordered pairs / triples.
+long long g_cnt[12];
+inline void cnt_add(int k, long long v) {
+#pragma omp atomic
+    g_cnt[k] += v;
+}
+
 // get_multiints, intgrad.f90:879-955.  out[c][mi][mj], c = 0..9 (S, D(3), Q(6)), Cartesian.
 void get_multiints(const Shell& si, const Shell& sj, const double* ri, const double* rj, const double* point,
                    double intcut, double out[10][6][6]) {
@@ -312,6 +320,7 @@ void get_multiints(const Shell& si, const Shell& sj, const double* ri, const dou
     double rij2 = 0;
     for (int k = 0; k < 3; ++k) rij2 += (ri[k] - rj[k]) * (ri[k] - rj[k]);
     if (rij2 > 2000.0) return;
+    cnt_add(0, 1);
     const double sqrtpi = std::sqrt(PI);
     const int naoi = NCART[si.l], naoj = NCART[sj.l];
     for (int ip = 0; ip < si.nprim; ++ip) {
@@ -320,6 +329,7 @@ void get_multiints(const Shell& si, const Shell& sj, const double* ri, const dou
             double alpj = sj.alp[jp];
             double est = alpi * alpj * rij2;
             if (est > intcut * (alpi + alpj)) continue;
+            cnt_add(1, 1);
             double ab = 1.0 / (alpi + alpj);
             est = est * ab;
             double sq = sqrtpi * std::sqrt(ab);
@@ -386,6 +396,7 @@ void get_grad_multiint(const Shell& si, const Shell& sj, const double* ri, const
             double alpj = sj.alp[jp];
             double est = alpi * alpj * rij2;
             if (est > intcut * (alpi + alpj)) continue;
+            cnt_add(3, 1);
             double ab = 1.0 / (alpi + alpj);
             est = est * ab;
             double sq = sqrtpi * std::sqrt(ab);
@@ -495,6 +506,7 @@ void cn_lp(const Oracle& o, bool gfn, dvec& cn, std::vector<CNPair>& pairs) {
             double rij[3], r2 = 0;
             for (int k = 0; k < 3; ++k) { rij[k] = R(o, i)[k] - R(o, j)[k]; r2 += rij[k] * rij[k]; }
             if (r2 > cutoff2 || r2 < 1.0e-12) continue;
+            if (gfn) cnt_add(4, 1);
             double r1 = std::sqrt(r2);
             int zi = o.Z[i], zj = o.Z[j];
             double rc = el_cov_rad_d3(zi) + el_cov_rad_d3(zj);
@@ -539,6 +551,7 @@ void ncoord_erf_d4(const Oracle& o, bool d4, dvec& cn) {
             double r2 = 0;
             for (int k = 0; k < 3; ++k) { double t = R(o, j)[k] - R(o, i)[k]; r2 += t * t; }
             if (r2 > 1600.0) continue;
+            if (d4) cnt_add(5, 1);
             double r = std::sqrt(r2);
             double rco = el_ncoord_rcov(o.Z[j]) + el_ncoord_rcov(o.Z[i]);
             double den = 1.0;
@@ -1382,6 +1395,7 @@ int singlepoint(Oracle& o) {
     const int nao = b.nao, nsh = b.nshell;
     auto& D = o.d;
     std::memset(o.timers, 0, sizeof(o.timers));
+    std::memset(g_cnt, 0, sizeof(g_cnt));
     double t0 = now_s();
 
     // ---- guess (src/api/interface.f90:82-101, src/xtb/calculator.f90:432-496)
@@ -1483,6 +1497,7 @@ int singlepoint(Oracle& o) {
                 double rij[3], r2 = 0;
                 for (int k = 0; k < 3; ++k) { rij[k] = R(o, i)[k] - R(o, j)[k]; r2 += rij[k] * rij[k]; }
                 if (r2 > 1600.0 || r2 < 1.0e-8) continue;
+                cnt_add(6, 1);
                 double r1 = std::sqrt(r2);
                 double t16 = std::pow(r1, kExp), t26 = std::exp(-alpha * t16), t27 = std::pow(r1, 1.0);
                 double dE = zeff * t26 / t27;
@@ -1549,6 +1564,7 @@ int singlepoint(Oracle& o) {
                     for (int jj = 0; jj < d4_refn[ja - 1]; ++jj) {
                         double gwgw = gw[k + ii] * gw[l + jj];
                         if (gwgw < 1.0e-7) continue;
+                        cnt_add(7, 1);
                         double c6ab = c6[ii * 7 + jj];
                         double c8 = r4r2ij * c6ab;
                         double v = gw[k + ii] * gw[l + jj] * (-s6 * (c6ab * oor6) - s8 * (c8 * oor8) - 0.0);
@@ -1968,6 +1984,7 @@ int singlepoint(Oracle& o) {
                     if (rij2 > 1600.0) continue;
                     for (int is = b.sh0[iat]; is < b.sh0[iat] + b.nsh[iat]; ++is)
                         for (int js = b.sh0[jat]; js < b.sh0[jat] + b.nsh[jat]; ++js) {
+                            cnt_add(2, 1);
                             const Shell& si = b.sh[is];
                             const Shell& sj = b.sh[js];
                             double hii = selfE[is], hjj = selfE[js];
@@ -2182,6 +2199,7 @@ int singlepoint(Oracle& o) {
                         double rij[3], r2 = 0;
                         for (int k = 0; k < 3; ++k) { rij[k] = R(o, i)[k] - R(o, j)[k]; r2 += rij[k] * rij[k]; }
                         if (r2 > 3600.0 || r2 < 1.0e-10) continue;
+                        cnt_add(8, 1);
                         double t6 = 1. / (r2 * r2 * r2 + std::pow(r0, 6)), t8 = 1. / (r2 * r2 * r2 * r2 + std::pow(r0, 8));
                         double d6 = -6 * r2 * r2 * t6 * t6, d8 = -8 * r2 * r2 * r2 * t8 * t8;
                         double disp = s6 * t6 + s8 * r4r2ij * t8;
@@ -2227,6 +2245,7 @@ int singlepoint(Oracle& o) {
                             if (r2ik > 1600.0) continue;
                             for (int k = 0; k < 3; ++k) { rjk[k] = R(o, kat)[k] - R(o, jat)[k]; r2jk += rjk[k] * rjk[k]; }
                             if (r2jk > 1600.0) continue;
+                            cnt_add(9, 1);
                             int ati = o.Z[iat], atj = o.Z[jat], atk = o.Z[kat];
                             double c6ij = c6a[(size_t)jat * n + iat], c6ik = c6a[(size_t)kat * n + iat], c6jk = c6a[(size_t)kat * n + jat];
                             double cij = a1 * std::sqrt(3.0 * el_sqrt_zr4r2(ati) * el_sqrt_zr4r2(atj)) + a2;
@@ -2349,6 +2368,7 @@ int singlepoint(Oracle& o) {
     // ---- properties (scf_module.F90:856-913)
     dvec wbo((size_t)n * n, 0.0);
     {
+        bool fac_first = true;      // the pair counter of the first call only (open shell: alpha, then beta)
         auto wib = [&](const double* Pm, double fac) {
             dvec PS(nn);
             scipy_dgemm_("N", "N", &nao, &nao, &nao, &one, Pm, &nao, S.data(), &nao, &zero, PS.data(), &nao);
@@ -2356,6 +2376,7 @@ int singlepoint(Oracle& o) {
                 for (int j = 0; j < i; ++j) {
                     double rab = 0, xsum = 0;
                     for (int k = 0; k < 3; ++k) { double t = R(o, i)[k] - R(o, j)[k]; rab += t * t; }
+                    if (rab < 100.0 && fac_first) cnt_add(10, 1);
                     if (rab < 100.0)
                         for (int k = b.ao0_at[i]; k < b.ao0_at[i] + b.nao_at[i]; ++k)
                             for (int m = b.ao0_at[j]; m < b.ao0_at[j] + b.nao_at[j]; ++m)
@@ -2368,7 +2389,7 @@ int singlepoint(Oracle& o) {
             dvec Pa(nn), Pb(nn);
             dmat(nao, focca.data(), H.data(), Pa.data());
             dmat(nao, foccb.data(), H.data(), Pb.data());
-            wib(Pa.data(), 2.0); wib(Pb.data(), 2.0);
+            wib(Pa.data(), 2.0); fac_first = false; wib(Pb.data(), 2.0);
         }
     }
     dvec dip(3, 0.0);
@@ -2393,6 +2414,11 @@ int singlepoint(Oracle& o) {
     D["selfenergy"] = selfE; D["radcn"] = radcn; D["shellshift"] = shellShift; D["vs"] = vs; D["vd"] = vd; D["vq"] = vq;
     D["zsh"] = zsh;
     D["timers"] = dvec(o.timers, o.timers + 8);
+    {
+        dvec dc(12);
+        for (int k = 0; k < 12; ++k) dc[k] = (double)g_cnt[k];
+        D["decisions"] = dc;
+    }
     o.iv["mdlst"] = mdlst; o.iv["mqlst"] = mqlst;
     o.iv["info"] = ivec{jter, converged ? 1 : 0, nao, nsh, ndp, nqp, nel, nopen, ihomo, ndim, nbr};
     o.timers[0] += now_s() - t0;

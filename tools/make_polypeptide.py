@@ -53,17 +53,16 @@ SIDE = {
     "L": [("CG", "C", ("N", "CA", "CB"), 1.530, 116.3, ("chi", 0, 0.0)),
           ("CD1", "C", ("CA", "CB", "CG"), 1.521, 110.5, ("chi", 1, 0.0)),
           ("CD2", "C", ("CA", "CB", "CG"), 1.521, 110.5, ("chi", 1, 120.0))],
-    "P": [("CG", "C", ("N", "CA", "CB"), 1.495, 104.5, 27.0),
-          ("CD", "C", ("CA", "CB", "CG"), 1.507, 105.5, -34.0)],
+    "P": [],      # ring atoms CD, CG are placed from the backbone (build_residue)
     "F": [("CG", "C", ("N", "CA", "CB"), 1.502, 113.8, ("chi", 0, 0.0)),
-          ("CD1", "C", ("CA", "CB", "CG"), 1.390, 120.7, ("chi", 1, 0.0)),
-          ("CD2", "C", ("CA", "CB", "CG"), 1.390, 120.7, ("chi", 1, 180.0)),
+          ("CD1", "C", ("CA", "CB", "CG"), 1.390, 120.0, ("chi", 1, 0.0)),
+          ("CD2", "C", ("CA", "CB", "CG"), 1.390, 120.0, ("chi", 1, 180.0)),
           ("CE1", "C", ("CB", "CG", "CD1"), 1.390, 120.0, 180.0),
           ("CE2", "C", ("CB", "CG", "CD2"), 1.390, 120.0, 180.0),
           ("CZ", "C", ("CG", "CD1", "CE1"), 1.390, 120.0, 0.0)],
     "Y": [("CG", "C", ("N", "CA", "CB"), 1.512, 113.8, ("chi", 0, 0.0)),
-          ("CD1", "C", ("CA", "CB", "CG"), 1.390, 120.8, ("chi", 1, 0.0)),
-          ("CD2", "C", ("CA", "CB", "CG"), 1.390, 120.8, ("chi", 1, 180.0)),
+          ("CD1", "C", ("CA", "CB", "CG"), 1.390, 120.0, ("chi", 1, 0.0)),
+          ("CD2", "C", ("CA", "CB", "CG"), 1.390, 120.0, ("chi", 1, 180.0)),
           ("CE1", "C", ("CB", "CG", "CD1"), 1.390, 120.0, 180.0),
           ("CE2", "C", ("CB", "CG", "CD2"), 1.390, 120.0, 180.0),
           ("CZ", "C", ("CG", "CD1", "CE1"), 1.390, 120.0, 0.0),
@@ -170,8 +169,29 @@ def build_residue(aa, prev, phi, psi_prev, chis, first):
         res.heavy["C"] = place(pC, res.heavy["N"], res.heavy["CA"], 1.525, 111.0, phi)
     res.el.update({"N": "N", "CA": "C", "C": "C"})
     if aa != "G":
-        res.heavy["CB"] = place(res.heavy["N"], res.heavy["C"], res.heavy["CA"], 1.530, 110.1, -122.6)
+        # L configuration; proline: N-CA-CB closed to 103.5 degrees so that the ring can close (CB-CD 2.40 A)
+        res.heavy["CB"] = place(res.heavy["N"], res.heavy["C"], res.heavy["CA"], 1.530, 110.1, 114.0 if aa == "P" else 122.6)
         res.el["CB"] = "C"
+    if aa == "P":
+        # CD on the amide nitrogen, cis to the preceding CA; CG closes the ring: 1.495 A from CB, 1.507 A from CD, on the side
+        # away from N / CA, 0.35 A out of the plane (pucker)
+        if first:
+            cd = place(res.heavy["C"], res.heavy["CA"], res.heavy["N"], 1.473, 111.0, 15.0)
+        else:
+            cd = place(prev.heavy["CA"], prev.heavy["C"], res.heavy["N"], 1.473, 125.0, 0.0)
+        cb = res.heavy["CB"]
+        mid, ax = 0.5 * (cb + cd), unit(cd - cb)
+        half = 0.5 * np.linalg.norm(cd - cb)
+        # sphere intersection (the two bond lengths differ by 0.012 A: treated as equal, 1.501 A)
+        h = np.sqrt(max(1.501 ** 2 - half ** 2, 0.0))
+        away = mid - 0.5 * (res.heavy["N"] + res.heavy["CA"])
+        away = unit(away - np.dot(away, ax) * ax)
+        nrm = unit(np.cross(ax, away))
+        ang = np.arcsin(min(0.35 / h, 1.0))
+        res.heavy["CG"] = mid + h * (np.cos(ang) * away + np.sin(ang) * nrm)
+        res.heavy["CD"] = cd
+        res.el["CG"] = "C"
+        res.el["CD"] = "C"
     for name, el, refs, r, th, tor in SIDE[aa]:
         if isinstance(tor, tuple):
             tor = chis[tor[1]] + tor[2]
@@ -247,11 +267,28 @@ def clashes(el_new, x_new, el_old, x_old, skip_bonded=None):
 
 
 def internal_clash(res):
-    """Side chain against the own backbone and hydrogens: anything closer than 1.5 A that is not a bond / geminal pair."""
+    """Atoms of one residue that are three bonds apart (1-4) or further must keep non-bonded distances."""
     el, x = atoms_of(res)
-    d = np.linalg.norm(x[:, None] - x[None, :], axis=2) + 10.0 * np.eye(len(x))
+    names = list(res.heavy)
+    n = len(x)
+    adj = np.zeros((n, n), dtype=bool)
+    bonds = [("N", "CA"), ("CA", "C"), ("C", "O")] + ([("CA", "CB")] if res.aa != "G" else []) + BONDS[res.aa]
+    if "OXT" in res.heavy:
+        bonds.append(("C", "OXT"))
+    for a, b in bonds:
+        adj[names.index(a), names.index(b)] = adj[names.index(b), names.index(a)] = True
+    for k, (_, parent) in enumerate(res.hyd):
+        adj[len(names) + k, names.index(parent)] = adj[names.index(parent), len(names) + k] = True
+    a1 = adj.astype(int)
+    a2 = (a1 @ a1) > 0
+    a3 = (a1 @ a1 @ a1) > 0
+    near = adj | a2 | np.eye(n, dtype=bool)          # 1-2, 1-3
+    d = np.linalg.norm(x[:, None] - x[None, :], axis=2)
     h = np.array([e == "H" for e in el])
-    lim = np.where(h[:, None] & h[None, :], 1.45, np.where(h[:, None] | h[None, :], 0.9, 1.15))
+    hh, hx = h[:, None] & h[None, :], h[:, None] ^ h[None, :]
+    lim14 = np.where(hh, 1.9, np.where(hx, 2.15, 2.45))
+    lim15 = np.where(hh, 2.0, np.where(hx, 2.3, 2.8))
+    lim = np.where(near, 0.0, np.where(a3, lim14, lim15))
     return bool(np.any(d < lim))
 
 
@@ -288,7 +325,7 @@ def generate(seed=1, max_tries=60):
                     d = np.linalg.norm(x_n[:, None] - x_o[None, :], axis=2)
                     hn = np.array([e == "H" for e in el_n])[:, None]
                     ho = np.array([e == "H" for e in el_o])[None, :]
-                    lim = np.where(hn & ho, 1.7, np.where(hn | ho, 1.9, 2.2))
+                    lim = np.where(hn & ho, 2.0, np.where(hn | ho, 2.2, 2.4))
                     near = np.zeros_like(d, dtype=bool)
                     names_n = list(res.heavy) + ["H:" + p for _, p in res.hyd]
                     names_o = list(chain[k].heavy) + ["H:" + p for _, p in chain[k].hyd]
@@ -320,12 +357,14 @@ def generate(seed=1, max_tries=60):
                 raise RuntimeError("generator failed")
             chain = chain[:i]
             psis = psis[:i]
-    el, xyz = [], []
-    for res in chain:
+    el, xyz, labels = [], [], []
+    for i, res in enumerate(chain):
         e, x = atoms_of(res)
         el += e
         xyz.append(x)
+        labels += ["%s%d:%s" % (res.aa, i + 1, k) for k in res.heavy] + ["%s%d:H(%s)" % (res.aa, i + 1, p) for _, p in res.hyd]
     xyz = np.concatenate(xyz)
+    generate.labels = labels
     return el, xyz
 
 
@@ -342,7 +381,7 @@ def main():
     d = np.linalg.norm(xyz[:, None] - xyz[None, :], axis=2) + 10 * np.eye(len(el))
     out = {"name": "polypeptide_1crn", "comment": "crambin-sequence random coil, seed 1 (tools/make_polypeptide.py)", "formula": f,
            "charge": 0, "uhf": 0, "numbers": [ZNUM[e] for e in el], "xyz": (xyz * AA2BOHR).round(10).tolist(),
-           "min_distance_angstrom": float(d.min()), "extent_angstrom": (xyz.max(0) - xyz.min(0)).round(2).tolist()}
+           "labels": generate.labels, "min_distance_angstrom": float(d.min()), "extent_angstrom": (xyz.max(0) - xyz.min(0)).round(2).tolist()}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "polypeptide_1crn.json")
     with open(path, "w") as fh:
         json.dump(out, fh)

@@ -788,6 +788,20 @@ int xtbb200_getCounts(xtbb200_TBatch batch, int imol, int* ndp, int* nqp, int* s
     return 0;
     XTBB_CATCH(-1)
 }
+int xtbb200_setDecisionCounting(xtbb200_TBatch batch, int on) {
+    XTBB_TRY
+    if (!batch) throw std::runtime_error("batch is not allocated");
+    batch->b->set_decision_counting(on != 0);
+    return 0;
+    XTBB_CATCH(-1)
+}
+int xtbb200_getDecisionCounts(xtbb200_TBatch batch, int imol, long long* counts12) {
+    XTBB_TRY
+    if (!batch || !counts12) throw std::runtime_error("batch is not allocated");
+    batch->b->decision_counts(imol, counts12);
+    return 0;
+    XTBB_CATCH(-1)
+}
 int xtbb200_getArrayLen(xtbb200_TBatch batch, const char* name, size_t* len) {
     XTBB_TRY
     if (!batch) throw std::runtime_error("batch is not allocated");

@@ -45,6 +45,11 @@ struct MolState {
 };
 
 // device pointer bundle
+constexpr int kNCnt = 12;
+// 0 shell pairs of build_SDQH0 inside r^2 <= 2000, 1 their surviving primitive pairs, 2 off-site shell pairs of
+// build_dSDQH0 inside r^2 <= 1600, 3 their surviving primitive pairs, 4 pairs of the gfn / covalent CN, 5 pairs of the
+// erf / D4 CN, 6 repulsion pairs, 7 non-zero reference pairs of the D4 self-consistent matrix, 8 D4 gradient pairs,
+// 9 ATM triples, 10 bond-order pairs
 struct Dev {
     const MolDesc* mol;
     MolState* st;
@@ -67,6 +72,9 @@ struct Dev {
     double jb_tol;    // relative orthogonality threshold of the block Jacobi solver (0: 8 sqrt(n) eps)
     double jb_qtol;   // quadratic stop of the block Jacobi solver: skip the verification sweep after a sweep whose largest
                       // relative off-diagonal was below this (0: always verify)
+    // diagnostic: counters of the discrete decisions (cutoffs, screening) at the places where the kernels take them,
+    // kNCnt per molecule; nullptr unless xtbb200_setDecisionCounting switched them on
+    unsigned long long* cnt;
     // per atom
     double *xyz, *cn, *cn_cov, *cn_d4, *cn_erf, *radcn;
     double *q, *q_out, *dipm, *dipm_out, *qp, *qp_out;
@@ -160,6 +168,11 @@ __device__ __forceinline__ long long shard_pair_cta(const Dev& d) { return (long
 __device__ __forceinline__ int lin0(int a, int b) {  // packed index, 0-based (src/lin_mod.f90:28-36)
     int mx = a > b ? a : b, mn = a > b ? b : a;
     return mn + mx * (mx + 1) / 2;
+}
+
+// one decision of molecule im counted (diagnostic, see Dev::cnt)
+__device__ __forceinline__ void cnt_add(const Dev& d, int im, int k, unsigned long long v) {
+    if (d.cnt && v) atomicAdd(d.cnt + (size_t)kNCnt * im + k, v);
 }
 
 }  // namespace xtbb200

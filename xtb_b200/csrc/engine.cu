@@ -196,6 +196,7 @@ struct Batch::Impl {
     bool fits_blk = false, fits_scalar = false;
     // diagnostic knobs, read once at construction and only under XTBB200_TUNING=1 (common.cuh: tuning_env)
     double knob_jb_tol = 0.0, knob_jb_qtol = kJbQuadraticStop;
+    unsigned long long* cnt_buf = nullptr;   // decision counters (diagnostic), allocated by set_decision_counting
     int knob_jb_inner = kJbInnerSweeps;
     int knob_jb_variant = 1;    // 1: jb_sweeps2 (cross-block Gram, unnormalised rotations), 0: jb_sweeps
     bool knob_no_cluster_eig = false, knob_cta_chol = false;
@@ -702,6 +703,7 @@ int Batch::singlepoint(bool restart) {
     d.jb_inner = I.knob_jb_inner;
     d.jb_tol = I.knob_jb_tol;
     d.jb_qtol = I.knob_jb_qtol;
+    if (d.cnt) XTB_CUDA_CHECK(cudaMemsetAsync(d.cnt, 0, sizeof(unsigned long long) * kNCnt * nmol, st));
     if (!I.ev_phase[0]) for (auto& e : I.ev_phase) cudaEventCreate(&e);
     if (!I.ev_comm[0]) for (auto& e : I.ev_comm) cudaEventCreate(&e);
     cudaEvent_t* ev = I.ev_phase;
@@ -1075,6 +1077,26 @@ int Batch::scc_passes() const { return p_->scc_passes; }
 int Batch::launches() const { return p_->launches; }
 void Batch::timings(float* t3) const { t3[0] = p_->t_setup; t3[1] = p_->t_scc; t3[2] = p_->t_grad; }
 float Batch::factorisation_ms() const { return p_->t_fact; }
+
+void Batch::set_decision_counting(bool on) {
+    Impl& I = *p_;
+    XTB_CUDA_CHECK(cudaSetDevice(I.device));
+    if (on && !I.cnt_buf) I.cnt_buf = I.dalloc<unsigned long long>((size_t)kNCnt * I.d.nmol);
+    I.d.cnt = on ? I.cnt_buf : nullptr;
+}
+
+void Batch::decision_counts(int i, long long* out) const {
+    const Impl& I = *p_;
+    if (!I.d.cnt) throw std::runtime_error("decision counting is off (xtbb200_setDecisionCounting)");
+    if (i < 0 || i >= I.d.nmol) throw std::runtime_error("invalid molecule index");
+    XTB_CUDA_CHECK(cudaSetDevice(I.device));
+    unsigned long long h[kNCnt];
+    XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+    XTB_CUDA_CHECK(cudaMemcpy(h, I.d.cnt + (size_t)kNCnt * i, sizeof(h), cudaMemcpyDeviceToHost));
+    // the pair kernels visit ordered pairs (i, j != i), the ATM kernel every triple from each of its three atoms
+    static const int div[kNCnt] = {1, 1, 1, 1, 2, 2, 2, 2, 2, 3, 2, 1};
+    for (int k = 0; k < kNCnt; ++k) out[k] = (long long)(h[k] / div[k]);
+}
 
 MolResult Batch::result(int i) const {
     const MolState& s = p_->h_state[i];

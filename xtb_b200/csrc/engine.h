@@ -101,6 +101,10 @@ class Batch {
     int scc_passes() const;          // batch-wide SCC passes of the last call (= max niter over molecules)
 
     MolResult result(int i) const;
+    // diagnostic: count the discrete decisions (cutoffs, primitive screening) where the kernels take them during the
+    // next single points (common.cuh: kNCnt counters per molecule, unordered pairs / triples)
+    void set_decision_counting(bool on);
+    void decision_counts(int i, long long* out) const;
     void fetch(const char* name, double* out) const;   // device -> host copy of a named array
     size_t fetch_len(const char* name) const;
     void fetch_mask(unsigned char* out) const;

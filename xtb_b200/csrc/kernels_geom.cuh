@@ -35,8 +35,10 @@ __global__ void k_cn(Dev d) {
         double dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
         double r2 = dx * dx + dy * dy + dz * dz;
         if (r2 > 1600.0) continue;
+        cnt_add(d, blockIdx.y, 5, 1);
         double r1 = sqrt(r2);
         if (r2 >= 1.0e-12) {
+            cnt_add(d, blockIdx.y, 4, 1);
             double rc = ai.rcov + aj.rcov;
             cg += exp_count(10.0, r1, rc) * exp_count(20.0, r1, rc + 2);
             cc += en_den(ai.en, aj.en) * 0.5 * (1.0 + erf(-7.5 * (r1 - rc) / rc));
@@ -157,6 +159,7 @@ __global__ void k_dispmat(Dev d) {
         double r2 = dx * dx + dy * dy + dz * dz;
         double gk = d.gw[m.ref0 + k], gl = d.gw[m.ref0 + l];
         if (r2 <= 72.0 * 72.0 && !(gk * gl < 1.0e-7)) {
+            cnt_add(d, blockIdx.y, 7, 1);
             double r4r2ij = 3.0 * a.r4r2 * b.r4r2;
             double cutoff = 0.52 * sqrt(r4r2ij) + 5.0;
             double oor6 = 1.0 / (r2 * r2 * r2 + pow(cutoff, 6.0));
@@ -188,6 +191,7 @@ __global__ void k_repulsion(Dev d) {
         double rij[3] = {xi[0] - xj[0], xi[1] - xj[1], xi[2] - xj[2]};
         double r2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
         if (r2 > 1600.0 || r2 < 1.0e-8) continue;
+        cnt_add(d, blockIdx.y, 6, 1);
         double alpha = sqrt(ai.rep_alpha * aj.rep_alpha);
         double zeff = ai.rep_zeff * aj.rep_zeff;
         double kExp = (ai.Z > 2 || aj.Z > 2) ? 1.5 : 1.0;

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
         if (lane < 4) out[lane] = 0.0;
         return;
     }
+    if (lane == 0) cnt_add(d, blockIdx.y, 2, 1);
     const int nci = c_ncart[li], ncj = c_ncart[lj], npi = si.nprim, npj = sj.nprim;
     const int nsi = c_nsph[li], nsj = c_nsph[lj];
     if (lane < 6) { s_alp[warp][0][lane] = si.alp[lane]; s_cont[warp][0][lane] = si.cont[lane]; }
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
             const double alpj = s_alp[warp][1][jp];
             double est = alpi * alpj * rij2;
             if (est > intcut * (alpi + alpj)) continue;
+            if (c == 0) cnt_add(d, blockIdx.y, 3, 1);
             const double ab = 1.0 / (alpi + alpj);
             est = est * ab;
             const double sq = sqrtpi * sqrt(ab);
@@ -408,6 +410,7 @@ __global__ void k_grad_pairs(Dev d) {
         const double rij[3] = {xi[0] - xj[0], xi[1] - xj[1], xi[2] - xj[2]};
         const double r2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
         if (!(r2 > 3600.0 || r2 < 1.0e-10)) {
+            cnt_add(d, blockIdx.y, 8, 1);
             const double r4r2ij = 3 * ai.r4r2 * aj.r4r2;
             const double r0 = 0.52 * sqrt(r4r2ij) + 5.0;
             const double t6 = 1. / (r2 * r2 * r2 + pow(r0, 6.0)), t8 = 1. / (r2 * r2 * r2 * r2 + pow(r0, 8.0));
@@ -515,6 +518,7 @@ __global__ void __launch_bounds__(128) k_grad_atm(Dev d) {
             const double rjk[3] = {rik[0] - rij[0], rik[1] - rij[1], rik[2] - rij[2]};
             const double r2jk = rjk[0] * rjk[0] + rjk[1] * rjk[1] + rjk[2] * rjk[2];
             if (r2jk > 1600.0) continue;
+            cnt_add(d, blockIdx.y, 9, 1);
             const double r4c = d.atoms[m.at0 + c].r4r2;
             const double c6ik = c6a[c], c6jk = c6b[c];
             const double cik = 0.52 * sqrt(3.0 * r4a * r4c) + 5.0, cjk = 0.52 * sqrt(3.0 * r4b * r4c) + 5.0;
@@ -619,6 +623,7 @@ __global__ void k_wbo(Dev d, int open_path) {
         const double* xj = d.xyz + 3 * (m.at0 + j);
         const double r2 = (xi[0] - xj[0]) * (xi[0] - xj[0]) + (xi[1] - xj[1]) * (xi[1] - xj[1]) + (xi[2] - xj[2]) * (xi[2] - xj[2]);
         if (r2 < 100.0) {
+            cnt_add(d, blockIdx.y, 10, 1);
             const AtomPar& a = d.atoms[m.at0 + i];
             const AtomPar& b = d.atoms[m.at0 + j];
             const double* PS = d.W + m.mat0;

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(kIntWarps * 32, 6) k_sdqh0(Dev d) {
     const double intcut = d.intcut;
     const double sqrtpi = sqrt(kPi);
     const int ncomp = nci * ncj;
+    if (lane == 0 && rij2 <= 2000.0) cnt_add(d, blockIdx.y, 0, 1);
     for (int c = lane; c < 36; c += 32)
         for (int k = 0; k < 10; ++k) s_blk[warp][k][c] = 0.0;
     __syncwarp();
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(kIntWarps * 32, 6) k_sdqh0(Dev d) {
                 const double alpj = s_alp[warp][1][jp];
                 double est = alpi * alpj * rij2;
                 if (est > intcut * (alpi + alpj)) continue;
+                if (c == 0) cnt_add(d, blockIdx.y, 1, 1);
                 const double ab = 1.0 / (alpi + alpj);
                 est = est * ab;
                 const double sq = sqrtpi * sqrt(ab);

@@ -86,6 +86,8 @@ def load_library():
         "xtbb200_getDeviceBytes": (ctypes.c_size_t, [vp]),
         "xtbb200_getResultsInfo": (ci, [vp, _c_double_p, _c_int_p]),
         "xtbb200_getResult": (ci, [vp, ci, _c_double_p]), "xtbb200_getCounts": (ci, [vp, ci, _c_int_p, _c_int_p, _c_int_p]),
+        "xtbb200_setDecisionCounting": (ci, [vp, ci]),
+        "xtbb200_getDecisionCounts": (ci, [vp, ci, ctypes.POINTER(ctypes.c_longlong)]),
         "xtbb200_getArrayLen": (ci, [vp, cp, ctypes.POINTER(ctypes.c_size_t)]),
         "xtbb200_getArray": (ci, [vp, cp, _c_double_p, ctypes.c_size_t]),
         "xtbb200_getOffsets": (ci, [vp, ci, ctypes.POINTER(ctypes.c_longlong)]),
@@ -522,6 +524,18 @@ class BatchCalculator:
         a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         self._check(self._lib.xtbb200_getCounts(self._b, int(imol), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return dict(ndp=a.value, nqp=b.value, sweeps=c.value)
+
+    DECISION_COUNTS = ("sdq_shell_pairs", "sdq_primitive_pairs", "grad_shell_pairs", "grad_primitive_pairs", "cn_pairs",
+                       "cn_d4_pairs", "repulsion_pairs", "d4_matrix_entries", "d4_gradient_pairs", "atm_triples", "wbo_pairs")
+
+    def set_decision_counting(self, on=True):
+        """Diagnostic: let the kernels count their cutoff / screening decisions during the next single points."""
+        self._check(self._lib.xtbb200_setDecisionCounting(self._b, int(bool(on))))
+
+    def decision_counts(self, imol):
+        out = (ctypes.c_longlong * 12)()
+        self._check(self._lib.xtbb200_getDecisionCounts(self._b, int(imol), out))
+        return dict(zip(self.DECISION_COUNTS, list(out)))
 
     def sizes(self, imol):
         a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
