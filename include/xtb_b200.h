@@ -139,6 +139,9 @@ int xtbb200_singlepointDevice(xtbb200_TBatch batch, const double* positions_dev,
 /* sizes */
 int xtbb200_getNMol(xtbb200_TBatch batch);
 int xtbb200_getSizes(xtbb200_TBatch batch, int imol, int* natoms, int* nshell, int* nao);
+/* number of valence electrons and of unpaired electrons (wfn%nel, wfn%nopen; header of the xtbrestart file,
+ * src/restart.f90:190-192) */
+int xtbb200_getElectrons(xtbb200_TBatch batch, int imol, int* nel, int* nopen);
 size_t xtbb200_getDeviceBytes(xtbb200_TBatch batch);
 
 /* per-molecule scalar results of the last call:
@@ -161,7 +164,8 @@ int xtbb200_getCounts(xtbb200_TBatch batch, int imol, int* ndp, int* nqp, int* s
  * src/xtb/repulsion.F90:107), [7] non-zero reference pairs of the D4 self-consistent matrix (r^2 <= 72^2 and
  * gw_i gw_j >= 1e-7, src/disp/dftd4.F90:674-713), [8] D4 gradient pairs (1e-10 <= r^2 <= 60^2, dftd4.F90:1894), [9] ATM
  * triples with all edges r^2 <= 40^2 (dftd4.F90:2126-2140), [10] bond-order pairs r^2 < 100 (src/scc_core.f90:1232),
- * [11] reserved.  Not defined for a batch split over several GPUs. */
+ * [11] pairs of the Born radii whose psi term re-uses the preceding pair's 1/r (src/solv/born.f90:292-309, see
+ * kernels_solv.cuh born_stale_r1; only with a solvation model).  Not defined for a batch split over several GPUs. */
 int xtbb200_setDecisionCounting(xtbb200_TBatch batch, int on);
 int xtbb200_getDecisionCounts(xtbb200_TBatch batch, int imol, long long* counts12);
 

@@ -1081,10 +1081,13 @@ bool solv_init(const Oracle& o, Solv& sv) {
     return true;
 }
 
-// one descreening term psi_i <- j and its radial derivative factor (d psi / d r) / r: src/solv/born.f90:130-330
-inline bool born_psi_term(double r, double rho_j, double vdw_i, double& g, double& dg) {
-    const double r1 = 1.0 / r;
+// one descreening term psi_i <- j and its radial derivative factor (d psi / d r) / r: src/solv/born.f90:130-330.
+// r1: the value the reference's variable r1 holds when the non-overlap formula is evaluated (1/r of this pair except in
+// the case described at solv_update)
+inline bool born_psi_term(double r, double r1_nonoverlap, double rho_j, double vdw_i, double& g, double& dg) {
+    double r1 = 1.0 / r;
     if (r >= vdw_i + rho_j) {   // no overlap
+        r1 = r1_nonoverlap;
         const double ap = r + rho_j, am = r - rho_j, ab = ap * am, rhab = rho_j / ab, lnab = 0.5 * std::log(am / ap) * r1;
         g = rhab + lnab;
         dg = -2.0 * rhab / ab + (rhab - lnab) * r1 * r1;
@@ -1106,22 +1109,32 @@ void solv_update(const Oracle& o, Solv& sv) {
     const int n = sv.n;
     const size_t nn = (size_t)n * n;
     // ---- compute_psi / compute_bornr (GBOBC II): src/solv/born.f90:36-84,87-345
-    // (the reference re-uses 1/r of the preceding pair when only the j <- i term of an i-overlaps-j pair exists,
-    //  born.f90:224-262; the restatement always takes 1/r of the pair itself)
+    // The reference keeps 1/r in a variable r1 that every branch of its pair loop sets before use, except one: when the
+    // descreening sphere of j lies completely inside the van der Waals sphere of i (r + rho_j <= vdw_i, nothing to add to
+    // psi_i) while i does not overlap j, the j <- i term (born.f90:292-309, `case(1)`) is evaluated with the r1 left behind
+    // by the preceding pair of the list.  Reproduced here: r1_state is that variable, the pair order is the list's
+    // (i ascending, j < i ascending, gbsa.f90:883-906); before the first assignment the reference's value is undefined, 0 here.
     sv.brad.assign(n, 0.0); sv.brdr.assign(3 * nn, 0.0);
     const double lr2 = sv.lrcut * sv.lrcut;
+    double r1_state = 0.0;
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < i; ++j) {
             double dr[3], r2 = 0;
             for (int k = 0; k < 3; ++k) { dr[k] = R(o, i)[k] - R(o, j)[k]; r2 += dr[k] * dr[k]; }
             if (!(r2 < lr2)) continue;
             const double r = std::sqrt(r2);
+            const bool ovij = r < sv.vdwr[i] + sv.rho[j], ovji = r < sv.rho[i] + sv.vdwr[j];
+            const bool ij_term = !ovij || r + sv.rho[j] > sv.vdwr[i], ji_term = !ovji || r + sv.rho[i] > sv.vdwr[j];
+            // which branches assign r1: every one that evaluates a term, except the j <- i term of case(1)
+            const bool stale = ovij && !ovji && !ij_term;
+            if (stale) cnt_add(11, 1);
+            else if (ij_term || ji_term) r1_state = 1.0 / r;
             double g, dg;
-            if (born_psi_term(r, sv.rho[j], sv.vdwr[i], g, dg)) {
+            if (born_psi_term(r, 1.0 / r, sv.rho[j], sv.vdwr[i], g, dg)) {
                 sv.brad[i] += g;
                 for (int k = 0; k < 3; ++k) { sv.brdr[3 * ((size_t)i * n + i) + k] += dg * dr[k]; sv.brdr[3 * ((size_t)i * n + j) + k] -= dg * dr[k]; }
             }
-            if (born_psi_term(r, sv.rho[i], sv.vdwr[j], g, dg)) {
+            if (born_psi_term(r, stale ? r1_state : 1.0 / r, sv.rho[i], sv.vdwr[j], g, dg)) {
                 sv.brad[j] += g;
                 for (int k = 0; k < 3; ++k) { sv.brdr[3 * ((size_t)j * n + j) + k] -= dg * dr[k]; sv.brdr[3 * ((size_t)j * n + i) + k] += dg * dr[k]; }
             }

@@ -102,6 +102,66 @@ def test_cli_alpb_single_point(kat, tmp_path):
     assert np.max(np.abs(g - o.get("gradient").reshape(-1, 3))) < 1e-6
 
 
+def test_xtbrestart_round_trip_and_mismatch_rules(tmp_path):
+    """The binary restart file (src/restart.f90:33-86, 182-200): record layout byte for byte, round trip, and the
+    reference's acceptance rules (dimension mismatch refuses, electron count / multiplicity / version only warn)."""
+    rng = np.random.default_rng(1)
+    nat, nsh = 5, 9
+    qsh, dipm, qp = rng.normal(size=nsh), rng.normal(size=(nat, 3)), rng.normal(size=(nat, 6))
+    p = str(tmp_path / "xtbrestart")
+    cli.write_xtbrestart(qsh, dipm, qp, nat, nel=14, nopen=0, path=p)
+    raw = open(p, "rb").read()
+    # Fortran sequential unformatted records: marker, payload, marker
+    assert len(raw) == (4 + 48 + 4) + (4 + 8 * nsh + 4) + (4 + 24 * nat + 4) + (4 + 48 * nat + 4)
+    assert np.frombuffer(raw[:4], "<i4")[0] == 48 and np.frombuffer(raw[52:56], "<i4")[0] == 48
+    assert np.frombuffer(raw[4:52], "<i8").tolist() == [2, 2, nat, nsh, 14, 0]
+    assert np.frombuffer(raw[56:60], "<i4")[0] == 8 * nsh
+    assert np.array_equal(np.frombuffer(raw[60:60 + 8 * nsh], "<f8"), qsh)
+    # dipm(3, n), qp(6, n) in Fortran order = [atom][component] in C order
+    off = 60 + 8 * nsh + 4 + 4
+    assert np.array_equal(np.frombuffer(raw[off:off + 24 * nat], "<f8").reshape(nat, 3), dipm)
+    got = cli.read_xtbrestart(nat, nsh, 14, 0, path=p)
+    assert all(np.array_equal(a, b) for a, b in zip(got, (qsh, dipm, qp)))
+    msgs = []
+    assert cli.read_xtbrestart(nat, nsh, 16, 2, path=p, warn=msgs.append) is not None
+    assert msgs == ["Number of electron missmatch in restart file.", "Multiplicity missmatch in restart file."]
+    msgs.clear()
+    assert cli.read_xtbrestart(nat + 1, nsh, 14, 0, path=p, warn=msgs.append) is None
+    assert cli.read_xtbrestart(nat, nsh - 1, 14, 0, path=p, warn=msgs.append) is None
+    assert msgs == ["Dimension missmatch in restart file."] * 2
+    assert cli.read_xtbrestart(nat, nsh, path=str(tmp_path / "missing")) is None
+    open(p, "wb").write(raw[:70])                        # truncated file
+    assert cli.read_xtbrestart(nat, nsh, 14, 0, path=p) is None
+
+
+@pytest.mark.gpu
+def test_cli_restarts_from_xtbrestart(kat, tmp_path):
+    """A second run in the same directory starts from the first run's xtbrestart (fewer SCC iterations, same energy); the
+    file's shell charges and multipoles are the converged ones of the engine."""
+    import re
+    s = kat["caffeine"]
+    (tmp_path / "caffeine.xyz").write_text("%d\n\n" % len(s["numbers"]) + "".join(
+        "%-2s %20.14f %20.14f %20.14f\n" % (cli.SYMBOLS[z - 1], *(r / cli.AATOAU)) for z, r in zip(s["numbers"], s["xyz"])))
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    runs = []
+    for k in range(2):
+        out = subprocess.run([sys.executable, "-m", "xtb_b200", "caffeine.xyz", "--gfn", "2"], cwd=tmp_path, env=env,
+                             capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        niter = int(re.search(r"after (\d+) iterations", out.stdout).group(1))
+        energy = float(re.search(r"total energy\s+(-?\d+\.\d+)", out.stdout).group(1))
+        runs.append((niter, energy, "taken from xtbrestart" in out.stdout))
+    assert runs[0][2] is False and runs[1][2] is True
+    assert runs[1][0] < runs[0][0]
+    assert abs(runs[1][1] - runs[0][1]) < 1e-7
+    import xtb_b200
+    b = xtb_b200.BatchCalculator([s["numbers"]])
+    b.singlepoint(s["xyz"] if False else cli.read_geometry(str(tmp_path / "caffeine.xyz"))[1])
+    qsh, dipm, qp = cli.read_xtbrestart(len(s["numbers"]), b.sizes(0)["nshell"], path=str(tmp_path / "xtbrestart"))
+    assert np.max(np.abs(qsh - b.array("qsh"))) < 1e-5 and np.max(np.abs(dipm.ravel() - b.array("dipm"))) < 1e-5
+    assert np.max(np.abs(qp.ravel() - b.array("qp"))) < 1e-5
+
+
 def test_md_restart_and_trajectory_formats(tmp_path):
     """mdrestart (src/dynamic.f90:814-844: '-1.0' + 6D22.14 per atom) round trip and the xyz frames of xtb.trj."""
     rng = np.random.default_rng(0)

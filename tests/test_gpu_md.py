@@ -83,3 +83,38 @@ def test_md_invariants_at_ensemble_size(xb, kat):
         com = (mass[rep][:, None] * xyz[rep]).sum(axis=0) / mass[rep].sum()
         ang = (mass[rep][:, None] * np.cross(xyz[rep] - com, vel[rep])).sum(axis=0)
         assert np.max(np.abs(p)) < 1e-9 and np.max(np.abs(ang)) < 1e-7
+
+
+def test_md_start_state_from_the_reference_rules(xb, kat):
+    """Start state of an MD run pinned on what the reference's source prescribes, without the Python MD restatement:
+    masses (src/param/atomicmass.f90:37-39 times amutoau of src/mctc/convert.f90:51-55, hydrogens at hmass),
+    the constraint list of init_shake (src/shake_module.f90:77-148: X-H bonds to the nearest neighbour, or every pair within
+    1.2 x the covalent radii whose Wiberg bond order exceeds 0.5), the degrees of freedom 3N - ncons (src/dynamic.f90:292-294)
+    and the start velocities of mdinitu (src/dynamic.f90:304-308, 850-877): every component has the magnitude
+    sqrt(2 e / m) with e = T kB nfreedom / (2 * 3N), doubled for hydrogen."""
+    s = kat["caffeine"]                                   # C8 H10 N4 O2: 25 covalent bonds, 10 of them C-H
+    Z, xyz = np.asarray(s["numbers"]), np.asarray(s["xyz"], dtype=float).reshape(-1, 3)
+    n = len(Z)
+    amutoau = 1.660539040e-27 / 9.10938356e-31
+    kB = 3.166808578545117e-06
+    amu = {1: 1.00794075, 6: 12.01073590, 7: 14.00670321, 8: 15.99940492}
+    # bonds from the geometry alone (1.2 x covalent radii of the reference's atomicRad table are ample here: use 1.3 A for
+    # X-H and 1.7 A for pairs of C / N / O, which separates bonded from non-bonded pairs of caffeine by > 0.5 A)
+    dist = np.linalg.norm(xyz[:, None] - xyz[None], axis=2) * 0.52917726
+    isH = Z == 1
+    bonded = (dist < np.where(isH[:, None] | isH[None, :], 1.3, 1.7)) & ~np.eye(n, dtype=bool)
+    assert bonded.sum() // 2 == 25 and (bonded & (isH[:, None] ^ isH[None, :])).sum() // 2 == 10
+    for mode, hmass, thermostat in ((2, 4, True), (1, 0, False)):
+        b = xb.BatchCalculator([Z])
+        ncons = b.md_init(xyz, temperature=298.15, thermostat=thermostat, shake=mode, hmass=hmass, seed=11)
+        assert ncons == (25 if mode == 2 else 10)
+        mass = b.array("md_mass")
+        ref_mass = np.array([(hmass if (z == 1 and hmass > 0) else amu[int(z)]) * amutoau for z in Z])
+        assert np.max(np.abs(mass - ref_mass) / ref_mass) < 1e-12
+        nfree = 3.0 * n - ncons
+        ekin = (1.0 if thermostat else 2.0) * 298.15 * 0.5 * kB * nfree
+        eperat = ekin / (3.0 * n)
+        v = b.array("velocities").reshape(n, 3)
+        ref_v = np.sqrt(2.0 * eperat / ref_mass) * np.where(isH, 2.0, 1.0)
+        assert np.max(np.abs(np.abs(v) - ref_v[:, None]) / ref_v[:, None]) < 1e-12
+        assert set(np.sign(v).ravel().tolist()) == {-1.0, 1.0}

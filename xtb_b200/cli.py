@@ -170,6 +170,71 @@ def read_mdrestart(path="mdrestart"):
     return vals[:, :3].copy(), vals[:, 3:].copy()
 
 
+def write_xtbrestart(qsh, dipm, qp, nat, nel, nopen, path="xtbrestart", gfn_method=2):
+    """The binary restart file of the reference (writeRestart, src/restart.f90:182-200): Fortran sequential unformatted
+    records (4-byte length markers, the default of the compilers xtb is built with): six int64 (method, method, atoms, shells,
+    electrons, unpaired electrons), then the shell charges qsh(nshell), the atomic dipoles dipm(3, n) and the atomic
+    quadrupoles qp(6, n) as float64."""
+    qsh = np.ascontiguousarray(qsh, dtype="<f8").ravel()
+    dipm = np.ascontiguousarray(dipm, dtype="<f8").ravel()
+    qp = np.ascontiguousarray(qp, dtype="<f8").ravel()
+    if dipm.size != 3 * nat or qp.size != 6 * nat:
+        raise ValueError("dipm / qp do not match the number of atoms")
+    head = np.array([gfn_method, gfn_method, nat, qsh.size, nel, nopen], dtype="<i8")
+    with open(path, "wb") as f:
+        for rec in (head, qsh, dipm, qp):
+            raw = rec.tobytes()
+            mark = np.array([len(raw)], dtype="<i4").tobytes()
+            f.write(mark + raw + mark)
+
+
+def read_xtbrestart(nat, nshell, nel=None, nopen=None, path="xtbrestart", gfn_method=2, warn=None):
+    """readRestart (src/restart.f90:33-86): None when the file is missing, unreadable or written for another number of
+    atoms / shells (`Dimension missmatch`); a different method, electron count or multiplicity only warns, as in the
+    reference.  Returns (qsh, dipm[n][3], qp[n][6])."""
+    warn = warn or (lambda msg: None)
+
+    def record(f):
+        m = f.read(4)
+        if len(m) < 4:
+            raise EOFError
+        n = int(np.frombuffer(m, dtype="<i4")[0])
+        raw = f.read(n)
+        if len(raw) < n or f.read(4) != m:
+            raise EOFError
+        return raw
+
+    try:
+        with open(path, "rb") as f:
+            head = np.frombuffer(record(f), dtype="<i8")
+            if head.size != 6:
+                raise EOFError
+            iver, _, n8, nshell8, nel8, nopen8 = (int(x) for x in head)
+            if iver != gfn_method:
+                warn("Version number missmatch in restart file.")
+            if nel is not None and nel8 != nel:
+                warn("Number of electron missmatch in restart file.")
+            if nopen is not None and nopen8 != nopen:
+                warn("Multiplicity missmatch in restart file.")
+            if n8 != nat or nshell8 != nshell:
+                warn("Dimension missmatch in restart file.")
+                return None
+            qsh = np.frombuffer(record(f), dtype="<f8").copy()
+            if qsh.size != nshell:
+                raise EOFError
+            if gfn_method > 1 and iver > 1:
+                dipm = np.frombuffer(record(f), dtype="<f8").copy().reshape(nat, 3)
+                qp = np.frombuffer(record(f), dtype="<f8").copy().reshape(nat, 6)
+            else:
+                dipm, qp = np.zeros((nat, 3)), np.zeros((nat, 6))
+            return qsh, dipm, qp
+    except FileNotFoundError:
+        return None
+    except (EOFError, ValueError):
+        warn("Dimension missmatch in restart file.")
+        return None
+
+
 def read_xcontrol_md(text):
     """The `$md` block of an xcontrol input (keys of set_md, src/set_module.f90:1975-2072: temp, time, dump / dumpxyz /
     dumptrj, step, hmass, shake, nvt, restart; `key=value`, `#` comments, first occurrence wins as in the reference).
@@ -310,6 +375,7 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=1, help="MD: seed of the start velocities' signs")
     ap.add_argument("--restart", action="store_true", help="MD: positions and velocities from ./mdrestart")
     ap.add_argument("-I", "--input", default=None, help="xcontrol file: its $md block sets the MD parameters not given as flags")
+    ap.add_argument("--norestart", action="store_true", help="do not read ./xtbrestart (it is still written)")
     ap.add_argument("-v", "--verbose", action="store_true")
     ap.add_argument("--silent", action="store_true")
     args = ap.parse_args(argv)
@@ -338,21 +404,35 @@ def main(argv=None):
                     setattr(args, dest, val)
         return run_md(args, numbers, xyz)
     t0 = time.perf_counter()
-    calc = xtb_b200.Calculator(xtb_b200.Param.GFN2xTB, numbers, xyz, charge=args.chrg, uhf=args.uhf)
-    calc.set_verbosity(0 if args.silent else (2 if args.verbose else 1))
-    calc.set_accuracy(args.acc)
-    calc.set_electronic_temperature(args.etemp)
-    calc.set_max_iterations(args.iterations)
+    # one molecule through the batched ABI: it takes the restart wavefunction of an `xtbrestart` file (src/restart.f90)
+    b = xtb_b200.BatchCalculator([numbers], charges=[args.chrg], uhf=[args.uhf], accuracy=args.acc, etemp=args.etemp,
+                                 maxiter=args.iterations)
     if args.alpb:
-        calc.set_solvent(args.alpb, model="alpb")
+        b.set_solvent(args.alpb, model="alpb")
     elif args.gbsa:
-        calc.set_solvent(args.gbsa, model="gbsa")
-    res = calc.singlepoint()
+        b.set_solvent(args.gbsa, model="gbsa")
+    sz, ne = b.sizes(0), b.electrons(0)
+    restarted = False
+    if not args.norestart:
+        wfn = read_xtbrestart(len(numbers), sz["nshell"], ne["nel"], ne["nopen"],
+                              warn=lambda msg: print("xtb_b200: warning: " + msg, file=sys.stderr))
+        if wfn is not None:
+            b.set_wavefunction(*wfn)
+            restarted = True
+            if not args.silent:
+                print("q/qsh data taken from xtbrestart\nCAMM data taken from xtbrestart")
+    r = b.singlepoint(xyz, restart=restarted)
     wall = time.perf_counter() - t0
-    energy, grad = res.get_energy(), res.get_gradient()
-    q, wbo, dip = res.get_charges(), res.get_bond_orders(), res.get_dipole()
-    eps, occ = res.get_orbital_eigenvalues(), res.get_orbital_occupations()
-    gap = res.get_info()["hl_gap"]   # the engine's egap from ihomoa (src/scc_core.f90:501), not re-derived from occupations
+    res = b.result(0)
+    if not r["all_converged"]:
+        print("xtb_b200: SCC did not converge in %d iterations" % int(res["niter"]), file=sys.stderr)
+    energy, grad = float(r["energies"][0]), r["gradients"]
+    q, dip = r["charges"], np.array([res["dipole_x"], res["dipole_y"], res["dipole_z"]])
+    wbo = b.array("wbo").reshape(len(numbers), len(numbers))
+    gap = res["hl_gap"]       # the engine's egap from ihomoa (src/scc_core.f90:501), not re-derived from occupations
+    write_xtbrestart(b.array("qsh"), b.array("dipm"), b.array("qp"), len(numbers), ne["nel"], ne["nopen"])
+    if not args.silent:
+        print("convergence criteria %s after %d iterations" % ("satisfied" if r["all_converged"] else "cannot be satisfied", int(res["niter"])))
     write_turbomole(numbers, xyz, energy, grad if args.grad else None)
     write_charges(q)
     write_wbo(wbo)

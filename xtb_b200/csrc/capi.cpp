@@ -758,6 +758,14 @@ int xtbb200_getSizes(xtbb200_TBatch batch, int imol, int* natoms, int* nshell, i
     return 0;
     XTBB_CATCH(-1)
 }
+int xtbb200_getElectrons(xtbb200_TBatch batch, int imol, int* nel, int* nopen) {
+    XTBB_TRY
+    if (!batch || imol < 0 || imol >= batch->b->nmol()) throw std::runtime_error("invalid molecule index");
+    if (nel) *nel = batch->b->nel(imol);
+    if (nopen) *nopen = batch->b->nopen(imol);
+    return 0;
+    XTBB_CATCH(-1)
+}
 size_t xtbb200_getDeviceBytes(xtbb200_TBatch batch) { return batch ? batch->b->device_bytes() : 0; }
 int xtbb200_getResult(xtbb200_TBatch batch, int imol, double* out16) {
     XTBB_TRY

@@ -49,7 +49,7 @@ constexpr int kNCnt = 12;
 // 0 shell pairs of build_SDQH0 inside r^2 <= 2000, 1 their surviving primitive pairs, 2 off-site shell pairs of
 // build_dSDQH0 inside r^2 <= 1600, 3 their surviving primitive pairs, 4 pairs of the gfn / covalent CN, 5 pairs of the
 // erf / D4 CN, 6 repulsion pairs, 7 non-zero reference pairs of the D4 self-consistent matrix, 8 D4 gradient pairs,
-// 9 ATM triples, 10 bond-order pairs
+// 9 ATM triples, 10 bond-order pairs, 11 Born-radius pairs evaluated with the preceding pair's 1/r (kernels_solv.cuh)
 struct Dev {
     const MolDesc* mol;
     MolState* st;

@@ -398,6 +398,8 @@ int Batch::nmol() const { return p_->d.nmol; }
 int Batch::natoms(int i) const { return p_->sys.mol[i].nat; }
 int Batch::nao(int i) const { return p_->sys.mol[i].nao; }
 int Batch::nshell(int i) const { return p_->sys.mol[i].nsh; }
+int Batch::nel(int i) const { return p_->sys.mol[i].nel; }
+int Batch::nopen(int i) const { return p_->sys.mol[i].nopen; }
 int Batch::atom_offset(int i) const { return p_->sys.mol[i].at0; }
 int Batch::shell_offset(int i) const { return p_->sys.mol[i].sh0; }
 int Batch::ao_offset(int i) const { return p_->sys.mol[i].ao0; }

@@ -77,6 +77,8 @@ class Batch {
     int natoms(int i) const;
     int nao(int i) const;
     int nshell(int i) const;
+    int nel(int i) const;      // valence electrons (src/scf_module.F90:334)
+    int nopen(int i) const;    // unpaired electrons
     int atom_offset(int i) const;
     int shell_offset(int i) const;
     int ao_offset(int i) const;

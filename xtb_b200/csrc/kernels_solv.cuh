@@ -34,11 +34,12 @@ enum { SVP_VDWR = 0, SVP_RHO, SVP_SVDW, SVP_VDWSA, SVP_WRP, SVP_GAM, SVP_HBMAG, 
 enum { SVM_GSASA = 0, SVM_ADET, SVM_CX, SVM_CY, SVM_CZ, SVM_TOTRAD3, SVM_I00, SVM_I01, SVM_I02, SVM_I11, SVM_I12, SVM_I22,
        SVM_GSOLV, SVM_GBORN, SVM_GHB, SVM_GSHIFT, SVM_QTOT, SVM_STRIDE = 24 };
 
-// one descreening term psi_i <- j and (d psi / d r) / r, src/solv/born.f90:130-330.  (The reference re-uses 1/r of the
-// preceding pair when only the second term of an "i overlaps j" pair exists, born.f90:224-262; 1/r of the pair is used.)
-__device__ __forceinline__ bool born_psi_term(double r, double rho_j, double vdw_i, double& g, double& dg) {
-    const double r1 = 1.0 / r;
+// one descreening term psi_i <- j and (d psi / d r) / r, src/solv/born.f90:130-330.  r1_nonoverlap: the value of the
+// reference's variable r1 when the non-overlap formula is evaluated: 1/r, except in the case of born_stale_r1 below.
+__device__ __forceinline__ bool born_psi_term(double r, double r1_nonoverlap, double rho_j, double vdw_i, double& g, double& dg) {
+    double r1 = 1.0 / r;
     if (r >= vdw_i + rho_j) {
+        r1 = r1_nonoverlap;
         const double ap = r + rho_j, am = r - rho_j, ab = ap * am, rhab = rho_j / ab, lnab = 0.5 * log(am / ap) * r1;
         g = rhab + lnab;
         dg = -2.0 * rhab / ab + (rhab - lnab) * r1 * r1;
@@ -54,6 +55,38 @@ __device__ __forceinline__ bool born_psi_term(double r, double rho_j, double vdw
     }
     g = 0.0; dg = 0.0;
     return false;
+}
+
+// The reference's pair loop (compute_psi, born.f90:118-337; pairs (hi, lo), hi ascending, lo < hi ascending, inside
+// lrcut) keeps 1/r in a variable r1 that every branch sets before use except one: when the descreening sphere of lo lies
+// completely inside the van der Waals sphere of hi (r + rho_lo <= vdw_hi) while hi does not overlap lo (r >= rho_hi +
+// vdw_lo), the term psi_lo <- hi (`case(1)`, born.f90:292-309) is evaluated with the r1 left by the preceding pair of the
+// list that set it.  born_is_stale tells whether (hi, lo) is such a pair; born_stale_r1 walks the list backwards to the
+// pair whose 1/r the reference would still hold (0 before the first assignment, where the reference is undefined).  No GFN2
+// test system of the reference reaches this; tests/test_gpu_solvation.py constructs one (RbH in GBSA acetone).
+__device__ __forceinline__ bool born_is_stale(double r, double vdw_hi, double rho_hi, double vdw_lo, double rho_lo) {
+    return r < vdw_hi + rho_lo && !(r < rho_hi + vdw_lo) && !(r + rho_lo > vdw_hi);
+}
+__device__ __noinline__ double born_stale_r1(const Dev& d, const MolDesc& m, int hi, int lo) {
+    int i = hi, j = lo;
+    for (;;) {
+        if (--j < 0) {
+            if (--i < 1) return 0.0;
+            j = i - 1;
+        }
+        const double* xi = d.xyz + 3 * (m.at0 + i);
+        const double* xj = d.xyz + 3 * (m.at0 + j);
+        const double dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        if (!(r2 < kSolvLrcut * kSolvLrcut)) continue;
+        const double r = sqrt(r2);
+        const double* pi = d.sv_par + 8 * (size_t)(m.at0 + i);
+        const double* pj = d.sv_par + 8 * (size_t)(m.at0 + j);
+        const bool ovij = r < pi[SVP_VDWR] + pj[SVP_RHO], ovji = r < pi[SVP_RHO] + pj[SVP_VDWR];
+        const bool ij_term = !ovij || r + pj[SVP_RHO] > pi[SVP_VDWR], ji_term = !ovji || r + pi[SVP_RHO] > pj[SVP_VDWR];
+        if (ovij && !ovji && !ij_term) continue;      // a stale pair itself: r1 untouched
+        if (ij_term || ji_term) return 1.0 / r;
+    }
 }
 
 // ---- Born radii: CTA per atom, threads over the partners (compute_psi + compute_bornr) ----
@@ -72,7 +105,14 @@ __global__ void __launch_bounds__(128) k_solv_born(Dev d) {
         const double r2 = dx * dx + dy * dy + dz * dz;
         if (!(r2 < kSolvLrcut * kSolvLrcut)) continue;
         double g, dg;
-        if (born_psi_term(sqrt(r2), d.sv_par[8 * (size_t)(m.at0 + j) + SVP_RHO], vdwi, g, dg)) psi += g;
+        const double r = sqrt(r2);
+        const double* pj = d.sv_par + 8 * (size_t)(m.at0 + j);
+        double r1 = 1.0 / r;
+        if (j > i && born_is_stale(r, pj[SVP_VDWR], pj[SVP_RHO], vdwi, pi[SVP_RHO])) {   // psi_i <- j of the pair (hi = j, lo = i)
+            r1 = born_stale_r1(d, m, j, i);
+            cnt_add(d, blockIdx.y, 11, 1);
+        }
+        if (born_psi_term(r, r1, pj[SVP_RHO], vdwi, g, dg)) psi += g;
     }
     psi = block_sum(psi, red);
     if (threadIdx.x == 0) {
@@ -392,8 +432,11 @@ __global__ void __launch_bounds__(64) k_solv_grad_chain(Dev d) {
         const double r = sqrt(r2);
         const double* pb = d.sv_par + 8 * (size_t)(m.at0 + b);
         double g, dga, dgb;
-        born_psi_term(r, pb[SVP_RHO], pa[SVP_VDWR], g, dga);   // psi_a <- b
-        born_psi_term(r, pa[SVP_RHO], pb[SVP_VDWR], g, dgb);   // psi_b <- a
+        double r1a = 1.0 / r, r1b = r1a;
+        if (b > a) { if (born_is_stale(r, pb[SVP_VDWR], pb[SVP_RHO], pa[SVP_VDWR], pa[SVP_RHO])) r1a = born_stale_r1(d, m, b, a); }
+        else if (born_is_stale(r, pa[SVP_VDWR], pa[SVP_RHO], pb[SVP_VDWR], pb[SVP_RHO])) r1b = born_stale_r1(d, m, a, b);
+        born_psi_term(r, r1a, pb[SVP_RHO], pa[SVP_VDWR], g, dga);   // psi_a <- b
+        born_psi_term(r, r1b, pa[SVP_RHO], pb[SVP_VDWR], g, dgb);   // psi_b <- a
         const double f = wa * dga + d.sv_grddb[m.at0 + b] * d.sv_dbr[m.at0 + b] * dgb;
         gx += f * dx; gy += f * dy; gz += f * dz;
     }

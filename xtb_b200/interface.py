@@ -83,6 +83,7 @@ def load_library():
         "xtbb200_singlepoint": (ci, [vp, _c_double_p, ci, _c_double_p, _c_double_p, _c_double_p, _c_int_p, _c_int_p]),
         "xtbb200_singlepointDevice": (ci, [vp, vp, ci, vp]),
         "xtbb200_getNMol": (ci, [vp]), "xtbb200_getSizes": (ci, [vp, ci, _c_int_p, _c_int_p, _c_int_p]),
+        "xtbb200_getElectrons": (ci, [vp, ci, _c_int_p, _c_int_p]),
         "xtbb200_getDeviceBytes": (ctypes.c_size_t, [vp]),
         "xtbb200_getResultsInfo": (ci, [vp, _c_double_p, _c_int_p]),
         "xtbb200_getResult": (ci, [vp, ci, _c_double_p]), "xtbb200_getCounts": (ci, [vp, ci, _c_int_p, _c_int_p, _c_int_p]),
@@ -525,8 +526,13 @@ class BatchCalculator:
         self._check(self._lib.xtbb200_getCounts(self._b, int(imol), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return dict(ndp=a.value, nqp=b.value, sweeps=c.value)
 
+    def electrons(self, imol):
+        a, b = ctypes.c_int(), ctypes.c_int()
+        self._check(self._lib.xtbb200_getElectrons(self._b, int(imol), ctypes.byref(a), ctypes.byref(b)))
+        return dict(nel=a.value, nopen=b.value)
+
     DECISION_COUNTS = ("sdq_shell_pairs", "sdq_primitive_pairs", "grad_shell_pairs", "grad_primitive_pairs", "cn_pairs",
-                       "cn_d4_pairs", "repulsion_pairs", "d4_matrix_entries", "d4_gradient_pairs", "atm_triples", "wbo_pairs")
+                       "cn_d4_pairs", "repulsion_pairs", "d4_matrix_entries", "d4_gradient_pairs", "atm_triples", "wbo_pairs", "born_stale_pairs")
 
     def set_decision_counting(self, on=True):
         """Diagnostic: let the kernels count their cutoff / screening decisions during the next single points."""
