@@ -595,7 +595,7 @@ def eig_roofline(prof, topk, n, ndiag, steps, step_ms, stage_ms, peak, hbm):
              "share_of_step": pk["ms"] / steps / step_ms}
         tr = ncu_traffic("k_sytrd_panel", n)
         if tr:
-            r["traffic"] = tr["bytes_per_launch"]
+            r["traffic"] = tr["ratio_to_algorithmic"] * alg / npan
             r["traffic_source"] = tr.get("source")
         r.update(common)
         return r

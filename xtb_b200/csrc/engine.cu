@@ -853,8 +853,21 @@ int Batch::singlepoint(bool restart) {
     }
     cudaEventRecord(ev[1], st);
     // ---- SCC iterations
-    const int tiles = (s.max_nao + GT - 1) / GT;
+    // GEMM tile: 48 or 64, whichever pads the batch's matrices less (144 AOs: 3 x 48 exactly instead of 192 x 192)
+    double pad48 = 0, pad64 = 0;
+    for (const MolDesc& mm : s.mol) {
+        const double t48 = 48.0 * ((mm.nao + 47) / 48), t64 = 64.0 * ((mm.nao + 63) / 64);
+        pad48 += t48 * t48 * t48; pad64 += t64 * t64 * t64;
+    }
+    const bool gt48 = pad48 < 0.9 * pad64;
+    const int gtile = gt48 ? 48 : 64;
+    const int tiles = (s.max_nao + gtile - 1) / gtile;
     const dim3 ggrid(tiles * tiles, nmol);
+#define KGEMM(id, TA, TB, ...)                                                          \
+    do {                                                                                \
+        if (gt48) KL(id, (k_gemm<TA, TB, 48><<<ggrid, 128, 0, st>>>(__VA_ARGS__)));   \
+        else KL(id, (k_gemm<TA, TB, 64><<<ggrid, 128, 0, st>>>(__VA_ARGS__)));        \
+    } while (0)
     const int npairs = (s.max_nao + 1) / 2;
     // ensemble-sized matrices: block Jacobi on the FP64 tensor path, matrix resident in shared memory
     const int jb_warps = std::max(1, std::min(20, jb_dims(s.max_nao).nb / 2));   // k_jacobi_blk: __launch_bounds__(640)
@@ -871,10 +884,10 @@ int Batch::singlepoint(bool restart) {
         if (d.solv_on) KL(K_SOLV_SCC, k_solv_matvec<<<dim3((s.max_nat + 31) / 32, nmol), 256, 0, st>>>(d, 0));
         KL(K_D4SCC, k_d4_shift<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
         KL(K_FOCK, k_fock<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
-        KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.H, d.X, d.T, xtri ? 2 : 0, 1));   // T = H X
-        KL(K_GEMM_XHX, k_gemm<true, false><<<ggrid, 128, 0, st>>>(d, d.X, d.T, d.W, xtri ? 3 : 0, 1));    // W = X^T T
+        KGEMM(K_GEMM_XHX, false, false, d, d.H, d.X, d.T, xtri ? 2 : 0, 1);   // T = H X
+        KGEMM(K_GEMM_XHX, true, false, d, d.X, d.T, d.W, xtri ? 3 : 0, 1);    // W = X^T T
         if (!dc && !bdc && (it > 0 || (restart && I.have_wfn)))
-            KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.W, d.Zm, d.T, 0, 2));   // T = A' Z_prev
+            KGEMM(K_GEMM_XHX, false, false, d, d.W, d.Zm, d.T, 0, 2);   // T = A' Z_prev
         if (bdc) {
             I.prof_begin(K_JACOBI, st);
             k_eig_skip_b<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.eig.bskip);
@@ -886,7 +899,7 @@ int Batch::singlepoint(bool restart) {
             // first diagonalisation of an ensemble: leaders cold, followers warm from their leader's eigenvectors
             KL(K_JACOBI, jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d, 1));
             KL(K_JACOBI, k_lead_copy<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
-            KL(K_GEMM_XHX, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.W, d.Zm, d.T, 0, 3));
+            KGEMM(K_GEMM_XHX, false, false, d, d.W, d.Zm, d.T, 0, 3);
             KL(K_JACOBI, jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d, 2));
         } else if (use_blk) KL(K_JACOBI, jacobi_blk<<<nmol, 32 * jb_warps, jb_bytes, st>>>(d, 0));
         else if (dc) {
@@ -906,10 +919,10 @@ int Batch::singlepoint(bool restart) {
         else if (npairs * 16 <= 1024) KL(K_JACOBI, launch_jacobi<16>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 8 <= 1024) KL(K_JACOBI, launch_jacobi<8>(d, nmol, s.max_nao, sm, st));
         else KL(K_JACOBI, launch_jacobi<4>(d, nmol, s.max_nao, sm, st));
-        KL(K_GEMM_C, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.Zm, d.C, xtri ? 4 : 0, 1));   // C = X Z
+        KGEMM(K_GEMM_C, false, false, d, d.X, d.Zm, d.C, xtri ? 4 : 0, 1);   // C = X Z
         KL(K_FERMI, k_fermi<<<nmol, 32, 0, st>>>(d));
         KL(K_DENSITY, k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 0));                // T = C f
-        KL(K_DENSITY, k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.P, 1, 1));       // P = T C^T
+        KGEMM(K_DENSITY, false, true, d, d.T, d.C, d.P, 1, 1);       // P = T C^T
         KL(K_POP, k_pop_rows<<<grid2((long long)s.max_nao * 32, 256, nmol), 256, 0, st>>>(d));
         KL(K_POP, k_pop_atoms<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
         KL(K_ENERGY, k_es_rows<<<grid2(8LL * s.max_nsh, 256, nmol), 256, 0, st>>>(d));
@@ -930,7 +943,7 @@ int Batch::singlepoint(bool restart) {
     cudaEventRecord(ev[2], st);
     // ---- gradient
     KL(K_GRAD_H0, k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 1));                     // T = C (f e)
-    KL(K_GRAD_H0, k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.H, 1, 0));            // H <- energy weighted density
+    KGEMM(K_GRAD_H0, false, true, d, d.T, d.C, d.H, 1, 0);            // H <- energy weighted density
     KL(K_GRAD_AES, k_pot_aes<false><<<grid2(8LL * s.max_nat, 256, nmol), 256, 0, st>>>(d));
     if (R > 1) {   // partial gradients: repulsion stays on rank 0, unowned shell pairs contribute zeros
         if (d.srank != 0) XTB_CUDA_CHECK(cudaMemsetAsync(d.grad, 0, 3 * s.atoms.size() * sizeof(double), st));
@@ -974,15 +987,15 @@ int Batch::singlepoint(bool restart) {
     bool any_open = false;
     for (auto& m : s.mol) any_open |= (m.nopen != 0);
     if (!any_open) {
-        KL(K_WBO, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.P, d.S, d.W, 0, 0));
+        KGEMM(K_WBO, false, false, d, d.P, d.S, d.W, 0, 0);
     } else {
         // alpha / beta densities (scf_module.F90:869-879); closed-shell members of a mixed batch take this path too
         KL(K_WBO, k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 2));
-        KL(K_WBO, k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.X, 0, 0));
-        KL(K_WBO, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.S, d.W, 0, 0));
+        KGEMM(K_WBO, false, true, d, d.T, d.C, d.X, 0, 0);
+        KGEMM(K_WBO, false, false, d, d.X, d.S, d.W, 0, 0);
         KL(K_WBO, k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 3));
-        KL(K_WBO, k_gemm<false, true><<<ggrid, 128, 0, st>>>(d, d.T, d.C, d.X, 0, 0));
-        KL(K_WBO, k_gemm<false, false><<<ggrid, 128, 0, st>>>(d, d.X, d.S, d.H, 0, 0));   // not Zm: it is the warm start of the next call
+        KGEMM(K_WBO, false, true, d, d.T, d.C, d.X, 0, 0);
+        KGEMM(K_WBO, false, false, d, d.X, d.S, d.H, 0, 0);   // not Zm: it is the warm start of the next call
     }
     KL(K_WBO, k_wbo<<<grid2((long long)s.max_nat * s.max_nat, 128, nmol), 128, 0, st>>>(d, any_open ? 1 : 0));
     KL(K_FINISH, k_finish<<<nmol, 256, 0, st>>>(d));

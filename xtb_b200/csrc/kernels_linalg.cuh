@@ -33,7 +33,9 @@ constexpr int GLD = GT + 4;
 // skip_done: 1 = skip molecules that already left the SCC loop; 2 = additionally skip molecules without a valid
 // eigenvector guess (warm-start product A' Z_prev); 3 = as 2, and only molecules that follow a leader (first
 // diagonalisation of an ensemble, see k_lead_copy)
-template <bool TA, bool TB>
+// GTT: CTA tile, 64 or 48 (2 x 2 warps of GTT/2 x GTT/2); 48 fits orders like 144 = 3 x 48 without the 44 % of padding a
+// 64-wide tiling of 192 x 192 multiplies (the engine picks the tile with the smaller padded area for the batch)
+template <bool TA, bool TB, int GTT>
 __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ Ag, const double* __restrict__ Bg,
                                               double* __restrict__ Cg, int kmode, int skip_done) {
     const MolDesc m = d.mol[blockIdx.y];
@@ -41,34 +43,35 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
     if (skip_done >= 2 && !d.st[blockIdx.y].zvalid) return;
     if (skip_done == 3 && d.leader[blockIdx.y] == (int)blockIdx.y) return;
     const int n = m.nao;
-    const int tiles = (n + GT - 1) / GT;
+    constexpr int GTL = GTT + 4, NI = GTT / 16;
+    const int tiles = (n + GTT - 1) / GTT;
     if ((int)blockIdx.x >= tiles * tiles) return;
-    const int r0 = (blockIdx.x % tiles) * GT, c0 = (blockIdx.x / tiles) * GT;
+    const int r0 = (blockIdx.x % tiles) * GTT, c0 = (blockIdx.x / tiles) * GTT;
     if (kmode == 3 && r0 < c0) return;
     int K = n, kbeg = 0;
     if (kmode == 1) K = d.st[blockIdx.y].kocc;
-    else if (kmode == 2) K = min(n, c0 + GT);
-    else if (kmode == 3) K = min(n, r0 + GT);
+    else if (kmode == 2) K = min(n, c0 + GTT);
+    else if (kmode == 3) K = min(n, r0 + GTT);
     else if (kmode == 4) kbeg = r0;
     const double* A = Ag + m.mat0;
     const double* B = Bg + m.mat0;
     double* C = Cg + m.mat0;
-    __shared__ double As[GK][GLD], Bs[GK][GLD];
+    __shared__ double As[GK][GTL], Bs[GK][GTL];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wr = (warp & 1) * 32, wc = (warp >> 1) * 32;
-    double acc[4][4][2];
+    const int wr = (warp & 1) * (GTT / 2), wc = (warp >> 1) * (GTT / 2);
+    double acc[NI][NI][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < NI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     // software pipeline: the global loads of tile k+1 are in flight (registers) while tile k is multiplied from shared memory
-    double ra[GT * GK / 128], rb[GT * GK / 128];
+    double ra[GTT * GK / 128], rb[GTT * GK / 128];
     auto fetch = [&](int k0) {
 #pragma unroll
-        for (int u = 0; u < GT * GK / 128; ++u) {
+        for (int u = 0; u < GTT * GK / 128; ++u) {
             const int t = tid + 128 * u;
             if (!TA) {
-                const int r = t % GT, kk = t / GT, gr = r0 + r, gk = k0 + kk;
+                const int r = t % GTT, kk = t / GTT, gr = r0 + r, gk = k0 + kk;
                 ra[u] = (gr < n && gk < K) ? A[gr + (long long)n * gk] : 0.0;
             } else {
                 const int kk = t % GK, r = t / GK, gr = r0 + r, gk = k0 + kk;
@@ -78,17 +81,17 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
                 const int kk = t % GK, c = t / GK, gc = c0 + c, gk = k0 + kk;
                 rb[u] = (gc < n && gk < K) ? B[gk + (long long)n * gc] : 0.0;
             } else {
-                const int c = t % GT, kk = t / GT, gc = c0 + c, gk = k0 + kk;
+                const int c = t % GTT, kk = t / GTT, gc = c0 + c, gk = k0 + kk;
                 rb[u] = (gc < n && gk < K) ? B[gc + (long long)n * gk] : 0.0;
             }
         }
     };
     auto stage = [&]() {   // As[kk][r] = op(A)(r0+r, k0+kk), Bs[kk][c] = op(B)(k0+kk, c0+c)
 #pragma unroll
-        for (int u = 0; u < GT * GK / 128; ++u) {
+        for (int u = 0; u < GTT * GK / 128; ++u) {
             const int t = tid + 128 * u;
-            if (!TA) As[t / GT][t % GT] = ra[u]; else As[t % GK][t / GK] = ra[u];
-            if (!TB) Bs[t % GK][t / GK] = rb[u]; else Bs[t / GT][t % GT] = rb[u];
+            if (!TA) As[t / GTT][t % GTT] = ra[u]; else As[t % GK][t / GK] = ra[u];
+            if (!TB) Bs[t % GK][t / GK] = rb[u]; else Bs[t / GTT][t % GTT] = rb[u];
         }
     };
     if (K > kbeg) fetch(kbeg);
@@ -98,23 +101,23 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
         if (k0 + GK < K) fetch(k0 + GK);
 #pragma unroll
         for (int ks = 0; ks < GK; ks += 4) {
-            double af[4], bf[4];
+            double af[NI], bf[NI];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = As[ks + (lane & 3)][wr + 8 * i + (lane >> 2)];
+            for (int i = 0; i < NI; ++i) af[i] = As[ks + (lane & 3)][wr + 8 * i + (lane >> 2)];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = Bs[ks + (lane & 3)][wc + 8 * j + (lane >> 2)];
+            for (int j = 0; j < NI; ++j) bf[j] = Bs[ks + (lane & 3)][wc + 8 * j + (lane >> 2)];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < NI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < NI; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
         __syncthreads();
     }
     const bool mirror = kmode == 3 && r0 > c0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < NI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NI; ++j) {
             int gr = r0 + wr + 8 * i + (lane >> 2);
             int gc = c0 + wc + 8 * j + 2 * (lane & 3);
             if (gr < n) {
