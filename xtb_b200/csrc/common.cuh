@@ -123,6 +123,11 @@ struct Dev {
     // shell-pair gradient partials
     double *gpair;   // [npair][4] : gx,gy,gz,dCN
     const long long* pair0;
+    // shell pairs of a molecule in the order the integral kernels work through them: descending cost (components x
+    // primitive pairs), so that the warps of a CTA hold pairs of one kind and finish together; pord0[im]: the molecule's
+    // slice of pair_order (molecules of one composition share it)
+    const int* pair_order;
+    const long long* pord0;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {

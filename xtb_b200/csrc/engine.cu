@@ -367,6 +367,32 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
                 o2 += natoms[i];
             }
             d.leader = I.upload(lead);
+            // cost-sorted shell-pair order, one list per composition (k_sdqh0 / k_grad_h0)
+            std::vector<long long> pord0(nmol);
+            std::vector<int> order;
+            static const int ncart[3] = {1, 3, 6};
+            for (int i = 0; i < nmol; ++i) {
+                if (lead[i] != i) { pord0[i] = pord0[lead[i]]; continue; }
+                const MolDesc& mm = s.mol[i];
+                const long long np = (long long)mm.nsh * (mm.nsh + 1) / 2;
+                pord0[i] = (long long)order.size();
+                std::vector<std::pair<int, int>> cost((size_t)np);
+                int pidx = 0;
+                for (int is = 0; is < mm.nsh; ++is)
+                    for (int js = 0; js <= is; ++js, ++pidx) {
+                        const ShellPar& a = s.shells[mm.sh0 + is];
+                        const ShellPar& b = s.shells[mm.sh0 + js];
+                        const int ncomp = ncart[a.l] * ncart[b.l];
+                        // passes over the component groups of a warp x primitive pairs per lane, as the kernels loop
+                        const int lpc = ncomp >= 32 ? 1 : 32 / ncomp, ngrp = 32 / lpc;
+                        const int c = ((ncomp + ngrp - 1) / ngrp) * ((a.nprim * b.nprim + lpc - 1) / lpc) * 64 + (a.atom == b.atom ? 0 : 1);
+                        cost[pidx] = std::make_pair(-c, pidx);
+                    }
+                std::sort(cost.begin(), cost.end());
+                for (auto& c : cost) order.push_back(c.second);
+            }
+            d.pair_order = I.upload(order);
+            d.pord0 = I.upload(pord0);
             XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
         }
         I.d_active = I.dalloc<int>(1);

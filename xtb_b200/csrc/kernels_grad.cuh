@@ -57,10 +57,11 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long npair = (long long)m.nsh * (m.nsh + 1) / 2;
-    const long long p = shard_pair_cta(d) * kIntWarps + warp;
+    const long long pk = shard_pair_cta(d) * kIntWarps + warp;
     __shared__ double s_alp[kIntWarps][2][6], s_cont[kIntWarps][2][6];
     __shared__ double s_wf[kIntWarps][25], s_wp[kIntWarps][25];
-    if (p >= npair) return;
+    if (pk >= npair) return;
+    const long long p = d.pair_order[d.pord0[blockIdx.y] + pk];
     int is = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
     while ((long long)is * (is + 1) / 2 > p) --is;
     while ((long long)(is + 1) * (is + 2) / 2 <= p) ++is;

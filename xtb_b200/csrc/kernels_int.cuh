@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kIntWarps * 32, 6) k_sdqh0(Dev d) {
     __shared__ double s_part[kIntWarps][10][33];
     __shared__ double s_alp[kIntWarps][2][6], s_cont[kIntWarps][2][6];
     if (p >= npair) return;   // whole warp exits together
+    p = d.pair_order[d.pord0[blockIdx.y] + p];
     int is = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
     while ((long long)is * (is + 1) / 2 > p) --is;
     while ((long long)(is + 1) * (is + 2) / 2 <= p) ++is;
