@@ -362,7 +362,8 @@ __device__ __forceinline__ void jb_publish(volatile int* ver, int P, int Q, int 
 
 // default of Dev::jb_qtol.  The columns of G are then orthogonal to ~1e-14 after the last sweep, but the rotation angle between
 // two eigenvectors is larger than the non-orthogonality of their columns by (lambda + sigma) / (2 gap): at 1e-5 the density
-// matrix carried errors of 1e-6 (energy still right to 3e-12, gradients only to 1e-7, numerical Hessians to 1e-5)
+// matrix carried errors of 1e-6 (energy still right to 3e-12, but gradients only to 1e-7 and numerical Hessians to 8e-6), and
+// at 1e-6 (52 instead of 56 sweeps per single point) the numerical Hessian test still missed its 1e-6
 constexpr double kJbQuadraticStop = 1.0e-7;
 constexpr int kJbInnerSweeps = 1;  // inner sweeps per Gram block (early exit when a sweep rotates nothing)
 constexpr int kJbScratch = 192;   // doubles of per-warp scratch: M and J, 8 x 8 with row stride 9 (jb_sweeps) or kJs (jb_sweeps2)
