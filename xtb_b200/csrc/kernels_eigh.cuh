@@ -163,6 +163,149 @@ __global__ void __launch_bounds__(128, 3) k_eg_gemm(GemmTask t0, const GemmTask*
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The same GEMM with the operand tiles brought in by the bulk asynchronous copy engine (TMA, cp.async.bulk: SASS UBLKCP)
+// through a ring of kTmaStages shared-memory stages guarded by mbarriers: one producer warp issues the copies of k-tile
+// i + kTmaStages - 1 while the four consumer warps run the DMMAs of k-tile i; no register staging, no __syncthreads in
+// the main loop.  Every copy is one line of the tile that is contiguous in global memory (64 rows of a column: 512 B, or
+// 16 k-values of a row: 128 B) and lands at a padded pitch (68 / 20 doubles), so the fragment loads stay free of bank
+// conflicts; the hardware swizzles of the tensor-map form of TMA do not fit the 8-byte m8n8k4 fragments.
+// Requirements (checked by EighWork::gemm, which otherwise launches k_eg_gemm): base pointers 16-byte aligned, lda / ldb
+// even, M and N even, K and the segment boundaries multiples of GK.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTmaStages = 4;
+constexpr int kTmaPitchK = GK + 4;      // lines of 16 k-values
+template <bool TA, bool TB>
+constexpr size_t eg_tma_smem() {
+    return (size_t)kTmaStages * ((TA ? GT * kTmaPitchK : GK * GLD) + (TB ? GK * GLD : GT * kTmaPitchK)) * sizeof(double) +
+           2 * kTmaStages * sizeof(unsigned long long);
+}
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(160) k_eg_gemm_tma(GemmTask t) {
+    const int tm = (t.M + GT - 1) / GT, tn = (t.N + GT - 1) / GT;
+    if ((int)blockIdx.x >= tm * tn) return;
+    const int r0 = (blockIdx.x % tm) * GT, c0 = (blockIdx.x / tm) * GT;
+    int kb = 0, ke = t.K;
+    double* __restrict__ C = t.C + r0 + (long long)t.ldc * c0;
+    if (t.ksplit > 1) {
+        const int ch = (((t.K + t.ksplit - 1) / t.ksplit + GK - 1) / GK) * GK;
+        kb = min(t.K, (int)blockIdx.z * ch);
+        ke = min(t.K, kb + ch);
+        C += (long long)blockIdx.z * t.csplit;
+    }
+    const double* __restrict__ A = TA ? t.A + (long long)t.lda * r0 : t.A + r0;
+    const double* __restrict__ B = TB ? t.B + c0 : t.B + (long long)t.ldb * c0;
+    const int lda = t.lda, ldb = t.ldb, ldc = t.ldc;
+    const int M = t.M - r0, N = t.N - c0;
+    const int rows = min(M, GT), cols = min(N, GT);
+    const int sgA = t.ksegA ? t.ksegA : 0x7fffffff, oA = t.offA2 - t.ksegA;
+    const int sgB = t.ksegB ? t.ksegB : 0x7fffffff, oB = t.offB2 - t.ksegB;
+    constexpr int ASZ = TA ? GT * kTmaPitchK : GK * GLD, BSZ = TB ? GK * GLD : GT * kTmaPitchK;
+    extern __shared__ __align__(128) unsigned char eg_smem[];
+    double* Abuf = reinterpret_cast<double*>(eg_smem);
+    double* Bbuf = Abuf + kTmaStages * ASZ;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(Bbuf + kTmaStages * BSZ);
+    unsigned long long* empty = full + kTmaStages;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kTmaStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nk = (ke - kb) / GK;
+    if (warp == 4) {
+        // ---- producer warp
+        const unsigned bytes = (unsigned)(rows + cols) * GK * sizeof(double);
+        for (int it = 0; it < nk; ++it) {
+            const int s = it % kTmaStages, k0 = kb + it * GK;
+            if (it >= kTmaStages) mbar_wait(empty + s, ((it / kTmaStages) - 1) & 1);
+            if (lane == 0) mbar_expect_tx(full + s, bytes);
+            __syncwarp();
+            const int ka = k0 >= sgA ? k0 + oA : k0, kq = k0 >= sgB ? k0 + oB : k0;
+            double* As = Abuf + s * ASZ;
+            double* Bs = Bbuf + s * BSZ;
+            if (!TA) { if (lane < GK) bulk_g2s(As + lane * GLD, A + (long long)lda * (ka + lane), rows * 8, full + s); }
+            else { for (int r = lane; r < rows; r += 32) bulk_g2s(As + r * kTmaPitchK, A + ka + (long long)lda * r, GK * 8, full + s); }
+            if (TB) { if (lane < GK) bulk_g2s(Bs + lane * GLD, B + (long long)ldb * (kq + lane), cols * 8, full + s); }
+            else { for (int c = lane; c < cols; c += 32) bulk_g2s(Bs + c * kTmaPitchK, B + kq + (long long)ldb * c, GK * 8, full + s); }
+        }
+        return;
+    }
+    // ---- consumer warps
+    const int wr = (warp & 1) * 32, wc = (warp >> 1) * 32;
+    const int l4 = lane >> 2, l3 = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int it = 0; it < nk; ++it) {
+        const int s = it % kTmaStages;
+        mbar_wait(full + s, (it / kTmaStages) & 1);
+        const double* As = Abuf + s * ASZ;
+        const double* Bs = Bbuf + s * BSZ;
+#pragma unroll
+        for (int ks = 0; ks < GK; ks += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = TA ? As[(wr + 8 * i + l4) * kTmaPitchK + ks + l3] : As[(ks + l3) * GLD + wr + 8 * i + l4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = TB ? Bs[(ks + l3) * GLD + wc + 8 * j + l4] : Bs[(wc + 8 * j + l4) * kTmaPitchK + ks + l3];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+    const double alpha = t.alpha, beta = t.beta;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gr = wr + 8 * i + l4;
+            const int gc = wc + 8 * j + 2 * l3;
+            if (gr < M) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (gc + h < N) {
+                        double* p = C + gr + (long long)ldc * (gc + h);
+                        const double v = alpha * acc[i][j][h];
+                        *p = (beta == 0.0) ? v : v + beta * *p;
+                    }
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // tridiagonalisation
 // ---------------------------------------------------------------------------------------------------------------
 struct SytrdArgs {
@@ -1358,10 +1501,36 @@ struct EighWork {
         return nl;
     }
 
+    // eligibility of the bulk-copy kernel: alignment of every copied line and whole k-tiles
+    static bool gemm_tma_ok(const GemmTask& t, int nz) {
+        static const bool off = std::getenv("XTBB200_NO_TMA_GEMM") != nullptr;
+        if (off) return false;
+        auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+        if (!al16(t.A) || !al16(t.B) || (t.lda & 1) || (t.ldb & 1) || (t.M & 1) || (t.N & 1)) return false;
+        if (t.K % GK || t.K < 2 * GK || t.ksegA % GK || t.ksegB % GK || (t.offA2 & 1) || (t.offB2 & 1)) return false;
+        if (t.ksplit > 1 && nz != t.ksplit) return false;
+        return nz == 1 || t.ksplit > 1;
+    }
+    template <bool TA, bool TB>
+    static void gemm_tma(cudaStream_t st, const GemmTask& t, const dim3& g) {
+        static bool once = [] {
+            cudaFuncSetAttribute(k_eg_gemm_tma<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eg_tma_smem<TA, TB>());
+            return true;
+        }();
+        (void)once;
+        k_eg_gemm_tma<TA, TB><<<g, 160, eg_tma_smem<TA, TB>(), st>>>(t);
+    }
     static void gemm(cudaStream_t st, bool ta, bool tb, const GemmTask& t, int nz = 1) {
         const int tm = (t.M + GT - 1) / GT, tn = (t.N + GT - 1) / GT;
         if (tm * tn == 0) return;
         const dim3 g(tm * tn, 1, nz);
+        if (gemm_tma_ok(t, nz)) {
+            if (!ta && !tb) gemm_tma<false, false>(st, t, g);
+            else if (ta && !tb) gemm_tma<true, false>(st, t, g);
+            else if (!ta && tb) gemm_tma<false, true>(st, t, g);
+            else gemm_tma<true, true>(st, t, g);
+            return;
+        }
         if (!ta && !tb) k_eg_gemm<false, false><<<g, 128, 0, st>>>(t, nullptr);
         else if (ta && !tb) k_eg_gemm<true, false><<<g, 128, 0, st>>>(t, nullptr);
         else if (!ta && tb) k_eg_gemm<false, true><<<g, 128, 0, st>>>(t, nullptr);
