@@ -104,3 +104,33 @@ def test_results_info_and_parameter_file_warning(xb, kat):
     L.xtb_getError(env, buf, ctypes.byref(n))
     assert b"not supported" in buf.value
     L.xtb_delCalculator(ctypes.byref(c)); L.xtb_delMolecule(ctypes.byref(mol)); L.xtb_delEnvironment(ctypes.byref(env))
+
+
+def test_scc_iteration_table_at_verbosity_one(xb, kat, tmp_path):
+    """xtb_singlepoint at verbosity >= 1 prints the reference's SCC iteration table (header src/scf_module.F90:612-616, rows
+    src/scc_core.f90:621-622, format (i4,F15.7,E14.6,E11.3,f8.2,2x,f8.1,l3)): one row per iteration, the electronic energy
+    of the last row is the converged one, dE and RMSdq of the last two rows are below the convergence thresholds."""
+    from oracle.oracle import Oracle
+    s = kat["caffeine"]
+    calc = xb.Calculator(xb.Param.GFN2xTB, s["numbers"], s["xyz"])
+    log = tmp_path / "xtb.out"
+    calc.set_output(str(log))
+    calc.set_verbosity(1)
+    res = calc.singlepoint()
+    calc.release_output()
+    text = log.read_text().splitlines()
+    head = [k for k, ln in enumerate(text) if ln.startswith(" iter      E             dE          RMSdq      gap      omega  full diag")]
+    assert len(head) == 1
+    rows = []
+    for ln in text[head[0] + 1:]:
+        if not ln.strip():
+            break
+        assert len(ln) == 4 + 15 + 14 + 11 + 8 + 2 + 8 + 3 and ln.endswith("  T")
+        rows.append((int(ln[:4]), float(ln[4:19]), float(ln[19:33]), float(ln[33:44]), float(ln[44:52]), float(ln[54:62])))
+    o = Oracle(s["numbers"], s["xyz"])
+    assert o.singlepoint() == 0
+    assert [r[0] for r in rows] == list(range(1, o.info["niter"] + 1))
+    assert abs(rows[-1][1] - o.energies["eel"]) < 5e-7
+    assert all(abs(r[2]) < 1e-6 and r[3] < 1e-4 for r in rows[-2:])          # two consecutive converged iterations
+    assert abs(rows[-1][4] - res.get_info()["hl_gap"]) < 0.006
+    assert rows[0][5] == 0.0 and all(r[5] >= 1.0 for r in rows[1:])          # Broyden weights: none in the first iteration

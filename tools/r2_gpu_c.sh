@@ -1,11 +1,12 @@
 #!/bin/bash
 set -x
 O=gpurun_out
-timeout 600 python bench.py --workload ensemble --steps 3 --warmup 3 --secondary off > $O/c_bench.json 2> $O/c_bench.err
-python - $O/c_bench.json <<'PY'
+timeout 600 python -m pytest tests/test_gpu_round2.py -x -q 2>&1 | tail -5
+( time timeout 900 python bench.py --steps 3 --warmup 3 > $O/c_bench_full.json 2> $O/c_bench_full.err ) 2>&1 | tail -3
+python - $O/c_bench_full.json <<'PY'
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-cb=d.get('cpu_baseline') or {}
-print(sys.argv[1], round(d['value'],1), round(d['ms_per_step'],1), d['config'].get('converged'), cb.get('max_abs_dE_vs_gpu'), cb.get('niter_identical'), d['roofline'].get('avg_launch_ms'), d['roofline'].get('note')[-70:])
+print(round(d['value'],1), d['e2e']['value'], d.get('calibration'))
+for k,v in d['secondary'].items(): print(k, v.get('value'), v.get('unit'), v.get('e2e',{}).get('value'), v.get('calibration'), v.get('error'))
 PY
-timeout 900 python -m pytest tests/test_gpu_hessian.py tests/test_gpu_parity.py -x -q 2>&1 | tail -3
+tail -3 $O/c_bench_full.err

@@ -431,6 +431,27 @@ void xtb_hessian(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator calc, 
     }
 }
 
+// Fortran Ew.d edit descriptor: 0.dddddE+ee, right-adjusted in w columns
+static std::string fortran_e(double v, int w, int d) {
+    char buf[64];
+    if (v == 0.0 || !(v == v) || std::fabs(v) > 1e300) {
+        snprintf(buf, sizeof buf, "%*.*E", w, d, v);
+        if (v == 0.0) snprintf(buf, sizeof buf, "%*s", w, (std::string("0.") + std::string(d, '0') + "E+00").c_str());
+        return buf;
+    }
+    int e = (int)std::floor(std::log10(std::fabs(v))) + 1;
+    double m = v / std::pow(10.0, e);
+    char mant[48];
+    snprintf(mant, sizeof mant, "%.*f", d, std::fabs(m));
+    if (mant[0] == '1') { ++e; m /= 10.0; snprintf(mant, sizeof mant, "%.*f", d, std::fabs(m)); }   // rounding carried into the leading digit
+    char body[64];
+    snprintf(body, sizeof body, "%s%s%c%02d", v < 0 ? "-" : "", mant, e < 0 ? '-' : '+', std::abs(e));
+    std::string t(body);
+    t.insert(t.find_last_of("+-"), "E");
+    snprintf(buf, sizeof buf, "%*s", w, t.c_str());
+    return buf;
+}
+
 void xtb_singlepoint(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator calc, xtb_TResults res) {
     const char* source = "xtb_api_singlepoint";
     if (!check_env(env)) return;
@@ -453,6 +474,7 @@ void xtb_singlepoint(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator ca
         else if (b.external_charge_count() > 0) b.release_external_charges();
         if (cached) b.set_wavefunction(res->qsh.data(), res->dipm.data(), res->qp.data());
         else b.invalidate_wavefunction();
+        b.set_iteration_log(env->verbosity > 0);
         int nfail = b.singlepoint(true);
         MolResult r = b.result(0);
         res->n = n; res->nao = nao; res->nshell = nsh;
@@ -473,6 +495,17 @@ void xtb_singlepoint(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator ca
         res->has_energy = res->has_gradient = res->has_wfn = res->has_dipole = true;
         if (env->verbosity > 0) {
             FILE* f = env->out();
+            // the SCC iteration table of the reference (header src/scf_module.F90:612-616, rows src/scc_core.f90:621-622,
+            // format (i4,F15.7,E14.6,E11.3,f8.2,2x,f8.1,l3); the engine always diagonalises fully)
+            std::vector<double> lg(5 * (size_t)std::max(r.niter, 1));
+            const int rows = b.iteration_log(lg.data(), std::max(r.niter, 1));
+            fprintf(f, "\n iter      E             dE          RMSdq      gap      omega  full diag\n");
+            for (int k = 0; k < rows; ++k) {
+                const double* x = &lg[5 * (size_t)k];
+                fprintf(f, "%4d%15.7f%s%s%8.2f  %8.1f  T\n", k + 1, x[0], fortran_e(x[1], 14, 6).c_str(), fortran_e(x[2], 11, 3).c_str(),
+                        x[3], x[4]);
+            }
+            fprintf(f, "\n");
             fprintf(f, "   *** GFN2-xTB (B200): %s after %d iterations ***\n",
                     r.converged ? "convergence criteria satisfied" : "convergence criteria cannot be satisfied", r.niter);
             if (env->verbosity > 1) {

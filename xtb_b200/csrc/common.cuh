@@ -75,6 +75,9 @@ struct Dev {
     // diagnostic: counters of the discrete decisions (cutoffs, screening) at the places where the kernels take them,
     // kNCnt per molecule; nullptr unless xtbb200_setDecisionCounting switched them on
     unsigned long long* cnt;
+    // diagnostic / verbose printout: per SCC iteration of molecule 0 {E_el, E_el - E_old, rms dq, gap / eV, omega} (the columns
+    // of the reference's iteration table, src/scc_core.f90:621-622); nullptr unless Batch::set_iteration_log switched it on
+    double* iterlog;
     // per atom
     double *xyz, *cn, *cn_cov, *cn_d4, *cn_erf, *radcn;
     double *q, *q_out, *dipm, *dipm_out, *qp, *qp_out;

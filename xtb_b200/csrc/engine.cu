@@ -196,6 +196,9 @@ struct Batch::Impl {
     bool fits_blk = false, fits_scalar = false;
     // diagnostic knobs, read once at construction and only under XTBB200_TUNING=1 (common.cuh: tuning_env)
     double knob_jb_tol = 0.0, knob_jb_qtol = kJbQuadraticStop;
+    bool iterlog_on = false;
+    double* iterlog_buf = nullptr;
+    int iterlog_rows = 0;
     unsigned long long* cnt_buf = nullptr;   // decision counters (diagnostic), allocated by set_decision_counting
     int knob_jb_inner = kJbInnerSweeps;
     int knob_jb_variant = 1;    // 1: jb_sweeps2 (cross-block Gram, unnormalised rotations), 0: jb_sweeps
@@ -732,6 +735,10 @@ int Batch::singlepoint(bool restart) {
     d.jb_tol = I.knob_jb_tol;
     d.jb_qtol = I.knob_jb_qtol;
     if (d.cnt) XTB_CUDA_CHECK(cudaMemsetAsync(d.cnt, 0, sizeof(unsigned long long) * kNCnt * nmol, st));
+    if (I.iterlog_on) {
+        if (I.iterlog_rows < I.maxiter) { I.iterlog_buf = I.dalloc<double>(5 * (size_t)I.maxiter); I.iterlog_rows = I.maxiter; }
+        d.iterlog = I.iterlog_buf;
+    } else d.iterlog = nullptr;
     if (!I.ev_phase[0]) for (auto& e : I.ev_phase) cudaEventCreate(&e);
     if (!I.ev_comm[0]) for (auto& e : I.ev_comm) cudaEventCreate(&e);
     cudaEvent_t* ev = I.ev_phase;
@@ -1118,6 +1125,18 @@ int Batch::scc_passes() const { return p_->scc_passes; }
 int Batch::launches() const { return p_->launches; }
 void Batch::timings(float* t3) const { t3[0] = p_->t_setup; t3[1] = p_->t_scc; t3[2] = p_->t_grad; }
 float Batch::factorisation_ms() const { return p_->t_fact; }
+
+void Batch::set_iteration_log(bool on) { p_->iterlog_on = on; }
+
+int Batch::iteration_log(double* out, int max_rows) const {
+    const Impl& I = *p_;
+    if (!I.iterlog_on || !I.d.iterlog) return 0;
+    XTB_CUDA_CHECK(cudaSetDevice(I.device));
+    XTB_CUDA_CHECK(cudaStreamSynchronize(I.stream));
+    const int rows = std::min(max_rows, std::min(result(0).niter, I.iterlog_rows));
+    if (rows > 0) XTB_CUDA_CHECK(cudaMemcpy(out, I.d.iterlog, 5 * (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost));
+    return rows;
+}
 
 void Batch::set_decision_counting(bool on) {
     Impl& I = *p_;

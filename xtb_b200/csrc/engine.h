@@ -105,6 +105,11 @@ class Batch {
     MolResult result(int i) const;
     // diagnostic: count the discrete decisions (cutoffs, primitive screening) where the kernels take them during the
     // next single points (common.cuh: kNCnt counters per molecule, unordered pairs / triples)
+    // per-iteration log of molecule 0 (energy, energy change, rms charge change, gap, Broyden weight): the columns of the
+    // reference's SCC iteration table (src/scc_core.f90:621-622); iteration_log returns the number of rows written to
+    // out[rows][5] by the last single point
+    void set_iteration_log(bool on);
+    int iteration_log(double* out, int max_rows) const;
     void set_decision_counting(bool on);
     void decision_counts(int i, long long* out) const;
     void fetch(const char* name, double* out) const;   // device -> host copy of a named array

@@ -596,6 +596,7 @@ __global__ void __launch_bounds__(256) k_scc_finish(Dev d) {
     double* qlast = d.bqlast + m.q0;
     double* dqlast = d.bdqlast + m.q0;
     const double alpha = d.broydamp;
+    double omegap = 0.0;      // weight of this iteration's Broyden vector (printed by the reference as omega)
     if (m.nat > 1) {
         if (iter == 1) {
             for (int k = tid; k < m.nbr; k += nt) { dqlast[k] = dq[k]; qlast[k] = qin[k]; qin[k] = qin[k] + alpha * dq[k]; }
@@ -612,6 +613,7 @@ __global__ void __launch_bounds__(256) k_scc_finish(Dev d) {
             double om = sqrt(dq2);
             om = (om > (0.01 / 100000.0)) ? 0.01 / om : 100000.0;
             if (om < 1.0) om = 1.0;
+            omegap = om;
             double* dfc = df + (long long)c1 * m.nbr;
             p = 0;
             for (int k = tid; k < m.nbr; k += nt) { double v = dq[k] - dqlast[k]; dfc[k] = v; p += v * v; }
@@ -688,6 +690,10 @@ __global__ void __launch_bounds__(256) k_scc_finish(Dev d) {
         st.eold = eold; st.eel = eel; st.ees = ees; st.eaes = eaes; st.epol = epol; st.ed = ed; st.eh0 = eh0; st.epcem = epcem;
         st.rmsq = rmsq;
         st.iter = iter;
+        if (d.iterlog && im == 0 && iter <= d.maxiter) {
+            double* lg = d.iterlog + 5 * (size_t)(iter - 1);
+            lg[0] = eel; lg[1] = eel - eold; lg[2] = rmsq; lg[3] = st.egap; lg[4] = omegap;
+        }
         if (econv && qconv) {
             st.converged = 1;
             if (st.lastdiag) st.done = 1;
