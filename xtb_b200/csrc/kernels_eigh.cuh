@@ -20,9 +20,12 @@
 // Replaces dsyevd('V') inside TEigenSolver%fact_solve (src/mctc/lapack/eigensolve.F90:218-246) for large n; the
 // reduction to standard form (dsygst) and the back-substitution (dtrsm) are the X^T H X and X Z products of engine.cu.
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only: the encoder is looked up through the runtime, no link against libcuda)
+
 #include "common.cuh"
 #include "eig_dc_core.h"
 #include "kernels_linalg.cuh"
+#include "sytrd_sym_grid.h"
 
 namespace xtbb200 {
 
@@ -63,6 +66,49 @@ __device__ __forceinline__ GemmTask gemm_task_dev(const double* A, int lda, cons
     return t;
 }
 
+// C = alpha acc + beta C for a warp's 32 x 32 accumulator block (row gr0 + 8 i, columns gc0 + 8 j + {0, 1}).  With beta != 0
+// the old values are fetched sixteen at a time before the first store, so that their latencies overlap (a load after a
+// store to the same array cannot be moved up by the compiler: one L2 / HBM round trip per element otherwise).
+__device__ __forceinline__ void gemm_epilogue(const double (&acc)[4][4][2], double* __restrict__ C, int ldc, int M, int N, int gr0, int gc0,
+                                              double alpha, double beta) {
+    if (beta == 0.0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int gr = gr0 + 8 * i, gc = gc0 + 8 * j;
+                if (gr < M) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (gc + h < N) C[gr + (long long)ldc * (gc + h)] = alpha * acc[i][j][h];
+                }
+            }
+        return;
+    }
+#pragma unroll
+    for (int ih = 0; ih < 4; ih += 2) {
+        double old[2][4][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int gr = gr0 + 8 * (ih + i), gc = gc0 + 8 * j + h;
+                    old[i][j][h] = (gr < M && gc < N) ? C[gr + (long long)ldc * gc] : 0.0;
+                }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int gr = gr0 + 8 * (ih + i), gc = gc0 + 8 * j + h;
+                    if (gr < M && gc < N) C[gr + (long long)ldc * gc] = alpha * acc[ih + i][j][h] + beta * old[i][j][h];
+                }
+    }
+}
+
 // tasks != null: task = tasks[blockIdx.y + zstride * blockIdx.z] (zstride > 0: batch of matrices along z, no K split)
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(128, 3) k_eg_gemm(GemmTask t0, const GemmTask* __restrict__ tasks, int zstride = 0,
@@ -87,7 +133,10 @@ __global__ void __launch_bounds__(128, 3) k_eg_gemm(GemmTask t0, const GemmTask*
     const int M = t.M - r0, N = t.N - c0;   // valid rows / columns of this tile (may exceed GT)
     const int sgA = t.ksegA ? t.ksegA : 0x7fffffff, oA = t.offA2 - t.ksegA;
     const int sgB = t.ksegB ? t.ksegB : 0x7fffffff, oB = t.offB2 - t.ksegB;
-    __shared__ double As[GK][GLD], Bs[GK][GLD];
+    // operand tiles: [k][row] with pitch GLD when the k index is the slow one in global memory, [row][k] with pitch GK + 4 when it
+    // is the fast one (TA / !TB): in both layouts the staging stores and the m8n8k4 fragment loads are free of bank conflicts
+    constexpr int PK = GK + 4;
+    __shared__ double As[TA ? GT * PK : GK * GLD], Bs[TB ? GK * GLD : GT * PK];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wr = (warp & 1) * 32, wc = (warp >> 1) * 32;
     double acc[4][4][2];
@@ -120,8 +169,8 @@ __global__ void __launch_bounds__(128, 3) k_eg_gemm(GemmTask t0, const GemmTask*
 #pragma unroll
         for (int u = 0; u < GT * GK / 128; ++u) {
             const int tt = tid + 128 * u;
-            if (!TA) As[tt / GT][tt % GT] = ra[u]; else As[tt % GK][tt / GK] = ra[u];
-            if (!TB) Bs[tt % GK][tt / GK] = rb[u]; else Bs[tt / GT][tt % GT] = rb[u];
+            if (!TA) As[(tt / GT) * GLD + tt % GT] = ra[u]; else As[(tt / GK) * PK + tt % GK] = ra[u];
+            if (!TB) Bs[(tt / GK) * PK + tt % GK] = rb[u]; else Bs[(tt / GT) * GLD + tt % GT] = rb[u];
         }
     };
     if (ke > kb) fetch(kb);
@@ -133,9 +182,11 @@ __global__ void __launch_bounds__(128, 3) k_eg_gemm(GemmTask t0, const GemmTask*
         for (int ks = 0; ks < GK; ks += 4) {
             double af[4], bf[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = As[ks + (lane & 3)][wr + 8 * i + (lane >> 2)];
+            for (int i = 0; i < 4; ++i)
+                af[i] = TA ? As[(wr + 8 * i + (lane >> 2)) * PK + ks + (lane & 3)] : As[(ks + (lane & 3)) * GLD + wr + 8 * i + (lane >> 2)];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = Bs[ks + (lane & 3)][wc + 8 * j + (lane >> 2)];
+            for (int j = 0; j < 4; ++j)
+                bf[j] = TB ? Bs[(ks + (lane & 3)) * GLD + wc + 8 * j + (lane >> 2)] : Bs[(wc + 8 * j + (lane >> 2)) * PK + ks + (lane & 3)];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -143,23 +194,7 @@ __global__ void __launch_bounds__(128, 3) k_eg_gemm(GemmTask t0, const GemmTask*
         }
         __syncthreads();
     }
-    const double alpha = t.alpha, beta = t.beta;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gr = wr + 8 * i + (lane >> 2);
-            const int gc = wc + 8 * j + 2 * (lane & 3);
-            if (gr < M) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    if (gc + h < N) {
-                        double* p = C + gr + (long long)ldc * (gc + h);
-                        const double v = alpha * acc[i][j][h];
-                        *p = (beta == 0.0) ? v : v + beta * *p;
-                    }
-            }
-        }
+    gemm_epilogue(acc, C, ldc, M, N, wr + (lane >> 2), wc + 2 * (lane & 3), t.alpha, t.beta);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -204,6 +239,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// one box of a 2-D tensor map (dimension 0 = rows of the column-major matrix, dimension 1 = columns) into shared memory:
+// SASS UTMALDG.2D; lines outside the matrix arrive as zeros and count towards the transaction bytes like the others
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int row0, int col0, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(row0), "r"(col0), "r"(smem_u32(bar))
                  : "memory");
 }
 
@@ -286,23 +330,7 @@ __global__ void __launch_bounds__(160) k_eg_gemm_tma(GemmTask t) {
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
     }
-    const double alpha = t.alpha, beta = t.beta;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gr = wr + 8 * i + l4;
-            const int gc = wc + 8 * j + 2 * l3;
-            if (gr < M) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    if (gc + h < N) {
-                        double* p = C + gr + (long long)ldc * (gc + h);
-                        const double v = alpha * acc[i][j][h];
-                        *p = (beta == 0.0) ? v : v + beta * *p;
-                    }
-            }
-        }
+    gemm_epilogue(acc, C, ldc, M, N, wr + l4, wc + 2 * l3, t.alpha, t.beta);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -326,6 +354,12 @@ struct SytrdArgs {
     int gq;             // offset of this panel inside the block reflector (0 or EB)
     unsigned* bar;      // grid barrier counter (zeroed before the launch)
     long long* prof;    // optional: cycles of CTA 0 per phase section (diagnostics), else null
+    // symmetric form of the trailing-matrix product (sym != 0): only the lower triangle is read, as 128 x 32 tiles streamed
+    // through a shared-memory ring by the bulk asynchronous copy engine; partial sums of y per tile / per CTA segment
+    int sym;            // 0: warp-per-column dot products over both triangles
+    int nst;            // stages of the tile ring (2 .. kSyStagesMax)
+    double* colbuf;     // [tile][kSyCW]  column sums of every tile (the transposed product)
+    double* rowbuf;     // [(row chunk - first row chunk) + CTA][kSyRH]  row sums of a CTA's consecutive tiles of one row chunk
 };
 #define SY_T(k) do { if (a.prof && cta == 0 && tid == 0) { const long long t_ = clock64(); a.prof[k] += t_ - tprof; tprof = t_; } } while (0)
 
@@ -377,15 +411,28 @@ __device__ __forceinline__ void grid_sum_barrier(double v, double* red, double* 
     __syncthreads();
 }
 
+
+constexpr int kSyGT = kSytrdThreads / kSyGroups;   // threads of a group of warps of the symmetric panel product
+static_assert(kSyRH == 4 * kSyCW && kSyRH == 4 * 32 && kSyGT / 32 * 4 == kSyCW , "tile mapping of k_sytrd_panel");
+
 constexpr int kSyRows = 64;                         // rows per CTA pass of the panel update
 constexpr int kSySlices = kSytrdThreads / kSyRows;  // threads per row, each with a slice of the panel columns
 constexpr int kSyKmax = (EB + kSySlices - 1) / kSySlices;
 
-// dynamic shared memory: sv[n] | sh_part[(n / grid + 6) * 8]
-__global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
-    extern __shared__ double sm_dyn[];
+// dynamic shared memory: sv[n] | sh_part[(n / grid + 6) * 8]; symmetric form: sv[npad] (absolute row index, zero outside the
+// trailing range) | sh_part | tile ring [nst][kSyTile] (128-byte aligned)
+inline size_t sytrd_sym_ring_offset(int n, int grid) {   // in doubles
+    const size_t npad = (size_t)(n + kSyRH - 1) / kSyRH * kSyRH;
+    return (npad + (size_t)(n / grid + 6) * 8 + 15) / 16 * 16;
+}
+__global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) double sm_dyn[];
     __shared__ double sh_vtv[EB], sh_wtv[EB], sh_vrow[EB], sh_wrow[EB], red[32], sh_sc[4];
-    __shared__ double sh_r1[kSySlices][kSyRows], sh_r2[kSySlices][kSyRows];
+    __shared__ __align__(16) double sh_r12[2][kSySlices][kSyRows];
+    __shared__ double sh_r3[kSySlices][kSyRows];
+    double (*sh_r1)[kSyRows] = sh_r12[0];
+    double (*sh_r2)[kSyRows] = sh_r12[1];
+    __shared__ unsigned long long sy_full[kSyGroups];
     const int n = a.n, G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const int rl = tid & (kSyRows - 1), ks = tid / kSyRows;
@@ -393,8 +440,28 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
     double* __restrict__ A = a.A;
     double* __restrict__ V = a.V;
     double* __restrict__ W = a.W;
-    double* sv = sm_dyn;
-    double* sh_part = sm_dyn + n;
+    const bool sym = a.sym != 0;
+    const int npad = (n + kSyRH - 1) / kSyRH * kSyRH;
+    double* svabs = sm_dyn;                                   // symmetric form: v by absolute row
+    double* sv = sm_dyn;                                      // v by row relative to j + 1 (set per column in the symmetric form)
+    double* sh_part = sm_dyn + (sym ? npad : n);
+    double* ring = sm_dyn + (sym ? ((size_t)npad + (size_t)(n / G + 6) * 8 + 15) / 16 * 16 : 0);
+    // symmetric form: the CTA works as kSyGroups groups of 8 warps; group q takes every kSyGroups-th tile of the CTA's range
+    // into ring stage q (one tensor-map box per tile, issued by the group's first thread, completion on sy_full[q])
+    const int grp = tid / kSyGT, gw = warp & (kSyGT / 32 - 1);
+    unsigned guse = 0;                                        // tiles this group has taken since the launch (mbarrier phase)
+    if (sym) {
+        for (int t = tid; t < npad; t += nthr) svabs[t] = 0.0;
+        if (tid == 0) {
+            for (int s = 0; s < kSyGroups; ++s) mbar_init(sy_full + s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    auto issue_tile = [&](int R, int S) {                     // one thread of the group
+        mbar_expect_tx(sy_full + grp, (unsigned)(kSyTile * sizeof(double)));
+        tma_load_2d(ring + (size_t)grp * kSyTile, &tmap, R * kSyRH, S * kSyCW, sy_full + grp);
+    };
     unsigned target = 0;
     double taup = 0.0;   // tau of the previous column
     long long tprof = clock64();
@@ -402,6 +469,7 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
         const int j = a.j0 + i;
         const bool fin = i > 0, upd = i < a.ncols;
         const int ip = i - 1, jp = j - 1;
+        const SymGrid gy = (sym && fin) ? sym_grid(j, n) : SymGrid();   // tile grid of the product with column j-1's reflector
         // ---------------- phase A: finish w of column j-1, update column j, partial norm.  A CTA pass covers kSyRows
         // rows; the panel columns of a row are shared out over kSySlices threads so that all loads of a pass are in
         // flight together (the panel sits in L2; a serial loop per row would pay its latency 2*ip times).
@@ -409,7 +477,11 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
         for (int base = j + cta * kSyRows, pass = 0; base < n || pass == 0; base += G * kSyRows, ++pass) {
             const int r = base + rl;
             const bool rv = r < n;
-            double vk[kSyKmax], wk[kSyKmax], vr = 0.0, yr = 0.0, ar = 0.0;
+            double vk[kSyKmax], wk[kSyKmax], vr = 0.0, yr = 0.0, ar = 0.0, yg = 0.0, yjg = 0.0;
+            if (sym && fin) {   // y = A v of column j-1 from the tile sums: this thread's slice of the terms of row r (and of row j)
+                if (rv) yg = sym_gather(gy, G, r, ks, kSySlices, a.rowbuf, a.colbuf);
+                if (pass == 0 && warp == 0 && lane < kSySlices) yjg = sym_gather(gy, G, j, lane, kSySlices, a.rowbuf, a.colbuf);
+            }
             if (fin) {
 #pragma unroll
                 for (int u = 0; u < kSyKmax; ++u) {
@@ -418,7 +490,7 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
                     vk[u] = ok ? __ldcg(V + r + ld * k) : 0.0;
                     wk[u] = ok ? __ldcg(W + r + ld * k) : 0.0;
                 }
-                if (ks == 0 && rv) { vr = __ldcg(V + r + ld * ip); yr = __ldcg(a.y + r); }
+                if (ks == 0 && rv) { vr = __ldcg(V + r + ld * ip); if (!sym) yr = __ldcg(a.y + r); }
             }
             if (ks == 0 && rv && upd) ar = __ldcg(A + r + ld * j);
             double alpha2 = 0.0;
@@ -427,7 +499,10 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
                     double vy = 0.0, yj = 0.0;
                     if (warp == 0) {
                         for (int c = lane; c < G; c += 32) vy += __ldcg(a.part_vy + c);
-                        if (lane == 0) yj = __ldcg(a.y + j);
+                        if (sym) {
+#pragma unroll
+                            for (int u = 0; u < kSySlices; ++u) yj += __shfl_sync(0xffffffffu, yjg, u);
+                        } else if (lane == 0) yj = __ldcg(a.y + j);
                     }
                     for (int k = tid; k < ip; k += nthr) {
                         sh_vtv[k] = __ldcg(a.vtv + k); sh_wtv[k] = __ldcg(a.wtv + k);
@@ -459,6 +534,7 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
                     }
                 }
                 sh_r1[ks][rl] = s1; sh_r2[ks][rl] = s2;
+                if (sym) sh_r3[ks][rl] = yg;
                 __syncthreads();
             }
             if (ks == 0 && rv) {
@@ -467,6 +543,10 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
                     double s1 = 0.0;
 #pragma unroll
                     for (int u = 0; u < kSySlices; ++u) { s1 += sh_r1[u][rl]; s2 += sh_r2[u][rl]; }
+                    if (sym) {
+#pragma unroll
+                        for (int u = 0; u < kSySlices; ++u) yr += sh_r3[u][rl];
+                    }
                     const double wr = taup * (yr - s1) + alpha2 * vr;
                     W[r + ld * ip] = wr;
                     if (r > j) A[r + ld * jp] = vr;             // reflector storage below the sub-diagonal
@@ -483,10 +563,27 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
         }
         if (!upd || j == n - 1) break;
         SY_T(1);
+        // symmetric form: this CTA's tiles of the product with column j's reflector; the trailing matrix does not change
+        // inside a panel, so the first copies are issued before the barrier and land while it is being crossed
+        const SymGrid sg = sym ? sym_grid(j + 1, n) : SymGrid();
+        int tcur = 0, tend = 0, cR = 0, cS = 0;   // tiles [tcur, tend) of this CTA, the first one is (cR, cS)
+        if (sym) {
+            tcur = sym_start(sg, cta, G); tend = sym_start(sg, cta + 1, G);
+            if (tcur < tend) sym_locate(sg, tcur, cR, cS);
+            if ((tid & (kSyGT - 1)) == 0 && tcur + grp < tend) {
+                int R = cR, S = cS;
+                for (int u = 0; u < grp; ++u) sym_next(sg, R, S);
+                issue_tile(R, S);
+            }
+        }
         grid_sum_barrier(sq, red, a.part_n, a.bar, G, target);
         SY_T(3);
         // ---------------- phase B: reflector, trailing-matrix product, V^T v, W^T v
         const int m = n - j - 1;
+        if (sym) {
+            sv = svabs + j + 1;
+            if (tid == 0) svabs[j] = 0.0;   // the unit entry of the previous reflector
+        }
         {   // raw column and the norm partials are loaded together; the column is scaled once the reflector is known
             double s = 0.0, alpha = 0.0;
             if (warp == 0) {
@@ -516,10 +613,10 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
         SY_T(4);
         // jobs of this CTA: its share of the trailing columns, plus V / W (/ previous panel V) columns dealt round-robin
         const int cb = j + 1 + (int)(((long long)m * cta) / G), ce = j + 1 + (int)(((long long)m * (cta + 1)) / G);
-        const int ncA = ce - cb;
+        const int ncA = sym ? 0 : ce - cb;
         int nex = 0, nex2 = 0;
         for (int k = cta; k < i; k += G) ++nex;
-        if (a.Vprev) for (int k = cta; k < EB; k += G) ++nex2;
+        if (a.Vprev && !sym) for (int k = cta; k < EB; k += G) ++nex2;   // symmetric form: Gram matrices by one GEMM afterwards
         const int nloc = ncA + 2 * nex + nex2;
         int Q = 1;
         if (nloc > 0) {
@@ -567,11 +664,107 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a) {
             } else if (lc < ncA + 2 * nex) {
                 const int x = lc - ncA, k = cta + (x >> 1) * G;
                 if (x & 1) a.wtv[k] = s;
-                else { a.vtv[k] = s; a.G[(a.gq + k) + NB * (a.gq + i)] = s; }
+                else { a.vtv[k] = s; if (!sym) a.G[(a.gq + k) + NB * (a.gq + i)] = s; }
             } else a.G[(cta + (lc - ncA - 2 * nex) * G) + NB * (a.gq + i)] = s;
         }
         taup = tau;
         SY_T(6);
+        if (sym) {
+            // ---- lower-triangle tiles: y[r] += T[r, c] v[c] (row sums) and y[c] += T[r, c] v[r] (column sums); diagonal tiles
+            // count A[r, r] once and nothing above it.  Inside a group: lane = 4 consecutive rows, warp = 4 consecutive columns
+            // of the tile; every element is read once.  The row sums stay in registers over the tiles of a row chunk and are
+            // added up over the CTA when the chunk ends; the column sums of a tile are complete inside the warp.
+            double rowacc[4] = {0.0, 0.0, 0.0, 0.0};
+            double* scr = &sh_r12[0][0][0];                              // [16 warps][kSyRH]
+            auto flush_rows = [&](int R) {
+                double tot = 0.0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if ((warp >> 4) == h) {
+                        double* q = scr + (warp & 15) * kSyRH + 4 * lane;
+                        *reinterpret_cast<double2*>(q) = make_double2(rowacc[0], rowacc[1]);
+                        *reinterpret_cast<double2*>(q + 2) = make_double2(rowacc[2], rowacc[3]);
+                    }
+                    __syncthreads();
+                    if (tid < kSyRH) {
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) tot += scr[u * kSyRH + tid];
+                    }
+                    __syncthreads();
+                }
+                if (tid < kSyRH) {
+                    a.rowbuf[(size_t)(R - sg.Rmin + cta) * kSyRH + tid] = tot;
+                    vyl += svabs[R * kSyRH + tid] * tot;
+                }
+                rowacc[0] = rowacc[1] = rowacc[2] = rowacc[3] = 0.0;
+            };
+            const int ntile = tend - tcur;
+            int kR = cR, kS = cS;
+            for (int k = 0; k < ntile; ++k) {
+                if ((k & (kSyGroups - 1)) == grp) {
+                    mbar_wait(sy_full + grp, guse & 1);
+                    ++guse;
+                    const double* T = ring + (size_t)grp * kSyTile;
+                    const int r0 = kR * kSyRH + 4 * lane, c0 = kS * kSyCW + 4 * gw;   // first row / column of this thread
+                    const bool diag = (kS >> 2) == kR;
+                    double vr[4], vc[4], colp[4];
+                    {
+                        const double2 p0 = *reinterpret_cast<const double2*>(svabs + r0), p1 = *reinterpret_cast<const double2*>(svabs + r0 + 2);
+                        const double2 q0 = *reinterpret_cast<const double2*>(svabs + c0), q1 = *reinterpret_cast<const double2*>(svabs + c0 + 2);
+                        vr[0] = p0.x; vr[1] = p0.y; vr[2] = p1.x; vr[3] = p1.y;
+                        vc[0] = q0.x; vc[1] = q0.y; vc[2] = q1.x; vc[3] = q1.y;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double* q = T + (4 * gw + u) * kSyRH + 4 * lane;
+                        const double2 xa = *reinterpret_cast<const double2*>(q), xb = *reinterpret_cast<const double2*>(q + 2);
+                        double x[4] = {xa.x, xa.y, xb.x, xb.y};
+                        if (diag) {
+                            double cp = 0.0;
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                const int d = (r0 + h) - (c0 + u);
+                                rowacc[h] += (d >= 0 ? x[h] : 0.0) * vc[u];
+                                cp += (d > 0 ? x[h] : 0.0) * vr[h];
+                            }
+                            colp[u] = cp;
+                        } else {
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) rowacc[h] += x[h] * vc[u];
+                            colp[u] = (x[0] * vr[0] + x[1] * vr[1]) + (x[2] * vr[2] + x[3] * vr[3]);
+                        }
+                    }
+                    // four column sums over the 32 lanes: halve the number of values per lane twice, then three plain steps
+                    double cs;
+                    {
+                        const bool h4 = lane & 16, h3 = lane & 8;
+                        const double b0 = (h4 ? colp[2] : colp[0]) + __shfl_xor_sync(0xffffffffu, h4 ? colp[0] : colp[2], 16);
+                        const double b1 = (h4 ? colp[3] : colp[1]) + __shfl_xor_sync(0xffffffffu, h4 ? colp[1] : colp[3], 16);
+                        cs = (h3 ? b1 : b0) + __shfl_xor_sync(0xffffffffu, h3 ? b0 : b1, 8);
+                        cs += __shfl_xor_sync(0xffffffffu, cs, 4);
+                        cs += __shfl_xor_sync(0xffffffffu, cs, 2);
+                        cs += __shfl_xor_sync(0xffffffffu, cs, 1);
+                    }
+                    if ((lane & 7) == 0) {                                // lanes 0, 8, 16, 24: columns 0, 1, 2, 3 of the warp
+                        const int c = c0 + (lane >> 3);
+                        if (c < n) {
+                            a.colbuf[(size_t)(tcur + k) * kSyCW + 4 * gw + (lane >> 3)] = cs;
+                            vyl += svabs[c] * cs;
+                        }
+                    }
+                    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kSyGT) : "memory");   // the group has read its stage
+                    if ((tid & (kSyGT - 1)) == 0 && k + kSyGroups < ntile) {
+                        int R = kR, S = kS;
+#pragma unroll
+                        for (int u = 0; u < kSyGroups; ++u) sym_next(sg, R, S);
+                        issue_tile(R, S);
+                    }
+                }
+                const int Rdone = kR;
+                sym_next(sg, kR, kS);
+                if (kR != Rdone || k + 1 == ntile) flush_rows(Rdone);
+            }
+        }
         grid_sum_barrier(vyl, red, a.part_vy, a.bar, G, target);
         SY_T(7);
     }
@@ -1282,6 +1475,9 @@ struct EighWork {
     size_t res_smem_cap = 0;
     int res_grid_want = 0;   // CTAs of the resident tridiagonalisation (0: automatic)
     size_t smem_limit = 0;
+    size_t panel_smem_cap = 0; // dynamic shared memory the panel kernel may use
+    double *sym_colbuf = nullptr, *sym_rowbuf = nullptr;   // tile sums of the symmetric trailing-matrix product
+    bool sym_off = false;
     int resident_max = 0;      // largest trailing order the shared-memory resident tridiagonalisation takes
     long long* prof = nullptr;
     GemmTask* tasks = nullptr;
@@ -1290,6 +1486,19 @@ struct EighWork {
     float ms[3] = {0, 0, 0};   // tridiagonalisation, divide and conquer, back-transformation of the last timed call
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int launches = 0;
+
+    // tensor map of a column-major n x n FP64 matrix with boxes of kSyRH rows x kSyCW columns (symmetric panel product)
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    EncodeTiledFn encode_tiled = nullptr;
+    bool make_tile_map(CUtensorMap* map, double* A, int n) const {
+        if (!encode_tiled) return false;
+        const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)n}, gstride[1] = {(cuuint64_t)n * sizeof(double)};
+        const cuuint32_t box[2] = {(cuuint32_t)kSyRH, (cuuint32_t)kSyCW}, estr[2] = {1, 1};
+        return encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, A, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
 
     template <class T>
     T* alloc(size_t cnt) {
@@ -1326,10 +1535,25 @@ struct EighWork {
         kcnt = alloc<int>(n); nrot = alloc<int>(n); fail = alloc<int>(1); rank = alloc<int>(n);
         bar = alloc<unsigned>(1);
         cbuf = alloc<double>(2 * n); ybuf = alloc<double>(2 * n);
-        prof = alloc<long long>(8);
+        prof = alloc<long long>(16);
         tasks = alloc<GemmTask>(2 * n);
         grid = nsm;
-        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sytrd_smem(nmax, grid)));
+        {   // the panel kernel may use all the shared memory its static part leaves (tile ring of the symmetric form)
+            cudaFuncAttributes fa;
+            XTB_CUDA_CHECK(cudaFuncGetAttributes(&fa, k_sytrd_panel));
+            panel_smem_cap = (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes;
+            if (sytrd_smem(nmax, grid) > panel_smem_cap) throw std::runtime_error("xtb_b200: tridiagonalisation kernel: matrix order too large");
+            XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sytrd_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem_cap));
+            const size_t nS = (n + kSyCW - 1) / kSyCW, nR = (n + kSyRH - 1) / kSyRH;
+            sym_colbuf = alloc<double>(nS * nR * kSyCW);
+            sym_rowbuf = alloc<double>((nR + (size_t)nsm + 1) * kSyRH);
+            sym_off = tuning_env("XTBB200_NO_SYM_SYTRD") != nullptr;
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qr;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+                encode_tiled = (EncodeTiledFn)fn;
+            cudaGetLastError();
+        }
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 8)));
         smem_limit = (size_t)prop.sharedMemPerBlockOptin - 1024;
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_dc_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1366,7 +1590,7 @@ struct EighWork {
         }
         if (const char* e = tuning_env("XTBB200_RES_GRID")) res_grid_want = std::max(1, std::atoi(e));   // tuning knob
         int occ = 0;
-        XTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sytrd_panel, kSytrdThreads, sytrd_smem(nmax, grid)));
+        XTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sytrd_panel, kSytrdThreads, panel_smem_cap));
         if (occ < 1) throw std::runtime_error("xtb_b200: tridiagonalisation kernel does not fit on an SM");
         for (auto& e : ev) cudaEventCreate(&e);
     }
@@ -1552,6 +1776,18 @@ struct EighWork {
         double* Wp = PB + (size_t)n * NB;
         XTB_CUDA_CHECK(cudaMemsetAsync(Gf, 0, (size_t)nblk * NB * NB * sizeof(double), st));
         int jres = -1;   // column from which the shared-memory resident kernel takes over (block reflector boundary)
+        // symmetric form of the trailing-matrix product (lower triangle only, tiles streamed by the copy engine): needs
+        // 16-byte aligned tile lines (even order, aligned base) and room for at least two ring stages
+        int sym_nst = 0;
+        CUtensorMap tmap;
+        std::memset(&tmap, 0, sizeof(tmap));
+        if (!sym_off && (n & 1) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && n - EB > resident_max) {
+            const size_t off = sytrd_sym_ring_offset(n, grid) * sizeof(double);
+            if (panel_smem_cap > off) sym_nst = (int)std::min<size_t>(kSyStagesMax, (panel_smem_cap - off) / (kSyTile * sizeof(double)));
+            if (sym_nst < kSyGroups || !make_tile_map(&tmap, A, n)) sym_nst = 0;   // one ring stage per group of warps
+        }
+        const size_t panel_smem = sym_nst ? sytrd_sym_ring_offset(n, grid) * sizeof(double) + (size_t)sym_nst * kSyTile * sizeof(double)
+                                          : sytrd_smem(n, grid);
         for (int p = 0; p < npan; ++p) {
             const int j0 = p * EB, nc = std::min(EB, n - j0), q = p & 1;
             if (q == 0 && n - j0 <= resident_max) { jres = j0; break; }
@@ -1564,10 +1800,10 @@ struct EighWork {
             sa.d = dd; sa.e = ee; sa.tau = tau; sa.y = y; sa.part_n = part; sa.part_vy = part + nsm; sa.vtv = vtv; sa.wtv = wtv;
             sa.G = Gf + (size_t)(p >> 1) * NB * NB; sa.gq = EB * q; sa.bar = bar;
             sa.prof = tuning_env("XTBB200_SYTRD_PROF") ? prof : nullptr;
-            void* args[] = {&sa};
+            sa.sym = sym_nst ? 1 : 0; sa.nst = sym_nst; sa.colbuf = sym_colbuf; sa.rowbuf = sym_rowbuf;
+            void* args[] = {&sa, &tmap};
             hook(0, 0, 0);
-            XTB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sytrd_panel, dim3(grid), dim3(kSytrdThreads), args,
-                                                       sytrd_smem(n, grid), st));
+            XTB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_sytrd_panel, dim3(grid), dim3(kSytrdThreads), args, panel_smem, st));
             hook(0, 1, 1);
             ++nl;
             const int j1 = j0 + nc, mt = n - j1;
@@ -1609,11 +1845,12 @@ struct EighWork {
             XTB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(gres), dim3(tres), args, sytrd_smem_resident_bytes(n - jres, gres), st));
             hook(0, 1, 1);
             ++nl;
-            const int nrb = (n - 1 - jres + NB - 1) / NB;    // block reflectors of the resident range
+            const int jg = sym_nst ? 0 : jres;               // symmetric panel kernel: it leaves all Gram matrices to this step
+            const int nrb = (n - 1 - jg + NB - 1) / NB;      // block reflectors of the resident range
             if (nrb > 0) {
                 hook(1, 0, 0);
-                k_gram_formv<<<(unsigned)(((size_t)n * (n - 1 - jres) + 255) / 256), 256, 0, st>>>(A, n, jres, Qg);
-                k_gram_tasks<<<(nrb + 63) / 64, 64, 0, st>>>(tasks, n, jres, Qg, Gf);
+                k_gram_formv<<<(unsigned)(((size_t)n * (n - 1 - jg) + 255) / 256), 256, 0, st>>>(A, n, jg, Qg);
+                k_gram_tasks<<<(nrb + 63) / 64, 64, 0, st>>>(tasks, n, jg, Qg, Gf);
                 k_eg_gemm<true, false><<<dim3(4, nrb), 128, 0, st>>>(GemmTask(), tasks);
                 hook(1, 1, 3);
                 nl += 3;
@@ -1703,11 +1940,11 @@ struct EighWork {
             for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
         }
         if (timed && tuning_env("XTBB200_SYTRD_PROF")) {
-            long long h[8];
+            long long h[16];
             cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
-            static const char* nm[8] = {"A:scalars", "A:rows", "A:reduce", "barrier1", "B:reflector+v", "B:column dots", "B:collect",
-                                        "barrier2"};
-            for (int k = 0; k < 8; ++k) std::fprintf(stderr, "sytrd phase %-14s %10.3f us per column (n=%d)\n", nm[k], h[k] / 1.965e3 / n, n);
+            static const char* nm[16] = {"A:gather+scalars", "A:rows", "A:reduce", "barrier1", "B:reflector+v", "B:column dots", "B:collect",
+                                         "barrier2", "T:wait full", "T:column sums", "T:row sums", "T:issue", "T:flush", "-", "-", "-"};
+            for (int k = 0; k < 13; ++k) std::fprintf(stderr, "sytrd phase %-14s %10.3f us per column (n=%d)\n", nm[k], h[k] / 1.965e3 / n, n);
             cudaMemset(prof, 0, sizeof(h));
         }
         launches = nl;
