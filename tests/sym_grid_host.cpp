@@ -12,7 +12,7 @@ using namespace xtbb200;
 
 // A: n x n column-major (only the lower triangle is read), jj: first trailing index, v: n entries (entries < jj ignored).
 // y[r], r >= jj.  stats: [0] tiles, [1] largest row-sum slot + 1, [2] largest tile index + 1, [3] CTAs with work,
-// [4] largest number of tiles of one CTA.  Returns 0, or a negative code when a slot would be written twice.
+// [4] largest number of tiles of one CTA, [5] largest number of terms of a row of y while the trailing order is at least 1800 (the resident kernel takes over at about 1860).  Returns 0, or a negative code when a slot would be written twice.
 extern "C" int sym_product_host(int n, int jj, int G, const double* A, const double* vin, double* y, long long* stats) {
     const int npad = (n + kSyRH - 1) / kSyRH * kSyRH;
     std::vector<double> v(npad, 0.0);
@@ -78,9 +78,14 @@ extern "C" int sym_product_host(int n, int jj, int G, const double* A, const dou
     }
     for (int r = jj; r < n; ++r) {
         double s = 0.0;
-        for (int ks = 0; ks < 16; ++ks) s += sym_gather(g, G, r, ks, 16, rowbuf.data(), colbuf.data());
+        for (int ks = 0; ks < 16; ++ks) {
+            const double* q[kSyGatherTerms];
+            if (!sym_gather_ptrs(g, G, r, ks, 16, rowbuf.data(), colbuf.data(), q)) return -7;
+            s += sym_gather_sum(q);
+        }
         y[r] = s;
     }
+    stats[5] = sym_gather_max_terms(n, G, n - 1800);
     stats[0] = g.T; stats[1] = maxrow; stats[2] = maxtile; stats[3] = busy; stats[4] = most;
     return 0;
 }

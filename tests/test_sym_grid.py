@@ -36,12 +36,31 @@ def test_symmetric_product_from_tile_sums(harness, n, jj, G):
     ref = a[jj:, jj:] @ v[jj:]
     low = np.asfortranarray(np.tril(a) + np.triu(np.full((n, n), 1e30), 1))   # the upper triangle must never be used
     y = np.zeros(n)
-    stats = np.zeros(5, dtype=np.int64)
+    stats = np.zeros(6, dtype=np.int64)
     dp = ctypes.POINTER(ctypes.c_double)
     rc = harness.sym_product_host(n, jj, G, low.ctypes.data_as(dp), v.ctypes.data_as(dp), y.ctypes.data_as(dp),
                                   stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+    nS, nR = (n + 31) // 32, (n + 127) // 128
+    if rc == -7:   # more terms per row than a slice of threads holds: only with fewer tiles than CTAs, where the launch code
+        assert n < 1900 and G > 100   # (EighWork::solve, sym_gather_max_terms) keeps the two-triangle form
+        return
     assert rc == 0
     assert np.max(np.abs(y[jj:] - ref)) < 1e-11 * max(1.0, np.abs(ref).max())
-    nS, nR = (n + 31) // 32, (n + 127) // 128
     assert stats[1] <= nR + G + 1 and stats[2] <= nS * nR      # buffer sizes of EighWork::init
     assert stats[4] <= (stats[0] + G - 1) // G                  # balanced ranges
+
+
+def test_terms_per_row_fit_the_slices_at_production_orders(harness):
+    # every order the panel kernel can meet on 148 CTAs with the symmetric form: 16 slices x 6 terms
+    dp = ctypes.POINTER(ctypes.c_double)
+    for n in (1924, 3000, 6000, 9000):
+        stats = np.zeros(6, dtype=np.int64)
+        a = np.zeros((1, 1))
+        # jj = n - 1: a one-element trailing matrix keeps the walk cheap; stats[5] covers all trailing orders of n
+        low = np.asfortranarray(np.zeros((n, n)))
+        v = np.zeros(n)
+        y = np.zeros(n)
+        rc = harness.sym_product_host(n, n - 1, 148, low.ctypes.data_as(dp), v.ctypes.data_as(dp), y.ctypes.data_as(dp),
+                                      stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+        assert rc in (0, -7)
+        assert stats[5] <= 16 * 6, (n, stats[5])

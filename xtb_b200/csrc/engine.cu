@@ -202,7 +202,7 @@ struct Batch::Impl {
     unsigned long long* cnt_buf = nullptr;   // decision counters (diagnostic), allocated by set_decision_counting
     int knob_jb_inner = kJbInnerSweeps;
     int knob_jb_variant = 1;    // 1: jb_sweeps2 (cross-block Gram, unnormalised rotations), 0: jb_sweeps
-    bool knob_no_cluster_eig = false, knob_cta_chol = false;
+    bool knob_no_cluster_eig = false, knob_cta_chol = false, knob_cluster_single = false;
     size_t bytes = 0;
     // timing (ms) of the last single point
     float t_setup = 0, t_scc = 0, t_grad = 0, t_fact = 0;   // t_fact: overlap factorisation, part of t_setup
@@ -268,6 +268,7 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         if (const char* e = tuning_env("XTBB200_JB_VARIANT")) I.knob_jb_variant = std::atoi(e) ? 1 : 0;
         if (const char* e = tuning_env("XTBB200_SOLVER")) I.solver = std::atoi(e);   // initial value only: set_solver() wins
         I.knob_no_cluster_eig = tuning_env("XTBB200_NO_CLUSTER_EIG") != nullptr;
+        I.knob_cluster_single = tuning_env("XTBB200_CLUSTER_SINGLE") != nullptr;
         I.knob_cta_chol = tuning_env("XTBB200_CTA_CHOL") != nullptr;
         const int maxhist = 120;
         int off = 0;
@@ -822,7 +823,7 @@ int Batch::singlepoint(bool restart) {
     // (a) solver mode 4 for ensemble-sized matrices (cross-check of the block Jacobi); (b) batches of mid-size matrices of one
     // order (conformers of a 60-150 atom molecule): instead of one matrix after the other through the GPU-wide solver, all
     // of them at once with one thread-block cluster per matrix in the tridiagonalisation
-    const bool clu_batch = dc && nmol >= 2 && (I.solver == 4 || (I.solver == 0 && !I.knob_no_cluster_eig));
+    const bool clu_batch = dc && nmol >= (I.knob_cluster_single ? 1 : 2) && (I.solver == 4 || (I.solver == 0 && !I.knob_no_cluster_eig));
     if ((use_blk && I.solver == 4) || clu_batch) {
         bool uniform = true;
         for (auto& m : s.mol) uniform = uniform && m.nao == s.max_nao;

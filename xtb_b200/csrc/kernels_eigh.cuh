@@ -412,6 +412,7 @@ __device__ __forceinline__ void grid_sum_barrier(double v, double* red, double* 
 }
 
 
+constexpr int kSyMaxChunks = 96;                    // row chunks of the largest order the symmetric form takes
 constexpr int kSyGT = kSytrdThreads / kSyGroups;   // threads of a group of warps of the symmetric panel product
 static_assert(kSyRH == 4 * kSyCW && kSyRH == 4 * 32 && kSyGT / 32 * 4 == kSyCW , "tile mapping of k_sytrd_panel");
 
@@ -433,6 +434,10 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a, c
     double (*sh_r1)[kSyRows] = sh_r12[0];
     double (*sh_r2)[kSyRows] = sh_r12[1];
     __shared__ unsigned long long sy_full[kSyGroups];
+    // tables of the tile grid of the product in flight, for the gather of its sums in the next column update: tiles before
+    // every row chunk; first owner CTA and number of owner CTAs of three row chunks (the two this CTA's rows of the next
+    // update lie in, and the one of row j + 1)
+    __shared__ int sy_pre[kSyMaxChunks], sy_plo[3], sy_nseg[3];
     const int n = a.n, G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const int rl = tid & (kSyRows - 1), ks = tid / kSyRows;
@@ -479,8 +484,23 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a, c
             const bool rv = r < n;
             double vk[kSyKmax], wk[kSyKmax], vr = 0.0, yr = 0.0, ar = 0.0, yg = 0.0, yjg = 0.0;
             if (sym && fin) {   // y = A v of column j-1 from the tile sums: this thread's slice of the terms of row r (and of row j)
-                if (rv) yg = sym_gather(gy, G, r, ks, kSySlices, a.rowbuf, a.colbuf);
-                if (pass == 0 && warp == 0 && lane < kSySlices) yjg = sym_gather(gy, G, j, lane, kSySlices, a.rowbuf, a.colbuf);
+                auto gather = [&](int row, int e, int slice) {   // e: which of the three tabulated row chunks
+                    const int R = row / kSyRH, S = row / kSyCW, plo = sy_plo[e], nseg = sy_nseg[e], nit = nseg + gy.nR - R;
+                    const double* rowp = a.rowbuf + (size_t)(R - gy.Rmin + plo) * kSyRH + (row - R * kSyRH);
+                    const double* colp = a.colbuf + (size_t)(S - gy.Smin) * kSyCW + (row - S * kSyCW);
+                    double x[kSyGatherTerms], sum = 0.0;
+#pragma unroll
+                    for (int u = 0; u < kSyGatherTerms; ++u) {
+                        const int t = slice + u * kSySlices;
+                        x[u] = t < nseg ? __ldcg(rowp + (size_t)t * kSyRH)
+                                        : (t < nit ? __ldcg(colp + (size_t)sy_pre[R + (t - nseg) - gy.Rmin] * kSyCW) : 0.0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kSyGatherTerms; ++u) sum += x[u];
+                    return sum;
+                };
+                if (rv) yg = gather(r, r / kSyRH - (j + cta * kSyRows) / kSyRH, ks);
+                if (warp == 0 && lane < kSySlices) yjg = gather(j, 2, lane);
             }
             if (fin) {
 #pragma unroll
@@ -493,6 +513,7 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a, c
                 if (ks == 0 && rv) { vr = __ldcg(V + r + ld * ip); if (!sym) yr = __ldcg(a.y + r); }
             }
             if (ks == 0 && rv && upd) ar = __ldcg(A + r + ld * j);
+            SY_T(8);
             double alpha2 = 0.0;
             if (fin) {
                 if (pass == 0) {
@@ -509,6 +530,7 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a, c
                         sh_vrow[k] = __ldcg(V + j + ld * k); sh_wrow[k] = __ldcg(W + j + ld * k);
                     }
                     __syncthreads();
+                    SY_T(9);
                     if (warp == 0) {
                         double vw = 0.0, s = 0.0;
                         for (int k = lane; k < ip; k += 32) { vw += sh_vtv[k] * sh_wtv[k]; s += sh_vrow[k] * sh_wtv[k] + sh_wrow[k] * sh_vtv[k]; }
@@ -568,6 +590,14 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a, c
         const SymGrid sg = sym ? sym_grid(j + 1, n) : SymGrid();
         int tcur = 0, tend = 0, cR = 0, cS = 0;   // tiles [tcur, tend) of this CTA, the first one is (cR, cS)
         if (sym) {
+            if (tid < sg.nR - sg.Rmin) sy_pre[tid] = sym_pre(sg, sg.Rmin + tid);
+            if (tid >= 96 && tid < 99) {
+                const int e = tid - 96, R = e == 2 ? sg.Rmin : (j + 1 + cta * kSyRows) / kSyRH + e;
+                if (R < sg.nR) {
+                    const int tb = sym_pre(sg, R), plo = sym_owner(sg, tb, G);
+                    sy_plo[e] = plo; sy_nseg[e] = sym_owner(sg, tb + sym_cnt(sg, R) - 1, G) - plo + 1;
+                }
+            }
             tcur = sym_start(sg, cta, G); tend = sym_start(sg, cta + 1, G);
             if (tcur < tend) sym_locate(sg, tcur, cR, cS);
             if ((tid & (kSyGT - 1)) == 0 && tcur + grp < tend) {
@@ -614,24 +644,31 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a, c
         // jobs of this CTA: its share of the trailing columns, plus V / W (/ previous panel V) columns dealt round-robin
         const int cb = j + 1 + (int)(((long long)m * cta) / G), ce = j + 1 + (int)(((long long)m * (cta + 1)) / G);
         const int ncA = sym ? 0 : ce - cb;
-        int nex = 0, nex2 = 0;
-        for (int k = cta; k < i; k += G) ++nex;
-        if (a.Vprev && !sym) for (int k = cta; k < EB; k += G) ++nex2;   // symmetric form: Gram matrices by one GEMM afterwards
-        const int nloc = ncA + 2 * nex + nex2;
+        // two-triangle form: V and W column k = cta, cta + G, ... as a pair; symmetric form (no trailing columns here, the CTAs
+        // are otherwise idle): the 2 i columns singly, f = cta, cta + G, ... (f even: V column f / 2, odd: W), up to 32 warps each
+        int nex = 0, nex2 = 0, nvw = 0;
+        if (sym) { for (int f = cta; f < 2 * i; f += G) ++nvw; }
+        else {
+            for (int k = cta; k < i; k += G) ++nex;
+            nvw = 2 * nex;
+            if (a.Vprev) for (int k = cta; k < EB; k += G) ++nex2;       // symmetric form: Gram matrices by one GEMM afterwards
+        }
+        const int nloc = ncA + nvw + nex2;
         int Q = 1;
         if (nloc > 0) {
             Q = (4 * nwarp + nloc - 1) / nloc;
-            Q = max(1, min(8, min(Q, m / 128)));
+            Q = max(1, min(sym ? 32 : 8, min(Q, m / 128)));
+            if (sym) Q = min(Q, max(1, nwarp / nloc));
         }
         const int njobs = nloc * Q;
         for (int job = warp; job < njobs; job += nwarp) {
             const int lc = job / Q, q = job - lc * Q;
             const double* col;
             if (lc < ncA) col = A + (j + 1) + ld * (cb + lc);
-            else if (lc < ncA + 2 * nex) {
-                const int x = lc - ncA, k = cta + (x >> 1) * G;
-                col = ((x & 1) ? W : V) + (j + 1) + ld * k;
-            } else col = a.Vprev + (j + 1) + ld * (cta + (lc - ncA - 2 * nex) * G);
+            else if (lc < ncA + nvw) {
+                const int x = lc - ncA, f = sym ? cta + x * G : 0, k = sym ? f >> 1 : cta + (x >> 1) * G;
+                col = (((sym ? f : x) & 1) ? W : V) + (j + 1) + ld * k;
+            } else col = a.Vprev + (j + 1) + ld * (cta + (lc - ncA - nvw) * G);
             const int tb = (int)(((long long)m * q) / Q), te = (int)(((long long)m * (q + 1)) / Q);
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int t = tb + lane;
@@ -661,17 +698,17 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a, c
                 const int c = cb + lc;
                 a.y[c] = s;
                 vyl += sv[c - (j + 1)] * s;
-            } else if (lc < ncA + 2 * nex) {
-                const int x = lc - ncA, k = cta + (x >> 1) * G;
-                if (x & 1) a.wtv[k] = s;
+            } else if (lc < ncA + nvw) {
+                const int x = lc - ncA, f = sym ? cta + x * G : 0, k = sym ? f >> 1 : cta + (x >> 1) * G;
+                if ((sym ? f : x) & 1) a.wtv[k] = s;
                 else { a.vtv[k] = s; if (!sym) a.G[(a.gq + k) + NB * (a.gq + i)] = s; }
-            } else a.G[(cta + (lc - ncA - 2 * nex) * G) + NB * (a.gq + i)] = s;
+            } else a.G[(cta + (lc - ncA - nvw) * G) + NB * (a.gq + i)] = s;
         }
         taup = tau;
         SY_T(6);
         if (sym) {
             // ---- lower-triangle tiles: y[r] += T[r, c] v[c] (row sums) and y[c] += T[r, c] v[r] (column sums); diagonal tiles
-            // count A[r, r] once and nothing above it.  Inside a group: lane = 4 consecutive rows, warp = 4 consecutive columns
+            // count A[r, r] once and nothing above it.  Inside a group: lane = 2 + 2 rows (half a tile apart), warp = 4 consecutive columns
             // of the tile; every element is read once.  The row sums stay in registers over the tiles of a row chunk and are
             // added up over the CTA when the chunk ends; the column sums of a tile are complete inside the warp.
             double rowacc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -681,9 +718,9 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a, c
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     if ((warp >> 4) == h) {
-                        double* q = scr + (warp & 15) * kSyRH + 4 * lane;
+                        double* q = scr + (warp & 15) * kSyRH + 2 * lane;
                         *reinterpret_cast<double2*>(q) = make_double2(rowacc[0], rowacc[1]);
-                        *reinterpret_cast<double2*>(q + 2) = make_double2(rowacc[2], rowacc[3]);
+                        *reinterpret_cast<double2*>(q + kSyRH / 2) = make_double2(rowacc[2], rowacc[3]);
                     }
                     __syncthreads();
                     if (tid < kSyRH) {
@@ -705,25 +742,26 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_panel(SytrdArgs a, c
                     mbar_wait(sy_full + grp, guse & 1);
                     ++guse;
                     const double* T = ring + (size_t)grp * kSyTile;
-                    const int r0 = kR * kSyRH + 4 * lane, c0 = kS * kSyCW + 4 * gw;   // first row / column of this thread
+                    // rows r0, r0 + 1, r0 + 64, r0 + 65 (16-byte loads of consecutive lanes are contiguous: no bank conflicts)
+                    const int r0 = kR * kSyRH + 2 * lane, c0 = kS * kSyCW + 4 * gw;   // first row / column of this thread
                     const bool diag = (kS >> 2) == kR;
                     double vr[4], vc[4], colp[4];
                     {
-                        const double2 p0 = *reinterpret_cast<const double2*>(svabs + r0), p1 = *reinterpret_cast<const double2*>(svabs + r0 + 2);
+                        const double2 p0 = *reinterpret_cast<const double2*>(svabs + r0), p1 = *reinterpret_cast<const double2*>(svabs + r0 + kSyRH / 2);
                         const double2 q0 = *reinterpret_cast<const double2*>(svabs + c0), q1 = *reinterpret_cast<const double2*>(svabs + c0 + 2);
                         vr[0] = p0.x; vr[1] = p0.y; vr[2] = p1.x; vr[3] = p1.y;
                         vc[0] = q0.x; vc[1] = q0.y; vc[2] = q1.x; vc[3] = q1.y;
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const double* q = T + (4 * gw + u) * kSyRH + 4 * lane;
-                        const double2 xa = *reinterpret_cast<const double2*>(q), xb = *reinterpret_cast<const double2*>(q + 2);
+                        const double* q = T + (4 * gw + u) * kSyRH + 2 * lane;
+                        const double2 xa = *reinterpret_cast<const double2*>(q), xb = *reinterpret_cast<const double2*>(q + kSyRH / 2);
                         double x[4] = {xa.x, xa.y, xb.x, xb.y};
                         if (diag) {
                             double cp = 0.0;
 #pragma unroll
                             for (int h = 0; h < 4; ++h) {
-                                const int d = (r0 + h) - (c0 + u);
+                                const int d = (r0 + (h & 1) + (h >> 1) * (kSyRH / 2)) - (c0 + u);
                                 rowacc[h] += (d >= 0 ? x[h] : 0.0) * vc[u];
                                 cp += (d > 0 ? x[h] : 0.0) * vr[h];
                             }
@@ -1785,6 +1823,11 @@ struct EighWork {
             const size_t off = sytrd_sym_ring_offset(n, grid) * sizeof(double);
             if (panel_smem_cap > off) sym_nst = (int)std::min<size_t>(kSyStagesMax, (panel_smem_cap - off) / (kSyTile * sizeof(double)));
             if (sym_nst < kSyGroups || !make_tile_map(&tmap, A, n)) sym_nst = 0;   // one ring stage per group of warps
+            // single-pass column update, every CTA owns tiles, and a slice of threads holds its share of the terms of a row
+            const int jjmax = n - resident_max + EB;
+            if (n - 1 > grid * kSyRows || (n + kSyRH - 1) / kSyRH > kSyMaxChunks || sym_grid(std::min(jjmax, n - 1), n).T < grid ||
+                sym_gather_max_terms(n, grid, jjmax) > kSySlices * kSyGatherTerms)
+                sym_nst = 0;
         }
         const size_t panel_smem = sym_nst ? sytrd_sym_ring_offset(n, grid) * sizeof(double) + (size_t)sym_nst * kSyTile * sizeof(double)
                                           : sytrd_smem(n, grid);
@@ -1943,8 +1986,8 @@ struct EighWork {
             long long h[16];
             cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
             static const char* nm[16] = {"A:gather+scalars", "A:rows", "A:reduce", "barrier1", "B:reflector+v", "B:column dots", "B:collect",
-                                         "barrier2", "T:wait full", "T:column sums", "T:row sums", "T:issue", "T:flush", "-", "-", "-"};
-            for (int k = 0; k < 13; ++k) std::fprintf(stderr, "sytrd phase %-14s %10.3f us per column (n=%d)\n", nm[k], h[k] / 1.965e3 / n, n);
+                                         "barrier2", "A:loads issued", "A:scalars loaded", "-", "-", "-", "-", "-", "-"};
+            for (int k = 0; k < 10; ++k) std::fprintf(stderr, "sytrd phase %-14s %10.3f us per column (n=%d)\n", nm[k], h[k] / 1.965e3 / n, n);
             cudaMemset(prof, 0, sizeof(h));
         }
         launches = nl;

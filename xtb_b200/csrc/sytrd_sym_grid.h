@@ -46,11 +46,13 @@ XTBB200_HD void sym_locate(const SymGrid& g, int t, int& R, int& S) {
     }
     R = lo; S = g.Smin + (t - sym_pre(g, lo));
 }
-// y[r] of the product whose tile grid is g: the row sums of the CTA segments of r's row chunk, then the column sums of
-// the tiles of r's strip, every nsl-th term starting at term ks (fixed order: the caller adds the slices in order).
-// Four terms per round so that their loads are in flight together.
-XTBB200_HD double sym_gather(const SymGrid& g, int G, int r, int ks, int nsl, const double* __restrict__ rowbuf,
-                             const double* __restrict__ colbuf) {
+// y[r] of the product whose tile grid is g = the row sums of the CTA segments of r's row chunk, then the column sums of
+// the tiles of r's strip.  Slice ks of nsl takes the terms ks, ks + nsl, ...: their addresses go to q[0 .. kSyGatherTerms)
+// (null: no such term), so that the kernel can work them out before the grid barrier and only has to load afterwards; the
+// caller adds the slices in order (fixed order of summation).  Returns false when a slice has more terms than q holds.
+constexpr int kSyGatherTerms = 6;
+XTBB200_HD bool sym_gather_ptrs(const SymGrid& g, int G, int r, int ks, int nsl, const double* rowbuf, const double* colbuf,
+                                const double* (&q)[kSyGatherTerms]) {
     const int R = r / kSyRH, S = r / kSyCW;
     const int tb = sym_pre(g, R);
     const int plo = sym_owner(g, tb, G), phi = sym_owner(g, tb + sym_cnt(g, R) - 1, G);
@@ -58,24 +60,42 @@ XTBB200_HD double sym_gather(const SymGrid& g, int G, int r, int ks, int nsl, co
     const bool sparse = g.T < G;   // fewer tiles than CTAs: CTAs between two owners may have no tile at all
     const double* rowp = rowbuf + (size_t)(R - g.Rmin + plo) * kSyRH + (r - R * kSyRH);
     const double* colp = colbuf + (size_t)(S - g.Smin) * kSyCW + (r - S * kSyCW);
-    double s = 0.0;
-    for (int i0 = ks; i0 < nit; i0 += 4 * nsl) {
-        const double* q[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * nsl;
-            q[u] = nullptr;
-            if (i < nseg) {
-                if (!sparse || sym_start(g, plo + i, G) < sym_start(g, plo + i + 1, G)) q[u] = rowp + (size_t)i * kSyRH;
-            } else if (i < nit) q[u] = colp + (size_t)sym_pre(g, R + (i - nseg)) * kSyCW;
-        }
-        double x[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = q[u] ? XTBB200_LDCG(q[u]) : 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) s += x[u];
+    for (int u = 0; u < kSyGatherTerms; ++u) {
+        const int i = ks + u * nsl;
+        q[u] = nullptr;
+        if (i < nseg) {
+            if (!sparse || sym_start(g, plo + i, G) < sym_start(g, plo + i + 1, G)) q[u] = rowp + (size_t)i * kSyRH;
+        } else if (i < nit) q[u] = colp + (size_t)sym_pre(g, R + (i - nseg)) * kSyCW;
     }
+    return nit <= kSyGatherTerms * nsl;
+}
+XTBB200_HD double sym_gather_sum(const double* const (&q)[kSyGatherTerms]) {
+    double x[kSyGatherTerms], s = 0.0;
+#pragma unroll
+    for (int u = 0; u < kSyGatherTerms; ++u) x[u] = q[u] ? XTBB200_LDCG(q[u]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < kSyGatherTerms; ++u) s += x[u];
     return s;
+}
+XTBB200_HD double sym_gather(const SymGrid& g, int G, int r, int ks, int nsl, const double* rowbuf, const double* colbuf) {
+    const double* q[kSyGatherTerms];
+    sym_gather_ptrs(g, G, r, ks, nsl, rowbuf, colbuf, q);
+    return sym_gather_sum(q);
+}
+// largest number of terms of any row for order n on G CTAs while the first trailing index is at most jjmax (host: the
+// symmetric form is used only when every slice of kSySlices threads can hold its share)
+inline int sym_gather_max_terms(int n, int G, int jjmax) {
+    int worst = 0;
+    for (int jj = 1; jj < n && jj <= jjmax; ++jj) {
+        const SymGrid g = sym_grid(jj, n);
+        for (int R = g.Rmin; R < g.nR; ++R) {
+            const int tb = sym_pre(g, R);
+            const int nseg = sym_owner(g, tb + sym_cnt(g, R) - 1, G) - sym_owner(g, tb, G) + 1;
+            if (nseg + g.nR - R > worst) worst = nseg + g.nR - R;
+        }
+    }
+    return worst;
 }
 
 }  // namespace xtbb200
