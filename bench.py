@@ -608,7 +608,9 @@ def run_water(ctx, args, steps=None, warmup=None):
 
 def eig_roofline(prof, topk, n, ndiag, steps, step_ms, stage_ms, peak, hbm):
     """Roofline of the dominant kernel class of a large single system."""
-    gemm_flops = {"eig:trailing update(k_eg_gemm)": 4.0 * n ** 3 / 3.0, "eig:back-transformation": 2.0 * n ** 3,
+    # trailing update: the lower triangle of the symmetric rank-2k update (what the symmetric panel kernel needs; the
+    # two-triangle form used for odd orders executes twice that)
+    gemm_flops = {"eig:trailing update(k_eg_gemm)": 2.0 * n ** 3 / 3.0, "eig:back-transformation": 2.0 * n ** 3,
                   "eig:band reduction(DMMA)": 4.0 * n ** 3 / 3.0}
     common = {"eigensolver_ms_per_diagonalisation": stage_ms,
               "dmma_tflops": {kk: gemm_flops[kk] / (stage_ms[kk] * 1e-3) / 1e12 for kk in gemm_flops if stage_ms.get(kk)},

@@ -49,12 +49,13 @@ struct GemmTask {
     int ksegA, offA2, ksegB, offB2;
     int ksplit;           // > 1: blockIdx.z selects a K chunk, partial products go to C + blockIdx.z * csplit
     long long csplit;
+    int lower;            // != 0: only the tiles on and below the diagonal of a square C are computed
 };
 inline GemmTask gemm_task(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
                           double alpha, double beta) {
     GemmTask t;
     t.A = A; t.B = B; t.C = C; t.lda = lda; t.ldb = ldb; t.ldc = ldc; t.M = M; t.N = N; t.K = K; t.alpha = alpha; t.beta = beta;
-    t.ksegA = 0; t.offA2 = 0; t.ksegB = 0; t.offB2 = 0; t.ksplit = 1; t.csplit = 0;
+    t.ksegA = 0; t.offA2 = 0; t.ksegB = 0; t.offB2 = 0; t.ksplit = 1; t.csplit = 0; t.lower = 0;
     return t;
 }
 
@@ -62,7 +63,7 @@ __device__ __forceinline__ GemmTask gemm_task_dev(const double* A, int lda, cons
                                                   int N, int K) {
     GemmTask t;
     t.A = A; t.B = B; t.C = C; t.lda = lda; t.ldb = ldb; t.ldc = ldc; t.M = M; t.N = N; t.K = K; t.alpha = 1.0; t.beta = 0.0;
-    t.ksegA = 0; t.offA2 = 0; t.ksegB = 0; t.offB2 = 0; t.ksplit = 1; t.csplit = 0;
+    t.ksegA = 0; t.offA2 = 0; t.ksegB = 0; t.offB2 = 0; t.ksplit = 1; t.csplit = 0; t.lower = 0;
     return t;
 }
 
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(128, 3) k_eg_gemm(GemmTask t0, const GemmTask*
     const int tm = (t.M + GT - 1) / GT, tn = (t.N + GT - 1) / GT;
     if ((int)blockIdx.x >= tm * tn) return;
     const int r0 = (blockIdx.x % tm) * GT, c0 = (blockIdx.x / tm) * GT;
+    if (t.lower && c0 > r0) return;
     int kb = 0, ke = t.K;
     double* __restrict__ C = t.C + r0 + (long long)t.ldc * c0;
     if (t.ksplit > 1) {
@@ -256,6 +258,7 @@ __global__ void __launch_bounds__(160) k_eg_gemm_tma(GemmTask t) {
     const int tm = (t.M + GT - 1) / GT, tn = (t.N + GT - 1) / GT;
     if ((int)blockIdx.x >= tm * tn) return;
     const int r0 = (blockIdx.x % tm) * GT, c0 = (blockIdx.x / tm) * GT;
+    if (t.lower && c0 > r0) return;
     int kb = 0, ke = t.K;
     double* __restrict__ C = t.C + r0 + (long long)t.ldc * c0;
     if (t.ksplit > 1) {
@@ -830,6 +833,7 @@ struct SytrdSmemArgs {
     int clu;
     long long ms, vs;
     const int* skip;
+    int lower_only;     // != 0: only the lower triangle of A[j0:, j0:] is valid on entry
 };
 // barrier over the CTAs of a thread-block cluster (hardware barrier; release / acquire at cluster scope also orders the
 // global-memory exchange buffers, which are read back with ld.cg)
@@ -867,8 +871,12 @@ __global__ void __launch_bounds__(kSytrdThreads, 1) k_sytrd_smem(SytrdSmemArgs a
     double* sw = sv + m0;
     double* part = sw + m0;                                    // 128 doubles
     for (int s = 0; s < nslot; ++s) {
-        const double* src = a.A + j0 + ld * (j0 + cta + s * G);
-        for (int r = tid; r < m0; r += nthr) cols[(size_t)s * m0 + r] = src[r];
+        const int c = cta + s * G;
+        const double* src = a.A + j0 + ld * (j0 + c);
+        if (a.lower_only)   // the panel kernel's updates kept only the lower triangle current: rows above the diagonal from the row
+            for (int r = tid; r < m0; r += nthr) cols[(size_t)s * m0 + r] = r >= c ? src[r] : a.A[(j0 + c) + ld * (j0 + r)];
+        else
+            for (int r = tid; r < m0; r += nthr) cols[(size_t)s * m0 + r] = src[r];
     }
     __syncthreads();
     unsigned target = 0;
@@ -1854,6 +1862,7 @@ struct EighWork {
                 GemmTask t = gemm_task(V + j1, n, Wp + j1, n, A + j1 + ld * j1, n, mt, mt, 2 * EB, -1.0, 1.0);
                 t.ksegA = EB; t.offA2 = NB - EB * q;          // K index of W's first column relative to V
                 t.ksegB = EB; t.offB2 = -(NB - EB * q);       // K index of V's first column relative to W
+                t.lower = sym_nst ? 1 : 0;                     // symmetric panel kernel: nobody reads the upper triangle any more
                 hook(1, 0, 0);
                 gemm(st, false, true, t);
                 hook(1, 1, 1);
@@ -1864,7 +1873,8 @@ struct EighWork {
             XTB_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
             SytrdSmemArgs ra;
             ra.A = A; ra.n = n; ra.j0 = jres; ra.d = dd; ra.e = ee; ra.tau = tau; ra.cbuf = cbuf; ra.ybuf = ybuf;
-            ra.Gf = Gf; ra.bar = bar;
+            ra.Gf = Gf; ra.bar = bar; ra.clu = 0; ra.ms = 0; ra.vs = 0; ra.skip = nullptr;
+            ra.lower_only = (sym_nst && jres > 0) ? 1 : 0;
             void* args[] = {&ra};
             hook(0, 0, 0);
             // Grid of the resident kernel: the grid barrier per column costs more the more CTAs take part, and a mid-size
