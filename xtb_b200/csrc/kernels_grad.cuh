@@ -482,7 +482,7 @@ __global__ void k_grad_pcem_charges(Dev d) {
 }
 
 // Axilrod-Teller-Muto three-body term with neutral reference weights (atm_gradient_latp,
-// deriv_atm_triple): one CTA per atom a, threads over partner pairs (b strided over the CTA, c < b); each triple is
+// deriv_atm_triple): one CTA per atom a, threads over the partner pairs (b, c < b), flattened; each triple is
 // visited from its three atoms, every CTA accumulates only its own gradient / dE/dCN and reduces in a fixed order
 // (no atomics).  dynamic shared memory: nat doubles (row a of dC6/dCN, strided in HBM).
 __global__ void __launch_bounds__(128) k_grad_atm(Dev d) {
@@ -501,50 +501,66 @@ __global__ void __launch_bounds__(128) k_grad_atm(Dev d) {
     __syncthreads();
     const double* c6a = c60 + (long long)n * a;     // C6(a, .) ; the matrix is symmetric
     double g[3] = {0, 0, 0}, dcn = 0, e3 = 0;
-    for (int b = threadIdx.x; b < n; b += blockDim.x) {
-        if (b == a) continue;
-        const double rij[3] = {xyz[3 * b] - ra[0], xyz[3 * b + 1] - ra[1], xyz[3 * b + 2] - ra[2]};
-        const double r2ij = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
-        if (r2ij > 1600.0) continue;
-        const double r4b = d.atoms[m.at0 + b].r4r2;
-        const double c6ij = c6a[b];
-        const double cij = 0.52 * sqrt(3.0 * r4a * r4b) + 5.0;
-        const double dc6ij = s_dc6a[b];
-        const double* c6b = c60 + (long long)n * b;
-        for (int c = 0; c < b; ++c) {
-            if (c == a) continue;
+    // partner pairs (b, c), c < b, numbered b (b - 1) / 2 + c and dealt to the threads round-robin: every thread gets the same
+    // number of pairs whatever the size of the molecule (a loop over b per thread leaves 2/3 of the CTA idle for 47 atoms)
+    const long long npair = (long long)n * (n - 1) / 2;
+    int b = 0, c = 0;
+    {
+        const long long p0 = threadIdx.x;
+        b = (int)(0.5 * (1.0 + sqrt(1.0 + 8.0 * (double)p0)));
+        while ((long long)b * (b - 1) / 2 > p0) --b;
+        while ((long long)(b + 1) * b / 2 <= p0) ++b;
+        c = (int)(p0 - (long long)b * (b - 1) / 2);
+    }
+    int bc = -1;                                   // atom whose pair quantities with a are in the registers below
+    double rij[3] = {0, 0, 0}, r2ij = 0, r4b = 0, c6ij = 0, cij = 0, dc6ij = 0;
+    const double* c6b = c60;
+    for (long long p = threadIdx.x; p < npair; p += blockDim.x) {
+        if (b != a && c != a) {
+            if (b != bc) {
+                bc = b;
+                rij[0] = xyz[3 * b] - ra[0]; rij[1] = xyz[3 * b + 1] - ra[1]; rij[2] = xyz[3 * b + 2] - ra[2];
+                r2ij = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
+                r4b = d.atoms[m.at0 + b].r4r2;
+                c6ij = c6a[b];
+                cij = 0.52 * sqrt(3.0 * r4a * r4b) + 5.0;
+                dc6ij = s_dc6a[b];
+                c6b = c60 + (long long)n * b;
+            }
             const double rik[3] = {xyz[3 * c] - ra[0], xyz[3 * c + 1] - ra[1], xyz[3 * c + 2] - ra[2]};
             const double r2ik = rik[0] * rik[0] + rik[1] * rik[1] + rik[2] * rik[2];
-            if (r2ik > 1600.0) continue;
             const double rjk[3] = {rik[0] - rij[0], rik[1] - rij[1], rik[2] - rij[2]};
             const double r2jk = rjk[0] * rjk[0] + rjk[1] * rjk[1] + rjk[2] * rjk[2];
-            if (r2jk > 1600.0) continue;
-            cnt_add(d, blockIdx.y, 9, 1);
-            const double r4c = d.atoms[m.at0 + c].r4r2;
-            const double c6ik = c6a[c], c6jk = c6b[c];
-            const double cik = 0.52 * sqrt(3.0 * r4a * r4c) + 5.0, cjk = 0.52 * sqrt(3.0 * r4b * r4c) + 5.0;
-            const double c9 = -sqrt(c6ij * c6ik * c6jk);
-            const double ccc1 = cij * cjk * cik;
-            const double rrr2 = r2ij * r2jk * r2ik, rrr1 = sqrt(rrr2), rrr3 = rrr1 * rrr2;
-            const double ang_fact = 0.375 / (rrr2 * rrr3);
-            const double ang = ang_fact * (r2ij + r2jk - r2ik) * (r2ij - r2jk + r2ik) * (-r2ij + r2jk + r2ik) + 1.0 / rrr3;
-            const double cralp = pow(ccc1 / rrr1, 16.0 / 3.0);
-            const double fdmp = 1.0 / (1.0 + 6.0 * cralp);
-            const double dfdmp = -(2.0 * 16 * cralp) * fdmp * fdmp;
-            const double dE = -fdmp * ang * c9;
-            const double dang1 = -ang_fact * (r2ij * r2ij * r2ij + r2ij * r2ij * (r2jk + r2ik) +
-                                              r2ij * (3.0 * r2jk * r2jk + 2.0 * r2jk * r2ik + 3.0 * r2ik * r2ik) -
-                                              5.0 * (r2jk - r2ik) * (r2jk - r2ik) * (r2jk + r2ik));
-            const double dGr1 = (-dang1 * c9 * fdmp + dfdmp * c9 * ang) / r2ij;
-            const double dang2 = -ang_fact * (r2ik * r2ik * r2ik + r2ik * r2ik * (r2jk + r2ij) +
-                                              r2ik * (3.0 * r2jk * r2jk + 2.0 * r2jk * r2ij + 3.0 * r2ij * r2ij) -
-                                              5.0 * (r2jk - r2ij) * (r2jk - r2ij) * (r2jk + r2ij));
-            const double dGr2 = (-dang2 * c9 * fdmp + dfdmp * c9 * ang) / r2ik;
-            const double scale = 5.0;   // s9
-            for (int k = 0; k < 3; ++k) g[k] += (-dGr1 * rij[k] - dGr2 * rik[k]) * scale;
-            e3 += dE * scale / 3.0;
-            dcn += -ang * fdmp * (0.5 * c9 * (dc6ij / c6ij + s_dc6a[c] / c6ik)) * scale;
+            if (r2ij <= 1600.0 && r2ik <= 1600.0 && r2jk <= 1600.0) {
+                cnt_add(d, blockIdx.y, 9, 1);
+                const double r4c = d.atoms[m.at0 + c].r4r2;
+                const double c6ik = c6a[c], c6jk = c6b[c];
+                const double cik = 0.52 * sqrt(3.0 * r4a * r4c) + 5.0, cjk = 0.52 * sqrt(3.0 * r4b * r4c) + 5.0;
+                const double c9 = -sqrt(c6ij * c6ik * c6jk);
+                const double ccc1 = cij * cjk * cik;
+                const double rrr2 = r2ij * r2jk * r2ik, rrr1 = sqrt(rrr2), rrr3 = rrr1 * rrr2;
+                const double ang_fact = 0.375 / (rrr2 * rrr3);
+                const double ang = ang_fact * (r2ij + r2jk - r2ik) * (r2ij - r2jk + r2ik) * (-r2ij + r2jk + r2ik) + 1.0 / rrr3;
+                const double cralp = pow(ccc1 / rrr1, 16.0 / 3.0);
+                const double fdmp = 1.0 / (1.0 + 6.0 * cralp);
+                const double dfdmp = -(2.0 * 16 * cralp) * fdmp * fdmp;
+                const double dE = -fdmp * ang * c9;
+                const double dang1 = -ang_fact * (r2ij * r2ij * r2ij + r2ij * r2ij * (r2jk + r2ik) +
+                                                  r2ij * (3.0 * r2jk * r2jk + 2.0 * r2jk * r2ik + 3.0 * r2ik * r2ik) -
+                                                  5.0 * (r2jk - r2ik) * (r2jk - r2ik) * (r2jk + r2ik));
+                const double dGr1 = (-dang1 * c9 * fdmp + dfdmp * c9 * ang) / r2ij;
+                const double dang2 = -ang_fact * (r2ik * r2ik * r2ik + r2ik * r2ik * (r2jk + r2ij) +
+                                                  r2ik * (3.0 * r2jk * r2jk + 2.0 * r2jk * r2ij + 3.0 * r2ij * r2ij) -
+                                                  5.0 * (r2jk - r2ij) * (r2jk - r2ij) * (r2jk + r2ij));
+                const double dGr2 = (-dang2 * c9 * fdmp + dfdmp * c9 * ang) / r2ik;
+                const double scale = 5.0;   // s9
+                for (int k = 0; k < 3; ++k) g[k] += (-dGr1 * rij[k] - dGr2 * rik[k]) * scale;
+                e3 += dE * scale / 3.0;
+                dcn += -ang * fdmp * (0.5 * c9 * (dc6ij / c6ij + s_dc6a[c] / c6ik)) * scale;
+            }
         }
+        c += blockDim.x;
+        while (c >= b) { c -= b; ++b; }
     }
     for (int k = 0; k < 3; ++k) g[k] = block_sum(g[k], red);
     dcn = block_sum(dcn, red);
