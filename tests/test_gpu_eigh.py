@@ -64,6 +64,18 @@ def test_panel_kernel_hands_over_to_the_resident_kernel():
     _check((a + a.T) / 2)
 
 
+@pytest.mark.parametrize("n", [1926, 2101, 2432, 3006])
+def test_both_forms_of_the_panel_kernel(n):
+    """Even orders take the symmetric trailing-matrix product (lower triangle through the tensor-map TMA ring, tile sums
+    gathered in the next column update), odd orders the two-triangle form (a tile line must start 16-byte aligned);
+    1926: a single panel before the resident kernel; 2432 = 19 * 128: whole row chunks; 3006: ragged last chunk and strip."""
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n))
+    if n == 2432:   # bands of nearly degenerate levels on top of the random matrix
+        a = a * 1e-3 + np.kron(np.eye(n // 8), rng.standard_normal((8, 8)))
+    _check((a + a.T) / 2)
+
+
 def test_order_beyond_the_shared_memory_deflation_scan():
     """n = 9700 (deflation scan of the top levels in global memory): matrix with a known spectrum, A = H3 H2 H1 D H1 H2 H3
     with three Householder reflectors, so that no LAPACK call of this size is needed; sampled residuals."""

@@ -56,7 +56,10 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
     const double* A = Ag + m.mat0;
     const double* B = Bg + m.mat0;
     double* C = Cg + m.mat0;
-    __shared__ double As[GK][GTL], Bs[GK][GTL];
+    // operand tiles: [k][row] with pitch GTL when consecutive threads of the staging fetch consecutive rows, [row][k] with pitch
+    // GK + 4 when they fetch consecutive k (TA / !TB): staging stores and m8n8k4 fragment loads are free of bank conflicts in both
+    constexpr int PK = GK + 4;
+    __shared__ double As[TA ? GTT * PK : GK * GTL], Bs[TB ? GK * GTL : GTT * PK];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wr = (warp & 1) * (GTT / 2), wc = (warp >> 1) * (GTT / 2);
     double acc[NI][NI][2];
@@ -90,8 +93,8 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
 #pragma unroll
         for (int u = 0; u < GTT * GK / 128; ++u) {
             const int t = tid + 128 * u;
-            if (!TA) As[t / GTT][t % GTT] = ra[u]; else As[t % GK][t / GK] = ra[u];
-            if (!TB) Bs[t % GK][t / GK] = rb[u]; else Bs[t / GTT][t % GTT] = rb[u];
+            if (!TA) As[(t / GTT) * GTL + t % GTT] = ra[u]; else As[(t / GK) * PK + t % GK] = ra[u];
+            if (!TB) Bs[(t / GK) * PK + t % GK] = rb[u]; else Bs[(t / GTT) * GTL + t % GTT] = rb[u];
         }
     };
     if (K > kbeg) fetch(kbeg);
@@ -103,9 +106,11 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
         for (int ks = 0; ks < GK; ks += 4) {
             double af[NI], bf[NI];
 #pragma unroll
-            for (int i = 0; i < NI; ++i) af[i] = As[ks + (lane & 3)][wr + 8 * i + (lane >> 2)];
+            for (int i = 0; i < NI; ++i)
+                af[i] = TA ? As[(wr + 8 * i + (lane >> 2)) * PK + ks + (lane & 3)] : As[(ks + (lane & 3)) * GTL + wr + 8 * i + (lane >> 2)];
 #pragma unroll
-            for (int j = 0; j < NI; ++j) bf[j] = Bs[ks + (lane & 3)][wc + 8 * j + (lane >> 2)];
+            for (int j = 0; j < NI; ++j)
+                bf[j] = TB ? Bs[(ks + (lane & 3)) * GTL + wc + 8 * j + (lane >> 2)] : Bs[(wc + 8 * j + (lane >> 2)) * PK + ks + (lane & 3)];
 #pragma unroll
             for (int i = 0; i < NI; ++i)
 #pragma unroll
