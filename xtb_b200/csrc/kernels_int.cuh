@@ -88,17 +88,88 @@ __device__ __forceinline__ double h0scal(int li, int lj, double eni, double enj)
     return ks * enpoly * 1.0;
 }
 
+// The same integrals for all exponent pairs (a <= LI, b <= LJ) of one direction at once: out[(a (LJ + 1) + b) 3 + t].  The
+// moment factors of every power of (x - P) are shared; the loops are static (the shell pair, hence LI / LJ, is uniform over
+// the warp), the sums run in the order of moments_1d.
+template <int LI, int LJ>
+__device__ __forceinline__ void moments_table(double pa, double pb, double rpc, const double* s1d, double* out) {
+    double m0[LI + LJ + 1], m1[LI + LJ + 1], m2[LI + LJ + 1];
+#pragma unroll
+    for (int l = 0; l <= LI + LJ; ++l) {
+        m0[l] = s1d[l];
+        m1[l] = s1d[l + 1] + rpc * s1d[l];
+        m2[l] = s1d[l + 2] + 2 * rpc * s1d[l + 1] + rpc * rpc * s1d[l];
+    }
+    double pi[LI + 1][LI + 1], pj[LJ + 1][LJ + 1];   // (x - A)^a and (x - B)^b in powers of (x - P)
+#pragma unroll
+    for (int a = 0; a <= LI; ++a) {
+#pragma unroll
+        for (int k = 0; k <= LI; ++k) pi[a][k] = 0.0;
+        pi[a][a] = 1.0;
+        if (a == 1) pi[a][0] += pa * pi[a][1];
+        else if (a == 2) { pi[a][0] += pa * pa * pi[a][2]; pi[a][1] += 2 * pa * pi[a][2]; }
+    }
+#pragma unroll
+    for (int b = 0; b <= LJ; ++b) {
+#pragma unroll
+        for (int k = 0; k <= LJ; ++k) pj[b][k] = 0.0;
+        pj[b][b] = 1.0;
+        if (b == 1) pj[b][0] += pb * pj[b][1];
+        else if (b == 2) { pj[b][0] += pb * pb * pj[b][2]; pj[b][1] += 2 * pb * pj[b][2]; }
+    }
+#pragma unroll
+    for (int a = 0; a <= LI; ++a)
+#pragma unroll
+        for (int b = 0; b <= LJ; ++b) {
+            double v0 = 0, v1 = 0, v2 = 0;
+#pragma unroll
+            for (int l = 0; l <= a + b; ++l) {
+                double vv = 0.0;
+#pragma unroll
+                for (int k = 0; k <= a; ++k)
+                    if (l - k >= 0 && l - k <= b) vv += pi[a][k] * pj[b][l - k];
+                v0 += m0[l] * vv; v1 += m1[l] * vv; v2 += m2[l] * vv;
+            }
+            double* o = out + 3 * (a * (LJ + 1) + b);
+            o[0] = v0; o[1] = v1; o[2] = v2;
+        }
+}
+__device__ __forceinline__ void moments_table_dyn(int li, int lj, double pa, double pb, double rpc, const double* s1d, double* out) {
+    switch (3 * li + lj) {
+        case 0: moments_table<0, 0>(pa, pb, rpc, s1d, out); break;
+        case 1: moments_table<0, 1>(pa, pb, rpc, s1d, out); break;
+        case 2: moments_table<0, 2>(pa, pb, rpc, s1d, out); break;
+        case 3: moments_table<1, 0>(pa, pb, rpc, s1d, out); break;
+        case 4: moments_table<1, 1>(pa, pb, rpc, s1d, out); break;
+        case 5: moments_table<1, 2>(pa, pb, rpc, s1d, out); break;
+        case 6: moments_table<2, 0>(pa, pb, rpc, s1d, out); break;
+        case 7: moments_table<2, 1>(pa, pb, rpc, s1d, out); break;
+        default: moments_table<2, 2>(pa, pb, rpc, s1d, out); break;
+    }
+}
+
 constexpr int kIntWarps = 4;
+// One-dimensional moment integrals are shared by all Cartesian components of a shell pair: for every primitive pair and
+// direction there are only (li + 1) (lj + 1) different ones, while a p-p pair has 9 components that each need three.  They are
+// tabulated per warp in shared memory ([primitive pair][direction][(a, b)][moment], primitive pairs in chunks that fit), the
+// prefactors exp(-est) (pi / (alpha_i + alpha_j))^(3/2) once per primitive pair; the component lanes then only multiply.
+constexpr int kIntTab = 864;          // doubles per warp
+constexpr int kIntMaxPP = 36;         // primitive pairs of a shell pair (6 x 6)
 
 // S, D, Q, H0, H0_noovlp for all shell pairs (is >= js).  grid = (ceil(npair/kIntWarps), nmol)
-__global__ void __launch_bounds__(kIntWarps * 32, 6) k_sdqh0(Dev d) {
+__global__ void __launch_bounds__(kIntWarps * 32, 5) k_sdqh0(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long npair = (long long)m.nsh * (m.nsh + 1) / 2;
     long long p = shard_pair_cta(d) * kIntWarps + warp;
     __shared__ double s_blk[kIntWarps][10][36];
-    __shared__ double s_part[kIntWarps][10][33];
+    __shared__ double s_tabs[kIntWarps][kIntTab];
+    __shared__ double s_kab[kIntWarps][kIntMaxPP];
     __shared__ double s_alp[kIntWarps][2][6], s_cont[kIntWarps][2][6];
+    __shared__ unsigned char s_ipjp[kIntWarps][kIntMaxPP], s_slot[kIntWarps][kIntMaxPP];   // (ip, jp) of a primitive pair; block slot of a component
+    static_assert(kIntTab >= 10 * 33, "the lane partial sums of the reduction reuse the table");
+    double (*s_part)[33] = reinterpret_cast<double (*)[33]>(&s_tabs[warp][0]);   // [10][33], after the table is dead
+    double* tab = &s_tabs[warp][0];
     if (p >= npair) return;   // whole warp exits together
     p = d.pair_order[d.pord0[blockIdx.y] + p];
     int is = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
@@ -111,6 +182,12 @@ __global__ void __launch_bounds__(kIntWarps * 32, 6) k_sdqh0(Dev d) {
     const int nci = c_ncart[li], ncj = c_ncart[lj], npi = si.nprim, npj = sj.nprim;
     if (lane < 6) { s_alp[warp][0][lane] = si.alp[lane]; s_cont[warp][0][lane] = si.cont[lane]; }
     else if (lane < 12) { s_alp[warp][1][lane - 6] = sj.alp[lane - 6]; s_cont[warp][1][lane - 6] = sj.cont[lane - 6]; }
+    const int ncomp = nci * ncj;
+    for (int q = lane; q < kIntMaxPP; q += 32) {   // the divisions by the run-time npj / ncj once per shell pair, not per term
+        const int ip = q / npj, cc = q / ncj;
+        s_ipjp[warp][q] = (unsigned char)(ip | ((q - ip * npj) << 4));
+        s_slot[warp][q] = (unsigned char)(cc * 6 + (q - cc * ncj));
+    }
     __syncwarp();
     const double* ri = d.xyz + 3 * (m.at0 + iat);
     const double* rj = d.xyz + 3 * (m.at0 + jat);
@@ -118,77 +195,102 @@ __global__ void __launch_bounds__(kIntWarps * 32, 6) k_sdqh0(Dev d) {
     const double rij2 = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
     const double intcut = d.intcut;
     const double sqrtpi = sqrt(kPi);
-    const int ncomp = nci * ncj;
-    if (lane == 0 && rij2 <= 2000.0) cnt_add(d, blockIdx.y, 0, 1);
-    for (int c = lane; c < 36; c += 32)
-        for (int k = 0; k < 10; ++k) s_blk[warp][k][c] = 0.0;
-    __syncwarp();
+    const bool inrange = rij2 <= 2000.0;
+    if (lane == 0 && inrange) cnt_add(d, blockIdx.y, 0, 1);
     // Work decomposition: lpc lanes share one Cartesian component pair and split its primitive pairs, so that s-s,
     // s-p and p-p shell pairs (1, 3, 9 components) still occupy most of the warp.
     const int npp = npi * npj;
     const int lpc = ncomp >= 32 ? 1 : 32 / ncomp;
     const int ngrp = 32 / lpc;
     const int grp = lane / lpc, sub = lane % lpc;
+    const int nbj = lj + 1, nab = (li + 1) * nbj;
+    const int ppstride = 9 * nab + 1;                       // + 1: the lanes of a component group hit different banks
+    const int chunk = min(npp, kIntTab / ppstride);         // primitive pairs per table filling (>= 3 for d-d)
     for (int c0 = 0; c0 < ncomp; c0 += ngrp) {
         const int c = c0 + grp;
         const bool on = (grp < ngrp) && (c < ncomp);
         double acc[10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) acc[k] = 0.0;
-        int mli = 0, mlj = 0;
-        if (on && rij2 <= 2000.0) {
-            mli = c / ncj; mlj = c % ncj;
-            const int lix = c_lx[c_itt[li] + mli], liy = c_ly[c_itt[li] + mli], liz = c_lz[c_itt[li] + mli];
-            const int ljx = c_lx[c_itt[lj] + mlj], ljy = c_ly[c_itt[lj] + mlj], ljz = c_lz[c_itt[lj] + mlj];
-            const double fi = (li == 2) ? c_dcart[mli] : 1.0, fj = (lj == 2) ? c_dcart[mlj] : 1.0;
-            for (int pp = sub; pp < npp; pp += lpc) {
-                const int ip = pp / npj, jp = pp % npj;
-                const double alpi = s_alp[warp][0][ip];
-                const double ci = s_cont[warp][0][ip] * fi;
-                const double alpj = s_alp[warp][1][jp];
+        int ix = 0, iy = 0, iz = 0;
+        double fi = 1.0, fj = 1.0;
+        if (on) {
+            const int mli = c / ncj, mlj = c % ncj;
+            ix = 3 * (c_lx[c_itt[li] + mli] * nbj + c_lx[c_itt[lj] + mlj]);
+            iy = 3 * (nab + c_ly[c_itt[li] + mli] * nbj + c_ly[c_itt[lj] + mlj]);
+            iz = 3 * (2 * nab + c_lz[c_itt[li] + mli] * nbj + c_lz[c_itt[lj] + mlj]);
+            fi = (li == 2) ? c_dcart[mli] : 1.0; fj = (lj == 2) ? c_dcart[mlj] : 1.0;
+        }
+        for (int p0 = 0; inrange && p0 < npp; p0 += chunk) {
+            const int nch = min(chunk, npp - p0);
+            // ---- prefactors, one lane per primitive pair (negative: screened out)
+            for (int q = lane; q < nch; q += 32) {
+                const int ij = s_ipjp[warp][p0 + q], ip = ij & 15, jp = ij >> 4;
+                const double alpi = s_alp[warp][0][ip], alpj = s_alp[warp][1][jp];
                 double est = alpi * alpj * rij2;
-                if (est > intcut * (alpi + alpj)) continue;
-                if (c == 0) cnt_add(d, blockIdx.y, 1, 1);
-                const double ab = 1.0 / (alpi + alpj);
-                est = est * ab;
-                const double sq = sqrtpi * sqrt(ab);
-                const double kab = exp(-est) * (sq * sq * sq);
-                const double cc = kab * (s_cont[warp][1][jp] * fj) * ci;
-                const double gm = 0.5 * ab;
+                double kab = -1.0;
+                if (!(est > intcut * (alpi + alpj))) {
+                    if (c0 == 0) cnt_add(d, blockIdx.y, 1, 1);
+                    const double ab = 1.0 / (alpi + alpj);
+                    est = est * ab;
+                    const double sq = sqrtpi * sqrt(ab);
+                    kab = exp(-est) * (sq * sq * sq);
+                }
+                s_kab[warp][q] = kab;
+            }
+            __syncwarp();
+            // ---- moments <(x - A)^a | (x - C)^{0,1,2} | (x - B)^b>, one lane per (primitive pair, direction)
+            for (int e = lane; e < 3 * nch; e += 32) {
+                const int q = e / 3, dim = e - 3 * q;
+                if (s_kab[warp][q] < 0.0) continue;
+                const int ij = s_ipjp[warp][p0 + q], ip = ij & 15, jp = ij >> 4;
+                const double alpi = s_alp[warp][0][ip], alpj = s_alp[warp][1][jp];
+                const double ab = 1.0 / (alpi + alpj), gm = 0.5 * ab;
                 double t[9];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) t[k] = olapp(k, gm);
-                double vx[3], vy[3], vz[3];
-                {
-                    double rp = (alpi * ri[0] + alpj * rj[0]) * ab;
-                    moments_1d<2>(lix, ljx, rp - ri[0], rp - rj[0], rp, t, vx);
-                    rp = (alpi * ri[1] + alpj * rj[1]) * ab;
-                    moments_1d<2>(liy, ljy, rp - ri[1], rp - rj[1], rp, t, vy);
-                    rp = (alpi * ri[2] + alpj * rj[2]) * ab;
-                    moments_1d<2>(liz, ljz, rp - ri[2], rp - rj[2], rp, t, vz);
-                }
-                acc[0] += vx[0] * vy[0] * vz[0] * cc;
-                acc[1] += vx[1] * vy[0] * vz[0] * cc;
-                acc[2] += vx[0] * vy[1] * vz[0] * cc;
-                acc[3] += vx[0] * vy[0] * vz[1] * cc;
-                acc[4] += vx[2] * vy[0] * vz[0] * cc;
-                acc[5] += vx[0] * vy[2] * vz[0] * cc;
-                acc[6] += vx[0] * vy[0] * vz[2] * cc;
-                acc[7] += vx[1] * vy[1] * vz[0] * cc;
-                acc[8] += vx[1] * vy[0] * vz[1] * cc;
-                acc[9] += vx[0] * vy[1] * vz[1] * cc;
+                const double xi = ri[dim], xj = rj[dim];
+                const double rp = (alpi * xi + alpj * xj) * ab;
+                moments_table_dyn(li, lj, rp - xi, rp - xj, rp, t, tab + q * ppstride + 3 * dim * nab);
             }
+            __syncwarp();
+            // ---- this lane's component: products of three tabulated moments per primitive pair
+            if (on) {
+                for (int pp = p0 + sub; pp < p0 + nch; pp += lpc) {
+                    const int q = pp - p0;
+                    const double kab = s_kab[warp][q];
+                    if (kab < 0.0) continue;
+                    const int ij = s_ipjp[warp][pp], ip = ij & 15, jp = ij >> 4;
+                    const double ci = s_cont[warp][0][ip] * fi;
+                    const double cc = kab * (s_cont[warp][1][jp] * fj) * ci;
+                    const double* vx = tab + q * ppstride + ix;
+                    const double* vy = tab + q * ppstride + iy;
+                    const double* vz = tab + q * ppstride + iz;
+                    const double x0 = vx[0], x1 = vx[1], x2 = vx[2], y0 = vy[0], y1 = vy[1], y2 = vy[2], z0 = vz[0], z1 = vz[1], z2 = vz[2];
+                    acc[0] += x0 * y0 * z0 * cc;
+                    acc[1] += x1 * y0 * z0 * cc;
+                    acc[2] += x0 * y1 * z0 * cc;
+                    acc[3] += x0 * y0 * z1 * cc;
+                    acc[4] += x2 * y0 * z0 * cc;
+                    acc[5] += x0 * y2 * z0 * cc;
+                    acc[6] += x0 * y0 * z2 * cc;
+                    acc[7] += x1 * y1 * z0 * cc;
+                    acc[8] += x1 * y0 * z1 * cc;
+                    acc[9] += x0 * y1 * z1 * cc;
+                }
+            }
+            __syncwarp();
         }
         // fixed-order reduction over the lanes of each component group (deterministic)
 #pragma unroll
-        for (int k = 0; k < 10; ++k) s_part[warp][k][lane] = acc[k];
+        for (int k = 0; k < 10; ++k) s_part[k][lane] = acc[k];
         __syncwarp();
         for (int e = lane; e < ngrp * 10; e += 32) {
             const int g = e / 10, k = e % 10, cc2 = c0 + g;
             if (cc2 < ncomp) {
                 double v = 0.0;
-                for (int u = 0; u < lpc; ++u) v += s_part[warp][k][g * lpc + u];
-                s_blk[warp][k][(cc2 / ncj) * 6 + (cc2 % ncj)] = v;
+                for (int u = 0; u < lpc; ++u) v += s_part[k][g * lpc + u];
+                s_blk[warp][k][s_slot[warp][cc2]] = v;
             }
         }
         __syncwarp();
@@ -202,7 +304,7 @@ __global__ void __launch_bounds__(kIntWarps * 32, 6) k_sdqh0(Dev d) {
         const AtomPar& a = d.atoms[m.at0 + iat];
         const AtomPar& b = d.atoms[m.at0 + jat];
         double hii = d.selfE[m.sh0 + is], hjj = d.selfE[m.sh0 + js];
-        double zetaij = pow(2 * sqrt(si.zeta * sj.zeta) / (si.zeta + sj.zeta), 0.5);
+        double zetaij = sqrt(2 * sqrt(si.zeta * sj.zeta) / (si.zeta + sj.zeta));
         double km = h0scal(li, lj, a.en, b.en);
         hav = 0.5 * km * (hii + hjj) * zetaij;
         double r = sqrt(rij2) / (b.rad + a.rad);
