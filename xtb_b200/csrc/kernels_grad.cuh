@@ -48,6 +48,71 @@ __device__ __forceinline__ void moments_grad_1d(int li, int lj, double ai, doubl
     gra[0] = g0; gra[1] = g1; gra[2] = g2;
 }
 
+// The same for all exponent pairs (a <= LI, b <= LJ) of one direction: out[(a (LJ + 1) + b) 6 + {val 0..2, gra 0..2}], static
+// loops (LI / LJ are uniform over the warp), sums in the order of moments_grad_1d.
+template <int LI, int LJ>
+__device__ __forceinline__ void moments_grad_table(double ai, double pa, double pb, double rpc, const double* s1d, double* out) {
+    constexpr int NK = LI + LJ + 2;   // powers 0 .. LI + LJ + 1 of (x - P)
+    double m0[NK], m1[NK], m2[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        m0[k] = s1d[k];
+        m1[k] = s1d[k + 1] + rpc * s1d[k];
+        m2[k] = s1d[k + 2] + 2 * rpc * s1d[k + 1] + rpc * rpc * s1d[k];
+    }
+    double pj[LJ + 1][3];
+#pragma unroll
+    for (int b = 0; b <= LJ; ++b) {
+        pj[b][0] = pj[b][1] = pj[b][2] = 0.0;
+        pj[b][b] = 1.0;
+        shift_poly(pb, b, pj[b]);
+    }
+#pragma unroll
+    for (int a = 0; a <= LI; ++a) {
+        double vi[4] = {0, 0, 0, 0}, gi[5] = {0, 0, 0, 0, 0};
+        vi[a] = 1.0;
+        gi[a + 1] = 2 * ai;
+        if (a > 0) gi[a - 1] = -a;
+        if (a - 1 >= 1) shift_poly(pa, a - 1, gi);
+        if (a + 1 == 1) gi[0] += pa * gi[1];
+        else if (a + 1 == 2) { gi[0] += pa * pa * gi[2]; gi[1] += 2 * pa * gi[2]; }
+        else { gi[0] += pa * pa * pa * gi[3]; gi[1] += 3 * pa * pa * gi[3]; gi[2] += 3 * pa * gi[3]; }
+        shift_poly(pa, a, vi);
+#pragma unroll
+        for (int b = 0; b <= LJ; ++b) {
+            double v0 = 0, v1 = 0, v2 = 0, g0 = 0, g1 = 0, g2 = 0;
+#pragma unroll
+            for (int k = 0; k <= a + b + 1; ++k) {
+                double sv = 0.0, sg = 0.0;
+#pragma unroll
+                for (int q = 0; q <= a + 1; ++q) {
+                    const int r = k - q;
+                    if (r >= 0 && r <= b) { if (q <= a) sv += vi[q] * pj[b][r]; sg += gi[q] * pj[b][r]; }
+                }
+                v0 += m0[k] * sv; v1 += m1[k] * sv; v2 += m2[k] * sv;
+                g0 += m0[k] * sg; g1 += m1[k] * sg; g2 += m2[k] * sg;
+            }
+            double* o = out + 6 * (a * (LJ + 1) + b);
+            o[0] = v0; o[1] = v1; o[2] = v2; o[3] = g0; o[4] = g1; o[5] = g2;
+        }
+    }
+}
+__device__ __forceinline__ void moments_grad_table_dyn(int li, int lj, double ai, double pa, double pb, double rpc, const double* s1d,
+                                                       double* out) {
+    switch (3 * li + lj) {
+        case 0: moments_grad_table<0, 0>(ai, pa, pb, rpc, s1d, out); break;
+        case 1: moments_grad_table<0, 1>(ai, pa, pb, rpc, s1d, out); break;
+        case 2: moments_grad_table<0, 2>(ai, pa, pb, rpc, s1d, out); break;
+        case 3: moments_grad_table<1, 0>(ai, pa, pb, rpc, s1d, out); break;
+        case 4: moments_grad_table<1, 1>(ai, pa, pb, rpc, s1d, out); break;
+        case 5: moments_grad_table<1, 2>(ai, pa, pb, rpc, s1d, out); break;
+        case 6: moments_grad_table<2, 0>(ai, pa, pb, rpc, s1d, out); break;
+        case 7: moments_grad_table<2, 1>(ai, pa, pb, rpc, s1d, out); break;
+        default: moments_grad_table<2, 2>(ai, pa, pb, rpc, s1d, out); break;
+    }
+}
+constexpr int kGradTab = 1184;        // doubles of the moment table per warp (16 primitive pairs of a p-p shell pair)
+
 __constant__ int c_ord[10][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {1, 1, 0}, {1, 0, 1}, {0, 1, 1}};
 
 // Hamiltonian gradient: one warp per off-site shell pair (is > js, different atoms, r^2 <= 1600).
@@ -60,6 +125,9 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
     const long long pk = shard_pair_cta(d) * kIntWarps + warp;
     __shared__ double s_alp[kIntWarps][2][6], s_cont[kIntWarps][2][6];
     __shared__ double s_wf[kIntWarps][25], s_wp[kIntWarps][25];
+    __shared__ double s_tabs[kIntWarps][kGradTab], s_kab[kIntWarps][kIntMaxPP];
+    __shared__ unsigned char s_ipjp[kIntWarps][kIntMaxPP];
+    double* tab = &s_tabs[warp][0];
     if (pk >= npair) return;
     const long long p = d.pair_order[d.pord0[blockIdx.y] + pk];
     int is = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
@@ -83,6 +151,10 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
     const int nsi = c_nsph[li], nsj = c_nsph[lj];
     if (lane < 6) { s_alp[warp][0][lane] = si.alp[lane]; s_cont[warp][0][lane] = si.cont[lane]; }
     else if (lane < 12) { s_alp[warp][1][lane - 6] = sj.alp[lane - 6]; s_cont[warp][1][lane - 6] = sj.cont[lane - 6]; }
+    for (int q = lane; q < kIntMaxPP; q += 32) {
+        const int ip = q / npj;
+        s_ipjp[warp][q] = (unsigned char)(ip | ((q - ip * npj) << 4));
+    }
     const int nao = m.nao;
     // spherical weights + shell-pair scalars
     const double ves = (d.sshift[m.sh0 + is] + d.ashift[m.at0 + iat]) + (d.sshift[m.sh0 + js] + d.ashift[m.at0 + jat]);
@@ -114,14 +186,22 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
     const int lpc = ncomp >= 32 ? 1 : 32 / ncomp;
     const int ngrp = 32 / lpc;
     const int grp = lane / lpc, sub = lane % lpc;
-    for (int c = grp; c < ncomp; c += ngrp) {
-        if (grp >= ngrp) break;
-        const int mli = c / ncj, mlj = c % ncj;
-        const int lxi[3] = {c_lx[c_itt[li] + mli], c_ly[c_itt[li] + mli], c_lz[c_itt[li] + mli]};
-        const int lxj[3] = {c_lx[c_itt[lj] + mlj], c_ly[c_itt[lj] + mlj], c_lz[c_itt[lj] + mlj]};
+    // One-dimensional moments and their derivatives are tabulated per primitive pair and direction for all exponent pairs of the
+    // shell pair (k_sdqh0 does the same), the prefactors once per primitive pair; primitive pairs in chunks that fit the table.
+    const int nbj = lj + 1, nab = (li + 1) * nbj;
+    const int ppstride = 18 * nab + 1;
+    const int chunk = min(npp, kGradTab / ppstride);
+    for (int c0 = 0; c0 < ncomp; c0 += ngrp) {
+        const int c = c0 + grp;
+        const bool on = (grp < ngrp) && (c < ncomp);
+        const int mli = on ? c / ncj : 0, mlj = on ? c % ncj : 0;
+        const int ix = 6 * (c_lx[c_itt[li] + mli] * nbj + c_lx[c_itt[lj] + mlj]);
+        const int iy = 6 * (nab + c_ly[c_itt[li] + mli] * nbj + c_ly[c_itt[lj] + mlj]);
+        const int iz = 6 * (2 * nab + c_lz[c_itt[li] + mli] * nbj + c_lz[c_itt[lj] + mlj]);
         const double fi = (li == 2) ? c_dcart[mli] : 1.0, fj = (lj == 2) ? c_dcart[mlj] : 1.0;
         // Cartesian weights: W_c(mli,mlj) = sum_{ii,jj} T_i(mli,ii) W(ii,jj) T_j(mlj,jj)
         double wf = 0.0, wp = 0.0;
+        if (on)
         for (int ii = 0; ii < nsi; ++ii) {
             const double ti = (li == 2) ? c_dtrafo[mli][ii] : (ii == mli ? 1.0 : 0.0);
             if (ti == 0.0) continue;
@@ -135,39 +215,71 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
         double sdq[10], sdqg[3][10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) { sdq[k] = 0.0; sdqg[0][k] = sdqg[1][k] = sdqg[2][k] = 0.0; }
-        for (int pp = sub; pp < npp; pp += lpc) {
-            const int ip = pp / npj, jp = pp % npj;
-            const double alpi = s_alp[warp][0][ip];
-            const double ci = s_cont[warp][0][ip] * fi;
-            const double alpj = s_alp[warp][1][jp];
-            double est = alpi * alpj * rij2;
-            if (est > intcut * (alpi + alpj)) continue;
-            if (c == 0) cnt_add(d, blockIdx.y, 3, 1);
-            const double ab = 1.0 / (alpi + alpj);
-            est = est * ab;
-            const double sq = sqrtpi * sqrt(ab);
-            const double kab = exp(-est) * (sq * sq * sq);
-            const double cc = kab * (s_cont[warp][1][jp] * fj) * ci;
-            const double gm = 0.5 * ab;
-            double t[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) t[k] = olapp(k, gm);
-            double val[3][3], gra[3][3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const double rp = (alpi * ri[k] + alpj * rj[k]) * ab;
-                // operator origin on atom j (rc = rj), intgrad.f90:1020
-                moments_grad_1d(lxi[k], lxj[k], alpi, rp - ri[k], rp - rj[k], rp - rj[k], t, val[k], gra[k]);
+        for (int p0 = 0; p0 < npp; p0 += chunk) {
+            const int nch = min(chunk, npp - p0);
+            __syncwarp();
+            for (int q = lane; q < nch; q += 32) {   // prefactors (negative: screened out)
+                const int ij = s_ipjp[warp][p0 + q], ip = ij & 15, jp = ij >> 4;
+                const double alpi = s_alp[warp][0][ip], alpj = s_alp[warp][1][jp];
+                double est = alpi * alpj * rij2;
+                double kab = -1.0;
+                if (!(est > intcut * (alpi + alpj))) {
+                    if (c0 == 0) cnt_add(d, blockIdx.y, 3, 1);
+                    const double ab = 1.0 / (alpi + alpj);
+                    est = est * ab;
+                    const double sq = sqrtpi * sqrt(ab);
+                    kab = exp(-est) * (sq * sq * sq);
+                }
+                s_kab[warp][q] = kab;
             }
+            __syncwarp();
+            for (int e = lane; e < 3 * nch; e += 32) {   // one lane per (primitive pair, direction)
+                const int q = e / 3, dim = e - 3 * q;
+                if (s_kab[warp][q] < 0.0) continue;
+                const int ij = s_ipjp[warp][p0 + q], ip = ij & 15, jp = ij >> 4;
+                const double alpi = s_alp[warp][0][ip], alpj = s_alp[warp][1][jp];
+                const double ab = 1.0 / (alpi + alpj), gm = 0.5 * ab;
+                double t[9];
 #pragma unroll
-            for (int k = 0; k < 10; ++k) {
-                const int ox = c_ord[k][0], oy = c_ord[k][1], oz = c_ord[k][2];
-                sdq[k] += val[0][ox] * val[1][oy] * val[2][oz] * cc;
-                sdqg[0][k] += gra[0][ox] * val[1][oy] * val[2][oz] * cc;
-                sdqg[1][k] += val[0][ox] * gra[1][oy] * val[2][oz] * cc;
-                sdqg[2][k] += val[0][ox] * val[1][oy] * gra[2][oz] * cc;
+                for (int k = 0; k < 9; ++k) t[k] = olapp(k, gm);
+                const double xi = ri[dim], xj = rj[dim];
+                const double rp = (alpi * xi + alpj * xj) * ab;
+                // operator origin on atom j (rc = rj), intgrad.f90:1020
+                moments_grad_table_dyn(li, lj, alpi, rp - xi, rp - xj, rp - xj, t, tab + q * ppstride + 6 * dim * nab);
+            }
+            __syncwarp();
+            if (on)
+            for (int pp = p0 + sub; pp < p0 + nch; pp += lpc) {
+                const int q = pp - p0;
+                const double kab = s_kab[warp][q];
+                if (kab < 0.0) continue;
+                const int ij = s_ipjp[warp][pp], ip = ij & 15, jp = ij >> 4;
+                const double ci = s_cont[warp][0][ip] * fi;
+                const double cc = kab * (s_cont[warp][1][jp] * fj) * ci;
+                double val[3][3], gra[3][3];
+                {
+                    const double* bx = tab + q * ppstride + ix;
+                    const double* by = tab + q * ppstride + iy;
+                    const double* bz = tab + q * ppstride + iz;
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        val[0][u] = bx[u]; gra[0][u] = bx[3 + u];
+                        val[1][u] = by[u]; gra[1][u] = by[3 + u];
+                        val[2][u] = bz[u]; gra[2][u] = bz[3 + u];
+                    }
+                }
+                constexpr int ord[10][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {1, 1, 0}, {1, 0, 1}, {0, 1, 1}};
+#pragma unroll
+                for (int k = 0; k < 10; ++k) {
+                    const int ox = ord[k][0], oy = ord[k][1], oz = ord[k][2];
+                    sdq[k] += val[0][ox] * val[1][oy] * val[2][oz] * cc;
+                    sdqg[0][k] += gra[0][ox] * val[1][oy] * val[2][oz] * cc;
+                    sdqg[1][k] += val[0][ox] * gra[1][oy] * val[2][oz] * cc;
+                    sdqg[2][k] += val[0][ox] * val[1][oy] * gra[2][oz] * cc;
+                }
             }
         }
+        if (!on) continue;
         // shiftintg (intgrad.f90:703-728): operator moved from j to i, then contract
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
