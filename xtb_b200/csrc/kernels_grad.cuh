@@ -174,11 +174,6 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
     __syncwarp();
     const double intcut = d.intcut;
     const double sqrtpi = sqrt(kPi);
-    double vdi[3], vdj[3], vqi[6], vqj[6];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { vdi[k] = d.vd[3 * (m.at0 + iat) + k]; vdj[k] = d.vd[3 * (m.at0 + jat) + k]; }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { vqi[k] = d.vq[6 * (m.at0 + iat) + k]; vqj[k] = d.vq[6 * (m.at0 + jat) + k]; }
     double gx[3] = {0, 0, 0};
     // lpc lanes share one Cartesian component pair and split its primitive pairs (everything below is linear in the
     // primitive contributions, so per-lane partial sums are contracted independently and added by the warp reduction)
@@ -280,6 +275,12 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
             }
         }
         if (!on) continue;
+        // multipole potentials of the two atoms: loaded here, not before the primitive loop (18 doubles less to keep in registers)
+        double vdi[3], vdj[3], vqi[6], vqj[6];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { vdi[k] = d.vd[3 * (m.at0 + iat) + k]; vdj[k] = d.vd[3 * (m.at0 + jat) + k]; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { vqi[k] = d.vq[6 * (m.at0 + iat) + k]; vqj[k] = d.vq[6 * (m.at0 + jat) + k]; }
         // shiftintg (intgrad.f90:703-728): operator moved from j to i, then contract
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
