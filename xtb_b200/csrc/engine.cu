@@ -78,6 +78,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
@@ -96,6 +97,7 @@ struct NcclApi {
         api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
         api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
         api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
         api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
         api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
         api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
@@ -125,6 +127,17 @@ struct Batch::Impl {
     void allreduce(double* p, size_t count, cudaStream_t st) {
         NcclApi& n = NcclApi::get();
         n.check(n.AllReduce(p, p, count, ncclDouble, ncclSum, comm, st), "ncclAllReduce");
+    }
+    // column blocks of an n x n matrix, block r (tile columns split[r] .. split[r + 1], gt columns each) valid on rank r ->
+    // every rank holds the whole matrix: one in-place broadcast per owner, grouped
+    void gather_cols(double* p, int n, const std::vector<int>& split, int gt, cudaStream_t st) {
+        NcclApi& a = NcclApi::get();
+        a.check(a.GroupStart(), "ncclGroupStart");
+        for (int r = 0; r + 1 < (int)split.size(); ++r) {
+            const long long c0 = std::min<long long>(n, (long long)split[r] * gt), c1 = std::min<long long>(n, (long long)split[r + 1] * gt);
+            if (c1 > c0) a.check(a.Broadcast(p + c0 * n, p + c0 * n, (size_t)((c1 - c0) * n), ncclDouble, r, comm, st), "ncclBroadcast");
+        }
+        a.check(a.GroupEnd(), "ncclGroupEnd");
     }
     // per-kernel-class timers: events bracket every launch whose class bit is set in prof_mask
     unsigned long long prof_mask = 0;
@@ -202,7 +215,7 @@ struct Batch::Impl {
     unsigned long long* cnt_buf = nullptr;   // decision counters (diagnostic), allocated by set_decision_counting
     int knob_jb_inner = kJbInnerSweeps;
     int knob_jb_variant = 1;    // 1: jb_sweeps2 (cross-block Gram, unnormalised rotations), 0: jb_sweeps
-    bool knob_no_cluster_eig = false, knob_cta_chol = false, knob_cluster_single = false;
+    bool knob_no_cluster_eig = false, knob_cta_chol = false, knob_cluster_single = false, knob_no_gemm_split = false;
     size_t bytes = 0;
     // timing (ms) of the last single point
     float t_setup = 0, t_scc = 0, t_grad = 0, t_fact = 0;   // t_fact: overlap factorisation, part of t_setup
@@ -211,6 +224,8 @@ struct Batch::Impl {
     cudaEvent_t ev_phase[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [4]: begin of the overlap factorisation
     cudaEvent_t ev_call[2] = {nullptr, nullptr};
     cudaEvent_t ev_comm[4] = {nullptr, nullptr, nullptr, nullptr};   // integral exchange begin/end, gradient exchange begin/end
+    cudaEvent_t ev_gather[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // the three gathers of an SCC iteration
+    float t_gather = 0;                                              // summed over the iterations of the last call
     long long pair_total = 0;
     float t_call = 0;
 
@@ -238,6 +253,7 @@ struct Batch::Impl {
         for (auto& e : ev_phase) if (e) cudaEventDestroy(e);
         for (auto& e : ev_call) if (e) cudaEventDestroy(e);
         for (auto& e : ev_comm) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_gather) if (e) cudaEventDestroy(e);
         if (comm) NcclApi::get().CommDestroy(comm);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -269,6 +285,7 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         if (const char* e = tuning_env("XTBB200_SOLVER")) I.solver = std::atoi(e);   // initial value only: set_solver() wins
         I.knob_no_cluster_eig = tuning_env("XTBB200_NO_CLUSTER_EIG") != nullptr;
         I.knob_cluster_single = tuning_env("XTBB200_CLUSTER_SINGLE") != nullptr;
+        I.knob_no_gemm_split = tuning_env("XTBB200_NO_GEMM_SPLIT") != nullptr;
         I.knob_cta_chol = tuning_env("XTBB200_CTA_CHOL") != nullptr;
         const int maxhist = 120;
         int off = 0;
@@ -902,6 +919,40 @@ int Batch::singlepoint(bool restart) {
         if (gt48) KL(id, (k_gemm<TA, TB, 48><<<ggrid, 128, 0, st>>>(__VA_ARGS__)));   \
         else KL(id, (k_gemm<TA, TB, 64><<<ggrid, 128, 0, st>>>(__VA_ARGS__)));        \
     } while (0)
+    // One large system on several GPUs: the column-parallel products of an SCC iteration (X^T H X, back-transformation, C = X Z,
+    // density) are split by tile columns, every rank computes its block with the tile decomposition of the unsplit run (bit-
+    // identical columns) and the blocks are gathered by grouped NCCL broadcasts.  X^T H X has triangular work (K stops at the
+    // tile, W on the lower tiles): its split balances the cost, the others are even.
+    const bool gsplit = d.snranks > 1 && nmol == 1 && dc && !I.knob_no_gemm_split;
+    std::vector<int> sp_xhx(d.snranks + 1, 0), sp_eq(d.snranks + 1, 0);
+    if (gsplit) {
+        std::vector<double> cost(tiles);
+        double tot = 0.0;
+        for (int tc = 0; tc < tiles; ++tc) {
+            cost[tc] = (double)tiles * (tc + 1) + 0.5 * ((double)tiles * (tiles + 1) - (double)tc * (tc + 1));
+            tot += cost[tc];
+        }
+        double acc = 0.0;
+        int r = 1;
+        for (int tc = 0; tc < tiles && r < d.snranks; ++tc) {
+            acc += cost[tc];
+            while (r < d.snranks && acc >= tot * r / d.snranks) sp_xhx[r++] = tc + 1;
+        }
+        for (; r < d.snranks; ++r) sp_xhx[r] = tiles;
+        sp_xhx[d.snranks] = tiles;
+        for (int q = 0; q <= d.snranks; ++q) sp_eq[q] = (int)((long long)tiles * q / d.snranks);
+    }
+    const int xb = gsplit ? sp_xhx[d.srank] : 0, xe = gsplit ? sp_xhx[d.srank + 1] : 1 << 30;
+    const int eb = gsplit ? sp_eq[d.srank] : 0, ee = gsplit ? sp_eq[d.srank + 1] : 1 << 30;
+    if (gsplit && !I.ev_gather[0]) for (auto& e : I.ev_gather) cudaEventCreate(&e);
+    I.t_gather = 0;
+    auto gather = [&](double* p, const std::vector<int>& split, int which) {
+        I.prof_begin(K_COMM, st);
+        cudaEventRecord(I.ev_gather[2 * which], st);
+        I.gather_cols(p, s.max_nao, split, gtile, st);
+        cudaEventRecord(I.ev_gather[2 * which + 1], st);
+        I.prof_end(K_COMM, st);
+    };
     const int npairs = (s.max_nao + 1) / 2;
     // ensemble-sized matrices: block Jacobi on the FP64 tensor path, matrix resident in shared memory
     const int jb_warps = std::max(1, std::min(20, jb_dims(s.max_nao).nb / 2));   // k_jacobi_blk: __launch_bounds__(640)
@@ -918,8 +969,12 @@ int Batch::singlepoint(bool restart) {
         if (d.solv_on) KL(K_SOLV_SCC, k_solv_matvec<<<dim3((s.max_nat + 31) / 32, nmol), 256, 0, st>>>(d, 0));
         KL(K_D4SCC, k_d4_shift<<<grid2(s.max_nat, B, nmol), B, 0, st>>>(d));
         KL(K_FOCK, k_fock<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d));
-        KGEMM(K_GEMM_XHX, false, false, d, d.H, d.X, d.T, xtri ? 2 : 0, 1);   // T = H X
-        KGEMM(K_GEMM_XHX, true, false, d, d.X, d.T, d.W, xtri ? 3 : 0, 1);    // W = X^T T
+        KGEMM(K_GEMM_XHX, false, false, d, d.H, d.X, d.T, xtri ? 2 : 0, 1, xb, xe);   // T = H X
+        KGEMM(K_GEMM_XHX, true, false, d, d.X, d.T, d.W, xtri ? 3 : 0, 1, xb, xe);    // W = X^T T
+        if (gsplit) {
+            gather(d.W, sp_xhx, 0);
+            if (xtri) KL(K_GEMM_XHX, k_mirror_lower<<<(unsigned)((nn2 + 255) / 256), 256, 0, st>>>(d.W, s.max_nao));
+        }
         if (!dc && !bdc && (it > 0 || (restart && I.have_wfn)))
             KGEMM(K_GEMM_XHX, false, false, d, d.W, d.Zm, d.T, 0, 2);   // T = A' Z_prev
         if (bdc) {
@@ -946,17 +1001,20 @@ int Batch::singlepoint(bool restart) {
             };
             for (int im = 0; im < nmol; ++im)
                 if (!I.h_done[im])
-                    I.eig.solve(st, d.W + s.mol[im].mat0, s.mol[im].nao, d.emo + s.mol[im].ao0, d.Zm + s.mol[im].mat0, false, hook);
+                    I.eig.solve(st, d.W + s.mol[im].mat0, s.mol[im].nao, d.emo + s.mol[im].ao0, d.Zm + s.mol[im].mat0, false, hook,
+                                gsplit ? eb * gtile : 0, gsplit ? ee * gtile : -1);
             KL(K_EIG_BT, k_eigh_finish<<<(nmol + 127) / 128, 128, 0, st>>>(d, I.eig.fail, 0));
         } else if (hier) hjacobi(d.W, 1, K_JACOBI);
         else if (npairs * 32 <= 1024) KL(K_JACOBI, launch_jacobi<32>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 16 <= 1024) KL(K_JACOBI, launch_jacobi<16>(d, nmol, s.max_nao, sm, st));
         else if (npairs * 8 <= 1024) KL(K_JACOBI, launch_jacobi<8>(d, nmol, s.max_nao, sm, st));
         else KL(K_JACOBI, launch_jacobi<4>(d, nmol, s.max_nao, sm, st));
-        KGEMM(K_GEMM_C, false, false, d, d.X, d.Zm, d.C, xtri ? 4 : 0, 1);   // C = X Z
+        KGEMM(K_GEMM_C, false, false, d, d.X, d.Zm, d.C, xtri ? 4 : 0, 1, eb, ee);   // C = X Z
+        if (gsplit) gather(d.C, sp_eq, 1);
         KL(K_FERMI, k_fermi<<<nmol, 32, 0, st>>>(d));
         KL(K_DENSITY, k_scale_cols<<<grid2(nn2, 256, nmol), 256, 0, st>>>(d, 0));                // T = C f
-        KGEMM(K_DENSITY, false, true, d, d.T, d.C, d.P, 1, 1);       // P = T C^T
+        KGEMM(K_DENSITY, false, true, d, d.T, d.C, d.P, 1, 1, eb, ee);       // P = T C^T
+        if (gsplit) gather(d.P, sp_eq, 2);
         KL(K_POP, k_pop_rows<<<grid2((long long)s.max_nao * 32, 256, nmol), 256, 0, st>>>(d));
         KL(K_POP, k_pop_atoms<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));
         KL(K_ENERGY, k_es_rows<<<grid2(8LL * s.max_nsh, 256, nmol), 256, 0, st>>>(d));
@@ -972,6 +1030,12 @@ int Batch::singlepoint(bool restart) {
             XTB_CUDA_CHECK(cudaMemcpy2DAsync(I.h_done.data(), sizeof(int), &d.st[0].done, sizeof(MolState), sizeof(int), nmol,
                                              cudaMemcpyDeviceToHost, st));
         XTB_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (gsplit)
+            for (int w = 0; w < 3; ++w) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, I.ev_gather[2 * w], I.ev_gather[2 * w + 1]);
+                I.t_gather += ms;
+            }
         iters++;
     }
     cudaEventRecord(ev[2], st);
@@ -1046,7 +1110,7 @@ int Batch::singlepoint(bool restart) {
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, I.ev_comm[0], I.ev_comm[1]);
         cudaEventElapsedTime(&b, I.ev_comm[2], I.ev_comm[3]);   // includes k_grad_cn between the two exchanges
-        I.t_comm = a + b;
+        I.t_comm = a + b + I.t_gather;
     }
     I.prof_collect();
     I.launches = nl;

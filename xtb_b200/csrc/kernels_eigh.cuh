@@ -1818,8 +1818,11 @@ struct EighWork {
     // *fail (device int) is incremented when a secular equation did not converge.  Returns the number of launches.
     // hook(stage, end, launches) brackets the stages for the caller's timers: 0 panel kernel, 1 trailing update,
     // 2 divide and conquer, 3 back-transformation.
+    // zc0 / zc1 (multiples of GT, zc1 < 0: all): the back-transformation is applied to the columns [zc0, zc1) of Z only -- one
+    // large system with the column-parallel products split over the GPUs; the caller gathers the column blocks afterwards.
+    // Tile boundaries and the K split are those of the full matrix, so the columns are bit-identical to the unsplit run.
     template <class Hook>
-    int solve(cudaStream_t st, double* A, int n, double* w, double* Z, bool timed, Hook hook) {
+    int solve(cudaStream_t st, double* A, int n, double* w, double* Z, bool timed, Hook hook, int zc0 = 0, int zc1 = -1) {
         int nl = 0;
         const long long ld = n;
         const size_t n2 = (size_t)n * n;
@@ -1984,12 +1987,16 @@ struct EighWork {
                 // (I - V T V^T) Z = Z - (V T) (V^T Z): W = V^T Z (K split only while there are too few tiles), VT = V T, Z -= VT W
                 const int tiles = ((kb + GT - 1) / GT) * ((n + GT - 1) / GT);
                 const int split = std::max(1, std::min(kBtSplit, (2 * nsm + tiles - 1) / tiles));
-                GemmTask t = gemm_task(Vb + r0, n, Z + r0, n, Wz, NB, kb, n, mr, 1.0, 0.0);
-                t.ksplit = split; t.csplit = (long long)NB * n;
-                gemm(st, true, false, t, split);
-                if (split > 1) k_bt_sum<<<(unsigned)(((size_t)NB * n + 255) / 256), 256, 0, st>>>(Wz, (long long)NB * n, split, (long long)NB * n);
-                gemm(st, false, false, gemm_task(Vb + r0, n, Tf + (size_t)b * NB * NB, NB, VT + r0, n, mr, kb, kb, 1.0, 0.0));
-                gemm(st, false, false, gemm_task(VT + r0, n, Wz, NB, Z + r0, n, mr, n, kb, -1.0, 1.0));
+                const int zb = zc0, ze = zc1 < 0 ? n : std::min(n, zc1), nz = ze - zb;   // columns of Z of this rank
+                if (nz > 0) {
+                    double* Zc = Z + (size_t)n * zb;
+                    GemmTask t = gemm_task(Vb + r0, n, Zc + r0, n, Wz, NB, kb, nz, mr, 1.0, 0.0);
+                    t.ksplit = split; t.csplit = (long long)NB * n;
+                    gemm(st, true, false, t, split);
+                    if (split > 1) k_bt_sum<<<(unsigned)(((size_t)NB * nz + 255) / 256), 256, 0, st>>>(Wz, (long long)NB * n, split, (long long)NB * nz);
+                    gemm(st, false, false, gemm_task(Vb + r0, n, Tf + (size_t)b * NB * NB, NB, VT + r0, n, mr, kb, kb, 1.0, 0.0));
+                    gemm(st, false, false, gemm_task(VT + r0, n, Wz, NB, Zc + r0, n, mr, nz, kb, -1.0, 1.0));
+                }
                 nl += split > 1 ? 5 : 4;
             }
         }

@@ -36,8 +36,9 @@ constexpr int GLD = GT + 4;
 // GTT: CTA tile, 64 or 48 (2 x 2 warps of GTT/2 x GTT/2); 48 fits orders like 144 = 3 x 48 without the 44 % of padding a
 // 64-wide tiling of 192 x 192 multiplies (the engine picks the tile with the smaller padded area for the batch)
 template <bool TA, bool TB, int GTT>
+// tcb / tce: only the tile columns [tcb, tce) are computed (one large system with the GEMM columns split over the GPUs)
 __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ Ag, const double* __restrict__ Bg,
-                                              double* __restrict__ Cg, int kmode, int skip_done) {
+                                              double* __restrict__ Cg, int kmode, int skip_done, int tcb = 0, int tce = 1 << 30) {
     const MolDesc m = d.mol[blockIdx.y];
     if (skip_done && d.st[blockIdx.y].done) return;
     if (skip_done >= 2 && !d.st[blockIdx.y].zvalid) return;
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
     const int tiles = (n + GTT - 1) / GTT;
     if ((int)blockIdx.x >= tiles * tiles) return;
     const int r0 = (blockIdx.x % tiles) * GTT, c0 = (blockIdx.x / tiles) * GTT;
+    if ((int)(blockIdx.x / tiles) < tcb || (int)(blockIdx.x / tiles) >= tce) return;
     if (kmode == 3 && r0 < c0) return;
     int K = n, kbeg = 0;
     if (kmode == 1) K = d.st[blockIdx.y].kocc;
@@ -134,6 +136,15 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
                 }
             }
         }
+}
+
+// upper triangle <- lower triangle of an n x n matrix (after the column blocks of a symmetric product computed on its lower
+// tiles were gathered from the ranks that own them); thread per element
+__global__ void k_mirror_lower(double* __restrict__ A, int n) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n * n) return;
+    const int i = (int)(t % n), j = (int)(t / n);
+    if (i < j) A[t] = A[j + (long long)n * i];
 }
 
 // ---------------------------------------------------------------------------------------------
