@@ -111,8 +111,10 @@ int xtbb200_symmetricEigen(int n, const double* a, double* w, double* z, float* 
  * derivative (build_dSDQH0, :575-792) are dealt to the ranks CTA by CTA, the per-atom gradient terms (AES, D4 two- and
  * three-body, Coulomb derivative, CN chain rule) in chunks of 32 atoms; the contributions are summed with NCCL
  * allreduce over NVLink: S/D/Q/H0 (12 n^2 doubles, disjoint blocks: bit-identical to one GPU), the dE/dCN vectors
- * (4 N) and the gradient (3 N).  The SCC iterations, i.e. the eigensolver, run replicated on every rank (they stay on
- * one GPU by design), so every rank ends with the complete result.
+ * (4 N) and the gradient (3 N).  In the SCC iterations the tridiagonalisation and the divide and conquer run replicated on
+ * every rank; the column-parallel products (X^T H X, back-transformation of the eigenvectors, C = X Z, density) are split by
+ * tile columns and their blocks gathered with grouped ncclBroadcast (bit-identical to one GPU), so every rank ends with the
+ * complete result.
  *   xtbb200_shardUniqueId: rank 0 creates the 128-byte NCCL id; the caller ships it to the other ranks (MPI,
  *                          torch.distributed, a file ...).
  *   xtbb200_setShard:      collective over all ranks; nranks == 1 switches the split off again.
