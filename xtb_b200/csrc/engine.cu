@@ -405,7 +405,7 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
                         const ShellPar& b = s.shells[mm.sh0 + js];
                         const int ncomp = ncart[a.l] * ncart[b.l];
                         // passes over the component groups of a warp x primitive pairs per lane, as the kernels loop
-                        const int lpc = ncomp >= 32 ? 1 : 32 / ncomp, ngrp = 32 / lpc;
+                        const int lpc = ncomp >= kIntLG ? 1 : kIntLG / ncomp, ngrp = kIntLG / lpc;
                         const int c = ((ncomp + ngrp - 1) / ngrp) * ((a.nprim * b.nprim + lpc - 1) / lpc) * 64 + (a.atom == b.atom ? 0 : 1);
                         cost[pidx] = std::make_pair(-c, pidx);
                     }
@@ -426,6 +426,7 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         cudaFuncSetAttribute(k_jacobi_blk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_hj_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_grad_atm, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sdqh0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdqSmem));
         cudaFuncSetAttribute(k_bchol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBcholDiagSmem);
         cudaFuncSetAttribute(k_hj_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, HP * GLD * (int)sizeof(double));
         cudaFuncSetAttribute(k_jacobi<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
@@ -814,7 +815,9 @@ int Batch::singlepoint(bool restart) {
         XTB_CUDA_CHECK(cudaMemsetAsync(d.H0, 0, tmb, st));
         XTB_CUDA_CHECK(cudaMemsetAsync(d.H0n, 0, tmb, st));
     }
-    KL(K_SDQH0, k_sdqh0<<<pair_grid, kIntWarps * 32, 0, st>>>(d));
+    const long long pair_ctas2 = (max_pairs + kIntPairs - 1) / kIntPairs;   // k_sdqh0: half a warp per shell pair
+    const dim3 pair_grid2((unsigned)std::max<long long>(1, (pair_ctas2 + R - 1) / R), nmol);
+    KL(K_SDQH0, k_sdqh0<<<pair_grid2, kIntWarps * 32, kSdqSmem, st>>>(d));
     if (R > 1) {
         NcclApi& n = NcclApi::get();
         I.prof_begin(K_COMM, st);

@@ -153,24 +153,36 @@ constexpr int kIntWarps = 4;
 // direction there are only (li + 1) (lj + 1) different ones, while a p-p pair has 9 components that each need three.  They are
 // tabulated per warp in shared memory ([primitive pair][direction][(a, b)][moment], primitive pairs in chunks that fit), the
 // prefactors exp(-est) (pi / (alpha_i + alpha_j))^(3/2) once per primitive pair; the component lanes then only multiply.
-constexpr int kIntTab = 864;          // doubles per warp
+constexpr int kIntTab = 592;          // doubles per shell pair (16 primitive pairs of a p-p shell pair)
 constexpr int kIntMaxPP = 36;         // primitive pairs of a shell pair (6 x 6)
 
-// S, D, Q, H0, H0_noovlp for all shell pairs (is >= js).  grid = (ceil(npair/kIntWarps), nmol)
-__global__ void __launch_bounds__(kIntWarps * 32, 5) k_sdqh0(Dev d) {
+// Half a warp per shell pair: most of the instructions of a shell pair do not depend on its size (pair decoding, shell data,
+// shell-pair constants, Cartesian -> spherical transformation, scatter), and 1128 + 1363 of the 3081 shell pairs of a molecule
+// like rivaroxaban are s-s / s-p pairs with 1 or 3 components; two pairs per warp share that instruction stream.  Everything
+// below is written for groups of kIntLG lanes (`lane` = lane of the group, `slot` = group of the CTA) and synchronises the
+// group only (__syncwarp(gmask)), so the two halves of a warp may take different paths.
+constexpr int kIntLG = 16;                          // lanes per shell pair
+constexpr int kIntPairs = kIntWarps * (32 / kIntLG); // shell pairs per CTA
+
+constexpr size_t kSdqSmem = (size_t)kIntPairs * (360 + kIntTab) * sizeof(double);   // dynamic shared memory of k_sdqh0
+
+// S, D, Q, H0, H0_noovlp for all shell pairs (is >= js).  grid = (ceil(npair/kIntPairs), nmol)
+__global__ void __launch_bounds__(kIntWarps * 32, 3) k_sdqh0(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x / kIntLG, lane = threadIdx.x % kIntLG;   // "warp": the group of kIntLG lanes of this shell pair
+    const unsigned gmask = kIntLG == 32 ? 0xffffffffu : ((1u << kIntLG) - 1u) << ((threadIdx.x & 31) / kIntLG * kIntLG);
     long long npair = (long long)m.nsh * (m.nsh + 1) / 2;
-    long long p = shard_pair_cta(d) * kIntWarps + warp;
-    __shared__ double s_blk[kIntWarps][10][36];
-    __shared__ double s_tabs[kIntWarps][kIntTab];
-    __shared__ double s_kab[kIntWarps][kIntMaxPP];
-    __shared__ double s_alp[kIntWarps][2][6], s_cont[kIntWarps][2][6];
-    __shared__ unsigned char s_ipjp[kIntWarps][kIntMaxPP], s_slot[kIntWarps][kIntMaxPP];   // (ip, jp) of a primitive pair; block slot of a component
-    static_assert(kIntTab >= 10 * 33, "the lane partial sums of the reduction reuse the table");
-    double (*s_part)[33] = reinterpret_cast<double (*)[33]>(&s_tabs[warp][0]);   // [10][33], after the table is dead
+    long long p = shard_pair_cta(d) * kIntPairs + warp;
+    extern __shared__ __align__(16) double s_dyn_int[];                    // kSdqSmem bytes: s_blk | s_tabs (more than 48 kB together)
+    double (*s_blk)[10][36] = reinterpret_cast<double (*)[10][36]>(s_dyn_int);
+    double (*s_tabs)[kIntTab] = reinterpret_cast<double (*)[kIntTab]>(s_dyn_int + kIntPairs * 360);
+    __shared__ double s_kab[kIntPairs][kIntMaxPP];
+    __shared__ double s_alp[kIntPairs][2][6], s_cont[kIntPairs][2][6];
+    __shared__ unsigned char s_ipjp[kIntPairs][kIntMaxPP], s_slot[kIntPairs][kIntMaxPP];   // (ip, jp) of a primitive pair; block slot of a component
+    static_assert(kIntTab >= 10 * (kIntLG + 1), "the lane partial sums of the reduction reuse the table");
+    double (*s_part)[kIntLG + 1] = reinterpret_cast<double (*)[kIntLG + 1]>(&s_tabs[warp][0]);   // [10][kIntLG + 1], after the table is dead
     double* tab = &s_tabs[warp][0];
-    if (p >= npair) return;   // whole warp exits together
+    if (p >= npair) return;   // the whole group exits together
     p = d.pair_order[d.pord0[blockIdx.y] + p];
     int is = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
     while ((long long)is * (is + 1) / 2 > p) --is;
@@ -183,12 +195,12 @@ __global__ void __launch_bounds__(kIntWarps * 32, 5) k_sdqh0(Dev d) {
     if (lane < 6) { s_alp[warp][0][lane] = si.alp[lane]; s_cont[warp][0][lane] = si.cont[lane]; }
     else if (lane < 12) { s_alp[warp][1][lane - 6] = sj.alp[lane - 6]; s_cont[warp][1][lane - 6] = sj.cont[lane - 6]; }
     const int ncomp = nci * ncj;
-    for (int q = lane; q < kIntMaxPP; q += 32) {   // the divisions by the run-time npj / ncj once per shell pair, not per term
+    for (int q = lane; q < kIntMaxPP; q += kIntLG) {   // the divisions by the run-time npj / ncj once per shell pair, not per term
         const int ip = q / npj, cc = q / ncj;
         s_ipjp[warp][q] = (unsigned char)(ip | ((q - ip * npj) << 4));
         s_slot[warp][q] = (unsigned char)(cc * 6 + (q - cc * ncj));
     }
-    __syncwarp();
+    __syncwarp(gmask);
     const double* ri = d.xyz + 3 * (m.at0 + iat);
     const double* rj = d.xyz + 3 * (m.at0 + jat);
     const double rij[3] = {ri[0] - rj[0], ri[1] - rj[1], ri[2] - rj[2]};
@@ -200,8 +212,8 @@ __global__ void __launch_bounds__(kIntWarps * 32, 5) k_sdqh0(Dev d) {
     // Work decomposition: lpc lanes share one Cartesian component pair and split its primitive pairs, so that s-s,
     // s-p and p-p shell pairs (1, 3, 9 components) still occupy most of the warp.
     const int npp = npi * npj;
-    const int lpc = ncomp >= 32 ? 1 : 32 / ncomp;
-    const int ngrp = 32 / lpc;
+    const int lpc = ncomp >= kIntLG ? 1 : kIntLG / ncomp;
+    const int ngrp = kIntLG / lpc;
     const int grp = lane / lpc, sub = lane % lpc;
     const int nbj = lj + 1, nab = (li + 1) * nbj;
     const int ppstride = 9 * nab + 1;                       // + 1: the lanes of a component group hit different banks
@@ -224,7 +236,7 @@ __global__ void __launch_bounds__(kIntWarps * 32, 5) k_sdqh0(Dev d) {
         for (int p0 = 0; inrange && p0 < npp; p0 += chunk) {
             const int nch = min(chunk, npp - p0);
             // ---- prefactors, one lane per primitive pair (negative: screened out)
-            for (int q = lane; q < nch; q += 32) {
+            for (int q = lane; q < nch; q += kIntLG) {
                 const int ij = s_ipjp[warp][p0 + q], ip = ij & 15, jp = ij >> 4;
                 const double alpi = s_alp[warp][0][ip], alpj = s_alp[warp][1][jp];
                 double est = alpi * alpj * rij2;
@@ -238,9 +250,9 @@ __global__ void __launch_bounds__(kIntWarps * 32, 5) k_sdqh0(Dev d) {
                 }
                 s_kab[warp][q] = kab;
             }
-            __syncwarp();
+            __syncwarp(gmask);
             // ---- moments <(x - A)^a | (x - C)^{0,1,2} | (x - B)^b>, one lane per (primitive pair, direction)
-            for (int e = lane; e < 3 * nch; e += 32) {
+            for (int e = lane; e < 3 * nch; e += kIntLG) {
                 const int q = e / 3, dim = e - 3 * q;
                 if (s_kab[warp][q] < 0.0) continue;
                 const int ij = s_ipjp[warp][p0 + q], ip = ij & 15, jp = ij >> 4;
@@ -253,7 +265,7 @@ __global__ void __launch_bounds__(kIntWarps * 32, 5) k_sdqh0(Dev d) {
                 const double rp = (alpi * xi + alpj * xj) * ab;
                 moments_table_dyn(li, lj, rp - xi, rp - xj, rp, t, tab + q * ppstride + 3 * dim * nab);
             }
-            __syncwarp();
+            __syncwarp(gmask);
             // ---- this lane's component: products of three tabulated moments per primitive pair
             if (on) {
                 for (int pp = p0 + sub; pp < p0 + nch; pp += lpc) {
@@ -279,13 +291,13 @@ __global__ void __launch_bounds__(kIntWarps * 32, 5) k_sdqh0(Dev d) {
                     acc[9] += x0 * y1 * z1 * cc;
                 }
             }
-            __syncwarp();
+            __syncwarp(gmask);
         }
         // fixed-order reduction over the lanes of each component group (deterministic)
 #pragma unroll
         for (int k = 0; k < 10; ++k) s_part[k][lane] = acc[k];
-        __syncwarp();
-        for (int e = lane; e < ngrp * 10; e += 32) {
+        __syncwarp(gmask);
+        for (int e = lane; e < ngrp * 10; e += kIntLG) {
             const int g = e / 10, k = e % 10, cc2 = c0 + g;
             if (cc2 < ncomp) {
                 double v = 0.0;
@@ -293,7 +305,7 @@ __global__ void __launch_bounds__(kIntWarps * 32, 5) k_sdqh0(Dev d) {
                 s_blk[warp][k][s_slot[warp][cc2]] = v;
             }
         }
-        __syncwarp();
+        __syncwarp(gmask);
     }
     // CAO -> SAO and scatter.  Output element (ii, jj) of the spherical block, 10 operators.
     const int nsi = c_nsph[li], nsj = c_nsph[lj];
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(kIntWarps * 32, 5) k_sdqh0(Dev d) {
         double r = sqrt(rij2) / (b.rad + a.rad);
         shpoly = (1.0 + 0.01 * si.poly * sqrt(r)) * (1.0 + 0.01 * sj.poly * sqrt(r));
     }
-    for (int e = lane; e < nsi * nsj; e += 32) {
+    for (int e = lane; e < nsi * nsj; e += kIntLG) {
         const int ii = e / nsj, jj = e % nsj;
         const int iao = si.ao0 + ii, jao = sj.ao0 + jj;
         if (!offsite && is == js && jao > iao) continue;
