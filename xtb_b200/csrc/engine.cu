@@ -427,6 +427,7 @@ Batch::Batch(int nmol, const int* natoms, const int* numbers, const double* char
         cudaFuncSetAttribute(k_hj_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         cudaFuncSetAttribute(k_grad_atm, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
         XTB_CUDA_CHECK(cudaFuncSetAttribute(k_sdqh0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSdqSmem));
+        XTB_CUDA_CHECK(cudaFuncSetAttribute(k_grad_h0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmem));
         cudaFuncSetAttribute(k_bchol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBcholDiagSmem);
         cudaFuncSetAttribute(k_hj_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, HP * GLD * (int)sizeof(double));
         cudaFuncSetAttribute(k_jacobi<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
@@ -1050,7 +1051,11 @@ int Batch::singlepoint(bool restart) {
         if (d.srank != 0) XTB_CUDA_CHECK(cudaMemsetAsync(d.grad, 0, 3 * s.atoms.size() * sizeof(double), st));
         XTB_CUDA_CHECK(cudaMemsetAsync(d.gpair, 0, 4 * (size_t)I.pair_total * sizeof(double), st));
     }
-    KL(K_GRAD_H0, k_grad_h0<<<pair_grid, kIntWarps * 32, 0, st>>>(d));
+    {
+        const long long pc2 = (max_pairs + kIntPairs - 1) / kIntPairs;   // half a warp per shell pair
+        const dim3 pg2((unsigned)std::max<long long>(1, (pc2 + d.snranks - 1) / d.snranks), nmol);
+        KL(K_GRAD_H0, k_grad_h0<<<pg2, kIntWarps * 32, kGradSmem, st>>>(d));
+    }
     KL(K_GRAD_H0, k_grad_h0_collect<<<grid2((long long)kAS * s.max_nat, 64, nmol), 64, 0, st>>>(d));
     KL(K_GRAD_AES, k_grad_aes<<<grid2((long long)kAS * s.max_nat, 64, nmol), 64, 0, st>>>(d));
     KL(K_GRAD_D4, k_d4_weights<<<grid2(s.max_nat, 64, nmol), 64, 0, st>>>(d));

@@ -118,15 +118,25 @@ __constant__ int c_ord[10][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {2,
 // Hamiltonian gradient: one warp per off-site shell pair (is > js, different atoms, r^2 <= 1600).
 // The spherical weights are transformed to the Cartesian basis so that each lane contracts its own
 // Cartesian component pair; result per pair: gpair[p] = (gx, gy, gz, dCN).
-__global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
+constexpr size_t kGradSmem = (size_t)kIntPairs * kGradTab * sizeof(double);   // dynamic shared memory of k_grad_h0 (the tables)
+// half a warp per shell pair, as k_sdqh0: `warp` = group of kIntLG lanes, `lane` = lane of the group
+__global__ void __launch_bounds__(kIntWarps * 32, 2) k_grad_h0(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x / kIntLG, lane = threadIdx.x % kIntLG;
+    const unsigned gmask = kIntLG == 32 ? 0xffffffffu : ((1u << kIntLG) - 1u) << ((threadIdx.x & 31) / kIntLG * kIntLG);
+    auto group_sum = [&](double v) {
+#pragma unroll
+        for (int o = kIntLG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+        return v;
+    };
     const long long npair = (long long)m.nsh * (m.nsh + 1) / 2;
-    const long long pk = shard_pair_cta(d) * kIntWarps + warp;
-    __shared__ double s_alp[kIntWarps][2][6], s_cont[kIntWarps][2][6];
-    __shared__ double s_wf[kIntWarps][25], s_wp[kIntWarps][25];
-    __shared__ double s_tabs[kIntWarps][kGradTab], s_kab[kIntWarps][kIntMaxPP];
-    __shared__ unsigned char s_ipjp[kIntWarps][kIntMaxPP];
+    const long long pk = shard_pair_cta(d) * kIntPairs + warp;
+    __shared__ double s_alp[kIntPairs][2][6], s_cont[kIntPairs][2][6];
+    __shared__ double s_wf[kIntPairs][25], s_wp[kIntPairs][25];
+    extern __shared__ __align__(16) double s_dyn_grad[];                  // kGradSmem bytes
+    double (*s_tabs)[kGradTab] = reinterpret_cast<double (*)[kGradTab]>(s_dyn_grad);
+    __shared__ double s_kab[kIntPairs][kIntMaxPP];
+    __shared__ unsigned char s_ipjp[kIntPairs][kIntMaxPP];
     double* tab = &s_tabs[warp][0];
     if (pk >= npair) return;
     const long long p = d.pair_order[d.pord0[blockIdx.y] + pk];
@@ -151,7 +161,7 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
     const int nsi = c_nsph[li], nsj = c_nsph[lj];
     if (lane < 6) { s_alp[warp][0][lane] = si.alp[lane]; s_cont[warp][0][lane] = si.cont[lane]; }
     else if (lane < 12) { s_alp[warp][1][lane - 6] = sj.alp[lane - 6]; s_cont[warp][1][lane - 6] = sj.cont[lane - 6]; }
-    for (int q = lane; q < kIntMaxPP; q += 32) {
+    for (int q = lane; q < kIntMaxPP; q += kIntLG) {
         const int ip = q / npj;
         s_ipjp[warp][q] = (unsigned char)(ip | ((q - ip * npj) << 4));
     }
@@ -161,25 +171,25 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
     const double vss = d.vs[m.at0 + iat] + d.vs[m.at0 + jat];
     const double hav = 0.5 * (d.selfE[m.sh0 + is] + d.selfE[m.sh0 + js]);
     double hps = 0.0;   // sum HPij * S
-    if (lane < nsi * nsj) {
-        const int ii = lane / nsj, jj = lane % nsj;
+    for (int e = lane; e < nsi * nsj; e += kIntLG) {
+        const int ii = e / nsj, jj = e % nsj;
         const long long a = m.mat0 + (sj.ao0 + jj) + (long long)nao * (si.ao0 + ii);
         const double Pij = d.P[a];
         const double HPij = d.H0n[a] * kEVtoAU * Pij;
-        s_wf[warp][lane] = 2 * HPij - 2 * d.H[a] - Pij * ves + Pij * vss;   // d.H holds the energy weighted density here
-        s_wp[warp][lane] = Pij;
-        hps = HPij * d.S[a];
+        s_wf[warp][e] = 2 * HPij - 2 * d.H[a] - Pij * ves + Pij * vss;   // d.H holds the energy weighted density here
+        s_wp[warp][e] = Pij;
+        hps += HPij * d.S[a];
     }
-    hps = warp_sum(hps);
-    __syncwarp();
+    hps = group_sum(hps);
+    __syncwarp(gmask);
     const double intcut = d.intcut;
     const double sqrtpi = sqrt(kPi);
     double gx[3] = {0, 0, 0};
     // lpc lanes share one Cartesian component pair and split its primitive pairs (everything below is linear in the
     // primitive contributions, so per-lane partial sums are contracted independently and added by the warp reduction)
     const int ncomp = nci * ncj, npp = npi * npj;
-    const int lpc = ncomp >= 32 ? 1 : 32 / ncomp;
-    const int ngrp = 32 / lpc;
+    const int lpc = ncomp >= kIntLG ? 1 : kIntLG / ncomp;
+    const int ngrp = kIntLG / lpc;
     const int grp = lane / lpc, sub = lane % lpc;
     // One-dimensional moments and their derivatives are tabulated per primitive pair and direction for all exponent pairs of the
     // shell pair (k_sdqh0 does the same), the prefactors once per primitive pair; primitive pairs in chunks that fit the table.
@@ -212,8 +222,8 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
         for (int k = 0; k < 10; ++k) { sdq[k] = 0.0; sdqg[0][k] = sdqg[1][k] = sdqg[2][k] = 0.0; }
         for (int p0 = 0; p0 < npp; p0 += chunk) {
             const int nch = min(chunk, npp - p0);
-            __syncwarp();
-            for (int q = lane; q < nch; q += 32) {   // prefactors (negative: screened out)
+            __syncwarp(gmask);
+            for (int q = lane; q < nch; q += kIntLG) {   // prefactors (negative: screened out)
                 const int ij = s_ipjp[warp][p0 + q], ip = ij & 15, jp = ij >> 4;
                 const double alpi = s_alp[warp][0][ip], alpj = s_alp[warp][1][jp];
                 double est = alpi * alpj * rij2;
@@ -227,8 +237,8 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
                 }
                 s_kab[warp][q] = kab;
             }
-            __syncwarp();
-            for (int e = lane; e < 3 * nch; e += 32) {   // one lane per (primitive pair, direction)
+            __syncwarp(gmask);
+            for (int e = lane; e < 3 * nch; e += kIntLG) {   // one lane per (primitive pair, direction)
                 const int q = e / 3, dim = e - 3 * q;
                 if (s_kab[warp][q] < 0.0) continue;
                 const int ij = s_ipjp[warp][p0 + q], ip = ij & 15, jp = ij >> 4;
@@ -242,7 +252,7 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
                 // operator origin on atom j (rc = rj), intgrad.f90:1020
                 moments_grad_table_dyn(li, lj, alpi, rp - xi, rp - xj, rp - xj, t, tab + q * ppstride + 6 * dim * nab);
             }
-            __syncwarp();
+            __syncwarp(gmask);
             if (on)
             for (int pp = p0 + sub; pp < p0 + nch; pp += lpc) {
                 const int q = pp - p0;
@@ -317,7 +327,7 @@ __global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
         }
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) gx[k] = warp_sum(gx[k]);
+    for (int k = 0; k < 3; ++k) gx[k] = group_sum(gx[k]);
     if (lane == 0) {
         // distance dependent polynomial, grad_core.f90:40-72
         const AtomPar& a = d.atoms[m.at0 + iat];
