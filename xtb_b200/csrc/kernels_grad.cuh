@@ -111,7 +111,7 @@ __device__ __forceinline__ void moments_grad_table_dyn(int li, int lj, double ai
         default: moments_grad_table<2, 2>(ai, pa, pb, rpc, s1d, out); break;
     }
 }
-constexpr int kGradTab = 1184;        // doubles of the moment table per warp (16 primitive pairs of a p-p shell pair)
+constexpr int kGradTab = 888;         // doubles of the moment table per shell pair (12 primitive pairs of a p-p shell pair: 16 take two fillings, but three CTAs fit an SM)
 
 __constant__ int c_ord[10][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {1, 1, 0}, {1, 0, 1}, {0, 1, 1}};
 
@@ -120,7 +120,7 @@ __constant__ int c_ord[10][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {2,
 // Cartesian component pair; result per pair: gpair[p] = (gx, gy, gz, dCN).
 constexpr size_t kGradSmem = (size_t)kIntPairs * kGradTab * sizeof(double);   // dynamic shared memory of k_grad_h0 (the tables)
 // half a warp per shell pair, as k_sdqh0: `warp` = group of kIntLG lanes, `lane` = lane of the group
-__global__ void __launch_bounds__(kIntWarps * 32, 2) k_grad_h0(Dev d) {
+__global__ void __launch_bounds__(kIntWarps * 32, 3) k_grad_h0(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     const int warp = threadIdx.x / kIntLG, lane = threadIdx.x % kIntLG;
     const unsigned gmask = kIntLG == 32 ? 0xffffffffu : ((1u << kIntLG) - 1u) << ((threadIdx.x & 31) / kIntLG * kIntLG);

@@ -153,7 +153,7 @@ constexpr int kIntWarps = 4;
 // direction there are only (li + 1) (lj + 1) different ones, while a p-p pair has 9 components that each need three.  They are
 // tabulated per warp in shared memory ([primitive pair][direction][(a, b)][moment], primitive pairs in chunks that fit), the
 // prefactors exp(-est) (pi / (alpha_i + alpha_j))^(3/2) once per primitive pair; the component lanes then only multiply.
-constexpr int kIntTab = 592;          // doubles per shell pair (16 primitive pairs of a p-p shell pair)
+constexpr int kIntTab = 432;          // doubles per shell pair
 constexpr int kIntMaxPP = 36;         // primitive pairs of a shell pair (6 x 6)
 
 // Half a warp per shell pair: most of the instructions of a shell pair do not depend on its size (pair decoding, shell data,
@@ -167,7 +167,7 @@ constexpr int kIntPairs = kIntWarps * (32 / kIntLG); // shell pairs per CTA
 constexpr size_t kSdqSmem = (size_t)kIntPairs * (360 + kIntTab) * sizeof(double);   // dynamic shared memory of k_sdqh0
 
 // S, D, Q, H0, H0_noovlp for all shell pairs (is >= js).  grid = (ceil(npair/kIntPairs), nmol)
-__global__ void __launch_bounds__(kIntWarps * 32, 3) k_sdqh0(Dev d) {
+__global__ void __launch_bounds__(kIntWarps * 32, 4) k_sdqh0(Dev d) {
     const MolDesc m = d.mol[blockIdx.y];
     const int warp = threadIdx.x / kIntLG, lane = threadIdx.x % kIntLG;   // "warp": the group of kIntLG lanes of this shell pair
     const unsigned gmask = kIntLG == 32 ? 0xffffffffu : ((1u << kIntLG) - 1u) << ((threadIdx.x & 31) / kIntLG * kIntLG);
