@@ -664,7 +664,8 @@ __global__ void __launch_bounds__(128) k_grad_atm(Dev d) {
                 const double rrr2 = r2ij * r2jk * r2ik, rrr1 = sqrt(rrr2), rrr3 = rrr1 * rrr2;
                 const double ang_fact = 0.375 / (rrr2 * rrr3);
                 const double ang = ang_fact * (r2ij + r2jk - r2ik) * (r2ij - r2jk + r2ik) * (-r2ij + r2jk + r2ik) + 1.0 / rrr3;
-                const double cralp = pow(ccc1 / rrr1, 16.0 / 3.0);
+                const double crr = ccc1 / rrr1, crr2 = crr * crr;
+                const double cralp = crr2 * crr2 * crr * cbrt(crr);   // (c / r)^(16/3) without the general pow
                 const double fdmp = 1.0 / (1.0 + 6.0 * cralp);
                 const double dfdmp = -(2.0 * 16 * cralp) * fdmp * fdmp;
                 const double dE = -fdmp * ang * c9;
