@@ -788,6 +788,17 @@ int Batch::singlepoint(bool restart) {
             KL(K_EEQ, k_eeq_build<<<grid2((long long)(s.max_nat + 1) * (s.max_nat + 2), 256, nmol), 256, 0, st>>>(d));
             if (s.max_nat <= 320) {
                 KL(K_EEQ, k_eeq_solve<<<nmol, 256, 0, st>>>(d));
+            } else if (nmol == 1 && I.have_eig && (s.max_nat + 2) / I.eig.nsm + 2 <= kEeqRowMax && !tuning_env("XTBB200_EEQ_LAUNCHES")) {
+                // one large molecule: the same elimination as one cooperative launch (grid barriers instead of 2 N launches)
+                XTB_CUDA_CHECK(cudaMemsetAsync(I.eig.bar, 0, sizeof(unsigned), st));
+                Dev dd = d;
+                unsigned* barp = I.eig.bar;
+                void* args[] = {&dd, &barp};
+                I.prof_begin(K_EEQ, st);
+                XTB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_eeq_lu_coop, dim3(I.eig.nsm), dim3(1024), args, 0, st));
+                I.prof_end(K_EEQ, st);
+                I.k_launches[K_EEQ] += 1; nl += 1;
+                KL(K_EEQ, k_eeq_finish<<<nmol, 1024, 0, st>>>(d));
             } else {   // large molecules: the same elimination spread over the GPU, two launches per column
                 for (int k = 0; k < s.max_nat + 1; ++k) {
                     KL(K_EEQ, k_eeq_pivot<<<nmol, 1024, 0, st>>>(d, k));

@@ -382,6 +382,71 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, un
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// EEQ guess of one large molecule (more than 320 atoms): the Gaussian elimination with partial pivoting of k_eeq_pivot /
+// k_eeq_elim (kernels_geom.cuh; replaces dsysv, src/eeq_model.f90:858-862) as ONE cooperative launch with two grid barriers
+// per column instead of two launches per column (6000 launches for 3000 atoms).  Same pivot rule, same arithmetic per
+// element (f = A_ik / A_kk as A_ik * (1 / A_kk); A_ij -= f A_kj), hence the same charges bit for bit.  Every CTA finds the
+// pivot itself (the column is read by all); the row swap and the elimination are spread over the grid, a warp per column.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kEeqRowMax = 256;   // columns of a CTA's share: (natoms + 2) / grid + 1 must fit
+__global__ void __launch_bounds__(1024, 1) k_eeq_lu_coop(Dev d, unsigned* bar) {
+    const MolDesc m = d.mol[0];
+    const int n1 = m.nat + 1, nc = n1 + 1;
+    double* A = d.eeqA + d.eeq0[0];
+    const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    __shared__ int s_piv;
+    __shared__ double s_red[32];
+    __shared__ int s_idx[32];
+    __shared__ double s_row[kEeqRowMax];
+    unsigned target = 0;
+    for (int k = 0; k < n1; ++k) {
+        double best = -1.0; int bi = k;
+        for (int i = k + tid; i < n1; i += blockDim.x) {
+            const double v = fabs(__ldcg(A + i + (long long)n1 * k));
+            if (v > best) { best = v; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) { s_red[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            const int nw = (blockDim.x + 31) >> 5;
+            double b = s_red[0]; int ix = s_idx[0];
+            for (int w = 1; w < nw; ++w) if (s_red[w] > b || (s_red[w] == b && s_idx[w] < ix)) { b = s_red[w]; ix = s_idx[w]; }
+            s_piv = ix;
+            if (b == 0.0 && cta == 0) d.st[0].fail = 10;
+        }
+        __syncthreads();
+        const int p = s_piv;
+        if (p != k)
+            for (int j = k + cta * (int)blockDim.x + tid; j < nc; j += G * (int)blockDim.x) {
+                const double t = __ldcg(A + k + (long long)n1 * j);
+                A[k + (long long)n1 * j] = __ldcg(A + p + (long long)n1 * j);
+                A[p + (long long)n1 * j] = t;
+            }
+        grid_barrier(bar, G, target);
+        // elimination: this CTA's share of the trailing columns, threads along the rows (multiplier in a register, the columns'
+        // updates independent: many loads in flight); the pivot row segment is staged in shared memory
+        const double pinv = 1.0 / __ldcg(A + k + (long long)n1 * k);
+        const int ntc = nc - k - 1;
+        const int jb = k + 1 + (int)(((long long)ntc * cta) / G), je = k + 1 + (int)(((long long)ntc * (cta + 1)) / G);
+        for (int j = jb + tid; j < je; j += blockDim.x) s_row[j - jb] = __ldcg(A + k + (long long)n1 * j);
+        __syncthreads();
+        for (int i = k + 1 + tid; i < n1; i += blockDim.x) {
+            const double f = __ldcg(A + i + (long long)n1 * k) * pinv;
+            for (int j = jb; j < je; ++j) {
+                double* q = A + i + (long long)n1 * j;
+                *q = __ldcg(q) - f * s_row[j - jb];
+            }
+        }
+        grid_barrier(bar, G, target);
+    }
+}
+
 // deterministic block sum, result in all threads; second stage by shuffles in every warp (red: 32 doubles)
 __device__ __forceinline__ double block_sum_sh(double v, double* red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
