@@ -372,6 +372,9 @@ void xtb_hessian(xtb_TEnvironment env, xtb_TMolecule mol, xtb_TCalculator calc, 
         Batch& b = *calc->hess_batch;
         b.set_options(calc->accuracy, calc->etemp, calc->maxiter);
         b.set_guess(0);
+        // central differences with a step of 0.005 bohr multiply the noise of gradients and dipoles by 100: the eigenvectors of
+        // the displaced geometries are converged further than a single point needs (quadratic stop)
+        b.set_jacobi_stop(1.0e-9);
         if (calc->solv_on) b.set_solvent(calc->solv_name.c_str(), calc->solv_alpb, calc->solv_kernel, calc->solv_state, calc->solv_temp, 0.0, 0.0);
         else if (b.has_solvent()) b.release_solvent();
         const int npc = (int)calc->pc_q.size();

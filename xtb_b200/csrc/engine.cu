@@ -465,6 +465,7 @@ void Batch::set_options(double accuracy, double etemp, int maxiter) {
 }
 void Batch::set_guess(int mode) { p_->guess = mode; }
 void Batch::set_solver(int mode) { p_->solver = mode; }
+void Batch::set_jacobi_stop(double qtol) { p_->knob_jb_qtol = qtol > 0.0 ? qtol : kJbQuadraticStop; }
 
 void Batch::set_shard(int rank, int nranks, const char* id128) {
     Impl& I = *p_;

@@ -33,6 +33,8 @@ class Batch {
 
     void set_options(double accuracy, double etemp, int maxiter);
     void set_guess(int mode);                      // 0: EEQ (default), 1: uniform charges
+    void set_jacobi_stop(double qtol);             // quadratic stop of the block Jacobi solver (<= 0: default 1e-7); numerical
+                                                   // differentiation of the results (xtb_hessian) wants it tighter
     void set_solver(int mode);                     // 0: automatic, 1: scalar Jacobi, 2: X from eig(S), 3: two-level Jacobi, 4: batched D&C, 5: D&C one matrix at a time
     // this process becomes rank `rank` of `nranks` working on the SAME molecules: shell-pair integral / gradient blocks
     // and the per-atom gradient terms are split, NCCL allreduce of the contributions; nranks == 1 switches it off
