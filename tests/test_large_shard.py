@@ -86,8 +86,14 @@ def test_two_gpu_split_matches_single_gpu():
     if xtb_b200.device_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", str(port),
-                          os.path.join(ROOT, "tools", "shard_check.py"), "water", "64"],
-                         capture_output=True, text=True, timeout=800)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tools", "shard_check.py"), "water", "64"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=800)
+    assert "SHARD OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    # the same with the column-parallel products of the SCC iterations split over the two ranks as well (by default only
+    # from 2500 AOs on): X^T H X, back-transformation, C = X Z and density by tile columns, gathered by NCCL broadcasts
+    env = dict(os.environ, XTBB200_TUNING="1", XTBB200_GEMM_SPLIT_MIN="0")
+    cmd[cmd.index(str(port))] = str(port + 1 if port < 65000 else port - 1)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=800, env=env)
     assert "SHARD OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -939,7 +939,11 @@ int Batch::singlepoint(bool restart) {
     // density) are split by tile columns, every rank computes its block with the tile decomposition of the unsplit run (bit-
     // identical columns) and the blocks are gathered by grouped NCCL broadcasts.  X^T H X has triangular work (K stops at the
     // tile, W on the lower tiles): its split balances the cost, the others are even.
-    const bool gsplit = d.snranks > 1 && nmol == 1 && dc && !I.knob_no_gemm_split;
+    // (from 2500 AOs on: below, the three gathers per iteration cost more than the split products save -- 552 AOs: 470 instead
+    // of 453 ms of SCC on two GPUs, 1998 AOs: break-even; XTBB200_GEMM_SPLIT_MIN overrides the threshold for tests)
+    int gsplit_min = 2500;
+    if (const char* e = tuning_env("XTBB200_GEMM_SPLIT_MIN")) gsplit_min = std::atoi(e);
+    const bool gsplit = d.snranks > 1 && nmol == 1 && dc && !I.knob_no_gemm_split && s.max_nao >= gsplit_min;
     std::vector<int> sp_xhx(d.snranks + 1, 0), sp_eq(d.snranks + 1, 0);
     if (gsplit) {
         std::vector<double> cost(tiles);
@@ -989,7 +993,7 @@ int Batch::singlepoint(bool restart) {
         KGEMM(K_GEMM_XHX, true, false, d, d.X, d.T, d.W, xtri ? 3 : 0, 1, xb, xe);    // W = X^T T
         if (gsplit) {
             gather(d.W, sp_xhx, 0);
-            if (xtri) KL(K_GEMM_XHX, k_mirror_lower<<<(unsigned)((nn2 + 255) / 256), 256, 0, st>>>(d.W, s.max_nao));
+            if (xtri) KL(K_GEMM_XHX, k_mirror_lower<<<(unsigned)((nn2 + 255) / 256), 256, 0, st>>>(d.W, s.max_nao, gtile));
         }
         if (!dc && !bdc && (it > 0 || (restart && I.have_wfn)))
             KGEMM(K_GEMM_XHX, false, false, d, d.W, d.Zm, d.T, 0, 2);   // T = A' Z_prev

@@ -139,12 +139,14 @@ __global__ void __launch_bounds__(128) k_gemm(Dev d, const double* __restrict__ 
 }
 
 // upper triangle <- lower triangle of an n x n matrix (after the column blocks of a symmetric product computed on its lower
-// tiles were gathered from the ranks that own them); thread per element
-__global__ void k_mirror_lower(double* __restrict__ A, int n) {
+// tiles were gathered from the ranks that own them); thread per element.
+// Only the tiles above the diagonal tiles are mirrored (gt = tile width of the product): the diagonal tiles were computed
+// whole by the owner of their column block, exactly as in the unsplit run (their two triangles differ in the last bit).
+__global__ void k_mirror_lower(double* __restrict__ A, int n, int gt) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * n) return;
     const int i = (int)(t % n), j = (int)(t / n);
-    if (i < j) A[t] = A[j + (long long)n * i];
+    if (i / gt < j / gt) A[t] = A[j + (long long)n * i];
 }
 
 // ---------------------------------------------------------------------------------------------
