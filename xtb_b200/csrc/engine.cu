@@ -975,7 +975,7 @@ int Batch::singlepoint(bool restart) {
     };
     const int npairs = (s.max_nao + 1) / 2;
     // ensemble-sized matrices: block Jacobi on the FP64 tensor path, matrix resident in shared memory
-    const int jb_warps = std::max(1, std::min(20, jb_dims(s.max_nao).nb / 2));   // k_jacobi_blk: __launch_bounds__(640)
+    const int jb_warps = std::max(1, std::min(kJbMaxWarps, jb_dims(s.max_nao).nb / 2));   // k_jacobi_blk: __launch_bounds__(32 * kJbMaxWarps)
     const size_t jb_bytes = jb_smem_bytes(s.max_nao, jb_warps);
     auto jacobi_blk = I.knob_jb_variant ? k_jacobi_blk<1> : k_jacobi_blk<0>;
     int active = nmol;

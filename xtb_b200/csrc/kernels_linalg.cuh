@@ -385,6 +385,7 @@ __device__ __forceinline__ void jb_publish(volatile int* ver, int P, int Q, int 
 constexpr double kJbQuadraticStop = 1.0e-7;
 constexpr int kJbInnerSweeps = 1;  // inner sweeps per Gram block (early exit when a sweep rotates nothing)
 constexpr int kJbScratch = 192;   // doubles of per-warp scratch: M and J, 8 x 8 with row stride 9 (jb_sweeps) or kJs (jb_sweeps2)
+constexpr int kJbLoadBatch = 8;   // global loads in flight per thread and operand while k_jacobi_blk fills its shared memory
 constexpr int kJs = 12;           // jb_sweeps2: with lane = (idx = lane >> 2, slot = lane & 3) the P x Q rounds are free of bank conflicts
 
 struct JbDims { int nr, ld, nb; };
@@ -792,8 +793,11 @@ __global__ void k_lead_copy(Dev d) {
 }
 
 // phase: 0 all molecules, 1 leaders only, 2 followers only.  V: 0 = jb_sweeps, 1 = jb_sweeps2 (G scaled by 1/sigma)
+// at most kJbMaxWarps warps (one per block pair of the largest order, 152 = 38 blocks); with the bound of 608 instead of 640
+// threads ptxas keeps everything in registers (no stack), measured 0.8 % on the ensemble step (15.81 -> 15.60 ms per launch)
+constexpr int kJbMaxWarps = 19;
 template <int V>
-__global__ void __launch_bounds__(640) k_jacobi_blk(Dev d, int phase) {
+__global__ void __launch_bounds__(32 * kJbMaxWarps) k_jacobi_blk(Dev d, int phase) {
 #ifdef XTBB200_JB_TIMING
     long long jbt[6] = {0, 0, 0, 0, 0, 0}, jbt0 = clock64();
 #endif
@@ -817,11 +821,32 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d, int phase) {
     // the latency-bound inner solves of others.
     __shared__ volatile int ver[64];
     const double* A = d.W + m.mat0;
-    // Gershgorin bound -> shift that makes G positive definite
+    // Gershgorin bound -> shift that makes G positive definite.  A' is staged in the (still unused) shared memory of G by
+    // all threads, kJbLoadBatch loads in flight per thread, and the row sums are formed from there in the order j = 0 .. n-1
+    // (same sums as a loop over global memory per row thread).  One CTA per SM: nothing else hides the HBM latency of this
+    // prologue -- but it is a small part of the ~570 us a matrix spends on its SM: batching the loads did not change the
+    // launch time measurably (15.81 ms over 4096 matrices before and after)
+    {
+        const int total = n * n;
+        for (int t0 = tid; t0 < total; t0 += nt * kJbLoadBatch) {
+            double v[kJbLoadBatch];
+#pragma unroll
+            for (int u = 0; u < kJbLoadBatch; ++u) {
+                const int t = t0 + u * nt;
+                v[u] = t < total ? A[t] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kJbLoadBatch; ++u) {
+                const int t = t0 + u * nt;
+                if (t < total) G[(t % n) + (size_t)ld * (t / n)] = v[u];
+            }
+        }
+    }
+    __syncthreads();
     double mx = 0.0;
     for (int i = tid; i < n; i += nt) {
         double s = 0;
-        for (int j = 0; j < n; ++j) s += fabs(A[i + (long long)n * j]);
+        for (int j = 0; j < n; ++j) s += fabs(G[i + (size_t)ld * j]);
         mx = fmax(mx, s);
     }
     mx = warp_max(mx);
@@ -838,18 +863,36 @@ __global__ void __launch_bounds__(640) k_jacobi_blk(Dev d, int phase) {
     const int ncolp = nb * 4;
     const bool warm = st.zvalid != 0;
     {
+        // warm: G = T + sigma Z_prev; cold: the symmetrised A' + sigma I.  Both operands of kJbLoadBatch elements are
+        // requested before the first one is used (SASS of the one-element-per-iteration form: two loads, then the
+        // dependent DFMA and the store, 37 times at n = 144); same arithmetic per element, identical energies
         const double* T = d.T + m.mat0;
         const double* Zp = d.Zm + m.mat0;
-        for (int t = tid; t < ld * ncolp; t += nt) {
-            const int i = t % ld, j = t / ld;
-            double v = 0.0;
-            if (i < n && j < n) {
-                const long long a = i + (long long)n * j;
-                if (warm) v = T[a] + sigma * Zp[a];
-                else v = 0.5 * (A[a] + A[j + (long long)n * i]) + (i == j ? sigma : 0.0);
-                v *= gscale;
+        const double* p0 = warm ? T : A;
+        const double* p1 = warm ? Zp : A;
+        const int total = ld * ncolp;
+        for (int t0 = tid; t0 < total; t0 += nt * kJbLoadBatch) {
+            double x[kJbLoadBatch], y[kJbLoadBatch];
+#pragma unroll
+            for (int u = 0; u < kJbLoadBatch; ++u) {
+                const int t = t0 + u * nt, i = t % ld, j = t / ld;
+                const bool ok = i < n && j < n;     // (t >= total implies j >= ncolp >= n)
+                x[u] = ok ? p0[i + (long long)n * j] : 0.0;
+                y[u] = ok ? p1[warm ? i + (long long)n * j : j + (long long)n * i] : 0.0;
             }
-            G[t] = v;
+#pragma unroll
+            for (int u = 0; u < kJbLoadBatch; ++u) {
+                const int t = t0 + u * nt, i = t % ld, j = t / ld;
+                if (t < total) {
+                    double v = 0.0;
+                    if (i < n && j < n) {
+                        if (warm) v = fma(sigma, y[u], x[u]);
+                        else v = fma(x[u] + y[u], 0.5, i == j ? sigma : 0.0);
+                        v *= gscale;
+                    }
+                    G[t] = v;
+                }
+            }
         }
     }
     const double tol = d.jb_tol > 0.0 ? d.jb_tol : 8.0 * sqrt((double)n) * 2.220446049250313e-16;
