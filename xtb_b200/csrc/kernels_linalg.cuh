@@ -385,6 +385,12 @@ __device__ __forceinline__ void jb_publish(volatile int* ver, int P, int Q, int 
 constexpr double kJbQuadraticStop = 1.0e-7;
 constexpr int kJbInnerSweeps = 1;  // inner sweeps per Gram block (early exit when a sweep rotates nothing)
 constexpr int kJbScratch = 192;   // doubles of per-warp scratch: M and J, 8 x 8 with row stride 9 (jb_sweeps) or kJs (jb_sweeps2)
+// jb_sweeps2: largest |sin| of the 16 P x Q rotation angles of a block pair up to which they are taken simultaneously from the
+// Gram matrix as it stands (0: always the sequential rounds)
+#ifndef XTBB200_JB_SIMUL
+#define XTBB200_JB_SIMUL 0.1
+#endif
+constexpr double kJbSimulMaxSin = XTBB200_JB_SIMUL;
 constexpr int kJbLoadBatch = 8;   // global loads in flight per thread and operand while k_jacobi_blk fills its shared memory
 constexpr int kJs = 12;           // jb_sweeps2: with lane = (idx = lane >> 2, slot = lane & 3) the P x Q rounds are free of bank conflicts
 
@@ -708,6 +714,53 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                 else rotbig = 1;
                 // ---- two-sided Jacobi on the 8x8 Gram matrix; lane = (pair slot, row/column index)
                 __syncwarp();
+                bool simul = false;
+                if (!full && kJbSimulMaxSin > 0.0) {
+                    // Small angles (every sweep but the first part of the first one): the 16 P x Q rotations with the angles of
+                    // the Gram matrix as it stands -- they differ from the angles of the sequential rounds in second order, like
+                    // what the rounds put back into each other's zeros.  Nothing of M has to be updated between the rounds then:
+                    // J = product of the 16 (exactly orthogonal) rotations is accumulated in registers (the lane of (slot, idx)
+                    // keeps J[idx][slot]; column 4 + (slot + r) % 4 comes from the lane of slot + 1 by one shuffle per round) and
+                    // the tracked Gram blocks are the diagonal blocks of J^T M J, two 8 x 8 x 8 products = four DMMAs.  Shared-
+                    // memory wavefronts of the inner solve: ~50 instead of ~125 per block pair (the phase counters show the
+                    // inner solves of all warps in lock step: a third of the kernel with the FP64 pipe idle).
+                    double cr[4], sr[4];
+                    const double app = Msh[slot * (kJs + 1)];
+                    int small = 1;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int q = 4 + ((slot + r) & 3);
+                        jb_rotation(app, Msh[q * (kJs + 1)], Msh[slot * kJs + q], cr[r], sr[r]);
+                        small &= (fabs(sr[r]) <= kJbSimulMaxSin) ? 1 : 0;
+                    }
+                    simul = __all_sync(0xffffffffu, small);
+                    if (simul) {
+                        double jp = (idx == slot) ? 1.0 : 0.0, jq = (idx == 4 + slot) ? 1.0 : 0.0;
+                        const int src = (lane & ~3) | ((lane + 1) & 3);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const double np = cr[r] * jp - sr[r] * jq, nq = sr[r] * jp + cr[r] * jq;
+                            jp = np;
+                            jq = r < 3 ? __shfl_sync(0xffffffffu, nq, src) : nq;
+                        }
+                        Jsh[idx * kJs + slot] = jp; Jsh[idx * kJs + 4 + ((slot + 3) & 3)] = jq;
+                        __syncwarp();
+                        // X = M J (A fragment M[l4][k], B fragment J[k][l4]), then M' = J^T X (A fragment J[k][l4], B fragment X[k][l4])
+                        double x0 = 0.0, x1 = 0.0;
+                        dmma_884(x0, x1, Msh[l4 * kJs + l3], Jsh[l3 * kJs + l4]);
+                        dmma_884(x0, x1, Msh[l4 * kJs + 4 + l3], Jsh[(4 + l3) * kJs + l4]);
+                        __syncwarp();
+                        Msh[l4 * kJs + 2 * l3] = x0; Msh[l4 * kJs + 2 * l3 + 1] = x1;
+                        __syncwarp();
+                        double y0 = 0.0, y1 = 0.0;
+                        dmma_884(y0, y1, Jsh[l3 * kJs + l4], Msh[l3 * kJs + l4]);
+                        dmma_884(y0, y1, Jsh[(4 + l3) * kJs + l4], Msh[(4 + l3) * kJs + l4]);
+                        __syncwarp();
+                        Msh[l4 * kJs + 2 * l3] = y0; Msh[l4 * kJs + 2 * l3 + 1] = y1;
+                        __syncwarp();
+                    }
+                }
+                if (!simul) {
                 Jsh[l4 * kJs + j0] = (l4 == j0) ? 1.0 : 0.0; Jsh[l4 * kJs + j1] = (l4 == j1) ? 1.0 : 0.0;
                 __syncwarp();
                 {
@@ -732,6 +785,7 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                         }
                         __syncwarp();
                     }
+                }
                 }
                 JB_T(2);
                 // ---- tracked Gram matrices of the two blocks
