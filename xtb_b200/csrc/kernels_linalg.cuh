@@ -708,12 +708,10 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                 // the rotation of this lane's pair (see below) is evaluated here already, ahead of the votes, so that its chain of
                 // dependent instructions overlaps the test
                 double c1 = 1.0, s1 = 0.0;
-#ifndef XTBB200_JB_ROT_LATE
                 if (!full && kJbSimulMaxSin > 0.0) {
                     const int q = 4 + ((slot + idx) & 3);
                     jb_rotation(Msh[slot * (kJs + 1)], Msh[q * (kJs + 1)], Msh[slot * kJs + q], c1, s1);
                 }
-#endif
                 int need = 0, big = 0;
                 {
                     const double d0 = dii * dj0, d1 = dii * dj1;
@@ -743,12 +741,6 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                     double cr[4], sr[4];
                     // one rotation per lane: the lane of (slot, idx) evaluates the pair of round idx & 3 of its slot (the FP64 pipe
                     // is shared by all warps, which reach this point together: four rotations per lane were half of its load here)
-#ifdef XTBB200_JB_ROT_LATE
-                    {
-                        const int q = 4 + ((slot + idx) & 3);
-                        jb_rotation(Msh[slot * (kJs + 1)], Msh[q * (kJs + 1)], Msh[slot * kJs + q], c1, s1);
-                    }
-#endif
                     simul = __all_sync(0xffffffffu, fabs(s1) <= kJbSimulMaxSin);
                     JB_T(0);
                     if (simul) {
@@ -820,19 +812,6 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                     const double* ap1 = G + (size_t)ld * (4 * Q + l3) + l4;
                     const int oc = (l3 < 2) ? 4 * P + 2 * l3 : 4 * Q + 2 * l3 - 4;
                     double* op = G + (size_t)ld * oc + l4;
-#ifdef XTBB200_JB_APPLY_PIPE
-                    // one tile per pass, the operands of the next tile requested before the DMMAs of this one
-                    double xan = ap0[0], xbn = ap1[0];
-                    for (int r0 = 0; r0 < nr; r0 += 8) {
-                        const double xa1 = xan, xb1 = xbn;
-                        if (r0 + 8 < nr) { xan = ap0[r0 + 8]; xbn = ap1[r0 + 8]; }
-                        double z0 = 0.0, z1 = 0.0;
-                        dmma_884(z0, z1, xa1, bj0);
-                        dmma_884(z0, z1, xb1, bj1);
-                        op[r0 + (l3 < 2 ? 0 : ld)] = l3 < 2 ? z0 : z1;
-                        op[r0 + (l3 < 2 ? ld : 0)] = l3 < 2 ? z1 : z0;
-                    }
-#else
                     for (int r0 = 0; r0 < nr; r0 += 8 * kJbApplyTiles) {
                         double xa[kJbApplyTiles], xb[kJbApplyTiles], y0[kJbApplyTiles], y1[kJbApplyTiles];
 #pragma unroll
@@ -855,7 +834,6 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                                 op[r0 + 8 * u + (l3 < 2 ? ld : 0)] = l3 < 2 ? y1[u] : y0[u];
                             }
                     }
-#endif
                 }
                 jb_publish(ver, P, Q, tstep + 1, lane);
                 JB_T(3);
