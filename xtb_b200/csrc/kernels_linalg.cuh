@@ -353,10 +353,15 @@ __global__ void __launch_bounds__(1024) k_jacobi(Dev d) {
 // columns touched by a half-warp fall into 16 distinct 8-byte banks.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void jb_block_pair(int step, int pr, int nb, int& P, int& Q) {
+    // step < nb - 1 and pr < nb / 2: the residues modulo nb - 1 by one conditional subtraction / addition (two integer divisions
+    // by a run-time divisor at the head of every tournament step were 5 % of the kernel's stall samples)
     const int mm1 = nb - 1;
     int p, q;
-    if (pr == 0) { p = step % mm1; q = mm1; }
-    else { p = (step + pr) % mm1; q = (step - pr + mm1) % mm1; }
+    if (pr == 0) { p = step; q = mm1; }
+    else {
+        p = step + pr; if (p >= mm1) p -= mm1;
+        q = step - pr; if (q < 0) q += mm1;
+    }
     P = p < q ? p : q; Q = p < q ? q : p;
 }
 
@@ -1000,9 +1005,11 @@ __global__ void __launch_bounds__(32 * kJbMaxWarps) k_jacobi_blk(Dev d, int phas
         rank[j] = rk;
     }
     __syncthreads();
-    for (int t = tid; t < n * n; t += nt) {
-        const int r = t % n, j = t / n;
-        Z[r + (long long)n * rank[j]] = G[r + (size_t)ld * j] / nrm[j];
+    for (int j = warp; j < n; j += nwarps) {      // warp per column: no index divisions, coalesced stores
+        const double nj = nrm[j];
+        double* zc = Z + (long long)n * rank[j];
+        const double* gc = G + (size_t)ld * j;
+        for (int r = lane; r < n; r += 32) zc[r] = gc[r] / nj;
     }
     if (tid == 0) { st.sweeps = sweep; st.sweeps_total += sweep; st.zvalid = 1; if (sweep >= 40) st.fail = 12; }
 #ifdef XTBB200_JB_TIMING
