@@ -110,12 +110,37 @@ def test_lane_mapping_of_the_simultaneous_inner_solve():
 
 
 def _block_pair(step, pr, nb):
+    """jb_block_pair as the kernel evaluates it: residues modulo nb - 1 by one conditional subtraction / addition."""
     mm1 = nb - 1
     if pr == 0:
-        p, q = step % mm1, mm1
+        p, q = step, mm1
     else:
-        p, q = (step + pr) % mm1, (step - pr + mm1) % mm1
+        p = step + pr
+        if p >= mm1:
+            p -= mm1
+        q = step - pr
+        if q < 0:
+            q += mm1
     return min(p, q), max(p, q)
+
+
+def test_block_pairs_are_a_round_robin_tournament():
+    """Every sweep pairs every two column blocks exactly once, every step uses every block exactly once, and the division-free
+    indices are those of the circle method ((step + pr) mod (nb - 1), (step - pr) mod (nb - 1), block nb - 1 fixed)."""
+    for nb in range(2, 42, 2):
+        seen = set()
+        for step in range(nb - 1):
+            used = []
+            for pr in range(nb // 2):
+                P, Q = _block_pair(step, pr, nb)
+                mm1 = nb - 1
+                ref = (step % mm1, mm1) if pr == 0 else ((step + pr) % mm1, (step - pr + mm1) % mm1)
+                assert (P, Q) == (min(ref), max(ref))
+                assert P < Q and (P, Q) not in seen
+                seen.add((P, Q))
+                used += [P, Q]
+            assert sorted(used) == list(range(nb))
+        assert len(seen) == nb * (nb - 1) // 2
 
 
 _PAIRTAB = [[(s7, 7) if slot == 0 else tuple(sorted(((s7 + slot) % 7, (s7 - slot + 7) % 7))) for slot in range(4)]
