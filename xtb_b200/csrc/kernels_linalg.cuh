@@ -710,8 +710,10 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                 const int j0 = 2 * l3, j1 = 2 * l3 + 1;
                 const double dii = Msh[l4 * (kJs + 1)], dj0 = Msh[j0 * (kJs + 1)], dj1 = Msh[j1 * (kJs + 1)];
                 const double m0 = Msh[l4 * kJs + j0], m1 = Msh[l4 * kJs + j1];
-                // the rotation of this lane's pair (see below) is evaluated here already, ahead of the votes, so that its chain of
-                // dependent instructions overlaps the test
+                // the rotation of this lane's pair (simultaneous inner solve, see below: the lane of (slot, idx) evaluates the pair
+                // of round idx & 3 of its slot -- the FP64 pipe is shared by all warps, which reach this point together, and four
+                // rotations per lane were half of its load here) is evaluated ahead of the votes, so that its chain of dependent
+                // instructions overlaps the test
                 double c1 = 1.0, s1 = 0.0;
                 if (!full && kJbSimulMaxSin > 0.0) {
                     const int q = 4 + ((slot + idx) & 3);
@@ -744,8 +746,6 @@ __device__ __forceinline__ int jb_sweeps2(double* G, double* Msh, double* Tsh, v
                     // memory wavefronts of the inner solve: ~50 instead of ~125 per block pair (the phase counters show the
                     // inner solves of all warps in lock step: a third of the kernel with the FP64 pipe idle).
                     double cr[4], sr[4];
-                    // one rotation per lane: the lane of (slot, idx) evaluates the pair of round idx & 3 of its slot (the FP64 pipe
-                    // is shared by all warps, which reach this point together: four rotations per lane were half of its load here)
                     simul = __all_sync(0xffffffffu, fabs(s1) <= kJbSimulMaxSin);
                     JB_T(0);
                     if (simul) {
